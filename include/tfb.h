@@ -1,0 +1,296 @@
+/*
+ * tfb.h -- C ABI of libtfb_b200.so: B200 (sm_100a) kernels for the TopoFlow 3.6
+ * per-timestep grid update (channel routing + D8 toolkit + source terms).
+ *
+ * The reference (peckhams/topoflow36) is pure Python/numpy and has no FFI for
+ * this path; each entry point below cites the reference method(s) it replaces
+ * (paths relative to topoflow/).  The Python BMI components in
+ * topoflow36_b200/ bind these symbols with ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative tfb_status otherwise and
+ *     never throws; tfb_last_error() gives the text of the last failure on the
+ *     calling thread;
+ *   - all grid pointers are DEVICE pointers to row-major (ny, nx) arrays, row 0
+ *     = north, caller-owned; `stream` is a cudaStream_t passed as void*;
+ *   - "scalar-or-grid" inputs follow the reference's CFG convention
+ *     (<var>_type = Scalar | Grid): a tfb_sg with ptr == NULL means the scalar
+ *     `val` applies to every cell;
+ *   - no global state except the opaque plan objects; calls on one plan must be
+ *     serialised by the caller (one host thread per GPU, as in the reference).
+ */
+#ifndef TFB_H
+#define TFB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TFB_ABI_VERSION 1
+
+typedef enum {
+    TFB_OK = 0,
+    TFB_ERR_CUDA = -1,        /* a CUDA runtime call failed            */
+    TFB_ERR_ARG = -2,         /* bad argument (NULL, size, flag combo)  */
+    TFB_ERR_NO_DEVICE = -3,   /* no CUDA device / wrong architecture    */
+    TFB_ERR_NOT_CONVERGED = -4
+} tfb_status;
+
+/* scalar-or-grid fp64 input */
+typedef struct {
+    const double *ptr;        /* device pointer to (ny, nx) grid, or NULL */
+    double val;               /* used when ptr == NULL                    */
+} tfb_sg;
+
+int tfb_abi_version(void);
+const char *tfb_last_error(void);
+/* name, SM count, cc major/minor of the current device */
+int tfb_device_info(char *name, int name_len, int *sm_count, int *cc_major,
+                    int *cc_minor);
+
+/* ------------------------------------------------------------------------
+ * D8 toolkit  (components/d8_base.py, components/d8_global.py)
+ * ---------------------------------------------------------------------- */
+
+/* 256-entry tie-break table, copied to `out256` (HOST pointer).
+ * replaces d8_base.get_resolve_array (d8_base.py:711-772). */
+int tfb_d8_resolve_table(uint8_t *out256);
+
+/* D8 start codes from a float32 DEM: steepest-descent slopes to the 8
+ * neighbours in fp32, ties encoded as the SUM of tied codes, flats negated
+ * (link_flats != 0) or zeroed, pits -300 / 0, nodata/NaN and the four border
+ * lines 0.  `dem` points at the first OWNED row of a slab; `halo` rows above
+ * and below it are readable (0 for a whole grid: its border rows get code 0
+ * anyway); `row0`/`ny_global` place the slab in the global grid.
+ * replaces d8_global.start_new_d8_codes (d8_global.py:181-353). */
+int tfb_d8_codes(const float *dem, int32_t ny, int32_t nx, int32_t halo,
+                 int32_t row0, int32_t ny_global, float dx, float dy, float dd,
+                 double nodata, int32_t link_flats, int16_t *code, void *stream);
+
+/* code[code > 0] = resolve[code]   (d8_global.break_flow_grid_ties :355-372) */
+int tfb_d8_break_ties(int16_t *code, int64_t n, void *stream);
+
+/* ONE Jacobi sweep of flat linking: reads `code_in` (same halo convention),
+ * writes `code_out`; n_flats / n_fixed are DEVICE int32 counters that the sweep
+ * ADDS to.  (d8_global.link_flats :374-576, one trip of its while loop) */
+int tfb_d8_link_flats_sweep(const int16_t *code_in, int16_t *code_out,
+                            int32_t ny, int32_t nx, int32_t halo, int32_t row0,
+                            int32_t ny_global, int32_t *n_flats,
+                            int32_t *n_fixed, void *stream);
+
+/* Whole link_flats loop on one GPU (iterates sweeps to the reference's stop
+ * rule).  `scratch` = device int16 buffer of ny*nx.  n_reps: HOST out. */
+int tfb_d8_link_flats(int16_t *code, int16_t *scratch, int32_t ny, int32_t nx,
+                      int32_t max_reps, int32_t *n_reps, void *stream);
+
+/* negative / >128 leftovers -> 0, then to uint8 (d8_global.py:139-146) */
+int tfb_d8_finalize_codes(const int16_t *code, uint8_t *code_u8, int64_t n,
+                          void *stream);
+
+/* ds (flow length) and dw (flow width) float32 grids from the codes and the
+ * per-row float32 pixel sizes dx, dy, dd (DEVICE arrays of ny).
+ * (d8_global.update_flow_width_grid :873-958, update_flow_length_grid :960-1027)
+ * Either output may be NULL. */
+int tfb_d8_ds_dw(const uint8_t *code, const float *dx, const float *dy,
+                 const float *dd, int32_t ny, int32_t nx, float *ds, float *dw,
+                 void *stream);
+
+/* Total contributing area: A[cell] = pixel_area (stored fp32) + sum of the
+ * FINAL areas of the children, added in neighbour order NE,E,SE,S,SW,W,NW,N in
+ * fp32 -- the reference's result, computed in one topological pass instead of
+ * one whole-grid sweep per level.  Cells with code 0 and cells on / below a
+ * cycle keep A = 0.  `pixel_area_row` (DEVICE, ny doubles) may be NULL, then
+ * `pixel_area` applies.  `count` (DEVICE int64, may be NULL) receives the exact
+ * number of cells draining through each cell (itself included).
+ * `pending` = DEVICE scratch of ny*nx int32.   n_done: HOST out, number of
+ * cells that received an area.   (d8_global.update_area_grid :1029-1332) */
+int tfb_d8_area(const uint8_t *code, int32_t ny, int32_t nx, double pixel_area,
+                const double *pixel_area_row, float *A, int64_t *count,
+                int32_t *pending, int64_t *n_done, void *stream);
+
+/* S = (DEM - DEM[parent]) / ds in fp32, 0 at noflow cells
+ * (d8_global.update_slope_grid :1334-1348). */
+int tfb_d8_slope(const float *dem, const uint8_t *code, const float *dx,
+                 const float *dy, const float *dd, int32_t ny, int32_t nx,
+                 float *S, void *stream);
+
+/* parent_ID_grid (int32 flat IDs, 0 for noflow/border cells)
+ * (d8_global.update_parent_ID_grid :578-650). */
+int tfb_d8_parent_ids(const uint8_t *code, int32_t ny, int32_t nx,
+                      int32_t *pid, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Channel routing step  (components/channels_base.py update() :803-962 and
+ * subclasses channels_kinematic_wave.py :84-127, channels_diffusive_wave.py
+ * :85-139) with optionally fused source terms.
+ * ---------------------------------------------------------------------- */
+
+/* flags */
+#define TFB_CH_DIFFUSIVE   (1u << 0)  /* S = S_free (else kinematic: S_bed)   */
+#define TFB_CH_LAW_OF_WALL (1u << 1)  /* velocity law (else Manning)          */
+#define TFB_CH_DIAG        (1u << 2)  /* materialise Rh,A_wet,P_wet,f,tau,
+                                         u_star,froude (+S_free) every step   */
+#define TFB_CH_WRITE_R     (1u << 3)  /* store the R grid                     */
+#define TFB_CH_ET_INPLACE  (1u << 4)  /* zero the provider's ET grid where
+                                         vol < ET*da*dt (channels_base :1625)  */
+#define TFB_CH_SRC_MET     (1u << 8)  /* P -> P_rain/P_snow split fused       */
+#define TFB_CH_SRC_SNOW    (1u << 9)  /* degree-day snowmelt fused            */
+#define TFB_CH_SRC_EVAP    (1u << 10) /* Priestley-Taylor ET fused            */
+#define TFB_CH_SRC_INFIL   (1u << 11) /* Green-Ampt infiltration fused        */
+
+/* Device-resident scalar block: what the reference keeps in 0-D numpy arrays.
+ * The step kernel's last block updates it; the host reads it when it needs
+ * Q_outlet etc. (one D2H of sizeof(tfb_channels_scalars)). */
+typedef struct {
+    double vol_R, vol_Q, vol_edge;                 /* :1657, :2928, :2962     */
+    double Q_outlet, u_outlet, d_outlet, f_outlet; /* :2884-2906              */
+    double Q_peak, T_peak, u_peak, Tu_peak, d_peak, Td_peak; /* :2908-2926    */
+    double vol_P, vol_PR, vol_PS;                  /* met_base.py:1247-1446   */
+    double vol_SM, vol_ET, vol_IN;                 /* snow/evap/infil integrals */
+    double dt_cfl_min;                             /* diagnostic only: min ds/u */
+    int64_t n_neg_d, n_nan_d, n_inf_d;             /* check_flow_depth :3193  */
+    int64_t n_neg_u, n_nan_u, n_inf_u;             /* check_flow_velocity :3352 */
+    int64_t n_nan_IN;                              /* infil_base.py:906-950   */
+    int64_t step_count;
+} tfb_channels_scalars;
+
+typedef struct {
+    /* ---- geometry ---------------------------------------------------- */
+    int32_t ny, nx;           /* rows / cols held by this GPU (its slab)        */
+    int32_t row0, ny_global;  /* slab position in the global grid               */
+    uint32_t flags;
+    int32_t outlet_row, outlet_col;  /* GLOBAL indices; sampled by the owner    */
+    int32_t is_R_grid;        /* 1: vol_R sums R*da*dt per cell; 0: scalar rule  */
+    double dt;                /* channel time step [s]                          */
+    double time_min;          /* model time [min] at the start of the step      */
+    double rho_H2O;
+    int64_t n_pixels_global;  /* for scalar-R integral (channels_base :1668)    */
+    /* ---- static per-cell inputs --------------------------------------- */
+    int32_t halo;             /* rows readable above row 0 and below row ny-1 of
+                                 EVERY grid pointer (0, or >=1 KW / >=2 DW for a
+                                 slab with neighbours); rows beyond that read as
+                                 code 0 / Q 0                                   */
+    const uint8_t *code;      /* D8 codes (ny, nx)                              */
+    const float *dx, *dy, *dd;        /* per-row pixel sizes (ny), float32       */
+    tfb_sg sinu;              /* ds = sinu * ds_d8  (channels_base :1242)       */
+    tfb_sg da;                /* pixel area [m2]; ptr = per-ROW array (ny)      */
+    const double *S_bed;      /* bed slope (already / sinu, bad slopes fixed)   */
+    tfb_sg width;             /* trapezoid bottom width                         */
+    tfb_sg tan_angle;         /* tan / cos of the bank angle, evaluated on the  */
+    tfb_sg cos_angle;         /*   host by numpy at initialize()                */
+    tfb_sg angle;             /* radians; only its ==0 test is used             */
+    tfb_sg rough;             /* Manning n  or  z0 (law of the wall)            */
+    /* ---- state --------------------------------------------------------- */
+    const double *vol;        /* in: water volume per cell before the step      */
+    double *vol_out;          /* out: after the step; may alias `vol` for the
+                                 kinematic wave, must NOT for the diffusive one
+                                 (neighbours re-read the old volumes)           */
+    const double *Q_in;       /* discharge used by this step (= u*A_wet of the
+                                 previous one)                                  */
+    double *Q_out;            /* out: u*A_wet after this step                   */
+    double *d, *u;            /* out                                            */
+    /* ---- optional outputs (TFB_CH_DIAG / TFB_CH_WRITE_R), may be NULL --- */
+    double *Rh, *A_wet, *P_wet, *f, *tau, *u_star, *froude, *S_free, *R;
+    /* ---- source terms --------------------------------------------------- */
+    tfb_sg P_rain;            /* or total P when TFB_CH_SRC_MET                 */
+    tfb_sg SM, GW, MR, IN;    /* used as given unless the fused flag is set     */
+    tfb_sg ET;
+    double *ET_rw;            /* == ET.ptr when TFB_CH_ET_INPLACE               */
+    /* met (met_base.py:1300-1388) */
+    tfb_sg T_air; double T_rain_snow;
+    /* snow (snow_degree_day.py:293-360, snow_base.py:490-703) */
+    tfb_sg c0, T0; const double *h_swe; double *h_swe_out; /* alias rule as vol */
+    double *h_snow; double rho_snow;
+    /* evap (evap_priestley_taylor.py:308-413, evap_base.py:326-353) */
+    tfb_sg T_surf, Qn_SW, Qn_LW; double alpha, K_soil, soil_x, T_soil_x;
+    /* infil (infil_green_ampt.py:511-578, infil_base.py:654-811, :954-995) */
+    tfb_sg Ks, Ki, qs, qi, G; const double *I; double *I_out; /* alias rule as vol */
+    tfb_sg h_table, elev;
+    /* ---- reductions ----------------------------------------------------- */
+    tfb_channels_scalars *scalars;   /* DEVICE                                  */
+    double *partials;         /* DEVICE scratch, >= tfb_channels_partials_len()
+                                 doubles, zero-initialised once by the caller;
+                                 with finalize == 0 the per-rank sums are left
+                                 in its LAST TFB_NSUM doubles                   */
+    uint32_t *ticket;         /* DEVICE scratch, 1 word, zero-initialised       */
+    int32_t finalize;         /* 1: last block folds partials into `scalars`
+                                 (single GPU); 0: leave per-rank sums in
+                                 the tail of `partials` for an allreduce, then
+                                 call tfb_channels_fold()                       */
+} tfb_channels_step_args;
+
+#define TFB_NSUM 24           /* doubles per rank exchanged by the allreduce:
+                                 [0,15) sums and bad-value counts, [15] "this
+                                 rank owns the outlet", [16] dt_cfl_min (reduce
+                                 with MIN or ignore), [17,21) outlet Q,u,d,f
+                                 (zero on non-owners), rest padding            */
+
+/* sizeof() of the two structs above, so a binding can verify its own layout */
+int64_t tfb_sizeof_channels_step_args(void);
+int64_t tfb_sizeof_channels_scalars(void);
+
+/* number of doubles `partials` must hold for a (ny, nx) slab */
+int64_t tfb_channels_partials_len(int32_t ny, int32_t nx);
+
+/* one routing step of the slab */
+int tfb_channels_step(const tfb_channels_step_args *a, void *stream);
+
+/* multi-GPU: fold globally reduced sums (DEVICE, TFB_NSUM doubles laid out as
+ * tfb_channels_step leaves them in partials[]) into the scalar block */
+int tfb_channels_fold(const tfb_channels_step_args *a, const double *sums,
+                      void *stream);
+
+/* domain min/max of Q, u, d over interior cells and total channel volume
+ * (channels_base.update_mins_and_maxes :2986-3081,
+ *  update_total_channel_water_volume :3083-3110); out6 = DEVICE
+ * {Q_min,Q_max,u_min,u_max,d_min,d_max}, vol_sum = DEVICE */
+/* doubles of scratch the stand-alone source kernels and tfb_channels_minmax
+ * need in `partials` (their `ticket` is one zero-initialised uint32) */
+int64_t tfb_sources_partials_len(void);
+
+int tfb_channels_minmax(const double *Q, const double *u, const double *d,
+                        const double *vol, int32_t ny, int32_t nx, double *out6,
+                        double *vol_sum, double *partials, uint32_t *ticket,
+                        void *stream);
+
+/* ------------------------------------------------------------------------
+ * Stand-alone source-term kernels (one per reference component update()).
+ * ---------------------------------------------------------------------- */
+
+/* P_rain = P*(T_air > T_rs), P_snow = P*(T_air <= T_rs); sums[0..3) +=
+ * {vol_P, vol_PR, vol_PS} increments.  (met_base.py:1247-1446) */
+int tfb_met_precip(tfb_sg P, tfb_sg T_air, double T_rain_snow, tfb_sg da,
+                   double dt, int32_t ny, int32_t nx, double *P_rain,
+                   double *P_snow, double *sums3, double *partials,
+                   uint32_t *ticket, void *stream);
+
+/* Green-Ampt v1 (infil_green_ampt.py:511-578; infil_base.update :301-357):
+ * IN out, I in/out, sums[0] += vol_IN increment, nbad += #non-finite IN */
+int tfb_infil_green_ampt(tfb_sg P_rain, tfb_sg SM, tfb_sg Ks, tfb_sg Ki,
+                         tfb_sg qs, tfb_sg qi, tfb_sg G, tfb_sg h_table,
+                         tfb_sg elev, int32_t use_table, tfb_sg da, double dt,
+                         int32_t ny, int32_t nx, double *IN, double *I,
+                         double *sums2, double *partials, uint32_t *ticket,
+                         void *stream);
+
+/* degree-day (snow_degree_day.py:293-360; snow_base.update :214-278) */
+int tfb_snow_degree_day(tfb_sg P_snow, tfb_sg T_air, tfb_sg c0, tfb_sg T0,
+                        double rho_H2O, double rho_snow, tfb_sg da, double dt,
+                        int32_t ny, int32_t nx, double *SM, double *h_swe,
+                        double *h_snow, double *sums1, double *partials,
+                        uint32_t *ticket, void *stream);
+
+/* Priestley-Taylor (evap_priestley_taylor.py:308-413; evap_base :326-377) */
+int tfb_evap_priestley_taylor(tfb_sg T_air, tfb_sg T_surf, tfb_sg Qn_SW,
+                              tfb_sg Qn_LW, double alpha, double K_soil,
+                              double soil_x, double T_soil_x, tfb_sg da,
+                              double dt, int32_t ny, int32_t nx, double *Qc,
+                              double *ET, double *sums1, double *partials,
+                              uint32_t *ticket, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFB_H */

@@ -1,0 +1,315 @@
+"""Generate the committed fixtures under tests/golden/ by running the UNMODIFIED
+reference (/root/reference) in this container.  TEST INFRASTRUCTURE ONLY.
+
+    python -m oracle.gen_golden            # writes tests/golden/*.npz / *.json
+
+The GPU box has no reference tree; the `-m gpu` tests and the oracle tests read
+only these files.  Everything here is deterministic (fixed seeds, numpy 2.3.5).
+"""
+import json
+import os
+import shutil
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import ref_harness as rh          # noqa: E402
+from topoflow36_b200 import grid_io, synth    # noqa: E402
+
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+
+LONG = {'P_rain': 'atmosphere_water__rainfall_volume_flux',
+        'MR': 'glacier_ice__melt_volume_flux',
+        'GW': 'land_surface_water__baseflow_volume_flux',
+        'ET': 'land_surface_water__evaporation_volume_flux',
+        'IN': 'soil_surface_water__infiltration_volume_flux',
+        'SM': 'snowpack__melt_volume_flux',
+        'rho_H2O': 'water-liquid__mass-per-volume_density'}
+GRIDS = ('vol', 'd', 'u', 'Q', 'Rh', 'A_wet', 'P_wet', 'f', 'tau', 'u_star',
+         'froude')
+SCALARS = ('vol_R', 'vol_Q', 'vol_edge', 'Q_outlet', 'u_outlet', 'd_outlet',
+           'f_outlet', 'Q_peak', 'T_peak', 'u_peak', 'Tu_peak', 'd_peak',
+           'Td_peak')
+
+
+def z(v):
+    return np.array(v, dtype='float64')
+
+
+def standalone_channels(cfg_file, kinematic, inputs):
+    """Reference channels component driven without EMELI."""
+    from topoflow.components import channels_kinematic_wave as ckw
+    from topoflow.components import channels_diffusive_wave as cdw
+    c = (ckw if kinematic else cdw).channels_component()
+    rh.quiet_call(c.initialize, cfg_file=cfg_file, mode='driver', SILENT=True)
+    for k, v in inputs.items():
+        c.set_value(LONG[k], v)
+    c.n_steps = 10 ** 9
+    return c
+
+
+def snapshot(c, diag=True):
+    out = {n: np.array(getattr(c, n), dtype='float64') for n in GRIDS}
+    if not c.KINEMATIC_WAVE:
+        out['S_free'] = np.array(c.S_free)
+    for n in SCALARS:
+        out[n] = np.float64(getattr(c, n))
+    return out
+
+
+def gen_treynor(work):
+    cfg_dir, _ = rh.stage_treynor(work)
+    topo = os.path.join(os.path.dirname(cfg_dir.rstrip(os.sep)), '__topo')
+    info = grid_io.read_rti(os.path.join(topo, 'Treynor.rti'))
+    rd = lambda n, t=None: grid_io.read_rtg(os.path.join(topo, 'Treynor_' + n + '.rtg'), info, t)
+    rain = np.loadtxt(os.path.join(cfg_dir, 'June_20_67_rain_rates.txt'), dtype='float32')
+    inputs = dict(DEM=rd('DEM'), slope=rd('slope'), width=rd('chan-w'), angle=rd('chan-a'),
+                  nval=rd('chan-n'), z0val=rd('chan-z0'), flow=rd('flow', 'BYTE'),
+                  area=rd('area'), d8_area=rd('d8-area'), rain_mmph=rain,
+                  xres=np.float64(info.xres), yres=np.float64(info.yres),
+                  outlets_rc=np.array([[34, 16], [32, 16], [37, 19], [26, 14], [30, 15]]))
+    np.savez_compressed(os.path.join(GOLD, 'treynor_inputs.npz'), **inputs)
+
+    # ---- (1) full EMELI run: the reference's own integration "test" -----------
+    from topoflow.framework import emeli
+    f = emeli.framework()
+    rh.quiet_call(f.run_model, driver_comp_name='topoflow_driver', cfg_prefix='June_20_67',
+                  cfg_directory=cfg_dir, SILENT=True)
+    ch = f.comp_set['tf_channels_kin_wave']
+    emeli_out = {n: float(getattr(ch, n)) for n in SCALARS}
+    emeli_out['n_steps'] = int(ch.time_index)
+    emeli_out['vol_chan_sum'] = float(ch.vol_chan_sum)
+    np.savez_compressed(os.path.join(GOLD, 'treynor_emeli_final.npz'),
+                        **{n: np.array(getattr(ch, n)) for n in ('vol', 'd', 'u', 'Q')})
+
+    # ---- (2) stand-alone KW run forced by the 1-minute rain series -----------
+    # P is held for 10 channel steps (60 s / 6 s) like the met component does
+    # with time interpolation off; all fp64 grids captured in memory.
+    ny, nx = info.nrows, info.ncols
+    c = standalone_channels(cfg_dir + 'June_20_67_channels_kinematic_wave.cfg', True,
+                            dict(P_rain=z(0), MR=z(0), GW=z(0), SM=z(0), rho_H2O=z(1000.0),
+                                 ET=np.zeros((ny, nx)), IN=np.zeros((ny, nx))))
+    n_steps = 1200
+    series = np.zeros((n_steps, 4))
+    snaps = {}
+    for i in range(n_steps):
+        m = i // 10
+        P = np.float64(rain[m]) / (1000.0 * 3600.0) if m < rain.size else 0.0
+        c.set_value(LONG['P_rain'], z(P))
+        rh.quiet_call(c.update)
+        series[i] = (c.Q_outlet, c.u_outlet, c.d_outlet, c.f_outlet)
+        if (i + 1) in (100, 400, 1200):
+            for k, v in snapshot(c).items():
+                snaps['s%d_%s' % (i + 1, k)] = v
+    np.savez_compressed(os.path.join(GOLD, 'treynor_kw_standalone.npz'),
+                        outlet_series=series, **snaps)
+    return emeli_out
+
+
+def gen_synth_channels(work):
+    """KW/DW x Manning/law-of-wall on a 61 x 83 synthetic case, 150 steps, rain
+    for the first 100; ET and IN given as grids (exercises the ET masking)."""
+    import topoflow.components.d8_global as d8g
+    ny, nx = 61, 83
+    DEM = synth.fractal_dem(ny, nx, seed=7, sigma=1.0)
+    width, angle, nval = synth.channel_params(ny, nx, seed=7)
+    rng = np.random.default_rng(99)
+    angle = np.float32(np.where(rng.random((ny, nx)) < 0.15, 0.0, 20.0 + 40.0 * rng.random((ny, nx))))
+    z0val = np.float32(0.005 + 0.02 * rng.random((ny, nx)))
+    out = dict(DEM=DEM, width=width, angle=angle, nval=nval, z0val=z0val)
+    ETg = 2e-6 * rng.random((ny, nx))
+    INg = 3e-6 * rng.random((ny, nx))
+    out['ET0'] = ETg.copy()
+    out['IN0'] = INg.copy()
+    for kin in (True, False):
+        for man in (True, False):
+            tag = ('kw' if kin else 'dw') + ('_man' if man else '_low')
+            cdir = os.path.join(work, 'synth_' + tag)
+            # slope grid: the reference's own D8 slope of this DEM
+            cfg = synth.write_case(cdir, DEM, np.zeros_like(DEM), width, angle,
+                                   nval=nval if man else None,
+                                   z0val=None if man else z0val, dt=2.0,
+                                   kinematic=kin, manning=man, outlet=(ny - 2, nx // 2))
+            d8 = d8g.d8_component()
+            rh.quiet_call(d8.initialize, cfg_file=os.path.join(cdir, 'Case1_d8_global.cfg'),
+                          SILENT=True, REPORT=False)
+            rh.quiet_call(d8.update, 0)
+            d8.update_noflow_IDs()
+            d8.update_slope_grid()
+            info = grid_io.read_rti(os.path.join(cdir, 'Synth.rti'))
+            grid_io.write_rtg(os.path.join(cdir, 'Synth_slope.rtg'), d8.S, info)
+            if kin and man:
+                out['code'] = np.array(d8.d8_grid)
+                out['slope'] = np.float32(d8.S)
+                out['ds32'] = np.float32(d8.ds)
+                out['dw32'] = np.float32(d8.dw)
+                out['area'] = np.float32(d8.A)
+            ET = ETg.copy()
+            c = standalone_channels(cfg, kin, dict(
+                P_rain=z(80 / 3.6e6), MR=z(0), GW=z(1e-7), SM=z(2e-7), rho_H2O=z(1000.0),
+                ET=ET, IN=INg.copy()))
+            for i in range(150):
+                if i == 100:
+                    c.set_value(LONG['P_rain'], z(0))
+                rh.quiet_call(c.update)
+            for k, v in snapshot(c).items():
+                out[tag + '_' + k] = v
+            out[tag + '_ET_after'] = ET
+            out[tag + '_S_bed'] = np.array(c.S_bed)
+    np.savez_compressed(os.path.join(GOLD, 'synth_channels.npz'), **out)
+
+
+def gen_d8(work):
+    """D8 toolkit on a DEM with plenty of ties and flats (elevations quantised
+    to 0.25 m) and a few nodata cells; LINK_FLATS on and off."""
+    import topoflow.components.d8_global as d8g
+    ny, nx = 150, 131
+    DEM = synth.fractal_dem(ny, nx, seed=21, sigma=1.5, sy=0.004, sx=0.002)
+    DEM = np.float32(np.round(DEM * 4.0) / 4.0)
+    DEM[40:43, 50:53] = -9999.0
+    DEM[100, 20] = np.nan
+    out = dict(DEM=DEM)
+    w, a, n = synth.channel_params(ny, nx, seed=21)
+    for lf in (1, 0):
+        cdir = os.path.join(work, 'd8_lf%d' % lf)
+        synth.write_case(cdir, DEM, np.zeros_like(DEM), w, a, nval=n, link_flats=lf)
+        d8 = d8g.d8_component()
+        rh.quiet_call(d8.initialize, cfg_file=os.path.join(cdir, 'Case1_d8_global.cfg'),
+                      SILENT=True, REPORT=False)
+        # intermediate stages of update_flow_grid (d8_global.py:99-146)
+        rh.quiet_call(d8.start_new_d8_codes, None)
+        out['lf%d_start' % lf] = np.array(d8.d8_grid, dtype='int16', copy=True)
+        d8.break_flow_grid_ties()
+        out['lf%d_ties' % lf] = np.array(d8.d8_grid, dtype='int16', copy=True)
+        rh.quiet_call(d8.update, 0)
+        d8.update_noflow_IDs()
+        with np.errstate(all='ignore'):
+            d8.update_slope_grid()
+        out['lf%d_code' % lf] = np.uint8(d8.d8_grid)
+        out['lf%d_area' % lf] = np.float32(d8.A)
+        out['lf%d_ds' % lf] = np.float32(d8.ds)
+        out['lf%d_dw' % lf] = np.float32(d8.dw)
+        out['lf%d_slope' % lf] = np.float32(d8.S)
+        out['lf%d_pid' % lf] = np.int32(d8.parent_ID_grid)
+    d8.get_resolve_array()
+    out['resolve'] = np.uint8(d8.resolve)
+    np.savez_compressed(os.path.join(GOLD, 'd8_synth.npz'), **out)
+
+
+def gen_sources():
+    """Pin the per-cell source formulas by calling the reference METHODS on bare
+    component objects whose attributes are set by hand (no CFG machinery)."""
+    from topoflow.components import infil_green_ampt, snow_degree_day, \
+        evap_priestley_taylor, met_base
+    rng = np.random.default_rng(5)
+    ny, nx = 37, 41
+    g = lambda lo, hi: lo + (hi - lo) * rng.random((ny, nx))
+    out = {}
+    # ---- Green-Ampt, 3 consecutive updates
+    c = infil_green_ampt.infil_component()
+    c.DEBUG = False
+    c.RICHARDS = False
+    c.dt = z(5.0)
+    c.P_rain = g(0, 2e-5)
+    c.SM = g(0, 2e-6)
+    c.Ks = [g(1e-6, 9e-6)]
+    c.Ki = [g(1e-8, 9e-7)]
+    c.qs = [g(0.4, 0.5)]
+    c.qi = [g(0.2, 0.39)]
+    c.G = [g(0.1, 0.9)]
+    c.I = np.zeros((ny, nx)) + 1e-6
+    c.h_table = g(0, 10)
+    c.elev = g(5, 20)
+    for k in ('P_rain', 'SM', 'h_table', 'elev'):
+        out['ga_' + k] = np.array(getattr(c, k))
+    for k in ('Ks', 'Ki', 'qs', 'qi', 'G'):
+        out['ga_' + k] = np.array(getattr(c, k)[0])
+    for it in range(3):
+        c.update_surface_influx()
+        c.update_infil_rate()
+        c.adjust_infil_rate()
+        c.update_I()
+        out['ga_IN%d' % it] = np.array(c.IN)
+        out['ga_I%d' % it] = np.array(c.I)
+    # ---- degree-day, 3 updates
+    s = snow_degree_day.snow_component()
+    s.dt = z(3600.0)
+    s.T_air = g(-3, 6)
+    s.c0 = z(2.7)
+    s.T0 = z(-0.2)
+    s.P_snow = g(0, 1e-6)
+    s.h_swe = g(0, 0.002)
+    s.h_snow = s.h_swe * (1000.0 / 300.0)
+    s.SM = np.zeros((ny, nx))
+    s.rho_H2O = z(1000.0)
+    s.rho_snow = z(300.0)
+    s.rho_snow_type = 'Scalar'
+    s.density_ratio = (s.rho_H2O / s.rho_snow)
+    out['dd_T_air'] = np.array(s.T_air)
+    out['dd_P_snow'] = np.array(s.P_snow)
+    out['dd_h_swe_init'] = np.array(s.h_swe)
+    for it in range(3):
+        s.update_meltrate()
+        s.enforce_max_meltrate()
+        s.update_swe()
+        s.update_depth()
+        out['dd_SM%d' % it] = np.array(s.SM)
+        out['dd_h_swe%d' % it] = np.array(s.h_swe)
+        out['dd_h_snow%d' % it] = np.array(s.h_snow)
+    # ---- Priestley-Taylor
+    e = evap_priestley_taylor.evap_component()
+    e.T_air = g(-5, 30)
+    e.T_surf = g(-5, 35)
+    e.Qn_SW = g(0, 800)
+    e.Qn_LW = g(-120, 50)
+    e.alpha = z(1.26)
+    e.K_soil = z(0.45)
+    e.soil_x = z(0.05)
+    e.T_soil_x = z(12.0)
+    e.Qc = np.zeros((ny, nx))
+    e.ET = np.zeros((ny, nx))
+    e.update_Qc()
+    e.update_ET_rate()
+    for k in ('T_air', 'T_surf', 'Qn_SW', 'Qn_LW', 'Qc', 'ET'):
+        out['pt_' + k] = np.array(getattr(e, k))
+    # ---- met rain/snow split
+    m = met_base.met_component()
+    m.DEBUG = False
+    m.P = g(0, 3e-5)
+    m.T_air = g(-4, 4)
+    m.T_air_type = 'Grid'
+    m.T_rain_snow = z(0.5)
+    m.P_rain = np.zeros((ny, nx))
+    m.P_snow = np.zeros((ny, nx))
+    m.update_P_rain()
+    m.update_P_snow()
+    for k in ('P', 'T_air', 'P_rain', 'P_snow'):
+        out['met_' + k] = np.array(getattr(m, k))
+    np.savez_compressed(os.path.join(GOLD, 'sources.npz'), **out)
+
+
+def main():
+    rh.import_reference()
+    os.makedirs(GOLD, exist_ok=True)
+    work = tempfile.mkdtemp(prefix='tf_golden_')
+    try:
+        meta = {'numpy': np.__version__, 'reference': 'peckhams/topoflow36 @ /root/reference'}
+        meta['treynor_emeli'] = gen_treynor(work)
+        gen_synth_channels(work)
+        gen_d8(work)
+        gen_sources()
+        with open(os.path.join(GOLD, 'meta.json'), 'w') as fh:
+            json.dump(meta, fh, indent=1, sort_keys=True)
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+    for f in sorted(os.listdir(GOLD)):
+        print('%10d  %s' % (os.path.getsize(os.path.join(GOLD, f)), f))
+
+
+if __name__ == '__main__':
+    main()

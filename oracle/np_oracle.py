@@ -1,0 +1,582 @@
+"""numpy restatement of the TopoFlow 3.6 hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is the *oracle of record* for the floating-point (fp64) routing
+path: it re-states, expression by expression and in the same evaluation
+order, what the reference's numpy code computes, so that on the same inputs
+it reproduces the reference bit-for-bit (checked live against the unmodified
+reference in ``tests/test_oracle_vs_reference.py`` whenever /root/reference is
+present, and against the committed fixtures in ``tests/golden/`` otherwise).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs may import it.  The product package
+(``topoflow36_b200``) never does; it has no CPU path.
+
+Parity status: PINNED -- D8 codes/area against the reference's own RiverTools
+fixtures (Treynor_flow.rtg, Treynor_area.rtg: bit-exact) and against live
+reference runs; routing against live reference runs (Treynor June-20-1967
+storm, 1592 steps: bit-exact in every fp64 grid).
+
+All ``file:line`` citations are relative to /root/reference/topoflow/.
+"""
+import numpy as np
+
+# ---------------------------------------------------------------------------
+# D8 constants  (components/d8_base.py:561-607, :624-640)
+# neighbour index k = 0..7  <->  NE, E, SE, S, SW, W, NW, N
+# ---------------------------------------------------------------------------
+CODE_LIST = np.int16([1, 2, 4, 8, 16, 32, 64, 128])
+CODE_OPPS = np.int16([16, 32, 64, 128, 1, 2, 4, 8])
+# (drow, dcol) of the cell a code-k cell drains to / of neighbour k
+NBR_DROW = np.array([-1, 0, 1, 1, 1, 0, -1, -1])
+NBR_DCOL = np.array([1, 1, 1, 0, -1, -1, -1, 0])
+
+
+_RESOLVE_HEX = (
+    "0001020204010202080802020808020210010202040402020808080208080802"
+    "2020020220200202080808020808080220202020202002020808080808080808"
+    "4040020204010202080802020808020210400202100102020808080208080802"
+    "2020202020200202202020020808080220202020202020022020202008080808"
+    "8080808080800202088002020880020280808080808002020808080208080802"
+    "2080808020800202208002020808080220202080202020022020200808080802"
+    "8080808080808080808080808080020280808080808080800880808008080802"
+    "2080808020808080208080802080028020202080202020802020202020200808")
+
+
+def resolve_table():
+    """256-entry tie-break table: index = sum of the tied direction codes,
+    value = the single code RiverTools keeps.  It is DATA, not a rule (e.g.
+    {E,S,SW}->S but {NE,E,S,SW}->E), so it is carried as a literal dumped from
+    the reference's get_resolve_array (components/d8_base.py:711-772) by
+    oracle/gen_golden.py and pinned by tests: sum 10161, 255 non-zero entries,
+    sha256 b0cd03c82342c315...."""
+    return np.frombuffer(bytes.fromhex(_RESOLVE_HEX), dtype=np.uint8).copy()
+
+
+def pixel_dims(ny, xres, yres):
+    """dx, dy, dd per row as float32 (fixed-length pixels).
+    components/d8_base.py:505-518, utils/pixels.py:71-171."""
+    dx = np.float64(xres)
+    dy = np.float64(yres)
+    dd = np.sqrt(dx ** 2 + dy ** 2)
+    one = np.zeros(ny, dtype=np.float64)
+    return (np.float32(one + dx), np.float32(one + dy), np.float32(one + dd))
+
+
+def d8_start_codes(DEM, dx, dy, dd, nodata=-9999.0, link_flats=True):
+    """components/d8_global.py:181-353 (non-periodic). Returns int16 grid."""
+    ny, nx = DEM.shape
+    dx0, dy0, dd0 = dx[0], dy[0], dd[0]
+    r = np.roll
+    with np.errstate(invalid='ignore', over='ignore'):
+        s1 = (DEM - r(r(DEM, 1, axis=0), -1, axis=1)) / dd0
+        s2 = (DEM - r(DEM, -1, axis=1)) / dx0
+        s3 = (DEM - r(r(DEM, -1, axis=0), -1, axis=1)) / dd0
+        s4 = (DEM - r(DEM, -1, axis=0)) / dy0
+        s5 = (DEM - r(r(DEM, -1, axis=0), 1, axis=1)) / dd0
+        s6 = (DEM - r(DEM, 1, axis=1)) / dx0
+        s7 = (DEM - r(r(DEM, 1, axis=0), 1, axis=1)) / dd0
+        s8 = (DEM - r(DEM, 1, axis=0)) / dy0
+        mx = np.maximum(s1, s2)
+        for s in (s3, s4, s5, s6, s7, s8):
+            np.maximum(mx, s, mx)
+        g = CODE_LIST
+        code = ((s1 == mx) * g[0] + (s2 == mx) * g[1] + (s3 == mx) * g[2] +
+                (s4 == mx) * g[3] + (s5 == mx) * g[4] + (s6 == mx) * g[5] +
+                (s7 == mx) * g[6] + (s8 == mx) * g[7])
+        if not link_flats:
+            code[mx <= 0] = 0
+        else:
+            flats = (mx == 0)
+            code[flats] = -1 * code[flats]
+            code[mx < 0] = -300
+        bad = np.logical_or(DEM <= nodata, np.isfinite(DEM) != 1)
+    code[bad] = 0
+    code[:, 0] = 0
+    code[:, nx - 1] = 0
+    code[0, :] = 0
+    code[ny - 1, :] = 0
+    return code.astype(np.int16)
+
+
+def d8_break_ties(code, resolve):
+    """components/d8_global.py:355-372."""
+    w = code > 0
+    code[w] = resolve[code[w]]
+    return code
+
+
+def d8_link_flats(code, resolve):
+    """components/d8_global.py:374-576.  Jacobi sweeps; returns (code, n_reps)."""
+    ny, nx = code.shape
+    g, h = CODE_LIST, CODE_OPPS
+    not_edge = np.ones((ny, nx), dtype=bool)
+    not_edge[0, :] = not_edge[-1, :] = False
+    not_edge[:, 0] = not_edge[:, -1] = False
+    n_reps = 0
+    while True:
+        n_reps += 1
+        rows, cols = np.where((code < 0) & (code != -300) & not_edge)
+        n_flats = rows.size
+        if n_flats == 0:
+            break
+        cur = (-1 * code[rows, cols]).astype(np.int64)
+        ready = np.zeros(n_flats, dtype=np.int64)
+        for k in range(8):
+            nb = code[(rows + NBR_DROW[k]) % ny, (cols + NBR_DCOL[k]) % nx]
+            valid = (nb > 0) & (nb != h[k])
+            allowed = (cur & int(g[k])) != 0
+            ready += (valid & allowed) * int(g[k])
+        fix = ready > 0
+        n_fix = int(fix.sum())
+        if n_fix:
+            code[rows[fix], cols[fix]] = resolve[ready[fix]]
+        if n_fix == n_flats or n_fix == 0:
+            break
+    return code, n_reps
+
+
+def d8_finalize(code):
+    """components/d8_global.py:139-146: drop leftovers, map to uint8."""
+    code = code.copy()
+    code[(code < 0) | (code > 128)] = 0
+    vmap = np.zeros(256, dtype=np.uint8)
+    vmap[CODE_LIST] = np.uint8(CODE_LIST)
+    return vmap[code]
+
+
+def d8_flow_grid(DEM, dx, dy, dd, nodata=-9999.0, link_flats=True):
+    res = resolve_table()
+    code = d8_start_codes(DEM, dx, dy, dd, nodata, link_flats)
+    code = d8_break_ties(code, res)
+    n_reps = 0
+    if link_flats:
+        code, n_reps = d8_link_flats(code, res)
+    return d8_finalize(code), n_reps
+
+
+def d8_parent_ids(code):
+    """components/d8_global.py:578-688 (non-periodic): (rows, cols) of parent;
+    (0, 0) for noflow / edge cells."""
+    ny, nx = code.shape
+    inc = np.zeros(129, dtype=np.int32)
+    inc[CODE_LIST] = np.array([-nx + 1, 1, nx + 1, nx, nx - 1, -1, -nx - 1, -nx],
+                              dtype=np.int32)
+    ids = np.arange(nx * ny, dtype=np.int32).reshape(ny, nx)
+    pid = ids + inc[code]
+    pid[:, 0] = 0
+    pid[:, -1] = 0
+    pid[0, :] = 0
+    pid[-1, :] = 0
+    pid[code <= 0] = 0
+    return divmod(pid, nx)
+
+
+def d8_ds_dw(code, dx, dy, dd):
+    """components/d8_global.py:873-1027 -> (ds, dw) float32 grids."""
+    ny, nx = code.shape
+    rows = np.arange(ny)[:, None] + np.zeros((1, nx), dtype=np.int64)
+    diag = (code == 1) | (code == 4) | (code == 16) | (code == 64)
+    horiz = (code == 2) | (code == 32)
+    vert = (code == 8) | (code == 128)
+    none = (code == 0)
+    ds = np.zeros((ny, nx), dtype=np.float32)
+    dw = np.zeros((ny, nx), dtype=np.float32)
+    ds[diag] = dd[rows[diag]]
+    dw[diag] = dd[rows[diag]]
+    ds[horiz] = dx[rows[horiz]]
+    dw[horiz] = dy[rows[horiz]]
+    ds[vert] = dy[rows[vert]]
+    dw[vert] = dx[rows[vert]]
+    ds[none] = dx[rows[none]]
+    dw[none] = dx[rows[none]]
+    return ds, dw
+
+
+def d8_area_levels(code, pixel_area):
+    """components/d8_global.py:1029-1332, whole-grid level sweeps exactly as the
+    reference does them (O(levels x N)); use only at small sizes."""
+    ny, nx = code.shape
+    h = CODE_OPPS
+    A = np.zeros((ny, nx), dtype=np.float32)
+    pa = np.asarray(pixel_area)
+    n_reps = 0
+    while True:
+        n_reps += 1
+        rows, cols = np.where((A == 0) & (code != 0))
+        if rows.size == 0:
+            break
+        a = []
+        d = []
+        for k in range(8):
+            rr = (rows + NBR_DROW[k]) % ny
+            cc = (cols + NBR_DCOL[k]) % nx
+            a.append(A[rr, cc])
+            d.append(code[rr, cc])
+        ready = np.ones(rows.size, dtype=bool)
+        for k in range(8):
+            ready &= ~((d[k] == h[k]) & (a[k] == 0))
+        WR = np.where(ready)[0]
+        if WR.size == 0:
+            break
+        r2, c2 = rows[WR], cols[WR]
+        A[r2, c2] = pa if pa.size == 1 else pa[r2, c2]
+        for k in range(8):
+            w = np.where(d[k][WR] == h[k])[0]
+            if w.size:
+                A[r2[w], c2[w]] += a[k][WR[w]]
+        if WR.size == rows.size:
+            break
+    return A, n_reps
+
+
+def d8_area_kahn(code, pixel_area, with_counts=False):
+    """O(N) restatement of update_area_grid: same per-cell result because each
+    cell's value is pixel_area (stored fp32) plus its children's FINAL values
+    added in neighbour order k=0..7 in fp32 -- only the schedule differs
+    (frontier of ready cells instead of whole-grid sweeps).  Optionally also
+    returns exact integer contributing-cell counts (int64)."""
+    ny, nx = code.shape
+    h = CODE_OPPS
+    pa = np.asarray(pixel_area)
+    A = np.zeros((ny, nx), dtype=np.float32)
+    N = np.zeros((ny, nx), dtype=np.int64)
+    flow = code != 0
+    # number of children (neighbours draining into the cell)
+    nchild = np.zeros((ny, nx), dtype=np.int32)
+    for k in range(8):
+        nb = np.roll(np.roll(code, -NBR_DROW[k], axis=0), -NBR_DCOL[k], axis=1)
+        nchild += (nb == h[k])
+    prow, pcol = d8_parent_ids(code)
+    rows, cols = np.where(flow & (nchild == 0))
+    pending = nchild.copy()
+    while rows.size:
+        a = np.full(rows.size, 0, dtype=np.float32)
+        a[:] = pa if pa.size == 1 else pa[rows, cols]
+        n = np.ones(rows.size, dtype=np.int64)
+        for k in range(8):
+            rr = (rows + NBR_DROW[k]) % ny
+            cc = (cols + NBR_DCOL[k]) % nx
+            w = code[rr, cc] == h[k]
+            a[w] += A[rr[w], cc[w]]
+            n[w] += N[rr[w], cc[w]]
+        A[rows, cols] = a
+        N[rows, cols] = n
+        pr, pc = prow[rows, cols], pcol[rows, cols]
+        ok = flow[pr, pc] & ~((pr == 0) & (pc == 0))
+        pr, pc = pr[ok], pc[ok]
+        np.subtract.at(pending, (pr, pc), 1)
+        lin = np.unique(pr.astype(np.int64) * nx + pc)
+        r2, c2 = np.divmod(lin, nx)
+        done = pending[r2, c2] == 0
+        rows, cols = r2[done], c2[done]
+    if with_counts:
+        return A, N
+    return A
+
+
+def d8_slope(DEM, code, ds):
+    """components/d8_global.py:1334-1348."""
+    pr, pc = d8_parent_ids(code)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        S = (DEM - DEM[pr, pc]) / ds
+    S[code <= 0] = 0.0
+    return S
+
+
+# ---------------------------------------------------------------------------
+# Channel routing  (components/channels_base.py)
+# ---------------------------------------------------------------------------
+G_ACCEL = np.float64(9.81)
+AVAL = np.float64(0.476)
+KAPPA = np.float64(0.408)
+LAW_CONST = np.sqrt(G_ACCEL) / KAPPA
+ONE_THIRD = np.float64(1.0) / 3.0
+TWO_THIRDS = np.float64(2.0) / 3.0
+DEG_TO_RAD = np.pi / np.float64(180)
+
+
+def remove_bad_slopes(slope):
+    """components/channels_base.py:4164-4260 (in place)."""
+    bad = np.isnan(slope) | (slope == 0.0) | (slope < 0.0) | np.isinf(slope)
+    if bad.any():
+        slope[bad] = slope[~bad].min()
+    return slope
+
+
+class Channels(object):
+    """State + step of channels_component for the non-flood path.
+
+    Mirrors initialize_computed_vars (:1137-1405) and update (:803-962).
+    Inputs follow the reference's conventions: grids are (ny, nx) float64;
+    anything that may be 'Scalar' in the CFG is a 0-D float64 array.
+    """
+
+    def __init__(self, code, ds32, dw32, slope, width, angle_deg, nval=None,
+                 z0val=None, sinu=1.0, d0=0.0, da=900.0, dt=6.0,
+                 kinematic=True, manning=True, outlet=(0, 0),
+                 rho_H2O=1000.0, check_stability=True):
+        f64 = np.float64
+        self.code = code
+        self.ny, self.nx = code.shape
+        self.KINEMATIC_WAVE = kinematic
+        self.MANNING = manning
+        self.LAW_OF_WALL = not manning
+        self.dt = np.array(dt, dtype=f64)
+        self.da = np.array(da, dtype=f64)
+        self.rho_H2O = np.array(rho_H2O, dtype=f64)
+        self.outlet_ID = outlet
+        self.CHECK_STABILITY = check_stability
+        self.noflow = np.where(code <= 0)
+        self.parent_IDs = d8_parent_ids(code)
+        self.n_pixels = self.ny * self.nx
+        # ---- :1196  angle to radians (in place on a float64 copy)
+        self.angle = np.array(angle_deg, dtype=f64)
+        self.angle *= DEG_TO_RAD
+        # ---- :1206-1209 zero widths -> dw
+        self.width = np.array(width, dtype=f64)
+        if self.width.ndim == 2:
+            w1 = (self.width == 0)
+            if w1.sum() > 0:
+                self.width[w1] = dw32[w1]
+        self.sinu = np.array(sinu, dtype=f64)
+        self.nval = None if nval is None else np.array(nval, dtype=f64)
+        self.z0val = None if z0val is None else np.array(z0val, dtype=f64)
+        # ---- :1242-1249
+        self.ds = (self.sinu * ds32)           # float64 under numpy 2
+        self.slope = (np.array(slope, dtype=f64) / self.sinu)
+        self.S_bed = self.slope
+        self.S_free = self.S_bed.copy()
+        z = lambda: np.zeros((self.ny, self.nx), dtype=f64)
+        self.u, self.f, self.d = z(), z(), z()
+        self.d += np.array(d0, dtype=f64)
+        self.R = z()
+        self.tau, self.u_star, self.froude = z(), z(), z()
+        self.vol_R = np.array(0, dtype=f64)
+        self.vol_Q = np.array(0, dtype=f64)
+        self.vol_edge = np.array(0, dtype=f64)
+        if kinematic:
+            remove_bad_slopes(self.slope)
+        # ---- :1331-1336
+        L2 = self.d * np.tan(self.angle)
+        self.A_wet = self.d * (self.width + L2)
+        self.P_wet = self.width + (f64(2) * self.d / np.cos(self.angle))
+        self.vol = self.A_wet * self.ds
+        self.Q = z()
+        self.Rh = z()
+        self.vol_chan_sum0 = self.vol.sum()
+        for n in ('Q_outlet', 'u_outlet', 'd_outlet', 'f_outlet', 'Q_peak',
+                  'T_peak', 'u_peak', 'Tu_peak', 'd_peak', 'Td_peak'):
+            setattr(self, n, np.array(0, dtype=f64))
+        self.time = np.array(0, dtype=f64)
+        self.time_min = np.array(0, dtype=f64)
+        self.time_index = 0
+        zero = np.array(0, dtype=f64)
+        self.P_rain, self.SM, self.GW, self.MR = zero, zero, zero, zero
+        self.ET, self.IN = zero, zero
+
+    # ---------------------------------------------------------------- update
+    def step(self):
+        f64 = np.float64
+        dt = self.dt
+        # update_R :1548-1655
+        P, SM, GW, ET, IN, MR = (self.P_rain, self.SM, self.GW, self.ET,
+                                 self.IN, self.MR)
+        w = (self.vol < (ET * self.da * self.dt))
+        if np.ndim(ET) == self.vol.ndim:
+            ET[w] = 0.0
+        else:
+            ET = 0.0
+        self.R = (P + SM + GW + MR) - (ET + IN)
+        # update_R_integral :1657-1672
+        volume = f64(self.R * self.da * self.dt)
+        if np.size(volume) == 1:
+            self.vol_R += (volume * self.n_pixels)
+        else:
+            self.vol_R += np.sum(volume)
+        # update_channel_discharge :1697
+        self.Q[:] = self.u * self.A_wet
+        # update_flow_volume :2086-2145
+        self.vol += (self.R * self.da) * dt
+        pr, pc = self.parent_IDs
+        for k in range(8):
+            wk = np.where(self.code == CODE_LIST[k])
+            if wk[0].size:
+                self.vol[pr[wk], pc[wk]] += (dt * self.Q[wk])
+        self.vol -= (self.Q * dt)
+        np.maximum(self.vol, 0.0, self.vol)
+        # update_channel_depth :2250-2391
+        self._update_depth()
+        # update_trapezoid_Rh :2643-2712
+        d, wb = self.d, self.width
+        L2 = d * np.tan(self.angle)
+        A_wet = d * (wb + L2)
+        P_wet = wb + (f64(2) * d / np.cos(self.angle))
+        P_wet[self.noflow] = f64(1)
+        Rh = (A_wet / P_wet)
+        Rh[self.noflow] = f64(0)
+        self.Rh[:] = Rh
+        self.A_wet[:] = A_wet
+        self.P_wet[:] = P_wet
+        # update_free_surface_slope :2583-2618
+        if not self.KINEMATIC_WAVE:
+            delta_d = (self.d - self.d[self.parent_IDs])
+            self.S_free[:] = self.S_bed + (delta_d / self.ds)
+        # shear stress / speed :2620-2641
+        slope = self.S_bed if self.KINEMATIC_WAVE else np.abs(self.S_free)
+        self.tau[:] = self.rho_H2O * G_ACCEL * self.d * slope
+        self.u_star[:] = np.sqrt(self.tau / self.rho_H2O)
+        # update_friction_factor :2714-2833
+        wg = self.d_is_pos
+        wbad = self.d_is_zero
+        if self.MANNING:
+            if self.nval.size > 1:
+                n2 = self.nval[wg] ** f64(2)
+            else:
+                n2 = self.nval ** f64(2)
+            self.f[wg] = G_ACCEL * (n2 / (self.d[wg] ** ONE_THIRD))
+            self.f[wbad] = f64(0)
+        if self.LAW_OF_WALL:
+            smooth = (AVAL / self.z0val) * self.d
+            np.maximum(smooth, f64(1.1), out=smooth)
+            self.f[wg] = (KAPPA / np.log(smooth[wg])) ** f64(2)
+            self.f[wbad] = f64(0)
+        # update_velocity (kinematic_wave.py:84-127, :3960-4063)
+        S = self.S_bed if self.KINEMATIC_WAVE else self.S_free
+        S2 = np.abs(S)
+        if self.MANNING:
+            self.u[:] = (self.Rh ** TWO_THIRDS) * np.sqrt(S2) / self.nval
+        if self.LAW_OF_WALL:
+            smooth = (AVAL / self.z0val) * self.d
+            np.maximum(smooth, f64(1.1), out=smooth)
+            self.u[:] = LAW_CONST * np.sqrt(self.Rh * S2) * np.log(smooth)
+        # update_velocity_on_edges :2851
+        self.u[self.noflow] = f64(0)
+        # update_froude_number :2867
+        self.froude[wg] = self.u[wg] / np.sqrt(G_ACCEL * self.d[wg])
+        self.froude[wbad] = f64(0)
+        # outlet, peaks, integrals :2884-2936
+        o = self.outlet_ID
+        self.Q_outlet.fill(self.Q[o])
+        self.u_outlet.fill(self.u[o])
+        self.d_outlet.fill(self.d[o])
+        self.f_outlet.fill(self.f[o])
+        if self.Q_outlet > self.Q_peak:
+            self.Q_peak.fill(self.Q_outlet)
+            self.T_peak.fill(self.time_min)
+        if self.u_outlet > self.u_peak:
+            self.u_peak.fill(self.u_outlet)
+            self.Tu_peak.fill(self.time_min)
+        if self.d_outlet > self.d_peak:
+            self.d_peak.fill(self.d_outlet)
+            self.Td_peak.fill(self.time_min)
+        self.vol_Q += (self.Q_outlet * self.dt)
+        # update_edge_values :2938-2984
+        self.vol_edge += self.vol[self.noflow].sum()
+        self.vol[self.noflow] = 0.0
+        self.d[self.noflow] = 0.0
+        # checks :3193-3454
+        self.n_bad_depth = int((self.d < 0.0).sum() + np.isinf(self.d).sum())
+        self.n_bad_vel = int((self.u < 0.0).sum() + np.isnan(self.u).sum()
+                             + np.isinf(self.u).sum())
+        if self.CHECK_STABILITY:
+            if self.n_bad_depth:
+                raise RuntimeError('Negative or NaN depth found.')
+            if self.n_bad_vel:
+                raise RuntimeError('Found bad velocities.')
+        # update_time (utils/BMI_base.py:1029-1090)
+        self.time_index += 1
+        self.time += self.dt
+        self.time_min = self.time / f64(60)
+
+    def _update_depth(self):
+        vol, width, angle = self.vol, self.width, self.angle
+        d = self.d
+        with np.errstate(invalid='ignore', divide='ignore'):
+            if np.size(angle) == 1:
+                if angle == 0.0:
+                    d = vol / (width * self.ds)
+                else:
+                    denom = 2.0 * np.tan(angle)
+                    arg = 2.0 * denom * vol / self.ds
+                    arg += width ** (2.0)
+                    d = (np.sqrt(arg) - width) / denom
+            else:
+                w1 = (angle == 0)
+                w2 = np.invert(w1)
+                A_top = width[w1] * self.ds[w1]
+                d[w1] = vol[w1] / A_top
+                denom = 2.0 * np.tan(angle[w2])
+                arg = 2.0 * denom * vol[w2] / self.ds[w2]
+                arg += width[w2] ** (2.0)
+                d[w2] = (np.sqrt(arg) - width[w2]) / denom
+        np.maximum(d, 0.0, self.d)
+        self.d_is_pos = (self.d > 0)
+        self.d_is_zero = np.invert(self.d_is_pos)
+
+
+# ---------------------------------------------------------------------------
+# Source terms (each a separate BMI component in the reference)
+# ---------------------------------------------------------------------------
+def met_split_precip(P, T_air, T_rain_snow):
+    """components/met_base.py:1300-1388."""
+    return P * (T_air > T_rain_snow), P * (T_air <= T_rain_snow)
+
+
+def green_ampt_step(I, P_rain, SM, Ks, Ki, qs, qi, G, dt,
+                    h_table=None, elev=None):
+    """infil_green_ampt.py:511-578 + infil_base.py:562-571, :654-709,
+    :954-995, :782-811.  Returns (IN, I_new)."""
+    P_total = (P_rain + SM)
+    dK = (Ks - Ki)
+    dq = (qs - qi)
+    fc = (G * dK * dq / I) + Ks
+    IN = np.minimum(fc, P_total)
+    if np.size(P_total) == 1 and np.size(Ks) == 1:
+        if np.size(IN) == 1:
+            if P_total < Ks:
+                IN = P_total
+        else:
+            if P_total < Ks:
+                IN = np.zeros_like(IN) + P_total
+    else:
+        IN = np.array(IN, dtype=np.float64)
+        w = (P_total < Ks)
+        w = np.broadcast_to(w, IN.shape)
+        if np.size(P_total) > 1:
+            IN[w] = np.broadcast_to(P_total, IN.shape)[w]
+        else:
+            IN[w] = P_total
+    if np.size(IN) > 1 and h_table is not None and elev is not None:
+        IN[np.broadcast_to(h_table >= elev, IN.shape)] = 0.0
+    I_new = I + (IN * dt)
+    return IN, I_new
+
+
+def degree_day_step(h_swe, P_snow, T_air, c0, T0, dt, rho_H2O=1000.0,
+                    rho_snow=300.0):
+    """snow_degree_day.py:293-360; snow_base.py:490-512, :559-609, :631-703.
+    Returns (SM, h_swe_new, h_snow_new)."""
+    f64 = np.float64
+    M = (c0 / f64(8.64E7)) * (T_air - T0)
+    SM = np.array(M, dtype=f64) + np.zeros_like(h_swe)
+    SM_max = h_swe / dt
+    np.minimum(SM, SM_max, out=SM)
+    np.maximum(SM, f64(0), out=SM)
+    h_new = np.array(h_swe, dtype=f64, copy=True)
+    h_new += (P_snow * dt)
+    h_new -= (SM * dt)
+    np.maximum(h_new, f64(0), h_new)
+    h_snow = h_new * (rho_H2O / rho_snow)
+    return SM, h_new, h_snow
+
+
+def priestley_taylor_step(T_air, T_surf, Qn_SW, Qn_LW, alpha, K_soil, soil_x,
+                          T_soil_x):
+    """evap_base.py:326-353; evap_priestley_taylor.py:308-413. Returns ET."""
+    f64 = np.float64
+    delta_T = (T_surf - T_soil_x)
+    Qc = K_soil * delta_T / soil_x
+    Q_net = Qn_SW + Qn_LW
+    Qet = alpha * (f64(0.406) + (f64(0.011) * T_air)) * (Q_net + Qc)
+    ET = (Qet / f64(2.5E+9))
+    return np.maximum(ET, f64(0))

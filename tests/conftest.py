@@ -1,0 +1,54 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+    config.addinivalue_line('markers', 'reference: needs the read-only reference tree at /root/reference')
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLD, name)))
+
+
+@pytest.fixture(scope='session')
+def treynor():
+    return load_golden('treynor_inputs.npz')
+
+
+@pytest.fixture(scope='session')
+def treynor_kw():
+    return load_golden('treynor_kw_standalone.npz')
+
+
+@pytest.fixture(scope='session')
+def synth_channels():
+    return load_golden('synth_channels.npz')
+
+
+@pytest.fixture(scope='session')
+def d8_synth():
+    return load_golden('d8_synth.npz')
+
+
+@pytest.fixture(scope='session')
+def sources_gold():
+    return load_golden('sources.npz')
+
+
+def rel_err(a, b):
+    """max |a-b| / max(|b|) over the array (0 when both are all-zero)."""
+    a = np.asarray(a, dtype='float64')
+    b = np.asarray(b, dtype='float64')
+    scale = np.abs(b).max()
+    if scale == 0:
+        return float(np.abs(a).max())
+    return float(np.abs(a - b).max() / scale)

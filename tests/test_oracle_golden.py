@@ -1,0 +1,140 @@
+"""The numpy oracle against the committed reference fixtures (CPU only).
+
+These are the checks that PIN the oracle: every fixture under tests/golden was
+produced by the unmodified reference (oracle/gen_golden.py) or ships with it
+(Treynor_flow.rtg / Treynor_area.rtg, RiverTools output)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import np_oracle as o
+
+GRIDS = ('vol', 'd', 'u', 'Q', 'Rh', 'A_wet', 'P_wet', 'f', 'tau', 'u_star', 'froude')
+SCALARS = ('vol_R', 'vol_Q', 'vol_edge', 'Q_outlet', 'u_outlet', 'd_outlet', 'f_outlet',
+           'Q_peak', 'T_peak', 'u_peak', 'Tu_peak', 'd_peak', 'Td_peak')
+
+
+def test_resolve_table_golden(d8_synth):
+    t = o.resolve_table()
+    assert t.sum() == 10161 and (t != 0).sum() == 255
+    assert list(t[:16]) == [0, 1, 2, 2, 4, 1, 2, 2, 8, 8, 2, 2, 8, 8, 2, 2]
+    assert hashlib.sha256(t.tobytes()).hexdigest().startswith('b0cd03c82342c315')
+    assert np.array_equal(t, d8_synth['resolve'])
+
+
+def test_treynor_d8_matches_rivertools_fixtures(treynor):
+    """Treynor_flow.rtg / Treynor_area.rtg (shipped with the reference): bit-exact."""
+    DEM = treynor['DEM']
+    dx, dy, dd = o.pixel_dims(DEM.shape[0], treynor['xres'], treynor['yres'])
+    code, _ = o.d8_flow_grid(DEM, dx, dy, dd, link_flats=True)
+    assert np.array_equal(code, treynor['flow'])
+    pa = np.float64(treynor['xres'] * treynor['yres']) / 1e6
+    A_lv, _ = o.d8_area_levels(code, pa)
+    A_kahn, N = o.d8_area_kahn(code, pa, with_counts=True)
+    assert np.array_equal(A_lv, treynor['area'])
+    assert np.array_equal(A_kahn, treynor['area'])
+    assert np.array_equal(A_kahn, treynor['d8_area'])
+    hist = {int(k): int((code == k).sum()) for k in np.unique(code)}
+    assert hist == {0: 142, 1: 102, 2: 291, 4: 180, 8: 132, 16: 163, 32: 157, 64: 99, 128: 10}
+    assert N.max() == 554
+
+
+@pytest.mark.parametrize('lf', [1, 0])
+def test_d8_synth_bit_exact(d8_synth, lf):
+    g = d8_synth
+    DEM = g['DEM']
+    ny, nx = DEM.shape
+    dx, dy, dd = o.pixel_dims(ny, 30.0, 30.0)
+    res = o.resolve_table()
+    start = o.d8_start_codes(DEM, dx, dy, dd, link_flats=bool(lf))
+    assert np.array_equal(start, g['lf%d_start' % lf])
+    ties = o.d8_break_ties(start.copy(), res)
+    assert np.array_equal(ties, g['lf%d_ties' % lf])
+    code, _ = o.d8_flow_grid(DEM, dx, dy, dd, link_flats=bool(lf))
+    assert np.array_equal(code, g['lf%d_code' % lf])
+    ds, dw = o.d8_ds_dw(code, dx, dy, dd)
+    assert np.array_equal(ds, g['lf%d_ds' % lf]) and np.array_equal(dw, g['lf%d_dw' % lf])
+    A = o.d8_area_kahn(code, np.float64(900.0) / 1e6)
+    assert np.array_equal(A, g['lf%d_area' % lf])
+    pr, pc = o.d8_parent_ids(code)
+    assert np.array_equal(pr * nx + pc, g['lf%d_pid' % lf])
+    S = o.d8_slope(DEM, code, ds)
+    assert np.array_equal(S, g['lf%d_slope' % lf], equal_nan=True)
+
+
+def _treynor_channels(treynor):
+    DEM = treynor['DEM']
+    dx, dy, dd = o.pixel_dims(DEM.shape[0], treynor['xres'], treynor['yres'])
+    code = treynor['flow']
+    ds, dw = o.d8_ds_dw(code, dx, dy, dd)
+    ch = o.Channels(code, ds, dw, treynor['slope'], treynor['width'], treynor['angle'],
+                    nval=treynor['nval'], da=900.0, dt=6.0, outlet=(34, 16))
+    ch.ET = np.zeros(code.shape)
+    ch.IN = np.zeros(code.shape)
+    return ch
+
+
+def test_treynor_kw_storm_bit_exact(treynor, treynor_kw):
+    """1200 steps of the June-20-1967 storm, stand-alone reference run."""
+    ch = _treynor_channels(treynor)
+    rain = treynor['rain_mmph']
+    series = treynor_kw['outlet_series']
+    for i in range(1200):
+        m = i // 10
+        P = np.float64(rain[m]) / (1000.0 * 3600.0) if m < rain.size else 0.0
+        ch.P_rain = np.array(P, dtype='float64')
+        ch.step()
+        assert (float(ch.Q_outlet), float(ch.u_outlet), float(ch.d_outlet),
+                float(ch.f_outlet)) == tuple(series[i])
+        if (i + 1) in (100, 400, 1200):
+            for n in GRIDS:
+                assert np.array_equal(getattr(ch, n), treynor_kw['s%d_%s' % (i + 1, n)]), n
+            for n in SCALARS:
+                assert float(getattr(ch, n)) == float(treynor_kw['s%d_%s' % (i + 1, n)]), n
+
+
+@pytest.mark.parametrize('tag', ['kw_man', 'kw_low', 'dw_man', 'dw_low'])
+def test_synth_channels_bit_exact(synth_channels, tag):
+    g = synth_channels
+    kin, man = tag.startswith('kw'), tag.endswith('man')
+    code = g['code']
+    ch = o.Channels(code, g['ds32'], g['dw32'], g['slope'], g['width'], g['angle'],
+                    nval=g['nval'] if man else None, z0val=None if man else g['z0val'],
+                    da=900.0, dt=2.0, kinematic=kin, manning=man,
+                    outlet=(code.shape[0] - 2, code.shape[1] // 2))
+    z = lambda v: np.array(v, dtype='float64')
+    ch.P_rain, ch.GW, ch.SM = z(80 / 3.6e6), z(1e-7), z(2e-7)
+    ch.ET, ch.IN = g['ET0'].copy(), g['IN0'].copy()
+    assert np.array_equal(ch.S_bed, g[tag + '_S_bed'])
+    for i in range(150):
+        if i == 100:
+            ch.P_rain = z(0)
+        ch.step()
+    for n in GRIDS + (() if kin else ('S_free',)):
+        assert np.array_equal(getattr(ch, n), g[tag + '_' + n], equal_nan=True), n
+    for n in SCALARS:
+        assert float(getattr(ch, n)) == float(g[tag + '_' + n]), n
+    assert np.array_equal(ch.ET, g[tag + '_ET_after'])
+
+
+def test_sources_bit_exact(sources_gold):
+    g = sources_gold
+    I = np.zeros_like(g['ga_P_rain']) + 1e-6
+    for it in range(3):
+        IN, I = o.green_ampt_step(I, g['ga_P_rain'], g['ga_SM'], g['ga_Ks'], g['ga_Ki'],
+                                  g['ga_qs'], g['ga_qi'], g['ga_G'], 5.0,
+                                  h_table=g['ga_h_table'], elev=g['ga_elev'])
+        assert np.array_equal(IN, g['ga_IN%d' % it])
+        assert np.array_equal(I, g['ga_I%d' % it])
+    h = g['dd_h_swe_init']
+    for it in range(3):
+        SM, h, hs = o.degree_day_step(h, g['dd_P_snow'], g['dd_T_air'], 2.7, -0.2, 3600.0)
+        assert np.array_equal(SM, g['dd_SM%d' % it])
+        assert np.array_equal(h, g['dd_h_swe%d' % it])
+        assert np.array_equal(hs, g['dd_h_snow%d' % it])
+    ET = o.priestley_taylor_step(g['pt_T_air'], g['pt_T_surf'], g['pt_Qn_SW'], g['pt_Qn_LW'],
+                                 1.26, 0.45, 0.05, 12.0)
+    assert np.array_equal(ET, g['pt_ET'])
+    pr, ps = o.met_split_precip(g['met_P'], g['met_T_air'], 0.5)
+    assert np.array_equal(pr, g['met_P_rain']) and np.array_equal(ps, g['met_P_snow'])

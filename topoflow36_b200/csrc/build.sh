@@ -1,0 +1,23 @@
+#!/bin/bash
+# Build libtfb_b200.so in-tree for sm_100a (B200).  nvcc cross-compiles without a GPU.
+set -euo pipefail
+here="$(cd "$(dirname "$0")" && pwd)"
+out="$here/../libtfb_b200.so"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17
+       -fmad=false -Xcompiler -fPIC -Xcompiler -O2 --use_fast_math=false)
+# --use_fast_math=false is not a real flag; keep precise math explicitly:
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17
+       -fmad=false -prec-div=true -prec-sqrt=true -ftz=false
+       -Xcompiler -fPIC -Xcompiler -O2)
+objs=()
+for f in tfb_capi tfb_channels tfb_d8 tfb_sources; do
+  if [ ! -f "$here/$f.o" ] || [ "$here/$f.cu" -nt "$here/$f.o" ] || \
+     [ "$here/tfb_common.cuh" -nt "$here/$f.o" ] || [ "$here/../../include/tfb.h" -nt "$here/$f.o" ]; then
+    "$NVCC" "${FLAGS[@]}" ${TFB_EXTRA_NVCC_FLAGS:-} -c "$here/$f.cu" -o "$here/$f.o" &
+  fi
+  objs+=("$here/$f.o")
+done
+wait
+"$NVCC" -shared -gencode arch=compute_100a,code=sm_100a -o "$out" "${objs[@]}" -lcudart
+echo "built $out"

@@ -1,0 +1,434 @@
+// D8 preprocessing toolkit for B200 (sm_100a): flow codes, tie breaking, flat
+// linking, parent IDs, flow length/width, total contributing area, slope.
+//
+// Replaces components/d8_global.py (start_new_d8_codes :181-353,
+// break_flow_grid_ties :355-372, link_flats :374-576, update_parent_ID_grid
+// :578-650, update_flow_width_grid :873-958, update_flow_length_grid :960-1027,
+// update_area_grid :1029-1332, update_slope_grid :1334-1348) and the tie table
+// of components/d8_base.py:711-772.  All of it is integer / fp32 work and must
+// be BIT-EXACT against the reference; nothing here may be re-associated.
+#include "tfb_common.cuh"
+
+#include <string.h>
+
+namespace tfb {
+
+// Tie-break table: index = sum of tied codes, value = code RiverTools keeps.
+// Data dumped from the reference's get_resolve_array (d8_base.py:711-772);
+// pinned by tests (sum 10161, sha256 b0cd03c82342c315...).
+static const uint8_t kResolveHost[256] = {
+    0x00,0x01,0x02,0x02,0x04,0x01,0x02,0x02,0x08,0x08,0x02,0x02,0x08,0x08,0x02,0x02,
+    0x10,0x01,0x02,0x02,0x04,0x04,0x02,0x02,0x08,0x08,0x08,0x02,0x08,0x08,0x08,0x02,
+    0x20,0x20,0x02,0x02,0x20,0x20,0x02,0x02,0x08,0x08,0x08,0x02,0x08,0x08,0x08,0x02,
+    0x20,0x20,0x20,0x20,0x20,0x20,0x02,0x02,0x08,0x08,0x08,0x08,0x08,0x08,0x08,0x08,
+    0x40,0x40,0x02,0x02,0x04,0x01,0x02,0x02,0x08,0x08,0x02,0x02,0x08,0x08,0x02,0x02,
+    0x10,0x40,0x02,0x02,0x10,0x01,0x02,0x02,0x08,0x08,0x08,0x02,0x08,0x08,0x08,0x02,
+    0x20,0x20,0x20,0x20,0x20,0x20,0x02,0x02,0x20,0x20,0x20,0x02,0x08,0x08,0x08,0x02,
+    0x20,0x20,0x20,0x20,0x20,0x20,0x20,0x02,0x20,0x20,0x20,0x20,0x08,0x08,0x08,0x08,
+    0x80,0x80,0x80,0x80,0x80,0x80,0x02,0x02,0x08,0x80,0x02,0x02,0x08,0x80,0x02,0x02,
+    0x80,0x80,0x80,0x80,0x80,0x80,0x02,0x02,0x08,0x08,0x08,0x02,0x08,0x08,0x08,0x02,
+    0x20,0x80,0x80,0x80,0x20,0x80,0x02,0x02,0x20,0x80,0x02,0x02,0x08,0x08,0x08,0x02,
+    0x20,0x20,0x20,0x80,0x20,0x20,0x20,0x02,0x20,0x20,0x20,0x08,0x08,0x08,0x08,0x02,
+    0x80,0x80,0x80,0x80,0x80,0x80,0x80,0x80,0x80,0x80,0x80,0x80,0x80,0x80,0x02,0x02,
+    0x80,0x80,0x80,0x80,0x80,0x80,0x80,0x80,0x08,0x80,0x80,0x80,0x08,0x08,0x08,0x02,
+    0x20,0x80,0x80,0x80,0x20,0x80,0x80,0x80,0x20,0x80,0x80,0x80,0x20,0x80,0x02,0x80,
+    0x20,0x20,0x20,0x80,0x20,0x20,0x20,0x80,0x20,0x20,0x20,0x20,0x20,0x20,0x08,0x08};
+
+__device__ __constant__ uint8_t kResolve[256];
+static bool g_resolve_uploaded[64] = {false};
+
+static int ensure_resolve_uploaded() {
+    int dev = 0;
+    TFB_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 64 && g_resolve_uploaded[dev]) return TFB_OK;
+    TFB_CUDA_CHECK(cudaMemcpyToSymbol(kResolve, kResolveHost, 256));
+    if (dev < 64) g_resolve_uploaded[dev] = true;
+    return TFB_OK;
+}
+
+__device__ __forceinline__ float np_maxf(float a, float b) {
+    return (a >= b || a != a) ? a : b;
+}
+
+// ---------------------------------------------------------------- start codes
+__global__ void __launch_bounds__(256)
+d8_codes_kernel(const float *__restrict__ dem, int ny, int nx, int halo, int row0,
+                int ny_global, float dx, float dy, float dd, double nodata,
+                int link_flats, int16_t *__restrict__ code) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y * blockDim.y + threadIdx.y;
+    if (c >= nx || r >= ny) return;
+    const int64_t i = (int64_t)r * nx + c;
+    const int gr = r + row0;
+    int out = 0;
+    const bool border = (c == 0 || c == nx - 1 || gr == 0 || gr == ny_global - 1);
+    const bool rows_ok = (r - 1 >= -halo) && (r + 1 < ny + halo);
+    if (!border && rows_ok) {
+        const float z = dem[i];
+        const float *up = dem + i - nx, *dn = dem + i + nx;
+        // slopes in the DEM's dtype, in the reference's order s1..s8
+        const float s1 = (z - up[1]) / dd;    // NE
+        const float s2 = (z - dem[i + 1]) / dx;   // E
+        const float s3 = (z - dn[1]) / dd;    // SE
+        const float s4 = (z - dn[0]) / dy;    // S
+        const float s5 = (z - dn[-1]) / dd;   // SW
+        const float s6 = (z - dem[i - 1]) / dx;   // W
+        const float s7 = (z - up[-1]) / dd;   // NW
+        const float s8 = (z - up[0]) / dy;    // N
+        float mx = np_maxf(s1, s2);
+        mx = np_maxf(mx, s3); mx = np_maxf(mx, s4); mx = np_maxf(mx, s5);
+        mx = np_maxf(mx, s6); mx = np_maxf(mx, s7); mx = np_maxf(mx, s8);
+        int cd = (s1 == mx) * 1 + (s2 == mx) * 2 + (s3 == mx) * 4 + (s4 == mx) * 8 +
+                 (s5 == mx) * 16 + (s6 == mx) * 32 + (s7 == mx) * 64 + (s8 == mx) * 128;
+        if (!link_flats) {
+            if (mx <= 0.0f) cd = 0;
+        } else {
+            if (mx == 0.0f) cd = -cd;
+            if (mx < 0.0f) cd = -300;
+        }
+        if ((double)z <= nodata || !isfinite(z)) cd = 0;
+        out = cd;
+    }
+    code[i] = (int16_t)out;
+}
+
+__global__ void d8_break_ties_kernel(int16_t *code, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int v = code[i];
+    if (v > 0) code[i] = (int16_t)kResolve[v & 255];
+}
+
+// ---------------------------------------------------------------- flat linking
+__global__ void __launch_bounds__(256)
+d8_link_flats_kernel(const int16_t *__restrict__ in, int16_t *__restrict__ out, int ny,
+                     int nx, int halo, int row0, int ny_global, int *n_flats,
+                     int *n_fixed) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y * blockDim.y + threadIdx.y;
+    int is_flat = 0, is_fixed = 0;
+    if (c < nx && r < ny) {
+        const int64_t i = (int64_t)r * nx + c;
+        const int gr = r + row0;
+        int v = in[i];
+        const bool edge = (c == 0 || c == nx - 1 || gr == 0 || gr == ny_global - 1);
+        if (v < 0 && v != -300 && !edge && (r - 1 >= -halo) && (r + 1 < ny + halo)) {
+            is_flat = 1;
+            const int tied = -v;
+            int ready = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int nb = in[i + (int64_t)kNbrDRow[k] * nx + kNbrDCol[k]];
+                const int opp = 1 << ((k + 4) & 7);
+                // neighbour already drains somewhere, and not back into us
+                if (nb > 0 && nb != opp && (tied & (1 << k))) ready |= (1 << k);
+            }
+            if (ready > 0) {
+                v = kResolve[ready];
+                is_fixed = 1;
+            }
+        }
+        out[i] = (int16_t)v;
+    }
+    const unsigned mf = __ballot_sync(0xffffffffu, is_flat);
+    const unsigned mx = __ballot_sync(0xffffffffu, is_fixed);
+    if ((threadIdx.x & 31) == 0 && (threadIdx.y * blockDim.x + threadIdx.x) % 32 == 0) {
+        if (mf) atomicAdd(n_flats, __popc(mf));
+        if (mx) atomicAdd(n_fixed, __popc(mx));
+    }
+}
+
+__global__ void d8_finalize_kernel(const int16_t *__restrict__ in, uint8_t *__restrict__ out,
+                                   int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int v = in[i];
+    // valid_code_map (d8_base.py:597-607): only the 8 single-direction codes
+    const bool ok = (v > 0 && v <= 128 && (v & (v - 1)) == 0);
+    out[i] = ok ? (uint8_t)v : (uint8_t)0;
+}
+
+// ---------------------------------------------------------------- ds / dw
+__global__ void d8_ds_dw_kernel(const uint8_t *__restrict__ code, const float *dx,
+                                const float *dy, const float *dd, int ny, int nx,
+                                float *ds, float *dw) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y * blockDim.y + threadIdx.y;
+    if (c >= nx || r >= ny) return;
+    const int64_t i = (int64_t)r * nx + c;
+    const unsigned cd = code[i];
+    if (ds) ds[i] = ds_of(cd, dx[r], dy[r], dd[r]);
+    if (dw) dw[i] = dw_of(cd, dx[r], dy[r], dd[r]);
+}
+
+// ---------------------------------------------------------------- parent IDs
+__global__ void d8_parent_kernel(const uint8_t *__restrict__ code, int ny, int nx,
+                                 int32_t *pid) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y * blockDim.y + threadIdx.y;
+    if (c >= nx || r >= ny) return;
+    const int64_t i = (int64_t)r * nx + c;
+    const unsigned cd = code[i];
+    int32_t p = 0;
+    if (cd != 0 && c != 0 && c != nx - 1 && r != 0 && r != ny - 1) {
+        int dr, dc;
+        code_offset(cd, dr, dc);
+        p = (int32_t)(i + (int64_t)dr * nx + dc);
+    }
+    pid[i] = p;
+}
+
+// ---------------------------------------------------------------- slope
+__global__ void d8_slope_kernel(const float *__restrict__ dem, const uint8_t *__restrict__ code,
+                                const float *dx, const float *dy, const float *dd, int ny,
+                                int nx, float *S) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y * blockDim.y + threadIdx.y;
+    if (c >= nx || r >= ny) return;
+    const int64_t i = (int64_t)r * nx + c;
+    const unsigned cd = code[i];
+    float s = 0.0f;
+    if (cd != 0 && c != 0 && c != nx - 1 && r != 0 && r != ny - 1) {
+        int dr, dc;
+        code_offset(cd, dr, dc);
+        const float zp = dem[i + (int64_t)dr * nx + dc];
+        s = (dem[i] - zp) / ds_of(cd, dx[r], dy[r], dd[r]);
+    }
+    S[i] = s;
+}
+
+// ---------------------------------------------------------------- area
+// number of children = neighbours k whose code points back at the cell
+__device__ __forceinline__ int child_mask(const uint8_t *__restrict__ code, int ny, int nx,
+                                          int r, int c) {
+    int m = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int rr = r + kNbrDRow[k], cc = c + kNbrDCol[k];
+        if (rr < 0 || rr >= ny || cc < 0 || cc >= nx) continue;
+        if (code[(int64_t)rr * nx + cc] == (uint8_t)(1u << ((k + 4) & 7))) m |= (1 << k);
+    }
+    return m;
+}
+
+__global__ void __launch_bounds__(256)
+d8_area_init_kernel(const uint8_t *__restrict__ code, int ny, int nx, float *A,
+                    int64_t *count, int32_t *pending) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y * blockDim.y + threadIdx.y;
+    if (c >= nx || r >= ny) return;
+    const int64_t i = (int64_t)r * nx + c;
+    A[i] = 0.0f;
+    if (count) count[i] = 0;
+    pending[i] = (code[i] != 0) ? __popc(child_mask(code, ny, nx, r, c)) : -1;
+}
+
+// One topological pass: a thread starts at every source cell (flow cell with
+// no children) and walks downstream for as long as it is the LAST child to
+// arrive at the next cell; each cell's value is pixel_area (stored fp32) plus
+// its children's final values in neighbour order k = 0..7, exactly the
+// reference's per-cell sum (d8_global.py:1223-1258), so the result does not
+// depend on the schedule.
+__global__ void __launch_bounds__(256)
+d8_area_walk_kernel(const uint8_t *__restrict__ code, int ny, int nx, double pixel_area,
+                    const double *__restrict__ pa_row, float *A, int64_t *count,
+                    int32_t *pending, unsigned long long *n_done) {
+    const int c0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r0 = blockIdx.y * blockDim.y + threadIdx.y;
+    if (c0 >= nx || r0 >= ny) return;
+    int r = r0, c = c0;
+    unsigned cd = code[(int64_t)r * nx + c];
+    if (cd == 0) return;
+    int cm = child_mask(code, ny, nx, r, c);
+    if (cm != 0) return;              // not a source
+    unsigned long long done = 0;
+    volatile float *Av = A;
+    volatile int64_t *Cv = count;
+    while (true) {
+        const int64_t i = (int64_t)r * nx + c;
+        float a = (float)(pa_row ? pa_row[r] : pixel_area);
+        int64_t n = 1;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (cm & (1 << k)) {
+                const int64_t j = i + (int64_t)kNbrDRow[k] * nx + kNbrDCol[k];
+                a += Av[j];
+                if (count) n += Cv[j];
+            }
+        }
+        Av[i] = a;
+        if (count) Cv[i] = n;
+        ++done;
+        int dr, dc;
+        code_offset(cd, dr, dc);
+        const int pr = r + dr, pc = c + dc;
+        if (pr < 0 || pr >= ny || pc < 0 || pc >= nx) break;
+        const int64_t ip = (int64_t)pr * nx + pc;
+        const unsigned pcd = code[ip];
+        if (pcd == 0) break;          // drains into a noflow cell: A stays 0 there
+        __threadfence();              // publish A[i] before announcing arrival
+        const int old = atomicSub(&pending[ip], 1);
+        if (old != 1) break;          // a sibling arrives later and continues
+        __threadfence();
+        r = pr; c = pc; cd = pcd;
+        cm = child_mask(code, ny, nx, r, c);
+    }
+    atomicAdd(n_done, done);
+}
+
+static dim3 grid2d(int ny, int nx, dim3 b) {
+    return dim3((nx + b.x - 1) / b.x, (ny + b.y - 1) / b.y);
+}
+
+}  // namespace tfb
+
+using namespace tfb;
+
+extern "C" int tfb_d8_resolve_table(uint8_t *out256) {
+    TFB_ARG_CHECK(out256 != nullptr);
+    memcpy(out256, kResolveHost, 256);
+    return TFB_OK;
+}
+
+extern "C" int tfb_d8_codes(const float *dem, int32_t ny, int32_t nx, int32_t halo,
+                            int32_t row0, int32_t ny_global, float dx, float dy, float dd,
+                            double nodata, int32_t link_flats, int16_t *code,
+                            void *stream) {
+    TFB_ARG_CHECK(dem && code && ny > 0 && nx > 0 && halo >= 0);
+    TFB_ARG_CHECK(row0 >= 0 && row0 + ny <= ny_global);
+    dim3 b(32, 8);
+    d8_codes_kernel<<<grid2d(ny, nx, b), b, 0, (cudaStream_t)stream>>>(
+        dem, ny, nx, halo, row0, ny_global, dx, dy, dd, nodata, link_flats, code);
+    TFB_CUDA_CHECK(cudaGetLastError());
+    return TFB_OK;
+}
+
+extern "C" int tfb_d8_break_ties(int16_t *code, int64_t n, void *stream) {
+    TFB_ARG_CHECK(code && n > 0);
+    int rc = ensure_resolve_uploaded();
+    if (rc) return rc;
+    d8_break_ties_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(code, n);
+    TFB_CUDA_CHECK(cudaGetLastError());
+    return TFB_OK;
+}
+
+extern "C" int tfb_d8_link_flats_sweep(const int16_t *code_in, int16_t *code_out,
+                                       int32_t ny, int32_t nx, int32_t halo, int32_t row0,
+                                       int32_t ny_global, int32_t *n_flats,
+                                       int32_t *n_fixed, void *stream) {
+    TFB_ARG_CHECK(code_in && code_out && code_in != code_out && n_flats && n_fixed);
+    TFB_ARG_CHECK(ny > 0 && nx > 0 && halo >= 0);
+    int rc = ensure_resolve_uploaded();
+    if (rc) return rc;
+    dim3 b(32, 8);
+    d8_link_flats_kernel<<<grid2d(ny, nx, b), b, 0, (cudaStream_t)stream>>>(
+        code_in, code_out, ny, nx, halo, row0, ny_global, n_flats, n_fixed);
+    TFB_CUDA_CHECK(cudaGetLastError());
+    return TFB_OK;
+}
+
+extern "C" int tfb_d8_link_flats(int16_t *code, int16_t *scratch, int32_t ny, int32_t nx,
+                                 int32_t max_reps, int32_t *n_reps, void *stream) {
+    TFB_ARG_CHECK(code && scratch && ny > 0 && nx > 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t *d_cnt = nullptr;
+    TFB_CUDA_CHECK(cudaMalloc(&d_cnt, 2 * sizeof(int32_t)));
+    int16_t *cur = code, *nxt = scratch;
+    int reps = 0, rc = TFB_OK;
+    while (true) {
+        ++reps;
+        int32_t h[2] = {0, 0};
+        cudaError_t e = cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int32_t), st);
+        if (e == cudaSuccess) {
+            rc = tfb_d8_link_flats_sweep(cur, nxt, ny, nx, 0, 0, ny, d_cnt, d_cnt + 1, stream);
+            if (rc) break;
+            e = cudaMemcpyAsync(h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost, st);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            set_error("tfb_d8_link_flats: %s", cudaGetErrorString(e));
+            rc = TFB_ERR_CUDA;
+            break;
+        }
+        if (h[0] == 0) break;               // no flats left (sweep was a copy)
+        int16_t *t = cur; cur = nxt; nxt = t;   // Jacobi: results live in `nxt`
+        if (h[1] == h[0] || h[1] == 0) break;   // all fixed, or none fixable
+        if (max_reps > 0 && reps >= max_reps) { rc = TFB_ERR_NOT_CONVERGED; break; }
+    }
+    if (rc == TFB_OK && cur != code) {
+        cudaError_t e = cudaMemcpyAsync(code, cur, (size_t)ny * nx * sizeof(int16_t),
+                                        cudaMemcpyDeviceToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_error("tfb_d8_link_flats: %s", cudaGetErrorString(e)); rc = TFB_ERR_CUDA; }
+    }
+    cudaFree(d_cnt);
+    if (n_reps) *n_reps = reps;
+    return rc;
+}
+
+extern "C" int tfb_d8_finalize_codes(const int16_t *code, uint8_t *code_u8, int64_t n,
+                                     void *stream) {
+    TFB_ARG_CHECK(code && code_u8 && n > 0);
+    d8_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(code, code_u8, n);
+    TFB_CUDA_CHECK(cudaGetLastError());
+    return TFB_OK;
+}
+
+extern "C" int tfb_d8_ds_dw(const uint8_t *code, const float *dx, const float *dy,
+                            const float *dd, int32_t ny, int32_t nx, float *ds, float *dw,
+                            void *stream) {
+    TFB_ARG_CHECK(code && dx && dy && dd && ny > 0 && nx > 0 && (ds || dw));
+    dim3 b(32, 8);
+    d8_ds_dw_kernel<<<grid2d(ny, nx, b), b, 0, (cudaStream_t)stream>>>(code, dx, dy, dd, ny, nx, ds, dw);
+    TFB_CUDA_CHECK(cudaGetLastError());
+    return TFB_OK;
+}
+
+extern "C" int tfb_d8_parent_ids(const uint8_t *code, int32_t ny, int32_t nx, int32_t *pid,
+                                 void *stream) {
+    TFB_ARG_CHECK(code && pid && ny > 0 && nx > 0);
+    TFB_ARG_CHECK((int64_t)ny * nx < 2147483647LL);
+    dim3 b(32, 8);
+    d8_parent_kernel<<<grid2d(ny, nx, b), b, 0, (cudaStream_t)stream>>>(code, ny, nx, pid);
+    TFB_CUDA_CHECK(cudaGetLastError());
+    return TFB_OK;
+}
+
+extern "C" int tfb_d8_slope(const float *dem, const uint8_t *code, const float *dx,
+                            const float *dy, const float *dd, int32_t ny, int32_t nx,
+                            float *S, void *stream) {
+    TFB_ARG_CHECK(dem && code && dx && dy && dd && S && ny > 0 && nx > 0);
+    dim3 b(32, 8);
+    d8_slope_kernel<<<grid2d(ny, nx, b), b, 0, (cudaStream_t)stream>>>(dem, code, dx, dy, dd, ny, nx, S);
+    TFB_CUDA_CHECK(cudaGetLastError());
+    return TFB_OK;
+}
+
+extern "C" int tfb_d8_area(const uint8_t *code, int32_t ny, int32_t nx, double pixel_area,
+                           const double *pixel_area_row, float *A, int64_t *count,
+                           int32_t *pending, int64_t *n_done, void *stream) {
+    TFB_ARG_CHECK(code && A && pending && ny > 0 && nx > 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long *d_done = nullptr;
+    TFB_CUDA_CHECK(cudaMalloc(&d_done, sizeof(unsigned long long)));
+    cudaError_t e = cudaMemsetAsync(d_done, 0, sizeof(unsigned long long), st);
+    dim3 b(32, 8);
+    if (e == cudaSuccess) {
+        d8_area_init_kernel<<<grid2d(ny, nx, b), b, 0, st>>>(code, ny, nx, A, count, pending);
+        d8_area_walk_kernel<<<grid2d(ny, nx, b), b, 0, st>>>(code, ny, nx, pixel_area,
+                                                            pixel_area_row, A, count,
+                                                            pending, d_done);
+        e = cudaGetLastError();
+    }
+    unsigned long long h = 0;
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(&h, d_done, sizeof(h), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_done);
+    if (e != cudaSuccess) {
+        set_error("tfb_d8_area: %s", cudaGetErrorString(e));
+        return TFB_ERR_CUDA;
+    }
+    if (n_done) *n_done = (int64_t)h;
+    return TFB_OK;
+}

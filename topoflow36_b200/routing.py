@@ -1,0 +1,344 @@
+"""Device-resident routing state + one-call-per-step driver of the fused kernel.
+
+``ChannelsEngine`` owns the torch CUDA tensors of one row slab (or the whole
+grid), fills a ``tfb_channels_step_args`` once, and advances the slab with
+``tfb_channels_step`` (libtfb_b200.so).  It is the layer between the BMI
+component (``channels_base.py`` in this package) and the C ABI; it has no
+numerical code of its own apart from the one-time initial volume
+(channels_base.py:1331-1336 in the reference).
+
+Layout: every per-cell tensor is allocated as (ny + 2*halo, nx) and the kernels
+get a pointer to the first OWNED row, so neighbour rows of an adjacent slab are
+ordinary memory.  ``halo = 0`` for a single GPU.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import lib as L
+
+_DIAG_NAMES = ('Rh', 'A_wet', 'P_wet', 'f', 'tau', 'u_star', 'froude')
+_SRC_SG = ('P_rain', 'SM', 'GW', 'MR', 'IN', 'ET', 'T_air', 'c0', 'T0', 'T_surf',
+           'Qn_SW', 'Qn_LW', 'Ks', 'Ki', 'qs', 'qi', 'G', 'h_table', 'elev')
+
+
+def _is_grid(x):
+    return (isinstance(x, (np.ndarray, torch.Tensor)) and x.ndim == 2)
+
+
+class ChannelsEngine(object):
+
+    def __init__(self, ny, nx, dt, code, dx, dy, dd, S_bed, width, angle,
+                 rough, tan_angle=None, cos_angle=None, sinu=1.0, da=900.0,
+                 d0=0.0, kinematic=True, manning=True, diag=False,
+                 write_R=False, outlet=(0, 0), rho_H2O=1000.0, row0=0,
+                 ny_global=None, halo=0, device=None, finalize=True,
+                 n_pixels_global=None):
+        if not torch.cuda.is_available():
+            raise L.TfbError('ChannelsEngine needs a CUDA device (no CPU path)')
+        self.lib = L.load()
+        self.device = torch.device(device if device is not None
+                                   else 'cuda:%d' % torch.cuda.current_device())
+        self.ny, self.nx, self.halo = int(ny), int(nx), int(halo)
+        self.row0 = int(row0)
+        self.ny_global = int(ny_global if ny_global is not None else ny)
+        self.kinematic, self.manning, self.diag = kinematic, manning, diag
+        self.dt = float(dt)
+        self._keep = []           # tensors referenced only through raw pointers
+        a = L.ChannelsStepArgs()
+        self.args = a
+        a.ny, a.nx, a.row0, a.ny_global = self.ny, self.nx, self.row0, self.ny_global
+        a.halo = self.halo
+        a.outlet_row, a.outlet_col = int(outlet[0]), int(outlet[1])
+        a.dt = self.dt
+        a.rho_H2O = float(rho_H2O)
+        a.n_pixels_global = int(n_pixels_global if n_pixels_global is not None
+                                else self.ny_global * self.nx)
+        a.finalize = 1 if finalize else 0
+        flags = 0
+        if not kinematic:
+            flags |= L.CH_DIFFUSIVE
+        if not manning:
+            flags |= L.CH_LAW_OF_WALL
+        if diag:
+            flags |= L.CH_DIAG
+        if write_R:
+            flags |= L.CH_WRITE_R
+        self.flags = flags
+        # ---- static inputs --------------------------------------------------
+        self.code = self._grid(code, torch.uint8)
+        a.code = self._p(self.code)
+        self.dx = self._rows(dx, torch.float32)
+        self.dy = self._rows(dy, torch.float32)
+        self.dd = self._rows(dd, torch.float32)
+        a.dx, a.dy, a.dd = self._prow(self.dx), self._prow(self.dy), self._prow(self.dd)
+        self.S_bed = self._grid(S_bed, torch.float64)
+        a.S_bed = self._p(self.S_bed)
+        # tan / cos of the bank angle come from numpy on the host when the
+        # angle is handed over as numpy (bit-identical to the reference's
+        # np.tan / np.cos); torch inputs are evaluated on the device.
+        if tan_angle is None:
+            tan_angle = np.tan(angle) if not isinstance(angle, torch.Tensor) else torch.tan(angle)
+        if cos_angle is None:
+            cos_angle = np.cos(angle) if not isinstance(angle, torch.Tensor) else torch.cos(angle)
+        for name, val in (('sinu', sinu), ('width', width), ('angle', angle),
+                          ('tan_angle', tan_angle), ('cos_angle', cos_angle),
+                          ('rough', rough)):
+            setattr(a, name, self._sg(name, val))
+        if isinstance(da, (np.ndarray, torch.Tensor)) and np.ndim(da) >= 1:
+            da_rows = da[:, 0] if np.ndim(da) == 2 else da
+            self.da_rows = self._rows(da_rows, torch.float64)
+            a.da = L.SG(self._prow(self.da_rows), 0.0)
+            self._da_is_grid = True
+        else:
+            a.da = L.SG(None, float(da))
+            self._da_is_grid = False
+        # ---- state ---------------------------------------------------------
+        z = lambda: self._zeros(torch.float64)
+        self.vol_buf = [z(), z() if not kinematic else None]
+        self.Q_buf = [z(), z()]
+        self.qcur = 0             # Q buffer the NEXT step reads
+        self.scur = 0             # state buffer (vol, I, h_swe) the next step reads
+        self.d, self.u = z(), z()
+        a.d, a.u = self._p(self.d), self._p(self.u)
+        if diag:
+            for n in _DIAG_NAMES:
+                t = z()
+                setattr(self, n, t)
+                setattr(a, n, self._p(t))
+            if not kinematic:
+                self.S_free = z()
+                self.own(self.S_free).copy_(self.own(self.S_bed))
+                a.S_free = self._p(self.S_free)
+        if write_R:
+            self.R = z()
+            a.R = self._p(self.R)
+        # ---- sources default to scalar zeros --------------------------------
+        self.src = {}
+        for n in _SRC_SG:
+            self.set_input(n, 0.0)
+        self.h_swe_buf = self.I_buf = None
+        self.h_snow = None
+        # ---- reductions ----------------------------------------------------
+        self.scalars_dev = torch.zeros(C.sizeof(L.ChannelsScalars), dtype=torch.uint8,
+                                       device=self.device)
+        npart = self.lib.tfb_channels_partials_len(self.ny, self.nx)
+        self.partials = torch.zeros(npart, dtype=torch.float64, device=self.device)
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=self.device)
+        a.scalars = self.scalars_dev.data_ptr()
+        a.partials = self.partials.data_ptr()
+        a.ticket = self.ticket.data_ptr()
+        self._scalars_host = torch.zeros(C.sizeof(L.ChannelsScalars), dtype=torch.uint8).pin_memory()
+        self.set_initial_depth(d0)
+        self.n_steps = 0
+
+    # ------------------------------------------------------------ allocation
+    def _zeros(self, dtype):
+        return torch.zeros((self.ny + 2 * self.halo, self.nx), dtype=dtype, device=self.device)
+
+    def own(self, t):
+        """(ny, nx) view of the rows this slab owns."""
+        return t[self.halo:self.halo + self.ny]
+
+    def _p(self, t):
+        return t.data_ptr() + self.halo * self.nx * t.element_size()
+
+    def _prow(self, t):
+        return t.data_ptr() + self.halo * t.element_size()
+
+    def _grid(self, x, dtype):
+        """Upload an (ny, nx) or (ny+2h, nx) array into a haloed tensor."""
+        full = self._zeros(dtype)
+        src = torch.as_tensor(x) if not isinstance(x, torch.Tensor) else x
+        src = src.to(dtype=dtype, device=self.device)
+        if src.shape[0] == self.ny + 2 * self.halo:
+            full.copy_(src)
+        else:
+            if tuple(src.shape) != (self.ny, self.nx):
+                raise L.TfbError('grid shape %s != (%d, %d)' % (tuple(src.shape), self.ny, self.nx))
+            self.own(full).copy_(src)
+        return full
+
+    def _rows(self, x, dtype):
+        src = torch.as_tensor(np.asarray(x)) if not isinstance(x, torch.Tensor) else x
+        src = src.to(dtype=dtype, device=self.device).reshape(-1)
+        full = torch.zeros(self.ny + 2 * self.halo, dtype=dtype, device=self.device)
+        if src.numel() == 1:
+            full.fill_(float(src))
+        elif src.numel() == self.ny + 2 * self.halo:
+            full.copy_(src)
+        else:
+            full[self.halo:self.halo + self.ny].copy_(src)
+            if self.halo:
+                full[:self.halo] = src[0]
+                full[self.halo + self.ny:] = src[-1]
+        return full
+
+    def _sg(self, name, val):
+        if _is_grid(val):
+            t = self._grid(val, torch.float64)
+            setattr(self, name + '_grid', t)
+            return L.SG(self._p(t), 0.0)
+        setattr(self, name + '_grid', None)
+        return L.SG(None, float(val))
+
+    # ---------------------------------------------------------------- inputs
+    def set_input(self, name, val):
+        """Bind a source-term input: python/0-D scalar, numpy grid (uploaded) or
+        CUDA tensor (used in place when it already has the slab's layout)."""
+        if name not in _SRC_SG:
+            raise KeyError(name)
+        if _is_grid(val):
+            if (isinstance(val, torch.Tensor) and val.is_cuda and val.dtype == torch.float64
+                    and val.is_contiguous() and self.halo == 0
+                    and tuple(val.shape) == (self.ny, self.nx)):
+                t = val
+                sgv = L.SG(t.data_ptr(), 0.0)
+            else:
+                t = self.src.get(name)
+                if (not isinstance(t, torch.Tensor)
+                        or t.shape[0] != self.ny + 2 * self.halo):
+                    t = self._zeros(torch.float64)
+                src = torch.as_tensor(val) if not isinstance(val, torch.Tensor) else val
+                src = src.to(dtype=torch.float64, device=self.device)
+                (t if src.shape[0] == t.shape[0] else self.own(t)).copy_(src)
+                sgv = L.SG(self._p(t), 0.0)
+            self.src[name] = t
+        else:
+            v = float(val) if not isinstance(val, torch.Tensor) else float(val.item())
+            self.src[name] = v
+            sgv = L.SG(None, v)
+        setattr(self.args, name, sgv)
+        if name == 'ET':
+            self.args.ET_rw = sgv.ptr
+
+    def enable_fused_sources(self, met=False, snow=False, evap=False, infil=False,
+                             T_rain_snow=0.0, rho_snow=300.0, alpha=1.26,
+                             K_soil=0.45, soil_x=0.05, T_soil_x=0.0,
+                             h0_swe=0.0, I0=1e-6, use_table=False):
+        """Evaluate the met/snow/evap/infil source terms inside the routing
+        kernel (TFB_CH_SRC_* flags) instead of taking them as inputs."""
+        a = self.args
+        f = self.flags & ~(L.CH_SRC_MET | L.CH_SRC_SNOW | L.CH_SRC_EVAP | L.CH_SRC_INFIL)
+        dbl = not self.kinematic
+        if met:
+            f |= L.CH_SRC_MET
+            a.T_rain_snow = float(T_rain_snow)
+        if snow:
+            f |= L.CH_SRC_SNOW
+            a.rho_snow = float(rho_snow)
+            self.h_swe_buf = [self._grid_or_fill(h0_swe), self._zeros(torch.float64) if dbl else None]
+            self.h_snow = self._zeros(torch.float64)
+            self.own(self.h_snow).copy_(self.own(self.h_swe_buf[0]) * (a.rho_H2O / a.rho_snow))
+            a.h_snow = self._p(self.h_snow)
+        if evap:
+            f |= L.CH_SRC_EVAP
+            a.alpha, a.K_soil = float(alpha), float(K_soil)
+            a.soil_x, a.T_soil_x = float(soil_x), float(T_soil_x)
+        if infil:
+            f |= L.CH_SRC_INFIL
+            self.I_buf = [self._grid_or_fill(I0), self._zeros(torch.float64) if dbl else None]
+            if not use_table:
+                a.h_table = L.SG(None, 0.0)
+                a.elev = L.SG(None, 1.0)
+        self.flags = f
+
+    def _grid_or_fill(self, v):
+        if _is_grid(v):
+            return self._grid(v, torch.float64)
+        t = self._zeros(torch.float64)
+        self.own(t).fill_(float(v))
+        return t
+
+    def set_initial_depth(self, d0):
+        """d = d0; vol = A_wet(d0) * ds   (channels_base.py:1262-1265, :1331-1336)."""
+        a = self.args
+        d = self.own(self.d)
+        if _is_grid(d0):
+            d.copy_(torch.as_tensor(d0).to(device=self.device, dtype=torch.float64))
+        else:
+            d.fill_(float(d0))
+        vol = self.own(self._sbuf(self.vol_buf))
+        if float(d.abs().max()) == 0.0:
+            vol.zero_()
+            return
+        def g(name):
+            t = getattr(self, name + '_grid')
+            return self.own(t) if t is not None else getattr(a, name).val
+        ds32 = torch.empty((self.ny + 2 * self.halo, self.nx), dtype=torch.float32,
+                           device=self.device)
+        L.check(self.lib.tfb_d8_ds_dw(self.code.data_ptr(), self.dx.data_ptr(),
+                                      self.dy.data_ptr(), self.dd.data_ptr(),
+                                      self.ny + 2 * self.halo, self.nx,
+                                      ds32.data_ptr(), None, L.stream_ptr()), 'tfb_d8_ds_dw')
+        ds = g('sinu') * self.own(ds32).double()
+        L2 = d * g('tan_angle')
+        A_wet = d * (g('width') + L2)
+        vol.copy_(A_wet * ds)
+
+    # ------------------------------------------------------------------ step
+    # Q is always double-buffered (neighbours read the old Q while the new one
+    # is written); vol / I / h_swe only for the diffusive wave, where the
+    # parent's new depth is re-derived from its pre-step state.
+    def _sbuf(self, buf):
+        return buf[self.scur if buf[1] is not None else 0]
+
+    @property
+    def vol(self):
+        return self.own(self._sbuf(self.vol_buf))
+
+    @property
+    def I(self):
+        return self.own(self._sbuf(self.I_buf))
+
+    @property
+    def h_swe(self):
+        return self.own(self._sbuf(self.h_swe_buf))
+
+    @property
+    def Q(self):
+        """Discharge the LAST step used (= what the reference exposes as Q)."""
+        return self.own(self.Q_buf[self.qcur ^ 1] if self.n_steps else self.Q_buf[self.qcur])
+
+    @property
+    def Q_next(self):
+        """u * A_wet after the last step: the next step's discharge."""
+        return self.own(self.Q_buf[self.qcur])
+
+    def is_R_grid(self):
+        if self._da_is_grid or (self.flags & 0xF00):
+            return True
+        for n in ('P_rain', 'SM', 'GW', 'MR', 'IN', 'ET'):
+            if isinstance(self.src[n], torch.Tensor):
+                return True
+        return False
+
+    def step(self, time_min=0.0):
+        a = self.args
+        a.flags = self.flags | (L.CH_ET_INPLACE if a.ET.ptr else 0)
+        a.time_min = float(time_min)
+        a.is_R_grid = 1 if self.is_R_grid() else 0
+        a.Q_in = self._p(self.Q_buf[self.qcur])
+        a.Q_out = self._p(self.Q_buf[self.qcur ^ 1])
+        for name, buf in (('vol', self.vol_buf), ('h_swe', self.h_swe_buf),
+                          ('I', self.I_buf)):
+            if buf is None:
+                continue
+            dbl = buf[1] is not None
+            setattr(a, name, self._p(buf[self.scur if dbl else 0]))
+            setattr(a, name + '_out', self._p(buf[self.scur ^ 1 if dbl else 0]))
+        L.check(self.lib.tfb_channels_step(C.byref(a), L.stream_ptr()), 'tfb_channels_step')
+        self.qcur ^= 1
+        self.scur ^= 1
+        self.n_steps += 1
+
+    def read_scalars(self):
+        """One D2H of the scalar block (synchronises the stream)."""
+        self._scalars_host.copy_(self.scalars_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return L.ChannelsScalars.from_buffer_copy(self._scalars_host.numpy().tobytes())
+
+    def write_scalars(self, s):
+        raw = torch.frombuffer(bytearray(bytes(s)), dtype=torch.uint8)
+        self.scalars_dev.copy_(raw)
