@@ -172,15 +172,19 @@ typedef struct {
                                  EVERY grid pointer (0, or >=1 KW / >=2 DW for a
                                  slab with neighbours); rows beyond that read as
                                  code 0 / Q 0                                   */
-    const uint8_t *code;      /* D8 codes (ny, nx)                              */
+    const uint16_t *geo;      /* packed per-cell word from tfb_channels_pack_geo:
+                                 low byte D8 code, high byte child mask          */
     const float *dx, *dy, *dd;        /* per-row pixel sizes (ny), float32       */
     tfb_sg sinu;              /* ds = sinu * ds_d8  (channels_base :1242)       */
     tfb_sg da;                /* pixel area [m2]; ptr = per-ROW array (ny)      */
-    const double *S_bed;      /* bed slope (already / sinu, bad slopes fixed)   */
+    const double *S_bed;      /* bed slope (already / sinu, bad slopes fixed);
+                                 needed for DIFFUSIVE, LAW_OF_WALL or DIAG      */
+    const double *sqrtS;      /* sqrt(|S_bed|) evaluated on the host: the only
+                                 use of S_bed in the lean kinematic Manning step */
     tfb_sg width;             /* trapezoid bottom width                         */
     tfb_sg tan_angle;         /* tan / cos of the bank angle, evaluated on the  */
-    tfb_sg cos_angle;         /*   host by numpy at initialize()                */
-    tfb_sg angle;             /* radians; only its ==0 test is used             */
+    tfb_sg cos_angle;         /*   host by numpy at initialize(); the reference's
+                                 angle == 0 test is tan_angle == 0              */
     tfb_sg rough;             /* Manning n  or  z0 (law of the wall)            */
     /* ---- state --------------------------------------------------------- */
     const double *vol;        /* in: water volume per cell before the step      */
@@ -212,12 +216,12 @@ typedef struct {
     tfb_channels_scalars *scalars;   /* DEVICE                                  */
     double *partials;         /* DEVICE scratch, >= tfb_channels_partials_len()
                                  doubles, zero-initialised once by the caller;
-                                 with finalize == 0 the per-rank sums are left
-                                 in its LAST TFB_NSUM doubles                   */
+                                 after a step its FIRST TFB_NSUM doubles hold
+                                 this rank's sums                               */
     uint32_t *ticket;         /* DEVICE scratch, 1 word, zero-initialised       */
     int32_t finalize;         /* 1: last block folds partials into `scalars`
-                                 (single GPU); 0: leave per-rank sums in
-                                 the tail of `partials` for an allreduce, then
+                                 (single GPU); 0: only leave the per-rank sums
+                                 in partials[0..TFB_NSUM) for an allreduce, then
                                  call tfb_channels_fold()                       */
 } tfb_channels_step_args;
 
@@ -233,6 +237,14 @@ int64_t tfb_sizeof_channels_scalars(void);
 
 /* number of doubles `partials` must hold for a (ny, nx) slab */
 int64_t tfb_channels_partials_len(int32_t ny, int32_t nx);
+
+/* geo word of every cell of a slab INCLUDING its halo rows: code | mask << 8,
+ * mask bit k set <=> the neighbour that would drain into the cell with code
+ * 1<<k has that code (the per-direction w_k / p_k lists of
+ * d8_global.update_flow_from_IDs :723-764 / update_flow_to_IDs :766-841 as a
+ * parent-side gather mask).  `code` / `geo` point at the first owned row. */
+int tfb_channels_pack_geo(const uint8_t *code, int32_t ny, int32_t nx,
+                          int32_t halo, uint16_t *geo, void *stream);
 
 /* one routing step of the slab */
 int tfb_channels_step(const tfb_channels_step_args *a, void *stream);

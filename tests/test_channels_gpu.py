@@ -134,7 +134,7 @@ def test_lean_mode_equals_diag_mode(synth_channels):
         assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize('shape', [(1, 1), (3, 3), (2, 70), (70, 2), (33, 257)])
+@pytest.mark.parametrize('shape', [(1, 5), (3, 3), (2, 70), (70, 2), (33, 257)])
 def test_ragged_and_tiny_grids(shape):
     """Edge shapes: smaller than a tile, single row/column, non-multiples of the
     tile; all-border grids have code 0 everywhere (pure edge bookkeeping)."""

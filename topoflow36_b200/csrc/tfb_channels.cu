@@ -12,14 +12,23 @@
 // and, when the TFB_CH_SRC_* flags are set, the per-cell source terms of the
 // met / snow / evap / infil components evaluated just before it.
 //
-// The reference's D8 inflow SCATTER (vol[p_k] += dt*Q[w_k], k = 1..8) is done
-// as a deterministic parent-side GATHER in the same order (child at SW, W, NW,
-// N, NE, E, SE, S), which is bit-identical.
+// D8 inflow: the reference SCATTERS (vol[p_k] += dt*Q[w_k], k = 1..8).  Here each
+// cell GATHERS from its children in the same order (child at SW, W, NW, N, NE,
+// E, SE, S = codes 1, 2, 4, ..., 128), which is bit-identical.
+// Which neighbours are children is precomputed once into a per-cell bit mask
+// (tfb_channels_pack_geo), so the hot loop does 1 two-byte load instead of 8
+// neighbour-code loads and compares.
 //
-// Arithmetic is fp64 with the reference's operation order; the TU is compiled
-// with -fmad=false so that a*b+c is rounded twice exactly as numpy does.
-// Only x**(2/3), x**(1/3) and log() go through CUDA's libdevice (cbrt / log,
-// <= 1-2 ulp from numpy's), everything else (+ - * / sqrt) is IEEE-exact.
+// Mapping: a thread owns VEC (=2 when nx is even) adjacent cells of a row and
+// moves them with 128-bit loads/stores; a warp covers 64 columns of one row, a
+// CTA 8 rows; the grid is persistent (a multiple of the SM count) and strides
+// over 64 x 64 tiles, so neighbour rows are L1/L2 hits and only one row of
+// block partials per CTA reaches the deterministic last-block fold.
+//
+// Arithmetic is fp64 in the reference's operation order; the TU is compiled
+// with -fmad=false so a*b+c rounds twice exactly as numpy does.  Only
+// x**(2/3), x**(1/3) and log() go through libdevice (cbrt / log, <= 2 ulp from
+// numpy's pow/log); + - * / sqrt are IEEE-exact.
 #include "tfb_common.cuh"
 
 namespace tfb {
@@ -28,36 +37,69 @@ struct ChConsts {
     double g, aval, kappa, law_const;
 };
 
-// per-thread reduction slots
+// reduction slots ------------------------------------------------------------
 enum {
     S_VOL_R = 0, S_VOL_EDGE, S_VOL_P, S_VOL_PR, S_VOL_PS, S_VOL_SM, S_VOL_ET,
     S_VOL_IN, S_NNEG_D, S_NNAN_D, S_NINF_D, S_NNEG_U, S_NNAN_U, S_NINF_U,
-    S_NNAN_IN, S_NSLOT   // = 15 sums; slot 15 of TFB_NSUM carries outlet flag
+    S_NNAN_IN, S_NSLOT   // = 15
 };
+constexpr int kNSum = 8;        // fp64 sums  (slots 0..7)
+constexpr int kNCnt = 7;        // counters   (slots 8..14)
 constexpr int kPartialStride = 24;
-static_assert(kPartialStride == TFB_NSUM, "TFB_NSUM must equal the partial stride");   // 16 sums + dt_min + 4 outlet + pad
-constexpr int P_DTMIN = 16, P_QOUT = 17, P_UOUT = 18, P_DOUT = 19, P_FOUT = 20,
-              P_HASOUT = 21;
+static_assert(kPartialStride == TFB_NSUM, "TFB_NSUM must equal the partial stride");
+constexpr int P_HASOUT_SUM = 15, P_DTMIN = 16, P_QOUT = 17, P_UOUT = 18, P_DOUT = 19,
+              P_FOUT = 20, P_HASOUT = 21;
 
 struct Acc {
-    double s[S_NSLOT];
+    double s[kNSum];
+    unsigned n[kNCnt];
     float dt_min;
 };
 
-__device__ __forceinline__ unsigned code_at(const tfb_channels_step_args &a, int r, int c) {
-    if (c < 0 || c >= a.nx || r < -a.halo || r >= a.ny + a.halo) return 0u;
-    return a.code[(int64_t)r * a.nx + c];
+// child position for mask bit k (= child's code 1<<k): opposite of direction k
+__device__ __constant__ const int8_t kChildDR[8] = {1, 0, -1, -1, -1, 0, 1, 1};
+__device__ __constant__ const int8_t kChildDC[8] = {-1, -1, -1, 0, 1, 1, 1, 0};
+
+// ---------------------------------------------------------------------------
+// geo word: low byte = D8 code, high byte = child mask (bit k set <=> the
+// neighbour at the child position of code 1<<k has exactly that code)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_geo_kernel(const uint8_t *__restrict__ code, int ny, int nx, int halo,
+                uint16_t *__restrict__ geo) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = (int)(blockIdx.y * blockDim.y + threadIdx.y) - halo;
+    if (c >= nx || r >= ny + halo) return;
+    const int64_t i = (int64_t)r * nx + c;
+    unsigned m = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int rr = r + kChildDR[k], cc = c + kChildDC[k];
+        if (cc < 0 || cc >= nx || rr < -halo || rr >= ny + halo) continue;
+        if (code[(int64_t)rr * nx + cc] == (uint8_t)(1u << k)) m |= (1u << k);
+    }
+    geo[i] = (uint16_t)(code[i] | (m << 8));
 }
 
-// source terms of one cell ---------------------------------------------------
+// ---------------------------------------------------------------------------
+// per-cell inputs
+// ---------------------------------------------------------------------------
+struct Cell {
+    unsigned code, cmask;
+    double ds, da, width, tan_a, cos_a;
+    double vol, Q;
+};
+
 struct Src {
     double P_rain, SM, GW, MR, ET, IN;
     bool ET_is_grid;
 };
 
+// source terms of one cell; COMMIT=false is the diffusive wave re-deriving its
+// parent's inflow (no state update, no integrals)
 template <bool SRC, bool COMMIT>
-__device__ __forceinline__ void eval_sources(const tfb_channels_step_args &a, int r,
-                                             int64_t i, double da, Src &s, Acc *acc) {
+__device__ __forceinline__ void eval_sources(const tfb_channels_step_args &a, int64_t i,
+                                             double da, Src &s, Acc *acc) {
     const double dt = a.dt;
     s.GW = sg_at(a.GW, i);
     s.MR = sg_at(a.MR, i);
@@ -133,77 +175,63 @@ __device__ __forceinline__ void eval_sources(const tfb_channels_step_args &a, in
         if (COMMIT) {
             a.I_out[i] = Iv + (IN * dt);
             acc->s[S_VOL_IN] += (IN * da) * dt;
-            if (!isfinite(IN)) acc->s[S_NNAN_IN] += 1.0;
+            if (!isfinite(IN)) acc->n[S_NNAN_IN - kNSum] += 1u;
         }
     } else {
         s.IN = sg_at(a.IN, i);
     }
-    (void)r;
 }
 
-// static geometry of one cell --------------------------------------------------
-struct Geo {
-    unsigned code;
-    double ds, da, width, tan_a, cos_a, angle;
-};
-
-__device__ __forceinline__ void load_geo(const tfb_channels_step_args &a, int r, int c,
-                                         int64_t i, Geo &g) {
-    g.code = a.code[i];
+__device__ __forceinline__ void load_cell_scalar(const tfb_channels_step_args &a, int r,
+                                                 int64_t i, Cell &g) {
+    const unsigned w = a.geo[i];
+    g.code = w & 0xffu;
+    g.cmask = w >> 8;
     const float ds32 = ds_of(g.code, __ldg(a.dx + r), __ldg(a.dy + r), __ldg(a.dd + r));
     g.ds = sg_at(a.sinu, i) * (double)ds32;                      // channels_base :1242
     g.da = a.da.ptr ? __ldg(a.da.ptr + r) : a.da.val;
     g.width = sg_at(a.width, i);
     g.tan_a = sg_at(a.tan_angle, i);
     g.cos_a = sg_at(a.cos_angle, i);
-    g.angle = sg_at(a.angle, i);
-    (void)c;
+    g.vol = __ldg(a.vol + i);
+    g.Q = __ldg(a.Q_in + i);
 }
 
-// new volume (before the noflow zeroing) and new depth of cell (r, c) ----------
+// new volume (before the noflow zeroing) and new depth of a cell ---------------
 template <bool SRC, bool COMMIT>
-__device__ __forceinline__ void vol_depth(const tfb_channels_step_args &a, int r, int c,
-                                          int64_t i, const Geo &g, double vol_old,
-                                          double Q_own, double &vol_new, double &d_new,
-                                          double &R_out, Acc *acc) {
+__device__ __forceinline__ void vol_depth(const tfb_channels_step_args &a, int64_t i,
+                                          const Cell &g, const double *__restrict__ Qc,
+                                          double &vol_new, double &d_new, double &R_out,
+                                          Acc *acc) {
     const double dt = a.dt;
     Src s;
-    eval_sources<SRC, COMMIT>(a, r, i, g.da, s, acc);
+    eval_sources<SRC, COMMIT>(a, i, g.da, s, acc);
     // update_R :1625-1649
     double ET = s.ET;
     if (s.ET_is_grid) {
-        if (vol_old < ((ET * g.da) * dt)) {
+        if (g.vol < ((ET * g.da) * dt)) {
             ET = 0.0;
             if (COMMIT && (a.flags & TFB_CH_ET_INPLACE) && a.ET_rw) a.ET_rw[i] = 0.0;
         }
     } else {
-        ET = 0.0;                       // reference: scalar ET is dropped (:1629)
+        ET = 0.0;                       // reference: a scalar ET is dropped (:1629)
     }
     const double R = (((s.P_rain + s.SM) + s.GW) + s.MR) - (ET + s.IN);
     R_out = R;
     if (COMMIT && a.is_R_grid) acc->s[S_VOL_R] += (R * g.da) * dt;   // :1666-1670
-    // update_flow_volume :2086
-    double v = vol_old + ((R * g.da) * dt);
-    // parent-side gather, children in reference order (codes 1,2,4,...,128):
-    // a child with code g_k sits at the OPPOSITE neighbour position.
-    //   code 1 (NE) -> child at SW (r+1,c-1);  2 (E) -> W (r,c-1);
-    //   4 (SE) -> NW (r-1,c-1);  8 (S) -> N (r-1,c);  16 (SW) -> NE (r-1,c+1);
-    //   32 (W) -> E (r,c+1);  64 (NW) -> SE (r+1,c+1);  128 (N) -> S (r+1,c)
-    const int cdr[8] = {1, 0, -1, -1, -1, 0, 1, 1};
-    const int cdc[8] = {-1, -1, -1, 0, 1, 1, 1, 0};
+    double v = g.vol + ((R * g.da) * dt);                            // :2086
+    // children in the reference's order (codes 1,2,4,...,128) :2116-2131;
+    // Qc[k] is the child's discharge, meaningful only where the mask bit is set
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const int rr = r + cdr[k], cc = c + cdc[k];
-        if (code_at(a, rr, cc) == (1u << k)) {
-            v += dt * __ldg(a.Q_in + ((int64_t)rr * a.nx + cc));   // :2116-2131
-        }
+        if (g.cmask & (1u << k)) v += dt * Qc[k];
     }
-    v -= (Q_own * dt);                                             // :2138
-    v = np_max(v, 0.0);                                            // :2145
+    v -= (g.Q * dt);                                                 // :2138
+    v = np_max(v, 0.0);                                              // :2145
     vol_new = v;
-    // update_channel_depth :2299-2330, :2379
+    // update_channel_depth :2299-2330, :2379  (angle == 0  <=>  tan(angle) == 0)
     double d;
-    if (g.angle == 0.0) {
+    if (g.tan_a == 0.0) {
         d = v / (g.width * g.ds);
     } else {
         const double denom = 2.0 * g.tan_a;
@@ -214,16 +242,28 @@ __device__ __forceinline__ void vol_depth(const tfb_channels_step_args &a, int r
     d_new = np_max(d, 0.0);
 }
 
+// predicated loads of the children's discharge
+__device__ __forceinline__ void load_children(const double *__restrict__ Qp, int nx,
+                                              unsigned cmask, double *Qc) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        Qc[k] = 0.0;
+        if (cmask & (1u << k)) Qc[k] = __ldg(Qp + (kChildDR[k] * nx + kChildDC[k]));
+    }
+}
+
+struct CellOut {
+    double vol, d, u, Qn;
+    double Rh, A_wet, P_wet, f, tau, u_star, froude, S, R;
+};
+
+// everything after the depth: Rh, slope, velocity, diagnostics, bookkeeping
 template <bool DW, bool LOW, bool DIAG, bool SRC>
-__device__ __forceinline__ void route_cell(const tfb_channels_step_args &a,
-                                           const ChConsts &k, int r, int c, Acc &acc) {
-    const int64_t i = (int64_t)r * a.nx + c;
-    Geo g;
-    load_geo(a, r, c, i, g);
-    const double vol_old = __ldg(a.vol + i);
-    const double Q_own = __ldg(a.Q_in + i);
-    double v, d, R;
-    vol_depth<SRC, true>(a, r, c, i, g, vol_old, Q_own, v, d, R, &acc);
+__device__ __forceinline__ void finish_cell(const tfb_channels_step_args &a,
+                                            const ChConsts &k, int r, int c, int64_t i,
+                                            const Cell &g, double v, double d,
+                                            double slope_in, double rough, Acc &acc,
+                                            CellOut &o) {
     const bool noflow = (g.code == 0);
     // update_trapezoid_Rh :2668-2703
     const double L2 = d * g.tan_a;
@@ -232,40 +272,38 @@ __device__ __forceinline__ void route_cell(const tfb_channels_step_args &a,
     if (noflow) P_wet = 1.0;
     double Rh = A_wet / P_wet;
     if (noflow) Rh = 0.0;
-    // slope: bed (kinematic) or free surface (diffusive) :2583-2618
-    const double S_bed = __ldg(a.S_bed + i);
-    double S = S_bed;
+    // slope_in: sqrt(|S_bed|) precomputed on the host for the lean kinematic
+    // Manning case, S_bed otherwise (diffusive, law of the wall, DIAG)
+    double S = slope_in, sqrtS;
     if (DW) {
-        // depth of the D8 parent AFTER this step's volume update, before the
-        // noflow zeroing; noflow cells point at cell (0, 0) of the global grid
+        // depth of the D8 parent AFTER this step's volume update and before the
+        // noflow zeroing (:2606-2607); noflow cells point at global cell (0, 0)
         int dr, dc;
         code_offset(g.code, dr, dc);
         int pr = r + dr, pc = c + dc;
-        double d_par;
         if (noflow) { pr = -a.row0; pc = 0; }
-        const bool have = (pr >= -a.halo && pr < a.ny + a.halo);
-        if (have) {
+        double d_par = 0.0;
+        if (pr >= -a.halo && pr < a.ny + a.halo) {
             const int64_t ip = (int64_t)pr * a.nx + pc;
-            Geo gp;
-            load_geo(a, pr, pc, ip, gp);
-            double vp, Rp;
-            vol_depth<SRC, false>(a, pr, pc, ip, gp, __ldg(a.vol + ip), __ldg(a.Q_in + ip), vp,
-                                  d_par, Rp, nullptr);
-        } else {
-            d_par = 0.0;   // only reachable for noflow cells of a slab that does
-                           // not hold global cell (0,0): diagnostics only
+            Cell gp;
+            load_cell_scalar(a, pr, ip, gp);
+            double Qc[8], vp, Rp;
+            load_children(a.Q_in + ip, a.nx, gp.cmask, Qc);
+            vol_depth<SRC, false>(a, ip, gp, Qc, vp, d_par, Rp, nullptr);
         }
-        S = S_bed + ((d - d_par) / g.ds);
+        S = slope_in + ((d - d_par) / g.ds);
+        sqrtS = sqrt(fabs(S));
+    } else {
+        sqrtS = (DIAG || LOW) ? (LOW ? 0.0 : sqrt(fabs(slope_in))) : slope_in;
     }
-    const double S2 = fabs(S);
-    const double rough = sg_at(a.rough, i);
     // velocity: kinematic_wave.py:84-127 -> :3960-4003 / :4005-4063
     double u, smooth = 0.0;
     if (!LOW) {
         const double cb = cbrt(Rh);
-        u = ((cb * cb) * sqrt(S2)) / rough;
+        u = ((cb * cb) * sqrtS) / rough;
     } else {
         smooth = np_max((k.aval / rough) * d, 1.1);
+        const double S2 = DW ? fabs(S) : fabs(slope_in);
         u = (k.law_const * sqrt(Rh * S2)) * log(smooth);
     }
     if (noflow) u = 0.0;                                            // :2862
@@ -276,13 +314,13 @@ __device__ __forceinline__ void route_cell(const tfb_channels_step_args &a,
             if (!LOW) f_o = k.g * ((rough * rough) / cbrt(d));
             else { const double q = k.kappa / log(smooth); f_o = q * q; }
         }
-        double *p = a.partials + (int64_t)gridDim.x * gridDim.y * kPartialStride;
-        p[P_QOUT] = Q_own; p[P_UOUT] = u; p[P_DOUT] = d; p[P_FOUT] = f_o;
+        double *p = a.partials + kPartialStride;          // row 1: outlet staging
+        p[P_QOUT] = g.Q; p[P_UOUT] = u; p[P_DOUT] = d; p[P_FOUT] = f_o;
         p[P_HASOUT] = 1.0;
     }
     if (DIAG) {
         // :2620-2641, :2714-2788, :2867-2880 (all with the pre-zero depth)
-        const double slope_t = DW ? S2 : S_bed;
+        const double slope_t = DW ? fabs(S) : slope_in;
         const double tau = ((a.rho_H2O * k.g) * d) * slope_t;
         double f = 0.0, fr = 0.0;
         if (d > 0.0) {
@@ -290,12 +328,9 @@ __device__ __forceinline__ void route_cell(const tfb_channels_step_args &a,
             else { const double q = k.kappa / log(smooth); f = q * q; }
             fr = u / sqrt(k.g * d);
         }
-        a.Rh[i] = Rh; a.A_wet[i] = A_wet; a.P_wet[i] = P_wet;
-        a.f[i] = f; a.tau[i] = tau; a.u_star[i] = sqrt(tau / a.rho_H2O);
-        a.froude[i] = fr;
-        if (DW && a.S_free) a.S_free[i] = S;
+        o.Rh = Rh; o.A_wet = A_wet; o.P_wet = P_wet; o.f = f; o.tau = tau;
+        o.u_star = sqrt(tau / a.rho_H2O); o.froude = fr; o.S = S;
     }
-    if ((a.flags & TFB_CH_WRITE_R) && a.R) a.R[i] = R;
     // update_edge_values :2960-2966
     if (noflow) {
         acc.s[S_VOL_EDGE] += v;
@@ -303,44 +338,41 @@ __device__ __forceinline__ void route_cell(const tfb_channels_step_args &a,
         d = 0.0;
     }
     // checks :3193-3279, :3352-3454
-    if (d < 0.0) acc.s[S_NNEG_D] += 1.0;
-    if (d != d) acc.s[S_NNAN_D] += 1.0;
-    if (isinf(d)) acc.s[S_NINF_D] += 1.0;
-    if (u < 0.0) acc.s[S_NNEG_U] += 1.0;
-    if (u != u) acc.s[S_NNAN_U] += 1.0;
-    if (isinf(u)) acc.s[S_NINF_U] += 1.0;
+    if (d < 0.0) acc.n[S_NNEG_D - kNSum] += 1u;
+    if (d != d) acc.n[S_NNAN_D - kNSum] += 1u;
+    if (isinf(d)) acc.n[S_NINF_D - kNSum] += 1u;
+    if (u < 0.0) acc.n[S_NNEG_U - kNSum] += 1u;
+    if (u != u) acc.n[S_NNAN_U - kNSum] += 1u;
+    if (isinf(u)) acc.n[S_NINF_U - kNSum] += 1u;
     if (u > 0.0) acc.dt_min = fminf(acc.dt_min, __fdividef((float)g.ds, (float)u));
-    a.vol_out[i] = v;
-    a.d[i] = d;
-    a.u[i] = u;
-    a.Q_out[i] = u * A_wet;                                        // next :1697
+    o.vol = v; o.d = d; o.u = u;
+    o.Qn = u * A_wet;                                               // next :1697
+    (void)i;
 }
 
-// fold the block partials (fixed order => deterministic) ------------------------
-__device__ void fold_scalars(const tfb_channels_step_args &a, const double *sum,
-                             double dt_min, const double *outlet) {
+// fold the (locally or globally) reduced sums into the scalar block -------------
+__device__ void fold_scalars(const tfb_channels_step_args &a, const double *h) {
     tfb_channels_scalars &s = *a.scalars;
     const double dt = a.dt;
     if (a.is_R_grid) {
-        s.vol_R += sum[S_VOL_R];
+        s.vol_R += h[S_VOL_R];
     } else {
-        // scalar R: (R*da*dt) * n_pixels  (channels_base :1666-1668); the kernel
-        // left R in sum[S_VOL_R] slot unused, so recompute from the scalars
-        double ET = 0.0;   // scalar ET is dropped by the reference (:1629)
-        const double R = (((a.P_rain.val + a.SM.val) + a.GW.val) + a.MR.val) - (ET + a.IN.val);
+        // scalar R: (R*da*dt) * n_pixels (channels_base :1666-1668); a scalar ET
+        // is dropped by the reference (:1629)
+        const double R = (((a.P_rain.val + a.SM.val) + a.GW.val) + a.MR.val) - (0.0 + a.IN.val);
         s.vol_R += ((R * a.da.val) * dt) * (double)a.n_pixels_global;
     }
-    s.vol_edge += sum[S_VOL_EDGE];
-    s.vol_P += sum[S_VOL_P];   s.vol_PR += sum[S_VOL_PR]; s.vol_PS += sum[S_VOL_PS];
-    s.vol_SM += sum[S_VOL_SM]; s.vol_ET += sum[S_VOL_ET]; s.vol_IN += sum[S_VOL_IN];
-    s.n_neg_d = (int64_t)sum[S_NNEG_D]; s.n_nan_d = (int64_t)sum[S_NNAN_D];
-    s.n_inf_d = (int64_t)sum[S_NINF_D]; s.n_neg_u = (int64_t)sum[S_NNEG_U];
-    s.n_nan_u = (int64_t)sum[S_NNAN_U]; s.n_inf_u = (int64_t)sum[S_NINF_U];
-    s.n_nan_IN = (int64_t)sum[S_NNAN_IN];
-    s.dt_cfl_min = dt_min;
-    if (outlet) {
-        s.Q_outlet = outlet[0]; s.u_outlet = outlet[1];
-        s.d_outlet = outlet[2]; s.f_outlet = outlet[3];
+    s.vol_edge += h[S_VOL_EDGE];
+    s.vol_P += h[S_VOL_P];   s.vol_PR += h[S_VOL_PR]; s.vol_PS += h[S_VOL_PS];
+    s.vol_SM += h[S_VOL_SM]; s.vol_ET += h[S_VOL_ET]; s.vol_IN += h[S_VOL_IN];
+    s.n_neg_d = (int64_t)h[S_NNEG_D]; s.n_nan_d = (int64_t)h[S_NNAN_D];
+    s.n_inf_d = (int64_t)h[S_NINF_D]; s.n_neg_u = (int64_t)h[S_NNEG_U];
+    s.n_nan_u = (int64_t)h[S_NNAN_U]; s.n_inf_u = (int64_t)h[S_NINF_U];
+    s.n_nan_IN = (int64_t)h[S_NNAN_IN];
+    s.dt_cfl_min = h[P_DTMIN];
+    if (h[P_HASOUT_SUM] != 0.0) {
+        s.Q_outlet = h[P_QOUT]; s.u_outlet = h[P_UOUT];
+        s.d_outlet = h[P_DOUT]; s.f_outlet = h[P_FOUT];
     }
     // update_peak_values :2908-2926, update_Q_out_integral :2934
     if (s.Q_outlet > s.Q_peak) { s.Q_peak = s.Q_outlet; s.T_peak = a.time_min; }
@@ -350,159 +382,233 @@ __device__ void fold_scalars(const tfb_channels_step_args &a, const double *sum,
     s.step_count += 1;
 }
 
-constexpr int kBX = 32, kBY = 8, kRowsPerThread = 2;
-constexpr int kTileW = kBX, kTileH = kBY * kRowsPerThread;
+// ---------------------------------------------------------------------------
+// vector helpers: VEC adjacent cells per thread
+// ---------------------------------------------------------------------------
+template <int VEC> struct V { double v[VEC]; };
 
-template <bool DW, bool LOW, bool DIAG, bool SRC>
-__global__ void __launch_bounds__(kBX * kBY)
+template <int VEC>
+__device__ __forceinline__ V<VEC> ldv(const double *__restrict__ p, int64_t i) {
+    V<VEC> o;
+    if (VEC == 2) {
+        const double2 t = __ldg(reinterpret_cast<const double2 *>(p + i));
+        o.v[0] = t.x; o.v[VEC - 1] = t.y;
+    } else {
+        o.v[0] = __ldg(p + i);
+    }
+    return o;
+}
+template <int VEC>
+__device__ __forceinline__ V<VEC> ldsg(const tfb_sg &s, int64_t i) {
+    if (s.ptr) return ldv<VEC>(s.ptr, i);
+    V<VEC> o;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) o.v[j] = s.val;
+    return o;
+}
+template <int VEC>
+__device__ __forceinline__ void stv(double *__restrict__ p, int64_t i, const V<VEC> &x) {
+    if (VEC == 2) {
+        *reinterpret_cast<double2 *>(p + i) = make_double2(x.v[0], x.v[VEC - 1]);
+    } else {
+        p[i] = x.v[0];
+    }
+}
+
+constexpr int kBX = 32, kBY = 8;            // warp = one row segment, 8 rows per CTA
+constexpr int kTileRows = 64;               // rows a CTA walks per tile
+
+template <int VEC, bool DW, bool LOW, bool DIAG, bool SRC>
+__global__ void __launch_bounds__(kBX * kBY, (DW || DIAG || SRC) ? 1 : 2)
 channels_step_kernel(const tfb_channels_step_args a, const ChConsts k) {
     Acc acc;
 #pragma unroll
-    for (int j = 0; j < S_NSLOT; ++j) acc.s[j] = 0.0;
-    acc.dt_min = 3.0e38f;
-    const int c = blockIdx.x * kTileW + threadIdx.x;
-    const int rbase = blockIdx.y * kTileH + threadIdx.y;
-    if (c < a.nx) {
+    for (int j = 0; j < kNSum; ++j) acc.s[j] = 0.0;
 #pragma unroll
-        for (int j = 0; j < kRowsPerThread; ++j) {
-            const int r = rbase + j * kBY;
-            if (r < a.ny) route_cell<DW, LOW, DIAG, SRC>(a, k, r, c, acc);
+    for (int j = 0; j < kNCnt; ++j) acc.n[j] = 0u;
+    acc.dt_min = 3.0e38f;
+
+    constexpr int kTileW = kBX * VEC;
+    const int tiles_x = (a.nx + kTileW - 1) / kTileW;
+    const int tiles_y = (a.ny + kTileRows - 1) / kTileRows;
+    const int n_tiles = tiles_x * tiles_y;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int ty = t / tiles_x, tx = t - ty * tiles_x;
+        const int c0 = tx * kTileW + threadIdx.x * VEC;
+        if (c0 >= a.nx) continue;
+        const int r_end = min(a.ny, (ty + 1) * kTileRows);
+        for (int r = ty * kTileRows + threadIdx.y; r < r_end; r += kBY) {
+            const int64_t i = (int64_t)r * a.nx + c0;
+            // ---- own inputs, 128-bit where possible -----------------------
+            unsigned gw[VEC];
+            if (VEC == 2) {
+                const unsigned w2 = __ldg(reinterpret_cast<const unsigned *>(a.geo + i));
+                gw[0] = w2 & 0xffffu; gw[VEC - 1] = w2 >> 16;
+            } else {
+                gw[0] = a.geo[i];
+            }
+            const V<VEC> vol = ldv<VEC>(a.vol, i), Qo = ldv<VEC>(a.Q_in, i);
+            const V<VEC> wid = ldsg<VEC>(a.width, i), tn = ldsg<VEC>(a.tan_angle, i);
+            const V<VEC> cs = ldsg<VEC>(a.cos_angle, i), rg = ldsg<VEC>(a.rough, i);
+            const V<VEC> sl = ldv<VEC>((DW || DIAG || LOW) ? a.S_bed : a.sqrtS, i);
+            const V<VEC> sn = ldsg<VEC>(a.sinu, i);
+            const float dxr = __ldg(a.dx + r), dyr = __ldg(a.dy + r), ddr = __ldg(a.dd + r);
+            const double dar = a.da.ptr ? __ldg(a.da.ptr + r) : a.da.val;
+            // ---- children's discharge: predicated loads --------------------
+            double Qc[VEC][8];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+                load_children(a.Q_in + i + j, a.nx, gw[j] >> 8, Qc[j]);
+            V<VEC> o_vol, o_d, o_u, o_Q;
+            V<VEC> o_Rh, o_A, o_P, o_f, o_tau, o_us, o_fr, o_S, o_R;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                Cell g;
+                g.code = gw[j] & 0xffu;
+                g.cmask = gw[j] >> 8;
+                g.ds = sn.v[j] * (double)ds_of(g.code, dxr, dyr, ddr);
+                g.da = dar;
+                g.width = wid.v[j]; g.tan_a = tn.v[j]; g.cos_a = cs.v[j];
+                g.vol = vol.v[j]; g.Q = Qo.v[j];
+                double v, d, R;
+                vol_depth<SRC, true>(a, i + j, g, Qc[j], v, d, R, &acc);
+                CellOut o;
+                finish_cell<DW, LOW, DIAG, SRC>(a, k, r, c0 + j, i + j, g, v, d, sl.v[j],
+                                                rg.v[j], acc, o);
+                o_vol.v[j] = o.vol; o_d.v[j] = o.d; o_u.v[j] = o.u; o_Q.v[j] = o.Qn;
+                if (DIAG) {
+                    o_Rh.v[j] = o.Rh; o_A.v[j] = o.A_wet; o_P.v[j] = o.P_wet; o_f.v[j] = o.f;
+                    o_tau.v[j] = o.tau; o_us.v[j] = o.u_star; o_fr.v[j] = o.froude;
+                    o_S.v[j] = o.S;
+                }
+                o_R.v[j] = R;
+            }
+            stv<VEC>(a.vol_out, i, o_vol);
+            stv<VEC>(a.d, i, o_d);
+            stv<VEC>(a.u, i, o_u);
+            stv<VEC>(a.Q_out, i, o_Q);
+            if (DIAG) {
+                stv<VEC>(a.Rh, i, o_Rh); stv<VEC>(a.A_wet, i, o_A); stv<VEC>(a.P_wet, i, o_P);
+                stv<VEC>(a.f, i, o_f); stv<VEC>(a.tau, i, o_tau); stv<VEC>(a.u_star, i, o_us);
+                stv<VEC>(a.froude, i, o_fr);
+                if (DW && a.S_free) stv<VEC>(a.S_free, i, o_S);
+            }
+            if ((a.flags & TFB_CH_WRITE_R) && a.R) stv<VEC>(a.R, i, o_R);
         }
     }
-    // ---- block reduction: warp shuffles, then one smem hop ------------------
-    __shared__ double sm[kBY][S_NSLOT + 1];
+
+    // ---- CTA reduction: warp shuffles only where a warp has something -------
+    __shared__ double sm[kBY][kPartialStride];
     __shared__ bool is_last;
     const int lane = threadIdx.x, warp = threadIdx.y;
 #pragma unroll
-    for (int j = 0; j < S_NSLOT; ++j) {
-        const double v = warp_sum(acc.s[j]);
+    for (int j = 0; j < kNSum; ++j) {
+        double v = acc.s[j];
+        if (__any_sync(0xffffffffu, v != 0.0)) v = warp_sum(v);
         if (lane == 0) sm[warp][j] = v;
     }
     {
+        unsigned any = 0;
+#pragma unroll
+        for (int j = 0; j < kNCnt; ++j) any |= acc.n[j];
+        const bool some = __any_sync(0xffffffffu, any != 0u);
+#pragma unroll
+        for (int j = 0; j < kNCnt; ++j) {
+            unsigned v = acc.n[j];
+            if (some) v = __reduce_add_sync(0xffffffffu, v);
+            if (lane == 0) sm[warp][kNSum + j] = (double)v;
+        }
         const double m = warp_min((double)acc.dt_min);
-        if (lane == 0) sm[warp][S_NSLOT] = m;
+        if (lane == 0) sm[warp][P_DTMIN] = m;
     }
     __syncthreads();
     const int tid = warp * kBX + lane;
-    const int nblk = gridDim.x * gridDim.y;
-    const int bid = blockIdx.y * gridDim.x + blockIdx.x;
-    if (tid <= S_NSLOT) {
-        double v = sm[0][tid];
-        for (int w = 1; w < kBY; ++w)
-            v = (tid == S_NSLOT) ? fmin(v, sm[w][tid]) : (v + sm[w][tid]);
-        a.partials[(int64_t)bid * kPartialStride + tid] = v;
+    const int nblk = gridDim.x;
+    if (tid < kPartialStride) {
+        double v = 0.0;
+        if (tid < S_NSLOT) {
+            for (int w = 0; w < kBY; ++w) v += sm[w][tid];
+        } else if (tid == P_DTMIN) {
+            v = sm[0][tid];
+            for (int w = 1; w < kBY; ++w) v = fmin(v, sm[w][tid]);
+        }
+        a.partials[(int64_t)(blockIdx.x + 2) * kPartialStride + tid] = v;
     }
     __threadfence();
     __syncthreads();
     if (tid == 0) {
-        const unsigned t = atomicAdd(a.ticket, 1u);
-        is_last = (t == (unsigned)nblk - 1u);
+        const unsigned tk = atomicAdd(a.ticket, 1u);
+        is_last = (tk == (unsigned)nblk - 1u);
     }
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    // last block: every thread folds a strided subset in a FIXED order
-    __shared__ double red[kBX * kBY];
-    double tot[S_NSLOT + 1];
-    const volatile double *P = a.partials;
-    for (int j = 0; j <= S_NSLOT; ++j) {
-        double v = (j == S_NSLOT) ? 3.0e38 : 0.0;
-        for (int b = tid; b < nblk; b += kBX * kBY) {
-            const double x = P[(int64_t)b * kPartialStride + j];
-            v = (j == S_NSLOT) ? fmin(v, x) : (v + x);
+    // last CTA: thread j folds slot j over all CTAs in index order (deterministic)
+    __shared__ double tot[kPartialStride];
+    if (tid < kPartialStride) {
+        const volatile double *P = a.partials;
+        double v = (tid == P_DTMIN) ? 3.0e38 : 0.0;
+        if (tid < S_NSLOT || tid == P_DTMIN) {
+            for (int b = 0; b < nblk; ++b) {
+                const double x = P[(int64_t)(b + 2) * kPartialStride + tid];
+                v = (tid == P_DTMIN) ? fmin(v, x) : (v + x);
+            }
         }
-        red[tid] = v;
-        __syncthreads();
-        for (int s = (kBX * kBY) / 2; s > 0; s >>= 1) {
-            if (tid < s)
-                red[tid] = (j == S_NSLOT) ? fmin(red[tid], red[tid + s])
-                                          : (red[tid] + red[tid + s]);
-            __syncthreads();
-        }
-        tot[j] = red[0];
-        __syncthreads();
+        tot[tid] = v;
     }
+    __syncthreads();
     if (tid == 0) {
-        double *outp = a.partials + (int64_t)nblk * kPartialStride;
+        double *outp = a.partials + kPartialStride;       // row 1
         const bool has_out = (outp[P_HASOUT] != 0.0);
-        if (a.finalize) {
-            double o4[4] = {outp[P_QOUT], outp[P_UOUT], outp[P_DOUT], outp[P_FOUT]};
-            fold_scalars(a, tot, tot[S_NSLOT], has_out ? o4 : nullptr);
-        } else {
-            // leave per-rank sums at the head of `partials` for the allreduce:
-            // [0..15) sums, [15] has-outlet flag, then dt_min + outlet values
-            double *h = a.partials + (int64_t)(nblk + 1) * kPartialStride;
-            for (int j = 0; j < S_NSLOT; ++j) h[j] = tot[j];
-            h[S_NSLOT] = has_out ? 1.0 : 0.0;
-            h[P_DTMIN] = tot[S_NSLOT];
-            h[P_QOUT] = has_out ? outp[P_QOUT] : 0.0;
-            h[P_UOUT] = has_out ? outp[P_UOUT] : 0.0;
-            h[P_DOUT] = has_out ? outp[P_DOUT] : 0.0;
-            h[P_FOUT] = has_out ? outp[P_FOUT] : 0.0;
-        }
+        double *h = a.partials;                           // row 0: this rank's sums
+        for (int j = 0; j < S_NSLOT; ++j) h[j] = tot[j];
+        h[P_HASOUT_SUM] = has_out ? 1.0 : 0.0;
+        h[P_DTMIN] = tot[P_DTMIN];
+        h[P_QOUT] = has_out ? outp[P_QOUT] : 0.0;
+        h[P_UOUT] = has_out ? outp[P_UOUT] : 0.0;
+        h[P_DOUT] = has_out ? outp[P_DOUT] : 0.0;
+        h[P_FOUT] = has_out ? outp[P_FOUT] : 0.0;
+        h[P_HASOUT] = 0.0; h[22] = 0.0; h[23] = 0.0;
         outp[P_HASOUT] = 0.0;
+        if (a.finalize) fold_scalars(a, h);
         *a.ticket = 0u;    // re-arm for the next step
     }
 }
 
 __global__ void channels_fold_kernel(const tfb_channels_step_args a, const double *sums) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    // sums layout = the `h` block above after an allreduce(SUM) over ranks; the
-    // dt_min slot must have been reduced with MIN by the caller (or is ignored)
-    const bool has_out = sums[S_NSLOT] != 0.0;
-    double o4[4] = {sums[P_QOUT], sums[P_UOUT], sums[P_DOUT], sums[P_FOUT]};
-    fold_scalars(a, sums, sums[P_DTMIN], has_out ? o4 : nullptr);
+    if (threadIdx.x == 0 && blockIdx.x == 0) fold_scalars(a, sums);
 }
 
-template <bool DW, bool LOW, bool DIAG, bool SRC>
+static int persistent_grid(int64_t n_tiles, int ctas_per_sm) {
+    int64_t g = (int64_t)sm_count() * ctas_per_sm;
+    if (g > n_tiles) g = n_tiles;
+    return (int)(g < 1 ? 1 : g);
+}
+
+template <int VEC, bool DW, bool LOW, bool DIAG, bool SRC>
 static int launch(const tfb_channels_step_args &a, const ChConsts &k, cudaStream_t st) {
+    const int tw = kBX * VEC;
+    const int64_t n_tiles = (int64_t)((a.nx + tw - 1) / tw) * ((a.ny + kTileRows - 1) / kTileRows);
+    int per_sm = 0;
+    TFB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &per_sm, channels_step_kernel<VEC, DW, LOW, DIAG, SRC>, kBX * kBY, 0));
+    if (per_sm < 1) per_sm = 1;
     dim3 block(kBX, kBY);
-    dim3 grid((a.nx + kTileW - 1) / kTileW, (a.ny + kTileH - 1) / kTileH);
-    channels_step_kernel<DW, LOW, DIAG, SRC><<<grid, block, 0, st>>>(a, k);
+    channels_step_kernel<VEC, DW, LOW, DIAG, SRC>
+        <<<persistent_grid(n_tiles, per_sm), block, 0, st>>>(a, k);
     TFB_CUDA_CHECK(cudaGetLastError());
     return TFB_OK;
 }
 
-}  // namespace tfb
-
-using namespace tfb;
-
-extern "C" int64_t tfb_channels_partials_len(int32_t ny, int32_t nx) {
-    const int64_t gx = (nx + kTileW - 1) / kTileW, gy = (ny + kTileH - 1) / kTileH;
-    return (gx * gy + 2) * kPartialStride;
-}
-
-extern "C" int tfb_channels_step(const tfb_channels_step_args *ap, void *stream) {
-    TFB_ARG_CHECK(ap != nullptr);
-    const tfb_channels_step_args &a = *ap;
-    TFB_ARG_CHECK(a.ny > 0 && a.nx > 0 && a.halo >= 0);
-    TFB_ARG_CHECK(a.code && a.dx && a.dy && a.dd && a.S_bed);
-    TFB_ARG_CHECK(a.vol && a.vol_out && a.Q_in && a.Q_out && a.d && a.u);
-    TFB_ARG_CHECK(a.Q_in != a.Q_out);
-    TFB_ARG_CHECK(a.scalars && a.partials && a.ticket);
-    TFB_ARG_CHECK(a.dt > 0.0);
+template <int VEC>
+static int dispatch(const tfb_channels_step_args &a, const ChConsts &k, cudaStream_t st) {
     const bool dw = a.flags & TFB_CH_DIFFUSIVE, low = a.flags & TFB_CH_LAW_OF_WALL;
     const bool diag = a.flags & TFB_CH_DIAG;
     const bool src = a.flags & (TFB_CH_SRC_MET | TFB_CH_SRC_SNOW | TFB_CH_SRC_EVAP |
                                 TFB_CH_SRC_INFIL);
-    if (diag)
-        TFB_ARG_CHECK(a.Rh && a.A_wet && a.P_wet && a.f && a.tau && a.u_star && a.froude);
-    if (a.flags & TFB_CH_SRC_SNOW) TFB_ARG_CHECK(a.h_swe && a.h_swe_out);
-    if (a.flags & TFB_CH_SRC_INFIL) TFB_ARG_CHECK(a.I && a.I_out);
-    if (a.flags & TFB_CH_DIFFUSIVE) {
-        // neighbours re-read pre-step state: it must not be updated in place
-        TFB_ARG_CHECK(a.vol != a.vol_out);
-        if (a.flags & TFB_CH_SRC_SNOW) TFB_ARG_CHECK(a.h_swe != a.h_swe_out);
-        if (a.flags & TFB_CH_SRC_INFIL) TFB_ARG_CHECK(a.I != a.I_out);
-    }
-    if (src) TFB_ARG_CHECK(a.is_R_grid == 1);
-    ChConsts k;
-    k.g = 9.81; k.aval = 0.476; k.kappa = 0.408;
-    k.law_const = sqrt(k.g) / k.kappa;                 // channels_base :531
-    cudaStream_t st = (cudaStream_t)stream;
 #define TFB_DISPATCH(DW_, LOW_, DIAG_, SRC_)                                       \
     if (dw == DW_ && low == LOW_ && diag == DIAG_ && src == SRC_)                  \
-        return launch<DW_, LOW_, DIAG_, SRC_>(a, k, st);
+        return launch<VEC, DW_, LOW_, DIAG_, SRC_>(a, k, st);
     TFB_DISPATCH(false, false, false, false) TFB_DISPATCH(false, false, false, true)
     TFB_DISPATCH(false, false, true, false)  TFB_DISPATCH(false, false, true, true)
     TFB_DISPATCH(false, true, false, false)  TFB_DISPATCH(false, true, false, true)
@@ -513,6 +619,66 @@ extern "C" int tfb_channels_step(const tfb_channels_step_args *ap, void *stream)
     TFB_DISPATCH(true, true, true, false)    TFB_DISPATCH(true, true, true, true)
 #undef TFB_DISPATCH
     return TFB_ERR_ARG;
+}
+
+}  // namespace tfb
+
+using namespace tfb;
+
+extern "C" int64_t tfb_channels_partials_len(int32_t ny, int32_t nx) {
+    (void)ny; (void)nx;
+    // one row per resident CTA (<= 8 per SM) + outlet row + rank-sum row
+    return ((int64_t)sm_count() * 8 + 2) * kPartialStride;
+}
+
+extern "C" int tfb_channels_pack_geo(const uint8_t *code, int32_t ny, int32_t nx,
+                                     int32_t halo, uint16_t *geo, void *stream) {
+    TFB_ARG_CHECK(code && geo && ny > 0 && nx > 0 && halo >= 0);
+    dim3 b(32, 8), g((nx + 31) / 32, (ny + 2 * halo + 7) / 8);
+    pack_geo_kernel<<<g, b, 0, (cudaStream_t)stream>>>(code, ny, nx, halo, geo);
+    TFB_CUDA_CHECK(cudaGetLastError());
+    return TFB_OK;
+}
+
+extern "C" int tfb_channels_step(const tfb_channels_step_args *ap, void *stream) {
+    TFB_ARG_CHECK(ap != nullptr);
+    const tfb_channels_step_args &a = *ap;
+    TFB_ARG_CHECK(a.ny > 0 && a.nx > 0 && a.halo >= 0);
+    TFB_ARG_CHECK(a.geo && a.dx && a.dy && a.dd);
+    TFB_ARG_CHECK(a.vol && a.vol_out && a.Q_in && a.Q_out && a.d && a.u);
+    TFB_ARG_CHECK(a.Q_in != a.Q_out);
+    TFB_ARG_CHECK(a.scalars && a.partials && a.ticket);
+    TFB_ARG_CHECK(a.dt > 0.0);
+    const bool dw = a.flags & TFB_CH_DIFFUSIVE, diag = a.flags & TFB_CH_DIAG;
+    const bool src = a.flags & (TFB_CH_SRC_MET | TFB_CH_SRC_SNOW | TFB_CH_SRC_EVAP |
+                                TFB_CH_SRC_INFIL);
+    if (dw || diag || (a.flags & TFB_CH_LAW_OF_WALL)) TFB_ARG_CHECK(a.S_bed != nullptr);
+    else TFB_ARG_CHECK(a.sqrtS != nullptr);
+    if (diag)
+        TFB_ARG_CHECK(a.Rh && a.A_wet && a.P_wet && a.f && a.tau && a.u_star && a.froude);
+    if (a.flags & TFB_CH_SRC_SNOW) TFB_ARG_CHECK(a.h_swe && a.h_swe_out);
+    if (a.flags & TFB_CH_SRC_INFIL) TFB_ARG_CHECK(a.I && a.I_out);
+    if (dw) {
+        // neighbours re-read pre-step state: it must not be updated in place
+        TFB_ARG_CHECK(a.vol != a.vol_out);
+        if (a.flags & TFB_CH_SRC_SNOW) TFB_ARG_CHECK(a.h_swe != a.h_swe_out);
+        if (a.flags & TFB_CH_SRC_INFIL) TFB_ARG_CHECK(a.I != a.I_out);
+    }
+    if (src) TFB_ARG_CHECK(a.is_R_grid == 1);
+    ChConsts k;
+    k.g = 9.81; k.aval = 0.476; k.kappa = 0.408;
+    k.law_const = sqrt(k.g) / k.kappa;                 // channels_base :531
+    cudaStream_t st = (cudaStream_t)stream;
+    // 128-bit path needs every row 16-byte aligned: even nx and aligned bases
+    auto al16 = [](const void *p) { return p == nullptr || (((uintptr_t)p) & 15u) == 0; };
+    const bool vec2 = (a.nx % 2 == 0) && al16(a.vol) && al16(a.vol_out) && al16(a.Q_in) &&
+                      al16(a.Q_out) && al16(a.d) && al16(a.u) && al16(a.S_bed) &&
+                      al16(a.sqrtS) && al16(a.width.ptr) && al16(a.tan_angle.ptr) &&
+                      al16(a.cos_angle.ptr) && al16(a.rough.ptr) && al16(a.sinu.ptr) &&
+                      al16(a.Rh) && al16(a.A_wet) && al16(a.P_wet) && al16(a.f) &&
+                      al16(a.tau) && al16(a.u_star) && al16(a.froude) && al16(a.S_free) &&
+                      al16(a.R) && ((((uintptr_t)a.geo) & 3u) == 0);
+    return vec2 ? dispatch<2>(a, k, st) : dispatch<1>(a, k, st);
 }
 
 extern "C" int tfb_channels_fold(const tfb_channels_step_args *ap, const double *sums,

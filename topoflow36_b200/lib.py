@@ -61,9 +61,9 @@ class ChannelsStepArgs(C.Structure):
         ('dt', C.c_double), ('time_min', C.c_double), ('rho_H2O', C.c_double),
         ('n_pixels_global', C.c_int64),
         ('halo', C.c_int32),
-        ('code', vp), ('dx', vp), ('dy', vp), ('dd', vp),
-        ('sinu', SG), ('da', SG), ('S_bed', vp), ('width', SG),
-        ('tan_angle', SG), ('cos_angle', SG), ('angle', SG), ('rough', SG),
+        ('geo', vp), ('dx', vp), ('dy', vp), ('dd', vp),
+        ('sinu', SG), ('da', SG), ('S_bed', vp), ('sqrtS', vp), ('width', SG),
+        ('tan_angle', SG), ('cos_angle', SG), ('rough', SG),
         ('vol', vp), ('vol_out', vp), ('Q_in', vp), ('Q_out', vp),
         ('d', vp), ('u', vp),
         ('Rh', vp), ('A_wet', vp), ('P_wet', vp), ('f', vp), ('tau', vp),
@@ -108,6 +108,7 @@ SIGNATURES = {
     'tfb_sizeof_channels_step_args': (_i64, []),
     'tfb_sizeof_channels_scalars': (_i64, []),
     'tfb_channels_partials_len': (_i64, [_i32, _i32]),
+    'tfb_channels_pack_geo': (C.c_int, [vp, _i32, _i32, _i32, vp, vp]),
     'tfb_channels_step': (C.c_int, [C.POINTER(ChannelsStepArgs), vp]),
     'tfb_channels_fold': (C.c_int, [C.POINTER(ChannelsStepArgs), vp, vp]),
     'tfb_sources_partials_len': (_i64, []),

@@ -68,13 +68,28 @@ class ChannelsEngine(object):
         self.flags = flags
         # ---- static inputs --------------------------------------------------
         self.code = self._grid(code, torch.uint8)
-        a.code = self._p(self.code)
+        # packed geo word per cell: D8 code + child mask (parent-side gather)
+        self.geo = self._zeros(torch.int16)
+        L.check(self.lib.tfb_channels_pack_geo(self._p(self.code), self.ny, self.nx, self.halo,
+                                               self._p(self.geo), L.stream_ptr()),
+                'tfb_channels_pack_geo')
+        a.geo = self._p(self.geo)
         self.dx = self._rows(dx, torch.float32)
         self.dy = self._rows(dy, torch.float32)
         self.dd = self._rows(dd, torch.float32)
         a.dx, a.dy, a.dd = self._prow(self.dx), self._prow(self.dy), self._prow(self.dd)
         self.S_bed = self._grid(S_bed, torch.float64)
         a.S_bed = self._p(self.S_bed)
+        if kinematic and manning and not diag:
+            # lean kinematic step only ever uses sqrt(|S_bed|) (channels_base
+            # :3982-3983); evaluate it once -- by numpy when S_bed came as numpy,
+            # so the value is the very one np.sqrt gives the reference
+            if isinstance(S_bed, torch.Tensor):
+                self.sqrtS = torch.sqrt(torch.abs(self.S_bed))
+            else:
+                self.sqrtS = self._grid(np.sqrt(np.abs(np.asarray(S_bed, dtype='float64'))),
+                                        torch.float64)
+            a.sqrtS = self._p(self.sqrtS)
         # tan / cos of the bank angle come from numpy on the host when the
         # angle is handed over as numpy (bit-identical to the reference's
         # np.tan / np.cos); torch inputs are evaluated on the device.
@@ -82,7 +97,7 @@ class ChannelsEngine(object):
             tan_angle = np.tan(angle) if not isinstance(angle, torch.Tensor) else torch.tan(angle)
         if cos_angle is None:
             cos_angle = np.cos(angle) if not isinstance(angle, torch.Tensor) else torch.cos(angle)
-        for name, val in (('sinu', sinu), ('width', width), ('angle', angle),
+        for name, val in (('sinu', sinu), ('width', width),
                           ('tan_angle', tan_angle), ('cos_angle', cos_angle),
                           ('rough', rough)):
             setattr(a, name, self._sg(name, val))
