@@ -31,10 +31,20 @@
 // numpy's pow/log); + - * / sqrt are IEEE-exact.
 #include "tfb_common.cuh"
 
+// resident CTAs (of 256 threads) per SM the register allocator must allow:
+// the lean kinematic kernel wants occupancy more than registers (measured)
+#ifndef TFB_KW_MINBLOCKS
+#define TFB_KW_MINBLOCKS 3
+#endif
+#ifndef TFB_OTHER_MINBLOCKS
+#define TFB_OTHER_MINBLOCKS 2
+#endif
+
 namespace tfb {
 
 struct ChConsts {
     double g, aval, kappa, law_const;
+    double R_uniform, Rdadt_uniform;   // UR kernels: all six source inputs scalar
 };
 
 // reduction slots ------------------------------------------------------------
@@ -50,6 +60,8 @@ static_assert(kPartialStride == TFB_NSUM, "TFB_NSUM must equal the partial strid
 constexpr int P_HASOUT_SUM = 15, P_DTMIN = 16, P_QOUT = 17, P_UOUT = 18, P_DOUT = 19,
               P_FOUT = 20, P_HASOUT = 21;
 
+// (only slots 0..1 are live unless source terms are fused; the compiler drops
+// the dead registers because every use is guarded by a template constant)
 struct Acc {
     double s[kNSum];
     unsigned n[kNCnt];
@@ -198,28 +210,36 @@ __device__ __forceinline__ void load_cell_scalar(const tfb_channels_step_args &a
 }
 
 // new volume (before the noflow zeroing) and new depth of a cell ---------------
-template <bool SRC, bool COMMIT>
-__device__ __forceinline__ void vol_depth(const tfb_channels_step_args &a, int64_t i,
-                                          const Cell &g, const double *__restrict__ Qc,
-                                          double &vol_new, double &d_new, double &R_out,
-                                          Acc *acc) {
+template <bool SRC, bool UR, bool COMMIT>
+__device__ __forceinline__ void vol_depth(const tfb_channels_step_args &a, const ChConsts &kc,
+                                          int64_t i, const Cell &g,
+                                          const double *__restrict__ Qc, double &vol_new,
+                                          double &d_new, double &R_out, Acc *acc) {
     const double dt = a.dt;
-    Src s;
-    eval_sources<SRC, COMMIT>(a, i, g.da, s, acc);
-    // update_R :1625-1649
-    double ET = s.ET;
-    if (s.ET_is_grid) {
-        if (g.vol < ((ET * g.da) * dt)) {
-            ET = 0.0;
-            if (COMMIT && (a.flags & TFB_CH_ET_INPLACE) && a.ET_rw) a.ET_rw[i] = 0.0;
-        }
+    double v;
+    if (UR) {
+        // every source input is a scalar (and so is da): R and (R*da)*dt are the
+        // same for all cells -- evaluated once on the host in this very order
+        R_out = kc.R_uniform;
+        v = g.vol + kc.Rdadt_uniform;                                // :2086
     } else {
-        ET = 0.0;                       // reference: a scalar ET is dropped (:1629)
+        Src s;
+        eval_sources<SRC, COMMIT>(a, i, g.da, s, acc);
+        // update_R :1625-1649
+        double ET = s.ET;
+        if (s.ET_is_grid) {
+            if (g.vol < ((ET * g.da) * dt)) {
+                ET = 0.0;
+                if (COMMIT && (a.flags & TFB_CH_ET_INPLACE) && a.ET_rw) a.ET_rw[i] = 0.0;
+            }
+        } else {
+            ET = 0.0;                   // reference: a scalar ET is dropped (:1629)
+        }
+        const double R = (((s.P_rain + s.SM) + s.GW) + s.MR) - (ET + s.IN);
+        R_out = R;
+        if (COMMIT && a.is_R_grid) acc->s[S_VOL_R] += (R * g.da) * dt;   // :1666-1670
+        v = g.vol + ((R * g.da) * dt);                               // :2086
     }
-    const double R = (((s.P_rain + s.SM) + s.GW) + s.MR) - (ET + s.IN);
-    R_out = R;
-    if (COMMIT && a.is_R_grid) acc->s[S_VOL_R] += (R * g.da) * dt;   // :1666-1670
-    double v = g.vol + ((R * g.da) * dt);                            // :2086
     // children in the reference's order (codes 1,2,4,...,128) :2116-2131;
     // Qc[k] is the child's discharge, meaningful only where the mask bit is set
 #pragma unroll
@@ -258,7 +278,7 @@ struct CellOut {
 };
 
 // everything after the depth: Rh, slope, velocity, diagnostics, bookkeeping
-template <bool DW, bool LOW, bool DIAG, bool SRC>
+template <bool DW, bool LOW, bool DIAG, bool SRC, bool UR>
 __device__ __forceinline__ void finish_cell(const tfb_channels_step_args &a,
                                             const ChConsts &k, int r, int c, int64_t i,
                                             const Cell &g, double v, double d,
@@ -289,7 +309,7 @@ __device__ __forceinline__ void finish_cell(const tfb_channels_step_args &a,
             load_cell_scalar(a, pr, ip, gp);
             double Qc[8], vp, Rp;
             load_children(a.Q_in + ip, a.nx, gp.cmask, Qc);
-            vol_depth<SRC, false>(a, ip, gp, Qc, vp, d_par, Rp, nullptr);
+            vol_depth<SRC, UR, false>(a, k, ip, gp, Qc, vp, d_par, Rp, nullptr);
         }
         S = slope_in + ((d - d_par) / g.ds);
         sqrtS = sqrt(fabs(S));
@@ -418,8 +438,10 @@ __device__ __forceinline__ void stv(double *__restrict__ p, int64_t i, const V<V
 constexpr int kBX = 32, kBY = 8;            // warp = one row segment, 8 rows per CTA
 constexpr int kTileRows = 64;               // rows a CTA walks per tile
 
-template <int VEC, bool DW, bool LOW, bool DIAG, bool SRC>
-__global__ void __launch_bounds__(kBX * kBY, (DW || DIAG || SRC) ? 1 : 2)
+// GP: width / tan / cos / roughness are all grids and sinu, da scalars (the usual
+// case) -> straight 128-bit loads, no scalar-or-grid selects.  UR: see vol_depth.
+template <int VEC, bool DW, bool LOW, bool DIAG, bool SRC, bool GP, bool UR>
+__global__ void __launch_bounds__(kBX * kBY, (DW || DIAG || SRC) ? TFB_OTHER_MINBLOCKS : TFB_KW_MINBLOCKS)
 channels_step_kernel(const tfb_channels_step_args a, const ChConsts k) {
     Acc acc;
 #pragma unroll
@@ -448,12 +470,20 @@ channels_step_kernel(const tfb_channels_step_args a, const ChConsts k) {
                 gw[0] = a.geo[i];
             }
             const V<VEC> vol = ldv<VEC>(a.vol, i), Qo = ldv<VEC>(a.Q_in, i);
-            const V<VEC> wid = ldsg<VEC>(a.width, i), tn = ldsg<VEC>(a.tan_angle, i);
-            const V<VEC> cs = ldsg<VEC>(a.cos_angle, i), rg = ldsg<VEC>(a.rough, i);
+            V<VEC> wid, tn, cs, rg, sn;
+            if (GP) {
+                wid = ldv<VEC>(a.width.ptr, i); tn = ldv<VEC>(a.tan_angle.ptr, i);
+                cs = ldv<VEC>(a.cos_angle.ptr, i); rg = ldv<VEC>(a.rough.ptr, i);
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) sn.v[j] = a.sinu.val;
+            } else {
+                wid = ldsg<VEC>(a.width, i); tn = ldsg<VEC>(a.tan_angle, i);
+                cs = ldsg<VEC>(a.cos_angle, i); rg = ldsg<VEC>(a.rough, i);
+                sn = ldsg<VEC>(a.sinu, i);
+            }
             const V<VEC> sl = ldv<VEC>((DW || DIAG || LOW) ? a.S_bed : a.sqrtS, i);
-            const V<VEC> sn = ldsg<VEC>(a.sinu, i);
             const float dxr = __ldg(a.dx + r), dyr = __ldg(a.dy + r), ddr = __ldg(a.dd + r);
-            const double dar = a.da.ptr ? __ldg(a.da.ptr + r) : a.da.val;
+            const double dar = (GP || !a.da.ptr) ? a.da.val : __ldg(a.da.ptr + r);
             // ---- children's discharge: predicated loads --------------------
             double Qc[VEC][8];
 #pragma unroll
@@ -471,9 +501,9 @@ channels_step_kernel(const tfb_channels_step_args a, const ChConsts k) {
                 g.width = wid.v[j]; g.tan_a = tn.v[j]; g.cos_a = cs.v[j];
                 g.vol = vol.v[j]; g.Q = Qo.v[j];
                 double v, d, R;
-                vol_depth<SRC, true>(a, i + j, g, Qc[j], v, d, R, &acc);
+                vol_depth<SRC, UR, true>(a, k, i + j, g, Qc[j], v, d, R, &acc);
                 CellOut o;
-                finish_cell<DW, LOW, DIAG, SRC>(a, k, r, c0 + j, i + j, g, v, d, sl.v[j],
+                finish_cell<DW, LOW, DIAG, SRC, UR>(a, k, r, c0 + j, i + j, g, v, d, sl.v[j],
                                                 rg.v[j], acc, o);
                 o_vol.v[j] = o.vol; o_d.v[j] = o.d; o_u.v[j] = o.u; o_Q.v[j] = o.Qn;
                 if (DIAG) {
@@ -585,39 +615,59 @@ static int persistent_grid(int64_t n_tiles, int ctas_per_sm) {
     return (int)(g < 1 ? 1 : g);
 }
 
-template <int VEC, bool DW, bool LOW, bool DIAG, bool SRC>
+template <int VEC, bool DW, bool LOW, bool DIAG, bool SRC, bool GP, bool UR>
 static int launch(const tfb_channels_step_args &a, const ChConsts &k, cudaStream_t st) {
     const int tw = kBX * VEC;
     const int64_t n_tiles = (int64_t)((a.nx + tw - 1) / tw) * ((a.ny + kTileRows - 1) / kTileRows);
     int per_sm = 0;
     TFB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &per_sm, channels_step_kernel<VEC, DW, LOW, DIAG, SRC>, kBX * kBY, 0));
+        &per_sm, channels_step_kernel<VEC, DW, LOW, DIAG, SRC, GP, UR>, kBX * kBY, 0));
     if (per_sm < 1) per_sm = 1;
     dim3 block(kBX, kBY);
-    channels_step_kernel<VEC, DW, LOW, DIAG, SRC>
+    channels_step_kernel<VEC, DW, LOW, DIAG, SRC, GP, UR>
         <<<persistent_grid(n_tiles, per_sm), block, 0, st>>>(a, k);
     TFB_CUDA_CHECK(cudaGetLastError());
     return TFB_OK;
 }
 
 template <int VEC>
-static int dispatch(const tfb_channels_step_args &a, const ChConsts &k, cudaStream_t st) {
+static int dispatch(const tfb_channels_step_args &a, ChConsts &k, cudaStream_t st) {
     const bool dw = a.flags & TFB_CH_DIFFUSIVE, low = a.flags & TFB_CH_LAW_OF_WALL;
     const bool diag = a.flags & TFB_CH_DIAG;
     const bool src = a.flags & (TFB_CH_SRC_MET | TFB_CH_SRC_SNOW | TFB_CH_SRC_EVAP |
                                 TFB_CH_SRC_INFIL);
-#define TFB_DISPATCH(DW_, LOW_, DIAG_, SRC_)                                       \
+    // fast-path eligibility
+    const bool gp = (VEC == 2) && !low && a.width.ptr && a.tan_angle.ptr && a.cos_angle.ptr &&
+                    a.rough.ptr && !a.sinu.ptr && !a.da.ptr;
+    const bool ur = gp && !src && !a.P_rain.ptr && !a.SM.ptr && !a.GW.ptr && !a.MR.ptr &&
+                    !a.IN.ptr && !a.ET.ptr && !a.is_R_grid && !(a.flags & TFB_CH_WRITE_R);
+    if (ur) {
+        const double R = (((a.P_rain.val + a.SM.val) + a.GW.val) + a.MR.val) - (0.0 + a.IN.val);
+        k.R_uniform = R;
+        k.Rdadt_uniform = (R * a.da.val) * a.dt;
+    }
+#define TFB_GENERIC(DW_, LOW_, DIAG_, SRC_)                                        \
     if (dw == DW_ && low == LOW_ && diag == DIAG_ && src == SRC_)                  \
-        return launch<VEC, DW_, LOW_, DIAG_, SRC_>(a, k, st);
-    TFB_DISPATCH(false, false, false, false) TFB_DISPATCH(false, false, false, true)
-    TFB_DISPATCH(false, false, true, false)  TFB_DISPATCH(false, false, true, true)
-    TFB_DISPATCH(false, true, false, false)  TFB_DISPATCH(false, true, false, true)
-    TFB_DISPATCH(false, true, true, false)   TFB_DISPATCH(false, true, true, true)
-    TFB_DISPATCH(true, false, false, false)  TFB_DISPATCH(true, false, false, true)
-    TFB_DISPATCH(true, false, true, false)   TFB_DISPATCH(true, false, true, true)
-    TFB_DISPATCH(true, true, false, false)   TFB_DISPATCH(true, true, false, true)
-    TFB_DISPATCH(true, true, true, false)    TFB_DISPATCH(true, true, true, true)
-#undef TFB_DISPATCH
+        return launch<VEC, DW_, LOW_, DIAG_, SRC_, false, false>(a, k, st);
+#define TFB_FAST(DW_, DIAG_, SRC_, UR_)                                            \
+    if (VEC == 2 && gp && ur == UR_ && dw == DW_ && diag == DIAG_ && src == SRC_)  \
+        return launch<2, DW_, false, DIAG_, SRC_, true, UR_>(a, k, st);
+    TFB_FAST(false, false, false, true)  TFB_FAST(false, false, false, false)
+    TFB_FAST(false, false, true, false)  TFB_FAST(false, true, false, true)
+    TFB_FAST(false, true, false, false)  TFB_FAST(false, true, true, false)
+    TFB_FAST(true, false, false, true)   TFB_FAST(true, false, false, false)
+    TFB_FAST(true, false, true, false)   TFB_FAST(true, true, false, true)
+    TFB_FAST(true, true, false, false)   TFB_FAST(true, true, true, false)
+    TFB_GENERIC(false, false, false, false) TFB_GENERIC(false, false, false, true)
+    TFB_GENERIC(false, false, true, false)  TFB_GENERIC(false, false, true, true)
+    TFB_GENERIC(false, true, false, false)  TFB_GENERIC(false, true, false, true)
+    TFB_GENERIC(false, true, true, false)   TFB_GENERIC(false, true, true, true)
+    TFB_GENERIC(true, false, false, false)  TFB_GENERIC(true, false, false, true)
+    TFB_GENERIC(true, false, true, false)   TFB_GENERIC(true, false, true, true)
+    TFB_GENERIC(true, true, false, false)   TFB_GENERIC(true, true, false, true)
+    TFB_GENERIC(true, true, true, false)    TFB_GENERIC(true, true, true, true)
+#undef TFB_GENERIC
+#undef TFB_FAST
     return TFB_ERR_ARG;
 }
 

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libtfb_b200.so')
+LIB_PATH = (os.environ.get('TFB_LIB_PATH') or os.path.join(_HERE, 'libtfb_b200.so'))  # override: kernel experiments
 
 c_dbl_p = C.POINTER(C.c_double)
 c_flt_p = C.POINTER(C.c_float)
