@@ -100,6 +100,10 @@ struct Cell {
     unsigned code, cmask;
     double ds, da, width, tan_a, cos_a;
     double vol, Q;
+    double I, h_swe;          // fused-source state in (read by the caller)
+};
+struct SrcState {             // fused-source state out (written by the caller)
+    double I, h_swe;
 };
 
 struct Src {
@@ -111,7 +115,8 @@ struct Src {
 // parent's inflow (no state update, no integrals)
 template <bool SRC, bool COMMIT>
 __device__ __forceinline__ void eval_sources(const tfb_channels_step_args &a, int64_t i,
-                                             double da, Src &s, Acc *acc) {
+                                             const Cell &g, Src &s, SrcState &ns, Acc *acc) {
+    const double da = g.da;
     const double dt = a.dt;
     s.GW = sg_at(a.GW, i);
     s.MR = sg_at(a.MR, i);
@@ -141,7 +146,7 @@ __device__ __forceinline__ void eval_sources(const tfb_channels_step_args &a, in
     // --- snow: degree-day (snow_degree_day.py:293-360, snow_base.py:490-703) --
     if (a.flags & TFB_CH_SRC_SNOW) {
         const double Ta = sg_at(a.T_air, i);
-        const double h = __ldg(a.h_swe + i);
+        const double h = g.h_swe;
         double M = (sg_at(a.c0, i) / 8.64E7) * (Ta - sg_at(a.T0, i));
         M = np_min(M, h / dt);
         M = np_max(M, 0.0);
@@ -150,8 +155,7 @@ __device__ __forceinline__ void eval_sources(const tfb_channels_step_args &a, in
             double hn = h + (P_snow * dt);
             hn = hn - (M * dt);
             hn = np_max(hn, 0.0);
-            a.h_swe_out[i] = hn;
-            if (a.h_snow) a.h_snow[i] = hn * (a.rho_H2O / a.rho_snow);
+            ns.h_swe = hn;
             acc->s[S_VOL_SM] += (M * da) * dt;
         }
     } else {
@@ -176,7 +180,7 @@ __device__ __forceinline__ void eval_sources(const tfb_channels_step_args &a, in
         const double P_total = s.P_rain + s.SM;
         const double dK = Ks - sg_at(a.Ki, i);
         const double dq = sg_at(a.qs, i) - sg_at(a.qi, i);
-        const double Iv = __ldg(a.I + i);
+        const double Iv = g.I;
         const double fc = (((sg_at(a.G, i) * dK) * dq) / Iv) + Ks;
         double IN = np_min(fc, P_total);
         if (P_total < Ks) IN = P_total;                       // infil_base.py:954-995
@@ -185,7 +189,7 @@ __device__ __forceinline__ void eval_sources(const tfb_channels_step_args &a, in
         }
         s.IN = IN;
         if (COMMIT) {
-            a.I_out[i] = Iv + (IN * dt);
+            ns.I = Iv + (IN * dt);
             acc->s[S_VOL_IN] += (IN * da) * dt;
             if (!isfinite(IN)) acc->n[S_NNAN_IN - kNSum] += 1u;
         }
@@ -207,6 +211,8 @@ __device__ __forceinline__ void load_cell_scalar(const tfb_channels_step_args &a
     g.cos_a = sg_at(a.cos_angle, i);
     g.vol = __ldg(a.vol + i);
     g.Q = __ldg(a.Q_in + i);
+    g.I = (a.flags & TFB_CH_SRC_INFIL) ? __ldg(a.I + i) : 0.0;
+    g.h_swe = (a.flags & TFB_CH_SRC_SNOW) ? __ldg(a.h_swe + i) : 0.0;
 }
 
 // new volume (before the noflow zeroing) and new depth of a cell ---------------
@@ -214,7 +220,8 @@ template <bool SRC, bool UR, bool COMMIT>
 __device__ __forceinline__ void vol_depth(const tfb_channels_step_args &a, const ChConsts &kc,
                                           int64_t i, const Cell &g,
                                           const double *__restrict__ Qc, double &vol_new,
-                                          double &d_new, double &R_out, Acc *acc) {
+                                          double &d_new, double &R_out, SrcState &ns,
+                                          Acc *acc) {
     const double dt = a.dt;
     double v;
     if (UR) {
@@ -224,7 +231,7 @@ __device__ __forceinline__ void vol_depth(const tfb_channels_step_args &a, const
         v = g.vol + kc.Rdadt_uniform;                                // :2086
     } else {
         Src s;
-        eval_sources<SRC, COMMIT>(a, i, g.da, s, acc);
+        eval_sources<SRC, COMMIT>(a, i, g, s, ns, acc);
         // update_R :1625-1649
         double ET = s.ET;
         if (s.ET_is_grid) {
@@ -308,8 +315,9 @@ __device__ __forceinline__ void finish_cell(const tfb_channels_step_args &a,
             Cell gp;
             load_cell_scalar(a, pr, ip, gp);
             double Qc[8], vp, Rp;
+            SrcState nsp;
             load_children(a.Q_in + ip, a.nx, gp.cmask, Qc);
-            vol_depth<SRC, UR, false>(a, k, ip, gp, Qc, vp, d_par, Rp, nullptr);
+            vol_depth<SRC, UR, false>(a, k, ip, gp, Qc, vp, d_par, Rp, nsp, nullptr);
         }
         S = slope_in + ((d - d_par) / g.ds);
         sqrtS = sqrt(fabs(S));
@@ -482,6 +490,11 @@ channels_step_kernel(const tfb_channels_step_args a, const ChConsts k) {
                 sn = ldsg<VEC>(a.sinu, i);
             }
             const V<VEC> sl = ldv<VEC>((DW || DIAG || LOW) ? a.S_bed : a.sqrtS, i);
+            V<VEC> Iin, hin, Iout, hout;
+            const bool f_infil = SRC && (a.flags & TFB_CH_SRC_INFIL);
+            const bool f_snow = SRC && (a.flags & TFB_CH_SRC_SNOW);
+            if (f_infil) Iin = ldv<VEC>(a.I, i);
+            if (f_snow) hin = ldv<VEC>(a.h_swe, i);
             const float dxr = __ldg(a.dx + r), dyr = __ldg(a.dy + r), ddr = __ldg(a.dd + r);
             const double dar = (GP || !a.da.ptr) ? a.da.val : __ldg(a.da.ptr + r);
             // ---- children's discharge: predicated loads --------------------
@@ -500,8 +513,12 @@ channels_step_kernel(const tfb_channels_step_args a, const ChConsts k) {
                 g.da = dar;
                 g.width = wid.v[j]; g.tan_a = tn.v[j]; g.cos_a = cs.v[j];
                 g.vol = vol.v[j]; g.Q = Qo.v[j];
+                g.I = f_infil ? Iin.v[j] : 0.0;
+                g.h_swe = f_snow ? hin.v[j] : 0.0;
                 double v, d, R;
-                vol_depth<SRC, UR, true>(a, k, i + j, g, Qc[j], v, d, R, &acc);
+                SrcState ns;
+                vol_depth<SRC, UR, true>(a, k, i + j, g, Qc[j], v, d, R, ns, &acc);
+                if (SRC) { Iout.v[j] = ns.I; hout.v[j] = ns.h_swe; }
                 CellOut o;
                 finish_cell<DW, LOW, DIAG, SRC, UR>(a, k, r, c0 + j, i + j, g, v, d, sl.v[j],
                                                 rg.v[j], acc, o);
@@ -512,6 +529,16 @@ channels_step_kernel(const tfb_channels_step_args a, const ChConsts k) {
                     o_S.v[j] = o.S;
                 }
                 o_R.v[j] = R;
+            }
+            if (f_infil) stv<VEC>(a.I_out, i, Iout);
+            if (f_snow) {
+                stv<VEC>(a.h_swe_out, i, hout);
+                if (a.h_snow) {
+                    V<VEC> hs;
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) hs.v[j] = hout.v[j] * (a.rho_H2O / a.rho_snow);
+                    stv<VEC>(a.h_snow, i, hs);
+                }
             }
             stv<VEC>(a.vol_out, i, o_vol);
             stv<VEC>(a.d, i, o_d);
@@ -727,7 +754,8 @@ extern "C" int tfb_channels_step(const tfb_channels_step_args *ap, void *stream)
                       al16(a.cos_angle.ptr) && al16(a.rough.ptr) && al16(a.sinu.ptr) &&
                       al16(a.Rh) && al16(a.A_wet) && al16(a.P_wet) && al16(a.f) &&
                       al16(a.tau) && al16(a.u_star) && al16(a.froude) && al16(a.S_free) &&
-                      al16(a.R) && ((((uintptr_t)a.geo) & 3u) == 0);
+                      al16(a.R) && al16(a.I) && al16(a.I_out) && al16(a.h_swe) && al16(a.h_swe_out) &&
+                      al16(a.h_snow) && ((((uintptr_t)a.geo) & 3u) == 0);
     return vec2 ? dispatch<2>(a, k, st) : dispatch<1>(a, k, st);
 }
 
