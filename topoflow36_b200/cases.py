@@ -1,0 +1,94 @@
+"""Seeded synthetic routing workloads built straight on the device
+for benchmarks and large-grid tests: fractal DEM -> GPU D8 toolkit -> channel
+parameters -> ChannelsEngine.  The same generator feeds every rank of a
+row-slab run: rank k owns rows [k*ny, (k+1)*ny) of a (world*ny, nx) grid whose
+noise tile repeats every `ny` rows on top of a global tilt, so the slabs join
+into ONE drainage network (flow crosses the slab boundaries).
+
+Parameters follow SURVEY.md 8d: dx = dy = 30 m, width = 1 + 4 U(0,1) m, bank
+angle 45 deg, Manning n = 0.03 + 0.02 U(0,1) -- float32 values, as they would
+sit in RTG files -- uniform rain 50 mm/h, dt = 1 s, Green-Ampt scalars of the
+Treynor CFG (Ks=7.2e-6, Ki=1e-7, qs=0.485, qi=0.375808, G=0.724, I0=1e-6).
+"""
+import numpy as np
+
+from . import synth
+
+GA_TREYNOR = dict(Ks=7.2e-6, Ki=1e-7, qs=0.485, qi=0.375808, G=0.724)
+RAIN_50MMPH = 50.0 / 3.6e6
+
+
+def noise_tile(ny, nx, seed=1234, sigma=2.0, beta=2.2):
+    """Periodic fractal noise (zero mean) of one slab, float64 on the host."""
+    z = synth.fractal_dem(ny, nx, seed=seed, sy=0.0, sx=0.0, sigma=sigma, beta=beta, z0=0.0)
+    return np.float64(z)
+
+
+def slab_dem(ny, nx, row0, ny_global, halo, tile, sy=0.02, sx=0.005, dx=30.0, dy=30.0,
+             sigma=2.0):
+    """float32 DEM rows [row0 - halo, row0 + ny + halo) of the global grid; rows
+    outside the grid repeat the nearest valid row's formula (they are never
+    owned, only read by the border stencil, whose result is forced to code 0)."""
+    r = np.arange(row0 - halo, row0 + ny + halo, dtype=np.float64)[:, None]
+    c = np.arange(nx, dtype=np.float64)[None, :]
+    z0 = sy * dy * ny_global + sx * dx * nx + 10.0 * sigma + 100.0
+    t = tile[np.mod(np.arange(row0 - halo, row0 + ny + halo), tile.shape[0])]
+    return np.float32(z0 - sy * dy * r - sx * dx * c + t)
+
+
+def slab_params(ny, nx, row0, halo, seed=1234):
+    """width, angle [deg], nval for the rows of a slab incl. halo (float32).
+    Halo rows only matter for the diffusive wave (parent depth re-derivation), so
+    they must equal what the owning rank generates: the stream is keyed by the
+    GLOBAL row."""
+    rows = np.arange(row0 - halo, row0 + ny + halo)
+    width = np.empty((rows.size, nx), dtype=np.float32)
+    nval = np.empty((rows.size, nx), dtype=np.float32)
+    # one Philox stream per 1024-row band keeps generation O(slab)
+    band = 1024
+    for b in np.unique(rows // band):
+        rng = np.random.Generator(np.random.Philox(key=int(seed) + 7919 * (int(b) + 1)))
+        w = rng.random((band, nx), dtype=np.float32)
+        n = rng.random((band, nx), dtype=np.float32)
+        sel = (rows // band) == b
+        idx = rows[sel] - b * band
+        width[sel] = np.float32(1.0) + np.float32(4.0) * w[idx]
+        nval[sel] = np.float32(0.03) + np.float32(0.02) * n[idx]
+    angle = np.full((rows.size, nx), 45.0, dtype=np.float32)
+    return width, angle, nval
+
+
+def build_engine(ny, nx, kinematic=True, infil=False, diag=False, dt=1.0, rank=0, world=1,
+                 seed=1234, device=None, group=None, link_flats=True, return_parts=False,
+                 tile_rows=None):
+    """Engine (and SlabChannels wrapper when world > 1) for rank `rank` of a
+    (world*ny, nx) synthetic grid."""
+    import torch
+    from .routing import ChannelsEngine
+    from .slab import SlabLayout, SlabChannels, slab_d8
+    ny_global = ny * world
+    halo = 0 if world == 1 else (1 if kinematic else 2)
+    lay = SlabLayout(ny_global, nx, rank, world, halo)
+    tile = noise_tile(tile_rows or ny, nx, seed=seed)
+    hd = halo + 1 if world > 1 else 0             # DEM halo: one more row than the codes need
+    DEM = slab_dem(ny, nx, lay.row0, ny_global, hd, tile)
+    d8 = slab_d8(DEM, lay, hd, link_flats=link_flats, device=device, group=group)
+    width, angle, nval = slab_params(ny, nx, lay.row0, halo, seed=seed)
+    DEG = np.pi / np.float64(180)
+    ang = np.float64(angle) * DEG
+    eng = ChannelsEngine(ny, nx, dt=dt, code=d8['code'], dx=d8['dx'], dy=d8['dy'], dd=d8['dd'],
+                         S_bed=d8['S_bed'], width=np.float64(width), angle=ang,
+                         rough=np.float64(nval), kinematic=kinematic, diag=diag,
+                         outlet=(ny_global - 2, nx // 2), row0=lay.row0, ny_global=ny_global,
+                         halo=halo, device=device, finalize=True,
+                         n_pixels_global=ny * nx)
+    eng.set_input('P_rain', RAIN_50MMPH)
+    if infil:
+        eng.enable_fused_sources(infil=True, I0=1e-6)
+        for k, v in GA_TREYNOR.items():
+            eng.set_input(k, v)
+    torch.cuda.current_stream().synchronize()
+    stepper = SlabChannels(lay, eng, group) if world > 1 else eng
+    if return_parts:
+        return stepper, dict(DEM=DEM, d8=d8, width=width, angle=angle, nval=nval, layout=lay)
+    return stepper

@@ -1,0 +1,630 @@
+"""GPU Channels component: drop-in for the reference's ``channels_component``.
+
+Mirrors ``topoflow/components/channels_base.py`` (class ``channels_component``
+:181): the same BMI surface (``initialize`` :633, ``update`` :803, ``finalize``
+:964, the CSDMS long names / short names / units of :186-468), driven by the same
+``<case>_channels_*.cfg`` + ``<case>_d8_global.cfg`` + RTI/RTG files -- but the
+state lives in torch CUDA tensors and every ``update()`` is ONE launch of the
+fused sm_100a routing kernel through the C ABI (``tfb_channels_step``,
+include/tfb.h).  There is no CPU path: without the CUDA library/device
+``initialize()`` raises ``TfbError``.
+
+What the caller sees:
+  * the 7 inputs arrive through ``set_value`` as 0-D numpy arrays, (ny, nx)
+    numpy grids (copied host->device each update) or CUDA tensors (used in place);
+  * outlet / peak / integral scalars are 0-D numpy arrays refreshed IN PLACE after
+    every update by one small device->host copy (``tfb_channels_scalars``), so
+    EMELI users holding references (e.g. topoflow_driver reading Q_outlet for its
+    stop rule) see them change;
+  * grids (Q, d, u, vol, ...) are numpy mirrors fetched from the device when the
+    attribute is read; a grid handed out by ``get_value_ptr`` is re-filled in
+    place after every update (EMELI's by-reference convention);
+    ``get_value_tensor`` returns the device tensor itself;
+  * the provider's ET grid is zeroed in place where ``vol < ET*da*dt``
+    (channels_base.py:1625-1627), on the device and -- for a numpy provider --
+    copied back into the provider's array;
+  * ``CHECK_STABILITY`` raises the reference's RuntimeErrors (:3275, :3429) from
+    the bad-value counters the kernel returns.
+Not handled (raise NotImplementedError): FLOOD_OPTION, ATTENUATE,
+dynamic wave.
+"""
+import os
+
+import numpy as np
+
+from . import BMI_base, grid_io
+from . import lib as L
+
+_IN = [
+    ('atmosphere_water__rainfall_volume_flux', 'P_rain', 'm s-1'),
+    ('glacier_ice__melt_volume_flux', 'MR', 'm s-1'),
+    ('land_surface_water__baseflow_volume_flux', 'GW', 'm s-1'),
+    ('land_surface_water__evaporation_volume_flux', 'ET', 'm s-1'),
+    ('soil_surface_water__infiltration_volume_flux', 'IN', 'm s-1'),
+    ('snowpack__melt_volume_flux', 'SM', 'm s-1'),
+    ('water-liquid__mass-per-volume_density', 'rho_H2O', 'kg m-3')]
+
+_OUT = [
+    ('basin_outlet_water_flow__half_of_fanning_friction_factor', 'f_outlet', '1'),
+    ('basin_outlet_water_x-section__mean_depth', 'd_outlet', 'm'),
+    ('basin_outlet_water_x-section__peak_time_of_depth', 'Td_peak', 'min'),
+    ('basin_outlet_water_x-section__peak_time_of_volume_flow_rate', 'T_peak', 'min'),
+    ('basin_outlet_water_x-section__peak_time_of_volume_flux', 'Tu_peak', 'min'),
+    ('basin_outlet_water_x-section__time_integral_of_volume_flow_rate', 'vol_Q', 'm3'),
+    ('basin_outlet_water_x-section__time_max_of_mean_depth', 'd_peak', 'm'),
+    ('basin_outlet_water_x-section__time_max_of_volume_flow_rate', 'Q_peak', 'm3 s-1'),
+    ('basin_outlet_water_x-section__time_max_of_volume_flux', 'u_peak', 'm s-1'),
+    ('basin_outlet_water_x-section__volume_flow_rate', 'Q_outlet', 'm3 s-1'),
+    ('basin_outlet_water_x-section__volume_flux', 'u_outlet', 'm s-1'),
+    ('canals_entrance_water__volume_flow_rate', 'Q_canals_in', 'm3 s-1'),
+    ('channel_bottom_surface__slope', 'S_bed', '1'),
+    ('channel_bottom_water_flow__domain_max_of_log_law_roughness_length', 'z0val_max', 'm'),
+    ('channel_bottom_water_flow__domain_min_of_log_law_roughness_length', 'z0val_min', 'm'),
+    ('channel_bottom_water_flow__log_law_roughness_length', 'z0val', 'm'),
+    ('channel_bottom_water_flow__magnitude_of_shear_stress', 'tau', 'kg m-1 s-2'),
+    ('channel_bottom_water_flow__shear_speed', 'u_star', 'm s-1'),
+    ('channel_centerline__sinuosity', 'sinu', '1'),
+    ('channel_water__volume', 'vol', 'm3'),
+    ('channel_water_flow__froude_number', 'froude', '1'),
+    ('channel_water_flow__half_of_fanning_friction_factor', 'f', '1'),
+    ('channel_water_flow__domain_max_of_manning_n_parameter', 'nval_max', 'm-1/3 s'),
+    ('channel_water_flow__domain_min_of_manning_n_parameter', 'nval_min', 'm-1/3 s'),
+    ('channel_water_flow__manning_n_parameter', 'nval', 'm-1/3 s'),
+    ('channel_water_surface__slope', 'S_free', '1'),
+    ('channel_water_x-section__domain_max_of_mean_depth', 'd_max', 'm'),
+    ('channel_water_x-section__domain_min_of_mean_depth', 'd_min', 'm'),
+    ('channel_water_x-section__domain_max_of_volume_flow_rate', 'Q_max', 'm3 s-1'),
+    ('channel_water_x-section__domain_min_of_volume_flow_rate', 'Q_min', 'm3 s-1'),
+    ('channel_water_x-section__domain_max_of_volume_flux', 'u_max', 'm s-1'),
+    ('channel_water_x-section__domain_min_of_volume_flux', 'u_min', 'm s-1'),
+    ('channel_water_x-section__hydraulic_radius', 'Rh', 'm'),
+    ('channel_water_x-section__initial_mean_depth', 'd0', 'm'),
+    ('channel_water_x-section__mean_depth', 'd', 'm'),
+    ('channel_water_x-section__volume_flow_rate', 'Q', 'm3 s-1'),
+    ('channel_water_x-section__volume_flux', 'u', 'm s-1'),
+    ('channel_water_x-section__wetted_area', 'A_wet', 'm2'),
+    ('channel_water_x-section__wetted_perimeter', 'P_wet', 'm'),
+    ('channel_water_x-section_top__width', 'w_top', 'm'),
+    ('channel_x-section_trapezoid_bottom__width', 'width', 'm'),
+    ('channel_x-section_trapezoid_side__flare_angle', 'angle', 'rad'),
+    ('land_surface_water__depth', 'df', 'm'),
+    ('land_surface_water__runoff_volume_flux', 'R', 'm s-1'),
+    ('land_surface_water__domain_time_integral_of_runoff_volume_flux', 'vol_R', 'm3'),
+    ('model__time_step', 'dt', 's'),
+    ('model_grid_cell__area', 'da', 'm2'),
+    ('channel_water_x-section__boundary_time_integral_of_volume_flow_rate', 'vol_edge', 'm3'),
+    ('river-network_channel_water__initial_volume', 'vol_chan_sum0', 'm3'),
+    ('river-network_channel_water__volume', 'vol_chan_sum', 'm3'),
+    ('land_surface_water__area_integral_of_depth', 'vol_flood_sum', 'm3')]
+
+# names the reference also maps although they are neither inputs nor outputs
+_EXTRA = [
+    ('channel_water_x-section__bankfull_depth', 'd_bankfull', 'm'),
+    ('canals__count', 'n_canals', '1'), ('sinks__count', 'n_sinks', '1'),
+    ('sources__count', 'n_sources', '1')]
+
+_SCALAR_BLOCK = ('vol_R', 'vol_Q', 'vol_edge', 'Q_outlet', 'u_outlet', 'd_outlet',
+                 'f_outlet', 'Q_peak', 'T_peak', 'u_peak', 'Tu_peak', 'd_peak', 'Td_peak')
+_SRC_INPUTS = ('P_rain', 'SM', 'GW', 'MR', 'ET', 'IN')
+_DIAG = ('Rh', 'A_wet', 'P_wet', 'f', 'tau', 'u_star', 'froude')
+# attribute -> how to find the device tensor (state & diagnostics)
+_DEVICE_GRIDS = ('Q', 'Qc', 'vol', 'vol_chan', 'd', 'u', 'R', 'S_free') + _DIAG
+
+
+class channels_component(BMI_base.BMI_component):
+
+    _input_var_names = [t[0] for t in _IN]
+    _output_var_names = [t[0] for t in _OUT]
+    _var_name_map = {t[0]: t[1] for t in _IN + _OUT + _EXTRA}
+    _var_units_map = {t[0]: t[2] for t in _IN + _OUT + _EXTRA}
+
+    def __init__(self):
+        BMI_base.BMI_component.__init__(self)
+        self.engine = None
+        self.device = None            # torch device; default = current CUDA device
+        self._mirrors = {}            # grid name -> numpy array handed out by reference
+        self._exported = set()        # grid names refreshed after every update
+        self.SYNC_SCALARS = True      # D2H the scalar block after every update
+        self.DIAGNOSTICS = False      # materialise Rh, A_wet, ... every step
+        self._fused = None
+
+    # ---------------------------------------------------------------- attributes
+    def __getattr__(self, name):
+        # only reached when normal lookup fails: device-backed grids
+        if name in _DEVICE_GRIDS and self.__dict__.get('engine') is not None:
+            return self._fetch(name)
+        raise AttributeError(name)
+
+    def _device_tensor(self, name):
+        e = self.engine
+        if name in ('Q', 'Qc'):
+            return e.Q
+        if name in ('vol', 'vol_chan'):
+            return e.vol
+        if name in ('d', 'u'):
+            return e.own(getattr(e, name))
+        if name == 'R':
+            if getattr(e, 'R', None) is None:
+                raise AttributeError('R grid is not materialised; set WRITE_R = True '
+                                     'before initialize()')
+            return e.own(e.R)
+        if name == 'S_free':
+            if e.kinematic:
+                return e.own(e.S_bed)
+            self._need_diag()
+            return e.own(e.S_free)
+        if name in _DIAG:
+            self._need_diag()
+            return e.own(getattr(e, name))
+        raise AttributeError(name)
+
+    def _need_diag(self):
+        if not self.engine.diag:
+            raise AttributeError(
+                'diagnostic grids (Rh, A_wet, P_wet, f, tau, u_star, froude, S_free) are '
+                'only materialised when DIAGNOSTICS is True before initialize() or one of '
+                'them was requested through get_value_ptr() before the first update')
+
+    def _fetch(self, name):
+        """numpy mirror of a device grid, refreshed now (same array object every
+        time, so references stay valid)."""
+        t = self._device_tensor(name)
+        m = self._mirrors.get(name)
+        if m is None or m.shape != tuple(t.shape):
+            m = np.empty(tuple(t.shape), dtype='float64')
+            self._mirrors[name] = m
+        import torch
+        torch.from_numpy(m).copy_(t)
+        return m
+
+    def get_value_tensor(self, long_var_name):
+        """Device tensor behind a grid variable (zero copy; GPU-aware users)."""
+        return self._device_tensor(self.get_var_name(long_var_name))
+
+    def get_value_ptr(self, long_var_name):
+        name = self.get_var_name(long_var_name)
+        if name in _DEVICE_GRIDS and self.engine is not None:
+            if name in _DIAG or (name == 'S_free' and not self.engine.kinematic):
+                if not self.engine.diag and self.engine.n_steps == 0:
+                    self._enable_diag()
+            self._exported.add(name)
+            return self._fetch(name)
+        return getattr(self, name)
+
+    # ---------------------------------------------------------------- constants
+    def set_constants(self):
+        self.g = np.float64(9.81)
+        self.aval = np.float64(0.476)
+        self.kappa = np.float64(0.408)
+        self.law_const = np.sqrt(self.g) / self.kappa
+        self.deg_to_rad = np.pi / np.float64(180)
+        self.rad_to_deg = np.float64(180) / np.pi
+        self.mmph_to_mps = 1.0 / (3600.0 * 1000.0)
+
+    def set_missing_cfg_options(self):
+        dflt = dict(CHECK_STABILITY=True, FLOOD_OPTION=False, ATTENUATE=False,
+                    d_bankfull_type='Scalar', CREATE_CHANNEL_FILES=False,
+                    slope_factor=1.0, nval_factor=1.0, z0val_factor=1.0, width_factor=1.0,
+                    angle_factor=1.0, sinu_factor=1.0, d0_factor=1.0, d_bankfull_factor=1.0,
+                    MANNING=1, LAW_OF_WALL=0, WRITE_R=False)
+        for k, v in dflt.items():
+            if not hasattr(self, k):
+                setattr(self, k, v)
+        if not hasattr(self, 'd_bankfull'):
+            self.d_bankfull = self.initialize_scalar(10.0)
+            self.d_bankfull_file = ''
+        for k in ('Q', 'U', 'D', 'F'):
+            for kind in ('GRIDS', 'PIXELS'):
+                if not hasattr(self, 'SAVE_%s_%s' % (k, kind)):
+                    setattr(self, 'SAVE_%s_%s' % (k, kind), False)
+        for k in ('save_grid_dt', 'save_pixels_dt'):
+            if not hasattr(self, k):
+                setattr(self, k, self.initialize_scalar(60.0))
+        self.MANNING = bool(int(self.MANNING))
+        self.LAW_OF_WALL = bool(int(self.LAW_OF_WALL))
+        if self.FLOOD_OPTION not in (False, 0):
+            raise NotImplementedError('FLOOD_OPTION (overbank flow) is not part of the GPU '
+                                      'path yet (SURVEY.md 8f-1)')
+        if self.ATTENUATE not in (False, 0):
+            raise NotImplementedError('ATTENUATE (Nash reservoir runoff) is not part of the '
+                                      'GPU path')
+        if self.CREATE_CHANNEL_FILES not in (False, 0):
+            raise NotImplementedError('CREATE_CHANNEL_FILES is input preparation '
+                                      '(SURVEY.md 8f-3), not part of the GPU path')
+
+    def set_computed_input_vars(self):
+        ext = self.get_attribute('cfg_extension').lower()
+        self.KINEMATIC_WAVE = 'kinematic' in ext
+        self.DIFFUSIVE_WAVE = 'diffusive' in ext
+        self.DYNAMIC_WAVE = 'dynamic' in ext
+        if self.DYNAMIC_WAVE:
+            raise NotImplementedError('dynamic wave is broken in the reference '
+                                      '(channels_dynamic_wave.py:164) and not provided')
+        self.code_type = 'Grid'
+        self.slope_type = 'Grid'
+        np.maximum(self.save_grid_dt, self.dt, out=self.save_grid_dt)
+        np.maximum(self.save_pixels_dt, self.dt, out=self.save_pixels_dt)
+
+    # ---------------------------------------------------------------- initialize
+    def initialize(self, cfg_file=None, mode='nondriver', SILENT=False):
+        self.SILENT = SILENT
+        if not SILENT:
+            print(' ')
+            print('Channels component (B200): Initializing...')
+        self.status = 'initializing'
+        self.mode, self.cfg_file = mode, cfg_file
+        L.load()                              # fail loudly if the CUDA library is absent
+        import torch
+        if not torch.cuda.is_available():
+            raise L.TfbError('the GPU Channels component needs a CUDA device; there is '
+                             'no CPU fallback')
+        self.set_constants()
+        self.initialize_config_vars()
+        self.set_missing_cfg_options()
+        self.initialize_basin_vars()
+        self.initialize_time_vars()
+        self._init_host_scalars()
+        if self.comp_status.lower() == 'disabled':
+            if not SILENT:
+                print('Channels component: Disabled in CFG file.')
+            self.DONE = True
+            self.status = 'initialized'
+            return
+        self.set_computed_input_vars()
+        self.initialize_d8_vars()
+        self.read_input_files()
+        self.initialize_computed_vars()
+        self.open_output_files()
+        self.status = 'initialized'
+
+    def _init_host_scalars(self):
+        z = lambda v=0.0: self.initialize_scalar(v, dtype='float64')
+        for n in _SCALAR_BLOCK:
+            setattr(self, n, z())
+        for n in ('vol_chan_sum', 'vol_chan_sum0', 'vol_flood_sum', 'Q_canals_in'):
+            setattr(self, n, z())
+        for n in ('Q_min', 'u_min', 'd_min'):
+            setattr(self, n, z(1e6))
+        for n in ('Q_max', 'u_max', 'd_max'):
+            setattr(self, n, z(-1e6))
+        for n in _SRC_INPUTS:
+            if not hasattr(self, n):
+                setattr(self, n, z())
+        if not hasattr(self, 'rho_H2O'):
+            self.rho_H2O = z(1000.0)
+        self.dt_cfl_min = z()
+        self.bad_counts = dict(n_neg_d=0, n_nan_d=0, n_inf_d=0, n_neg_u=0, n_nan_u=0,
+                               n_inf_u=0)
+
+    def initialize_d8_vars(self):
+        """channels_base.py:1074-1135: an embedded D8 component on the same DEM."""
+        from . import d8_global
+        self.d8 = d8_global.d8_component()
+        self.d8.device = self.device
+        cfg = self.cfg_directory + self.case_prefix + '_d8_global.cfg'
+        self.d8.initialize(cfg_file=cfg, SILENT=self.SILENT, REPORT=self.REPORT)
+        self.d8.update(self.time, REPORT=self.REPORT)
+
+    def _read_var(self, name, factor):
+        vtype = getattr(self, name + '_type', 'Scalar').lower()
+        if vtype == 'scalar':
+            v = getattr(self, name)
+            v = np.float64(v) if np.ndim(v) == 0 else v
+            if factor != 1.0:
+                v = v * factor
+            return np.array(v, dtype='float64')
+        if vtype not in ('grid', 'grid_sequence'):
+            raise RuntimeError('No match found for ' + vtype + '.')
+        path = self.topo_directory + getattr(self, name + '_file')
+        g = np.float64(grid_io.read_rtg(path, self.rti, 'FLOAT'))     # model_input.py:181
+        if factor != 1.0:
+            g *= factor
+        return g
+
+    def read_input_files(self):
+        """channels_base.py:3498-3558 (float32 on disk -> float64)."""
+        self.slope = self._read_var('slope', self.slope_factor)
+        if self.MANNING:
+            self.nval = self._read_var('nval', self.nval_factor)
+        if self.LAW_OF_WALL:
+            self.z0val = self._read_var('z0val', self.z0val_factor)
+        self.width = self._read_var('width', self.width_factor)
+        self.angle = self._read_var('angle', self.angle_factor)
+        self.sinu = self._read_var('sinu', self.sinu_factor)
+        self.d0 = self._read_var('d0', self.d0_factor)
+        if getattr(self, 'd_bankfull_type', 'Scalar').lower() == 'scalar' \
+                or os.path.exists(self.topo_directory + getattr(self, 'd_bankfull_file', '')):
+            self.d_bankfull = self._read_var('d_bankfull', self.d_bankfull_factor)
+
+    def initialize_computed_vars(self):
+        """channels_base.py:1137-1405, with the grids created on the device."""
+        import torch
+        from .routing import ChannelsEngine
+        z = lambda v=-1.0: self.initialize_scalar(v, dtype='float64')
+        if self.MANNING:
+            self.nval_min, self.nval_max = self.nval.min(), self.nval.max()
+            self.z0val, self.z0val_min, self.z0val_max = z(), z(), z()
+        elif self.LAW_OF_WALL:
+            self.z0val_min, self.z0val_max = self.z0val.min(), self.z0val.max()
+            self.nval, self.nval_min, self.nval_max = z(), z(), z()
+        else:
+            raise ValueError('In CFG file, MANNING=0 and LAW_OF_WALL=0.')
+        self.angle = self.angle * self.deg_to_rad                      # :1196
+        tk = self.d8.toolkit
+        if np.ndim(self.width) == 2:
+            w0 = (self.width == 0)                                     # :1206-1209
+            if w0.any():
+                self.width[w0] = tk.dw.cpu().numpy()[w0]
+        self.slope = self.slope / self.sinu                            # :1247
+        if self.KINEMATIC_WAVE:
+            self.remove_bad_slopes()                                   # :1316
+        self.S_bed = self.slope
+        rough = self.nval if self.MANNING else self.z0val
+        self.engine = ChannelsEngine(
+            self.ny, self.nx, dt=float(self.dt), code=tk.code, dx=tk.dx_host, dy=tk.dy_host,
+            dd=tk.dd_host, S_bed=self.S_bed, width=self.width, angle=self.angle,
+            tan_angle=np.tan(self.angle), cos_angle=np.cos(self.angle), rough=rough,
+            sinu=self.sinu if np.ndim(self.sinu) == 2 else float(self.sinu),
+            da=self.da, d0=self.d0 if np.ndim(self.d0) == 2 else float(self.d0),
+            kinematic=self.KINEMATIC_WAVE, manning=self.MANNING,
+            diag=bool(self.DIAGNOSTICS or self.SAVE_F_GRIDS or self.SAVE_F_PIXELS),
+            write_R=bool(self.WRITE_R), outlet=(int(self.outlet_ID[0]), int(self.outlet_ID[1])),
+            rho_H2O=float(self.rho_H2O), device=self.device)
+        if self._fused:
+            self.engine.enable_fused_sources(**self._fused)
+        self.update_total_channel_water_volume()
+        self.vol_chan_sum0 = self.vol_chan_sum.copy()
+        torch.cuda.current_stream().synchronize()
+
+    def _enable_diag(self):
+        """Switch the engine to the diagnostics kernel before the first step."""
+        import torch
+        e = self.engine
+        if e.diag:
+            return
+        z = lambda: e._zeros(torch.float64)
+        for n in _DIAG:
+            t = z()
+            setattr(e, n, t)
+            setattr(e.args, n, e._p(t))
+        if not e.kinematic:
+            e.S_free = z()
+            e.own(e.S_free).copy_(e.own(e.S_bed))
+            e.args.S_free = e._p(e.S_free)
+        e.diag = True
+        e.flags |= L.CH_DIAG
+        # initial A_wet / P_wet / Rh of the initial depth (channels_base :1331-1333)
+        d = e.own(e.d)
+        g = lambda name: (e.own(getattr(e, name + '_grid')) if getattr(e, name + '_grid')
+                          is not None else getattr(e.args, name).val)
+        e.own(e.A_wet).copy_(d * (g('width') + d * g('tan_angle')))
+        e.own(e.P_wet).copy_(g('width') + (2.0 * d) / g('cos_angle'))
+
+    def remove_bad_slopes(self):
+        """NaN / zero / negative / infinite slopes -> smallest good slope
+        (channels_base.py:4164-4260)."""
+        S = self.slope
+        bad = np.isnan(S) | (S == 0.0) | (S < 0.0) | np.isinf(S)
+        if not bad.any():
+            return
+        good = ~bad
+        if not good.any():
+            raise ValueError('remove_bad_slopes: no positive finite slope in the grid')
+        S_min = S[good].min()
+        S[bad] = S_min
+        if not self.SILENT:
+            print('WARNING: %d zero, negative or NaN slopes replaced with min(S) = %s'
+                  % (int(bad.sum()), S_min))
+        self.slope = np.float64(S)
+
+    def enable_fused_sources(self, **kw):
+        """Evaluate met / snow / evap / infil inside the routing kernel (north-star
+        fusion) instead of receiving their outputs.  Call before initialize() or
+        before the first update(); keyword arguments as
+        ChannelsEngine.enable_fused_sources; parameters are then bound with
+        set_source_input()."""
+        self._fused = dict(kw)
+        if self.engine is not None:
+            self.engine.enable_fused_sources(**self._fused)
+
+    def set_source_input(self, name, value):
+        """Bind a fused-source parameter/forcing (T_air, c0, T0, T_surf, Qn_SW,
+        Qn_LW, Ks, Ki, qs, qi, G, h_table, elev): scalar, numpy grid or CUDA tensor."""
+        self.engine.set_input(name, value)
+
+    # -------------------------------------------------------------------- update
+    def _bind_inputs(self):
+        import torch
+        e = self.engine
+        self._et_host = None
+        for n in _SRC_INPUTS:
+            v = getattr(self, n)
+            if isinstance(v, torch.Tensor):
+                e.set_input(n, v if v.dim() == 2 else float(v))
+            elif np.ndim(v) == 2:
+                e.set_input(n, v)
+                if n == 'ET':
+                    self._et_host = v
+            else:
+                e.set_input(n, float(v))
+        e.args.rho_H2O = float(self.rho_H2O)
+
+    def update(self, dt=-1.0):
+        if self.comp_status.lower() == 'disabled':
+            return
+        self.status = 'updating'
+        if self.mode == 'driver' and not self.SILENT:
+            self.print_time_and_value(self.Q_outlet, 'Q_out', '[m^3/s]')
+        self._bind_inputs()
+        self.engine.step(time_min=float(self.time_min))
+        if self._et_host is not None:
+            # provider's ET array is masked in place (channels_base.py:1625-1627)
+            import torch
+            torch.from_numpy(self._et_host).copy_(self.engine.own(self.engine.src['ET']))
+        OK = True
+        if self.SYNC_SCALARS or self.CHECK_STABILITY:
+            self.sync_scalars()
+            if self.CHECK_STABILITY:
+                OK = self.check_flow_depth() and self.check_flow_velocity()
+        for name in self._exported:
+            self._fetch(name)
+        self.write_output_files()
+        self.update_time(dt)
+        if OK:
+            self.status = 'updated'
+        else:
+            self.status = 'failed'
+            self.DONE = True
+
+    def sync_scalars(self):
+        """One D2H of tfb_channels_scalars into the 0-D arrays, in place."""
+        s = self.engine.read_scalars()
+        for n in _SCALAR_BLOCK:
+            getattr(self, n).fill(getattr(s, n))
+        self.dt_cfl_min.fill(s.dt_cfl_min)
+        for n in self.bad_counts:
+            self.bad_counts[n] = int(getattr(s, n))
+        return s
+
+    def _abort_banner(self, lines):
+        star = '*******************************************'
+        print(star)
+        print('ERROR: Simulation aborted.')
+        print(' ')
+        for ln in lines:
+            print(ln)
+        print('Time step may be too large for stability.')
+        print('Time step:      ' + str(self.dt) + ' [s]')
+        print('Try reducing timestep in channels CFG file.')
+        print(star)
+        print(' ')
+
+    def check_flow_depth(self):
+        b = self.bad_counts
+        if b['n_neg_d'] == 0 and b['n_inf_d'] == 0:        # :3218 (NaN alone passes)
+            return True
+        msg = []
+        if b['n_neg_d']:
+            msg.append('Found %d negative depths.' % b['n_neg_d'])
+        if b['n_nan_d']:
+            msg.append('Found %d NaN depths.' % b['n_nan_d'])
+        if b['n_inf_d']:
+            msg.append('Found %d infinite depths.' % b['n_inf_d'])
+        self._abort_banner(msg)
+        self.status = 'failed'
+        self.DONE = True
+        raise RuntimeError('Negative or NaN depth found.')
+
+    def check_flow_velocity(self):
+        b = self.bad_counts
+        if b['n_neg_u'] == 0 and b['n_nan_u'] == 0 and b['n_inf_u'] == 0:
+            return True
+        msg = []
+        if b['n_neg_u']:
+            msg.append('Found %d negative velocities.' % b['n_neg_u'])
+        if b['n_nan_u']:
+            msg.append('Found %d NaN velocities.' % b['n_nan_u'])
+        if b['n_inf_u']:
+            msg.append('Found %d infinite velocities.' % b['n_inf_u'])
+        self._abort_banner(msg)
+        self.status = 'failed'
+        self.DONE = True
+        raise RuntimeError('Found bad velocities.')
+
+    # ------------------------------------------------------------------ finalize
+    def update_total_channel_water_volume(self):
+        self._minmax()
+
+    def update_mins_and_maxes(self, REPORT=False):
+        self._minmax()
+
+    def _minmax(self):
+        """Q/u/d interior extrema and total channel volume (channels_base.py
+        :2986-3110) in one reduction kernel."""
+        import torch
+        e = self.engine
+        out = torch.zeros(7, dtype=torch.float64, device=e.device)
+        npart = e.lib.tfb_sources_partials_len()
+        part = torch.zeros(npart, dtype=torch.float64, device=e.device)
+        tick = torch.zeros(1, dtype=torch.int32, device=e.device)
+        Q = e.Q.contiguous()
+        L.check(e.lib.tfb_channels_minmax(
+            Q.data_ptr(), e.own(e.u).data_ptr(), e.own(e.d).data_ptr(), e.vol.data_ptr(),
+            e.ny, e.nx, out.data_ptr(), out[6:].data_ptr(), part.data_ptr(), tick.data_ptr(),
+            L.stream_ptr()), 'tfb_channels_minmax')
+        h = out.cpu().numpy()
+        if e.n_steps > 0:
+            for k, n in enumerate(('Q_min', 'Q_max', 'u_min', 'u_max', 'd_min', 'd_max')):
+                getattr(self, n).fill(h[k])
+        self.vol_chan_sum.fill(h[6])
+
+    def finalize(self):
+        if self.comp_status.lower() == 'disabled':
+            return
+        self.status = 'finalizing'
+        self.sync_scalars()
+        self.update_total_channel_water_volume()
+        self.update_mins_and_maxes()
+        if not self.SILENT:
+            self.print_final_report()
+        self.close_output_files()
+        self.status = 'finalized'
+
+    def print_final_report(self):
+        print('Channels component (B200): final report')
+        for n in ('Q_peak', 'T_peak', 'u_peak', 'd_peak', 'vol_Q', 'vol_R', 'vol_edge',
+                  'vol_chan_sum'):
+            print('   %-14s = %r' % (n, float(getattr(self, n))))
+
+    # -------------------------------------------------------------------- output
+    # Grid stacks as RTS (flat float32 frames) and outlet series as text -- the
+    # two writers of the reference that need no netCDF (utils/rts_files.py,
+    # utils/text_ts_files.py); frames are fetched from the device only when due.
+    def open_output_files(self):
+        self._out = {}
+        kinds = {'Q': 'Q', 'U': 'u', 'D': 'd', 'F': 'f'}
+        for K, v in kinds.items():
+            if getattr(self, 'SAVE_%s_GRIDS' % K):
+                f = getattr(self, v + '_gs_file', self.case_prefix + '_2D-' + v + '.nc')
+                path = self.out_directory + os.path.splitext(os.path.basename(f))[0] + '.rts'
+                os.makedirs(self.out_directory, exist_ok=True)
+                self._out[('gs', v)] = open(self._unique(path), 'wb')
+            if getattr(self, 'SAVE_%s_PIXELS' % K):
+                f = getattr(self, v + '_ts_file', self.case_prefix + '_0D-' + v + '.txt')
+                path = self.out_directory + os.path.splitext(os.path.basename(f))[0] + '.txt'
+                os.makedirs(self.out_directory, exist_ok=True)
+                fh = open(self._unique(path), 'w')
+                rows, cols = self.outlet_IDs
+                hdr = ['Time [min]'] + ['%s_%d_%d' % (v, r, c) for r, c in zip(rows, cols)]
+                fh.write(''.join(h.rjust(15) for h in hdr) + '\n')
+                fh.write('-' * (15 * len(hdr)) + '\n')
+                self._out[('ts', v)] = fh
+
+    def _unique(self, path):
+        if self.OVERWRITE_OK or not os.path.exists(path):
+            return path
+        stem, ext = os.path.splitext(path)
+        k = 1
+        while os.path.exists('%s_%d%s' % (stem, k, ext)):
+            k += 1
+        return '%s_%d%s' % (stem, k, ext)
+
+    def write_output_files(self, time_seconds=None):
+        if not getattr(self, '_out', None):
+            return
+        t = int(self.time_sec if time_seconds is None else time_seconds)
+        if t % int(self.save_grid_dt) == 0:
+            for (kind, v), fh in self._out.items():
+                if kind == 'gs':
+                    np.float32(self._fetch(v)).tofile(fh)
+        if t % int(self.save_pixels_dt) == 0:
+            for (kind, v), fh in self._out.items():
+                if kind == 'ts':
+                    vals = self._fetch(v)[self.outlet_IDs]
+                    fh.write(('%15.7f' % float(self.time_min)) +
+                             ''.join('%15.7f' % x for x in vals) + '\n')
+
+    def close_output_files(self):
+        for fh in getattr(self, '_out', {}).values():
+            fh.close()
+        self._out = {}

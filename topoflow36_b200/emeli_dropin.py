@@ -1,0 +1,55 @@
+"""Hand the GPU Channels / D8 components to the reference's EMELI coupler.
+
+EMELI discovers components BY NAME: ``component_repository.xml``
+maps ``tf_channels_kin_wave -> module channels_kinematic_wave, class
+channels_component`` (framework/component_repository.xml:6-42) and
+``instantiate_comp`` runs ``from topoflow.components import <module>``
+(framework/emeli.py:536-547).  ``install()`` pre-seeds ``sys.modules`` and the
+``topoflow.components`` package attribute with the modules of this package, so
+an UNMODIFIED providers file and repository resolve to the GPU classes.  Nothing
+in the reference tree is edited; ``uninstall()`` restores the originals.
+
+Needs the reference importable (``import topoflow``); it is only the coupler
+that comes from there -- the components run on the GPU through libtfb_b200.so.
+Run EMELI with ``time_interp_method='None'`` (emeli.py:893): the Linear
+interpolator copies every provided grid each step (time_interpolation.py:81-118).
+"""
+import importlib
+import sys
+
+_SWAPS = {'channels_kinematic_wave': 'topoflow36_b200.channels_kinematic_wave',
+          'channels_diffusive_wave': 'topoflow36_b200.channels_diffusive_wave'}
+_saved = {}
+
+
+def install(modules=None):
+    """Route EMELI's component lookup to the GPU components.  Returns the list
+    of swapped reference module names."""
+    import topoflow.components as pkg          # the reference package
+    done = []
+    for ref_name, ours in _SWAPS.items():
+        if modules is not None and ref_name not in modules:
+            continue
+        full = 'topoflow.components.' + ref_name
+        mod = importlib.import_module(ours)
+        _saved[full] = (sys.modules.get(full), getattr(pkg, ref_name, None))
+        sys.modules[full] = mod
+        setattr(pkg, ref_name, mod)
+        done.append(ref_name)
+    return done
+
+
+def uninstall():
+    import topoflow.components as pkg
+    for full, (old_mod, old_attr) in list(_saved.items()):
+        name = full.rsplit('.', 1)[1]
+        if old_mod is None:
+            sys.modules.pop(full, None)
+        else:
+            sys.modules[full] = old_mod
+        if old_attr is None:
+            if hasattr(pkg, name):
+                delattr(pkg, name)
+        else:
+            setattr(pkg, name, old_attr)
+        del _saved[full]

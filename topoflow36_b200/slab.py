@@ -98,11 +98,30 @@ def exchange_halos(tensors, layout, rows=None, group=None):
 
 
 class SlabChannels(object):
-    """A ChannelsEngine per rank + the per-step exchange."""
+    """A ChannelsEngine per rank + the per-step halo exchange.
+
+    Per step only the boundary discharge rows cross NVLink.  The volume
+    integrals and bad-value counters are sums over cells and steps, so every
+    rank folds ITS OWN share into its own scalar block each step (engine built
+    with finalize=True and n_pixels_global = its own cell count) and the global
+    values are formed on demand by ONE all-reduce in read_scalars(); the outlet
+    sample, peaks and vol_Q live on the rank that owns the outlet cell and are
+    zero elsewhere, so the same SUM delivers them.  No per-step collective."""
+
+    _SUM_FIELDS = ('vol_R', 'vol_Q', 'vol_edge', 'Q_outlet', 'u_outlet', 'd_outlet',
+                   'f_outlet', 'Q_peak', 'T_peak', 'u_peak', 'Tu_peak', 'd_peak', 'Td_peak',
+                   'vol_P', 'vol_PR', 'vol_PS', 'vol_SM', 'vol_ET', 'vol_IN')
+    _CNT_FIELDS = ('n_neg_d', 'n_nan_d', 'n_inf_d', 'n_neg_u', 'n_nan_u', 'n_inf_u', 'n_nan_IN')
 
     def __init__(self, layout, engine, group=None):
         self.layout, self.engine, self.group = layout, engine, group
-        self.sums = torch.zeros(L.NSUM, dtype=torch.float64, device=engine.device)
+        if layout.world_size > 1 and not engine.args.finalize:
+            raise L.TfbError('SlabChannels needs an engine built with finalize=True')
+        self.device = engine.device
+        self.n_launches_per_step = 1
+
+    def __getattr__(self, name):           # state access falls through to the engine
+        return getattr(self.__dict__['engine'], name)
 
     def exchange_state(self):
         e, lay = self.engine, self.layout
@@ -115,23 +134,116 @@ class SlabChannels(object):
         exchange_halos(ts, lay, rows, self.group)
 
     def step(self, time_min=0.0):
-        e = self.engine
-        e.step(time_min)                            # finalize = 0: sums stay per rank
-        if self.layout.world_size > 1:
-            self.sums.copy_(e.partials[:L.NSUM])
-            dist.all_reduce(self.sums, op=dist.ReduceOp.SUM, group=self.group)
-            # slot 16 (dt_cfl_min, a diagnostic) is a MIN, not a SUM: keep this
-            # rank's own value; global_dt_min() reduces it on demand
-            self.sums[16] = e.partials[16]
-            src = self.sums
-        else:
-            src = e.partials[:L.NSUM]
-        L.check(e.lib.tfb_channels_fold(C.byref(e.args), src.data_ptr(), L.stream_ptr()),
-                'tfb_channels_fold')
+        self.engine.step(time_min)
         self.exchange_state()
 
+    def read_scalars(self):
+        """Global scalar block (collective: every rank must call it)."""
+        s = self.engine.read_scalars()
+        if self.layout.world_size == 1:
+            return s
+        nf, nc = len(self._SUM_FIELDS), len(self._CNT_FIELDS)
+        v = torch.tensor([getattr(s, n) for n in self._SUM_FIELDS] +
+                         [float(getattr(s, n)) for n in self._CNT_FIELDS],
+                         dtype=torch.float64, device=self.device)
+        dist.all_reduce(v, op=dist.ReduceOp.SUM, group=self.group)
+        m = torch.tensor([s.dt_cfl_min], dtype=torch.float64, device=self.device)
+        dist.all_reduce(m, op=dist.ReduceOp.MIN, group=self.group)
+        h = v.cpu().tolist()
+        for k, n in enumerate(self._SUM_FIELDS):
+            setattr(s, n, h[k])
+        for k, n in enumerate(self._CNT_FIELDS):
+            setattr(s, n, int(h[nf + k]))
+        s.dt_cfl_min = float(m.item())
+        return s
+
     def global_dt_min(self):
-        t = self.engine.partials[16:17].clone()
-        if self.layout.world_size > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
-        return float(t.item())
+        return self.read_scalars().dt_cfl_min
+
+
+def slab_d8(DEM, layout, dem_halo, link_flats=True, xres=30.0, yres=30.0, nodata=-9999.0,
+            kinematic=True, device=None, group=None):
+    """D8 codes and bed slope of one slab, computed on the device.
+
+    `DEM`: float32 rows [row0 - dem_halo, row0 + ny + dem_halo) of the global grid
+    (dem_halo >= layout.halo + 1 when world_size > 1).  Flat linking is the
+    GLOBAL Jacobi iteration of d8_global.link_flats (:374-576): every rank sweeps
+    its owned rows, the boundary code rows are exchanged and the flat / fixed
+    counters all-reduced after each sweep, so the codes are bit-identical to a
+    single-GPU run on the whole grid.  Returns code (uint8, halo rows included),
+    S_bed (float64, owned rows; zero/negative slopes replaced by the GLOBAL
+    minimum positive slope for the kinematic wave, channels_base.py:4164-4260)
+    and the float32 pixel sizes."""
+    import numpy as np
+    from .d8 import D8Toolkit
+    lib = L.load()
+    dev = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
+    ny, nx, H, NY = layout.ny, layout.nx, layout.halo, layout.ny_global
+    dx64, dy64 = np.float64(xres), np.float64(yres)
+    dd64 = np.sqrt(dx64 ** 2 + dy64 ** 2)
+    dx, dy, dd = np.float32(dx64), np.float32(dy64), np.float32(dd64)
+    multi = layout.world_size > 1
+    st = L.stream_ptr
+    if not multi:
+        tk = D8Toolkit(DEM, xres=xres, yres=yres, link_flats=link_flats, nodata=nodata, device=dev)
+        tk.update_flow_grid()
+        S = tk.slope().double()
+        code = tk.code
+        n_reps = tk.n_reps
+    else:
+        if dem_halo < H + 1:
+            raise ValueError('dem_halo must be >= halo + 1')
+        dem = torch.as_tensor(np.ascontiguousarray(DEM, dtype=np.float32)).to(dev)
+        top = layout.row0 - dem_halo                      # global row of dem[0]
+        lo, hi = max(0, layout.row0 - H), min(NY, layout.row0 + ny + H)
+        code16 = torch.zeros((ny + 2 * H, nx), dtype=torch.int16, device=dev)
+        reg = code16[lo - (layout.row0 - H):hi - (layout.row0 - H)]
+        L.check(lib.tfb_d8_codes(dem[lo - top:].data_ptr(), hi - lo, nx, 1, lo, NY,
+                                 float(dx), float(dy), float(dd), float(nodata),
+                                 1 if link_flats else 0, reg.data_ptr(), st()), 'tfb_d8_codes')
+        L.check(lib.tfb_d8_break_ties(reg.data_ptr(), reg.numel(), st()), 'tfb_d8_break_ties')
+        n_reps = 0
+        if link_flats:
+            nxt = code16.clone()
+            cnt = torch.zeros(2, dtype=torch.int32, device=dev)
+            own = lambda t: t[H:H + ny]
+            while True:
+                n_reps += 1
+                cnt.zero_()
+                L.check(lib.tfb_d8_link_flats_sweep(
+                    own(code16).data_ptr(), own(nxt).data_ptr(), ny, nx, H, layout.row0, NY,
+                    cnt.data_ptr(), cnt[1:].data_ptr(), st()), 'tfb_d8_link_flats_sweep')
+                tot = cnt.to(torch.int64)
+                dist.all_reduce(tot, group=group)
+                n_flats, n_fixed = (int(v) for v in tot.cpu())
+                if n_flats == 0:
+                    break
+                code16, nxt = nxt, code16
+                exchange_halos([code16], layout, [H], group)
+                if n_fixed == n_flats or n_fixed == 0:
+                    break
+        code = torch.zeros((ny + 2 * H, nx), dtype=torch.uint8, device=dev)
+        L.check(lib.tfb_d8_finalize_codes(code16.data_ptr(), code.data_ptr(), code.numel(), st()),
+                'tfb_d8_finalize_codes')
+        # slope over owned rows +- 1 (clipped): parents may sit in the neighbour slab
+        s_lo, s_hi = max(0, layout.row0 - 1), min(NY, layout.row0 + ny + 1)
+        n_s = s_hi - s_lo
+        rows = lambda v: torch.full((n_s,), float(v), dtype=torch.float32, device=dev)
+        S32 = torch.empty((n_s, nx), dtype=torch.float32, device=dev)
+        L.check(lib.tfb_d8_slope(dem[s_lo - top:].data_ptr(),
+                                 code[s_lo - (layout.row0 - H):].data_ptr(), rows(dx).data_ptr(),
+                                 rows(dy).data_ptr(), rows(dd).data_ptr(), n_s, nx,
+                                 S32.data_ptr(), st()), 'tfb_d8_slope')
+        # rows s_lo / s_hi-1 are treated as array borders by the kernel; they are
+        # either true global borders (code 0) or outside the owned range
+        S = S32[layout.row0 - s_lo:layout.row0 - s_lo + ny].double()
+    if kinematic:
+        good = S > 0
+        big = torch.tensor(float('inf'), dtype=torch.float64, device=dev)
+        smin = torch.where(good, S, big).min().reshape(1)
+        if multi:
+            dist.all_reduce(smin, op=dist.ReduceOp.MIN, group=group)
+        bad = ~(good & torch.isfinite(S))
+        S = torch.where(bad, smin.expand_as(S), S)
+    return dict(code=code, S_bed=S.contiguous(), dx=np.array([dx]), dy=np.array([dy]),
+                dd=np.array([dd]), n_reps=n_reps)
