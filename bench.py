@@ -38,7 +38,8 @@ NX = 4096
 BYTES_PER_CELL = {'kw': 81, 'kw_ga': 97, 'dw': 106}
 METRIC = 'routing Gcell-updates/sec'
 WORKLOAD = ('synthetic fractal DEM %dx%d per GPU, kinematic wave + Manning, fused Green-Ampt '
-            'infiltration, uniform 50 mm/h rain, fp64, dt=1s' % (NY_PER_GPU, NX))
+            'infiltration (pre-wetted soil, I0=0.1 m), uniform 50 mm/h rain, fp64, dt=1s'
+            % (NY_PER_GPU, NX))
 
 
 # ------------------------------------------------------------------ clocks
@@ -119,7 +120,7 @@ def cpu_port_rate(budget_s, n_steps=None, warmup=1, threads=None):
                                outlet=(ny_s - 2, NX // 2), diag=False)
         ch.nthreads = threads
         ch.set_input('P_rain', cases.RAIN_50MMPH)
-        ch.enable_fused(infil=True, I0=1e-6)
+        ch.enable_fused(infil=True, I0=cases.I0_WET)
         for k, v in cases.GA_TREYNOR.items():
             ch.set_input(k, v)
         return ch
@@ -247,6 +248,7 @@ def main():
     ms_per_step = float(ms.item()) / args.steps
     value = cells / (ms_per_step * 1e-3) / 1e9
     sc = stepper.read_scalars()
+    path_used = eng.last_path
     sanity = {'Q_outlet': sc.Q_outlet, 'vol_R': sc.vol_R, 'vol_IN': sc.vol_IN,
               'bad_values': int(sc.n_neg_d + sc.n_inf_d + sc.n_neg_u + sc.n_nan_u + sc.n_inf_u)}
 
@@ -269,7 +271,7 @@ def main():
             cfg = write_component_case(work, parts)
             comp = ckw.channels_component()
             comp.device = dev
-            comp.enable_fused_sources(infil=True, I0=1e-6)
+            comp.enable_fused_sources(infil=True, I0=cases.I0_WET)
             comp.initialize(cfg_file=cfg, mode='nondriver', SILENT=True)
             for k, v in cases.GA_TREYNOR.items():
                 comp.set_source_input(k, v)
@@ -342,7 +344,8 @@ def main():
                 'frac': achieved / peak, 'traffic': traffic,
                 'peak_source': 'MEASURED_PEAKS.json hbm_gbs (measured)' if peaks
                 else 'B200_PROFILING.md fallback 6.65 TB/s',
-                'kernel': 'channels_step_kernel<KW, Manning, fused Green-Ampt>',
+                'kernel': 'channels_packed_kernel<GA=true> (TMA ring, KW + Manning + fused Green-Ampt)',
+                'path': path_used,
                 'algorithmic_bytes_per_cell': bpc, 'cells_per_launch': cells_per_launch,
                 'launch_ms': ms_per_step,
                 'note': 'one launch per step; launch time = timed region / launches (CUDA events)'}

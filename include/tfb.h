@@ -218,7 +218,7 @@ typedef struct {
                                  doubles, zero-initialised once by the caller;
                                  after a step its FIRST TFB_NSUM doubles hold
                                  this rank's sums                               */
-    uint32_t *ticket;         /* DEVICE scratch, 1 word, zero-initialised       */
+    uint32_t *ticket;         /* DEVICE scratch, 2 words, zero-initialised      */
     int32_t finalize;         /* 1: last block folds partials into `scalars`
                                  (single GPU); 0: only leave the per-rank sums
                                  in partials[0..TFB_NSUM) for an allreduce, then
@@ -248,6 +248,56 @@ int tfb_channels_pack_geo(const uint8_t *code, int32_t ny, int32_t nx,
 
 /* one routing step of the slab */
 int tfb_channels_step(const tfb_channels_step_args *a, void *stream);
+
+/* ---- packed fast path ------------------------------------------------------
+ * The common production case -- kinematic wave, Manning, no per-step
+ * diagnostics, scalar sinuosity and pixel area, scalar forcing, optionally
+ * fused Green-Ampt with scalar soil parameters -- runs from a COMPACT, lossless
+ * re-encoding of the static per-cell inputs built once at initialize():
+ *   geo32     code | child mask << 8 | bank-angle index << 16   (4 B / cell)
+ *   width32   bottom width as float32 (the RTG files hold float32; the caller
+ *             must have verified (double)(float)w == w)          (4 B / cell)
+ *   coef      sqrt(|S_bed|) / n  (both static, channels_base.py:3982-3983)
+ *                                                                 (8 B / cell)
+ *   angle_lut per distinct bank angle (<= 256): tan, 1/(2 tan) (0 when tan==0),
+ *             1/cos, 4 tan
+ * i.e. 16 B of static input per cell instead of 42.  Divisions by static
+ * quantities (ds, 2 tan, cos, n) become multiplications by reciprocals that are
+ * themselves correctly rounded, so results differ from the exact-order generic
+ * kernel by a few ulp per step (parity tests: rel <= 1e-11 over a storm).
+ * All pointers address the first OWNED row of (ny, nx) arrays. */
+typedef struct {
+    const uint32_t *geo32;
+    const float *width32;
+    const double *coef;
+    const double *angle_lut;  /* n_angles x 4 doubles, DEVICE */
+    const double *row_geom;   /* ny x 6 doubles from tfb_channels_pack_rows: flow
+                                 length ds = sinu * {dx, dd, dy} of the row (E/W and
+                                 noflow, diagonal, N/S) and the 3 reciprocals    */
+    double outlet_rough;      /* Manning n of the outlet cell (f_outlet only)    */
+    int32_t n_angles;
+} tfb_channels_packed;
+
+int64_t tfb_sizeof_channels_packed(void);
+
+/* geo32 of the owned rows from the D8 codes (halo rows readable as in
+ * tfb_channels_pack_geo) and a per-cell bank-angle index (owned rows) */
+int tfb_channels_pack_geo32(const uint8_t *code, const uint8_t *angle_idx,
+                            int32_t ny, int32_t nx, int32_t halo,
+                            uint32_t *geo32, void *stream);
+
+/* per-row flow lengths and their reciprocals (d8_global.py:960-1027 times the
+ * scalar sinuosity, channels_base.py:1242); dx, dy, dd = DEVICE float32 (ny) */
+int tfb_channels_pack_rows(const float *dx, const float *dy, const float *dd,
+                           double sinu, int32_t ny, double *row_geom,
+                           void *stream);
+
+/* one routing step through the packed path; TFB_ERR_ARG when the arguments do
+ * not meet the conditions above (the caller then uses tfb_channels_step).
+ * Reads a->vol, a->Q_in (with halo), a->I; writes a->vol_out, d, u, Q_out,
+ * I_out; uses a->partials / ticket / scalars like tfb_channels_step. */
+int tfb_channels_step_packed(const tfb_channels_step_args *a,
+                             const tfb_channels_packed *p, void *stream);
 
 /* multi-GPU: fold globally reduced sums (DEVICE, TFB_NSUM doubles laid out as
  * tfb_channels_step leaves them in partials[]) into the scalar block */

@@ -15,9 +15,9 @@ def build(n, kinematic=True, diag=False, infil=False):
         DEM = (1e4 - 0.6*r - 0.15*c + 2*torch.rand((n, n), device=dev, generator=g)).float()
     t = D8Toolkit(DEM); t0 = time.time(); t.update(); torch.cuda.synchronize(); print('d8 total s', time.time()-t0, 'reps', t.n_reps, 'area cells', t.n_area_cells)
     S = t.slope().double(); S[S <= 0] = S[S > 0].min()
-    width = 1 + 4*torch.rand((n, n), device=dev, dtype=torch.float64, generator=g)
+    width = (1 + 4*torch.rand((n, n), device=dev, dtype=torch.float64, generator=g)).float().double()
     angle = torch.full((n, n), float(np.pi/4), device=dev, dtype=torch.float64)
-    nval = 0.03 + 0.02*torch.rand((n, n), device=dev, dtype=torch.float64, generator=g)
+    nval = (0.03 + 0.02*torch.rand((n, n), device=dev, dtype=torch.float64, generator=g)).float().double()
     e = ChannelsEngine(n, n, dt=1.0, code=t.code, dx=t.dx, dy=t.dy, dd=t.dd, S_bed=S, width=width, angle=angle, rough=nval,
                        kinematic=kinematic, diag=diag, outlet=(n-2, n//2))
     e.set_input('P_rain', 50/3.6e6)
@@ -40,6 +40,6 @@ if __name__ == '__main__':
         e = build(n, **kw)
         ms = timeit(e)
         cells = n*n
-        print('%-8s n=%d  %.3f ms/step  %.2f Gcell/s  alg %.0f GB/s (%d B/cell)' % (name, n, ms, cells/ms/1e6, cells*B/ms/1e6, B))
+        print(e.last_path, '%-8s n=%d  %.3f ms/step  %.2f Gcell/s  alg %.0f GB/s (%d B/cell)' % (name, n, ms, cells/ms/1e6, cells*B/ms/1e6, B))
         s = e.read_scalars(); print('   Q_outlet', s.Q_outlet, 'vol_R', s.vol_R, 'bad', s.n_neg_d, s.n_nan_u)
         del e; torch.cuda.empty_cache()

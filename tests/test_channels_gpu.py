@@ -117,21 +117,36 @@ def test_synth_variants_vs_reference_fixture(synth_channels, tag):
 
 
 def test_lean_mode_equals_diag_mode(synth_channels):
-    """Without TFB_CH_DIAG the state grids must be bit-identical."""
+    """Without TFB_CH_DIAG the generic kernel's state grids are bit-identical to
+    the diagnostics kernel's; the packed fast path (reciprocal multiplications,
+    include/tfb.h) agrees to a few ulp per step (asserted: 1e-12 after 60 steps)."""
     g = synth_channels
     code = g['code']
     ny, nx = code.shape
+    nx2 = nx - (nx % 4)                      # the packed path needs nx % 4 == 0
     dx, dy, dd = o.pixel_dims(ny, 30.0, 30.0)
-    res = []
-    for diag in (False, True):
-        eng = _engine(code, dx, dy, dd, g['slope'], g['width'], g['angle'], g['nval'],
-                      dt=2.0, da=900.0, diag=diag, outlet=(ny - 2, nx // 2))
+    sl = (slice(None), slice(0, nx2))
+    code2, _ = o.d8_flow_grid(g['DEM'][sl], dx, dy, dd)     # D8 of the cropped DEM
+    res = {}
+    for name, kw in (('diag', dict(diag=True)), ('lean', dict(packed=False)), ('packed', dict())):
+        # bank angles rounded to whole degrees: <= 256 distinct values (packed path)
+        eng = _engine(code2, dx, dy, dd, g['slope'][sl], g['width'][sl],
+                      np.round(g['angle'][sl]), g['nval'][sl], dt=2.0, da=900.0,
+                      outlet=(ny - 2, nx2 // 2), **kw)
         eng.set_input('P_rain', 80 / 3.6e6)
         for i in range(60):
-            eng.step()
-        res.append([t.cpu().numpy().copy() for t in (eng.vol, eng.own(eng.d), eng.own(eng.u), eng.Q)])
-    for a, b in zip(*res):
+            eng.step(time_min=i / 30.0)
+        assert eng.last_path == ('packed' if name == 'packed' else 'generic')
+        res[name] = [t.cpu().numpy().copy() for t in (eng.vol, eng.own(eng.d), eng.own(eng.u), eng.Q)]
+        res[name + '_s'] = eng.read_scalars()
+    for a, b in zip(res['lean'], res['diag']):
         assert np.array_equal(a, b)
+    for a, b in zip(res['packed'], res['diag']):
+        assert rel_err(a, b) <= 1e-12
+    sp, sd = res['packed_s'], res['diag_s']
+    for n in SCALARS:
+        assert abs(getattr(sp, n) - getattr(sd, n)) <= 1e-12 * max(abs(getattr(sd, n)), 1e-300), n
+    assert abs(sp.dt_cfl_min - sd.dt_cfl_min) <= 1e-5 * sd.dt_cfl_min
 
 
 @pytest.mark.parametrize('shape', [(1, 5), (3, 3), (2, 70), (70, 2), (33, 257)])

@@ -83,6 +83,12 @@ class ChannelsStepArgs(C.Structure):
     ]
 
 
+class ChannelsPacked(C.Structure):
+    """tfb_channels_packed: compact static inputs of the packed fast path."""
+    _fields_ = [('geo32', vp), ('width32', vp), ('coef', vp), ('angle_lut', vp),
+                ('row_geom', vp), ('outlet_rough', C.c_double), ('n_angles', C.c_int32)]
+
+
 _i32, _i64, _f32, _f64 = C.c_int32, C.c_int64, C.c_float, C.c_double
 
 # name -> (restype, argtypes); every symbol include/tfb.h declares
@@ -110,6 +116,11 @@ SIGNATURES = {
     'tfb_channels_partials_len': (_i64, [_i32, _i32]),
     'tfb_channels_pack_geo': (C.c_int, [vp, _i32, _i32, _i32, vp, vp]),
     'tfb_channels_step': (C.c_int, [C.POINTER(ChannelsStepArgs), vp]),
+    'tfb_sizeof_channels_packed': (_i64, []),
+    'tfb_channels_pack_geo32': (C.c_int, [vp, vp, _i32, _i32, _i32, vp, vp]),
+    'tfb_channels_pack_rows': (C.c_int, [vp, vp, vp, _f64, _i32, vp, vp]),
+    'tfb_channels_step_packed': (C.c_int, [C.POINTER(ChannelsStepArgs),
+                                           C.POINTER(ChannelsPacked), vp]),
     'tfb_channels_fold': (C.c_int, [C.POINTER(ChannelsStepArgs), vp, vp]),
     'tfb_sources_partials_len': (_i64, []),
     'tfb_channels_minmax': (C.c_int, [vp, vp, vp, vp, _i32, _i32, vp, vp, vp,
@@ -156,6 +167,8 @@ def load():
                           C.sizeof(ChannelsStepArgs)))
     if lib.tfb_sizeof_channels_scalars() != C.sizeof(ChannelsScalars):
         raise TfbError('tfb_channels_scalars layout mismatch')
+    if lib.tfb_sizeof_channels_packed() != C.sizeof(ChannelsPacked):
+        raise TfbError('tfb_channels_packed layout mismatch')
     _lib = lib
     return lib
 

@@ -34,7 +34,7 @@ class ChannelsEngine(object):
                  d0=0.0, kinematic=True, manning=True, diag=False,
                  write_R=False, outlet=(0, 0), rho_H2O=1000.0, row0=0,
                  ny_global=None, halo=0, device=None, finalize=True,
-                 n_pixels_global=None):
+                 n_pixels_global=None, packed=True):
         if not torch.cuda.is_available():
             raise L.TfbError('ChannelsEngine needs a CUDA device (no CPU path)')
         self.lib = L.load()
@@ -140,13 +140,94 @@ class ChannelsEngine(object):
                                        device=self.device)
         npart = self.lib.tfb_channels_partials_len(self.ny, self.nx)
         self.partials = torch.zeros(npart, dtype=torch.float64, device=self.device)
-        self.ticket = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.ticket = torch.zeros(2, dtype=torch.int32, device=self.device)
         a.scalars = self.scalars_dev.data_ptr()
         a.partials = self.partials.data_ptr()
         a.ticket = self.ticket.data_ptr()
         self._scalars_host = torch.zeros(C.sizeof(L.ChannelsScalars), dtype=torch.uint8).pin_memory()
         self.set_initial_depth(d0)
         self.n_steps = 0
+        self.packed = None
+        self.use_packed = bool(packed)
+        self._angle_in = angle
+        self._rough_in = rough
+        if self.use_packed:
+            self._try_pack()
+
+    # ------------------------------------------------------------ packed path
+    def _try_pack(self):
+        """Build the compact static inputs of tfb_channels_step_packed when the
+        configuration allows it (kinematic, Manning, no diagnostics, nx % 4 == 0,
+        scalar sinuosity / pixel area, float32-exact widths, <= 256 distinct
+        bank angles).  Everything is lossless; otherwise the generic kernel runs."""
+        a = self.args
+        if (not self.kinematic) or (not self.manning) or self.diag or (self.flags & L.CH_WRITE_R):
+            return
+        if self.nx % 4 or self.sinu_grid is not None or self._da_is_grid:
+            return
+        dev = self.device
+        full = lambda g, v: (self.own(g) if g is not None
+                             else torch.full((self.ny, self.nx), float(v), dtype=torch.float64,
+                                             device=dev))
+        width = full(self.width_grid, a.width.val)
+        w32 = width.float()
+        if not bool((w32.double() == width).all()):
+            return
+        tan = full(self.tan_angle_grid, a.tan_angle.val)
+        cos = full(self.cos_angle_grid, a.cos_angle.val)
+        key = torch.stack((tan.reshape(-1), cos.reshape(-1)), dim=1)
+        uniq, inv = torch.unique(key, dim=0, return_inverse=True)
+        if uniq.shape[0] > 256:
+            return
+        t, c = uniq[:, 0], uniq[:, 1]
+        lut = torch.zeros((uniq.shape[0], 4), dtype=torch.float64, device=dev)
+        lut[:, 0] = t
+        lut[:, 1] = torch.where(t == 0, torch.zeros_like(t), 1.0 / (2.0 * t))
+        lut[:, 2] = 1.0 / c
+        lut[:, 3] = 2.0 * (2.0 * t)
+        aidx = inv.to(torch.uint8).reshape(self.ny, self.nx).contiguous()
+        rough = full(self.rough_grid, a.rough.val)
+        coef = (self.own(self.sqrtS) / rough).contiguous()
+        geo32 = torch.empty((self.ny, self.nx), dtype=torch.int32, device=dev)
+        L.check(self.lib.tfb_channels_pack_geo32(self._p(self.code), aidx.data_ptr(), self.ny,
+                                                 self.nx, self.halo, geo32.data_ptr(),
+                                                 L.stream_ptr()), 'tfb_channels_pack_geo32')
+        rowg = torch.empty((self.ny, 6), dtype=torch.float64, device=dev)
+        L.check(self.lib.tfb_channels_pack_rows(self._prow(self.dx), self._prow(self.dy),
+                                                self._prow(self.dd), float(a.sinu.val), self.ny,
+                                                rowg.data_ptr(), L.stream_ptr()),
+                'tfb_channels_pack_rows')
+        orow = a.outlet_row - self.row0
+        n_out = 0.0
+        if 0 <= orow < self.ny and 0 <= a.outlet_col < self.nx:
+            n_out = float(rough[orow, a.outlet_col])
+        pk = L.ChannelsPacked()
+        pk.geo32, pk.width32, pk.coef = geo32.data_ptr(), w32.data_ptr(), coef.data_ptr()
+        pk.angle_lut, pk.row_geom = lut.data_ptr(), rowg.data_ptr()
+        pk.outlet_rough, pk.n_angles = n_out, int(uniq.shape[0])
+        self._pack_keep = (geo32, w32.contiguous(), coef, lut, rowg)
+        pk.width32 = self._pack_keep[1].data_ptr()
+        self.packed = pk
+
+    def _packed_ok(self):
+        """Per-step eligibility: uniform forcing, at most scalar Green-Ampt fused."""
+        if self.packed is None or not self.use_packed:
+            return False
+        src = self.flags & (L.CH_SRC_MET | L.CH_SRC_SNOW | L.CH_SRC_EVAP | L.CH_SRC_INFIL)
+        if src not in (0, L.CH_SRC_INFIL):
+            return False
+        for n in ('P_rain', 'SM', 'GW', 'MR', 'ET'):
+            if isinstance(self.src[n], torch.Tensor):
+                return False
+        if src:
+            for n in ('Ks', 'Ki', 'qs', 'qi', 'G', 'h_table', 'elev'):
+                if isinstance(self.src[n], torch.Tensor):
+                    return False
+            if self.args.h_table.val >= self.args.elev.val:
+                return False
+        elif isinstance(self.src['IN'], torch.Tensor):
+            return False
+        return True
 
     # ------------------------------------------------------------ allocation
     def _zeros(self, dtype):
@@ -343,7 +424,13 @@ class ChannelsEngine(object):
             dbl = buf[1] is not None
             setattr(a, name, self._p(buf[self.scur if dbl else 0]))
             setattr(a, name + '_out', self._p(buf[self.scur ^ 1 if dbl else 0]))
-        L.check(self.lib.tfb_channels_step(C.byref(a), L.stream_ptr()), 'tfb_channels_step')
+        if self._packed_ok():
+            L.check(self.lib.tfb_channels_step_packed(C.byref(a), C.byref(self.packed),
+                                                      L.stream_ptr()), 'tfb_channels_step_packed')
+            self.last_path = 'packed'
+        else:
+            L.check(self.lib.tfb_channels_step(C.byref(a), L.stream_ptr()), 'tfb_channels_step')
+            self.last_path = 'generic'
         self.qcur ^= 1
         self.scur ^= 1
         self.n_steps += 1
