@@ -37,7 +37,12 @@ def _worker(rank, world, port, kinematic, infil, q):
                                  tile_rows=ny, dt=2.0)
         lay = parts['layout']
         rows = slice(lay.row0, lay.row0 + lay.ny)
+        fails = []
         ok = bool(torch.equal(slab.engine.own(slab.engine.code), one.code[rows]))
+        if not ok:
+            fails.append('code (%d cells differ)' % int((slab.engine.own(slab.engine.code) != one.code[rows]).sum()))
+        if not torch.equal(slab.engine.own(slab.engine.S_bed), one.S_bed[rows]):
+            fails.append('S_bed')
         for i in range(steps):
             if i == 80:
                 slab.engine.set_input('P_rain', 0.0)
@@ -45,17 +50,22 @@ def _worker(rank, world, port, kinematic, infil, q):
             slab.step(i * 2.0 / 60.0)
             one.step(i * 2.0 / 60.0)
         e = slab.engine
-        for a, b in ((e.vol, one.vol), (e.own(e.d), one.own(one.d)), (e.own(e.u), one.own(one.u)),
-                     (e.Q, one.Q)):
-            ok &= bool(torch.equal(a, b[rows]))
+        for nm, a, b in (('vol', e.vol, one.vol), ('d', e.own(e.d), one.own(one.d)),
+                         ('u', e.own(e.u), one.own(one.u)), ('Q', e.Q, one.Q)):
+            if not torch.equal(a, b[rows]):
+                ok = False
+                fails.append('%s (%d cells, max %g)' % (nm, int((a != b[rows]).sum()),
+                                                        float((a - b[rows]).abs().max())))
         moved = float(one.Q[rows].abs().max()) > 0
         sg, s1 = slab.read_scalars(), one.read_scalars()
         rel = lambda x, y: abs(x - y) <= 1e-12 * max(abs(y), 1e-300)
-        ok &= rel(sg.vol_R, s1.vol_R) and rel(sg.vol_edge, s1.vol_edge) and rel(sg.vol_Q, s1.vol_Q)
-        ok &= (sg.Q_outlet == s1.Q_outlet) and (sg.Q_peak == s1.Q_peak) and (sg.T_peak == s1.T_peak)
-        if infil:
-            ok &= rel(sg.vol_IN, s1.vol_IN)
-        q.put((rank, bool(ok), moved, sg.Q_outlet))
+        for nm in ('vol_R', 'vol_edge', 'vol_Q') + (('vol_IN',) if infil else ()):
+            if not rel(getattr(sg, nm), getattr(s1, nm)):
+                fails.append('%s %r vs %r' % (nm, getattr(sg, nm), getattr(s1, nm)))
+        for nm in ('Q_outlet', 'Q_peak', 'T_peak'):
+            if getattr(sg, nm) != getattr(s1, nm):
+                fails.append('%s %r vs %r' % (nm, getattr(sg, nm), getattr(s1, nm)))
+        q.put((rank, not fails, moved, fails))
     finally:
         dist.destroy_process_group()
 

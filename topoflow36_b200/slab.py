@@ -81,6 +81,8 @@ def exchange_halos(tensors, layout, rows=None, group=None):
     for t, k in zip(tensors, rows):
         if k <= 0:
             continue
+        if t.dtype in (torch.int16, torch.bool):      # NCCL has no 16-bit integer type
+            t = t.view(torch.uint8)
         if layout.up is not None:
             send = t[h:h + k]                       # my first k owned rows
             recv = t[h - k:h]                       # my upper halo (nearest k)
@@ -228,11 +230,14 @@ def slab_d8(DEM, layout, dem_halo, link_flats=True, xres=30.0, yres=30.0, nodata
         # slope over owned rows +- 1 (clipped): parents may sit in the neighbour slab
         s_lo, s_hi = max(0, layout.row0 - 1), min(NY, layout.row0 + ny + 1)
         n_s = s_hi - s_lo
-        rows = lambda v: torch.full((n_s,), float(v), dtype=torch.float32, device=dev)
+        # keep the three row arrays alive across the launch (a temporary would be
+        # recycled by the caching allocator before the kernel reads it)
+        rdx, rdy, rdd = (torch.full((n_s,), float(v), dtype=torch.float32, device=dev)
+                         for v in (dx, dy, dd))
         S32 = torch.empty((n_s, nx), dtype=torch.float32, device=dev)
         L.check(lib.tfb_d8_slope(dem[s_lo - top:].data_ptr(),
-                                 code[s_lo - (layout.row0 - H):].data_ptr(), rows(dx).data_ptr(),
-                                 rows(dy).data_ptr(), rows(dd).data_ptr(), n_s, nx,
+                                 code[s_lo - (layout.row0 - H):].data_ptr(), rdx.data_ptr(),
+                                 rdy.data_ptr(), rdd.data_ptr(), n_s, nx,
                                  S32.data_ptr(), st()), 'tfb_d8_slope')
         # rows s_lo / s_hi-1 are treated as array borders by the kernel; they are
         # either true global borders (code 0) or outside the owned range
