@@ -67,3 +67,37 @@ def test_larger_dem_vs_oracle_with_counts():
     # idempotence: a second update gives the same grids
     t.update()
     assert np.array_equal(t.A.cpu().numpy(), A)
+
+
+def test_d8_2048_bit_exact_vs_c_oracle_and_exact_properties():
+    """A grid too large for the numpy oracle: the C restatement (itself pinned to
+    the reference fixtures in test_c_oracle.py) must agree bit for bit, and the
+    size-independent identities used at 16384^2 (scripts/bench_d8.py) must hold."""
+    import torch
+    from oracle import c_oracle
+    from scripts import bench_d8
+    from topoflow36_b200.d8 import D8Toolkit
+    n = 2048
+    DEM = bench_d8.device_dem(n, seed=77)
+    DEM = (torch.round(DEM * 8.0) / 8.0).contiguous()        # quantise: ties and flats appear
+    tk = D8Toolkit(DEM)
+    tk.start_codes()
+    start = tk.code16.clone()
+    tk.update()
+    want = bench_d8.torch_start_codes(DEM, float(tk.dx_host[0]), float(tk.dy_host[0]),
+                                      float(tk.dd_host[0]))
+    assert torch.equal(start, want)
+    dx, dy, dd = o.pixel_dims(n, 30.0, 30.0)
+    code_o, _ = c_oracle.d8_flow_grid(DEM.cpu().numpy(), dx, dy, dd)
+    assert np.array_equal(tk.code.cpu().numpy(), code_o)
+    A_o, N_o = c_oracle.d8_area(code_o, np.float64(900.0) / 1e6, with_counts=True)
+    assert np.array_equal(tk.A.cpu().numpy(), A_o)
+    assert np.array_equal(tk.count.cpu().numpy(), N_o)
+    assert tk.n_reps > 1                                       # flats were actually linked
+    pid = tk.parent_ids().to(torch.int64).reshape(-1)
+    cnt = tk.count.reshape(-1)
+    flow = (tk.code.reshape(-1) != 0) & (pid > 0)
+    acc = torch.zeros_like(cnt)
+    acc.index_add_(0, pid[flow], cnt[flow])
+    has_area = tk.A.reshape(-1) > 0
+    assert torch.equal(cnt[has_area], (acc + 1)[has_area])
