@@ -249,7 +249,13 @@ def main():
     value = cells / (ms_per_step * 1e-3) / 1e9
     sc = stepper.read_scalars()
     path_used = eng.last_path
-    sanity = {'Q_outlet': sc.Q_outlet, 'vol_R': sc.vol_R, 'vol_IN': sc.vol_IN,
+    stored = eng.vol.sum().reshape(1)
+    qmax = eng.Q.max().reshape(1)
+    if world > 1:
+        dist.all_reduce(stored)
+        dist.all_reduce(qmax, op=dist.ReduceOp.MAX)
+    sanity = {'Q_outlet': sc.Q_outlet, 'Q_max': float(qmax), 'vol_R': sc.vol_R, 'vol_IN': sc.vol_IN,
+              'mass_balance_rel_err': abs(sc.vol_R - (float(stored) + sc.vol_edge)) / max(sc.vol_R, 1e-300),
               'bad_values': int(sc.n_neg_d + sc.n_inf_d + sc.n_neg_u + sc.n_nan_u + sc.n_inf_u)}
 
     # ---- `e2e`: through the public API with host inputs and a host read -------

@@ -255,3 +255,56 @@ def test_fused_sources_match_oracle_composition(sources_gold):
         assert abs(s.vol_SM - vol_SM) <= 1e-11 * abs(vol_SM)
         assert abs(s.vol_IN - vol_IN) <= 1e-11 * abs(vol_IN)
         assert abs(s.vol_ET - vol_ET) <= 1e-11 * abs(vol_ET)
+
+
+@pytest.mark.parametrize('infil', [False, True])
+def test_packed_path_2048_vs_c_oracle(infil):
+    """The benchmarked kernel (TMA ring, packed inputs) at a size the numpy oracle
+    cannot handle: 2048 x 2048, 60 steps, against the multithreaded C restatement
+    (pinned to the reference in test_c_oracle.py), plus exact mass conservation."""
+    import os
+    import torch
+    from oracle import c_oracle
+    from topoflow36_b200 import cases
+    from topoflow36_b200.d8 import D8Toolkit
+    ny = nx = 2048
+    tile = cases.noise_tile(ny, nx, seed=5)
+    DEM = cases.slab_dem(ny, nx, 0, ny, 0, tile)
+    width, angle, nval = cases.slab_params(ny, nx, 0, 0, seed=5)
+    angle[::3, ::5] = 30.0                         # three distinct bank angles
+    angle[::7, 1::4] = 0.0                         # including vertical banks (tan == 0)
+    tk = D8Toolkit(DEM)
+    tk.update_flow_grid()
+    code = tk.code.cpu().numpy()
+    slope = tk.slope().cpu().numpy()
+    dx, dy, dd = o.pixel_dims(ny, 30.0, 30.0)
+    eng = _engine(code, dx, dy, dd, slope, width, angle, nval, dt=1.0, da=900.0,
+                  outlet=(ny - 2, nx // 2))
+    ch = c_oracle.Channels(code, dx, dy, dd, slope, width, angle, nval, dt=1.0,
+                           outlet=(ny - 2, nx // 2), diag=False)
+    ch.nthreads = os.cpu_count() or 1
+    eng.set_input('P_rain', cases.RAIN_50MMPH)
+    ch.set_input('P_rain', cases.RAIN_50MMPH)
+    if infil:
+        eng.enable_fused_sources(infil=True, I0=cases.I0_WET)
+        ch.enable_fused(infil=True, I0=cases.I0_WET)
+        for k, v in cases.GA_TREYNOR.items():
+            eng.set_input(k, v)
+            ch.set_input(k, v)
+    for i in range(60):
+        eng.step(time_min=i / 60.0)
+        ch.time_min = i / 60.0
+        ch.step()
+    assert eng.last_path == 'packed'
+    for n in ('vol', 'd', 'u', 'Q'):
+        got = (eng.Q if n == 'Q' else eng.vol if n == 'vol' else eng.own(getattr(eng, n)))
+        e = rel_err(got.cpu().numpy(), getattr(ch, n))
+        assert e <= RTOL, '%s rel err %.3e' % (n, e)
+    s = eng.read_scalars()
+    for n in ('vol_R', 'vol_edge', 'vol_Q', 'Q_outlet', 'Q_peak', 'vol_IN'):
+        want = float(getattr(ch, n))
+        assert abs(getattr(s, n) - want) <= 1e-11 * max(abs(want), 1e-300), n
+    # water is conserved: runoff in = stored in channels + left through the edges
+    stored = float(eng.vol.sum())
+    assert abs(s.vol_R - (stored + s.vol_edge)) <= 1e-10 * s.vol_R
+    assert s.n_neg_d == s.n_nan_d == s.n_inf_d == s.n_neg_u == s.n_nan_u == s.n_inf_u == 0
