@@ -185,12 +185,18 @@ def write_component_case(work, eng_parts, dt=1.0):
 
 
 def main():
+    global NX, WORKLOAD
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=1000)
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--rows-per-gpu', type=int, default=NY_PER_GPU)
+    ap.add_argument('--nx', type=int, default=NX)
+    ap.add_argument('--workload', default='kw_ga', choices=['kw_ga', 'kw'],
+                    help='kw_ga = BASELINE configs[1] (default); kw = configs[4] (no infiltration)')
+    ap.add_argument('--device-gen', action='store_true',
+                    help='synthesise the case on the GPU (needed for 65536-wide slabs)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     args = ap.parse_args()
@@ -215,14 +221,26 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     ny = args.rows_per_gpu
+    NX = args.nx
+    infil = (args.workload == 'kw_ga')
+    WORKLOAD = ('synthetic %s DEM %dx%d per GPU, kinematic wave + Manning, %suniform 50 mm/h rain, '
+                'fp64, dt=1s' % ('closed-form (device-generated)' if args.device_gen else 'fractal',
+                                 ny, NX, 'fused Green-Ampt infiltration (pre-wetted soil, '
+                                 'I0=0.1 m), ' if infil else ''))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    stepper, parts = cases.build_engine(ny, NX, kinematic=True, infil=True, rank=rank, world=world,
-                                        device=dev, return_parts=True)
+    if args.device_gen:
+        stepper = cases.build_engine_device(ny, NX, kinematic=True, infil=infil, rank=rank,
+                                            world=world, device=dev)
+        parts = None
+        args.no_e2e = args.no_e2e or world == 1
+    else:
+        stepper, parts = cases.build_engine(ny, NX, kinematic=True, infil=infil, rank=rank,
+                                            world=world, device=dev, return_parts=True)
     eng = stepper.engine if world > 1 else stepper
     cells = ny * NX * world
     launches_per_step = 1
@@ -277,10 +295,12 @@ def main():
             cfg = write_component_case(work, parts)
             comp = ckw.channels_component()
             comp.device = dev
-            comp.enable_fused_sources(infil=True, I0=cases.I0_WET)
+            if infil:
+                comp.enable_fused_sources(infil=True, I0=cases.I0_WET)
             comp.initialize(cfg_file=cfg, mode='nondriver', SILENT=True)
-            for k, v in cases.GA_TREYNOR.items():
-                comp.set_source_input(k, v)
+            if infil:
+                for k, v in cases.GA_TREYNOR.items():
+                    comp.set_source_input(k, v)
             LONG = {n: ln for ln, n in comp._var_name_map.items()}
             host_in = {n: np.array(0.0) for n in ('MR', 'GW', 'ET', 'IN', 'SM')}
             host_in['P_rain'] = np.array(cases.RAIN_50MMPH)
@@ -337,27 +357,29 @@ def main():
     except (OSError, ValueError):
         pass
     peak = float(peaks.get('hbm_gbs', 6650.0))
-    bpc = BYTES_PER_CELL['kw_ga']
+    bpc = BYTES_PER_CELL[args.workload]
     cells_per_launch = ny * NX
     achieved = cells_per_launch * bpc / (ms_per_step * 1e-3) / 1e9
     traffic = None
     try:
         prof = json.load(open(os.path.join(ROOT, 'profiles', 'kernel_traffic.json')))
-        traffic = prof.get('kw_ga_4096', {}).get('dram_bytes_per_launch')
+        traffic = (prof.get(args.workload + '_4096', {}).get('dram_bytes_per_launch')
+                   if (ny, NX) == (4096, 4096) else None)
     except (OSError, ValueError):
         pass
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'traffic': traffic,
                 'peak_source': 'MEASURED_PEAKS.json hbm_gbs (measured)' if peaks
                 else 'B200_PROFILING.md fallback 6.65 TB/s',
-                'kernel': 'channels_packed_kernel<GA=true> (TMA ring, KW + Manning + fused Green-Ampt)',
+                'kernel': 'channels_packed_kernel<GA=%s> (TMA ring, KW + Manning%s)'
+                          % ('true' if infil else 'false', ' + fused Green-Ampt' if infil else ''),
                 'path': path_used,
                 'algorithmic_bytes_per_cell': bpc, 'cells_per_launch': cells_per_launch,
                 'launch_ms': ms_per_step,
                 'note': 'one launch per step; launch time = timed region / launches (CUDA events)'}
 
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and infil and NX == 4096:
         v, desc, cores, _, _ = cpu_port_rate(15.0)
         cpu = {'value': v, 'unit': 'Gcell-updates/s', 'cores': cores, 'kind': 'port', 'sample': desc}
 

@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, kinematic, infil, q):
+def _worker(rank, world, port, kinematic, infil, q, devgen=False):
     import torch
     import torch.distributed as dist
     from topoflow36_b200 import cases
@@ -31,11 +31,18 @@ def _worker(rank, world, port, kinematic, infil, q):
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
     try:
         ny, nx, steps = 96, 160, 120
-        slab, parts = cases.build_engine(ny, nx, kinematic=kinematic, infil=infil, rank=rank,
-                                         world=world, device=dev, return_parts=True, dt=2.0)
-        one = cases.build_engine(ny * world, nx, kinematic=kinematic, infil=infil, device=dev,
-                                 tile_rows=ny, dt=2.0)
-        lay = parts['layout']
+        if devgen:
+            slab = cases.build_engine_device(ny, nx, kinematic=kinematic, infil=infil, rank=rank,
+                                             world=world, device=dev, dt=2.0, lean_memory=False)
+            one = cases.build_engine_device(ny * world, nx, kinematic=kinematic, infil=infil,
+                                            device=dev, dt=2.0, lean_memory=False)
+            lay = slab.layout
+        else:
+            slab, parts = cases.build_engine(ny, nx, kinematic=kinematic, infil=infil, rank=rank,
+                                             world=world, device=dev, return_parts=True, dt=2.0)
+            one = cases.build_engine(ny * world, nx, kinematic=kinematic, infil=infil, device=dev,
+                                     tile_rows=ny, dt=2.0)
+            lay = parts['layout']
         rows = slice(lay.row0, lay.row0 + lay.ny)
         fails = []
         ok = bool(torch.equal(slab.engine.own(slab.engine.code), one.code[rows]))
@@ -70,8 +77,9 @@ def _worker(rank, world, port, kinematic, infil, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('kinematic,infil', [(True, False), (True, True), (False, False)])
-def test_two_slabs_equal_one_grid(kinematic, infil):
+@pytest.mark.parametrize('kinematic,infil,devgen', [(True, False, False), (True, True, False),
+                                                    (False, False, False), (True, True, True)])
+def test_two_slabs_equal_one_grid(kinematic, infil, devgen):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
@@ -80,7 +88,7 @@ def test_two_slabs_equal_one_grid(kinematic, infil):
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, kinematic, infil, q))
+    procs = [ctx.Process(target=_worker, args=(r, world, port, kinematic, infil, q, devgen))
              for r in range(world)]
     for p in procs:
         p.start()

@@ -63,6 +63,100 @@ def slab_params(ny, nx, row0, halo, seed=1234):
     return width, angle, nval
 
 
+# ---------------------------------------------------------------------------
+# device-side generator for slabs too large to synthesise on the host (65536^2)
+# ---------------------------------------------------------------------------
+def _hash01(r, c, seed):
+    """Uniform [0, 1) float64 from global (row, col): a 64-bit mix evaluated with
+    torch int64 ops (wrapping multiply), identical on every rank."""
+    import torch
+    x = (r * 73856093) ^ (c * 19349663) ^ int(seed)
+    x = x * -7046029254386353131            # 0x9E3779B97F4A7C15 as int64
+    x = x ^ (x >> 29)
+    x = x * -4658895280553007687            # 0xBF58476D1CE4E5B9
+    x = x ^ (x >> 32)
+    return ((x >> 11) & ((1 << 53) - 1)).to(torch.float64) * (1.0 / (1 << 53))
+
+
+def device_slab_dem(ny, nx, row0, ny_global, halo, device, seed=1234, sy=0.02, sx=0.005,
+                    dx=30.0, dy=30.0, sigma=2.0, n_modes=24, jitter=0.25, chunk=512):
+    """float32 DEM rows [row0 - halo, row0 + ny + halo) as a closed-form field of
+    the GLOBAL cell coordinates: tilt + n_modes plane waves with power-law
+    amplitudes (wavelengths 6 .. 6000 cells) + hashed per-cell jitter."""
+    import torch
+    rng = np.random.default_rng(seed)
+    lam = np.exp(rng.uniform(np.log(6.0), np.log(6000.0), n_modes))
+    th = rng.uniform(0, 2 * np.pi, n_modes)
+    ph = rng.uniform(0, 2 * np.pi, n_modes)
+    amp = lam ** 0.6
+    amp *= sigma * np.sqrt(2.0) / np.sqrt((amp ** 2).sum())
+    kx, ky = 2 * np.pi / lam * np.cos(th), 2 * np.pi / lam * np.sin(th)
+    z0 = sy * dy * ny_global + sx * dx * nx + 10.0 * sigma + 100.0
+    out = torch.empty((ny + 2 * halo, nx), dtype=torch.float32, device=device)
+    c = torch.arange(nx, device=device, dtype=torch.float64)[None, :]
+    ci = torch.arange(nx, device=device, dtype=torch.int64)[None, :]
+    for a in range(0, ny + 2 * halo, chunk):
+        b = min(ny + 2 * halo, a + chunk)
+        ri = torch.arange(row0 - halo + a, row0 - halo + b, device=device, dtype=torch.int64)[:, None]
+        r = ri.to(torch.float64)
+        z = z0 - (sy * dy) * r - (sx * dx) * c
+        for m in range(n_modes):
+            z = z + amp[m] * torch.sin(kx[m] * c + ky[m] * r + ph[m])
+        z = z + jitter * (_hash01(ri, ci, seed) - 0.5)
+        out[a:b] = z.to(torch.float32)
+    return out
+
+
+def device_slab_params(ny, nx, row0, halo, device, seed=1234, chunk=2048):
+    """width and Manning n (float32-exact float64 tensors) for the rows of a slab."""
+    import torch
+    width = torch.empty((ny + 2 * halo, nx), dtype=torch.float64, device=device)
+    nval = torch.empty_like(width)
+    ci = torch.arange(nx, device=device, dtype=torch.int64)[None, :]
+    for a in range(0, ny + 2 * halo, chunk):
+        b = min(ny + 2 * halo, a + chunk)
+        ri = torch.arange(row0 - halo + a, row0 - halo + b, device=device, dtype=torch.int64)[:, None]
+        width[a:b] = (1.0 + 4.0 * _hash01(ri, ci, seed + 11)).float().double()
+        nval[a:b] = (0.03 + 0.02 * _hash01(ri, ci, seed + 23)).float().double()
+    return width, nval
+
+
+def build_engine_device(ny, nx, kinematic=True, infil=False, dt=1.0, rank=0, world=1, seed=1234,
+                        device=None, group=None, link_flats=True, lean_memory=True):
+    """Like build_engine, but every array is generated on the GPU (any size that
+    fits HBM) and the generic fp64 static inputs are released once the packed
+    encoding exists."""
+    import torch
+    from .routing import ChannelsEngine
+    from .slab import SlabLayout, SlabChannels, slab_d8
+    ny_global = ny * world
+    halo = 0 if world == 1 else (1 if kinematic else 2)
+    lay = SlabLayout(ny_global, nx, rank, world, halo)
+    hd = halo + 1 if world > 1 else 0
+    DEM = device_slab_dem(ny, nx, lay.row0, ny_global, hd, device, seed=seed)
+    d8 = slab_d8(DEM, lay, hd, link_flats=link_flats, kinematic=kinematic, device=device,
+                 group=group)
+    del DEM
+    width, nval = device_slab_params(ny, nx, lay.row0, halo, device, seed=seed)
+    ang = float(np.float64(np.float32(45.0)) * (np.pi / np.float64(180)))
+    eng = ChannelsEngine(ny, nx, dt=dt, code=d8['code'], dx=d8['dx'], dy=d8['dy'], dd=d8['dd'],
+                         S_bed=d8['S_bed'], width=width, angle=ang, tan_angle=float(np.tan(ang)),
+                         cos_angle=float(np.cos(ang)), rough=nval, kinematic=kinematic,
+                         outlet=(ny_global - 2, nx // 2), row0=lay.row0, ny_global=ny_global,
+                         halo=halo, device=device, finalize=True, n_pixels_global=ny * nx)
+    del width, nval, d8
+    eng.set_input('P_rain', RAIN_50MMPH)
+    if infil:
+        eng.enable_fused_sources(infil=True, I0=I0_WET)
+        for k, v in GA_TREYNOR.items():
+            eng.set_input(k, v)
+    if lean_memory and eng.packed is not None:
+        eng.release_generic_inputs()
+    torch.cuda.current_stream().synchronize()
+    torch.cuda.empty_cache()
+    return SlabChannels(lay, eng, group) if world > 1 else eng
+
+
 def build_engine(ny, nx, kinematic=True, infil=False, diag=False, dt=1.0, rank=0, world=1,
                  seed=1234, device=None, group=None, link_flats=True, return_parts=False,
                  tile_rows=None):

@@ -173,23 +173,32 @@ class ChannelsEngine(object):
         w32 = width.float()
         if not bool((w32.double() == width).all()):
             return
-        tan = full(self.tan_angle_grid, a.tan_angle.val)
-        cos = full(self.cos_angle_grid, a.cos_angle.val)
-        key = torch.stack((tan.reshape(-1), cos.reshape(-1)), dim=1)
-        uniq, inv = torch.unique(key, dim=0, return_inverse=True)
-        if uniq.shape[0] > 256:
-            return
+        del width
+        if self.tan_angle_grid is None and self.cos_angle_grid is None:
+            uniq = torch.tensor([[a.tan_angle.val, a.cos_angle.val]], dtype=torch.float64,
+                                device=dev)
+            inv = None
+        else:
+            tan = full(self.tan_angle_grid, a.tan_angle.val)
+            cos = full(self.cos_angle_grid, a.cos_angle.val)
+            key = torch.stack((tan.reshape(-1), cos.reshape(-1)), dim=1)
+            uniq, inv = torch.unique(key, dim=0, return_inverse=True)
+            del key, tan, cos
+            if uniq.shape[0] > 256:
+                return
         t, c = uniq[:, 0], uniq[:, 1]
         lut = torch.zeros((uniq.shape[0], 4), dtype=torch.float64, device=dev)
         lut[:, 0] = t
         lut[:, 1] = torch.where(t == 0, torch.zeros_like(t), 1.0 / (2.0 * t))
         lut[:, 2] = 1.0 / c
         lut[:, 3] = 2.0 * (2.0 * t)
-        aidx = inv.to(torch.uint8).reshape(self.ny, self.nx).contiguous()
+        aidx = (None if inv is None
+                else inv.to(torch.uint8).reshape(self.ny, self.nx).contiguous())
         rough = full(self.rough_grid, a.rough.val)
         coef = (self.own(self.sqrtS) / rough).contiguous()
         geo32 = torch.empty((self.ny, self.nx), dtype=torch.int32, device=dev)
-        L.check(self.lib.tfb_channels_pack_geo32(self._p(self.code), aidx.data_ptr(), self.ny,
+        L.check(self.lib.tfb_channels_pack_geo32(self._p(self.code),
+                                                 None if aidx is None else aidx.data_ptr(), self.ny,
                                                  self.nx, self.halo, geo32.data_ptr(),
                                                  L.stream_ptr()), 'tfb_channels_pack_geo32')
         rowg = torch.empty((self.ny, 6), dtype=torch.float64, device=dev)
@@ -208,6 +217,21 @@ class ChannelsEngine(object):
         self._pack_keep = (geo32, w32.contiguous(), coef, lut, rowg)
         pk.width32 = self._pack_keep[1].data_ptr()
         self.packed = pk
+
+    def release_generic_inputs(self):
+        """Free the fp64 static grids the packed path does not read (width, tan,
+        cos, roughness, S_bed, sqrt|S_bed|, 16-bit geo): ~42 B/cell.  Afterwards
+        only configurations the packed kernel accepts can be stepped."""
+        if self.packed is None:
+            raise L.TfbError('release_generic_inputs: no packed encoding was built')
+        a = self.args
+        for n in ('width', 'tan_angle', 'cos_angle', 'rough'):
+            if getattr(self, n + '_grid') is not None:
+                setattr(self, n + '_grid', None)
+                setattr(a, n, L.SG(None, float('nan')))
+        self.S_bed = self.sqrtS = self.geo = None
+        a.S_bed = a.sqrtS = a.geo = None
+        self.generic_released = True
 
     def _packed_ok(self):
         """Per-step eligibility: uniform forcing, at most scalar Green-Ampt fused."""
@@ -429,6 +453,9 @@ class ChannelsEngine(object):
                                                       L.stream_ptr()), 'tfb_channels_step_packed')
             self.last_path = 'packed'
         else:
+            if getattr(self, 'generic_released', False):
+                raise L.TfbError('this configuration needs the generic kernel, but its static '
+                                 'inputs were released (release_generic_inputs)')
             L.check(self.lib.tfb_channels_step(C.byref(a), L.stream_ptr()), 'tfb_channels_step')
             self.last_path = 'generic'
         self.qcur ^= 1

@@ -195,7 +195,8 @@ def slab_d8(DEM, layout, dem_halo, link_flats=True, xres=30.0, yres=30.0, nodata
     else:
         if dem_halo < H + 1:
             raise ValueError('dem_halo must be >= halo + 1')
-        dem = torch.as_tensor(np.ascontiguousarray(DEM, dtype=np.float32)).to(dev)
+        dem = (DEM.to(device=dev, dtype=torch.float32).contiguous() if isinstance(DEM, torch.Tensor)
+               else torch.as_tensor(np.ascontiguousarray(DEM, dtype=np.float32)).to(dev))
         top = layout.row0 - dem_halo                      # global row of dem[0]
         lo, hi = max(0, layout.row0 - H), min(NY, layout.row0 + ny + H)
         code16 = torch.zeros((ny + 2 * H, nx), dtype=torch.int16, device=dev)
