@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 
 NY_PER_GPU = 4096
 NX = 4096
-BYTES_PER_CELL = {'kw': 81, 'kw_ga': 97, 'dw': 106}
+BYTES_PER_CELL = {'kw': 81, 'kw_ga': 97, 'dw': 106, 'dw_full': 146}
 METRIC = 'routing Gcell-updates/sec'
 WORKLOAD = ('synthetic fractal DEM %dx%d per GPU, kinematic wave + Manning, fused Green-Ampt '
             'infiltration (pre-wetted soil, I0=0.1 m), uniform 50 mm/h rain, fp64, dt=1s'
@@ -193,8 +193,9 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--rows-per-gpu', type=int, default=NY_PER_GPU)
     ap.add_argument('--nx', type=int, default=NX)
-    ap.add_argument('--workload', default='kw_ga', choices=['kw_ga', 'kw'],
-                    help='kw_ga = BASELINE configs[1] (default); kw = configs[4] (no infiltration)')
+    ap.add_argument('--workload', default='kw_ga', choices=['kw_ga', 'kw', 'dw', 'dw_full'],
+                    help='kw_ga = BASELINE configs[1] (default); kw = configs[4]; dw_full = '
+                         'configs[3] (diffusive wave + met/snow/evap/infil fused); dw = diffusive only')
     ap.add_argument('--device-gen', action='store_true',
                     help='synthesise the case on the GPU (needed for 65536-wide slabs)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -223,10 +224,14 @@ def main():
     ny = args.rows_per_gpu
     NX = args.nx
     infil = (args.workload == 'kw_ga')
-    WORKLOAD = ('synthetic %s DEM %dx%d per GPU, kinematic wave + Manning, %suniform 50 mm/h rain, '
+    kin = args.workload.startswith('kw')
+    sources = {'kw_ga': 'ga', 'kw': 'none', 'dw': 'none', 'dw_full': 'full'}[args.workload]
+    WORKLOAD = ('synthetic %s DEM %dx%d per GPU, %s wave + Manning, %suniform 50 mm/h rain, '
                 'fp64, dt=1s' % ('closed-form (device-generated)' if args.device_gen else 'fractal',
-                                 ny, NX, 'fused Green-Ampt infiltration (pre-wetted soil, '
-                                 'I0=0.1 m), ' if infil else ''))
+                                 ny, NX, 'kinematic' if kin else 'diffusive',
+                                 {'ga': 'fused Green-Ampt infiltration (pre-wetted soil, I0=0.1 m), ',
+                                  'none': '', 'full': 'fused rain/snow split + degree-day melt + '
+                                  'Priestley-Taylor ET + Green-Ampt (T_air grid), '}[sources]))
 
     def barrier():
         if world > 1:
@@ -234,16 +239,17 @@ def main():
         torch.cuda.synchronize()
 
     if args.device_gen:
-        stepper = cases.build_engine_device(ny, NX, kinematic=True, infil=infil, rank=rank,
+        stepper = cases.build_engine_device(ny, NX, kinematic=kin, sources=sources, rank=rank,
                                             world=world, device=dev)
         parts = None
         args.no_e2e = args.no_e2e or world == 1
     else:
-        stepper, parts = cases.build_engine(ny, NX, kinematic=True, infil=infil, rank=rank,
+        stepper, parts = cases.build_engine(ny, NX, kinematic=kin, sources=sources, rank=rank,
                                             world=world, device=dev, return_parts=True)
+        args.no_e2e = args.no_e2e or (world == 1 and args.workload != 'kw_ga' and args.workload != 'kw')
     eng = stepper.engine if world > 1 else stepper
     cells = ny * NX * world
-    launches_per_step = 1
+    launches_per_step = 1 if kin else 2
 
     # ---- `value`: state resident in HBM, no host round trip per step ----------
     tmin = 0.0
@@ -371,12 +377,13 @@ def main():
                 'frac': achieved / peak, 'traffic': traffic,
                 'peak_source': 'MEASURED_PEAKS.json hbm_gbs (measured)' if peaks
                 else 'B200_PROFILING.md fallback 6.65 TB/s',
-                'kernel': 'channels_packed_kernel<GA=%s> (TMA ring, KW + Manning%s)'
-                          % ('true' if infil else 'false', ' + fused Green-Ampt' if infil else ''),
+                'kernel': ('channels_packed_kernel<SRC=%s, %s>%s (TMA ring)'
+                           % (sources, 'KW' if kin else 'DW pass A', '' if kin else
+                              ' + channels_packed_dwb_kernel (both launches of the step)')),
                 'path': path_used,
                 'algorithmic_bytes_per_cell': bpc, 'cells_per_launch': cells_per_launch,
                 'launch_ms': ms_per_step,
-                'note': 'one launch per step; launch time = timed region / launches (CUDA events)'}
+                'note': '%d launch(es) per step; time = timed region / steps (CUDA events)' % launches_per_step}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline and infil and NX == 4096:

@@ -276,6 +276,9 @@ typedef struct {
                                  noflow, diagonal, N/S) and the 3 reciprocals    */
     double outlet_rough;      /* Manning n of the outlet cell (f_outlet only)    */
     int32_t n_angles;
+    /* diffusive wave only (coef may then be NULL): */
+    const double *inv_rough;  /* 1 / n                                   (8 B / cell) */
+    const float *S32;         /* bed slope as float32 (lossless)         (4 B / cell) */
 } tfb_channels_packed;
 
 int64_t tfb_sizeof_channels_packed(void);
@@ -298,6 +301,18 @@ int tfb_channels_pack_rows(const float *dx, const float *dy, const float *dd,
  * I_out; uses a->partials / ticket / scalars like tfb_channels_step. */
 int tfb_channels_step_packed(const tfb_channels_step_args *a,
                              const tfb_channels_packed *p, void *stream);
+
+/* Diffusive wave through the packed path: two launches per step.  Pass A updates
+ * the volumes and writes the NEW depth of every cell (update_flow_volume :1951,
+ * update_channel_depth :2250, fused sources, volume integrals); a slab run then
+ * exchanges one boundary row of `d`; pass B forms the free-surface slope from the
+ * new depths of each cell and its D8 parent (update_free_surface_slope
+ * :2583-2618), the velocity and the next discharge, and zeroes the depth of
+ * noflow cells.  Same eligibility rules as tfb_channels_step_packed. */
+int tfb_channels_step_packed_dw_a(const tfb_channels_step_args *a,
+                                  const tfb_channels_packed *p, void *stream);
+int tfb_channels_step_packed_dw_b(const tfb_channels_step_args *a,
+                                  const tfb_channels_packed *p, void *stream);
 
 /* multi-GPU: fold globally reduced sums (DEVICE, TFB_NSUM doubles laid out as
  * tfb_channels_step leaves them in partials[]) into the scalar block */

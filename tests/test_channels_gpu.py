@@ -257,17 +257,25 @@ def test_fused_sources_match_oracle_composition(sources_gold):
         assert abs(s.vol_ET - vol_ET) <= 1e-11 * abs(vol_ET)
 
 
-@pytest.mark.parametrize('infil', [False, True])
-def test_packed_path_2048_vs_c_oracle(infil):
-    """The benchmarked kernel (TMA ring, packed inputs) at a size the numpy oracle
-    cannot handle: 2048 x 2048, 60 steps, against the multithreaded C restatement
-    (pinned to the reference in test_c_oracle.py), plus exact mass conservation."""
+FULL_SRC = dict(met=True, snow=True, evap=True, infil=True, T_rain_snow=1.0, rho_snow=300.0,
+                alpha=0.95, K_soil=0.45, soil_x=0.05, T_soil_x=20.0, h0_swe=0.004, I0=0.05)
+
+
+@pytest.mark.parametrize('kinematic,src', [(True, 'none'), (True, 'ga'), (True, 'full'),
+                                           (False, 'none'), (False, 'ga'), (False, 'full')])
+def test_packed_path_vs_c_oracle(kinematic, src):
+    """The benchmarked kernels (TMA ring, packed inputs; kinematic = one launch,
+    diffusive = two passes) at a size the numpy oracle cannot handle -- 2048^2
+    kinematic, 1024^2 diffusive -- for 60 steps against the multithreaded C
+    restatement (pinned to the reference in test_c_oracle.py), with uniform
+    forcing, fused Green-Ampt, or all four fused sources with a T_air grid; plus
+    exact mass conservation."""
     import os
     import torch
     from oracle import c_oracle
     from topoflow36_b200 import cases
     from topoflow36_b200.d8 import D8Toolkit
-    ny = nx = 2048
+    ny = nx = 2048 if kinematic else 1024
     tile = cases.noise_tile(ny, nx, seed=5)
     DEM = cases.slab_dem(ny, nx, 0, ny, 0, tile)
     width, angle, nval = cases.slab_params(ny, nx, 0, 0, seed=5)
@@ -279,32 +287,45 @@ def test_packed_path_2048_vs_c_oracle(infil):
     slope = tk.slope().cpu().numpy()
     dx, dy, dd = o.pixel_dims(ny, 30.0, 30.0)
     eng = _engine(code, dx, dy, dd, slope, width, angle, nval, dt=1.0, da=900.0,
-                  outlet=(ny - 2, nx // 2))
+                  kinematic=kinematic, outlet=(ny - 2, nx // 2))
     ch = c_oracle.Channels(code, dx, dy, dd, slope, width, angle, nval, dt=1.0,
-                           outlet=(ny - 2, nx // 2), diag=False)
+                           kinematic=kinematic, outlet=(ny - 2, nx // 2), diag=False)
     ch.nthreads = os.cpu_count() or 1
-    eng.set_input('P_rain', cases.RAIN_50MMPH)
-    ch.set_input('P_rain', cases.RAIN_50MMPH)
-    if infil:
+    both = lambda n, v: (eng.set_input(n, v), ch.set_input(n, v))
+    both('P_rain', cases.RAIN_50MMPH)
+    if src == 'ga':
         eng.enable_fused_sources(infil=True, I0=cases.I0_WET)
         ch.enable_fused(infil=True, I0=cases.I0_WET)
-        for k, v in cases.GA_TREYNOR.items():
-            eng.set_input(k, v)
-            ch.set_input(k, v)
+    elif src == 'full':
+        eng.enable_fused_sources(**FULL_SRC)
+        ch.enable_fused(**FULL_SRC)
+        rng = np.random.default_rng(3)
+        both('T_air', 2.0 + 3.0 * (2.0 * rng.random((ny, nx)) - 1.0))
+        for n, v in (('c0', 2.7), ('T0', -0.2), ('T_surf', 5.0), ('Qn_SW', 300.0),
+                     ('Qn_LW', -40.0), ('GW', 1e-7), ('MR', 2e-8)):
+            both(n, v)
+    if src != 'none':
+        for n, v in cases.GA_TREYNOR.items():
+            both(n, v)
     for i in range(60):
         eng.step(time_min=i / 60.0)
         ch.time_min = i / 60.0
         ch.step()
     assert eng.last_path == 'packed'
-    for n in ('vol', 'd', 'u', 'Q'):
-        got = (eng.Q if n == 'Q' else eng.vol if n == 'vol' else eng.own(getattr(eng, n)))
+    names = ('vol', 'd', 'u', 'Q') + (('I',) if src != 'none' else ()) + \
+        (('h_swe',) if src == 'full' else ())
+    for n in names:
+        got = (eng.Q if n == 'Q' else getattr(eng, n) if n in ('vol', 'I', 'h_swe')
+               else eng.own(getattr(eng, n)))
         e = rel_err(got.cpu().numpy(), getattr(ch, n))
         assert e <= RTOL, '%s rel err %.3e' % (n, e)
     s = eng.read_scalars()
-    for n in ('vol_R', 'vol_edge', 'vol_Q', 'Q_outlet', 'Q_peak', 'vol_IN'):
+    for n in ('vol_R', 'vol_edge', 'vol_Q', 'Q_outlet', 'Q_peak', 'vol_IN', 'vol_SM', 'vol_ET',
+              'vol_P', 'vol_PR', 'vol_PS'):
         want = float(getattr(ch, n))
         assert abs(getattr(s, n) - want) <= 1e-11 * max(abs(want), 1e-300), n
     # water is conserved: runoff in = stored in channels + left through the edges
     stored = float(eng.vol.sum())
-    assert abs(s.vol_R - (stored + s.vol_edge)) <= 1e-10 * s.vol_R
+    assert abs(s.vol_R - (stored + s.vol_edge)) <= 1e-10 * abs(s.vol_R)
     assert s.n_neg_d == s.n_nan_d == s.n_inf_d == s.n_neg_u == s.n_nan_u == s.n_inf_u == 0
+    assert float(eng.Q.max()) > 0

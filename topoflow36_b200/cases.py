@@ -21,6 +21,36 @@ from . import synth
 GA_TREYNOR = dict(Ks=7.2e-6, Ki=1e-7, qs=0.485, qi=0.375808, G=0.724)
 RAIN_50MMPH = 50.0 / 3.6e6
 I0_WET = 0.1
+# BASELINE configs[3] source terms: T_air = 2 C +- 3 C noise (grid), degree-day
+# c0 = 2.7 mm/day/C, T0 = -0.2 C, h0_swe = 0.1 m, rho_snow = 300; Priestley-Taylor alpha = 0.95,
+# K_soil = 0.45, soil_x = 0.05, T_soil_x = 20 (cfg_templates/Test1); Green-Ampt as above
+FULL_SOURCES = dict(met=True, snow=True, evap=True, infil=True, T_rain_snow=1.0, rho_snow=300.0,
+                    alpha=0.95, K_soil=0.45, soil_x=0.05, T_soil_x=20.0, h0_swe=0.1, I0=I0_WET)
+FULL_SCALARS = dict(c0=2.7, T0=-0.2, T_surf=5.0, Qn_SW=300.0, Qn_LW=-40.0)
+
+
+def apply_sources(eng, mode, row0=0, halo=0, seed=1234):
+    """mode: 'none' | 'ga' (fused Green-Ampt) | 'full' (met + snow + evap + infil fused,
+    T_air a grid keyed by the GLOBAL cell so slabs agree)."""
+    import torch
+    eng.set_input('P_rain', RAIN_50MMPH)
+    if mode == 'none':
+        return
+    if mode == 'ga':
+        eng.enable_fused_sources(infil=True, I0=I0_WET)
+    else:
+        eng.enable_fused_sources(**FULL_SOURCES)
+        ny, nx = eng.ny, eng.nx
+        dev = eng.device
+        ri = torch.arange(row0 - halo, row0 + ny + halo, device=dev, dtype=torch.int64)[:, None]
+        ci = torch.arange(nx, device=dev, dtype=torch.int64)[None, :]
+        T_air = 2.0 + 3.0 * (2.0 * _hash01(ri, ci, seed + 5) - 1.0)
+        eng.set_input('T_air', T_air if halo else T_air.contiguous())
+        for k, v in FULL_SCALARS.items():
+            eng.set_input(k, v)
+    for k, v in GA_TREYNOR.items():
+        eng.set_input(k, v)
+
 
 
 def noise_tile(ny, nx, seed=1234, sigma=2.0, beta=2.2):
@@ -122,7 +152,7 @@ def device_slab_params(ny, nx, row0, halo, device, seed=1234, chunk=2048):
 
 
 def build_engine_device(ny, nx, kinematic=True, infil=False, dt=1.0, rank=0, world=1, seed=1234,
-                        device=None, group=None, link_flats=True, lean_memory=True):
+                        device=None, group=None, link_flats=True, lean_memory=True, sources=None):
     """Like build_engine, but every array is generated on the GPU (any size that
     fits HBM) and the generic fp64 static inputs are released once the packed
     encoding exists."""
@@ -145,11 +175,7 @@ def build_engine_device(ny, nx, kinematic=True, infil=False, dt=1.0, rank=0, wor
                          outlet=(ny_global - 2, nx // 2), row0=lay.row0, ny_global=ny_global,
                          halo=halo, device=device, finalize=True, n_pixels_global=ny * nx)
     del width, nval, d8
-    eng.set_input('P_rain', RAIN_50MMPH)
-    if infil:
-        eng.enable_fused_sources(infil=True, I0=I0_WET)
-        for k, v in GA_TREYNOR.items():
-            eng.set_input(k, v)
+    apply_sources(eng, sources or ('ga' if infil else 'none'), row0=lay.row0, halo=halo, seed=seed)
     if lean_memory and eng.packed is not None:
         eng.release_generic_inputs()
     torch.cuda.current_stream().synchronize()
@@ -159,7 +185,7 @@ def build_engine_device(ny, nx, kinematic=True, infil=False, dt=1.0, rank=0, wor
 
 def build_engine(ny, nx, kinematic=True, infil=False, diag=False, dt=1.0, rank=0, world=1,
                  seed=1234, device=None, group=None, link_flats=True, return_parts=False,
-                 tile_rows=None):
+                 tile_rows=None, sources=None):
     """Engine (and SlabChannels wrapper when world > 1) for rank `rank` of a
     (world*ny, nx) synthetic grid."""
     import torch
@@ -171,7 +197,8 @@ def build_engine(ny, nx, kinematic=True, infil=False, diag=False, dt=1.0, rank=0
     tile = noise_tile(tile_rows or ny, nx, seed=seed)
     hd = halo + 1 if world > 1 else 0             # DEM halo: one more row than the codes need
     DEM = slab_dem(ny, nx, lay.row0, ny_global, hd, tile)
-    d8 = slab_d8(DEM, lay, hd, link_flats=link_flats, device=device, group=group)
+    d8 = slab_d8(DEM, lay, hd, link_flats=link_flats, kinematic=kinematic, device=device,
+                 group=group)
     width, angle, nval = slab_params(ny, nx, lay.row0, halo, seed=seed)
     DEG = np.pi / np.float64(180)
     ang = np.float64(angle) * DEG
@@ -181,11 +208,7 @@ def build_engine(ny, nx, kinematic=True, infil=False, diag=False, dt=1.0, rank=0
                          outlet=(ny_global - 2, nx // 2), row0=lay.row0, ny_global=ny_global,
                          halo=halo, device=device, finalize=True,
                          n_pixels_global=ny * nx)
-    eng.set_input('P_rain', RAIN_50MMPH)
-    if infil:
-        eng.enable_fused_sources(infil=True, I0=I0_WET)
-        for k, v in GA_TREYNOR.items():
-            eng.set_input(k, v)
+    apply_sources(eng, sources or ('ga' if infil else 'none'), row0=lay.row0, halo=halo, seed=seed)
     torch.cuda.current_stream().synchronize()
     stepper = SlabChannels(lay, eng, group) if world > 1 else eng
     if return_parts:

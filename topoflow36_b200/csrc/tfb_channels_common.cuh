@@ -35,7 +35,8 @@ struct Acc {
 };
 
 // fold the (locally or globally) reduced sums into the scalar block -------------
-__device__ inline void fold_scalars(const tfb_channels_step_args &a, const double *h) {
+// (a) the volume integrals
+__device__ inline void fold_sums(const tfb_channels_step_args &a, const double *h) {
     tfb_channels_scalars &s = *a.scalars;
     const double dt = a.dt;
     if (a.is_R_grid) {
@@ -49,10 +50,14 @@ __device__ inline void fold_scalars(const tfb_channels_step_args &a, const doubl
     s.vol_edge += h[S_VOL_EDGE];
     s.vol_P += h[S_VOL_P];   s.vol_PR += h[S_VOL_PR]; s.vol_PS += h[S_VOL_PS];
     s.vol_SM += h[S_VOL_SM]; s.vol_ET += h[S_VOL_ET]; s.vol_IN += h[S_VOL_IN];
+    s.n_nan_IN = (int64_t)h[S_NNAN_IN];
+}
+// (b) stability counters, outlet sample, peaks, outlet integral, step counter
+__device__ inline void fold_status(const tfb_channels_step_args &a, const double *h) {
+    tfb_channels_scalars &s = *a.scalars;
     s.n_neg_d = (int64_t)h[S_NNEG_D]; s.n_nan_d = (int64_t)h[S_NNAN_D];
     s.n_inf_d = (int64_t)h[S_NINF_D]; s.n_neg_u = (int64_t)h[S_NNEG_U];
     s.n_nan_u = (int64_t)h[S_NNAN_U]; s.n_inf_u = (int64_t)h[S_NINF_U];
-    s.n_nan_IN = (int64_t)h[S_NNAN_IN];
     s.dt_cfl_min = h[P_DTMIN];
     if (h[P_HASOUT_SUM] != 0.0) {
         s.Q_outlet = h[P_QOUT]; s.u_outlet = h[P_UOUT];
@@ -62,9 +67,12 @@ __device__ inline void fold_scalars(const tfb_channels_step_args &a, const doubl
     if (s.Q_outlet > s.Q_peak) { s.Q_peak = s.Q_outlet; s.T_peak = a.time_min; }
     if (s.u_outlet > s.u_peak) { s.u_peak = s.u_outlet; s.Tu_peak = a.time_min; }
     if (s.d_outlet > s.d_peak) { s.d_peak = s.d_outlet; s.Td_peak = a.time_min; }
-    s.vol_Q += (s.Q_outlet * dt);
+    s.vol_Q += (s.Q_outlet * a.dt);
     s.step_count += 1;
 }
-
+__device__ inline void fold_scalars(const tfb_channels_step_args &a, const double *h) {
+    fold_sums(a, h);
+    fold_status(a, h);
+}
 
 }  // namespace tfb

@@ -36,12 +36,17 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <string.h>
+
 #include <mutex>
 #include <vector>
 
 namespace tfb {
 
 constexpr unsigned kFull = 0xffffffffu;
+
+enum { PK_SRC_NONE = 0, PK_SRC_GA = 1, PK_SRC_FULL = 2 };   // fused-source mode
+enum { PK_KW = 0, PK_DWA = 1 };                              // main-kernel variant
 
 struct PkConsts {
     double g, dt, da;
@@ -51,6 +56,12 @@ struct PkConsts {
     double Ks, gkq;          // Green-Ampt: Ks, (G*(Ks-Ki))*(qs-qi)
     int low_rain;            // P_total < Ks  (infil_base.py:954-995)
     int n_tiles, tiles_x;
+    // general fused sources (PK_SRC_FULL): every parameter a scalar, T_air may be a grid
+    unsigned flags;
+    int tair_grid;
+    double P, SMv, GW, MR, ETv, INv, T_air, T_rs;
+    double c0_864, T0, ratio;                    // c0 / 8.64e7, T0, rho_H2O / rho_snow
+    double Qc, Qnet, alpha;                      // K_soil (T_surf - T_soil_x) / soil_x, Qn_SW + Qn_LW
 };
 
 __global__ void pack_rows_kernel(const float *__restrict__ dx, const float *__restrict__ dy,
@@ -126,237 +137,212 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
            "r"(c0), "r"(c1) : "memory");
 }
 
-// tile geometry: 64 columns x 16 rows; consumer warp w owns row w, a lane 2 cells
-constexpr int kTW = 64, kTR = 16;
-constexpr int kQW = kTW + 4, kQR = kTR + 2;          // dt*Q halo box (cols c0-2 .. c0+65)
+// tile geometry: 64 columns x 15 rows; consumer warp w owns row w, a lane 2 cells
+#ifndef TFB_PK_ROWS
+#define TFB_PK_ROWS 15      // 15 consumer warps + 1 producer warp = 512 threads: 128 registers each
+#endif
+constexpr int kTW = 64, kTR = TFB_PK_ROWS;
+constexpr int kQW = kTW + 4, kQR = kTR + 2;          // halo box: cols c0-2 .. c0+65, rows r0-1 .. r0+16
 constexpr int kConsumerWarps = kTR;
 constexpr int kThreads = (kConsumerWarps + 1) * 32;  // + 1 producer warp
 constexpr int kSzQ = ((kQW * kQR * 8 + 127) / 128) * 128;
 constexpr int kSzD = kTW * kTR * 8;                  // one fp64 tile
 constexpr int kSzF = kTW * kTR * 4;                  // one 32-bit tile
+constexpr int kSmemBudget = 196 * 1024;              // dynamic shared memory for the ring
 
-template <bool GA> struct StageLayout {
+// ring slot of the main kernel (kinematic step, or pass A of the diffusive step)
+template <int SRC, int VAR> struct StageLayout {
+    static constexpr bool kCoef = (VAR == PK_KW);
+    static constexpr bool kI = (SRC != PK_SRC_NONE);
+    static constexpr bool kFullSrc = (SRC == PK_SRC_FULL);
     static constexpr int oQ = 0;
     static constexpr int oVol = oQ + kSzQ;
     static constexpr int oCoef = oVol + kSzD;
-    static constexpr int oI = oCoef + kSzD;
-    static constexpr int oW = oI + (GA ? kSzD : 0);
+    static constexpr int oI = oCoef + (kCoef ? kSzD : 0);
+    static constexpr int oH = oI + (kI ? kSzD : 0);          // h_swe   (FULL only)
+    static constexpr int oT = oH + (kFullSrc ? kSzD : 0);    // T_air   (FULL only)
+    static constexpr int oW = oT + (kFullSrc ? kSzD : 0);
     static constexpr int oGeo = oW + kSzF;
     static constexpr int bytes = oGeo + kSzF;
-    static constexpr int tx_bytes = kQW * kQR * 8 + kSzD * (GA ? 3 : 2) + 2 * kSzF;
-    static constexpr int stages = GA ? 4 : 5;
+    static constexpr int stages = (kSmemBudget / bytes) > 6 ? 6 : (kSmemBudget / bytes);
+};
+// ring slot of pass B of the diffusive step
+struct StageLayoutB {
+    static constexpr int oD = 0;                             // new depth with halo
+    static constexpr int oN = oD + kSzQ;                     // 1 / n
+    static constexpr int oS = oN + kSzD;                     // S_bed (f32)
+    static constexpr int oW = oS + kSzF;
+    static constexpr int oGeo = oW + kSzF;
+    static constexpr int bytes = oGeo + kSzF;
+    static constexpr int tx_bytes = kQW * kQR * 8 + kSzD + 3 * kSzF;
+    static constexpr int stages = 6;
 };
 
-struct PkOut { double vol, d, u, Qn, I; };
+struct PkIn { unsigned g; double vol, I, h, Ta, w, qself, ch[8]; };
+struct PkVD { double v, d, I, h; };    // new volume / depth before the noflow zeroing, new state
 
-template <bool GA>
-__device__ __forceinline__ void pk_cell(const tfb_channels_step_args &a, const PkConsts &k,
-                                        const double *__restrict__ lut, unsigned g, double vol,
-                                        double Iv, double w, double coef, double qself,
-                                        double c0_, double c1_, double c2_, double c3_,
-                                        double c4_, double c5_, double c6_, double c7_,
-                                        const double *__restrict__ rg, int r, int c,
-                                        const tfb_channels_packed &p, Acc &acc, float &rate_max,
-                                        PkOut &o) {
-    const unsigned code = g & 0xffu, cmask = (g >> 8) & 0xffu, ai = (g >> 16) & 0xffu;
-    const bool noflow = (code == 0);
-    const int cls = (code & 0x55u) ? 1 : ((code & 0x88u) ? 2 : 0);
-    const double ds = rg[cls], inv_ds = rg[3 + cls];
+// new volume and depth of one cell: update_R :1548, update_flow_volume :1951,
+// update_channel_depth :2250 (+ the fused source terms in front of them)
+template <int SRC>
+__device__ __forceinline__ void pk_vol_depth(const PkConsts &k, const double *__restrict__ lut,
+                                             const PkIn &x, const double2 g0, const double2 g1,
+                                             const double2 g2, Acc &acc, PkVD &o) {
+    const unsigned code = x.g & 0xffu, cmask = (x.g >> 8) & 0xffu, ai = (x.g >> 16) & 0xffu;
+    // row_geom = {ds_ew, ds_diag, ds_ns, 1/ds_ew, 1/ds_diag, 1/ds_ns}
+    const bool dg = (code & 0x55u) != 0u, ns = (code & 0x88u) != 0u;
+    const double ds = dg ? g0.y : (ns ? g1.x : g0.x);
+    const double inv_ds = dg ? g2.x : (ns ? g2.y : g1.y);
     const double dt = k.dt;
     double v;
-    if (GA) {
-        const double fc = (k.gkq / Iv) + k.Ks;                        // :540-542
+    o.I = 0.0; o.h = 0.0;
+    if (SRC == PK_SRC_GA) {
+        const double fc = (k.gkq / x.I) + k.Ks;                       // infil_green_ampt :540-542
         double IN = np_min(fc, k.P_total);                            // :567
         if (k.low_rain) IN = k.P_total;                               // infil_base :984-993
-        o.I = Iv + (IN * dt);                                         // :797
+        o.I = x.I + (IN * dt);                                        // :797
         acc.s[S_VOL_IN] += (IN * k.da) * dt;                          // :732-736
         if (!isfinite(IN)) acc.n[S_NNAN_IN - kNSum] += 1u;
         const double R = k.Psum - (0.0 + IN);                         // channels_base :1649
         const double Rv = (R * k.da) * dt;
         acc.s[S_VOL_R] += Rv;                                         // :1666-1670
-        v = vol + Rv;                                                 // :2086
+        v = x.vol + Rv;                                               // :2086
+    } else if (SRC == PK_SRC_FULL) {
+        const double Ta = k.tair_grid ? x.Ta : k.T_air;
+        double P_rain = k.P, P_snow = 0.0, SM = k.SMv, ET = 0.0, IN = k.INv;
+        bool et_grid = false;
+        if (k.flags & TFB_CH_SRC_MET) {                               // met_base :1300-1388
+            P_rain = k.P * ((Ta > k.T_rs) ? 1.0 : 0.0);
+            P_snow = k.P * ((Ta <= k.T_rs) ? 1.0 : 0.0);
+            acc.s[S_VOL_P] += (k.P * k.da) * dt;
+            acc.s[S_VOL_PR] += (P_rain * k.da) * dt;
+            acc.s[S_VOL_PS] += (P_snow * k.da) * dt;
+        }
+        if (k.flags & TFB_CH_SRC_SNOW) {                              // snow_degree_day :293-360
+            double M = k.c0_864 * (Ta - k.T0);
+            M = np_min(M, x.h / dt);                                  // snow_base :490-512
+            M = np_max(M, 0.0);
+            SM = M;
+            double hn = x.h + (P_snow * dt);                          // snow_base :559-609
+            hn = hn - (M * dt);
+            o.h = np_max(hn, 0.0);
+            acc.s[S_VOL_SM] += (M * k.da) * dt;
+        }
+        if (k.flags & TFB_CH_SRC_EVAP) {                              // evap_priestley_taylor :308-413
+            const double Qet = (k.alpha * (0.406 + (0.011 * Ta))) * (k.Qnet + k.Qc);
+            ET = np_max(Qet / 2.5E+9, 0.0);
+            et_grid = true;
+            acc.s[S_VOL_ET] += (ET * k.da) * dt;
+        }
+        if (k.flags & TFB_CH_SRC_INFIL) {                             // infil_green_ampt :511-578
+            const double P_total = P_rain + SM;
+            const double fc = (k.gkq / x.I) + k.Ks;
+            IN = np_min(fc, P_total);
+            if (P_total < k.Ks) IN = P_total;
+            o.I = x.I + (IN * dt);
+            acc.s[S_VOL_IN] += (IN * k.da) * dt;
+            if (!isfinite(IN)) acc.n[S_NNAN_IN - kNSum] += 1u;
+        }
+        if (et_grid) {                                                // channels_base :1625-1629
+            if (x.vol < ((ET * k.da) * dt)) ET = 0.0;
+        } else {
+            ET = 0.0;
+        }
+        const double R = (((P_rain + SM) + k.GW) + k.MR) - (ET + IN);
+        const double Rv = (R * k.da) * dt;
+        acc.s[S_VOL_R] += Rv;
+        v = x.vol + Rv;
     } else {
-        v = vol + k.Rdadt;
+        v = x.vol + k.Rdadt;
     }
-    if (cmask & 1u) v += dt * c0_;                                    // :2116-2131
-    if (cmask & 2u) v += dt * c1_;
-    if (cmask & 4u) v += dt * c2_;
-    if (cmask & 8u) v += dt * c3_;
-    if (cmask & 16u) v += dt * c4_;
-    if (cmask & 32u) v += dt * c5_;
-    if (cmask & 64u) v += dt * c6_;
-    if (cmask & 128u) v += dt * c7_;
-    v -= (qself * dt);                                                // :2138
+    if (cmask & 1u) v += dt * x.ch[0];                                // :2116-2131
+    if (cmask & 2u) v += dt * x.ch[1];
+    if (cmask & 4u) v += dt * x.ch[2];
+    if (cmask & 8u) v += dt * x.ch[3];
+    if (cmask & 16u) v += dt * x.ch[4];
+    if (cmask & 32u) v += dt * x.ch[5];
+    if (cmask & 64u) v += dt * x.ch[6];
+    if (cmask & 128u) v += dt * x.ch[7];
+    v -= (x.qself * dt);                                              // :2138
     v = np_max(v, 0.0);                                               // :2145
     // update_channel_depth :2299-2330, :2379
-    const double tn = lut[4 * ai], inv2tan = lut[4 * ai + 1], invcos = lut[4 * ai + 2];
+    const double tn = lut[4 * ai], inv2tan = lut[4 * ai + 1];
     double d;
     if (tn == 0.0) {
-        d = v / (w * ds);
+        d = v / (x.w * ds);
     } else {
         double arg = (lut[4 * ai + 3] * v) * inv_ds;
-        arg += w * w;
-        d = (sqrt(arg) - w) * inv2tan;
+        arg += x.w * x.w;
+        d = (sqrt(arg) - x.w) * inv2tan;
     }
-    d = np_max(d, 0.0);
-    // update_trapezoid_Rh :2668-2703
-    const double A_wet = d * (w + (d * tn));
+    o.v = v;
+    o.d = np_max(d, 0.0);
+}
+
+// hydraulic radius, velocity, next discharge, stability counters of one cell:
+// update_trapezoid_Rh :2643, manning_formula :3960, update_velocity_on_edges :2851,
+// update_outlet_values :2884, check_flow_depth :3193, check_flow_velocity :3352
+__device__ __forceinline__ void pk_velocity(const tfb_channels_step_args &a, const PkConsts &k,
+                                            const double *__restrict__ lut, unsigned g, double d,
+                                            double w, double umul, double inv_ds, double qself,
+                                            double outlet_rough, int r, int c, Acc &acc,
+                                            float &rate_max, double &u_out, double &Qn_out) {
+    const unsigned code = g & 0xffu, ai = (g >> 16) & 0xffu;
+    const bool noflow = (code == 0);
+    const double tn = lut[4 * ai], invcos = lut[4 * ai + 2];
+    const double A_wet = d * (w + (d * tn));                          // :2668-2703
     double P_wet = w + ((2.0 * d) * invcos);
     if (noflow) P_wet = 1.0;
     double Rh = A_wet / P_wet;
     if (noflow) Rh = 0.0;
-    // manning_formula :3982-3983 with coef = sqrt|S_bed| / n
     const double cb = cbrt(Rh);
-    double u = (cb * cb) * coef;
+    double u = (cb * cb) * umul;                                      // :3982-3983
     if (noflow) u = 0.0;                                              // :2862
     if (r + a.row0 == a.outlet_row && c == a.outlet_col) {            // :2896-2904
         double f_o = 0.0;
-        if (d > 0.0) f_o = k.g * ((p.outlet_rough * p.outlet_rough) / cbrt(d));
+        if (d > 0.0) f_o = k.g * ((outlet_rough * outlet_rough) / cbrt(d));
         double *po = a.partials + kPartialStride;
         po[P_QOUT] = qself; po[P_UOUT] = u; po[P_DOUT] = d; po[P_FOUT] = f_o; po[P_HASOUT] = 1.0;
     }
-    o.Qn = u * A_wet;                                                 // next step :1697
-    if (noflow) {                                                     // :2960-2966
-        acc.s[S_VOL_EDGE] += v;
-        v = 0.0;
-        d = 0.0;
-    }
-    // check_flow_depth :3193 / check_flow_velocity :3352 -- rare path only
-    if (!(d >= 0.0 && d <= 1.7976931348623157e308 && u >= 0.0 && u <= 1.7976931348623157e308)) {
-        if (d < 0.0) acc.n[S_NNEG_D - kNSum] += 1u;
-        if (d != d) acc.n[S_NNAN_D - kNSum] += 1u;
-        if (isinf(d)) acc.n[S_NINF_D - kNSum] += 1u;
+    Qn_out = u * A_wet;                                               // next step :1697
+    const double dz = noflow ? 0.0 : d;                               // :2960-2966
+    if (!(dz >= 0.0 && dz <= 1.7976931348623157e308 && u >= 0.0 && u <= 1.7976931348623157e308)) {
+        if (dz < 0.0) acc.n[S_NNEG_D - kNSum] += 1u;
+        if (dz != dz) acc.n[S_NNAN_D - kNSum] += 1u;
+        if (isinf(dz)) acc.n[S_NINF_D - kNSum] += 1u;
         if (u < 0.0) acc.n[S_NNEG_U - kNSum] += 1u;
         if (u != u) acc.n[S_NNAN_U - kNSum] += 1u;
         if (isinf(u)) acc.n[S_NINF_U - kNSum] += 1u;
     }
     rate_max = fmaxf(rate_max, (float)u * (float)inv_ds);             // CFL diagnostic: 1/dt_min
-    o.vol = v; o.d = d; o.u = u;
+    u_out = u;
 }
 
-struct PkMaps { CUtensorMap Q, vol, coef, I, w, geo; };
+struct PkMaps { CUtensorMap Q, vol, coef, I, H, T, w, geo; };
+struct PkMapsB { CUtensorMap D, N, S, w, geo; };
 
-template <bool GA>
-__global__ void __launch_bounds__(kThreads, 1)
-channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed p,
-                       const PkConsts k, const __grid_constant__ PkMaps maps) {
-    using SL = StageLayout<GA>;
-    constexpr int NS = SL::stages;
-    extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ double lut[256 * 4];
-    __shared__ double sm[kConsumerWarps][kPartialStride];
-    __shared__ __align__(8) uint64_t full_bar[NS], empty_bar[NS];
-    __shared__ bool is_last;
-    __shared__ int s_fail;
+// CTA-level reduction of the per-thread accumulators, per-CTA row, last-CTA fold in
+// CTA order (deterministic).  `mode`: 0 = everything, 1 = sums only (pass A), 2 =
+// status only (pass B).
+__device__ __forceinline__ void pk_finish(const tfb_channels_step_args &a, Acc &acc, float rate_max,
+                                          bool consumer, int fail, int mode,
+                                          double (*sm)[kPartialStride], double *tot, bool *is_last) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < p.n_angles * 4; i += kThreads) lut[i] = __ldg(p.angle_lut + i);
-    if (tid < kConsumerWarps * kPartialStride) (&sm[0][0])[tid] = 0.0;
-    if (tid == 0) {
-        s_fail = 0;
-        for (int s = 0; s < NS; ++s) {
-            mbar_init(&full_bar[s], 1u);
-            mbar_init(&empty_bar[s], (unsigned)kConsumerWarps);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncthreads();
-
-    Acc acc;
+    if (consumer) {
 #pragma unroll
-    for (int j = 0; j < kNSum; ++j) acc.s[j] = 0.0;
-#pragma unroll
-    for (int j = 0; j < kNCnt; ++j) acc.n[j] = 0u;
-    float rate_max = 0.0f;
-
-    if (warp == kConsumerWarps) {
-        // ---------------- producer: one lane streams tiles into the ring -------------
-        if (lane == 0) {
-            int stage = 0;
-            unsigned phase = 0;
-            for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
-                if (!mbar_wait(&empty_bar[stage], phase ^ 1u)) { s_fail = 1; break; }
-                const int ty = t / k.tiles_x, tx = t - ty * k.tiles_x;
-                const int c0 = tx * kTW, r0 = ty * kTR;
-                unsigned char *st = smem + (size_t)stage * SL::bytes;
-                mbar_arrive_expect_tx(&full_bar[stage], (unsigned)SL::tx_bytes);
-                // tensor rows are counted from the top of the halo'd allocation
-                tma_load_2d(st + SL::oQ, &maps.Q, &full_bar[stage], c0 - 2, r0 - 1 + a.halo);
-                tma_load_2d(st + SL::oVol, &maps.vol, &full_bar[stage], c0, r0 + a.halo);
-                tma_load_2d(st + SL::oCoef, &maps.coef, &full_bar[stage], c0, r0);
-                if (GA) tma_load_2d(st + SL::oI, &maps.I, &full_bar[stage], c0, r0 + a.halo);
-                tma_load_2d(st + SL::oW, &maps.w, &full_bar[stage], c0, r0);
-                tma_load_2d(st + SL::oGeo, &maps.geo, &full_bar[stage], c0, r0);
-                if (++stage == NS) { stage = 0; phase ^= 1u; }
-            }
-        }
-    } else {
-        // ---------------- consumers: warp w computes row w of every tile -------------
-        int stage = 0;
-        unsigned phase = 0;
-        for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
-            if (!mbar_wait(&full_bar[stage], phase)) { s_fail = 1; break; }
-            const int ty = t / k.tiles_x, tx = t - ty * k.tiles_x;
-            const int c0 = tx * kTW + lane * 2, r = ty * kTR + warp;
-            const unsigned char *st = smem + (size_t)stage * SL::bytes;
-            if (r < a.ny && c0 < a.nx) {
-                const int e = warp * kTW + lane * 2;                   // element in a 64x16 tile
-                const uint2 geo = *reinterpret_cast<const uint2 *>(st + SL::oGeo + e * 4);
-                const float2 w = *reinterpret_cast<const float2 *>(st + SL::oW + e * 4);
-                const double2 vol = *reinterpret_cast<const double2 *>(st + SL::oVol + e * 8);
-                const double2 coef = *reinterpret_cast<const double2 *>(st + SL::oCoef + e * 8);
-                double2 Iv = make_double2(0.0, 0.0);
-                if (GA) Iv = *reinterpret_cast<const double2 *>(st + SL::oI + e * 8);
-                // Q window: halo rows warp, warp+1, warp+2; halo cols 2*lane+1 .. 2*lane+4
-                const double *q = reinterpret_cast<const double *>(st + SL::oQ) + warp * kQW + lane * 2;
-                const double2 a0 = *reinterpret_cast<const double2 *>(q);
-                const double2 a1 = *reinterpret_cast<const double2 *>(q + 2);
-                const double2 m0 = *reinterpret_cast<const double2 *>(q + kQW);
-                const double2 m1 = *reinterpret_cast<const double2 *>(q + kQW + 2);
-                const double2 b0 = *reinterpret_cast<const double2 *>(q + 2 * kQW);
-                const double2 b1 = *reinterpret_cast<const double2 *>(q + 2 * kQW + 2);
-                // columns: x0 = c0-2 (unused), a0.y = c0-1, a1.x = c0, a1.y = c0+1; the
-                // east neighbour c0+2 of cell 1 is the first value of the next pair
-                const double aE = q[4], mE = q[kQW + 4], bE = q[2 * kQW + 4];
-                const double *rg = p.row_geom + (int64_t)r * 6;
-                PkOut o0, o1;
-                o0.I = o1.I = 0.0;
-                // cell 0 (col c0): west = *.0.y, same = *.1.x, east = *.1.y
-                pk_cell<GA>(a, k, lut, geo.x, vol.x, Iv.x, (double)w.x, coef.x, m1.x,
-                            b0.y, m0.y, a0.y, a1.x, a1.y, m1.y, b1.y, b1.x,
-                            rg, r, c0, p, acc, rate_max, o0);
-                // cell 1 (col c0+1): west = *.1.x, same = *.1.y, east = *E
-                pk_cell<GA>(a, k, lut, geo.y, vol.y, Iv.y, (double)w.y, coef.y, m1.y,
-                            b1.x, m1.x, a1.x, a1.y, aE, mE, bE, b1.y,
-                            rg, r, c0 + 1, p, acc, rate_max, o1);
-                const int64_t i = (int64_t)r * a.nx + c0;
-                *reinterpret_cast<double2 *>(a.vol_out + i) = make_double2(o0.vol, o1.vol);
-                *reinterpret_cast<double2 *>(a.d + i) = make_double2(o0.d, o1.d);
-                *reinterpret_cast<double2 *>(a.u + i) = make_double2(o0.u, o1.u);
-                *reinterpret_cast<double2 *>(a.Q_out + i) = make_double2(o0.Qn, o1.Qn);
-                if (GA) *reinterpret_cast<double2 *>(a.I_out + i) = make_double2(o0.I, o1.I);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[stage]);            // slot may be refilled
-            if (++stage == NS) { stage = 0; phase ^= 1u; }
-        }
-        // ---- per-CTA partial sums: warp shuffles only where a warp has something -------
-        double e = acc.s[S_VOL_EDGE];
-        if (__any_sync(kFull, e != 0.0)) e = warp_sum(e);
-        if (lane == 0) sm[warp][S_VOL_EDGE] = e;
-        if (GA) {
-            const double vr = warp_sum(acc.s[S_VOL_R]), vi = warp_sum(acc.s[S_VOL_IN]);
-            if (lane == 0) { sm[warp][S_VOL_R] = vr; sm[warp][S_VOL_IN] = vi; }
+        for (int j = 0; j < kNSum; ++j) {
+            double v = acc.s[j];
+            if (__any_sync(kFull, v != 0.0)) v = warp_sum(v);
+            if (lane == 0) sm[warp][j] = v;
         }
         unsigned any = 0;
 #pragma unroll
         for (int j = 0; j < kNCnt; ++j) any |= acc.n[j];
-        if (__any_sync(kFull, any != 0u)) {
+        const bool some = __any_sync(kFull, any != 0u);
 #pragma unroll
-            for (int j = 0; j < kNCnt; ++j) {
-                const unsigned n = __reduce_add_sync(kFull, acc.n[j]);
-                if (lane == 0) sm[warp][kNSum + j] = (double)n;
-            }
+        for (int j = 0; j < kNCnt; ++j) {
+            unsigned n = acc.n[j];
+            if (some) n = __reduce_add_sync(kFull, n);
+            if (lane == 0) sm[warp][kNSum + j] = (double)n;
         }
         const unsigned rb = __reduce_max_sync(kFull, __float_as_uint(fmaxf(rate_max, 0.0f)));
         if (lane == 0) sm[warp][P_DTMIN] = (double)__uint_as_float(rb);
@@ -369,20 +355,18 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
         } else if (tid < S_NSLOT) {
             for (int w = 0; w < kConsumerWarps; ++w) v += sm[w][tid];
         }
-        if (tid == S_NNAN_D && s_fail) v += 1.0e9;       // pipeline failure poisons the step
+        if (tid == S_NNAN_D && fail) v += 1.0e9;          // pipeline failure poisons the step
         a.partials[(int64_t)(blockIdx.x + 2) * kPartialStride + tid] = v;
     }
-    // ---- completion: the last CTA folds the per-CTA rows in CTA order ------------------
     __threadfence();
     __syncthreads();
     if (tid == 0) {
         const unsigned tk = atomicAdd(a.ticket, 1u);
-        is_last = (tk == gridDim.x - 1u);
+        *is_last = (tk == gridDim.x - 1u);
     }
     __syncthreads();
-    if (!is_last) return;
+    if (!*is_last) return;
     __threadfence();
-    __shared__ double tot[kPartialStride];
     if (tid < kPartialStride) {
         const volatile double *P = a.partials;
         double v = 0.0;
@@ -407,10 +391,277 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
         h[P_DOUT] = has_out ? outp[P_DOUT] : 0.0;
         h[P_FOUT] = has_out ? outp[P_FOUT] : 0.0;
         h[P_HASOUT] = 0.0; h[22] = 0.0; h[23] = 0.0;
-        outp[P_HASOUT] = 0.0;
-        if (a.finalize) fold_scalars(a, h);
-        a.ticket[0] = 0u;                                 // re-arm for the next step
+        if (mode != 1) outp[P_HASOUT] = 0.0;
+        if (a.finalize) {
+            if (mode == 0) fold_scalars(a, h);
+            else if (mode == 1) fold_sums(a, h);
+            else fold_status(a, h);
+        }
+        a.ticket[0] = 0u;                                 // re-arm for the next launch
     }
+}
+
+// ---------------------------------------------------------------------------
+// main kernel: the kinematic step (VAR = PK_KW) or pass A of the diffusive step
+// (VAR = PK_DWA: new volume, new depth and source state only)
+// ---------------------------------------------------------------------------
+template <int SRC, int VAR>
+__global__ void __launch_bounds__(kThreads, 1)
+channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed p,
+                       const PkConsts k, const __grid_constant__ PkMaps maps) {
+    using SL = StageLayout<SRC, VAR>;
+    constexpr int NS = SL::stages;
+    constexpr bool kKW = (VAR == PK_KW);
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ double lut[256 * 4];
+    __shared__ double sm[kConsumerWarps][kPartialStride];
+    __shared__ double tot[kPartialStride];
+    __shared__ __align__(8) uint64_t full_bar[NS], empty_bar[NS];
+    __shared__ bool is_last;
+    __shared__ int s_fail;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < p.n_angles * 4; i += kThreads) lut[i] = __ldg(p.angle_lut + i);
+    if (tid < kConsumerWarps * kPartialStride) (&sm[0][0])[tid] = 0.0;
+    if (tid == 0) {
+        s_fail = 0;
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&full_bar[s], 1u);
+            mbar_init(&empty_bar[s], (unsigned)kConsumerWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    Acc acc;
+#pragma unroll
+    for (int j = 0; j < kNSum; ++j) acc.s[j] = 0.0;
+#pragma unroll
+    for (int j = 0; j < kNCnt; ++j) acc.n[j] = 0u;
+    float rate_max = 0.0f;
+    const bool use_h = (SRC == PK_SRC_FULL) && (k.flags & TFB_CH_SRC_SNOW);
+    const bool use_i = (SRC == PK_SRC_GA) || ((SRC == PK_SRC_FULL) && (k.flags & TFB_CH_SRC_INFIL));
+    const bool use_t = (SRC == PK_SRC_FULL) && k.tair_grid;
+
+    if (warp == kConsumerWarps) {
+        // ---------------- producer: one lane streams tiles into the ring -------------
+        if (lane == 0) {
+            int stage = 0;
+            unsigned phase = 0;
+            const unsigned tx = (unsigned)(kQW * kQR * 8 + kSzD * (1 + (kKW ? 1 : 0) + (use_i ? 1 : 0) +
+                                                                 (use_h ? 1 : 0) + (use_t ? 1 : 0)) + 2 * kSzF);
+            for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
+                if (!mbar_wait(&empty_bar[stage], phase ^ 1u)) { s_fail = 1; break; }
+                const int ty = t / k.tiles_x, txi = t - ty * k.tiles_x;
+                const int c0 = txi * kTW, r0 = ty * kTR;
+                unsigned char *st = smem + (size_t)stage * SL::bytes;
+                mbar_arrive_expect_tx(&full_bar[stage], tx);
+                // tensor rows are counted from the top of the halo'd allocation
+                tma_load_2d(st + SL::oQ, &maps.Q, &full_bar[stage], c0 - 2, r0 - 1 + a.halo);
+                tma_load_2d(st + SL::oVol, &maps.vol, &full_bar[stage], c0, r0 + a.halo);
+                if (kKW) tma_load_2d(st + SL::oCoef, &maps.coef, &full_bar[stage], c0, r0);
+                if (use_i) tma_load_2d(st + SL::oI, &maps.I, &full_bar[stage], c0, r0 + a.halo);
+                if (use_h) tma_load_2d(st + SL::oH, &maps.H, &full_bar[stage], c0, r0 + a.halo);
+                if (use_t) tma_load_2d(st + SL::oT, &maps.T, &full_bar[stage], c0, r0 + a.halo);
+                tma_load_2d(st + SL::oW, &maps.w, &full_bar[stage], c0, r0);
+                tma_load_2d(st + SL::oGeo, &maps.geo, &full_bar[stage], c0, r0);
+                if (++stage == NS) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else {
+        // ---------------- consumers: warp w computes row w of every tile -------------
+        int stage = 0;
+        unsigned phase = 0;
+        for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
+            if (!mbar_wait(&full_bar[stage], phase)) { s_fail = 1; break; }
+            const int ty = t / k.tiles_x, txi = t - ty * k.tiles_x;
+            const int c0 = txi * kTW + lane * 2, r = ty * kTR + warp;
+            const unsigned char *st = smem + (size_t)stage * SL::bytes;
+            if (r < a.ny && c0 < a.nx) {
+                const int e = warp * kTW + lane * 2;                   // element in a 64x16 tile
+                const uint2 geo = *reinterpret_cast<const uint2 *>(st + SL::oGeo + e * 4);
+                const float2 w = *reinterpret_cast<const float2 *>(st + SL::oW + e * 4);
+                const double2 vol = *reinterpret_cast<const double2 *>(st + SL::oVol + e * 8);
+                double2 coef = make_double2(0.0, 0.0), Iv = coef, Hv = coef, Tv = coef;
+                if (kKW) coef = *reinterpret_cast<const double2 *>(st + SL::oCoef + e * 8);
+                if (use_i) Iv = *reinterpret_cast<const double2 *>(st + SL::oI + e * 8);
+                if (use_h) Hv = *reinterpret_cast<const double2 *>(st + SL::oH + e * 8);
+                if (use_t) Tv = *reinterpret_cast<const double2 *>(st + SL::oT + e * 8);
+                // Q window: halo rows warp, warp+1, warp+2; halo cols 2*lane .. 2*lane+4
+                const double *q = reinterpret_cast<const double *>(st + SL::oQ) + warp * kQW + lane * 2;
+                const double2 a0 = *reinterpret_cast<const double2 *>(q);
+                const double2 a1 = *reinterpret_cast<const double2 *>(q + 2);
+                const double2 m0 = *reinterpret_cast<const double2 *>(q + kQW);
+                const double2 m1 = *reinterpret_cast<const double2 *>(q + kQW + 2);
+                const double2 b0 = *reinterpret_cast<const double2 *>(q + 2 * kQW);
+                const double2 b1 = *reinterpret_cast<const double2 *>(q + 2 * kQW + 2);
+                // columns: *0.y = c0-1, *1.x = c0, *1.y = c0+1, *E = c0+2
+                const double aE = q[4], mE = q[kQW + 4], bE = q[2 * kQW + 4];
+                const double2 *rgp = reinterpret_cast<const double2 *>(p.row_geom + (int64_t)r * 6);
+                const double2 g0 = __ldg(rgp), g1 = __ldg(rgp + 1), g2 = __ldg(rgp + 2);
+                const int64_t i = (int64_t)r * a.nx + c0;
+                PkVD o0, o1;
+                double u0 = 0.0, u1 = 0.0, Q0 = 0.0, Q1 = 0.0;
+                {   // cell 0 (col c0): west = *0.y, same = *1.x, east = *1.y; children in the
+                    // order SW, W, NW, N, NE, E, SE, S
+                    PkIn x;
+                    x.g = geo.x; x.vol = vol.x; x.I = Iv.x; x.h = Hv.x; x.Ta = Tv.x; x.w = (double)w.x;
+                    x.qself = m1.x;
+                    x.ch[0] = b0.y; x.ch[1] = m0.y; x.ch[2] = a0.y; x.ch[3] = a1.x;
+                    x.ch[4] = a1.y; x.ch[5] = m1.y; x.ch[6] = b1.y; x.ch[7] = b1.x;
+                    pk_vol_depth<SRC>(k, lut, x, g0, g1, g2, acc, o0);
+                    if (kKW) {
+                        const bool dg = (geo.x & 0x55u) != 0u, ns = (geo.x & 0x88u) != 0u;
+                        pk_velocity(a, k, lut, geo.x, o0.d, x.w, coef.x, dg ? g2.x : (ns ? g2.y : g1.y),
+                                    x.qself, p.outlet_rough, r, c0, acc, rate_max, u0, Q0);
+                    }
+                }
+                {   // cell 1 (col c0+1): west = *1.x, same = *1.y, east = *E
+                    PkIn x;
+                    x.g = geo.y; x.vol = vol.y; x.I = Iv.y; x.h = Hv.y; x.Ta = Tv.y; x.w = (double)w.y;
+                    x.qself = m1.y;
+                    x.ch[0] = b1.x; x.ch[1] = m1.x; x.ch[2] = a1.x; x.ch[3] = a1.y;
+                    x.ch[4] = aE; x.ch[5] = mE; x.ch[6] = bE; x.ch[7] = b1.y;
+                    pk_vol_depth<SRC>(k, lut, x, g0, g1, g2, acc, o1);
+                    if (kKW) {
+                        const bool dg = (geo.y & 0x55u) != 0u, ns = (geo.y & 0x88u) != 0u;
+                        pk_velocity(a, k, lut, geo.y, o1.d, x.w, coef.y, dg ? g2.x : (ns ? g2.y : g1.y),
+                                    x.qself, p.outlet_rough, r, c0 + 1, acc, rate_max, u1, Q1);
+                    }
+                }
+                const bool nf0 = (geo.x & 0xffu) == 0u, nf1 = (geo.y & 0xffu) == 0u;
+                if (kKW) {
+                    *reinterpret_cast<double2 *>(a.u + i) = make_double2(u0, u1);
+                    *reinterpret_cast<double2 *>(a.Q_out + i) = make_double2(Q0, Q1);
+                }
+                // update_edge_values :2960-2966 (pass A keeps the PRE-zero depth for the
+                // free-surface slope of pass B, which then zeroes it)
+                if (nf0) { acc.s[S_VOL_EDGE] += o0.v; o0.v = 0.0; if (kKW) o0.d = 0.0; }
+                if (nf1) { acc.s[S_VOL_EDGE] += o1.v; o1.v = 0.0; if (kKW) o1.d = 0.0; }
+                *reinterpret_cast<double2 *>(a.vol_out + i) = make_double2(o0.v, o1.v);
+                *reinterpret_cast<double2 *>(a.d + i) = make_double2(o0.d, o1.d);
+                if (use_i) *reinterpret_cast<double2 *>(a.I_out + i) = make_double2(o0.I, o1.I);
+                if (use_h) {
+                    *reinterpret_cast<double2 *>(a.h_swe_out + i) = make_double2(o0.h, o1.h);
+                    if (a.h_snow)
+                        *reinterpret_cast<double2 *>(a.h_snow + i) =
+                            make_double2(o0.h * k.ratio, o1.h * k.ratio);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[stage]);            // slot may be refilled
+            if (++stage == NS) { stage = 0; phase ^= 1u; }
+        }
+    }
+    pk_finish(a, acc, rate_max, warp < kConsumerWarps, s_fail, kKW ? 0 : 1, sm, tot, &is_last);
+}
+
+// ---------------------------------------------------------------------------
+// pass B of the diffusive step: free-surface slope from the NEW depths of the
+// cell and its D8 parent (channels_base.py:2583-2618), velocity, next discharge
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_packed p,
+                           const PkConsts k, const __grid_constant__ PkMapsB maps) {
+    using SL = StageLayoutB;
+    constexpr int NS = SL::stages;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ double lut[256 * 4];
+    __shared__ double sm[kConsumerWarps][kPartialStride];
+    __shared__ double tot[kPartialStride];
+    __shared__ __align__(8) uint64_t full_bar[NS], empty_bar[NS];
+    __shared__ bool is_last;
+    __shared__ int s_fail;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < p.n_angles * 4; i += kThreads) lut[i] = __ldg(p.angle_lut + i);
+    if (tid < kConsumerWarps * kPartialStride) (&sm[0][0])[tid] = 0.0;
+    if (tid == 0) {
+        s_fail = 0;
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&full_bar[s], 1u);
+            mbar_init(&empty_bar[s], (unsigned)kConsumerWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    Acc acc;
+#pragma unroll
+    for (int j = 0; j < kNSum; ++j) acc.s[j] = 0.0;
+#pragma unroll
+    for (int j = 0; j < kNCnt; ++j) acc.n[j] = 0u;
+    float rate_max = 0.0f;
+
+    if (warp == kConsumerWarps) {
+        if (lane == 0) {
+            int stage = 0;
+            unsigned phase = 0;
+            for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
+                if (!mbar_wait(&empty_bar[stage], phase ^ 1u)) { s_fail = 1; break; }
+                const int ty = t / k.tiles_x, txi = t - ty * k.tiles_x;
+                const int c0 = txi * kTW, r0 = ty * kTR;
+                unsigned char *st = smem + (size_t)stage * SL::bytes;
+                mbar_arrive_expect_tx(&full_bar[stage], (unsigned)SL::tx_bytes);
+                tma_load_2d(st + SL::oD, &maps.D, &full_bar[stage], c0 - 2, r0 - 1 + a.halo);
+                tma_load_2d(st + SL::oN, &maps.N, &full_bar[stage], c0, r0);
+                tma_load_2d(st + SL::oS, &maps.S, &full_bar[stage], c0, r0);
+                tma_load_2d(st + SL::oW, &maps.w, &full_bar[stage], c0, r0);
+                tma_load_2d(st + SL::oGeo, &maps.geo, &full_bar[stage], c0, r0);
+                if (++stage == NS) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else {
+        int stage = 0;
+        unsigned phase = 0;
+        for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
+            if (!mbar_wait(&full_bar[stage], phase)) { s_fail = 1; break; }
+            const int ty = t / k.tiles_x, txi = t - ty * k.tiles_x;
+            const int c0 = txi * kTW + lane * 2, r = ty * kTR + warp;
+            const unsigned char *st = smem + (size_t)stage * SL::bytes;
+            if (r < a.ny && c0 < a.nx) {
+                const int e = warp * kTW + lane * 2;
+                const uint2 geo = *reinterpret_cast<const uint2 *>(st + SL::oGeo + e * 4);
+                const float2 w = *reinterpret_cast<const float2 *>(st + SL::oW + e * 4);
+                const float2 S = *reinterpret_cast<const float2 *>(st + SL::oS + e * 4);
+                const double2 invn = *reinterpret_cast<const double2 *>(st + SL::oN + e * 8);
+                // depth tile with halo: own cell (row warp+1, col 2*lane+2)
+                const double *dT = reinterpret_cast<const double *>(st + SL::oD);
+                const double *dc = dT + (warp + 1) * kQW + lane * 2 + 2;
+                const double2 dv = *reinterpret_cast<const double2 *>(dc);
+                const double2 *rgp = reinterpret_cast<const double2 *>(p.row_geom + (int64_t)r * 6);
+                const double2 g1 = __ldg(rgp + 1), g2 = __ldg(rgp + 2);
+                const int64_t i = (int64_t)r * a.nx + c0;
+                double uo[2], Qo[2], dd_[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const unsigned g = j ? geo.y : geo.x;
+                    const unsigned code = g & 0xffu;
+                    const double d = j ? dv.y : dv.x;
+                    int dr, dcol;
+                    code_offset(code, dr, dcol);
+                    const double d_par = dc[j + dr * kQW + dcol];     // new depth of the D8 parent
+                    const bool dg = (code & 0x55u) != 0u, ns = (code & 0x88u) != 0u;
+                    const double inv_ds = dg ? g2.x : (ns ? g2.y : g1.y);
+                    const double Sf = (double)(j ? S.y : S.x) + ((d - d_par) * inv_ds);   // :2606-2607
+                    const double umul = sqrt(fabs(Sf)) * (j ? invn.y : invn.x);
+                    double qs = 0.0;
+                    if (r + a.row0 == a.outlet_row && c0 + j == a.outlet_col)
+                        qs = __ldg(a.Q_in + i + j);
+                    pk_velocity(a, k, lut, g, d, (double)(j ? w.y : w.x), umul, inv_ds, qs,
+                                p.outlet_rough, r, c0 + j, acc, rate_max, uo[j], Qo[j]);
+                    dd_[j] = (code == 0u) ? 0.0 : d;                  // :2966
+                }
+                *reinterpret_cast<double2 *>(a.u + i) = make_double2(uo[0], uo[1]);
+                *reinterpret_cast<double2 *>(a.Q_out + i) = make_double2(Qo[0], Qo[1]);
+                if (((geo.x & 0xffu) == 0u) || ((geo.y & 0xffu) == 0u))
+                    *reinterpret_cast<double2 *>(a.d + i) = make_double2(dd_[0], dd_[1]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[stage]);
+            if (++stage == NS) { stage = 0; phase ^= 1u; }
+        }
+    }
+    pk_finish(a, acc, rate_max, warp < kConsumerWarps, s_fail, 2, sm, tot, &is_last);
 }
 
 }  // namespace tfb
@@ -497,37 +748,143 @@ int get_map(const void *ptr, int64_t rows, int64_t cols, CUtensorMapDataType dty
     return TFB_OK;
 }
 
-template <bool GA>
-int launch_packed(const tfb_channels_step_args &a, const tfb_channels_packed &p, const PkConsts &k,
-                  cudaStream_t st) {
-    using SL = StageLayout<GA>;
+template <int SRC, int VAR>
+int launch_main(const tfb_channels_step_args &a, const tfb_channels_packed &p, const PkConsts &k,
+                cudaStream_t st) {
+    using SL = StageLayout<SRC, VAR>;
+    static_assert(SL::stages >= 2, "ring needs at least two slots");
     PkMaps m;
     const int64_t rows_h = (int64_t)a.ny + 2 * a.halo;
     const size_t hb = (size_t)a.halo * a.nx;               // elements between allocation and row 0
+    const CUtensorMapDataType F64 = CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
     int rc;
-    if ((rc = get_map(a.Q_in - hb, rows_h, a.nx, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, kQW, kQR, &m.Q))) return rc;
-    if ((rc = get_map(a.vol - hb, rows_h, a.nx, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, kTW, kTR, &m.vol))) return rc;
-    if ((rc = get_map(p.coef, a.ny, a.nx, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, kTW, kTR, &m.coef))) return rc;
-    if (GA) {
-        if ((rc = get_map(a.I - hb, rows_h, a.nx, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, kTW, kTR, &m.I))) return rc;
-    } else {
-        m.I = m.vol;
-    }
+    if ((rc = get_map(a.Q_in - hb, rows_h, a.nx, F64, 8, kQW, kQR, &m.Q))) return rc;
+    if ((rc = get_map(a.vol - hb, rows_h, a.nx, F64, 8, kTW, kTR, &m.vol))) return rc;
+    m.coef = m.I = m.H = m.T = m.vol;
+    if (VAR == PK_KW)
+        if ((rc = get_map(p.coef, a.ny, a.nx, F64, 8, kTW, kTR, &m.coef))) return rc;
+    const bool use_h = (SRC == PK_SRC_FULL) && (k.flags & TFB_CH_SRC_SNOW);
+    const bool use_i = (SRC == PK_SRC_GA) || ((SRC == PK_SRC_FULL) && (k.flags & TFB_CH_SRC_INFIL));
+    const bool use_t = (SRC == PK_SRC_FULL) && k.tair_grid;
+    if (use_i) if ((rc = get_map(a.I - hb, rows_h, a.nx, F64, 8, kTW, kTR, &m.I))) return rc;
+    if (use_h) if ((rc = get_map(a.h_swe - hb, rows_h, a.nx, F64, 8, kTW, kTR, &m.H))) return rc;
+    if (use_t) if ((rc = get_map(a.T_air.ptr - hb, rows_h, a.nx, F64, 8, kTW, kTR, &m.T))) return rc;
     if ((rc = get_map(p.width32, a.ny, a.nx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, kTW, kTR, &m.w))) return rc;
     if ((rc = get_map(p.geo32, a.ny, a.nx, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, kTW, kTR, &m.geo))) return rc;
     const int smem = SL::stages * SL::bytes;
-    static bool attr_set[2][64] = {{false}};
+    static bool attr_set[64] = {false};
     int dev = 0;
     TFB_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev >= 64 || !attr_set[GA ? 1 : 0][dev]) {
-        TFB_CUDA_CHECK(cudaFuncSetAttribute(channels_packed_kernel<GA>,
+    if (dev >= 64 || !attr_set[dev]) {
+        TFB_CUDA_CHECK(cudaFuncSetAttribute(channels_packed_kernel<SRC, VAR>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        if (dev < 64) attr_set[GA ? 1 : 0][dev] = true;
+        if (dev < 64) attr_set[dev] = true;
     }
     int64_t grid = sm_count();
     if (grid > k.n_tiles) grid = k.n_tiles;
-    channels_packed_kernel<GA><<<(int)grid, kThreads, smem, st>>>(a, p, k, m);
+    channels_packed_kernel<SRC, VAR><<<(int)grid, kThreads, smem, st>>>(a, p, k, m);
     TFB_CUDA_CHECK(cudaGetLastError());
+    return TFB_OK;
+}
+
+int launch_dwb(const tfb_channels_step_args &a, const tfb_channels_packed &p, const PkConsts &k,
+               cudaStream_t st) {
+    using SL = StageLayoutB;
+    PkMapsB m;
+    const int64_t rows_h = (int64_t)a.ny + 2 * a.halo;
+    const size_t hb = (size_t)a.halo * a.nx;
+    int rc;
+    if ((rc = get_map(a.d - hb, rows_h, a.nx, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, kQW, kQR, &m.D))) return rc;
+    if ((rc = get_map(p.inv_rough, a.ny, a.nx, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, kTW, kTR, &m.N))) return rc;
+    if ((rc = get_map(p.S32, a.ny, a.nx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, kTW, kTR, &m.S))) return rc;
+    if ((rc = get_map(p.width32, a.ny, a.nx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, kTW, kTR, &m.w))) return rc;
+    if ((rc = get_map(p.geo32, a.ny, a.nx, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, kTW, kTR, &m.geo))) return rc;
+    const int smem = SL::stages * SL::bytes;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    TFB_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev >= 64 || !attr_set[dev]) {
+        TFB_CUDA_CHECK(cudaFuncSetAttribute(channels_packed_dwb_kernel,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (dev < 64) attr_set[dev] = true;
+    }
+    int64_t grid = sm_count();
+    if (grid > k.n_tiles) grid = k.n_tiles;
+    channels_packed_dwb_kernel<<<(int)grid, kThreads, smem, st>>>(a, p, k, m);
+    TFB_CUDA_CHECK(cudaGetLastError());
+    return TFB_OK;
+}
+
+// argument checks and constants shared by the three entry points
+int prepare(const tfb_channels_step_args *ap, const tfb_channels_packed *pp, bool diffusive,
+            PkConsts &k, int &src_mode) {
+    TFB_ARG_CHECK(ap != nullptr && pp != nullptr);
+    const tfb_channels_step_args &a = *ap;
+    const tfb_channels_packed &p = *pp;
+    TFB_ARG_CHECK(a.ny > 0 && a.nx > 0 && a.halo >= 0 && (a.nx % 4) == 0);
+    TFB_ARG_CHECK(p.geo32 && p.width32 && p.angle_lut && p.row_geom && p.n_angles >= 1 &&
+                  p.n_angles <= 256);
+    TFB_ARG_CHECK(a.vol && a.vol_out && a.Q_in && a.Q_out && a.d && a.u);
+    TFB_ARG_CHECK(a.Q_in != a.Q_out && a.scalars && a.partials && a.ticket && a.dt > 0.0);
+    // eligibility: Manning, lean outputs, uniform forcing
+    const uint32_t src = a.flags & (TFB_CH_SRC_MET | TFB_CH_SRC_SNOW | TFB_CH_SRC_EVAP |
+                                    TFB_CH_SRC_INFIL);
+    TFB_ARG_CHECK(!(a.flags & (TFB_CH_LAW_OF_WALL | TFB_CH_DIAG | TFB_CH_WRITE_R)));
+    TFB_ARG_CHECK(((a.flags & TFB_CH_DIFFUSIVE) != 0) == diffusive);
+    if (diffusive) TFB_ARG_CHECK(p.inv_rough && p.S32 && a.halo != 0 ? a.halo >= 1 : true);
+    else TFB_ARG_CHECK(p.coef != nullptr);
+    TFB_ARG_CHECK(!a.sinu.ptr && !a.da.ptr);
+    TFB_ARG_CHECK(!a.P_rain.ptr && !a.SM.ptr && !a.GW.ptr && !a.MR.ptr && !a.ET.ptr && !a.IN.ptr);
+    auto al16 = [](const void *q) { return (((uintptr_t)q) & 15u) == 0; };
+    TFB_ARG_CHECK(al16(a.vol) && al16(a.vol_out) && al16(a.Q_in) && al16(a.Q_out) && al16(a.d) &&
+                  al16(a.u) && al16(p.coef) && al16(p.inv_rough) && al16(p.row_geom) &&
+                  ((((uintptr_t)p.geo32) & 7u) == 0) && ((((uintptr_t)p.width32) & 7u) == 0) &&
+                  ((((uintptr_t)p.S32) & 7u) == 0));
+    memset(&k, 0, sizeof(k));
+    k.g = 9.81;
+    k.dt = a.dt;
+    k.da = a.da.val;
+    k.Psum = ((a.P_rain.val + a.SM.val) + a.GW.val) + a.MR.val;
+    k.P_total = a.P_rain.val + a.SM.val;
+    k.tiles_x = (a.nx + kTW - 1) / kTW;
+    k.n_tiles = k.tiles_x * ((a.ny + kTR - 1) / kTR);
+    k.flags = src;
+    if (src == 0) {
+        TFB_ARG_CHECK(a.is_R_grid == 0);
+        const double R = k.Psum - (0.0 + a.IN.val);
+        k.Rdadt = (R * a.da.val) * a.dt;
+        src_mode = PK_SRC_NONE;
+        return TFB_OK;
+    }
+    TFB_ARG_CHECK(a.is_R_grid == 1);
+    if (src & TFB_CH_SRC_INFIL) {
+        TFB_ARG_CHECK(a.I && a.I_out && al16(a.I) && al16(a.I_out));
+        TFB_ARG_CHECK(!a.Ks.ptr && !a.Ki.ptr && !a.qs.ptr && !a.qi.ptr && !a.G.ptr &&
+                      !a.h_table.ptr && !a.elev.ptr);
+        TFB_ARG_CHECK(!(a.h_table.val >= a.elev.val));          // infil_base.py:697-701
+        k.Ks = a.Ks.val;
+        k.gkq = (a.G.val * (a.Ks.val - a.Ki.val)) * (a.qs.val - a.qi.val);
+        k.low_rain = (k.P_total < k.Ks) ? 1 : 0;
+    }
+    if (src == TFB_CH_SRC_INFIL) {
+        src_mode = PK_SRC_GA;
+        return TFB_OK;
+    }
+    // general fused sources: every parameter a scalar, T_air optionally a grid
+    src_mode = PK_SRC_FULL;
+    TFB_ARG_CHECK(!a.c0.ptr && !a.T0.ptr && !a.T_surf.ptr && !a.Qn_SW.ptr && !a.Qn_LW.ptr);
+    TFB_ARG_CHECK(al16(a.T_air.ptr));
+    if (src & TFB_CH_SRC_SNOW)
+        TFB_ARG_CHECK(a.h_swe && a.h_swe_out && al16(a.h_swe) && al16(a.h_swe_out) && al16(a.h_snow));
+    k.tair_grid = a.T_air.ptr ? 1 : 0;
+    k.P = a.P_rain.val; k.SMv = a.SM.val; k.GW = a.GW.val; k.MR = a.MR.val;
+    k.ETv = a.ET.val; k.INv = a.IN.val; k.T_air = a.T_air.val; k.T_rs = a.T_rain_snow;
+    k.c0_864 = a.c0.val / 8.64E7;
+    k.T0 = a.T0.val;
+    k.ratio = a.rho_H2O / a.rho_snow;
+    k.Qc = a.K_soil * (a.T_surf.val - a.T_soil_x) / a.soil_x;     // evap_base.py:326-353
+    k.Qnet = a.Qn_SW.val + a.Qn_LW.val;
+    k.alpha = a.alpha;
     return TFB_OK;
 }
 
@@ -535,50 +892,33 @@ int launch_packed(const tfb_channels_step_args &a, const tfb_channels_packed &p,
 
 extern "C" int tfb_channels_step_packed(const tfb_channels_step_args *ap,
                                         const tfb_channels_packed *pp, void *stream) {
-    TFB_ARG_CHECK(ap != nullptr && pp != nullptr);
-    const tfb_channels_step_args &a = *ap;
-    const tfb_channels_packed &p = *pp;
-    TFB_ARG_CHECK(a.ny > 0 && a.nx > 0 && a.halo >= 0 && (a.nx % 4) == 0);
-    TFB_ARG_CHECK(p.geo32 && p.width32 && p.coef && p.angle_lut && p.row_geom && p.n_angles >= 1 &&
-                  p.n_angles <= 256);
-    TFB_ARG_CHECK(a.dx && a.dy && a.dd && a.vol && a.vol_out && a.Q_in && a.Q_out && a.d && a.u);
-    TFB_ARG_CHECK(a.Q_in != a.Q_out && a.scalars && a.partials && a.ticket && a.dt > 0.0);
-    // eligibility: kinematic + Manning, lean outputs, uniform forcing
-    const uint32_t src = a.flags & (TFB_CH_SRC_MET | TFB_CH_SRC_SNOW | TFB_CH_SRC_EVAP |
-                                    TFB_CH_SRC_INFIL);
-    TFB_ARG_CHECK(!(a.flags & (TFB_CH_DIFFUSIVE | TFB_CH_LAW_OF_WALL | TFB_CH_DIAG |
-                               TFB_CH_WRITE_R)));
-    TFB_ARG_CHECK(src == 0 || src == TFB_CH_SRC_INFIL);
-    TFB_ARG_CHECK(!a.sinu.ptr && !a.da.ptr);
-    TFB_ARG_CHECK(!a.P_rain.ptr && !a.SM.ptr && !a.GW.ptr && !a.MR.ptr && !a.ET.ptr);
-    auto al16 = [](const void *q) { return (((uintptr_t)q) & 15u) == 0; };
-    TFB_ARG_CHECK(al16(a.vol) && al16(a.vol_out) && al16(a.Q_in) && al16(a.Q_out) && al16(a.d) &&
-                  al16(a.u) && al16(p.coef) && al16(p.row_geom) && ((((uintptr_t)p.geo32) & 7u) == 0) &&
-                  ((((uintptr_t)p.width32) & 7u) == 0));
     PkConsts k;
-    k.g = 9.81;
-    k.dt = a.dt;
-    k.da = a.da.val;
-    k.Psum = ((a.P_rain.val + a.SM.val) + a.GW.val) + a.MR.val;
-    k.P_total = a.P_rain.val + a.SM.val;
-    k.Ks = 0.0; k.gkq = 0.0; k.low_rain = 0;
-    k.tiles_x = (a.nx + kTW - 1) / kTW;
-    k.n_tiles = k.tiles_x * ((a.ny + kTR - 1) / kTR);
+    int mode = 0;
+    const int rc = prepare(ap, pp, false, k, mode);
+    if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (src) {
-        TFB_ARG_CHECK(a.I && a.I_out && al16(a.I) && al16(a.I_out) && a.is_R_grid == 1);
-        TFB_ARG_CHECK(!a.Ks.ptr && !a.Ki.ptr && !a.qs.ptr && !a.qi.ptr && !a.G.ptr &&
-                      !a.h_table.ptr && !a.elev.ptr);
-        TFB_ARG_CHECK(!(a.h_table.val >= a.elev.val));          // infil_base.py:697-701
-        k.Ks = a.Ks.val;
-        k.gkq = (a.G.val * (a.Ks.val - a.Ki.val)) * (a.qs.val - a.qi.val);
-        k.low_rain = (k.P_total < k.Ks) ? 1 : 0;
-        k.Rdadt = 0.0;
-        return launch_packed<true>(a, p, k, st);
-    } else {
-        TFB_ARG_CHECK(!a.IN.ptr && a.is_R_grid == 0);
-        const double R = k.Psum - (0.0 + a.IN.val);
-        k.Rdadt = (R * a.da.val) * a.dt;
-        return launch_packed<false>(a, p, k, st);
-    }
+    if (mode == PK_SRC_NONE) return launch_main<PK_SRC_NONE, PK_KW>(*ap, *pp, k, st);
+    if (mode == PK_SRC_GA) return launch_main<PK_SRC_GA, PK_KW>(*ap, *pp, k, st);
+    return launch_main<PK_SRC_FULL, PK_KW>(*ap, *pp, k, st);
+}
+
+extern "C" int tfb_channels_step_packed_dw_a(const tfb_channels_step_args *ap,
+                                             const tfb_channels_packed *pp, void *stream) {
+    PkConsts k;
+    int mode = 0;
+    const int rc = prepare(ap, pp, true, k, mode);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == PK_SRC_NONE) return launch_main<PK_SRC_NONE, PK_DWA>(*ap, *pp, k, st);
+    if (mode == PK_SRC_GA) return launch_main<PK_SRC_GA, PK_DWA>(*ap, *pp, k, st);
+    return launch_main<PK_SRC_FULL, PK_DWA>(*ap, *pp, k, st);
+}
+
+extern "C" int tfb_channels_step_packed_dw_b(const tfb_channels_step_args *ap,
+                                             const tfb_channels_packed *pp, void *stream) {
+    PkConsts k;
+    int mode = 0;
+    const int rc = prepare(ap, pp, true, k, mode);
+    if (rc) return rc;
+    return launch_dwb(*ap, *pp, k, (cudaStream_t)stream);
 }

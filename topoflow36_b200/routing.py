@@ -148,6 +148,7 @@ class ChannelsEngine(object):
         self.set_initial_depth(d0)
         self.n_steps = 0
         self.packed = None
+        self.mid_step_hook = None
         self.use_packed = bool(packed)
         self._angle_in = angle
         self._rough_in = rough
@@ -161,7 +162,7 @@ class ChannelsEngine(object):
         scalar sinuosity / pixel area, float32-exact widths, <= 256 distinct
         bank angles).  Everything is lossless; otherwise the generic kernel runs."""
         a = self.args
-        if (not self.kinematic) or (not self.manning) or self.diag or (self.flags & L.CH_WRITE_R):
+        if (not self.manning) or self.diag or (self.flags & L.CH_WRITE_R):
             return
         if self.nx % 4 or self.sinu_grid is not None or self._da_is_grid:
             return
@@ -195,7 +196,15 @@ class ChannelsEngine(object):
         aidx = (None if inv is None
                 else inv.to(torch.uint8).reshape(self.ny, self.nx).contiguous())
         rough = full(self.rough_grid, a.rough.val)
-        coef = (self.own(self.sqrtS) / rough).contiguous()
+        coef = inv_rough = S32 = None
+        if self.kinematic:
+            coef = (self.own(self.sqrtS) / rough).contiguous()
+        else:
+            S = self.own(self.S_bed)
+            S32 = S.float().contiguous()
+            if not bool((S32.double() == S).all()):
+                return
+            inv_rough = (1.0 / rough).contiguous()
         geo32 = torch.empty((self.ny, self.nx), dtype=torch.int32, device=dev)
         L.check(self.lib.tfb_channels_pack_geo32(self._p(self.code),
                                                  None if aidx is None else aidx.data_ptr(), self.ny,
@@ -211,11 +220,14 @@ class ChannelsEngine(object):
         if 0 <= orow < self.ny and 0 <= a.outlet_col < self.nx:
             n_out = float(rough[orow, a.outlet_col])
         pk = L.ChannelsPacked()
-        pk.geo32, pk.width32, pk.coef = geo32.data_ptr(), w32.data_ptr(), coef.data_ptr()
+        w32 = w32.contiguous()
+        pk.geo32, pk.width32 = geo32.data_ptr(), w32.data_ptr()
+        pk.coef = None if coef is None else coef.data_ptr()
+        pk.inv_rough = None if inv_rough is None else inv_rough.data_ptr()
+        pk.S32 = None if S32 is None else S32.data_ptr()
         pk.angle_lut, pk.row_geom = lut.data_ptr(), rowg.data_ptr()
         pk.outlet_rough, pk.n_angles = n_out, int(uniq.shape[0])
-        self._pack_keep = (geo32, w32.contiguous(), coef, lut, rowg)
-        pk.width32 = self._pack_keep[1].data_ptr()
+        self._pack_keep = (geo32, w32, coef, inv_rough, S32, lut, rowg)
         self.packed = pk
 
     def release_generic_inputs(self):
@@ -238,18 +250,11 @@ class ChannelsEngine(object):
         if self.packed is None or not self.use_packed:
             return False
         src = self.flags & (L.CH_SRC_MET | L.CH_SRC_SNOW | L.CH_SRC_EVAP | L.CH_SRC_INFIL)
-        if src not in (0, L.CH_SRC_INFIL):
+        # fused sources with scalar parameters; only T_air may be a grid (set_input
+        # gives it the slab's halo layout)
+        if any(isinstance(self.src[n], torch.Tensor) for n in _SRC_SG if n != 'T_air'):
             return False
-        for n in ('P_rain', 'SM', 'GW', 'MR', 'ET'):
-            if isinstance(self.src[n], torch.Tensor):
-                return False
-        if src:
-            for n in ('Ks', 'Ki', 'qs', 'qi', 'G', 'h_table', 'elev'):
-                if isinstance(self.src[n], torch.Tensor):
-                    return False
-            if self.args.h_table.val >= self.args.elev.val:
-                return False
-        elif isinstance(self.src['IN'], torch.Tensor):
+        if (src & L.CH_SRC_INFIL) and self.args.h_table.val >= self.args.elev.val:
             return False
         return True
 
@@ -449,8 +454,18 @@ class ChannelsEngine(object):
             setattr(a, name, self._p(buf[self.scur if dbl else 0]))
             setattr(a, name + '_out', self._p(buf[self.scur ^ 1 if dbl else 0]))
         if self._packed_ok():
-            L.check(self.lib.tfb_channels_step_packed(C.byref(a), C.byref(self.packed),
-                                                      L.stream_ptr()), 'tfb_channels_step_packed')
+            if self.kinematic:
+                L.check(self.lib.tfb_channels_step_packed(C.byref(a), C.byref(self.packed),
+                                                          L.stream_ptr()), 'tfb_channels_step_packed')
+            else:
+                # diffusive wave: new depths first, (slab: exchange one row of d), then
+                # free-surface slope, velocity and discharge
+                L.check(self.lib.tfb_channels_step_packed_dw_a(
+                    C.byref(a), C.byref(self.packed), L.stream_ptr()), 'tfb_channels_step_packed_dw_a')
+                if self.mid_step_hook is not None:
+                    self.mid_step_hook()
+                L.check(self.lib.tfb_channels_step_packed_dw_b(
+                    C.byref(a), C.byref(self.packed), L.stream_ptr()), 'tfb_channels_step_packed_dw_b')
             self.last_path = 'packed'
         else:
             if getattr(self, 'generic_released', False):

@@ -121,6 +121,10 @@ class SlabChannels(object):
             raise L.TfbError('SlabChannels needs an engine built with finalize=True')
         self.device = engine.device
         self.n_launches_per_step = 1
+        if layout.world_size > 1 and not engine.kinematic:
+            # packed diffusive step: the new depths of the boundary rows cross the link
+            # between pass A and pass B
+            engine.mid_step_hook = lambda: exchange_halos([engine.d], layout, [1], group)
 
     def __getattr__(self, name):           # state access falls through to the engine
         return getattr(self.__dict__['engine'], name)
