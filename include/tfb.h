@@ -223,6 +223,11 @@ typedef struct {
                                  (single GPU); 0: only leave the per-rank sums
                                  in partials[0..TFB_NSUM) for an allreduce, then
                                  call tfb_channels_fold()                       */
+    tfb_channels_scalars *scalars_mirror;  /* optional: device-visible address of
+                                 PINNED HOST memory; the folding thread copies the
+                                 updated scalar block there (posted writes over
+                                 PCIe), so the host reads Q_outlet etc. after a
+                                 stream synchronise without issuing a copy        */
 } tfb_channels_step_args;
 
 #define TFB_NSUM 24           /* doubles per rank exchanged by the allreduce:

@@ -127,6 +127,7 @@ class channels_component(BMI_base.BMI_component):
         self.SYNC_SCALARS = True      # D2H the scalar block after every update
         self.DIAGNOSTICS = False      # materialise Rh, A_wet, ... every step
         self._fused = None
+        self._last_scalar_in = {}
 
     # ---------------------------------------------------------------- attributes
     def __getattr__(self, name):
@@ -434,11 +435,23 @@ class channels_component(BMI_base.BMI_component):
 
     # -------------------------------------------------------------------- update
     def _bind_inputs(self):
+        """Hand the 6 source inputs to the engine.  Scalars are re-bound only when
+        their value changed (EMELI re-sets every input every step, mostly unchanged
+        0-D arrays); numpy grids are uploaded every step (the provider may have
+        mutated them in place); CUDA tensors are used where they are."""
         import torch
         e = self.engine
         self._et_host = None
+        last = self._last_scalar_in
         for n in _SRC_INPUTS:
             v = getattr(self, n)
+            if type(v) is np.ndarray and v.ndim == 0 or isinstance(v, (float, int, np.floating)):
+                f = float(v)
+                if last.get(n) != f:
+                    e.set_input(n, f)
+                    last[n] = f
+                continue
+            last[n] = None
             if isinstance(v, torch.Tensor):
                 e.set_input(n, v if v.dim() == 2 else float(v))
             elif np.ndim(v) == 2:
@@ -447,7 +460,9 @@ class channels_component(BMI_base.BMI_component):
                     self._et_host = v
             else:
                 e.set_input(n, float(v))
-        e.args.rho_H2O = float(self.rho_H2O)
+        rho = float(self.rho_H2O)
+        if rho != e.args.rho_H2O:
+            e.args.rho_H2O = rho
 
     def update(self, dt=-1.0):
         if self.comp_status.lower() == 'disabled':
@@ -477,13 +492,15 @@ class channels_component(BMI_base.BMI_component):
             self.DONE = True
 
     def sync_scalars(self):
-        """One D2H of tfb_channels_scalars into the 0-D arrays, in place."""
+        """Refresh the 0-D arrays in place from the scalar block the kernel wrote
+        into pinned host memory (one stream synchronise, no copy)."""
         s = self.engine.read_scalars()
         for n in _SCALAR_BLOCK:
             getattr(self, n).fill(getattr(s, n))
         self.dt_cfl_min.fill(s.dt_cfl_min)
-        for n in self.bad_counts:
-            self.bad_counts[n] = int(getattr(s, n))
+        b = self.bad_counts
+        b['n_neg_d'], b['n_nan_d'], b['n_inf_d'] = s.n_neg_d, s.n_nan_d, s.n_inf_d
+        b['n_neg_u'], b['n_nan_u'], b['n_inf_u'] = s.n_neg_u, s.n_nan_u, s.n_inf_u
         return s
 
     def _abort_banner(self, lines):

@@ -70,9 +70,19 @@ __device__ inline void fold_status(const tfb_channels_step_args &a, const double
     s.vol_Q += (s.Q_outlet * a.dt);
     s.step_count += 1;
 }
+// copy the scalar block to the pinned-host mirror, if any (called by the folding thread)
+__device__ inline void mirror_scalars(const tfb_channels_step_args &a) {
+    if (!a.scalars_mirror) return;
+    const double *src = reinterpret_cast<const double *>(a.scalars);
+    volatile double *dst = reinterpret_cast<volatile double *>(a.scalars_mirror);
+#pragma unroll 4
+    for (int j = 0; j < (int)(sizeof(tfb_channels_scalars) / sizeof(double)); ++j) dst[j] = src[j];
+    __threadfence_system();
+}
 __device__ inline void fold_scalars(const tfb_channels_step_args &a, const double *h) {
     fold_sums(a, h);
     fold_status(a, h);
+    mirror_scalars(a);
 }
 
 }  // namespace tfb

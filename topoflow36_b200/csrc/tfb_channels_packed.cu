@@ -395,7 +395,7 @@ __device__ __forceinline__ void pk_finish(const tfb_channels_step_args &a, Acc &
         if (a.finalize) {
             if (mode == 0) fold_scalars(a, h);
             else if (mode == 1) fold_sums(a, h);
-            else fold_status(a, h);
+            else { fold_status(a, h); mirror_scalars(a); }
         }
         a.ticket[0] = 0u;                                 // re-arm for the next launch
     }

@@ -80,6 +80,7 @@ class ChannelsStepArgs(C.Structure):
         ('I', vp), ('I_out', vp), ('h_table', SG), ('elev', SG),
         ('scalars', vp), ('partials', vp), ('ticket', vp),
         ('finalize', C.c_int32),
+        ('scalars_mirror', vp),
     ]
 
 

@@ -134,7 +134,7 @@ class ChannelsEngine(object):
         for n in _SRC_SG:
             self.set_input(n, 0.0)
         self.h_swe_buf = self.I_buf = None
-        self.h_snow = None
+        self._h_snow = None
         # ---- reductions ----------------------------------------------------
         self.scalars_dev = torch.zeros(C.sizeof(L.ChannelsScalars), dtype=torch.uint8,
                                        device=self.device)
@@ -144,10 +144,15 @@ class ChannelsEngine(object):
         a.scalars = self.scalars_dev.data_ptr()
         a.partials = self.partials.data_ptr()
         a.ticket = self.ticket.data_ptr()
+        # pinned host mirror of the scalar block: with unified addressing the device can
+        # write it directly, so reading Q_outlet costs a stream synchronise, not a copy
         self._scalars_host = torch.zeros(C.sizeof(L.ChannelsScalars), dtype=torch.uint8).pin_memory()
+        self._scalars_np = self._scalars_host.numpy()
+        a.scalars_mirror = self._scalars_host.data_ptr()
         self.set_initial_depth(d0)
         self.n_steps = 0
         self.packed = None
+        self._scalars_dirty = False
         self.mid_step_hook = None
         self.use_packed = bool(packed)
         self._angle_in = angle
@@ -341,7 +346,7 @@ class ChannelsEngine(object):
     def enable_fused_sources(self, met=False, snow=False, evap=False, infil=False,
                              T_rain_snow=0.0, rho_snow=300.0, alpha=1.26,
                              K_soil=0.45, soil_x=0.05, T_soil_x=0.0,
-                             h0_swe=0.0, I0=1e-6, use_table=False):
+                             h0_swe=0.0, I0=1e-6, use_table=False, materialize_h_snow=False):
         """Evaluate the met/snow/evap/infil source terms inside the routing
         kernel (TFB_CH_SRC_* flags) instead of taking them as inputs."""
         a = self.args
@@ -354,9 +359,15 @@ class ChannelsEngine(object):
             f |= L.CH_SRC_SNOW
             a.rho_snow = float(rho_snow)
             self.h_swe_buf = [self._grid_or_fill(h0_swe), self._zeros(torch.float64) if dbl else None]
-            self.h_snow = self._zeros(torch.float64)
-            self.own(self.h_snow).copy_(self.own(self.h_swe_buf[0]) * (a.rho_H2O / a.rho_snow))
-            a.h_snow = self._p(self.h_snow)
+            # snow depth = h_swe * rho_H2O / rho_snow (snow_base.py:631-703) is a pure
+            # function of the state: materialised every step only on request
+            if materialize_h_snow:
+                self._h_snow = self._zeros(torch.float64)
+                self.own(self._h_snow).copy_(self.own(self.h_swe_buf[0]) * (a.rho_H2O / a.rho_snow))
+                a.h_snow = self._p(self._h_snow)
+            else:
+                self._h_snow = None
+                a.h_snow = None
         if evap:
             f |= L.CH_SRC_EVAP
             a.alpha, a.K_soil = float(alpha), float(K_soil)
@@ -422,6 +433,14 @@ class ChannelsEngine(object):
         return self.own(self._sbuf(self.h_swe_buf))
 
     @property
+    def h_snow(self):
+        if self._h_snow is not None:
+            return self.own(self._h_snow)
+        if self.h_swe_buf is None:
+            return None
+        return self.h_swe * (self.args.rho_H2O / self.args.rho_snow)
+
+    @property
     def Q(self):
         """Discharge the LAST step used (= what the reference exposes as Q)."""
         return self.own(self.Q_buf[self.qcur ^ 1] if self.n_steps else self.Q_buf[self.qcur])
@@ -478,11 +497,16 @@ class ChannelsEngine(object):
         self.n_steps += 1
 
     def read_scalars(self):
-        """One D2H of the scalar block (synchronises the stream)."""
-        self._scalars_host.copy_(self.scalars_dev, non_blocking=True)
+        """The scalar block after the last step.  The kernel has already written it
+        into the pinned host mirror; this only synchronises the stream.  (Before the
+        first step, or after write_scalars, the block is copied explicitly.)"""
+        if self.n_steps == 0 or self._scalars_dirty:
+            self._scalars_host.copy_(self.scalars_dev, non_blocking=True)
+            self._scalars_dirty = False
         torch.cuda.current_stream().synchronize()
-        return L.ChannelsScalars.from_buffer_copy(self._scalars_host.numpy().tobytes())
+        return L.ChannelsScalars.from_buffer_copy(self._scalars_np)
 
     def write_scalars(self, s):
         raw = torch.frombuffer(bytearray(bytes(s)), dtype=torch.uint8)
         self.scalars_dev.copy_(raw)
+        self._scalars_dirty = True
