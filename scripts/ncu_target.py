@@ -1,15 +1,17 @@
-"""Tiny fixed workload for ncu captures: N routing steps at n x n."""
+"""Tiny fixed workload for ncu captures: N routing steps of a bench workload at n x n.
+    python scripts/ncu_target.py [n] [kw|kw_ga|dw|dw_full] [steps]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from scripts.probe_kernel import build
+from topoflow36_b200 import cases
 if __name__ == '__main__':
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-    mode = sys.argv[2] if len(sys.argv) > 2 else 'kw'
+    mode = sys.argv[2] if len(sys.argv) > 2 else 'kw_ga'
     steps = int(sys.argv[3]) if len(sys.argv) > 3 else 12
-    kw = dict(kw=dict(), ga=dict(infil=True), diag=dict(diag=True), dw=dict(kinematic=False))[mode]
-    e = build(n, **kw)
-    for _ in range(steps):
-        e.step()
+    src = {'kw_ga': 'ga', 'kw': 'none', 'dw': 'none', 'dw_full': 'full'}[mode]
+    e = cases.build_engine(n, n, kinematic=mode.startswith('kw'), sources=src,
+                           device=torch.device('cuda', 0))
+    for i in range(steps):
+        e.step(i / 60.0)
     torch.cuda.synchronize()
-    print('done', e.read_scalars().vol_R)
+    print('done', e.last_path, e.read_scalars().vol_R)

@@ -137,21 +137,29 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
            "r"(c0), "r"(c1) : "memory");
 }
 
-// tile geometry: 64 columns x 15 rows; consumer warp w owns row w, a lane 2 cells
-#ifndef TFB_PK_ROWS
-#define TFB_PK_ROWS 15      // 15 consumer warps + 1 producer warp = 512 threads: 128 registers each
-#endif
-constexpr int kTW = 64, kTR = TFB_PK_ROWS;
-constexpr int kQW = kTW + 4, kQR = kTR + 2;          // halo box: cols c0-2 .. c0+65, rows r0-1 .. r0+16
-constexpr int kConsumerWarps = kTR;
-constexpr int kThreads = (kConsumerWarps + 1) * 32;  // + 1 producer warp
-constexpr int kSzQ = ((kQW * kQR * 8 + 127) / 128) * 128;
-constexpr int kSzD = kTW * kTR * 8;                  // one fp64 tile
-constexpr int kSzF = kTW * kTR * 4;                  // one 32-bit tile
+// tile geometry: 64 columns x R rows.  CPL = cells per lane: 2 -> one consumer warp
+// per tile row (R + 1 warps, up to 128 registers per thread), 1 -> two warps per row
+// (2R + 1 warps: more latency hiding, 64 registers).  The best choice depends on the
+// register needs of the variant and is made per kernel instantiation (launch_main).
+constexpr int kTW = 64;
+constexpr int kQW = kTW + 4;                         // halo box: cols c0-2 .. c0+65
 constexpr int kSmemBudget = 196 * 1024;              // dynamic shared memory for the ring
+constexpr int kMaxWarps = 32;
+template <int ROWS, int CPL> struct TileCfg {
+    static constexpr int R = ROWS;
+    static constexpr int QR = ROWS + 2;              // halo box: rows r0-1 .. r0+R
+    static constexpr int cpl = CPL;
+    static constexpr int warps = ROWS * (2 / CPL);   // consumer warps
+    static constexpr int threads = (warps + 1) * 32; // + 1 producer warp
+    static constexpr int szQ = ((kQW * QR * 8 + 127) / 128) * 128;
+    static constexpr int szD = ((kTW * ROWS * 8 + 127) / 128) * 128;   // one fp64 tile
+    static constexpr int szF = ((kTW * ROWS * 4 + 127) / 128) * 128;   // one 32-bit tile
+    static constexpr int nD = kTW * ROWS * 8, nF = kTW * ROWS * 4, nQ = kQW * QR * 8;  // TMA bytes
+};
 
 // ring slot of the main kernel (kinematic step, or pass A of the diffusive step)
-template <int SRC, int VAR> struct StageLayout {
+template <int SRC, int VAR, class TC> struct StageLayout {
+    static constexpr int kSzQ = TC::szQ, kSzD = TC::szD, kSzF = TC::szF;
     static constexpr bool kCoef = (VAR == PK_KW);
     static constexpr bool kI = (SRC != PK_SRC_NONE);
     static constexpr bool kFullSrc = (SRC == PK_SRC_FULL);
@@ -167,18 +175,25 @@ template <int SRC, int VAR> struct StageLayout {
     static constexpr int stages = (kSmemBudget / bytes) > 6 ? 6 : (kSmemBudget / bytes);
 };
 // ring slot of pass B of the diffusive step
-struct StageLayoutB {
+template <class TC> struct StageLayoutB {
+    static constexpr int kSzQ = TC::szQ, kSzD = TC::szD, kSzF = TC::szF;
     static constexpr int oD = 0;                             // new depth with halo
     static constexpr int oN = oD + kSzQ;                     // 1 / n
     static constexpr int oS = oN + kSzD;                     // S_bed (f32)
     static constexpr int oW = oS + kSzF;
     static constexpr int oGeo = oW + kSzF;
     static constexpr int bytes = oGeo + kSzF;
-    static constexpr int tx_bytes = kQW * kQR * 8 + kSzD + 3 * kSzF;
-    static constexpr int stages = 6;
+    static constexpr int tx_bytes = TC::nQ + TC::nD + 3 * TC::nF;
+    static constexpr int stages = (kSmemBudget / bytes) > 6 ? 6 : (kSmemBudget / bytes);
 };
 
 struct PkIn { unsigned g; double vol, I, h, Ta, w, qself, ch[8]; };
+
+// v += x where the child-mask bit is set: a predicated DADD instead of add + select
+__device__ __forceinline__ void add_if(double &v, unsigned m, unsigned bit, double x) {
+    asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\t"
+        "@p add.rn.f64 %0, %0, %3;\n\t}" : "+d"(v) : "r"(m), "r"(bit), "d"(x));
+}
 struct PkVD { double v, d, I, h; };    // new volume / depth before the noflow zeroing, new state
 
 // new volume and depth of one cell: update_R :1548, update_flow_volume :1951,
@@ -220,16 +235,16 @@ __device__ __forceinline__ void pk_vol_depth(const PkConsts &k, const double *__
         if (k.flags & TFB_CH_SRC_SNOW) {                              // snow_degree_day :293-360
             double M = k.c0_864 * (Ta - k.T0);
             M = np_min(M, x.h / dt);                                  // snow_base :490-512
-            M = np_max(M, 0.0);
+            M = np_max0(M);
             SM = M;
             double hn = x.h + (P_snow * dt);                          // snow_base :559-609
             hn = hn - (M * dt);
-            o.h = np_max(hn, 0.0);
+            o.h = np_max0(hn);
             acc.s[S_VOL_SM] += (M * k.da) * dt;
         }
         if (k.flags & TFB_CH_SRC_EVAP) {                              // evap_priestley_taylor :308-413
             const double Qet = (k.alpha * (0.406 + (0.011 * Ta))) * (k.Qnet + k.Qc);
-            ET = np_max(Qet / 2.5E+9, 0.0);
+            ET = np_max0(Qet / 2.5E+9);
             et_grid = true;
             acc.s[S_VOL_ET] += (ET * k.da) * dt;
         }
@@ -254,28 +269,22 @@ __device__ __forceinline__ void pk_vol_depth(const PkConsts &k, const double *__
     } else {
         v = x.vol + k.Rdadt;
     }
-    if (cmask & 1u) v += dt * x.ch[0];                                // :2116-2131
-    if (cmask & 2u) v += dt * x.ch[1];
-    if (cmask & 4u) v += dt * x.ch[2];
-    if (cmask & 8u) v += dt * x.ch[3];
-    if (cmask & 16u) v += dt * x.ch[4];
-    if (cmask & 32u) v += dt * x.ch[5];
-    if (cmask & 64u) v += dt * x.ch[6];
-    if (cmask & 128u) v += dt * x.ch[7];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) add_if(v, cmask, 1u << j, dt * x.ch[j]);   // :2116-2131
     v -= (x.qself * dt);                                              // :2138
-    v = np_max(v, 0.0);                                               // :2145
-    // update_channel_depth :2299-2330, :2379
-    const double tn = lut[4 * ai], inv2tan = lut[4 * ai + 1];
+    v = np_max0(v);                                                   // :2145
+    // update_channel_depth :2299-2330, :2379; table entry = {tan, 1/(2 tan), 1/cos, 4 tan}
+    const double2 t01 = *reinterpret_cast<const double2 *>(lut + 4 * ai);
     double d;
-    if (tn == 0.0) {
+    if (t01.x == 0.0) {
         d = v / (x.w * ds);
     } else {
         double arg = (lut[4 * ai + 3] * v) * inv_ds;
         arg += x.w * x.w;
-        d = (sqrt(arg) - x.w) * inv2tan;
+        d = (sqrt(arg) - x.w) * t01.y;
     }
     o.v = v;
-    o.d = np_max(d, 0.0);
+    o.d = np_max0(d);
 }
 
 // hydraulic radius, velocity, next discharge, stability counters of one cell:
@@ -288,14 +297,13 @@ __device__ __forceinline__ void pk_velocity(const tfb_channels_step_args &a, con
                                             float &rate_max, double &u_out, double &Qn_out) {
     const unsigned code = g & 0xffu, ai = (g >> 16) & 0xffu;
     const bool noflow = (code == 0);
-    const double tn = lut[4 * ai], invcos = lut[4 * ai + 2];
+    const double tn = lut[4 * ai], invcos = lut[4 * ai + 2];          // {tan, 1/(2 tan), 1/cos, 4 tan}
     const double A_wet = d * (w + (d * tn));                          // :2668-2703
     double P_wet = w + ((2.0 * d) * invcos);
     if (noflow) P_wet = 1.0;
     double Rh = A_wet / P_wet;
     if (noflow) Rh = 0.0;
-    const double cb = cbrt(Rh);
-    double u = (cb * cb) * umul;                                      // :3982-3983
+    double u = pow23(Rh) * umul;                                      // :3982-3983
     if (noflow) u = 0.0;                                              // :2862
     if (r + a.row0 == a.outlet_row && c == a.outlet_col) {            // :2896-2904
         double f_o = 0.0;
@@ -323,6 +331,7 @@ struct PkMapsB { CUtensorMap D, N, S, w, geo; };
 // CTA-level reduction of the per-thread accumulators, per-CTA row, last-CTA fold in
 // CTA order (deterministic).  `mode`: 0 = everything, 1 = sums only (pass A), 2 =
 // status only (pass B).
+template <int NWARPS>
 __device__ __forceinline__ void pk_finish(const tfb_channels_step_args &a, Acc &acc, float rate_max,
                                           bool consumer, int fail, int mode,
                                           double (*sm)[kPartialStride], double *tot, bool *is_last) {
@@ -351,9 +360,9 @@ __device__ __forceinline__ void pk_finish(const tfb_channels_step_args &a, Acc &
     if (tid < kPartialStride) {
         double v = 0.0;
         if (tid == P_DTMIN) {
-            for (int w = 0; w < kConsumerWarps; ++w) v = fmax(v, sm[w][tid]);
+            for (int w = 0; w < NWARPS; ++w) v = fmax(v, sm[w][tid]);
         } else if (tid < S_NSLOT) {
-            for (int w = 0; w < kConsumerWarps; ++w) v += sm[w][tid];
+            for (int w = 0; w < NWARPS; ++w) v += sm[w][tid];
         }
         if (tid == S_NNAN_D && fail) v += 1.0e9;          // pipeline failure poisons the step
         a.partials[(int64_t)(blockIdx.x + 2) * kPartialStride + tid] = v;
@@ -405,15 +414,16 @@ __device__ __forceinline__ void pk_finish(const tfb_channels_step_args &a, Acc &
 // main kernel: the kinematic step (VAR = PK_KW) or pass A of the diffusive step
 // (VAR = PK_DWA: new volume, new depth and source state only)
 // ---------------------------------------------------------------------------
-template <int SRC, int VAR>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int SRC, int VAR, class TC>
+__global__ void __launch_bounds__(TC::threads, 1)
 channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed p,
                        const PkConsts k, const __grid_constant__ PkMaps maps) {
-    using SL = StageLayout<SRC, VAR>;
+    using SL = StageLayout<SRC, VAR, TC>;
+    constexpr int kTR = TC::R, kConsumerWarps = TC::warps, kThreads = TC::threads;
     constexpr int NS = SL::stages;
     constexpr bool kKW = (VAR == PK_KW);
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ double lut[256 * 4];
+    __shared__ __align__(16) double lut[256 * 4];
     __shared__ double sm[kConsumerWarps][kPartialStride];
     __shared__ double tot[kPartialStride];
     __shared__ __align__(8) uint64_t full_bar[NS], empty_bar[NS];
@@ -448,8 +458,8 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
         if (lane == 0) {
             int stage = 0;
             unsigned phase = 0;
-            const unsigned tx = (unsigned)(kQW * kQR * 8 + kSzD * (1 + (kKW ? 1 : 0) + (use_i ? 1 : 0) +
-                                                                 (use_h ? 1 : 0) + (use_t ? 1 : 0)) + 2 * kSzF);
+            const unsigned tx = (unsigned)(TC::nQ + TC::nD * (1 + (kKW ? 1 : 0) + (use_i ? 1 : 0) +
+                                                              (use_h ? 1 : 0) + (use_t ? 1 : 0)) + 2 * TC::nF);
             for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
                 if (!mbar_wait(&empty_bar[stage], phase ^ 1u)) { s_fail = 1; break; }
                 const int ty = t / k.tiles_x, txi = t - ty * k.tiles_x;
@@ -475,6 +485,50 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
         for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
             if (!mbar_wait(&full_bar[stage], phase)) { s_fail = 1; break; }
             const int ty = t / k.tiles_x, txi = t - ty * k.tiles_x;
+            if constexpr (TC::cpl == 1) {
+            const int row = warp >> 1, ct = ((warp & 1) << 5) + lane;  // two warps per tile row
+            const int c0 = txi * kTW + ct, r = ty * kTR + row;
+            const unsigned char *st = smem + (size_t)stage * SL::bytes;
+            if (r < a.ny && c0 < a.nx) {
+                const int e = row * kTW + ct;
+                PkIn x;
+                x.g = *reinterpret_cast<const unsigned *>(st + SL::oGeo + e * 4);
+                x.w = (double)*reinterpret_cast<const float *>(st + SL::oW + e * 4);
+                x.vol = *reinterpret_cast<const double *>(st + SL::oVol + e * 8);
+                x.I = use_i ? *reinterpret_cast<const double *>(st + SL::oI + e * 8) : 0.0;
+                x.h = use_h ? *reinterpret_cast<const double *>(st + SL::oH + e * 8) : 0.0;
+                x.Ta = use_t ? *reinterpret_cast<const double *>(st + SL::oT + e * 8) : 0.0;
+                // Q window: halo rows row .. row+2, halo cols ct+1 .. ct+3 (= c0-1 .. c0+1);
+                // children in the order SW, W, NW, N, NE, E, SE, S
+                const double *q = reinterpret_cast<const double *>(st + SL::oQ) + row * kQW + ct + 1;
+                x.ch[0] = q[2 * kQW]; x.ch[1] = q[kQW]; x.ch[2] = q[0]; x.ch[3] = q[1];
+                x.ch[4] = q[2]; x.ch[5] = q[kQW + 2]; x.ch[6] = q[2 * kQW + 2]; x.ch[7] = q[2 * kQW + 1];
+                x.qself = q[kQW + 1];
+                const double2 *rgp = reinterpret_cast<const double2 *>(p.row_geom + (int64_t)r * 6);
+                const double2 g0 = __ldg(rgp), g1 = __ldg(rgp + 1), g2 = __ldg(rgp + 2);
+                PkVD o;
+                pk_vol_depth<SRC>(k, lut, x, g0, g1, g2, acc, o);
+                const int64_t i = (int64_t)r * a.nx + c0;
+                const bool nf = (x.g & 0xffu) == 0u;
+                if (kKW) {
+                    const bool dg = (x.g & 0x55u) != 0u, ns = (x.g & 0x88u) != 0u;
+                    const double coef = *reinterpret_cast<const double *>(st + SL::oCoef + e * 8);
+                    double u, Qn;
+                    pk_velocity(a, k, lut, x.g, o.d, x.w, coef, dg ? g2.x : (ns ? g2.y : g1.y),
+                                x.qself, p.outlet_rough, r, c0, acc, rate_max, u, Qn);
+                    a.u[i] = u;
+                    a.Q_out[i] = Qn;
+                }
+                if (nf) { acc.s[S_VOL_EDGE] += o.v; o.v = 0.0; if (kKW) o.d = 0.0; }   // :2960-2966
+                a.vol_out[i] = o.v;
+                a.d[i] = o.d;
+                if (use_i) a.I_out[i] = o.I;
+                if (use_h) {
+                    a.h_swe_out[i] = o.h;
+                    if (a.h_snow) a.h_snow[i] = o.h * k.ratio;
+                }
+            }
+            } else {
             const int c0 = txi * kTW + lane * 2, r = ty * kTR + warp;
             const unsigned char *st = smem + (size_t)stage * SL::bytes;
             if (r < a.ny && c0 < a.nx) {
@@ -548,25 +602,29 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
                             make_double2(o0.h * k.ratio, o1.h * k.ratio);
                 }
             }
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[stage]);            // slot may be refilled
             if (++stage == NS) { stage = 0; phase ^= 1u; }
         }
     }
-    pk_finish(a, acc, rate_max, warp < kConsumerWarps, s_fail, kKW ? 0 : 1, sm, tot, &is_last);
+    pk_finish<kConsumerWarps>(a, acc, rate_max, warp < kConsumerWarps, s_fail, kKW ? 0 : 1, sm, tot,
+                              &is_last);
 }
 
 // ---------------------------------------------------------------------------
 // pass B of the diffusive step: free-surface slope from the NEW depths of the
 // cell and its D8 parent (channels_base.py:2583-2618), velocity, next discharge
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1)
+template <class TC>
+__global__ void __launch_bounds__(TC::threads, 1)
 channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_packed p,
                            const PkConsts k, const __grid_constant__ PkMapsB maps) {
-    using SL = StageLayoutB;
+    using SL = StageLayoutB<TC>;
+    constexpr int kTR = TC::R, kConsumerWarps = TC::warps, kThreads = TC::threads;
     constexpr int NS = SL::stages;
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ double lut[256 * 4];
+    __shared__ __align__(16) double lut[256 * 4];
     __shared__ double sm[kConsumerWarps][kPartialStride];
     __shared__ double tot[kPartialStride];
     __shared__ __align__(8) uint64_t full_bar[NS], empty_bar[NS];
@@ -616,6 +674,38 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
         for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
             if (!mbar_wait(&full_bar[stage], phase)) { s_fail = 1; break; }
             const int ty = t / k.tiles_x, txi = t - ty * k.tiles_x;
+            if constexpr (TC::cpl == 1) {
+            const int row = warp >> 1, ct = ((warp & 1) << 5) + lane;
+            const int c0 = txi * kTW + ct, r = ty * kTR + row;
+            const unsigned char *st = smem + (size_t)stage * SL::bytes;
+            if (r < a.ny && c0 < a.nx) {
+                const int e = row * kTW + ct;
+                const unsigned g = *reinterpret_cast<const unsigned *>(st + SL::oGeo + e * 4);
+                const double w = (double)*reinterpret_cast<const float *>(st + SL::oW + e * 4);
+                const double Sb = (double)*reinterpret_cast<const float *>(st + SL::oS + e * 4);
+                const double invn = *reinterpret_cast<const double *>(st + SL::oN + e * 8);
+                const double *dc = reinterpret_cast<const double *>(st + SL::oD) + (row + 1) * kQW + ct + 2;
+                const double d = dc[0];
+                const unsigned code = g & 0xffu;
+                int dr, dcol;
+                code_offset(code, dr, dcol);
+                const double d_par = dc[dr * kQW + dcol];                 // new depth of the D8 parent
+                const double2 *rgp = reinterpret_cast<const double2 *>(p.row_geom + (int64_t)r * 6);
+                const double2 g1 = __ldg(rgp + 1), g2 = __ldg(rgp + 2);
+                const bool dg = (code & 0x55u) != 0u, ns = (code & 0x88u) != 0u;
+                const double inv_ds = dg ? g2.x : (ns ? g2.y : g1.y);
+                const double Sf = Sb + ((d - d_par) * inv_ds);            // :2606-2607
+                const int64_t i = (int64_t)r * a.nx + c0;
+                double qs = 0.0;
+                if (r + a.row0 == a.outlet_row && c0 == a.outlet_col) qs = __ldg(a.Q_in + i);
+                double u, Qn;
+                pk_velocity(a, k, lut, g, d, w, sqrt(fabs(Sf)) * invn, inv_ds, qs, p.outlet_rough, r, c0,
+                            acc, rate_max, u, Qn);
+                a.u[i] = u;
+                a.Q_out[i] = Qn;
+                if (code == 0u) a.d[i] = 0.0;                              // :2966
+            }
+            } else {
             const int c0 = txi * kTW + lane * 2, r = ty * kTR + warp;
             const unsigned char *st = smem + (size_t)stage * SL::bytes;
             if (r < a.ny && c0 < a.nx) {
@@ -656,12 +746,13 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
                 if (((geo.x & 0xffu) == 0u) || ((geo.y & 0xffu) == 0u))
                     *reinterpret_cast<double2 *>(a.d + i) = make_double2(dd_[0], dd_[1]);
             }
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[stage]);
             if (++stage == NS) { stage = 0; phase ^= 1u; }
         }
     }
-    pk_finish(a, acc, rate_max, warp < kConsumerWarps, s_fail, 2, sm, tot, &is_last);
+    pk_finish<kConsumerWarps>(a, acc, rate_max, warp < kConsumerWarps, s_fail, 2, sm, tot, &is_last);
 }
 
 }  // namespace tfb
@@ -748,10 +839,12 @@ int get_map(const void *ptr, int64_t rows, int64_t cols, CUtensorMapDataType dty
     return TFB_OK;
 }
 
-template <int SRC, int VAR>
-int launch_main(const tfb_channels_step_args &a, const tfb_channels_packed &p, const PkConsts &k,
+template <int SRC, int VAR, class TC>
+int launch_main(const tfb_channels_step_args &a, const tfb_channels_packed &p, PkConsts k,
                 cudaStream_t st) {
-    using SL = StageLayout<SRC, VAR>;
+    using SL = StageLayout<SRC, VAR, TC>;
+    constexpr int kTR = TC::R, kQR = TC::QR, kThreads = TC::threads;
+    k.n_tiles = k.tiles_x * ((a.ny + kTR - 1) / kTR);
     static_assert(SL::stages >= 2, "ring needs at least two slots");
     PkMaps m;
     const int64_t rows_h = (int64_t)a.ny + 2 * a.halo;
@@ -776,20 +869,23 @@ int launch_main(const tfb_channels_step_args &a, const tfb_channels_packed &p, c
     int dev = 0;
     TFB_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev >= 64 || !attr_set[dev]) {
-        TFB_CUDA_CHECK(cudaFuncSetAttribute(channels_packed_kernel<SRC, VAR>,
+        TFB_CUDA_CHECK(cudaFuncSetAttribute(channels_packed_kernel<SRC, VAR, TC>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         if (dev < 64) attr_set[dev] = true;
     }
     int64_t grid = sm_count();
     if (grid > k.n_tiles) grid = k.n_tiles;
-    channels_packed_kernel<SRC, VAR><<<(int)grid, kThreads, smem, st>>>(a, p, k, m);
+    channels_packed_kernel<SRC, VAR, TC><<<(int)grid, kThreads, smem, st>>>(a, p, k, m);
     TFB_CUDA_CHECK(cudaGetLastError());
     return TFB_OK;
 }
 
-int launch_dwb(const tfb_channels_step_args &a, const tfb_channels_packed &p, const PkConsts &k,
+template <class TC>
+int launch_dwb(const tfb_channels_step_args &a, const tfb_channels_packed &p, PkConsts k,
                cudaStream_t st) {
-    using SL = StageLayoutB;
+    using SL = StageLayoutB<TC>;
+    constexpr int kTR = TC::R, kQR = TC::QR, kThreads = TC::threads;
+    k.n_tiles = k.tiles_x * ((a.ny + kTR - 1) / kTR);
     PkMapsB m;
     const int64_t rows_h = (int64_t)a.ny + 2 * a.halo;
     const size_t hb = (size_t)a.halo * a.nx;
@@ -804,13 +900,13 @@ int launch_dwb(const tfb_channels_step_args &a, const tfb_channels_packed &p, co
     int dev = 0;
     TFB_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev >= 64 || !attr_set[dev]) {
-        TFB_CUDA_CHECK(cudaFuncSetAttribute(channels_packed_dwb_kernel,
+        TFB_CUDA_CHECK(cudaFuncSetAttribute(channels_packed_dwb_kernel<TC>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         if (dev < 64) attr_set[dev] = true;
     }
     int64_t grid = sm_count();
     if (grid > k.n_tiles) grid = k.n_tiles;
-    channels_packed_dwb_kernel<<<(int)grid, kThreads, smem, st>>>(a, p, k, m);
+    channels_packed_dwb_kernel<TC><<<(int)grid, kThreads, smem, st>>>(a, p, k, m);
     TFB_CUDA_CHECK(cudaGetLastError());
     return TFB_OK;
 }
@@ -847,7 +943,7 @@ int prepare(const tfb_channels_step_args *ap, const tfb_channels_packed *pp, boo
     k.Psum = ((a.P_rain.val + a.SM.val) + a.GW.val) + a.MR.val;
     k.P_total = a.P_rain.val + a.SM.val;
     k.tiles_x = (a.nx + kTW - 1) / kTW;
-    k.n_tiles = k.tiles_x * ((a.ny + kTR - 1) / kTR);
+    k.n_tiles = 0;                                   // set per tile configuration by the launcher
     k.flags = src;
     if (src == 0) {
         TFB_ARG_CHECK(a.is_R_grid == 0);
@@ -890,6 +986,20 @@ int prepare(const tfb_channels_step_args *ap, const tfb_channels_packed *pp, boo
 
 }  // namespace
 
+// tile configurations (rows, cells per lane), chosen from measurements on B200: variants
+// that fit 64 registers run two warps per tile row (31 warps per SM), the register-
+// hungry fused-source variants one warp per row with 128 registers
+#ifndef TFB_PK_GA_ROWS
+#define TFB_PK_GA_ROWS 15
+#endif
+#ifndef TFB_PK_GA_CPL
+#define TFB_PK_GA_CPL 2
+#endif
+typedef TileCfg<15, 1> CfgNone;
+typedef TileCfg<TFB_PK_GA_ROWS, TFB_PK_GA_CPL> CfgGA;
+typedef TileCfg<15, 2> CfgFull;
+typedef TileCfg<15, 1> CfgDwB;
+
 extern "C" int tfb_channels_step_packed(const tfb_channels_step_args *ap,
                                         const tfb_channels_packed *pp, void *stream) {
     PkConsts k;
@@ -897,9 +1007,9 @@ extern "C" int tfb_channels_step_packed(const tfb_channels_step_args *ap,
     const int rc = prepare(ap, pp, false, k, mode);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (mode == PK_SRC_NONE) return launch_main<PK_SRC_NONE, PK_KW>(*ap, *pp, k, st);
-    if (mode == PK_SRC_GA) return launch_main<PK_SRC_GA, PK_KW>(*ap, *pp, k, st);
-    return launch_main<PK_SRC_FULL, PK_KW>(*ap, *pp, k, st);
+    if (mode == PK_SRC_NONE) return launch_main<PK_SRC_NONE, PK_KW, CfgNone>(*ap, *pp, k, st);
+    if (mode == PK_SRC_GA) return launch_main<PK_SRC_GA, PK_KW, CfgGA>(*ap, *pp, k, st);
+    return launch_main<PK_SRC_FULL, PK_KW, CfgFull>(*ap, *pp, k, st);
 }
 
 extern "C" int tfb_channels_step_packed_dw_a(const tfb_channels_step_args *ap,
@@ -909,9 +1019,9 @@ extern "C" int tfb_channels_step_packed_dw_a(const tfb_channels_step_args *ap,
     const int rc = prepare(ap, pp, true, k, mode);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (mode == PK_SRC_NONE) return launch_main<PK_SRC_NONE, PK_DWA>(*ap, *pp, k, st);
-    if (mode == PK_SRC_GA) return launch_main<PK_SRC_GA, PK_DWA>(*ap, *pp, k, st);
-    return launch_main<PK_SRC_FULL, PK_DWA>(*ap, *pp, k, st);
+    if (mode == PK_SRC_NONE) return launch_main<PK_SRC_NONE, PK_DWA, CfgNone>(*ap, *pp, k, st);
+    if (mode == PK_SRC_GA) return launch_main<PK_SRC_GA, PK_DWA, CfgGA>(*ap, *pp, k, st);
+    return launch_main<PK_SRC_FULL, PK_DWA, CfgFull>(*ap, *pp, k, st);
 }
 
 extern "C" int tfb_channels_step_packed_dw_b(const tfb_channels_step_args *ap,
@@ -920,5 +1030,5 @@ extern "C" int tfb_channels_step_packed_dw_b(const tfb_channels_step_args *ap,
     int mode = 0;
     const int rc = prepare(ap, pp, true, k, mode);
     if (rc) return rc;
-    return launch_dwb(*ap, *pp, k, (cudaStream_t)stream);
+    return launch_dwb<CfgDwB>(*ap, *pp, k, (cudaStream_t)stream);
 }
