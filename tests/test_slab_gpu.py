@@ -97,3 +97,101 @@ def test_two_slabs_equal_one_grid(kinematic, infil, devgen):
         p.join(timeout=60)
     assert all(ok for _, ok, _, _ in res), res
     assert any(m for _, _, m, _ in res)
+
+
+def _comp_worker(rank, world, port, case_dir, kinematic, q):
+    """The BMI component under torch.distributed: each rank initialises from the
+    SAME CFG/RTG files, reads only its rows, and the gathered grids must equal a
+    single-GPU component run (made on rank 0's device)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world,
+                            device_id=torch.device('cuda', rank))
+    try:
+        from topoflow36_b200 import channels_kinematic_wave as ckw, channels_diffusive_wave as cdw
+        mod = ckw if kinematic else cdw
+        cfg = os.path.join(case_dir, 'Case1' + mod.channels_component._att_map['cfg_extension'])
+        c = mod.channels_component()
+        c.initialize(cfg_file=cfg, mode='nondriver', SILENT=True)
+        assert c.layout is not None and c.layout.world_size == world
+        ny, nx = c.ny, c.nx
+        rng = np.random.default_rng(4)
+        ETg, INg = 2e-6 * rng.random((ny, nx)), 3e-6 * rng.random((ny, nx))
+        ET = ETg.copy()
+        z = lambda v: np.array(v, dtype='float64')
+        L = {n: ln for ln, n in c._var_name_map.items()}
+        for k, v in dict(P_rain=z(80 / 3.6e6), MR=z(0), GW=z(1e-7), SM=z(2e-7), rho_H2O=z(1000.0),
+                         ET=ET, IN=INg.copy()).items():
+            c.set_value(L[k], v)
+        for i in range(80):
+            c.update()
+        grids = {n: c.gather_grid(n) for n in ('vol', 'd', 'u', 'Q')}
+        scal = {n: float(getattr(c, n)) for n in ('vol_R', 'vol_edge', 'vol_Q', 'Q_outlet', 'Q_peak',
+                                                   'T_peak')}
+        c.finalize()
+        scal['vol_chan_sum'] = float(c.vol_chan_sum)
+        scal['Q_max'] = float(c.Q_max)
+        ok, fails = True, []
+        if rank == 0:
+            dist.destroy_process_group()          # the comparison run is a plain 1-GPU component
+            one = mod.channels_component()
+            one.initialize(cfg_file=cfg, mode='nondriver', SILENT=True)
+            assert one.layout is None
+            ET1 = ETg.copy()
+            for k, v in dict(P_rain=z(80 / 3.6e6), MR=z(0), GW=z(1e-7), SM=z(2e-7),
+                             rho_H2O=z(1000.0), ET=ET1, IN=INg.copy()).items():
+                one.set_value(L[k], v)
+            for i in range(80):
+                one.update()
+            for n, g in grids.items():
+                if not np.array_equal(g, getattr(one, n)):
+                    fails.append('%s differs in %d cells' % (n, int((g != getattr(one, n)).sum())))
+            one.finalize()
+            for n, v in scal.items():
+                w = float(getattr(one, n))
+                if abs(v - w) > 1e-12 * max(abs(w), 1e-300):
+                    fails.append('%s %r vs %r' % (n, v, w))
+            lay_rows = slice(0, c.layout.ny)
+            if not np.array_equal(ET[lay_rows], ET1[lay_rows]):
+                fails.append('ET mask of the owned rows')
+            if not float(one.Q.max()) > 0:
+                fails.append('nothing moved')
+        q.put((rank, not fails, fails))
+    finally:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('kinematic', [True, False])
+def test_component_two_slabs_equal_one_gpu(tmp_path, kinematic):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    from topoflow36_b200 import cases, synth
+    from topoflow36_b200.d8 import D8Toolkit
+    ny, nx = 130, 96
+    DEM = synth.fractal_dem(ny, nx, seed=9, sigma=1.0)
+    DEM = np.float32(np.round(DEM * 4) / 4)                 # flats across the slab boundary
+    width, angle, nval = synth.channel_params(ny, nx, seed=9)
+    tk = D8Toolkit(DEM)
+    tk.update_flow_grid()
+    slope = tk.slope().cpu().numpy()
+    synth.write_case(str(tmp_path), DEM, slope, width, angle, nval=nval, dt=2.0,
+                     kinematic=kinematic, outlet=(ny - 2, nx // 2), check_stability='Yes')
+    world = 2
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_comp_worker, args=(r, world, port, str(tmp_path), kinematic, q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res

@@ -128,6 +128,9 @@ class channels_component(BMI_base.BMI_component):
         self.DIAGNOSTICS = False      # materialise Rh, A_wet, ... every step
         self._fused = None
         self._last_scalar_in = {}
+        self.layout = None            # SlabLayout in multi-GPU (row-slab) mode
+        self.stepper = None           # SlabChannels wrapper in slab mode, else the engine
+        self.group = None             # torch.distributed process group (None = world)
 
     # ---------------------------------------------------------------- attributes
     def __getattr__(self, name):
@@ -177,6 +180,22 @@ class channels_component(BMI_base.BMI_component):
         import torch
         torch.from_numpy(m).copy_(t)
         return m
+
+    def gather_grid(self, name, dst=0):
+        """Slab mode: the GLOBAL (ny, nx) numpy grid of a device variable on rank
+        `dst` (None elsewhere); collective.  Single GPU: the grid itself."""
+        import torch
+        import torch.distributed as dist
+        t = self._device_tensor(name).contiguous()
+        if self.layout is None or self.layout.world_size == 1:
+            return t.cpu().numpy()
+        lay = self.layout
+        parts = ([torch.empty((n, lay.nx), dtype=t.dtype, device=t.device) for _, n in lay.parts]
+                 if lay.rank == dst else None)
+        dist.gather(t, parts, dst=dst, group=self.group)
+        if lay.rank != dst:
+            return None
+        return torch.cat(parts, 0).cpu().numpy()
 
     def get_value_tensor(self, long_var_name):
         """Device tensor behind a grid variable (zero copy; GPU-aware users)."""
@@ -272,6 +291,7 @@ class channels_component(BMI_base.BMI_component):
             self.status = 'initialized'
             return
         self.set_computed_input_vars()
+        self.initialize_slab_layout()
         self.initialize_d8_vars()
         self.read_input_files()
         self.initialize_computed_vars()
@@ -297,11 +317,37 @@ class channels_component(BMI_base.BMI_component):
         self.bad_counts = dict(n_neg_d=0, n_nan_d=0, n_inf_d=0, n_neg_u=0, n_nan_u=0,
                                n_inf_u=0)
 
+    def initialize_slab_layout(self):
+        """Row-slab sharding when the component runs under torch.distributed with
+        more than one rank (one process per GPU): this rank owns rows [row0, row0+ny)
+        of the global grid; `self.ny`, `self.nx` keep the GLOBAL shape (BMI grid
+        info), `self.layout` describes the slab."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return
+        world = dist.get_world_size(self.group)
+        if world == 1:
+            return
+        from .slab import SlabLayout
+        halo = 1 if self.KINEMATIC_WAVE else 2
+        self.layout = SlabLayout(self.ny, self.nx, dist.get_rank(self.group), world, halo)
+        if np.ndim(self.da) != 0:
+            raise NotImplementedError('slab mode needs fixed-length pixels (scalar da)')
+
+    def _rows(self):
+        """(row_lo, row_hi) of the rows this rank keeps of a per-cell input: its slab
+        plus halo (the whole grid on a single GPU)."""
+        if self.layout is None:
+            return 0, self.ny
+        lay = self.layout
+        return lay.row0 - lay.halo, lay.row0 + lay.ny + lay.halo
+
     def initialize_d8_vars(self):
         """channels_base.py:1074-1135: an embedded D8 component on the same DEM."""
         from . import d8_global
         self.d8 = d8_global.d8_component()
         self.d8.device = self.device
+        self.d8.layout, self.d8.group = self.layout, self.group
         cfg = self.cfg_directory + self.case_prefix + '_d8_global.cfg'
         self.d8.initialize(cfg_file=cfg, SILENT=self.SILENT, REPORT=self.REPORT)
         self.d8.update(self.time, REPORT=self.REPORT)
@@ -317,7 +363,8 @@ class channels_component(BMI_base.BMI_component):
         if vtype not in ('grid', 'grid_sequence'):
             raise RuntimeError('No match found for ' + vtype + '.')
         path = self.topo_directory + getattr(self, name + '_file')
-        g = np.float64(grid_io.read_rtg(path, self.rti, 'FLOAT'))     # model_input.py:181
+        lo, hi = self._rows()
+        g = np.float64(grid_io.read_rtg_rows(path, self.rti, lo, hi, 'FLOAT'))   # model_input.py:181
         if factor != 1.0:
             g *= factor
         return g
@@ -351,28 +398,54 @@ class channels_component(BMI_base.BMI_component):
         else:
             raise ValueError('In CFG file, MANNING=0 and LAW_OF_WALL=0.')
         self.angle = self.angle * self.deg_to_rad                      # :1196
-        tk = self.d8.toolkit
+        lay = self.layout
+        if lay is None:
+            tk = self.d8.toolkit
+            code, dxh, dyh, ddh = tk.code, tk.dx_host, tk.dy_host, tk.dd_host
+            dw = lambda: tk.dw.cpu().numpy()
+            ny_loc, row0, halo = self.ny, 0, 0
+        else:
+            sd = self.d8.slab
+            code, dxh, dyh, ddh = sd['code'], sd['dx'], sd['dy'], sd['dd']
+            ny_loc, row0, halo = lay.ny, lay.row0, lay.halo
+
+            def dw():
+                t = torch.empty(code.shape, dtype=torch.float32, device=code.device)
+                n = code.shape[0]
+                r = [torch.full((n,), float(v[0]), dtype=torch.float32, device=code.device)
+                     for v in (dxh, dyh, ddh)]
+                L.check(L.load().tfb_d8_ds_dw(code.data_ptr(), r[0].data_ptr(), r[1].data_ptr(),
+                                              r[2].data_ptr(), n, self.nx, None, t.data_ptr(),
+                                              L.stream_ptr()), 'tfb_d8_ds_dw')
+                return t.cpu().numpy()
         if np.ndim(self.width) == 2:
             w0 = (self.width == 0)                                     # :1206-1209
             if w0.any():
-                self.width[w0] = tk.dw.cpu().numpy()[w0]
+                self.width[w0] = dw()[w0]
         self.slope = self.slope / self.sinu                            # :1247
         if self.KINEMATIC_WAVE:
             self.remove_bad_slopes()                                   # :1316
         self.S_bed = self.slope
         rough = self.nval if self.MANNING else self.z0val
+        own = (lambda g: g) if lay is None else (lambda g: g)
         self.engine = ChannelsEngine(
-            self.ny, self.nx, dt=float(self.dt), code=tk.code, dx=tk.dx_host, dy=tk.dy_host,
-            dd=tk.dd_host, S_bed=self.S_bed, width=self.width, angle=self.angle,
+            ny_loc, self.nx, dt=float(self.dt), code=code, dx=dxh, dy=dyh,
+            dd=ddh, S_bed=self.S_bed, width=self.width, angle=self.angle,
             tan_angle=np.tan(self.angle), cos_angle=np.cos(self.angle), rough=rough,
             sinu=self.sinu if np.ndim(self.sinu) == 2 else float(self.sinu),
             da=self.da, d0=self.d0 if np.ndim(self.d0) == 2 else float(self.d0),
             kinematic=self.KINEMATIC_WAVE, manning=self.MANNING,
             diag=bool(self.DIAGNOSTICS or self.SAVE_F_GRIDS or self.SAVE_F_PIXELS),
             write_R=bool(self.WRITE_R), outlet=(int(self.outlet_ID[0]), int(self.outlet_ID[1])),
-            rho_H2O=float(self.rho_H2O), device=self.device)
+            rho_H2O=float(self.rho_H2O), device=self.device, row0=row0, ny_global=self.ny,
+            halo=halo, finalize=True, n_pixels_global=ny_loc * self.nx)
         if self._fused:
             self.engine.enable_fused_sources(**self._fused)
+        if lay is None:
+            self.stepper = self.engine
+        else:
+            from .slab import SlabChannels
+            self.stepper = SlabChannels(lay, self.engine, self.group)
         self.update_total_channel_water_volume()
         self.vol_chan_sum0 = self.vol_chan_sum.copy()
         torch.cuda.current_stream().synchronize()
@@ -406,12 +479,18 @@ class channels_component(BMI_base.BMI_component):
         (channels_base.py:4164-4260)."""
         S = self.slope
         bad = np.isnan(S) | (S == 0.0) | (S < 0.0) | np.isinf(S)
-        if not bad.any():
+        if not bad.any() and self.layout is None:
             return
         good = ~bad
-        if not good.any():
+        S_min = S[good].min() if good.any() else np.inf
+        if self.layout is not None:
+            import torch
+            import torch.distributed as dist
+            t = torch.tensor([float(S_min)], dtype=torch.float64, device=self.device or 'cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+            S_min = float(t.item())
+        if not np.isfinite(S_min):
             raise ValueError('remove_bad_slopes: no positive finite slope in the grid')
-        S_min = S[good].min()
         S[bad] = S_min
         if not self.SILENT:
             print('WARNING: %d zero, negative or NaN slopes replaced with min(S) = %s'
@@ -455,9 +534,17 @@ class channels_component(BMI_base.BMI_component):
             if isinstance(v, torch.Tensor):
                 e.set_input(n, v if v.dim() == 2 else float(v))
             elif np.ndim(v) == 2:
-                e.set_input(n, v)
-                if n == 'ET':
-                    self._et_host = v
+                lay = self.layout
+                if lay is not None and v.shape[0] == self.ny:
+                    # a GLOBAL grid: this rank takes its rows (+ halo); the in-place ET
+                    # masking goes back into the owned rows of the provider's array
+                    e.set_input(n, lay.take(v))
+                    if n == 'ET':
+                        self._et_host = v[lay.row0:lay.row0 + lay.ny]
+                else:
+                    e.set_input(n, v)
+                    if n == 'ET':
+                        self._et_host = v
             else:
                 e.set_input(n, float(v))
         rho = float(self.rho_H2O)
@@ -471,7 +558,7 @@ class channels_component(BMI_base.BMI_component):
         if self.mode == 'driver' and not self.SILENT:
             self.print_time_and_value(self.Q_outlet, 'Q_out', '[m^3/s]')
         self._bind_inputs()
-        self.engine.step(time_min=float(self.time_min))
+        self.stepper.step(float(self.time_min))
         if self._et_host is not None:
             # provider's ET array is masked in place (channels_base.py:1625-1627)
             import torch
@@ -493,8 +580,9 @@ class channels_component(BMI_base.BMI_component):
 
     def sync_scalars(self):
         """Refresh the 0-D arrays in place from the scalar block the kernel wrote
-        into pinned host memory (one stream synchronise, no copy)."""
-        s = self.engine.read_scalars()
+        into pinned host memory (one stream synchronise, no copy; in slab mode one
+        all-reduce forms the global values -- collective)."""
+        s = self.stepper.read_scalars()
         for n in _SCALAR_BLOCK:
             getattr(self, n).fill(getattr(s, n))
         self.dt_cfl_min.fill(s.dt_cfl_min)
@@ -557,9 +645,32 @@ class channels_component(BMI_base.BMI_component):
 
     def _minmax(self):
         """Q/u/d interior extrema and total channel volume (channels_base.py
-        :2986-3110) in one reduction kernel."""
+        :2986-3110): one reduction kernel on a single GPU; in slab mode local torch
+        reductions over the owned interior cells + one all-reduce each."""
         import torch
         e = self.engine
+        if self.layout is not None:
+            import torch.distributed as dist
+            lay = self.layout
+            r0 = 1 if lay.row0 == 0 else 0
+            r1 = lay.ny - 1 if lay.row0 + lay.ny == self.ny else lay.ny
+            inner = lambda t: t[r0:r1, 1:-1]
+            big = 1.0e308
+            mn = torch.stack([inner(t).min() if r1 > r0 else torch.tensor(big, device=e.device,
+                              dtype=torch.float64) for t in (e.Q, e.own(e.u), e.own(e.d))])
+            mx = torch.stack([inner(t).max() if r1 > r0 else torch.tensor(-big, device=e.device,
+                              dtype=torch.float64) for t in (e.Q, e.own(e.u), e.own(e.d))])
+            sm = e.vol.sum().reshape(1)
+            dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=self.group)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM, group=self.group)
+            mn, mx = mn.cpu().numpy(), mx.cpu().numpy()
+            if e.n_steps > 0:
+                for k, n in enumerate(('Q', 'u', 'd')):
+                    getattr(self, n + '_min').fill(mn[k])
+                    getattr(self, n + '_max').fill(mx[k])
+            self.vol_chan_sum.fill(float(sm))
+            return
         out = torch.zeros(7, dtype=torch.float64, device=e.device)
         npart = e.lib.tfb_sources_partials_len()
         part = torch.zeros(npart, dtype=torch.float64, device=e.device)
@@ -599,6 +710,11 @@ class channels_component(BMI_base.BMI_component):
     # utils/text_ts_files.py); frames are fetched from the device only when due.
     def open_output_files(self):
         self._out = {}
+        if self.layout is not None and self.layout.rank != 0:
+            self._out_any = any(getattr(self, 'SAVE_%s_%s' % (K, kind))
+                                for K in 'QUDF' for kind in ('GRIDS', 'PIXELS'))
+            return
+        self._out_any = True
         kinds = {'Q': 'Q', 'U': 'u', 'D': 'd', 'F': 'f'}
         for K, v in kinds.items():
             if getattr(self, 'SAVE_%s_GRIDS' % K):
@@ -627,17 +743,27 @@ class channels_component(BMI_base.BMI_component):
         return '%s_%d%s' % (stem, k, ext)
 
     def write_output_files(self, time_seconds=None):
-        if not getattr(self, '_out', None):
+        if not getattr(self, '_out', None) and not (self.layout is not None and
+                                                    getattr(self, '_out_any', False)):
             return
         t = int(self.time_sec if time_seconds is None else time_seconds)
-        if t % int(self.save_grid_dt) == 0:
-            for (kind, v), fh in self._out.items():
+        slab = self.layout is not None
+        names = {'Q': 'SAVE_Q', 'u': 'SAVE_U', 'd': 'SAVE_D', 'f': 'SAVE_F'}
+        for kind, dt_save in (('gs', self.save_grid_dt), ('ts', self.save_pixels_dt)):
+            if t % int(dt_save) != 0:
+                continue
+            for v, flag in names.items():
+                if not getattr(self, flag + ('_GRIDS' if kind == 'gs' else '_PIXELS')):
+                    continue
+                # slab mode: every rank takes part in the gather, rank 0 writes
+                grid = self.gather_grid(v) if slab else self._fetch(v)
+                fh = self._out.get((kind, v))
+                if fh is None:
+                    continue
                 if kind == 'gs':
-                    np.float32(self._fetch(v)).tofile(fh)
-        if t % int(self.save_pixels_dt) == 0:
-            for (kind, v), fh in self._out.items():
-                if kind == 'ts':
-                    vals = self._fetch(v)[self.outlet_IDs]
+                    np.float32(grid).tofile(fh)
+                else:
+                    vals = grid[self.outlet_IDs]
                     fh.write(('%15.7f' % float(self.time_min)) +
                              ''.join('%15.7f' % x for x in vals) + '\n')
 

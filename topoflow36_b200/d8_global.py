@@ -35,6 +35,8 @@ class d8_component(BMI_base.BMI_component):
         BMI_base.BMI_component.__init__(self)
         self.toolkit = None
         self.device = None
+        self.layout = None            # SlabLayout when the grid is row-sharded over ranks
+        self.group = None
         self._slope_dev = None
         self._pid_dev = None
 
@@ -64,6 +66,10 @@ class d8_component(BMI_base.BMI_component):
             self.DEM_file = self.site_prefix + '_DEM.rtg'
         self.DEM_file = self.topo_directory + os.path.basename(self.DEM_file) \
             if not os.path.isabs(self.DEM_file) else self.DEM_file
+        if self.layout is not None and self.layout.world_size > 1:
+            self._initialize_slab()
+            self.status = 'initialized'
+            return
         self.read_DEM()
         dx, dy, dd = grid_io.pixel_sizes_by_row(self.rti)
         # cast to float32 as the reference does (d8_base.py:515-518)
@@ -75,6 +81,25 @@ class d8_component(BMI_base.BMI_component):
                                  A_units=str(self.A_units), device=self.device)
         self.status = 'initialized'
 
+    def _initialize_slab(self):
+        """Row-sharded D8: this rank reads its rows (+ halo) of the DEM and runs the
+        distributed flow-grid construction of slab.slab_d8 (global Jacobi flat
+        linking); contributing area is a whole-basin quantity and is not computed
+        in slab mode."""
+        if int(self.rti.pixel_geom) != 1:
+            raise NotImplementedError('slab mode needs fixed-length pixels')
+        if self.rti.data_type != 'FLOAT':
+            raise L.TfbError('GPU D8 kernels take a FLOAT (float32) DEM')
+        from .slab import slab_d8
+        lay = self.layout
+        hd = lay.halo + 1
+        DEM = grid_io.read_rtg_rows(self.DEM_file, self.rti, lay.row0 - hd, lay.row0 + lay.ny + hd)
+        self.slab = slab_d8(DEM, lay, hd, link_flats=bool(int(self.LINK_FLATS)),
+                            xres=float(self.rti.xres), yres=float(self.rti.yres),
+                            nodata=getattr(self, 'nodata', -9999.0), kinematic=False,
+                            device=self.device, group=self.group)
+        self.n_flat_link_reps = self.slab['n_reps']
+
     def read_DEM(self):
         if self.rti.data_type != 'FLOAT':
             raise L.TfbError('GPU D8 kernels take a FLOAT (float32) DEM; %s is %s'
@@ -84,6 +109,9 @@ class d8_component(BMI_base.BMI_component):
     def update(self, time=None, REPORT=False, SILENT=True):
         """d8_base.update (:358-416): flow grid, parent IDs, ds/dw, area."""
         self.status = 'updating'
+        if self.toolkit is None:              # slab mode: everything was done in initialize()
+            self.status = 'updated'
+            return
         self.toolkit.update(with_counts=True)
         self._slope_dev = self._pid_dev = None
         self.n_flat_link_reps = self.toolkit.n_reps

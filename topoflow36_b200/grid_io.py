@@ -153,6 +153,25 @@ def read_rtg(path, info, rtg_type=None):
     return grid
 
 
+def read_rtg_rows(path, info, row_lo, row_hi, rtg_type=None):
+    """Rows [row_lo, row_hi) of a grid file (clipped to the grid); rows outside the
+    grid are returned as copies of the nearest valid row.  Used by slab-sharded
+    components so that every rank touches only its own part of the file."""
+    dtype = np.dtype(_NUMPY_TYPE[(rtg_type or info.data_type).upper()])
+    lo, hi = max(0, int(row_lo)), min(int(info.nrows), int(row_hi))
+    if os.path.getsize(path) < info.n_pixels * dtype.itemsize:
+        raise IOError('RTG file %s is shorter than %d values' % (path, info.n_pixels))
+    mm = np.memmap(path, dtype=dtype, mode='r', shape=(info.nrows, info.ncols))
+    part = np.array(mm[lo:hi])
+    del mm
+    if info.SWAP_ENDIAN:
+        part = part.byteswap()
+    top, bot = lo - int(row_lo), int(row_hi) - hi
+    if top or bot:
+        part = np.concatenate([np.repeat(part[:1], top, 0), part, np.repeat(part[-1:], bot, 0)], 0)
+    return part
+
+
 def write_rtg(path, grid, info, rtg_type='FLOAT'):
     rtg_type = rtg_type.upper()
     if rtg_type == 'BYTE':
