@@ -128,6 +128,7 @@ class channels_component(BMI_base.BMI_component):
         self.DIAGNOSTICS = False      # materialise Rh, A_wet, ... every step
         self._fused = None
         self._last_scalar_in = {}
+        self._et_slab_ready = False
         self.layout = None            # SlabLayout in multi-GPU (row-slab) mode
         self.stepper = None           # SlabChannels wrapper in slab mode, else the engine
         self.group = None             # torch.distributed process group (None = world)
@@ -537,10 +538,18 @@ class channels_component(BMI_base.BMI_component):
                 lay = self.layout
                 if lay is not None and v.shape[0] == self.ny:
                     # a GLOBAL grid: this rank takes its rows (+ halo); the in-place ET
-                    # masking goes back into the owned rows of the provider's array
-                    e.set_input(n, lay.take(v))
+                    # masking goes back into the owned rows of the provider's array.
+                    # The masked ET is STATE (zeros persist, channels_base.py:1625-1627):
+                    # after the first upload only the owned rows are refreshed from the
+                    # host, the halo rows come from the neighbours (update()).
+                    own = v[lay.row0:lay.row0 + lay.ny]
+                    if n == 'ET' and self._et_slab_ready:
+                        e.set_input(n, own)
+                    else:
+                        e.set_input(n, lay.take(v))
                     if n == 'ET':
-                        self._et_host = v[lay.row0:lay.row0 + lay.ny]
+                        self._et_host = own
+                        self._et_slab_ready = True
                 else:
                     e.set_input(n, v)
                     if n == 'ET':
@@ -563,6 +572,9 @@ class channels_component(BMI_base.BMI_component):
             # provider's ET array is masked in place (channels_base.py:1625-1627)
             import torch
             torch.from_numpy(self._et_host).copy_(self.engine.own(self.engine.src['ET']))
+            if self.layout is not None and not self.KINEMATIC_WAVE:
+                from .slab import exchange_halos
+                exchange_halos([self.engine.src['ET']], self.layout, [1], self.group)
         OK = True
         if self.SYNC_SCALARS or self.CHECK_STABILITY:
             self.sync_scalars()
