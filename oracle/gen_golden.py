@@ -164,6 +164,51 @@ def gen_synth_channels(work):
     np.savez_compressed(os.path.join(GOLD, 'synth_channels.npz'), **out)
 
 
+def gen_flood(work):
+    """FLOOD_OPTION (rectangle-over-trapezoid overbank flow) on the 61 x 83 synthetic
+    case with shallow banks, KW and DW, 150 steps of heavy rain then recession."""
+    import topoflow.components.d8_global as d8g
+    ny, nx = 61, 83
+    DEM = synth.fractal_dem(ny, nx, seed=7, sigma=1.0)
+    width, angle, nval = synth.channel_params(ny, nx, seed=7)
+    rng = np.random.default_rng(99)
+    angle = np.float32(np.where(rng.random((ny, nx)) < 0.15, 0.0, 20.0 + 40.0 * rng.random((ny, nx))))
+    d_bank = np.float32(0.02 + 0.05 * rng.random((ny, nx)))
+    out = dict(DEM=DEM, width=width, angle=angle, nval=nval, d_bankfull=d_bank)
+    for kin in (True, False):
+        tag = 'kw' if kin else 'dw'
+        cdir = os.path.join(work, 'flood_' + tag)
+        cfg = synth.write_case(cdir, DEM, np.zeros_like(DEM), width, angle, nval=nval, dt=2.0,
+                               kinematic=kin, outlet=(ny - 2, nx // 2), flood=True,
+                               d_bankfull=d_bank)
+        d8 = d8g.d8_component()
+        rh.quiet_call(d8.initialize, cfg_file=os.path.join(cdir, 'Case1_d8_global.cfg'),
+                      SILENT=True, REPORT=False)
+        rh.quiet_call(d8.update, 0)
+        d8.update_noflow_IDs()
+        d8.update_slope_grid()
+        info = grid_io.read_rti(os.path.join(cdir, 'Synth.rti'))
+        grid_io.write_rtg(os.path.join(cdir, 'Synth_slope.rtg'), d8.S, info)
+        if kin:
+            out['code'] = np.array(d8.d8_grid)
+            out['slope'] = np.float32(d8.S)
+        c = standalone_channels(cfg, kin, dict(
+            P_rain=z(150 / 3.6e6), MR=z(0), GW=z(0), SM=z(0), rho_H2O=z(1000.0),
+            ET=z(0), IN=z(0)))
+        assert c.FLOOD_OPTION
+        for i in range(150):
+            if i == 100:
+                c.set_value(LONG['P_rain'], z(0))
+            rh.quiet_call(c.update)
+            if i == 99:
+                out[tag + '_dflood_max_at_100'] = np.float64(c.d_flood.max())
+        for k, v in snapshot(c).items():
+            out[tag + '_' + k] = v
+        for k in ('d_flood', 'vol_flood', 'vol_chan', 'Qc', 'Qf'):
+            out[tag + '_' + k] = np.array(getattr(c, k), dtype='float64')
+    np.savez_compressed(os.path.join(GOLD, 'flood_channels.npz'), **out)
+
+
 def gen_d8(work):
     """D8 toolkit on a DEM with plenty of ties and flats (elevations quantised
     to 0.25 m) and a few nodata cells; LINK_FLATS on and off."""
@@ -301,6 +346,7 @@ def main():
         meta = {'numpy': np.__version__, 'reference': 'peckhams/topoflow36 @ /root/reference'}
         meta['treynor_emeli'] = gen_treynor(work)
         gen_synth_channels(work)
+        gen_flood(work)
         gen_d8(work)
         gen_sources()
         with open(os.path.join(GOLD, 'meta.json'), 'w') as fh:

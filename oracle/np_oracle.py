@@ -314,7 +314,7 @@ class Channels(object):
     def __init__(self, code, ds32, dw32, slope, width, angle_deg, nval=None,
                  z0val=None, sinu=1.0, d0=0.0, da=900.0, dt=6.0,
                  kinematic=True, manning=True, outlet=(0, 0),
-                 rho_H2O=1000.0, check_stability=True):
+                 rho_H2O=1000.0, check_stability=True, flood=False, d_bankfull=10.0):
         f64 = np.float64
         self.code = code
         self.ny, self.nx = code.shape
@@ -363,6 +363,20 @@ class Channels(object):
         self.vol = self.A_wet * self.ds
         self.Q = z()
         self.Rh = z()
+        # ---- flood option :1346-1388 (rectangle over trapezoid, Sep. 2019)
+        self.FLOOD_OPTION = bool(flood)
+        self.d_flood = z()
+        self.vol_flood = z()
+        if self.FLOOD_OPTION:
+            self.vol_chan = self.vol
+            self.vol = self.vol_chan.copy()
+            self.Qc, self.Qf = z(), z()
+            self.flood_manning_n = 0.10
+            self.width_ratio = 5.0
+            self.d_bankfull = np.array(d_bankfull, dtype=f64)
+            L3 = self.d_bankfull * np.tan(self.angle)
+            Ac_bankfull = self.d_bankfull * (self.width + L3)
+            self.vol_bankfull = Ac_bankfull * self.ds
         self.vol_chan_sum0 = self.vol.sum()
         for n in ('Q_outlet', 'u_outlet', 'd_outlet', 'f_outlet', 'Q_peak',
                   'T_peak', 'u_peak', 'Tu_peak', 'd_peak', 'Td_peak'):
@@ -393,8 +407,17 @@ class Channels(object):
             self.vol_R += (volume * self.n_pixels)
         else:
             self.vol_R += np.sum(volume)
-        # update_channel_discharge :1697
-        self.Q[:] = self.u * self.A_wet
+        # update_channel_discharge :1697 (+ update_flood_discharge :1701-1750,
+        # update_discharge :1791-1862 when FLOOD_OPTION)
+        if self.FLOOD_OPTION:
+            self.Qc[:] = self.u * self.A_wet
+            Sf = self.S_bed if self.KINEMATIC_WAVE else self.S_free
+            uf = (self.d_flood ** TWO_THIRDS) * np.sqrt(np.abs(Sf)) / self.flood_manning_n
+            Af = self.width_ratio * self.width * self.d_flood
+            self.Qf[:] = uf * Af
+            self.Q[:] = self.Qc + self.Qf
+        else:
+            self.Q[:] = self.u * self.A_wet
         # update_flow_volume :2086-2145
         self.vol += (self.R * self.da) * dt
         pr, pc = self.parent_IDs
@@ -404,8 +427,16 @@ class Channels(object):
                 self.vol[pr[wk], pc[wk]] += (dt * self.Q[wk])
         self.vol -= (self.Q * dt)
         np.maximum(self.vol, 0.0, self.vol)
+        if self.FLOOD_OPTION:
+            # update_channel_volume :2149, update_flood_volume :2158-2185
+            np.minimum(self.vol, self.vol_bankfull, self.vol_chan)
+            np.maximum(self.vol - self.vol_bankfull, 0.0, self.vol_flood)
         # update_channel_depth :2250-2391
         self._update_depth()
+        if self.FLOOD_OPTION:
+            # update_flood_depth :2393-2448
+            denom = (self.width_ratio * self.width * self.ds)
+            np.maximum(self.vol_flood / denom, 0.0, self.d_flood)
         # update_trapezoid_Rh :2643-2712
         d, wb = self.d, self.width
         L2 = d * np.tan(self.angle)
@@ -419,7 +450,11 @@ class Channels(object):
         self.P_wet[:] = P_wet
         # update_free_surface_slope :2583-2618
         if not self.KINEMATIC_WAVE:
-            delta_d = (self.d - self.d[self.parent_IDs])
+            if self.FLOOD_OPTION:
+                total_d = (self.d + self.d_flood)
+                delta_d = total_d - total_d[self.parent_IDs]
+            else:
+                delta_d = (self.d - self.d[self.parent_IDs])
             self.S_free[:] = self.S_bed + (delta_d / self.ds)
         # shear stress / speed :2620-2641
         slope = self.S_bed if self.KINEMATIC_WAVE else np.abs(self.S_free)
@@ -474,6 +509,9 @@ class Channels(object):
         self.vol_edge += self.vol[self.noflow].sum()
         self.vol[self.noflow] = 0.0
         self.d[self.noflow] = 0.0
+        if self.FLOOD_OPTION:
+            self.vol_flood[self.noflow] = 0.0
+            self.d_flood[self.noflow] = 0.0
         # checks :3193-3454
         self.n_bad_depth = int((self.d < 0.0).sum() + np.isinf(self.d).sum())
         self.n_bad_vel = int((self.u < 0.0).sum() + np.isnan(self.u).sum()
@@ -489,7 +527,8 @@ class Channels(object):
         self.time_min = self.time / f64(60)
 
     def _update_depth(self):
-        vol, width, angle = self.vol, self.width, self.angle
+        vol = self.vol_chan if self.FLOOD_OPTION else self.vol            # :2251
+        width, angle = self.width, self.angle
         d = self.d
         with np.errstate(invalid='ignore', divide='ignore'):
             if np.size(angle) == 1:

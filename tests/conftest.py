@@ -52,3 +52,8 @@ def rel_err(a, b):
     if scale == 0:
         return float(np.abs(a).max())
     return float(np.abs(a - b).max() / scale)
+
+
+@pytest.fixture(scope='session')
+def flood_gold():
+    return load_golden('flood_channels.npz')

@@ -138,3 +138,29 @@ def test_sources_bit_exact(sources_gold):
     assert np.array_equal(ET, g['pt_ET'])
     pr, ps = o.met_split_precip(g['met_P'], g['met_T_air'], 0.5)
     assert np.array_equal(pr, g['met_P_rain']) and np.array_equal(ps, g['met_P_snow'])
+
+
+@pytest.mark.parametrize('tag', ['kw', 'dw'])
+def test_flood_option_bit_exact(flood_gold, tag):
+    """FLOOD_OPTION (channels_base.py:1701-1862, :2149-2185, :2393-2448): the numpy
+    restatement against a stand-alone run of the reference with overbank flow."""
+    g = flood_gold
+    kin = (tag == 'kw')
+    code = g['code']
+    ny, nx = code.shape
+    dx, dy, dd = o.pixel_dims(ny, 30.0, 30.0)
+    ds32, dw32 = o.d8_ds_dw(code, dx, dy, dd)
+    ch = o.Channels(code, ds32, dw32, g['slope'], g['width'], g['angle'], nval=g['nval'],
+                    da=900.0, dt=2.0, kinematic=kin, outlet=(ny - 2, nx // 2), flood=True,
+                    d_bankfull=g['d_bankfull'])
+    z = lambda v: np.array(v, dtype='float64')
+    ch.P_rain = z(150 / 3.6e6)
+    for i in range(150):
+        if i == 100:
+            ch.P_rain = z(0)
+        ch.step()
+    assert g[tag + '_d_flood'].max() > 0.1          # the banks really overflow
+    for n in GRIDS + ('d_flood', 'vol_flood', 'vol_chan', 'Qc', 'Qf') + (() if kin else ('S_free',)):
+        assert np.array_equal(getattr(ch, n), g[tag + '_' + n], equal_nan=True), n
+    for n in SCALARS:
+        assert float(getattr(ch, n)) == float(g[tag + '_' + n]), n

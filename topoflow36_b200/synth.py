@@ -68,9 +68,9 @@ d0_type             | Scalar          | string    | allowed input types
 d0                  | {d0}               | float     | initial flow depth [m]
 sinu_type           | Scalar        | string    | allowed input types
 sinu                | {sinu}             | float     | absolute channel sinuosity [m/m]
-d_bankfull_type     | Scalar          | string     | allowed input types
-d_bankfull          | 10.0    | float      | channel bankfull water depth [m]
-CHECK_STABILITY     | {check}     | string    | option to check depths and velocities every step
+d_bankfull_type     | {dbank_type}          | string     | allowed input types
+d_bankfull          | {dbank}    | {dbank_kind}      | channel bankfull water depth [m]
+{flood_line}CHECK_STABILITY     | {check}     | string    | option to check depths and velocities every step
 #===============================================================================
 # Output 1
 save_grid_dt        | 60.0     | float     | time interval between saved grids [sec]
@@ -134,7 +134,8 @@ def write_case(case_dir, DEM, slope, width, angle, nval=None, z0val=None,
                site='Synth', case='Case1', dx=30.0, dy=30.0, dt=1.0,
                kinematic=True, manning=True, link_flats=1, outlet=None,
                n_steps=100, d0=0.0, sinu=1.0, scalar_angle=None,
-               scalar_width=None, check_stability='Yes', byte_order=None):
+               scalar_width=None, check_stability='Yes', byte_order=None, flood=False,
+               d_bankfull=None):
     """Write a stand-alone routing case into `case_dir` (all files side by
     side; in_directory = out_directory = '.').  Returns the channels CFG path."""
     os.makedirs(case_dir, exist_ok=True)
@@ -155,6 +156,8 @@ def write_case(case_dir, DEM, slope, width, angle, nval=None, z0val=None,
         grid_io.write_rtg(p(site + '_chan-n.rtg'), nval, info)
     if z0val is not None and np.ndim(z0val) == 2:
         grid_io.write_rtg(p(site + '_chan-z0.rtg'), z0val, info)
+    if d_bankfull is not None and np.ndim(d_bankfull) == 2:
+        grid_io.write_rtg(p(site + '_d-bank.rtg'), d_bankfull, info)
     with open(p(case + '_path_info.cfg'), 'w') as fh:
         fh.write('#' + '=' * 79 + '\n# TopoFlow Config File for: Path_Information\n'
                  '#' + '=' * 79 + '\n'
@@ -189,6 +192,15 @@ def write_case(case_dir, DEM, slope, width, angle, nval=None, z0val=None,
             0.01 if z0val is None else (z0val if np.ndim(z0val) == 0 else 0))
     wd = gs(scalar_width is None, '_chan-w.rtg', scalar_width or 0)
     an = gs(scalar_angle is None, '_chan-a.rtg', scalar_angle or 0)
+    db = gs(d_bankfull is not None and np.ndim(d_bankfull) == 2, '_d-bank.rtg',
+            10.0 if d_bankfull is None or np.ndim(d_bankfull) == 2 else d_bankfull)
+    flood_line = ''
+    if flood:
+        flood_line = ('FLOOD_OPTION        | 1     | int        | option to model overbank flow\n'
+                      'SAVE_DF_GRIDS       | No     | string    | option to save d_flood grids\n'
+                      'd_flood_gs_file     | [case_prefix]_2D-d-flood.nc  | string    | filename\n'
+                      'SAVE_DF_PIXELS      | No     | string    | option to save d_flood series\n'
+                      'd_flood_ts_file     | [case_prefix]_0D-d-flood.txt | string    | filename\n')
     ext = '_channels_kinematic_wave.cfg' if kinematic else '_channels_diffusive_wave.cfg'
     cfg = p(case + ext)
     with open(cfg, 'w') as fh:
@@ -200,5 +212,6 @@ def write_case(case_dir, DEM, slope, width, angle, nval=None, z0val=None,
             z0_type=z0[0], z0val=z0[1], z0_kind=z0[2],
             width_type=wd[0], width=wd[1], width_kind=wd[2],
             angle_type=an[0], angle=an[1], angle_kind=an[2],
-            d0=repr(float(d0)), sinu=repr(float(sinu)), check=check_stability))
+            d0=repr(float(d0)), sinu=repr(float(sinu)), check=check_stability,
+            dbank_type=db[0], dbank=db[1], dbank_kind=db[2], flood_line=flood_line))
     return cfg
