@@ -135,6 +135,9 @@ int tfb_d8_parent_ids(const uint8_t *code, int32_t ny, int32_t nx,
 #define TFB_CH_WRITE_R     (1u << 3)  /* store the R grid                     */
 #define TFB_CH_ET_INPLACE  (1u << 4)  /* zero the provider's ET grid where
                                          vol < ET*da*dt (channels_base :1625)  */
+#define TFB_CH_FLOOD       (1u << 5)  /* FLOOD_OPTION: rectangle-over-trapezoid
+                                         overbank flow (channels_base.py:1701-1862,
+                                         :2149-2185, :2393-2448); generic kernel only */
 #define TFB_CH_SRC_MET     (1u << 8)  /* P -> P_rain/P_snow split fused       */
 #define TFB_CH_SRC_SNOW    (1u << 9)  /* degree-day snowmelt fused            */
 #define TFB_CH_SRC_EVAP    (1u << 10) /* Priestley-Taylor ET fused            */
@@ -228,6 +231,13 @@ typedef struct {
                                  updated scalar block there (posted writes over
                                  PCIe), so the host reads Q_outlet etc. after a
                                  stream synchronise without issuing a copy        */
+    /* ---- FLOOD_OPTION (TFB_CH_FLOOD) ------------------------------------------ */
+    tfb_sg vol_bankfull;      /* channel volume at bankfull depth:
+                                 d_b (w + d_b tan(angle)) ds   (:1385-1387)      */
+    double *d_flood;          /* out: flood-plain water depth (may be NULL)      */
+    double *vol_flood;        /* out: water volume above bankfull (may be NULL)  */
+    double flood_manning_n;   /* 0.10 in the reference (:1367)                   */
+    double width_ratio;       /* flood-plain / channel width, 5.0 (:1368)        */
 } tfb_channels_step_args;
 
 #define TFB_NSUM 24           /* doubles per rank exchanged by the allreduce:

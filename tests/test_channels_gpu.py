@@ -329,3 +329,31 @@ def test_packed_path_vs_c_oracle(kinematic, src):
     assert abs(s.vol_R - (stored + s.vol_edge)) <= 1e-10 * abs(s.vol_R)
     assert s.n_neg_d == s.n_nan_d == s.n_inf_d == s.n_neg_u == s.n_nan_u == s.n_inf_u == 0
     assert float(eng.Q.max()) > 0
+
+
+@pytest.mark.parametrize('tag', ['kw', 'dw'])
+def test_flood_option_vs_reference_fixture(flood_gold, tag):
+    """FLOOD_OPTION (rectangle-over-trapezoid overbank flow, channels_base.py
+    :1701-1862, :2149-2185, :2393-2448) against a stand-alone REFERENCE run."""
+    g = flood_gold
+    kin = (tag == 'kw')
+    code = g['code']
+    ny, nx = code.shape
+    dx, dy, dd = o.pixel_dims(ny, 30.0, 30.0)
+    eng = _engine(code, dx, dy, dd, g['slope'], g['width'], g['angle'], g['nval'], dt=2.0,
+                  da=900.0, kinematic=kin, diag=True, outlet=(ny - 2, nx // 2), flood=True,
+                  d_bankfull=np.float64(g['d_bankfull']))
+    eng.set_input('P_rain', 150 / 3.6e6)
+    for i in range(150):
+        if i == 100:
+            eng.set_input('P_rain', 0.0)
+        eng.step(time_min=(i * 2.0) / 60.0)
+    assert eng.last_path == 'generic'
+    want = {n: g[tag + '_' + n] for n in GRIDS + SCALARS}
+    _cmp_grids(eng, want, GRIDS)
+    assert rel_err(eng.own(eng.d_flood).cpu().numpy(), g[tag + '_d_flood']) <= RTOL
+    assert rel_err(eng.own(eng.vol_flood).cpu().numpy(), g[tag + '_vol_flood']) <= RTOL
+    assert g[tag + '_d_flood'].max() > 0.1
+    if not kin:
+        assert rel_err(eng.own(eng.S_free).cpu().numpy(), g[tag + '_S_free']) <= RTOL
+    _cmp_scalars(eng, want)

@@ -25,8 +25,9 @@ What the caller sees:
     copied back into the provider's array;
   * ``CHECK_STABILITY`` raises the reference's RuntimeErrors (:3275, :3429) from
     the bad-value counters the kernel returns.
-Not handled (raise NotImplementedError): FLOOD_OPTION, ATTENUATE,
-dynamic wave.
+FLOOD_OPTION (rectangle-over-trapezoid overbank flow) is supported through the
+generic kernel.  Not handled (raise NotImplementedError): ATTENUATE, dynamic wave,
+CREATE_CHANNEL_FILES.
 """
 import os
 
@@ -108,7 +109,8 @@ _SCALAR_BLOCK = ('vol_R', 'vol_Q', 'vol_edge', 'Q_outlet', 'u_outlet', 'd_outlet
 _SRC_INPUTS = ('P_rain', 'SM', 'GW', 'MR', 'ET', 'IN')
 _DIAG = ('Rh', 'A_wet', 'P_wet', 'f', 'tau', 'u_star', 'froude')
 # attribute -> how to find the device tensor (state & diagnostics)
-_DEVICE_GRIDS = ('Q', 'Qc', 'vol', 'vol_chan', 'd', 'u', 'R', 'S_free') + _DIAG
+_DEVICE_GRIDS = ('Q', 'Qc', 'vol', 'vol_chan', 'd', 'u', 'R', 'S_free', 'd_flood', 'df',
+                 'vol_flood') + _DIAG
 
 
 class channels_component(BMI_base.BMI_component):
@@ -142,10 +144,19 @@ class channels_component(BMI_base.BMI_component):
 
     def _device_tensor(self, name):
         e = self.engine
-        if name in ('Q', 'Qc'):
+        if name in ('d_flood', 'df', 'vol_flood'):
+            if not e.flood:
+                raise AttributeError(name + ' exists only with FLOOD_OPTION')
+            return e.own(e.vol_flood if name == 'vol_flood' else e.d_flood)
+        if name == 'Q' or (name == 'Qc' and not e.flood):
             return e.Q
-        if name in ('vol', 'vol_chan'):
+        if name == 'Qc':
+            raise AttributeError('with FLOOD_OPTION only the total discharge Q is kept')
+        if name == 'vol' or (name == 'vol_chan' and not e.flood):
             return e.vol
+        if name == 'vol_chan':
+            import torch
+            return torch.minimum(e.vol, e.own(e.vol_bankfull))      # :2149
         if name in ('d', 'u'):
             return e.own(getattr(e, name))
         if name == 'R':
@@ -243,9 +254,7 @@ class channels_component(BMI_base.BMI_component):
                 setattr(self, k, self.initialize_scalar(60.0))
         self.MANNING = bool(int(self.MANNING))
         self.LAW_OF_WALL = bool(int(self.LAW_OF_WALL))
-        if self.FLOOD_OPTION not in (False, 0):
-            raise NotImplementedError('FLOOD_OPTION (overbank flow) is not part of the GPU '
-                                      'path yet (SURVEY.md 8f-1)')
+        self.FLOOD_OPTION = bool(int(self.FLOOD_OPTION))
         if self.ATTENUATE not in (False, 0):
             raise NotImplementedError('ATTENUATE (Nash reservoir runoff) is not part of the '
                                       'GPU path')
@@ -439,7 +448,9 @@ class channels_component(BMI_base.BMI_component):
             diag=bool(self.DIAGNOSTICS or self.SAVE_F_GRIDS or self.SAVE_F_PIXELS),
             write_R=bool(self.WRITE_R), outlet=(int(self.outlet_ID[0]), int(self.outlet_ID[1])),
             rho_H2O=float(self.rho_H2O), device=self.device, row0=row0, ny_global=self.ny,
-            halo=halo, finalize=True, n_pixels_global=ny_loc * self.nx)
+            halo=halo, finalize=True, n_pixels_global=ny_loc * self.nx,
+            flood=self.FLOOD_OPTION,
+            d_bankfull=self.d_bankfull if np.ndim(self.d_bankfull) == 2 else float(self.d_bankfull))
         if self._fused:
             self.engine.enable_fused_sources(**self._fused)
         if lay is None:
@@ -705,6 +716,10 @@ class channels_component(BMI_base.BMI_component):
         self.sync_scalars()
         self.update_total_channel_water_volume()
         self.update_mins_and_maxes()
+        if self.FLOOD_OPTION and self.layout is None:
+            # update_total_channel/flood_water_volume :3083-3135
+            self.vol_chan_sum.fill(float(self._device_tensor('vol_chan').sum()))
+            self.vol_flood_sum.fill(float(self._device_tensor('vol_flood').sum()))
         if not self.SILENT:
             self.print_final_report()
         self.close_output_files()

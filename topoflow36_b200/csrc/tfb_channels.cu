@@ -76,6 +76,7 @@ struct Cell {
     double ds, da, width, tan_a, cos_a;
     double vol, Q;
     double I, h_swe;          // fused-source state in (read by the caller)
+    double vb;                // bankfull channel volume (FLOOD_OPTION)
 };
 struct SrcState {             // fused-source state out (written by the caller)
     double I, h_swe;
@@ -188,6 +189,7 @@ __device__ __forceinline__ void load_cell_scalar(const tfb_channels_step_args &a
     g.Q = __ldg(a.Q_in + i);
     g.I = (a.flags & TFB_CH_SRC_INFIL) ? __ldg(a.I + i) : 0.0;
     g.h_swe = (a.flags & TFB_CH_SRC_SNOW) ? __ldg(a.h_swe + i) : 0.0;
+    g.vb = (a.flags & TFB_CH_FLOOD) ? sg_at(a.vol_bankfull, i) : 0.0;
 }
 
 // new volume (before the noflow zeroing) and new depth of a cell ---------------
@@ -195,8 +197,8 @@ template <bool SRC, bool UR, bool COMMIT>
 __device__ __forceinline__ void vol_depth(const tfb_channels_step_args &a, const ChConsts &kc,
                                           int64_t i, const Cell &g,
                                           const double *__restrict__ Qc, double &vol_new,
-                                          double &d_new, double &R_out, SrcState &ns,
-                                          Acc *acc) {
+                                          double &d_new, double &df_new, double &R_out,
+                                          SrcState &ns, Acc *acc) {
     const double dt = a.dt;
     double v;
     if (UR) {
@@ -231,6 +233,14 @@ __device__ __forceinline__ void vol_depth(const tfb_channels_step_args &a, const
     v -= (g.Q * dt);                                                 // :2138
     v = np_max(v, 0.0);                                              // :2145
     vol_new = v;
+    df_new = 0.0;
+    if (a.flags & TFB_CH_FLOOD) {
+        // update_channel_volume :2149, update_flood_volume :2158-2185,
+        // update_flood_depth :2393-2448: the depth below comes from min(vol, bankfull)
+        const double vf = np_max(v - g.vb, 0.0);
+        v = np_min(v, g.vb);
+        df_new = np_max(vf / ((a.width_ratio * g.width) * g.ds), 0.0);
+    }
     // update_channel_depth :2299-2330, :2379  (angle == 0  <=>  tan(angle) == 0)
     double d;
     if (g.tan_a == 0.0) {
@@ -257,13 +267,14 @@ __device__ __forceinline__ void load_children(const double *__restrict__ Qp, int
 struct CellOut {
     double vol, d, u, Qn;
     double Rh, A_wet, P_wet, f, tau, u_star, froude, S, R;
+    double df, vf;            // FLOOD_OPTION: flood depth and volume above bankfull
 };
 
 // everything after the depth: Rh, slope, velocity, diagnostics, bookkeeping
 template <bool DW, bool LOW, bool DIAG, bool SRC, bool UR>
 __device__ __forceinline__ void finish_cell(const tfb_channels_step_args &a,
                                             const ChConsts &k, int r, int c, int64_t i,
-                                            const Cell &g, double v, double d,
+                                            const Cell &g, double v, double d, double df,
                                             double slope_in, double rough, Acc &acc,
                                             CellOut &o) {
     const bool noflow = (g.code == 0);
@@ -289,12 +300,14 @@ __device__ __forceinline__ void finish_cell(const tfb_channels_step_args &a,
             const int64_t ip = (int64_t)pr * a.nx + pc;
             Cell gp;
             load_cell_scalar(a, pr, ip, gp);
-            double Qc[8], vp, Rp;
+            double Qc[8], vp, Rp, df_par;
             SrcState nsp;
             load_children(a.Q_in + ip, a.nx, gp.cmask, Qc);
-            vol_depth<SRC, UR, false>(a, k, ip, gp, Qc, vp, d_par, Rp, nsp, nullptr);
+            vol_depth<SRC, UR, false>(a, k, ip, gp, Qc, vp, d_par, df_par, Rp, nsp, nullptr);
+            if (a.flags & TFB_CH_FLOOD) d_par = d_par + df_par;      // total depth :2593-2596
         }
-        S = slope_in + ((d - d_par) / g.ds);
+        const double d_tot = (a.flags & TFB_CH_FLOOD) ? (d + df) : d;
+        S = slope_in + ((d_tot - d_par) / g.ds);
         sqrtS = sqrt(fabs(S));
     } else {
         sqrtS = (DIAG || LOW) ? (LOW ? 0.0 : sqrt(fabs(slope_in))) : slope_in;
@@ -350,6 +363,20 @@ __device__ __forceinline__ void finish_cell(const tfb_channels_step_args &a,
     if (u > 0.0) acc.dt_min = fminf(acc.dt_min, __fdividef((float)g.ds, (float)u));
     o.vol = v; o.d = d; o.u = u;
     o.Qn = u * A_wet;                                               // next :1697
+    o.df = 0.0; o.vf = 0.0;
+    if (a.flags & TFB_CH_FLOOD) {
+        // update_flood_discharge :1701-1750 and update_discharge :1791-1862, evaluated
+        // here for the NEXT step: d_flood after the noflow zeroing (:2968-2970), S_bed
+        // (kinematic) or this step's S_free (diffusive)
+        const double dfz = noflow ? 0.0 : df;
+        const double cbf = cbrt(dfz);
+        const double sq = DW ? sqrt(fabs(S)) : ((DIAG || LOW) ? sqrt(fabs(slope_in)) : slope_in);
+        const double uf = ((cbf * cbf) * sq) / a.flood_manning_n;
+        const double Af = (a.width_ratio * g.width) * dfz;
+        o.Qn = o.Qn + (uf * Af);
+        o.df = dfz;
+        o.vf = noflow ? 0.0 : np_max(v - g.vb, 0.0);
+    }
     (void)i;
 }
 
@@ -438,6 +465,9 @@ channels_step_kernel(const tfb_channels_step_args a, const ChConsts k) {
             const bool f_snow = SRC && (a.flags & TFB_CH_SRC_SNOW);
             if (f_infil) Iin = ldv<VEC>(a.I, i);
             if (f_snow) hin = ldv<VEC>(a.h_swe, i);
+            const bool f_flood = (a.flags & TFB_CH_FLOOD) != 0u;
+            V<VEC> vbk, o_df, o_vf;
+            if (f_flood) vbk = ldsg<VEC>(a.vol_bankfull, i);
             const float dxr = __ldg(a.dx + r), dyr = __ldg(a.dy + r), ddr = __ldg(a.dd + r);
             const double dar = (GP || !a.da.ptr) ? a.da.val : __ldg(a.da.ptr + r);
             // ---- children's discharge: predicated loads --------------------
@@ -458,13 +488,15 @@ channels_step_kernel(const tfb_channels_step_args a, const ChConsts k) {
                 g.vol = vol.v[j]; g.Q = Qo.v[j];
                 g.I = f_infil ? Iin.v[j] : 0.0;
                 g.h_swe = f_snow ? hin.v[j] : 0.0;
-                double v, d, R;
+                g.vb = f_flood ? vbk.v[j] : 0.0;
+                double v, d, df, R;
                 SrcState ns;
-                vol_depth<SRC, UR, true>(a, k, i + j, g, Qc[j], v, d, R, ns, &acc);
+                vol_depth<SRC, UR, true>(a, k, i + j, g, Qc[j], v, d, df, R, ns, &acc);
                 if (SRC) { Iout.v[j] = ns.I; hout.v[j] = ns.h_swe; }
                 CellOut o;
-                finish_cell<DW, LOW, DIAG, SRC, UR>(a, k, r, c0 + j, i + j, g, v, d, sl.v[j],
+                finish_cell<DW, LOW, DIAG, SRC, UR>(a, k, r, c0 + j, i + j, g, v, d, df, sl.v[j],
                                                 rg.v[j], acc, o);
+                o_df.v[j] = o.df; o_vf.v[j] = o.vf;
                 o_vol.v[j] = o.vol; o_d.v[j] = o.d; o_u.v[j] = o.u; o_Q.v[j] = o.Qn;
                 if (DIAG) {
                     o_Rh.v[j] = o.Rh; o_A.v[j] = o.A_wet; o_P.v[j] = o.P_wet; o_f.v[j] = o.f;
@@ -482,6 +514,10 @@ channels_step_kernel(const tfb_channels_step_args a, const ChConsts k) {
                     for (int j = 0; j < VEC; ++j) hs.v[j] = hout.v[j] * (a.rho_H2O / a.rho_snow);
                     stv<VEC>(a.h_snow, i, hs);
                 }
+            }
+            if (f_flood) {
+                if (a.d_flood) stv<VEC>(a.d_flood, i, o_df);
+                if (a.vol_flood) stv<VEC>(a.vol_flood, i, o_vf);
             }
             stv<VEC>(a.vol_out, i, o_vol);
             stv<VEC>(a.d, i, o_d);
@@ -685,6 +721,8 @@ extern "C" int tfb_channels_step(const tfb_channels_step_args *ap, void *stream)
         if (a.flags & TFB_CH_SRC_INFIL) TFB_ARG_CHECK(a.I != a.I_out);
     }
     if (src) TFB_ARG_CHECK(a.is_R_grid == 1);
+    if (a.flags & TFB_CH_FLOOD)
+        TFB_ARG_CHECK(a.flood_manning_n > 0.0 && a.width_ratio > 0.0);
     ChConsts k;
     k.g = 9.81; k.aval = 0.476; k.kappa = 0.408;
     k.law_const = sqrt(k.g) / k.kappa;                 // channels_base :531
@@ -698,7 +736,8 @@ extern "C" int tfb_channels_step(const tfb_channels_step_args *ap, void *stream)
                       al16(a.Rh) && al16(a.A_wet) && al16(a.P_wet) && al16(a.f) &&
                       al16(a.tau) && al16(a.u_star) && al16(a.froude) && al16(a.S_free) &&
                       al16(a.R) && al16(a.I) && al16(a.I_out) && al16(a.h_swe) && al16(a.h_swe_out) &&
-                      al16(a.h_snow) && ((((uintptr_t)a.geo) & 3u) == 0);
+                      al16(a.h_snow) && al16(a.vol_bankfull.ptr) && al16(a.d_flood) && al16(a.vol_flood) &&
+                      ((((uintptr_t)a.geo) & 3u) == 0);
     return vec2 ? dispatch<2>(a, k, st) : dispatch<1>(a, k, st);
 }
 

@@ -22,6 +22,7 @@ CH_LAW_OF_WALL = 1 << 1
 CH_DIAG = 1 << 2
 CH_WRITE_R = 1 << 3
 CH_ET_INPLACE = 1 << 4
+CH_FLOOD = 1 << 5
 CH_SRC_MET = 1 << 8
 CH_SRC_SNOW = 1 << 9
 CH_SRC_EVAP = 1 << 10
@@ -81,6 +82,8 @@ class ChannelsStepArgs(C.Structure):
         ('scalars', vp), ('partials', vp), ('ticket', vp),
         ('finalize', C.c_int32),
         ('scalars_mirror', vp),
+        ('vol_bankfull', SG), ('d_flood', vp), ('vol_flood', vp),
+        ('flood_manning_n', C.c_double), ('width_ratio', C.c_double),
     ]
 
 

@@ -34,7 +34,8 @@ class ChannelsEngine(object):
                  d0=0.0, kinematic=True, manning=True, diag=False,
                  write_R=False, outlet=(0, 0), rho_H2O=1000.0, row0=0,
                  ny_global=None, halo=0, device=None, finalize=True,
-                 n_pixels_global=None, packed=True):
+                 n_pixels_global=None, packed=True, flood=False, d_bankfull=10.0,
+                 flood_manning_n=0.10, width_ratio=5.0):
         if not torch.cuda.is_available():
             raise L.TfbError('ChannelsEngine needs a CUDA device (no CPU path)')
         self.lib = L.load()
@@ -65,6 +66,9 @@ class ChannelsEngine(object):
             flags |= L.CH_DIAG
         if write_R:
             flags |= L.CH_WRITE_R
+        self.flood = bool(flood)
+        if self.flood:
+            flags |= L.CH_FLOOD
         self.flags = flags
         # ---- static inputs --------------------------------------------------
         self.code = self._grid(code, torch.uint8)
@@ -151,6 +155,9 @@ class ChannelsEngine(object):
         a.scalars_mirror = self._scalars_host.data_ptr()
         self.set_initial_depth(d0)
         self.n_steps = 0
+        self.d_flood = self.vol_flood = self.vol_bankfull = None
+        if self.flood:
+            self._init_flood(d_bankfull, flood_manning_n, width_ratio)
         self.packed = None
         self._scalars_dirty = False
         self.mid_step_hook = None
@@ -160,6 +167,35 @@ class ChannelsEngine(object):
         if self.use_packed:
             self._try_pack()
 
+    # ------------------------------------------------------------ flood option
+    def _ds64(self):
+        """Flow length ds = sinu * ds_d8 (float64 values of the float32 D8 grid)."""
+        a = self.args
+        ds32 = torch.empty((self.ny + 2 * self.halo, self.nx), dtype=torch.float32,
+                           device=self.device)
+        L.check(self.lib.tfb_d8_ds_dw(self.code.data_ptr(), self.dx.data_ptr(),
+                                      self.dy.data_ptr(), self.dd.data_ptr(),
+                                      self.ny + 2 * self.halo, self.nx,
+                                      ds32.data_ptr(), None, L.stream_ptr()), 'tfb_d8_ds_dw')
+        sn = self.sinu_grid if self.sinu_grid is not None else a.sinu.val
+        return sn * ds32.double()
+
+    def _init_flood(self, d_bankfull, flood_manning_n, width_ratio):
+        """FLOOD_OPTION state (channels_base.py:1346-1388): bankfull channel volume
+        d_b (w + d_b tan(angle)) ds, flood depth and flood volume grids."""
+        a = self.args
+        g = lambda name: (getattr(self, name + '_grid') if getattr(self, name + '_grid') is not None
+                          else getattr(a, name).val)
+        db = (self._grid(d_bankfull, torch.float64) if _is_grid(d_bankfull) else float(d_bankfull))
+        L3 = db * g('tan_angle')
+        Ac = db * (g('width') + L3)
+        vb = Ac * self._ds64()
+        self.vol_bankfull = vb.contiguous()
+        a.vol_bankfull = L.SG(self._p(self.vol_bankfull), 0.0)
+        self.d_flood, self.vol_flood = self._zeros(torch.float64), self._zeros(torch.float64)
+        a.d_flood, a.vol_flood = self._p(self.d_flood), self._p(self.vol_flood)
+        a.flood_manning_n, a.width_ratio = float(flood_manning_n), float(width_ratio)
+
     # ------------------------------------------------------------ packed path
     def _try_pack(self):
         """Build the compact static inputs of tfb_channels_step_packed when the
@@ -167,7 +203,7 @@ class ChannelsEngine(object):
         scalar sinuosity / pixel area, float32-exact widths, <= 256 distinct
         bank angles).  Everything is lossless; otherwise the generic kernel runs."""
         a = self.args
-        if (not self.manning) or self.diag or (self.flags & L.CH_WRITE_R):
+        if (not self.manning) or self.diag or self.flood or (self.flags & L.CH_WRITE_R):
             return
         if self.nx % 4 or self.sinu_grid is not None or self._da_is_grid:
             return
