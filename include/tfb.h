@@ -382,6 +382,28 @@ int tfb_evap_priestley_taylor(tfb_sg T_air, tfb_sg T_surf, tfb_sg Qn_SW,
                               double *ET, double *sums1, double *partials,
                               uint32_t *ticket, void *stream);
 
+/* Meteorology energy chain (met_base.update() :790-809 with PRECIP_ONLY = No):
+ * vapour pressures, dew point, surface temperature, bulk Richardson number and
+ * aerodynamic conductances, sensible / latent heat, precipitable water,
+ * clear-sky shortwave on a sloping cell (solar_funcs.Clear_Sky_Radiation :870 and
+ * everything below it), air emissivity, net longwave, net energy flux.  Every
+ * input is scalar-or-grid; outputs are optional DEVICE grids.  julian_day (and
+ * TSN_offset, the clock time relative to true solar noon [h]) are formed on the
+ * host from the model date (met_base.update_julian_day :1938-1993).  Albedo is
+ * an input: the 'aging' method's 3-day snowfall ring buffer is not on this path. */
+typedef struct {
+    int32_t ny, nx;
+    int32_t satterlund;       /* saturation vapour pressure method (else Brutsaert) */
+    tfb_sg T_air, RH, uz, z, z0_air, h_snow, h_ice, p0, albedo, em_surf;
+    tfb_sg lat_deg, alpha, beta, TSN_offset, cloud_factor, canopy_factor, Qa, Qc;
+    double julian_day, dust_atten;
+    double *e_sat_air, *e_air, *T_dew, *T_surf, *e_sat_surf, *Ri, *Dn, *Dh, *Qh, *W_p,
+           *e_surf, *Qe, *Qn_SW, *em_air, *Qn_LW, *Q_sum;
+} tfb_met_energy_args;
+
+int64_t tfb_sizeof_met_energy_args(void);
+int tfb_met_energy(const tfb_met_energy_args *a, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

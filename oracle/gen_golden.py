@@ -338,6 +338,84 @@ def gen_sources():
     np.savez_compressed(os.path.join(GOLD, 'sources.npz'), **out)
 
 
+def gen_met_energy():
+    """Pin the meteorology energy chain (met_base.update :790-809, PRECIP_ONLY = No)
+    by calling the reference METHODS, in the reference's order, on a bare component
+    whose attributes are set by hand.  Albedo is held fixed (albedo_type that skips
+    the 'aging' branch); julian_day / TSN_offset come from the reference's own
+    solar functions for 1967-06-20 14:30 local time."""
+    from topoflow.components import met_base, solar_funcs as solar
+    rng = np.random.default_rng(17)
+    ny, nx = 33, 47
+    g = lambda lo, hi: lo + (hi - lo) * rng.random((ny, nx))
+    out = {}
+    for case, hour in (('day', 14.5), ('dusk', 19.6), ('night', 2.0)):
+        m = met_base.met_component()
+        m.DEBUG = False
+        m.set_constants()
+        m.SATTERLUND = False
+        m.T_air, m.T_surf = g(-6, 28), g(-6, 30)
+        m.RH = g(0.2, 0.98)
+        m.uz = g(0.5, 9.0)
+        m.z, m.z0_air = z(10.0), g(0.005, 0.04)
+        m.h_snow = np.where(rng.random((ny, nx)) < 0.3, g(0, 0.6), 0.0)
+        m.h_ice = np.where(rng.random((ny, nx)) < 0.1, 0.2, 0.0)
+        m.p0 = g(880, 1020)
+        m.albedo, m.albedo_type = g(0.1, 0.8), 'Grid_Sequence'
+        m.T_surf_type = 'Grid'
+        m.em_surf = g(0.9, 0.99)
+        m.dust_atten, m.cloud_factor, m.canopy_factor = z(0.08), g(0, 1), g(0, 0.7)
+        m.lat_deg = g(41.0, 41.6)
+        m.lon_deg = g(-95.8, -95.2)
+        m.alpha = g(0, 2 * np.pi)            # aspect [rad]
+        m.beta = g(0, 0.6)                   # slope angle [rad]
+        m.GMT_offset = np.int16(-6)
+        m.Qn_SW, m.Qn_LW = np.zeros((ny, nx)), np.zeros((ny, nx))
+        m.Q_sum = np.zeros((ny, nx))
+        m.Qa = m.Qc = z(0)
+        m.julian_day = solar.Julian_Day(6, 20, hour_num=hour, year=1967)
+        dec_part = m.julian_day - np.int16(m.julian_day)
+        clock_hour = dec_part * m.hours_per_day
+        solar_noon = solar.True_Solar_Noon(m.julian_day, m.lon_deg, m.GMT_offset,
+                                           DST_offset=None, year=1967)
+        m.TSN_offset = (clock_hour - solar_noon)
+        # the component's own date arithmetic (update_julian_day :1938-1993), kept
+        # separately: it drops the minutes of the hour
+        m.start_datetime, m.time_min = '1967-06-20 00:00:00', np.float64(hour * 60.0)
+        jd_keep, tsn_keep = m.julian_day, m.TSN_offset
+        m.update_julian_day()
+        out[case + '_ujd_julian_day'] = np.float64(m.julian_day)
+        out[case + '_ujd_TSN_offset'] = np.array(m.TSN_offset, dtype='float64')
+        m.julian_day, m.TSN_offset = jd_keep, tsn_keep
+        for k in ('T_air', 'RH', 'uz', 'z0_air', 'h_snow', 'h_ice', 'p0', 'albedo', 'em_surf',
+                  'cloud_factor', 'canopy_factor', 'lat_deg', 'lon_deg', 'alpha', 'beta',
+                  'TSN_offset'):
+            out[case + '_in_' + k] = np.array(getattr(m, k), dtype='float64')
+        out[case + '_in_julian_day'] = np.float64(m.julian_day)
+        out[case + '_in_hour'] = np.float64(hour)
+        out['current_year'] = np.int64(solar.Current_Year())
+        m.update_saturation_vapor_pressure(MBAR=True)
+        m.update_vapor_pressure()
+        m.update_dew_point()
+        m.update_T_surf()
+        m.update_saturation_vapor_pressure(MBAR=True, SURFACE=True)
+        m.update_bulk_richardson_number()
+        m.update_bulk_aero_conductance()
+        m.update_sensible_heat_flux()
+        m.update_precipitable_water_content()
+        m.update_vapor_pressure(SURFACE=True)
+        m.update_latent_heat_flux()
+        m.update_albedo(method='aging')
+        m.update_net_shortwave_radiation()
+        m.update_em_air()
+        m.update_net_longwave_radiation()
+        m.update_net_energy_flux()
+        for k in ('e_sat_air', 'e_air', 'T_dew', 'T_surf', 'e_sat_surf', 'Ri', 'Dn', 'Dh', 'Qh',
+                  'W_p', 'e_surf', 'Qe', 'Qn_SW', 'em_air', 'Qn_LW', 'Q_sum'):
+            out[case + '_' + k] = np.array(getattr(m, k), dtype='float64')
+    np.savez_compressed(os.path.join(GOLD, 'met_energy.npz'), **out)
+
+
 def main():
     rh.import_reference()
     os.makedirs(GOLD, exist_ok=True)
@@ -349,6 +427,7 @@ def main():
         gen_flood(work)
         gen_d8(work)
         gen_sources()
+        gen_met_energy()
         with open(os.path.join(GOLD, 'meta.json'), 'w') as fh:
             json.dump(meta, fh, indent=1, sort_keys=True)
     finally:

@@ -619,3 +619,165 @@ def priestley_taylor_step(T_air, T_surf, Qn_SW, Qn_LW, alpha, K_soil, soil_x,
     Qet = alpha * (f64(0.406) + (f64(0.011) * T_air)) * (Q_net + Qc)
     ET = (Qet / f64(2.5E+9))
     return np.maximum(ET, f64(0))
+
+
+# ---------------------------------------------------------------------------
+# Meteorology energy chain (components/met_base.py update() :790-809 with
+# PRECIP_ONLY = No) and the clear-sky radiation model it calls
+# (components/solar_funcs.py).  Point-wise; every function cites its source.
+# ---------------------------------------------------------------------------
+I_SC = np.float64(1361.5)                                   # solar_funcs.py:133
+OMEGA_H = (np.float64(360) / np.float64(24)) * (np.pi / np.float64(180))   # :236-246
+
+
+def solar_day_terms(julian_day):
+    """Day angle, declination, eccentricity correction (solar_funcs.py:147-234)."""
+    f = np.float64
+    G = (2 * np.pi) * julian_day / f(365)
+    E0 = f(1.000110) + (f(0.034221) * np.cos(G)) + (f(0.001280) * np.sin(G)) + \
+        (f(0.000719) * np.cos(f(2) * G)) + (f(0.000077) * np.sin(f(2) * G))
+    delta = f(0.006918) - (f(0.399912) * np.cos(G)) + (f(0.070257) * np.sin(G)) - \
+        (f(0.006758) * np.cos(f(2) * G)) + (f(0.000907) * np.sin(f(2) * G)) - \
+        (f(0.002697) * np.cos(f(3) * G)) + (f(0.001480) * np.sin(f(3) * G))
+    return G, delta, E0
+
+
+def _zenith(lat_deg, delta, th):                             # solar_funcs.py:248-269
+    lat_rad = lat_deg * (np.pi / np.float64(180))
+    term1 = np.sin(lat_rad) * np.sin(delta)
+    term2 = np.cos(lat_rad) * np.cos(delta) * np.cos(OMEGA_H * th)
+    return np.arccos(term1 + term2)
+
+
+def _optical_air_mass(lat_deg, delta, th):                   # :477-551
+    a, b, c = 0.50572, 6.07995, 1.6364
+    Z_deg = _zenith(lat_deg, delta, th) * (180 / np.pi)
+    gamma = np.maximum(90.0 - Z_deg, 0.0)
+    term1 = np.sin(gamma * (np.pi / 180))
+    term2 = a / (gamma + b) ** c
+    return np.float64(1) / (term1 + term2)
+
+
+def _et_flux(lat_deg, delta, E0, th):                        # :354-411
+    lat_rad = lat_deg * (np.pi / np.float64(180))
+    term1 = np.cos(delta) * np.cos(lat_rad) * np.cos(OMEGA_H * th)
+    term2 = np.sin(delta) * np.sin(lat_rad)
+    return np.maximum(I_SC * E0 * (term1 + term2), 0.0)
+
+
+def _lon_offset(lat_deg, alpha, beta):                       # :701-721
+    lat_rad = lat_deg * (np.pi / np.float64(180))
+    term1 = np.sin(beta) * np.sin(alpha)
+    term2 = np.cos(beta) * np.cos(lat_rad)
+    term3 = np.sin(beta) * np.sin(lat_rad) * np.cos(alpha)
+    return np.arctan(term1 / (term2 - term3))
+
+
+def _eq_lat(lat_deg, alpha, beta):                           # :723-751 (radians)
+    lat_rad = lat_deg * (np.pi / np.float64(180))
+    term1 = np.sin(beta) * np.cos(alpha) * np.cos(lat_rad)
+    term2 = np.cos(beta) * np.sin(lat_rad)
+    return np.arcsin(term1 + term2)
+
+
+def _sun_offset(lat_deg, delta, sign):                       # :286-340
+    lat_rad = lat_deg * (np.pi / np.float64(180))
+    arg = -np.float64(1) * np.tan(lat_rad) * np.tan(delta)
+    arg = np.minimum(np.maximum(-1, arg), 1)
+    return sign * np.arccos(arg) / OMEGA_H
+
+
+def clear_sky_radiation(lat_deg, julian_day, W_p, th, alpha, beta, albedo, dust):
+    """solar_funcs.Clear_Sky_Radiation :870-942 and everything below it."""
+    f = np.float64
+    G, delta, E0 = solar_day_terms(julian_day)
+    M_opt = _optical_air_mass(lat_deg, delta, th)
+    a_sa = -f(0.1240) - (f(0.0207) * W_p)                     # :567-594
+    b_sa = -f(0.0682) - (f(0.0248) * W_p)
+    tau = np.minimum(np.maximum(np.exp(a_sa + (b_sa * M_opt)) - dust, 0), 1)
+    lat_eq = _eq_lat(lat_deg, alpha, beta)                    # :822-868
+    dlon = _lon_offset(lat_deg, alpha, beta)
+    term1 = np.cos(delta) * np.cos(lat_eq)
+    term2 = np.cos((OMEGA_H * th) + dlon)
+    term3 = np.sin(lat_eq) * np.sin(delta)
+    K_ET_slope = np.maximum(I_SC * E0 * ((term1 * term2) + term3), 0)
+    a_s = -f(0.0363) - (f(0.0084) * W_p)                      # :619-636
+    b_s = -f(0.0572) - (f(0.0173) * W_p)
+    gam_s = (1 - np.exp(a_s + (b_s * M_opt))) + dust
+    K_ET = _et_flux(lat_deg, delta, E0, th)
+    K_dif = f(0.5) * gam_s * K_ET                             # :638-651
+    K_global = (tau * K_ET) + K_dif                           # :653-669
+    K_bs = f(0.5) * gam_s * albedo * K_global                 # :671-699
+    K_cs = (tau * K_ET_slope) + K_dif + K_bs
+    eq_lat_deg = lat_eq * (f(180) / np.pi)
+    t_noon = -f(1) * dlon / OMEGA_H                           # :753-761
+    T_sr = np.maximum(_sun_offset(eq_lat_deg, delta, -f(1)) + t_noon,
+                      _sun_offset(lat_deg, delta, -f(1)))     # :763-786
+    T_ss = np.minimum(_sun_offset(eq_lat_deg, delta, f(1)) + t_noon,
+                      _sun_offset(lat_deg, delta, f(1)))      # :788-811
+    dark = np.logical_or((th <= T_sr), (th >= T_ss))
+    K_cs = np.where(dark, f(0), K_cs)
+    return K_cs
+
+
+def met_energy_chain(T_air, RH, uz, z, z0_air, h_snow, h_ice, p0, albedo, em_surf, lat_deg,
+                     alpha, beta, julian_day, TSN_offset, dust_atten=0.08, cloud_factor=0.0,
+                     canopy_factor=0.0, Qa=0.0, Qc=0.0, satterlund=False):
+    """met_base.update() :790-809 in its own order (albedo is an input: the 'aging'
+    method's 3-day snowfall ring buffer is not part of this path).  Returns a dict."""
+    f = np.float64
+    g, kappa, rho_air, Cp_air, Lv = f(9.81), f(0.408), f(1.2614), f(1005.7), f(2500000)
+    sigma, C_to_K = f(5.67E-8), f(273.15)
+
+    def e_sat_mbar(T):                                        # :1657-1741
+        if not satterlund:
+            term1 = (f(17.3) * T) / (T + f(237.3))
+            e = f(0.611) * np.exp(term1)
+        else:
+            term1 = f(2353) / (T + f(273.15))
+            e = f(10) ** (f(11.4) - term1)
+            e = (e / f(1000))
+        return e * f(10)
+    o = {}
+    o['e_sat_air'] = e_sat_mbar(T_air)
+    o['e_air'] = (RH * o['e_sat_air'])                        # :1743-1788
+    log_term = np.log(o['e_air'] / 6.1121)                    # :1790-1835
+    o['T_dew'] = 257.14 * log_term / (18.678 - log_term)
+    o['T_surf'] = np.where(((h_snow > 0) | (h_ice > 0)), np.minimum(o['T_dew'], f(0)),
+                           o['T_dew'])                        # :1837-1853
+    T_surf = o['T_surf']
+    o['e_sat_surf'] = e_sat_mbar(T_surf)
+    top = g * z * (T_air - T_surf)                            # :1448-1475
+    bot = (uz) ** 2.0 * (T_air + f(273.15))
+    o['Ri'] = (top / bot)
+    arg = kappa / np.log((z - h_snow) / z0_air)               # :1477-1625
+    Dn = uz * (arg) ** 2.0
+    Dn = Dn + np.zeros(np.shape(o['Ri']))
+    Ri = o['Ri']
+    with np.errstate(all='ignore'):
+        Dh = np.where(Ri > 0, Dn / (f(1) + (f(10) * Ri)), Dn * (f(1) - (f(10) * Ri)))
+    o['Dn'], o['Dh'] = Dn, Dh
+    o['Qh'] = (rho_air * Cp_air) * Dh * (T_air - T_surf)      # :1627-1655
+    o['W_p'] = f(1.12) * np.exp(f(0.0614 * o['T_dew']))       # :1855-1873
+    o['e_surf'] = (RH * o['e_sat_surf'])
+    factor = (rho_air * Lv * Dh)                              # :1875-1936
+    o['Qe'] = factor * (o['e_air'] - o['e_surf']) * (f(0.622) / p0)
+    K_cs = clear_sky_radiation(lat_deg, julian_day, o['W_p'], TSN_offset, alpha, beta, albedo,
+                               dust_atten)
+    o['Qn_SW'] = K_cs * (1 - albedo)                          # :2048-2088
+    T_air_K = T_air + C_to_K                                  # :2090-2161
+    if not satterlund:
+        e_air_kPa = o['e_air'] / f(10)
+        term1 = (1.0 - canopy_factor) * 1.72 * (e_air_kPa / T_air_K) ** (f(1) / 7)
+        term2 = (1.0 + (0.22 * cloud_factor ** 2.0))
+        o['em_air'] = (term1 * term2) + canopy_factor
+    else:
+        eterm = np.exp(-1 * (o['e_air']) ** (T_air_K / 2016))
+        o['em_air'] = 1.08 * (1.0 - eterm)
+    T_surf_K = T_surf + C_to_K                                # :2163-2224
+    LW_in = o['em_air'] * sigma * (T_air_K) ** 4.0
+    LW_out = em_surf * sigma * (T_surf_K) ** 4.0
+    LW_out = LW_out + ((1.0 - em_surf) * LW_in)
+    o['Qn_LW'] = (LW_in - LW_out)
+    o['Q_sum'] = o['Qn_SW'] + o['Qn_LW'] + o['Qh'] + o['Qe'] + Qa + Qc   # :2305-2306
+    return o

@@ -57,3 +57,8 @@ def rel_err(a, b):
 @pytest.fixture(scope='session')
 def flood_gold():
     return load_golden('flood_channels.npz')
+
+
+@pytest.fixture(scope='session')
+def met_gold():
+    return load_golden('met_energy.npz')

@@ -164,3 +164,34 @@ def test_flood_option_bit_exact(flood_gold, tag):
         assert np.array_equal(getattr(ch, n), g[tag + '_' + n], equal_nan=True), n
     for n in SCALARS:
         assert float(getattr(ch, n)) == float(g[tag + '_' + n]), n
+
+
+@pytest.mark.parametrize('case', ['day', 'dusk', 'night'])
+def test_met_energy_chain_bit_exact(met_gold, case):
+    """The numpy restatement of met_base.update()'s energy chain and of
+    solar_funcs.Clear_Sky_Radiation equals the reference's own methods bit for bit
+    (full sun, partial darkness on sloping cells, night)."""
+    g = met_gold
+    I = {k[len(case) + 4:]: g[k] for k in g if k.startswith(case + '_in_')}
+    r = o.met_energy_chain(I['T_air'], I['RH'], I['uz'], np.float64(10.0), I['z0_air'], I['h_snow'],
+                           I['h_ice'], I['p0'], I['albedo'], I['em_surf'], I['lat_deg'], I['alpha'],
+                           I['beta'], I['julian_day'], I['TSN_offset'], dust_atten=np.float64(0.08),
+                           cloud_factor=I['cloud_factor'], canopy_factor=I['canopy_factor'])
+    for k, v in r.items():
+        assert np.array_equal(v, g[case + '_' + k], equal_nan=True), k
+    if case == 'dusk':
+        sw = g['dusk_Qn_SW']
+        assert (sw == 0).any() and (sw > 0).any()
+
+
+@pytest.mark.parametrize('case', ['day', 'dusk', 'night'])
+def test_solar_host_date_arithmetic(met_gold, case):
+    """solar_host.day_and_tsn == met_base.update_julian_day (Julian day with integer
+    hour, equation of time, true solar noon) for a longitude grid."""
+    from topoflow36_b200 import solar_host as sh
+    g = met_gold
+    h = float(g[case + '_in_hour'])
+    JD, tsn = sh.day_and_tsn('1967-06-20 00:00:00', h * 60.0, g[case + '_in_lon_deg'], -6,
+                             current_year=int(g['current_year']))
+    assert JD == float(g[case + '_ujd_julian_day'])
+    assert np.array_equal(tsn, g[case + '_ujd_TSN_offset'])

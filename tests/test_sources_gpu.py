@@ -60,3 +60,27 @@ def test_met_rain_snow_split(sources_gold):
     # scalar forcing and a scalar air temperature
     m.update(2e-5, 3.0)
     assert float(m.P_rain.min()) == 2e-5 and float(m.P_snow.max()) == 0.0
+
+
+@pytest.mark.parametrize('case', ['day', 'dusk', 'night'])
+def test_met_energy_chain(met_gold, case):
+    """tfb_met_energy against the REFERENCE's met_base / solar_funcs methods.  The
+    chain is ~25 transcendental calls deep (exp, log, pow, sin, cos, tan, acos, asin,
+    atan): libdevice and numpy agree to ~1-2 ulp per call, asserted rel <= 1e-11 of
+    each field's range."""
+    from conftest import rel_err
+    from topoflow36_b200.sources import MetEnergy
+    g = met_gold
+    I = {k[len(case) + 4:]: g[k] for k in g if k.startswith(case + '_in_')}
+    ny, nx = I['T_air'].shape
+    m = MetEnergy(ny, nx, dust_atten=0.08)
+    m.update(float(I['julian_day']), z=10.0,
+             **{k: I[k] for k in ('T_air', 'RH', 'uz', 'z0_air', 'h_snow', 'h_ice', 'p0', 'albedo',
+                                  'em_surf', 'lat_deg', 'alpha', 'beta', 'TSN_offset',
+                                  'cloud_factor', 'canopy_factor')})
+    for k in ('e_sat_air', 'e_air', 'T_dew', 'T_surf', 'e_sat_surf', 'Ri', 'Dn', 'Dh', 'Qh', 'W_p',
+              'e_surf', 'Qe', 'Qn_SW', 'em_air', 'Qn_LW', 'Q_sum'):
+        e = rel_err(getattr(m, k).cpu().numpy(), g[case + '_' + k])
+        assert e <= 1e-11, '%s rel err %.3e' % (k, e)
+    dark_ref = (g[case + '_Qn_SW'] == 0)
+    assert np.array_equal(m.Qn_SW.cpu().numpy() == 0, dark_ref)      # same sunrise/sunset cells

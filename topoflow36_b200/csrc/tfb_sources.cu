@@ -7,6 +7,8 @@
 // block-partial -> last-block reduction for the volume integrals.
 #include "tfb_common.cuh"
 
+#include <math.h>
+
 namespace tfb {
 
 constexpr int kThreads = 256;
@@ -198,6 +200,127 @@ minmax_kernel(const double *Q, const double *u, const double *d, const double *v
     if (threadIdx.x == 0) *ticket = 0u;
 }
 
+// ---- met: energy chain (met_base.py update :790-809; solar_funcs.py) -----------
+struct MetDay { double delta, E0, sin_d, cos_d, tan_d; };
+
+constexpr double kPi = 3.141592653589793;
+constexpr double kOmegaH = (360.0 / 24.0) * (kPi / 180.0);     // solar_funcs.py:236-246
+constexpr double kIsc = 1361.5;                                // :133
+
+__device__ __forceinline__ double sun_offset(double lat_deg, double tan_d, double sign) {
+    const double lat_rad = lat_deg * (kPi / 180.0);            // :286-340
+    double arg = (-1.0 * tan(lat_rad)) * tan_d;
+    arg = np_min(np_max(-1.0, arg), 1.0);
+    return (sign * acos(arg)) / kOmegaH;
+}
+
+__global__ void __launch_bounds__(kThreads)
+met_energy_kernel(const tfb_met_energy_args a, const MetDay dy) {
+    const int64_t n = (int64_t)a.ny * a.nx;
+    const double g = 9.81, kappa = 0.408, rho_air = 1.2614, Cp_air = 1005.7, Lv = 2500000.0;
+    const double sigma = 5.67E-8, C_to_K = 273.15;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * kThreads) {
+        const double Ta = sg_at(a.T_air, i), RH = sg_at(a.RH, i), uz = sg_at(a.uz, i);
+        const double z = sg_at(a.z, i), z0 = sg_at(a.z0_air, i), hs = sg_at(a.h_snow, i);
+        const double hi = sg_at(a.h_ice, i), p0 = sg_at(a.p0, i), alb = sg_at(a.albedo, i);
+        const double ems = sg_at(a.em_surf, i), lat = sg_at(a.lat_deg, i);
+        const double al = sg_at(a.alpha, i), be = sg_at(a.beta, i), th = sg_at(a.TSN_offset, i);
+        const double Cf = sg_at(a.cloud_factor, i), Ff = sg_at(a.canopy_factor, i);
+        // saturation vapour pressure [mbar] :1657-1741
+        auto e_sat = [&](double T) {
+            double e;
+            if (!a.satterlund) {
+                const double term1 = (17.3 * T) / (T + 237.3);
+                e = 0.611 * exp(term1);
+            } else {
+                const double term1 = 2353.0 / (T + 273.15);
+                e = pow(10.0, 11.4 - term1);
+                e = e / 1000.0;
+            }
+            return e * 10.0;
+        };
+        const double esa = e_sat(Ta);
+        const double ea = RH * esa;                                  // :1743-1788
+        const double lt = log(ea / 6.1121);                          // :1790-1835
+        const double Td = (257.14 * lt) / (18.678 - lt);
+        const double Ts = (hs > 0.0 || hi > 0.0) ? np_min(Td, 0.0) : Td;   // :1837-1853
+        const double ess = e_sat(Ts);
+        const double top = (g * z) * (Ta - Ts);                      // :1448-1475
+        const double bot = (uz * uz) * (Ta + 273.15);
+        const double Ri = top / bot;
+        const double arg = kappa / log((z - hs) / z0);               // :1477-1625
+        const double Dn = uz * (arg * arg);
+        const double Dh = (Ri > 0.0) ? (Dn / (1.0 + (10.0 * Ri))) : (Dn * (1.0 - (10.0 * Ri)));
+        const double Qh = ((rho_air * Cp_air) * Dh) * (Ta - Ts);     // :1627-1655
+        const double Wp = 1.12 * exp(0.0614 * Td);                   // :1855-1873
+        const double es = RH * ess;
+        const double Qe = (((rho_air * Lv) * Dh) * (ea - es)) * (0.622 / p0);   // :1875-1936
+        // ---- clear-sky radiation on the sloping cell, solar_funcs.py:870-942 ------------
+        const double lat_rad = lat * (kPi / 180.0);
+        const double sl = sin(lat_rad), cl = cos(lat_rad);
+        const double coth = cos(kOmegaH * th);
+        const double Z = acos((sl * dy.sin_d) + ((cl * dy.cos_d) * coth));      // :248-269
+        const double gam = np_max(90.0 - (Z * (180.0 / kPi)), 0.0);            // :477-551
+        const double M_opt = 1.0 / (sin(gam * (kPi / 180.0)) + (0.50572 / pow(gam + 6.07995, 1.6364)));
+        const double a_sa = -0.1240 - (0.0207 * Wp), b_sa = -0.0682 - (0.0248 * Wp);   // :567-594
+        const double tau = np_min(np_max(exp(a_sa + (b_sa * M_opt)) - a.dust_atten, 0.0), 1.0);
+        const double sb = sin(be), cb = cos(be), sa = sin(al), ca = cos(al);
+        const double lat_eq = asin(((sb * ca) * cl) + (cb * sl));               // :723-751
+        const double dlon = atan((sb * sa) / ((cb * cl) - ((sb * sl) * ca)));   // :701-721
+        const double t1 = dy.cos_d * cos(lat_eq);                               // :822-868
+        const double t2 = cos((kOmegaH * th) + dlon);
+        const double t3 = sin(lat_eq) * dy.sin_d;
+        const double K_ETs = np_max((kIsc * dy.E0) * ((t1 * t2) + t3), 0.0);
+        const double a_s = -0.0363 - (0.0084 * Wp), b_s = -0.0572 - (0.0173 * Wp);   // :619-636
+        const double gam_s = (1.0 - exp(a_s + (b_s * M_opt))) + a.dust_atten;
+        const double K_ET = np_max((kIsc * dy.E0) * (((dy.cos_d * cl) * coth) + (dy.sin_d * sl)), 0.0);
+        const double K_dif = (0.5 * gam_s) * K_ET;                              // :638-651
+        const double K_glob = (tau * K_ET) + K_dif;                             // :653-669
+        const double K_bs = ((0.5 * gam_s) * alb) * K_glob;                     // :671-699
+        double K_cs = ((tau * K_ETs) + K_dif) + K_bs;
+        const double eq_deg = lat_eq * (180.0 / kPi);
+        const double t_noon = (-1.0 * dlon) / kOmegaH;                          // :753-761
+        const double T_sr = np_max(sun_offset(eq_deg, dy.tan_d, -1.0) + t_noon,
+                                   sun_offset(lat, dy.tan_d, -1.0));            // :763-786
+        const double T_ss = np_min(sun_offset(eq_deg, dy.tan_d, 1.0) + t_noon,
+                                   sun_offset(lat, dy.tan_d, 1.0));             // :788-811
+        if (th <= T_sr || th >= T_ss) K_cs = 0.0;
+        const double Qsw = K_cs * (1.0 - alb);                                  // met_base :2048-2088
+        // air emissivity and net longwave :2090-2224
+        const double TaK = Ta + C_to_K, TsK = Ts + C_to_K;
+        double em;
+        if (!a.satterlund) {
+            const double term1 = ((1.0 - Ff) * 1.72) * pow((ea / 10.0) / TaK, 1.0 / 7.0);
+            const double term2 = 1.0 + (0.22 * (Cf * Cf));
+            em = (term1 * term2) + Ff;
+        } else {
+            em = 1.08 * (1.0 - exp(-1.0 * pow(ea, TaK / 2016.0)));
+        }
+        const double LW_in = (em * sigma) * pow(TaK, 4.0);
+        double LW_out = (ems * sigma) * pow(TsK, 4.0);
+        LW_out = LW_out + ((1.0 - ems) * LW_in);
+        const double Qlw = LW_in - LW_out;
+        const double Qsum = ((((Qsw + Qlw) + Qh) + Qe) + sg_at(a.Qa, i)) + sg_at(a.Qc, i);   // :2305
+        if (a.e_sat_air) a.e_sat_air[i] = esa;
+        if (a.e_air) a.e_air[i] = ea;
+        if (a.T_dew) a.T_dew[i] = Td;
+        if (a.T_surf) a.T_surf[i] = Ts;
+        if (a.e_sat_surf) a.e_sat_surf[i] = ess;
+        if (a.Ri) a.Ri[i] = Ri;
+        if (a.Dn) a.Dn[i] = Dn;
+        if (a.Dh) a.Dh[i] = Dh;
+        if (a.Qh) a.Qh[i] = Qh;
+        if (a.W_p) a.W_p[i] = Wp;
+        if (a.e_surf) a.e_surf[i] = es;
+        if (a.Qe) a.Qe[i] = Qe;
+        if (a.Qn_SW) a.Qn_SW[i] = Qsw;
+        if (a.em_air) a.em_air[i] = em;
+        if (a.Qn_LW) a.Qn_LW[i] = Qlw;
+        if (a.Q_sum) a.Q_sum[i] = Qsum;
+    }
+}
+
 static int n_blocks(int64_t n) {
     int64_t want = (n + kThreads - 1) / kThreads;
     int64_t cap = (int64_t)sm_count() * 8;      // 8 resident CTAs of 256 per SM
@@ -264,6 +387,24 @@ extern "C" int tfb_evap_priestley_taylor(tfb_sg T_air, tfb_sg T_surf, tfb_sg Qn_
     priestley_taylor_kernel<<<n_blocks(n), kThreads, 0, (cudaStream_t)stream>>>(
         T_air, T_surf, Qn_SW, Qn_LW, alpha, K_soil, soil_x, T_soil_x, da, dt, n, nx, Qc, ET,
         sums1, partials, ticket);
+    TFB_CUDA_CHECK(cudaGetLastError());
+    return TFB_OK;
+}
+
+extern "C" int64_t tfb_sizeof_met_energy_args(void) { return (int64_t)sizeof(tfb_met_energy_args); }
+
+extern "C" int tfb_met_energy(const tfb_met_energy_args *ap, void *stream) {
+    TFB_ARG_CHECK(ap != nullptr && ap->ny > 0 && ap->nx > 0);
+    // day terms on the host (solar_funcs.py:147-234), shared by every cell
+    const double G = (2.0 * M_PI) * ap->julian_day / 365.0;
+    MetDay dy;
+    dy.E0 = 1.000110 + (0.034221 * cos(G)) + (0.001280 * sin(G)) + (0.000719 * cos(2.0 * G)) +
+            (0.000077 * sin(2.0 * G));
+    dy.delta = 0.006918 - (0.399912 * cos(G)) + (0.070257 * sin(G)) - (0.006758 * cos(2.0 * G)) +
+               (0.000907 * sin(2.0 * G)) - (0.002697 * cos(3.0 * G)) + (0.001480 * sin(3.0 * G));
+    dy.sin_d = sin(dy.delta); dy.cos_d = cos(dy.delta); dy.tan_d = tan(dy.delta);
+    const int64_t n = (int64_t)ap->ny * ap->nx;
+    met_energy_kernel<<<n_blocks(n), kThreads, 0, (cudaStream_t)stream>>>(*ap, dy);
     TFB_CUDA_CHECK(cudaGetLastError());
     return TFB_OK;
 }

@@ -87,6 +87,18 @@ class ChannelsStepArgs(C.Structure):
     ]
 
 
+class MetEnergyArgs(C.Structure):
+    """tfb_met_energy_args."""
+    _IN = ('T_air', 'RH', 'uz', 'z', 'z0_air', 'h_snow', 'h_ice', 'p0', 'albedo', 'em_surf',
+           'lat_deg', 'alpha', 'beta', 'TSN_offset', 'cloud_factor', 'canopy_factor', 'Qa', 'Qc')
+    _OUT = ('e_sat_air', 'e_air', 'T_dew', 'T_surf', 'e_sat_surf', 'Ri', 'Dn', 'Dh', 'Qh', 'W_p',
+            'e_surf', 'Qe', 'Qn_SW', 'em_air', 'Qn_LW', 'Q_sum')
+    _fields_ = ([('ny', C.c_int32), ('nx', C.c_int32), ('satterlund', C.c_int32)] +
+                [(n, SG) for n in _IN] +
+                [('julian_day', C.c_double), ('dust_atten', C.c_double)] +
+                [(n, vp) for n in _OUT])
+
+
 class ChannelsPacked(C.Structure):
     """tfb_channels_packed: compact static inputs of the packed fast path."""
     _fields_ = [('geo32', vp), ('width32', vp), ('coef', vp), ('angle_lut', vp),
@@ -141,6 +153,8 @@ SIGNATURES = {
                                        vp]),
     'tfb_snow_degree_day': (C.c_int, [SG, SG, SG, SG, _f64, _f64, SG, _f64,
                                       _i32, _i32, vp, vp, vp, vp, vp, vp, vp]),
+    'tfb_sizeof_met_energy_args': (_i64, []),
+    'tfb_met_energy': (C.c_int, [C.POINTER(MetEnergyArgs), vp]),
     'tfb_evap_priestley_taylor': (C.c_int, [SG, SG, SG, SG, _f64, _f64, _f64,
                                             _f64, SG, _f64, _i32, _i32, vp, vp,
                                             vp, vp, vp, vp]),
@@ -176,6 +190,8 @@ def load():
                           C.sizeof(ChannelsStepArgs)))
     if lib.tfb_sizeof_channels_scalars() != C.sizeof(ChannelsScalars):
         raise TfbError('tfb_channels_scalars layout mismatch')
+    if lib.tfb_sizeof_met_energy_args() != C.sizeof(MetEnergyArgs):
+        raise TfbError('tfb_met_energy_args layout mismatch')
     if lib.tfb_sizeof_channels_packed() != C.sizeof(ChannelsPacked):
         raise TfbError('tfb_channels_packed layout mismatch')
     _lib = lib

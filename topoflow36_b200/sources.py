@@ -132,3 +132,29 @@ class PriestleyTaylor(_Base):
             self.sums.data_ptr(), *self._tail()), 'tfb_evap_priestley_taylor')
 
     vol_ET = property(lambda s: float(s.sums[0]))
+
+
+class MetEnergy(_Base):
+    """The meteorology energy chain of met_base.update() (:790-809, PRECIP_ONLY = No)
+    in one point-wise kernel: e_sat/e (air and surface), T_dew, T_surf, Ri, Dn, Dh, Qh,
+    W_p, Qe, clear-sky Qn_SW on sloping cells (solar_funcs.Clear_Sky_Radiation), em_air,
+    Qn_LW, Q_sum.  Inputs are scalars or (ny, nx) grids; `julian_day` and `TSN_offset`
+    come from solar_host.julian_day / tsn_offset (the date arithmetic stays on the
+    host).  Albedo is an input (the reference's 'aging' ring buffer is not here)."""
+
+    def __init__(self, ny, nx, satterlund=False, dust_atten=0.08, **kw):
+        _Base.__init__(self, ny, nx, 1.0, **kw)
+        self.satterlund, self.dust_atten = bool(satterlund), float(dust_atten)
+        for n in L.MetEnergyArgs._OUT:
+            setattr(self, n, self._zeros())
+
+    def update(self, julian_day, **inputs):
+        a = L.MetEnergyArgs()
+        a.ny, a.nx, a.satterlund = self.ny, self.nx, int(self.satterlund)
+        a.julian_day, a.dust_atten = float(julian_day), self.dust_atten
+        for n in L.MetEnergyArgs._IN:
+            setattr(a, n, self._sg(n, inputs.get(n, 0.0)))
+        for n in L.MetEnergyArgs._OUT:
+            setattr(a, n, getattr(self, n).data_ptr())
+        import ctypes as C
+        L.check(self.lib.tfb_met_energy(C.byref(a), L.stream_ptr()), 'tfb_met_energy')
