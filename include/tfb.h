@@ -138,6 +138,9 @@ int tfb_d8_parent_ids(const uint8_t *code, int32_t ny, int32_t nx,
 #define TFB_CH_FLOOD       (1u << 5)  /* FLOOD_OPTION: rectangle-over-trapezoid
                                          overbank flow (channels_base.py:1701-1862,
                                          :2149-2185, :2393-2448); generic kernel only */
+#define TFB_CH_ATTENUATE   (1u << 6)  /* ATTENUATE: runoff passes through a per-cell
+                                         linear reservoir (channels_base.py:2077-2084);
+                                         generic kernel only                        */
 #define TFB_CH_SRC_MET     (1u << 8)  /* P -> P_rain/P_snow split fused       */
 #define TFB_CH_SRC_SNOW    (1u << 9)  /* degree-day snowmelt fused            */
 #define TFB_CH_SRC_EVAP    (1u << 10) /* Priestley-Taylor ET fused            */
@@ -238,6 +241,10 @@ typedef struct {
     double *vol_flood;        /* out: water volume above bankfull (may be NULL)  */
     double flood_manning_n;   /* 0.10 in the reference (:1367)                   */
     double width_ratio;       /* flood-plain / channel width, 5.0 (:1368)        */
+    /* ---- ATTENUATE (TFB_CH_ATTENUATE) ------------------------------------------ */
+    const double *vol_stored; /* in: water held back on the hillslope             */
+    double *vol_stored_out;   /* out (alias rule as vol)                          */
+    double t_drain;           /* 86400 * n_days [s]                               */
 } tfb_channels_step_args;
 
 #define TFB_NSUM 24           /* doubles per rank exchanged by the allreduce:

@@ -209,6 +209,33 @@ def gen_flood(work):
     np.savez_compressed(os.path.join(GOLD, 'flood_channels.npz'), **out)
 
 
+def gen_attenuate(work):
+    """ATTENUATE (per-cell linear reservoir in front of the channel, :2077-2084) on the
+    61 x 83 synthetic case, KW and DW, rain for 100 of 150 steps."""
+    import topoflow.components.d8_global as d8g
+    g0 = dict(np.load(os.path.join(GOLD, 'flood_channels.npz')))
+    DEM, width, angle, nval = g0['DEM'], g0['width'], g0['angle'], g0['nval']
+    ny, nx = DEM.shape
+    out = {}
+    for kin in (True, False):
+        tag = 'kw' if kin else 'dw'
+        cdir = os.path.join(work, 'atten_' + tag)
+        cfg = synth.write_case(cdir, DEM, g0['slope'], width, angle, nval=nval, dt=2.0,
+                               kinematic=kin, outlet=(ny - 2, nx // 2), attenuate_days=0.002)
+        c = standalone_channels(cfg, kin, dict(
+            P_rain=z(150 / 3.6e6), MR=z(0), GW=z(0), SM=z(0), rho_H2O=z(1000.0),
+            ET=z(0), IN=z(0)))
+        assert c.ATTENUATE
+        for i in range(150):
+            if i == 100:
+                c.set_value(LONG['P_rain'], z(0))
+            rh.quiet_call(c.update)
+        for k, v in snapshot(c).items():
+            out[tag + '_' + k] = v
+        out[tag + '_vol_stored'] = np.array(c.vol_stored, dtype='float64')
+    np.savez_compressed(os.path.join(GOLD, 'attenuate_channels.npz'), **out)
+
+
 def gen_d8(work):
     """D8 toolkit on a DEM with plenty of ties and flats (elevations quantised
     to 0.25 m) and a few nodata cells; LINK_FLATS on and off."""
@@ -425,6 +452,7 @@ def main():
         meta['treynor_emeli'] = gen_treynor(work)
         gen_synth_channels(work)
         gen_flood(work)
+        gen_attenuate(work)
         gen_d8(work)
         gen_sources()
         gen_met_energy()

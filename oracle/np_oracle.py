@@ -314,7 +314,8 @@ class Channels(object):
     def __init__(self, code, ds32, dw32, slope, width, angle_deg, nval=None,
                  z0val=None, sinu=1.0, d0=0.0, da=900.0, dt=6.0,
                  kinematic=True, manning=True, outlet=(0, 0),
-                 rho_H2O=1000.0, check_stability=True, flood=False, d_bankfull=10.0):
+                 rho_H2O=1000.0, check_stability=True, flood=False, d_bankfull=10.0,
+                 attenuate=False, n_days=5.0):
         f64 = np.float64
         self.code = code
         self.ny, self.nx = code.shape
@@ -363,6 +364,8 @@ class Channels(object):
         self.vol = self.A_wet * self.ds
         self.Q = z()
         self.Rh = z()
+        self.ATTENUATE, self.n_days = bool(attenuate), n_days
+        self.vol_stored = z()                                  # :1343
         # ---- flood option :1346-1388 (rectangle over trapezoid, Sep. 2019)
         self.FLOOD_OPTION = bool(flood)
         self.d_flood = z()
@@ -418,8 +421,18 @@ class Channels(object):
             self.Q[:] = self.Qc + self.Qf
         else:
             self.Q[:] = self.u * self.A_wet
-        # update_flow_volume :2086-2145
-        self.vol += (self.R * self.da) * dt
+        # update_flow_volume :2077-2145
+        if self.ATTENUATE:
+            # all runoff passes through a linear (Nash) reservoir per cell :2077-2084
+            self.vol_stored += (self.R * self.da) * dt
+            t_drain = 3600.0 * 24.0 * self.n_days
+            Q_sides = (self.vol_stored / t_drain)
+            vol_sides = np.minimum(Q_sides * dt, self.vol_stored)
+            self.vol += vol_sides
+            self.vol_stored -= vol_sides
+            np.maximum(self.vol_stored, 0.0, self.vol_stored)
+        else:
+            self.vol += (self.R * self.da) * dt
         pr, pc = self.parent_IDs
         for k in range(8):
             wk = np.where(self.code == CODE_LIST[k])

@@ -62,3 +62,8 @@ def flood_gold():
 @pytest.fixture(scope='session')
 def met_gold():
     return load_golden('met_energy.npz')
+
+
+@pytest.fixture(scope='session')
+def attenuate_gold():
+    return load_golden('attenuate_channels.npz')

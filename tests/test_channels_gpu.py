@@ -357,3 +357,50 @@ def test_flood_option_vs_reference_fixture(flood_gold, tag):
     if not kin:
         assert rel_err(eng.own(eng.S_free).cpu().numpy(), g[tag + '_S_free']) <= RTOL
     _cmp_scalars(eng, want)
+
+
+@pytest.mark.parametrize('tag', ['kw', 'dw'])
+def test_attenuate_vs_reference_fixture(flood_gold, attenuate_gold, tag):
+    """ATTENUATE (per-cell linear reservoir in front of the channel,
+    channels_base.py:2077-2084) against a stand-alone REFERENCE run."""
+    g0, g = flood_gold, attenuate_gold
+    kin = (tag == 'kw')
+    code = g0['code']
+    ny, nx = code.shape
+    dx, dy, dd = o.pixel_dims(ny, 30.0, 30.0)
+    eng = _engine(code, dx, dy, dd, g0['slope'], g0['width'], g0['angle'], g0['nval'], dt=2.0,
+                  da=900.0, kinematic=kin, diag=True, outlet=(ny - 2, nx // 2), attenuate=True,
+                  n_days=0.002)
+    eng.set_input('P_rain', 150 / 3.6e6)
+    for i in range(150):
+        if i == 100:
+            eng.set_input('P_rain', 0.0)
+        eng.step(time_min=(i * 2.0) / 60.0)
+    want = {n: g[tag + '_' + n] for n in GRIDS + SCALARS}
+    _cmp_grids(eng, want, GRIDS)
+    assert rel_err(eng.vol_stored.cpu().numpy(), g[tag + '_vol_stored']) <= RTOL
+    assert g[tag + '_vol_stored'].max() > 1.0
+    _cmp_scalars(eng, want)
+
+
+def test_flood_component_from_cfg(tmp_path, flood_gold):
+    """FLOOD_OPTION read from the CFG file by the BMI component."""
+    from topoflow36_b200 import channels_kinematic_wave as ckw, synth
+    g = flood_gold
+    ny, nx = g['code'].shape
+    cfg = synth.write_case(str(tmp_path), g['DEM'], g['slope'], g['width'], g['angle'],
+                           nval=g['nval'], dt=2.0, kinematic=True, outlet=(ny - 2, nx // 2),
+                           flood=True, d_bankfull=g['d_bankfull'])
+    c = ckw.channels_component()
+    c.initialize(cfg_file=cfg, mode='nondriver', SILENT=True)
+    assert c.FLOOD_OPTION and np.array_equal(c.d8.d8_grid, g['code'])
+    c.set_value('atmosphere_water__rainfall_volume_flux', np.array(150 / 3.6e6))
+    for i in range(150):
+        if i == 100:
+            c.set_value('atmosphere_water__rainfall_volume_flux', np.array(0.0))
+        c.update()
+    for n in ('vol', 'd', 'u', 'Q', 'd_flood', 'vol_flood'):
+        assert rel_err(getattr(c, n), g['kw_' + n]) <= RTOL, n
+    assert rel_err(c.get_value_ptr('land_surface_water__depth'), g['kw_d_flood']) <= RTOL
+    c.finalize()
+    assert abs(float(c.vol_flood_sum) - g['kw_vol_flood'].sum()) <= 1e-11 * g['kw_vol_flood'].sum()

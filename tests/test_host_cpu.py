@@ -146,7 +146,7 @@ def test_initialize_fails_loudly_without_gpu(tmp_path):
 def test_unsupported_options_raise(tmp_path):
     from topoflow36_b200 import channels_kinematic_wave as ckw
     cfg, _ = _write_case(tmp_path)
-    open(cfg, 'a').write('ATTENUATE           | 1     | int        | Nash reservoir runoff\n')
+    open(cfg, 'a').write('CREATE_CHANNEL_FILES | 1     | int        | make width / n grids from area\n')
     c = ckw.channels_component()
     c.mode, c.cfg_file = 'driver', cfg
     c.set_constants()

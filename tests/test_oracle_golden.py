@@ -195,3 +195,25 @@ def test_solar_host_date_arithmetic(met_gold, case):
                              current_year=int(g['current_year']))
     assert JD == float(g[case + '_ujd_julian_day'])
     assert np.array_equal(tsn, g[case + '_ujd_TSN_offset'])
+
+
+@pytest.mark.parametrize('tag', ['kw', 'dw'])
+def test_attenuate_bit_exact(flood_gold, attenuate_gold, tag):
+    """ATTENUATE (channels_base.py:2077-2084): numpy restatement == reference run."""
+    g0, g = flood_gold, attenuate_gold
+    code = g0['code']
+    ny, nx = code.shape
+    dx, dy, dd = o.pixel_dims(ny, 30.0, 30.0)
+    ds32, dw32 = o.d8_ds_dw(code, dx, dy, dd)
+    ch = o.Channels(code, ds32, dw32, g0['slope'], g0['width'], g0['angle'], nval=g0['nval'],
+                    da=900.0, dt=2.0, kinematic=(tag == 'kw'), outlet=(ny - 2, nx // 2),
+                    attenuate=True, n_days=0.002)
+    ch.P_rain = np.array(150 / 3.6e6)
+    for i in range(150):
+        if i == 100:
+            ch.P_rain = np.array(0.0)
+        ch.step()
+    for n in GRIDS + ('vol_stored',):
+        assert np.array_equal(getattr(ch, n), g[tag + '_' + n], equal_nan=True), n
+    for n in SCALARS:
+        assert float(getattr(ch, n)) == float(g[tag + '_' + n]), n

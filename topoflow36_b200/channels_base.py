@@ -26,7 +26,8 @@ What the caller sees:
   * ``CHECK_STABILITY`` raises the reference's RuntimeErrors (:3275, :3429) from
     the bad-value counters the kernel returns.
 FLOOD_OPTION (rectangle-over-trapezoid overbank flow) is supported through the
-generic kernel.  Not handled (raise NotImplementedError): ATTENUATE, dynamic wave,
+generic kernel, as is ATTENUATE (per-cell linear reservoir).  Not handled (raise
+NotImplementedError): dynamic wave,
 CREATE_CHANNEL_FILES.
 """
 import os
@@ -110,7 +111,7 @@ _SRC_INPUTS = ('P_rain', 'SM', 'GW', 'MR', 'ET', 'IN')
 _DIAG = ('Rh', 'A_wet', 'P_wet', 'f', 'tau', 'u_star', 'froude')
 # attribute -> how to find the device tensor (state & diagnostics)
 _DEVICE_GRIDS = ('Q', 'Qc', 'vol', 'vol_chan', 'd', 'u', 'R', 'S_free', 'd_flood', 'df',
-                 'vol_flood') + _DIAG
+                 'vol_flood', 'vol_stored') + _DIAG
 
 
 class channels_component(BMI_base.BMI_component):
@@ -144,6 +145,10 @@ class channels_component(BMI_base.BMI_component):
 
     def _device_tensor(self, name):
         e = self.engine
+        if name == 'vol_stored':
+            if not e.attenuate:
+                raise AttributeError('vol_stored exists only with ATTENUATE')
+            return e.vol_stored
         if name in ('d_flood', 'df', 'vol_flood'):
             if not e.flood:
                 raise AttributeError(name + ' exists only with FLOOD_OPTION')
@@ -255,9 +260,9 @@ class channels_component(BMI_base.BMI_component):
         self.MANNING = bool(int(self.MANNING))
         self.LAW_OF_WALL = bool(int(self.LAW_OF_WALL))
         self.FLOOD_OPTION = bool(int(self.FLOOD_OPTION))
-        if self.ATTENUATE not in (False, 0):
-            raise NotImplementedError('ATTENUATE (Nash reservoir runoff) is not part of the '
-                                      'GPU path')
+        self.ATTENUATE = bool(int(self.ATTENUATE))
+        if self.ATTENUATE and not hasattr(self, 'n_days'):
+            self.n_days = 5                                          # :566-568
         if self.CREATE_CHANNEL_FILES not in (False, 0):
             raise NotImplementedError('CREATE_CHANNEL_FILES is input preparation '
                                       '(SURVEY.md 8f-3), not part of the GPU path')
@@ -449,7 +454,8 @@ class channels_component(BMI_base.BMI_component):
             write_R=bool(self.WRITE_R), outlet=(int(self.outlet_ID[0]), int(self.outlet_ID[1])),
             rho_H2O=float(self.rho_H2O), device=self.device, row0=row0, ny_global=self.ny,
             halo=halo, finalize=True, n_pixels_global=ny_loc * self.nx,
-            flood=self.FLOOD_OPTION,
+            flood=self.FLOOD_OPTION, attenuate=self.ATTENUATE,
+            n_days=float(getattr(self, 'n_days', 5.0)),
             d_bankfull=self.d_bankfull if np.ndim(self.d_bankfull) == 2 else float(self.d_bankfull))
         if self._fused:
             self.engine.enable_fused_sources(**self._fused)

@@ -192,6 +192,22 @@ __device__ __forceinline__ void load_cell_scalar(const tfb_channels_step_args &a
     g.vb = (a.flags & TFB_CH_FLOOD) ? sg_at(a.vol_bankfull, i) : 0.0;
 }
 
+// volume that reaches the channel this step: all of the runoff volume, or -- with
+// ATTENUATE -- the outflow of the cell's linear reservoir (channels_base.py:2077-2084)
+template <bool COMMIT>
+__device__ __forceinline__ double attenuate(const tfb_channels_step_args &a, int64_t i,
+                                            double Rv) {
+    if (!(a.flags & TFB_CH_ATTENUATE)) return Rv;
+    double vs = __ldg(a.vol_stored + i) + Rv;
+    const double Q_sides = vs / a.t_drain;
+    const double vol_sides = np_min(Q_sides * a.dt, vs);
+    if (COMMIT) {
+        vs = vs - vol_sides;
+        a.vol_stored_out[i] = np_max(vs, 0.0);
+    }
+    return vol_sides;
+}
+
 // new volume (before the noflow zeroing) and new depth of a cell ---------------
 template <bool SRC, bool UR, bool COMMIT>
 __device__ __forceinline__ void vol_depth(const tfb_channels_step_args &a, const ChConsts &kc,
@@ -205,7 +221,7 @@ __device__ __forceinline__ void vol_depth(const tfb_channels_step_args &a, const
         // every source input is a scalar (and so is da): R and (R*da)*dt are the
         // same for all cells -- evaluated once on the host in this very order
         R_out = kc.R_uniform;
-        v = g.vol + kc.Rdadt_uniform;                                // :2086
+        v = g.vol + attenuate<COMMIT>(a, i, kc.Rdadt_uniform);       // :2077-2086
     } else {
         Src s;
         eval_sources<SRC, COMMIT>(a, i, g, s, ns, acc);
@@ -222,7 +238,7 @@ __device__ __forceinline__ void vol_depth(const tfb_channels_step_args &a, const
         const double R = (((s.P_rain + s.SM) + s.GW) + s.MR) - (ET + s.IN);
         R_out = R;
         if (COMMIT && a.is_R_grid) acc->s[S_VOL_R] += (R * g.da) * dt;   // :1666-1670
-        v = g.vol + ((R * g.da) * dt);                               // :2086
+        v = g.vol + attenuate<COMMIT>(a, i, (R * g.da) * dt);        // :2077-2086
     }
     // children in the reference's order (codes 1,2,4,...,128) :2116-2131;
     // Qc[k] is the child's discharge, meaningful only where the mask bit is set
@@ -723,6 +739,10 @@ extern "C" int tfb_channels_step(const tfb_channels_step_args *ap, void *stream)
     if (src) TFB_ARG_CHECK(a.is_R_grid == 1);
     if (a.flags & TFB_CH_FLOOD)
         TFB_ARG_CHECK(a.flood_manning_n > 0.0 && a.width_ratio > 0.0);
+    if (a.flags & TFB_CH_ATTENUATE) {
+        TFB_ARG_CHECK(a.vol_stored && a.vol_stored_out && a.t_drain > 0.0);
+        if (dw) TFB_ARG_CHECK(a.vol_stored != a.vol_stored_out);
+    }
     ChConsts k;
     k.g = 9.81; k.aval = 0.476; k.kappa = 0.408;
     k.law_const = sqrt(k.g) / k.kappa;                 // channels_base :531

@@ -925,7 +925,8 @@ int prepare(const tfb_channels_step_args *ap, const tfb_channels_packed *pp, boo
     // eligibility: Manning, lean outputs, uniform forcing
     const uint32_t src = a.flags & (TFB_CH_SRC_MET | TFB_CH_SRC_SNOW | TFB_CH_SRC_EVAP |
                                     TFB_CH_SRC_INFIL);
-    TFB_ARG_CHECK(!(a.flags & (TFB_CH_LAW_OF_WALL | TFB_CH_DIAG | TFB_CH_WRITE_R | TFB_CH_FLOOD)));
+    TFB_ARG_CHECK(!(a.flags & (TFB_CH_LAW_OF_WALL | TFB_CH_DIAG | TFB_CH_WRITE_R | TFB_CH_FLOOD |
+                               TFB_CH_ATTENUATE)));
     TFB_ARG_CHECK(((a.flags & TFB_CH_DIFFUSIVE) != 0) == diffusive);
     if (diffusive) TFB_ARG_CHECK(p.inv_rough && p.S32 && a.halo != 0 ? a.halo >= 1 : true);
     else TFB_ARG_CHECK(p.coef != nullptr);

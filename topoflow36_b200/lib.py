@@ -23,6 +23,7 @@ CH_DIAG = 1 << 2
 CH_WRITE_R = 1 << 3
 CH_ET_INPLACE = 1 << 4
 CH_FLOOD = 1 << 5
+CH_ATTENUATE = 1 << 6
 CH_SRC_MET = 1 << 8
 CH_SRC_SNOW = 1 << 9
 CH_SRC_EVAP = 1 << 10
@@ -84,6 +85,7 @@ class ChannelsStepArgs(C.Structure):
         ('scalars_mirror', vp),
         ('vol_bankfull', SG), ('d_flood', vp), ('vol_flood', vp),
         ('flood_manning_n', C.c_double), ('width_ratio', C.c_double),
+        ('vol_stored', vp), ('vol_stored_out', vp), ('t_drain', C.c_double),
     ]
 
 

@@ -35,7 +35,7 @@ class ChannelsEngine(object):
                  write_R=False, outlet=(0, 0), rho_H2O=1000.0, row0=0,
                  ny_global=None, halo=0, device=None, finalize=True,
                  n_pixels_global=None, packed=True, flood=False, d_bankfull=10.0,
-                 flood_manning_n=0.10, width_ratio=5.0):
+                 flood_manning_n=0.10, width_ratio=5.0, attenuate=False, n_days=5.0):
         if not torch.cuda.is_available():
             raise L.TfbError('ChannelsEngine needs a CUDA device (no CPU path)')
         self.lib = L.load()
@@ -69,6 +69,10 @@ class ChannelsEngine(object):
         self.flood = bool(flood)
         if self.flood:
             flags |= L.CH_FLOOD
+        self.attenuate = bool(attenuate)
+        if self.attenuate:
+            flags |= L.CH_ATTENUATE
+            a.t_drain = 3600.0 * 24.0 * float(n_days)             # channels_base.py:2079
         self.flags = flags
         # ---- static inputs --------------------------------------------------
         self.code = self._grid(code, torch.uint8)
@@ -156,6 +160,10 @@ class ChannelsEngine(object):
         self.set_initial_depth(d0)
         self.n_steps = 0
         self.d_flood = self.vol_flood = self.vol_bankfull = None
+        self.vol_stored_buf = None
+        if self.attenuate:
+            self.vol_stored_buf = [self._zeros(torch.float64),
+                                   self._zeros(torch.float64) if not kinematic else None]
         if self.flood:
             self._init_flood(d_bankfull, flood_manning_n, width_ratio)
         self.packed = None
@@ -203,7 +211,8 @@ class ChannelsEngine(object):
         scalar sinuosity / pixel area, float32-exact widths, <= 256 distinct
         bank angles).  Everything is lossless; otherwise the generic kernel runs."""
         a = self.args
-        if (not self.manning) or self.diag or self.flood or (self.flags & L.CH_WRITE_R):
+        if ((not self.manning) or self.diag or self.flood or self.attenuate
+                or (self.flags & L.CH_WRITE_R)):
             return
         if self.nx % 4 or self.sinu_grid is not None or self._da_is_grid:
             return
@@ -461,6 +470,10 @@ class ChannelsEngine(object):
         return self.own(self._sbuf(self.vol_buf))
 
     @property
+    def vol_stored(self):
+        return self.own(self._sbuf(self.vol_stored_buf))
+
+    @property
     def I(self):
         return self.own(self._sbuf(self.I_buf))
 
@@ -502,7 +515,7 @@ class ChannelsEngine(object):
         a.Q_in = self._p(self.Q_buf[self.qcur])
         a.Q_out = self._p(self.Q_buf[self.qcur ^ 1])
         for name, buf in (('vol', self.vol_buf), ('h_swe', self.h_swe_buf),
-                          ('I', self.I_buf)):
+                          ('I', self.I_buf), ('vol_stored', self.vol_stored_buf)):
             if buf is None:
                 continue
             dbl = buf[1] is not None

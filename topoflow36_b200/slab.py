@@ -134,7 +134,7 @@ class SlabChannels(object):
         ts, rows = [e.Q_buf[e.qcur]], [lay.halo]
         if not e.kinematic:
             ts.append(e._sbuf(e.vol_buf)); rows.append(1)
-            for buf in (e.I_buf, e.h_swe_buf):
+            for buf in (e.I_buf, e.h_swe_buf, e.vol_stored_buf):
                 if buf is not None:
                     ts.append(e._sbuf(buf)); rows.append(1)
         exchange_halos(ts, lay, rows, self.group)

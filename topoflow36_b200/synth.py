@@ -135,7 +135,7 @@ def write_case(case_dir, DEM, slope, width, angle, nval=None, z0val=None,
                kinematic=True, manning=True, link_flats=1, outlet=None,
                n_steps=100, d0=0.0, sinu=1.0, scalar_angle=None,
                scalar_width=None, check_stability='Yes', byte_order=None, flood=False,
-               d_bankfull=None):
+               d_bankfull=None, attenuate_days=None):
     """Write a stand-alone routing case into `case_dir` (all files side by
     side; in_directory = out_directory = '.').  Returns the channels CFG path."""
     os.makedirs(case_dir, exist_ok=True)
@@ -195,8 +195,12 @@ def write_case(case_dir, DEM, slope, width, angle, nval=None, z0val=None,
     db = gs(d_bankfull is not None and np.ndim(d_bankfull) == 2, '_d-bank.rtg',
             10.0 if d_bankfull is None or np.ndim(d_bankfull) == 2 else d_bankfull)
     flood_line = ''
+    if attenuate_days is not None:
+        flood_line += ('ATTENUATE           | 1     | int        | route runoff through a linear reservoir\n'
+                       'n_days              | %r    | float      | drainage time of the reservoir [days]\n'
+                       % float(attenuate_days))
     if flood:
-        flood_line = ('FLOOD_OPTION        | 1     | int        | option to model overbank flow\n'
+        flood_line += ('FLOOD_OPTION        | 1     | int        | option to model overbank flow\n'
                       'SAVE_DF_GRIDS       | No     | string    | option to save d_flood grids\n'
                       'd_flood_gs_file     | [case_prefix]_2D-d-flood.nc  | string    | filename\n'
                       'SAVE_DF_PIXELS      | No     | string    | option to save d_flood series\n'
