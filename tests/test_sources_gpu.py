@@ -84,3 +84,66 @@ def test_met_energy_chain(met_gold, case):
         assert e <= 1e-11, '%s rel err %.3e' % (k, e)
     dark_ref = (g[case + '_Qn_SW'] == 0)
     assert np.array_equal(m.Qn_SW.cpu().numpy() == 0, dark_ref)      # same sunrise/sunset cells
+
+
+def test_unfused_coupling_on_device_equals_fused(sources_gold):
+    """EMELI-style coupling without leaving the GPU: the stand-alone met / snow / evap /
+    infil steppers hand CUDA tensors to the Channels engine through its inputs (zero
+    copy), in provider order met, snow, evap, infil, channels -- the result equals the
+    run with the same source terms fused into the routing kernel."""
+    import torch
+    from conftest import rel_err
+    from oracle import np_oracle as o
+    from topoflow36_b200 import cases, synth
+    from topoflow36_b200.routing import ChannelsEngine
+    from topoflow36_b200.sources import MetPrecip, DegreeDay, PriestleyTaylor, GreenAmpt
+    ny, nx = 64, 96
+    DEM = synth.fractal_dem(ny, nx, seed=12, sigma=1.0)
+    dx, dy, dd = o.pixel_dims(ny, 30.0, 30.0)
+    code, _ = o.d8_flow_grid(DEM, dx, dy, dd)
+    ds, _ = o.d8_ds_dw(code, dx, dy, dd)
+    slope = np.array(o.d8_slope(DEM, code, ds), dtype='float64')
+    o.remove_bad_slopes(slope)
+    width, angle, nval = synth.channel_params(ny, nx, seed=12)
+    rng = np.random.default_rng(8)
+    T_air = 2.0 + 3.0 * (2.0 * rng.random((ny, nx)) - 1.0)
+    P, dt = 4e-5, 2.0
+    src = dict(cases.FULL_SOURCES, h0_swe=0.004, I0=0.05)
+    sc = cases.FULL_SCALARS
+
+    def engine():
+        return ChannelsEngine(ny, nx, dt=dt, code=code, dx=dx, dy=dy, dd=dd, S_bed=slope,
+                              width=np.float64(width), angle=np.float64(angle) * o.DEG_TO_RAD,
+                              rough=np.float64(nval), outlet=(ny - 2, nx // 2))
+    fused = engine()
+    fused.enable_fused_sources(**src)
+    fused.set_input('P_rain', P)
+    fused.set_input('T_air', T_air)
+    for k, v in list(sc.items()) + list(cases.GA_TREYNOR.items()):
+        fused.set_input(k, v)
+    eng = engine()
+    met = MetPrecip(ny, nx, dt, T_rain_snow=src['T_rain_snow'])
+    snow = DegreeDay(ny, nx, dt, sc['c0'], sc['T0'], h0_swe=src['h0_swe'], rho_snow=src['rho_snow'])
+    evap = PriestleyTaylor(ny, nx, dt, alpha=src['alpha'], K_soil=src['K_soil'],
+                           soil_x=src['soil_x'], T_soil_x=src['T_soil_x'])
+    infil = GreenAmpt(ny, nx, dt, I0=src['I0'], **cases.GA_TREYNOR)
+    Ta = torch.as_tensor(T_air).cuda()
+    for i in range(60):
+        met.update(P, Ta)
+        snow.update(met.P_snow, Ta)
+        evap.update(Ta, sc['T_surf'], sc['Qn_SW'], sc['Qn_LW'])
+        infil.update(met.P_rain, snow.SM)
+        for n, t in (('P_rain', met.P_rain), ('SM', snow.SM), ('ET', evap.ET), ('IN', infil.IN)):
+            eng.set_input(n, t)                      # CUDA tensors: bound in place
+        eng.step(time_min=i * dt / 60.0)
+        fused.step(time_min=i * dt / 60.0)
+    assert fused.last_path == 'packed' and eng.last_path == 'generic'
+    for a, b in ((eng.vol, fused.vol), (eng.own(eng.d), fused.own(fused.d)),
+                 (eng.own(eng.u), fused.own(fused.u)), (eng.Q, fused.Q),
+                 (infil.I, fused.I), (snow.h_swe, fused.h_swe)):
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-12
+    s1, s2 = eng.read_scalars(), fused.read_scalars()
+    assert abs(s1.vol_R - s2.vol_R) <= 1e-12 * abs(s2.vol_R)
+    assert abs(infil.vol_IN - s2.vol_IN) <= 1e-12 * s2.vol_IN
+    assert abs(snow.vol_SM - s2.vol_SM) <= 1e-12 * max(s2.vol_SM, 1e-300)
+    assert float(fused.Q.max()) > 0
