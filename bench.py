@@ -149,6 +149,40 @@ def cpu_port_rate(budget_s, n_steps=None, warmup=1, threads=None):
     return val, desc, threads, dt / n_steps * 1e3, n_steps
 
 
+def cpu_numpy_rate(n=1024, n_steps=6):
+    """The reference's OWN CPU path is whole-grid numpy (one core).  It cannot travel to
+    the GPU box, so its numpy restatement (oracle/np_oracle.py, the same expressions in
+    the same order, bit-exact against it) is timed instead on an n x n sub-case: KW +
+    Green-Ampt, like the benchmark.  Returns (Gcell/s, description)."""
+    from oracle import c_oracle, np_oracle as o
+    from topoflow36_b200 import cases
+    tile = cases.noise_tile(n, n, seed=1234)
+    DEM = cases.slab_dem(n, n, 0, n, 0, tile)
+    dx, dy, dd = o.pixel_dims(n, 30.0, 30.0)
+    code, _ = c_oracle.d8_flow_grid(DEM, dx, dy, dd)
+    ds32, dw32 = o.d8_ds_dw(code, dx, dy, dd)
+    with np.errstate(all='ignore'):
+        slope = o.d8_slope(DEM, code, ds32)
+    width, angle, nval = cases.slab_params(n, n, 0, 0, seed=1234)
+    ch = o.Channels(code, ds32, dw32, slope, width, angle, nval=nval, dt=1.0,
+                    outlet=(n - 2, n // 2), check_stability=True)
+    ch.P_rain = np.array(cases.RAIN_50MMPH)
+    I = np.zeros((n, n)) + cases.I0_WET
+
+    def step():
+        nonlocal I
+        ch.IN, I = o.green_ampt_step(I, ch.P_rain, 0.0, dt=1.0, **cases.GA_TREYNOR)
+        ch.step()
+    with np.errstate(all='ignore'):
+        step()
+        t0 = time.perf_counter()
+        for _ in range(n_steps):
+            step()
+        dt = time.perf_counter() - t0
+    return n_steps * n * n / dt / 1e9, ('%d x %d sub-case, %d steps, numpy restatement of the '
+                                        'reference path (np_oracle), 1 core' % (n, n, n_steps))
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -389,6 +423,8 @@ def main():
     if world == 1 and not args.no_cpu_baseline and infil and NX == 4096:
         v, desc, cores, _, _ = cpu_port_rate(15.0)
         cpu = {'value': v, 'unit': 'Gcell-updates/s', 'cores': cores, 'kind': 'port', 'sample': desc}
+        nv, ndesc = cpu_numpy_rate()
+        cpu['numpy_path'] = {'value': nv, 'unit': 'Gcell-updates/s', 'cores': 1, 'sample': ndesc}
 
     out = {
         'metric': METRIC, 'value': value, 'unit': 'Gcell-updates/s', 'n_gpus': world,
