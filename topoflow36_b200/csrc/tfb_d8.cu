@@ -211,16 +211,35 @@ __device__ __forceinline__ int child_mask(const uint8_t *__restrict__ code, int 
     return m;
 }
 
+// Per-cell word of the area pass (kept in the caller's int32 scratch):
+//   bits 0-3  children that have not arrived yet      bits 8-15  child mask (neighbour k
+//   bits 16-23 D8 code                                 drains into the cell)
+//   bit 24    the cell is the ONLY child of its parent bit 25    the parent is a flow cell
+constexpr int kWOnly = 1 << 24, kWParent = 1 << 25;
+
 __global__ void __launch_bounds__(256)
 d8_area_init_kernel(const uint8_t *__restrict__ code, int ny, int nx, float *A,
-                    int64_t *count, int32_t *pending) {
+                    int64_t *count, int32_t *word) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y * blockDim.y + threadIdx.y;
     if (c >= nx || r >= ny) return;
     const int64_t i = (int64_t)r * nx + c;
     A[i] = 0.0f;
     if (count) count[i] = 0;
-    pending[i] = (code[i] != 0) ? __popc(child_mask(code, ny, nx, r, c)) : -1;
+    const unsigned cd = code[i];
+    int w = 0;
+    if (cd != 0) {
+        const int m = child_mask(code, ny, nx, r, c);
+        w = __popc(m) | (m << 8) | ((int)cd << 16);
+        int dr, dc;
+        code_offset(cd, dr, dc);
+        const int pr = r + dr, pc = c + dc;
+        if (pr >= 0 && pr < ny && pc >= 0 && pc < nx && code[(int64_t)pr * nx + pc] != 0) {
+            w |= kWParent;
+            if (__popc(child_mask(code, ny, nx, pr, pc)) == 1) w |= kWOnly;
+        }
+    }
+    word[i] = w;
 }
 
 // One topological pass: a thread starts at every source cell (flow cell with
@@ -228,50 +247,58 @@ d8_area_init_kernel(const uint8_t *__restrict__ code, int ny, int nx, float *A,
 // arrive at the next cell; each cell's value is pixel_area (stored fp32) plus
 // its children's final values in neighbour order k = 0..7, exactly the
 // reference's per-cell sum (d8_global.py:1223-1258), so the result does not
-// depend on the schedule.
+// depend on the schedule.  Along unbranched reaches (the cell is its parent's only
+// child) no atomic or fence is needed and the running value stays in a register:
+// one dependent load per cell instead of fence + atomic + reload.
 __global__ void __launch_bounds__(256)
 d8_area_walk_kernel(const uint8_t *__restrict__ code, int ny, int nx, double pixel_area,
                     const double *__restrict__ pa_row, float *A, int64_t *count,
-                    int32_t *pending, unsigned long long *n_done) {
+                    int32_t *word, unsigned long long *n_done) {
     const int c0 = blockIdx.x * blockDim.x + threadIdx.x;
     const int r0 = blockIdx.y * blockDim.y + threadIdx.y;
     if (c0 >= nx || r0 >= ny) return;
     int r = r0, c = c0;
-    unsigned cd = code[(int64_t)r * nx + c];
-    if (cd == 0) return;
-    int cm = child_mask(code, ny, nx, r, c);
-    if (cm != 0) return;              // not a source
+    int64_t i = (int64_t)r * nx + c;
+    int w = word[i];
+    if (((w >> 16) & 0xff) == 0 || ((w >> 8) & 0xff) != 0) return;    // not a source
     unsigned long long done = 0;
     volatile float *Av = A;
     volatile int64_t *Cv = count;
+    float a = (float)(pa_row ? pa_row[r] : pixel_area);
+    int64_t n = 1;
     while (true) {
-        const int64_t i = (int64_t)r * nx + c;
-        float a = (float)(pa_row ? pa_row[r] : pixel_area);
-        int64_t n = 1;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (cm & (1 << k)) {
-                const int64_t j = i + (int64_t)kNbrDRow[k] * nx + kNbrDCol[k];
-                a += Av[j];
-                if (count) n += Cv[j];
-            }
-        }
         Av[i] = a;
         if (count) Cv[i] = n;
         ++done;
+        if (!(w & kWParent)) break;       // drains off the grid or into a noflow cell
         int dr, dc;
-        code_offset(cd, dr, dc);
-        const int pr = r + dr, pc = c + dc;
-        if (pr < 0 || pr >= ny || pc < 0 || pc >= nx) break;
-        const int64_t ip = (int64_t)pr * nx + pc;
-        const unsigned pcd = code[ip];
-        if (pcd == 0) break;          // drains into a noflow cell: A stays 0 there
-        __threadfence();              // publish A[i] before announcing arrival
-        const int old = atomicSub(&pending[ip], 1);
-        if (old != 1) break;          // a sibling arrives later and continues
-        __threadfence();
-        r = pr; c = pc; cd = pcd;
-        cm = child_mask(code, ny, nx, r, c);
+        code_offset((unsigned)((w >> 16) & 0xff), dr, dc);
+        r += dr; c += dc;
+        const int64_t ip = (int64_t)r * nx + c;
+        const float pa = (float)(pa_row ? pa_row[r] : pixel_area);
+        if (w & kWOnly) {
+            w = __ldcg(word + ip);        // static bits only: nobody else touches this word
+            a = pa + a;                   // the single child's value is still in the register
+            n = 1 + n;
+        } else {
+            __threadfence();              // publish A[i] before announcing arrival
+            const int old = atomicSub(&word[ip], 1);
+            if ((old & 0xf) != 1) break;  // a sibling arrives later and continues
+            __threadfence();
+            w = old;
+            const int cm = (old >> 8) & 0xff;
+            a = pa;
+            n = 1;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (cm & (1 << k)) {
+                    const int64_t j = ip + (int64_t)kNbrDRow[k] * nx + kNbrDCol[k];
+                    a += Av[j];
+                    if (count) n += Cv[j];
+                }
+            }
+        }
+        i = ip;
     }
     atomicAdd(n_done, done);
 }
