@@ -141,20 +141,21 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
 // per tile row (R + 1 warps, up to 128 registers per thread), 1 -> two warps per row
 // (2R + 1 warps: more latency hiding, 64 registers).  The best choice depends on the
 // register needs of the variant and is made per kernel instantiation (launch_main).
-constexpr int kTW = 64;
-constexpr int kQW = kTW + 4;                         // halo box: cols c0-2 .. c0+65
 constexpr int kSmemBudget = 196 * 1024;              // dynamic shared memory for the ring
 constexpr int kMaxWarps = 32;
-template <int ROWS, int CPL> struct TileCfg {
+template <int ROWS, int CPL, int WIDTH = 64> struct TileCfg {
     static constexpr int R = ROWS;
+    static constexpr int W = WIDTH;                  // tile columns
+    static constexpr int QW = WIDTH + 4;             // halo box: cols c0-2 .. c0+W+1
+    static constexpr int wpr = WIDTH / (32 * CPL);   // consumer warps per tile row
     static constexpr int QR = ROWS + 2;              // halo box: rows r0-1 .. r0+R
     static constexpr int cpl = CPL;
-    static constexpr int warps = ROWS * (2 / CPL);   // consumer warps
+    static constexpr int warps = ROWS * wpr;         // consumer warps
     static constexpr int threads = (warps + 1) * 32; // + 1 producer warp
-    static constexpr int szQ = ((kQW * QR * 8 + 127) / 128) * 128;
-    static constexpr int szD = ((kTW * ROWS * 8 + 127) / 128) * 128;   // one fp64 tile
-    static constexpr int szF = ((kTW * ROWS * 4 + 127) / 128) * 128;   // one 32-bit tile
-    static constexpr int nD = kTW * ROWS * 8, nF = kTW * ROWS * 4, nQ = kQW * QR * 8;  // TMA bytes
+    static constexpr int szQ = ((QW * QR * 8 + 127) / 128) * 128;
+    static constexpr int szD = ((WIDTH * ROWS * 8 + 127) / 128) * 128;   // one fp64 tile
+    static constexpr int szF = ((WIDTH * ROWS * 4 + 127) / 128) * 128;   // one 32-bit tile
+    static constexpr int nD = WIDTH * ROWS * 8, nF = WIDTH * ROWS * 4, nQ = QW * QR * 8;  // TMA bytes
 };
 
 // ring slot of the main kernel (kinematic step, or pass A of the diffusive step)
@@ -419,7 +420,7 @@ __global__ void __launch_bounds__(TC::threads, 1)
 channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed p,
                        const PkConsts k, const __grid_constant__ PkMaps maps) {
     using SL = StageLayout<SRC, VAR, TC>;
-    constexpr int kTR = TC::R, kConsumerWarps = TC::warps, kThreads = TC::threads;
+    constexpr int kTR = TC::R, kTW = TC::W, kQW = TC::QW, kConsumerWarps = TC::warps, kThreads = TC::threads;
     constexpr int NS = SL::stages;
     constexpr bool kKW = (VAR == PK_KW);
     extern __shared__ __align__(128) unsigned char smem[];
@@ -486,7 +487,7 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
             if (!mbar_wait(&full_bar[stage], phase)) { s_fail = 1; break; }
             const int ty = t / k.tiles_x, txi = t - ty * k.tiles_x;
             if constexpr (TC::cpl == 1) {
-            const int row = warp >> 1, ct = ((warp & 1) << 5) + lane;  // two warps per tile row
+            const int row = warp / TC::wpr, ct = ((warp % TC::wpr) << 5) + lane;  // wpr warps per tile row
             const int c0 = txi * kTW + ct, r = ty * kTR + row;
             const unsigned char *st = smem + (size_t)stage * SL::bytes;
             if (r < a.ny && c0 < a.nx) {
@@ -529,10 +530,11 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
                 }
             }
             } else {
-            const int c0 = txi * kTW + lane * 2, r = ty * kTR + warp;
+            const int row = warp / TC::wpr, ct = ((warp % TC::wpr) << 6) + lane * 2;
+            const int c0 = txi * kTW + ct, r = ty * kTR + row;
             const unsigned char *st = smem + (size_t)stage * SL::bytes;
             if (r < a.ny && c0 < a.nx) {
-                const int e = warp * kTW + lane * 2;                   // element in a 64x16 tile
+                const int e = row * kTW + ct;                          // element in the tile
                 const uint2 geo = *reinterpret_cast<const uint2 *>(st + SL::oGeo + e * 4);
                 const float2 w = *reinterpret_cast<const float2 *>(st + SL::oW + e * 4);
                 const double2 vol = *reinterpret_cast<const double2 *>(st + SL::oVol + e * 8);
@@ -542,7 +544,7 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
                 if (use_h) Hv = *reinterpret_cast<const double2 *>(st + SL::oH + e * 8);
                 if (use_t) Tv = *reinterpret_cast<const double2 *>(st + SL::oT + e * 8);
                 // Q window: halo rows warp, warp+1, warp+2; halo cols 2*lane .. 2*lane+4
-                const double *q = reinterpret_cast<const double *>(st + SL::oQ) + warp * kQW + lane * 2;
+                const double *q = reinterpret_cast<const double *>(st + SL::oQ) + row * kQW + ct;
                 const double2 a0 = *reinterpret_cast<const double2 *>(q);
                 const double2 a1 = *reinterpret_cast<const double2 *>(q + 2);
                 const double2 m0 = *reinterpret_cast<const double2 *>(q + kQW);
@@ -621,7 +623,7 @@ __global__ void __launch_bounds__(TC::threads, 1)
 channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_packed p,
                            const PkConsts k, const __grid_constant__ PkMapsB maps) {
     using SL = StageLayoutB<TC>;
-    constexpr int kTR = TC::R, kConsumerWarps = TC::warps, kThreads = TC::threads;
+    constexpr int kTR = TC::R, kTW = TC::W, kQW = TC::QW, kConsumerWarps = TC::warps, kThreads = TC::threads;
     constexpr int NS = SL::stages;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(16) double lut[256 * 4];
@@ -675,7 +677,7 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
             if (!mbar_wait(&full_bar[stage], phase)) { s_fail = 1; break; }
             const int ty = t / k.tiles_x, txi = t - ty * k.tiles_x;
             if constexpr (TC::cpl == 1) {
-            const int row = warp >> 1, ct = ((warp & 1) << 5) + lane;
+            const int row = warp / TC::wpr, ct = ((warp % TC::wpr) << 5) + lane;
             const int c0 = txi * kTW + ct, r = ty * kTR + row;
             const unsigned char *st = smem + (size_t)stage * SL::bytes;
             if (r < a.ny && c0 < a.nx) {
@@ -706,17 +708,18 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
                 if (code == 0u) a.d[i] = 0.0;                              // :2966
             }
             } else {
-            const int c0 = txi * kTW + lane * 2, r = ty * kTR + warp;
+            const int row = warp / TC::wpr, ct = ((warp % TC::wpr) << 6) + lane * 2;
+            const int c0 = txi * kTW + ct, r = ty * kTR + row;
             const unsigned char *st = smem + (size_t)stage * SL::bytes;
             if (r < a.ny && c0 < a.nx) {
-                const int e = warp * kTW + lane * 2;
+                const int e = row * kTW + ct;
                 const uint2 geo = *reinterpret_cast<const uint2 *>(st + SL::oGeo + e * 4);
                 const float2 w = *reinterpret_cast<const float2 *>(st + SL::oW + e * 4);
                 const float2 S = *reinterpret_cast<const float2 *>(st + SL::oS + e * 4);
                 const double2 invn = *reinterpret_cast<const double2 *>(st + SL::oN + e * 8);
                 // depth tile with halo: own cell (row warp+1, col 2*lane+2)
                 const double *dT = reinterpret_cast<const double *>(st + SL::oD);
-                const double *dc = dT + (warp + 1) * kQW + lane * 2 + 2;
+                const double *dc = dT + (row + 1) * kQW + ct + 2;
                 const double2 dv = *reinterpret_cast<const double2 *>(dc);
                 const double2 *rgp = reinterpret_cast<const double2 *>(p.row_geom + (int64_t)r * 6);
                 const double2 g1 = __ldg(rgp + 1), g2 = __ldg(rgp + 2);
@@ -843,7 +846,8 @@ template <int SRC, int VAR, class TC>
 int launch_main(const tfb_channels_step_args &a, const tfb_channels_packed &p, PkConsts k,
                 cudaStream_t st) {
     using SL = StageLayout<SRC, VAR, TC>;
-    constexpr int kTR = TC::R, kQR = TC::QR, kThreads = TC::threads;
+    constexpr int kTR = TC::R, kQR = TC::QR, kTW = TC::W, kQW = TC::QW, kThreads = TC::threads;
+    k.tiles_x = (a.nx + kTW - 1) / kTW;
     k.n_tiles = k.tiles_x * ((a.ny + kTR - 1) / kTR);
     static_assert(SL::stages >= 2, "ring needs at least two slots");
     PkMaps m;
@@ -884,7 +888,8 @@ template <class TC>
 int launch_dwb(const tfb_channels_step_args &a, const tfb_channels_packed &p, PkConsts k,
                cudaStream_t st) {
     using SL = StageLayoutB<TC>;
-    constexpr int kTR = TC::R, kQR = TC::QR, kThreads = TC::threads;
+    constexpr int kTR = TC::R, kQR = TC::QR, kTW = TC::W, kQW = TC::QW, kThreads = TC::threads;
+    k.tiles_x = (a.nx + kTW - 1) / kTW;
     k.n_tiles = k.tiles_x * ((a.ny + kTR - 1) / kTR);
     PkMapsB m;
     const int64_t rows_h = (int64_t)a.ny + 2 * a.halo;
@@ -943,7 +948,7 @@ int prepare(const tfb_channels_step_args *ap, const tfb_channels_packed *pp, boo
     k.da = a.da.val;
     k.Psum = ((a.P_rain.val + a.SM.val) + a.GW.val) + a.MR.val;
     k.P_total = a.P_rain.val + a.SM.val;
-    k.tiles_x = (a.nx + kTW - 1) / kTW;
+    k.tiles_x = 0;
     k.n_tiles = 0;                                   // set per tile configuration by the launcher
     k.flags = src;
     if (src == 0) {
@@ -996,8 +1001,17 @@ int prepare(const tfb_channels_step_args *ap, const tfb_channels_packed *pp, boo
 #ifndef TFB_PK_GA_CPL
 #define TFB_PK_GA_CPL 2
 #endif
-typedef TileCfg<15, 1> CfgNone;
-typedef TileCfg<TFB_PK_GA_ROWS, TFB_PK_GA_CPL> CfgGA;
+#ifndef TFB_PK_GA_W
+#define TFB_PK_GA_W 64
+#endif
+#ifndef TFB_PK_NONE_ROWS
+#define TFB_PK_NONE_ROWS 15
+#endif
+#ifndef TFB_PK_NONE_W
+#define TFB_PK_NONE_W 64
+#endif
+typedef TileCfg<TFB_PK_NONE_ROWS, 1, TFB_PK_NONE_W> CfgNone;
+typedef TileCfg<TFB_PK_GA_ROWS, TFB_PK_GA_CPL, TFB_PK_GA_W> CfgGA;
 typedef TileCfg<15, 2> CfgFull;
 typedef TileCfg<15, 1> CfgDwB;
 

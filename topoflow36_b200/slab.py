@@ -144,23 +144,28 @@ class SlabChannels(object):
         self.exchange_state()
 
     def read_scalars(self):
-        """Global scalar block (collective: every rank must call it)."""
-        s = self.engine.read_scalars()
+        """Global scalar block (collective: every rank must call it).  ONE all-gather
+        of the 28-value blocks, reduced on the device, one device->host copy."""
+        e = self.engine
         if self.layout.world_size == 1:
-            return s
+            return e.read_scalars()
         nf, nc = len(self._SUM_FIELDS), len(self._CNT_FIELDS)
-        v = torch.tensor([getattr(s, n) for n in self._SUM_FIELDS] +
-                         [float(getattr(s, n)) for n in self._CNT_FIELDS],
-                         dtype=torch.float64, device=self.device)
-        dist.all_reduce(v, op=dist.ReduceOp.SUM, group=self.group)
-        m = torch.tensor([s.dt_cfl_min], dtype=torch.float64, device=self.device)
-        dist.all_reduce(m, op=dist.ReduceOp.MIN, group=self.group)
-        h = v.cpu().tolist()
+        f64 = e.scalars_dev.view(torch.float64)          # 20 doubles, then 8 int64
+        i64 = e.scalars_dev.view(torch.int64)
+        mine = torch.cat((f64[:nf + 1], i64[nf + 1:nf + 1 + nc].to(torch.float64)))
+        allv = torch.empty((self.layout.world_size, mine.numel()), dtype=torch.float64,
+                           device=self.device)
+        dist.all_gather_into_tensor(allv, mine, group=self.group)
+        red = allv.sum(0)
+        red[nf] = allv[:, nf].min()                      # dt_cfl_min is a MIN
+        h = red.cpu().tolist()
+        s = L.ChannelsScalars()
         for k, n in enumerate(self._SUM_FIELDS):
             setattr(s, n, h[k])
+        s.dt_cfl_min = h[nf]
         for k, n in enumerate(self._CNT_FIELDS):
-            setattr(s, n, int(h[nf + k]))
-        s.dt_cfl_min = float(m.item())
+            setattr(s, n, int(h[nf + 1 + k]))
+        s.step_count = e.n_steps
         return s
 
     def global_dt_min(self):
