@@ -150,21 +150,24 @@ class SlabChannels(object):
         if self.layout.world_size == 1:
             return e.read_scalars()
         nf, nc = len(self._SUM_FIELDS), len(self._CNT_FIELDS)
-        f64 = e.scalars_dev.view(torch.float64)          # 20 doubles, then 8 int64
-        i64 = e.scalars_dev.view(torch.int64)
-        mine = torch.cat((f64[:nf + 1], i64[nf + 1:nf + 1 + nc].to(torch.float64)))
-        allv = torch.empty((self.layout.world_size, mine.numel()), dtype=torch.float64,
-                           device=self.device)
-        dist.all_gather_into_tensor(allv, mine, group=self.group)
-        red = allv.sum(0)
-        red[nf] = allv[:, nf].min()                      # dt_cfl_min is a MIN
-        h = red.cpu().tolist()
+        raw = e.scalars_dev.view(torch.float64)          # 20 doubles + 8 int64 bit patterns
+        if getattr(self, '_allv', None) is None:
+            self._allv = torch.empty((self.layout.world_size, raw.numel()), dtype=torch.float64,
+                                     device=self.device)
+            self._allh = torch.empty_like(self._allv, device='cpu').pin_memory()
+        dist.all_gather_into_tensor(self._allv, raw, group=self.group)
+        self._allh.copy_(self._allv, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        hf = self._allh.numpy()                          # (world, 28): reduced on the host
+        hi = hf.view('int64')
         s = L.ChannelsScalars()
+        sums = hf[:, :nf].sum(0)
         for k, n in enumerate(self._SUM_FIELDS):
-            setattr(s, n, h[k])
-        s.dt_cfl_min = h[nf]
+            setattr(s, n, float(sums[k]))
+        s.dt_cfl_min = float(hf[:, nf].min())            # a MIN, not a SUM
+        cnts = hi[:, nf + 1:nf + 1 + nc].sum(0)
         for k, n in enumerate(self._CNT_FIELDS):
-            setattr(s, n, int(h[nf + 1 + k]))
+            setattr(s, n, int(cnts[k]))
         s.step_count = e.n_steps
         return s
 
