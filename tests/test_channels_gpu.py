@@ -404,3 +404,49 @@ def test_flood_component_from_cfg(tmp_path, flood_gold):
     assert rel_err(c.get_value_ptr('land_surface_water__depth'), g['kw_d_flood']) <= RTOL
     c.finalize()
     assert abs(float(c.vol_flood_sum) - g['kw_vol_flood'].sum()) <= 1e-11 * g['kw_vol_flood'].sum()
+
+
+@pytest.mark.parametrize('shape', [(1, 4), (2, 8), (15, 64), (16, 68), (31, 132), (47, 260), (100, 60)])
+@pytest.mark.parametrize('kinematic', [True, False])
+def test_packed_path_ragged_shapes(shape, kinematic):
+    """TMA tiles that hang over the grid edge (zero-filled by the TMA unit), grids
+    smaller than one 64 x 15 tile, a single row: packed kinematic (1 launch) and
+    diffusive (2 launches) steps against the numpy oracle, with fused Green-Ampt."""
+    from topoflow36_b200 import cases
+    ny, nx = shape
+    rng = np.random.default_rng(ny * 1000 + nx)
+    DEM = np.float32(100 - 0.3 * np.arange(ny)[:, None] - 0.1 * np.arange(nx)[None, :]
+                     + 0.2 * rng.random((ny, nx)))
+    dx, dy, dd = o.pixel_dims(ny, 30.0, 30.0)
+    code, _ = o.d8_flow_grid(DEM, dx, dy, dd)
+    ds, dw = o.d8_ds_dw(code, dx, dy, dd)
+    with np.errstate(all='ignore'):
+        slope = np.float32(o.d8_slope(DEM, code, ds))
+    if not (slope > 0).any():
+        slope[:] = 0.01
+    width = np.float32(1 + rng.random((ny, nx)))
+    angle = np.float32(rng.choice([0.0, 30.0, 45.0], size=(ny, nx)))
+    nval = np.float32(0.03 + 0.01 * rng.random((ny, nx)))
+    out = (ny // 2, nx // 2)
+    ch = o.Channels(code, ds, dw, slope, width, angle, nval=nval, da=900.0, dt=3.0,
+                    kinematic=kinematic, outlet=out)
+    ch.P_rain = np.array(3e-5)
+    eng = _engine(code, dx, dy, dd, slope, width, angle, nval, dt=3.0, da=900.0,
+                  kinematic=kinematic, outlet=out)
+    eng.set_input('P_rain', 3e-5)
+    eng.enable_fused_sources(infil=True, I0=0.05)
+    for k, v in cases.GA_TREYNOR.items():
+        eng.set_input(k, v)
+    I = np.zeros((ny, nx)) + 0.05
+    for i in range(40):
+        ch.IN, I = o.green_ampt_step(I, ch.P_rain, 0.0, dt=3.0, **cases.GA_TREYNOR)
+        ch.step()
+        eng.step(time_min=i * 3.0 / 60.0)
+    assert eng.last_path == 'packed'
+    _cmp_grids(eng, ch, ('vol', 'd', 'u', 'Q'))
+    assert rel_err(eng.I.cpu().numpy(), I) <= RTOL
+    s = eng.read_scalars()
+    for n in ('vol_R', 'vol_edge', 'vol_Q', 'Q_outlet', 'u_outlet', 'd_outlet', 'f_outlet',
+              'Q_peak', 'T_peak'):
+        want = float(getattr(ch, n))
+        assert abs(getattr(s, n) - want) <= RTOL * max(abs(want), 1e-300), n
