@@ -94,8 +94,11 @@ def test_bmi_surface_and_outputs(tmp_path, treynor):
     shape = np.zeros(2, dtype='int64')
     assert tuple(c.get_grid_shape(0, shape)) == (ny, nx)
     c.set_value(LONG['P_rain'], z(100 / 3.6e6))
-    for _ in range(20):
+    Q_at_60s = None
+    for i in range(20):
         c.update(-1.0)
+        if i == 10:                      # the update that starts at t = 60 s saves a frame
+            Q_at_60s = c.Q.copy()
     dest = np.zeros((ny, nx))
     c.get_value('channel_water_x-section__mean_depth', dest)
     assert dest.max() > 0 and np.array_equal(dest, c.d)
@@ -107,6 +110,10 @@ def test_bmi_surface_and_outputs(tmp_path, treynor):
     c.finalize()
     rts = os.path.join(str(tmp_path), 'June_20_67_2D-Q.rts')
     assert os.path.getsize(rts) == 2 * ny * nx * 4          # frames at t = 0 s and 60 s
+    frames = np.fromfile(rts, dtype='float32').reshape(2, ny, nx)   # written asynchronously
+    assert np.array_equal(frames[1], np.float32(Q_at_60s)) and frames[1].max() > 0
+    last = np.loadtxt(os.path.join(str(tmp_path), 'June_20_67_0D-Q.txt'), skiprows=2)[-1]
+    assert abs(last[0] - 1.0) < 1e-9 and abs(last[1] - Q_at_60s[34, 16]) <= 5e-8
     lines = open(os.path.join(str(tmp_path), 'June_20_67_0D-Q.txt')).read().splitlines()
     assert len(lines) == 2 + 2
     # an absurd time step must abort like the reference (RuntimeError + 'failed')
