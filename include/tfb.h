@@ -293,9 +293,10 @@ typedef struct {
     const float *width32;
     const double *coef;
     const double *angle_lut;  /* n_angles x 4 doubles, DEVICE */
-    const double *row_geom;   /* ny x 6 doubles from tfb_channels_pack_rows: flow
+    const double *row_geom;   /* ny x 8 doubles from tfb_channels_pack_rows: flow
                                  length ds = sinu * {dx, dd, dy} of the row (E/W and
-                                 noflow, diagonal, N/S) and the 3 reciprocals    */
+                                 noflow, diagonal, N/S), the 3 reciprocals, the pixel
+                                 area of the row, padding                        */
     double outlet_rough;      /* Manning n of the outlet cell (f_outlet only)    */
     int32_t n_angles;
     /* diffusive wave only (coef may then be NULL): */
@@ -312,10 +313,12 @@ int tfb_channels_pack_geo32(const uint8_t *code, const uint8_t *angle_idx,
                             uint32_t *geo32, void *stream);
 
 /* per-row flow lengths and their reciprocals (d8_global.py:960-1027 times the
- * scalar sinuosity, channels_base.py:1242); dx, dy, dd = DEVICE float32 (ny) */
+ * scalar sinuosity, channels_base.py:1242) and the pixel area of the row
+ * (utils/pixels.py:173-233); dx, dy, dd = DEVICE float32 (ny); da_row = DEVICE
+ * float64 (ny) or NULL, then `da` applies to every row */
 int tfb_channels_pack_rows(const float *dx, const float *dy, const float *dd,
-                           double sinu, int32_t ny, double *row_geom,
-                           void *stream);
+                           double sinu, const double *da_row, double da,
+                           int32_t ny, double *row_geom, void *stream);
 
 /* one routing step through the packed path; TFB_ERR_ARG when the arguments do
  * not meet the conditions above (the caller then uses tfb_channels_step).

@@ -236,6 +236,44 @@ def gen_attenuate(work):
     np.savez_compressed(os.path.join(GOLD, 'attenuate_channels.npz'), **out)
 
 
+def gen_geographic(work):
+    """Fixed-angle (geographic) pixels, 1 arcsec at 41-42 N: per-row dx / dd / ds / dw and
+    a per-cell area grid da (utils/pixels.py:71-233).  D8 + KW and DW routing."""
+    import topoflow.components.d8_global as d8g
+    ny, nx = 75, 64
+    DEM = synth.fractal_dem(ny, nx, seed=31, sigma=1.0, dx=23.0, dy=31.0)
+    width, angle, nval = synth.channel_params(ny, nx, seed=31)
+    out = dict(DEM=DEM, width=width, angle=angle, nval=nval)
+    for kin in (True, False):
+        tag = 'kw' if kin else 'dw'
+        cdir = os.path.join(work, 'geo_' + tag)
+        cfg = synth.write_case(cdir, DEM, np.zeros_like(DEM), width, angle, nval=nval, dx=1.0, dy=1.0,
+                               dt=2.0, kinematic=kin, outlet=(ny - 2, nx // 2),
+                               geographic=(41.0, -95.7))
+        d8 = d8g.d8_component()
+        rh.quiet_call(d8.initialize, cfg_file=os.path.join(cdir, 'Case1_d8_global.cfg'),
+                      SILENT=True, REPORT=False)
+        rh.quiet_call(d8.update, 0)
+        d8.update_noflow_IDs()
+        d8.update_slope_grid()
+        info = grid_io.read_rti(os.path.join(cdir, 'Synth.rti'))
+        grid_io.write_rtg(os.path.join(cdir, 'Synth_slope.rtg'), d8.S, info)
+        if kin:
+            out.update(code=np.array(d8.d8_grid), slope=np.float32(d8.S), ds32=np.float32(d8.ds),
+                       dw32=np.float32(d8.dw), area=np.float32(d8.A), dx=np.float32(d8.dx),
+                       dy=np.float32(d8.dy), dd=np.float32(d8.dd), da=np.float64(d8.da))
+        c = standalone_channels(cfg, kin, dict(
+            P_rain=z(100 / 3.6e6), MR=z(0), GW=z(0), SM=z(0), rho_H2O=z(1000.0), ET=z(0), IN=z(0)))
+        assert np.ndim(c.da) == 2
+        for i in range(120):
+            if i == 80:
+                c.set_value(LONG['P_rain'], z(0))
+            rh.quiet_call(c.update)
+        for k, v in snapshot(c).items():
+            out[tag + '_' + k] = v
+    np.savez_compressed(os.path.join(GOLD, 'geo_channels.npz'), **out)
+
+
 def gen_d8(work):
     """D8 toolkit on a DEM with plenty of ties and flats (elevations quantised
     to 0.25 m) and a few nodata cells; LINK_FLATS on and off."""
@@ -453,6 +491,7 @@ def main():
         gen_synth_channels(work)
         gen_flood(work)
         gen_attenuate(work)
+        gen_geographic(work)
         gen_d8(work)
         gen_sources()
         gen_met_energy()

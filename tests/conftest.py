@@ -67,3 +67,8 @@ def met_gold():
 @pytest.fixture(scope='session')
 def attenuate_gold():
     return load_golden('attenuate_channels.npz')
+
+
+@pytest.fixture(scope='session')
+def geo_gold():
+    return load_golden('geo_channels.npz')

@@ -450,3 +450,36 @@ def test_packed_path_ragged_shapes(shape, kinematic):
               'Q_peak', 'T_peak'):
         want = float(getattr(ch, n))
         assert abs(getattr(s, n) - want) <= RTOL * max(abs(want), 1e-300), n
+
+
+@pytest.mark.parametrize('tag', ['kw', 'dw'])
+def test_geographic_pixels_vs_reference_fixture(geo_gold, tag):
+    """Fixed-angle (geographic) pixels: per-row dx / dd and a per-cell area grid, D8
+    toolkit and routing against a stand-alone REFERENCE run."""
+    import torch
+    from topoflow36_b200.d8 import D8Toolkit
+    from topoflow36_b200.routing import ChannelsEngine
+    g = geo_gold
+    ny, nx = g['DEM'].shape
+    tk = D8Toolkit(g['DEM'], dx=g['dx'], dy=g['dy'], dd=g['dd'], da=g['da'])
+    tk.update()
+    assert np.array_equal(tk.code.cpu().numpy(), g['code'])
+    assert np.array_equal(tk.ds.cpu().numpy(), g['ds32'])
+    assert np.array_equal(tk.dw.cpu().numpy(), g['dw32'])
+    assert np.array_equal(tk.A.cpu().numpy(), g['area'])
+    assert np.array_equal(tk.slope().cpu().numpy(), g['slope'])
+    kin = (tag == 'kw')
+    for diag in (True, False):
+        eng = _engine(g['code'], g['dx'], g['dy'], g['dd'], g['slope'], g['width'], g['angle'],
+                      g['nval'], dt=2.0, da=g['da'], kinematic=kin, diag=diag,
+                      outlet=(ny - 2, nx // 2))
+        eng.set_input('P_rain', 100 / 3.6e6)
+        for i in range(120):
+            if i == 80:
+                eng.set_input('P_rain', 0.0)
+            eng.step(time_min=(i * 2.0) / 60.0)
+        want = {n: g[tag + '_' + n] for n in GRIDS + SCALARS}
+        _cmp_grids(eng, want, GRIDS if diag else ('vol', 'd', 'u', 'Q'))
+        _cmp_scalars(eng, want)
+        if not diag:
+            assert eng.last_path == 'packed'       # per-row pixel areas ride the fast path too

@@ -217,3 +217,43 @@ def test_attenuate_bit_exact(flood_gold, attenuate_gold, tag):
         assert np.array_equal(getattr(ch, n), g[tag + '_' + n], equal_nan=True), n
     for n in SCALARS:
         assert float(getattr(ch, n)) == float(g[tag + '_' + n]), n
+
+
+def _geo_info(tmp_path, ny, nx):
+    # through the RTI file, like the reference run that produced the fixture (the header
+    # keeps 12 decimals of the box edges)
+    from topoflow36_b200 import grid_io
+    info = grid_io.make_rti(nx, ny, 1.0, 1.0, pixel_geom=0, y_south_edge=41.0, x_west_edge=-95.7)
+    grid_io.write_rti(str(tmp_path / 'geo.rti'), info)
+    return grid_io.read_rti(str(tmp_path / 'geo.rti'))
+
+
+def test_geographic_pixels_bit_exact(geo_gold, tmp_path):
+    """Fixed-angle pixels: per-row dx/dd, per-cell da (utils/pixels.py:71-233) through
+    the D8 toolkit and both wave types -- numpy restatement == reference run."""
+    from topoflow36_b200 import grid_io
+    g = geo_gold
+    ny, nx = g['DEM'].shape
+    info = _geo_info(tmp_path, ny, nx)
+    dx, dy, dd = (np.float32(v) for v in grid_io.pixel_sizes_by_row(info))
+    assert np.array_equal(dx, g['dx']) and np.array_equal(dy, g['dy']) and np.array_equal(dd, g['dd'])
+    da = grid_io.pixel_area(info)
+    assert np.array_equal(da, g['da'])
+    code, _ = o.d8_flow_grid(g['DEM'], dx, dy, dd)
+    assert np.array_equal(code, g['code'])
+    ds32, dw32 = o.d8_ds_dw(code, dx, dy, dd)
+    assert np.array_equal(ds32, g['ds32']) and np.array_equal(dw32, g['dw32'])
+    with np.errstate(all='ignore'):
+        assert np.array_equal(np.float32(o.d8_slope(g['DEM'], code, ds32)), g['slope'])
+    for tag in ('kw', 'dw'):
+        ch = o.Channels(code, ds32, dw32, g['slope'], g['width'], g['angle'], nval=g['nval'],
+                        da=da, dt=2.0, kinematic=(tag == 'kw'), outlet=(ny - 2, nx // 2))
+        ch.P_rain = np.array(100 / 3.6e6)
+        for i in range(120):
+            if i == 80:
+                ch.P_rain = np.array(0.0)
+            ch.step()
+        for n in GRIDS:
+            assert np.array_equal(getattr(ch, n), g[tag + '_' + n], equal_nan=True), n
+        for n in SCALARS:
+            assert float(getattr(ch, n)) == float(g[tag + '_' + n]), n

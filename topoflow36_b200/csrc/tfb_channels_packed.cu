@@ -50,7 +50,8 @@ enum { PK_KW = 0, PK_DWA = 1 };                              // main-kernel vari
 
 struct PkConsts {
     double g, dt, da;
-    double Rdadt;            // no fused source: (R*da)*dt, uniform
+    double Runi;             // no fused source: the uniform runoff rate R
+    int r_grid;              // accumulate vol_R per cell (pixel area varies by row)
     double Psum;             // ((P_rain + SM) + GW) + MR
     double P_total;          // P_rain + SM
     double Ks, gkq;          // Green-Ampt: Ks, (G*(Ks-Ki))*(qs-qi)
@@ -64,15 +65,20 @@ struct PkConsts {
     double Qc, Qnet, alpha;                      // K_soil (T_surf - T_soil_x) / soil_x, Qn_SW + Qn_LW
 };
 
+constexpr int kRowGeom = 8;      // doubles per row: ds x3, 1/ds x3, da, pad
+
 __global__ void pack_rows_kernel(const float *__restrict__ dx, const float *__restrict__ dy,
-                                 const float *__restrict__ dd, double sinu, int ny,
+                                 const float *__restrict__ dd, double sinu,
+                                 const double *__restrict__ da_row, double da, int ny,
                                  double *__restrict__ rg) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= ny) return;
     const double ds0 = sinu * (double)dx[r], ds1 = sinu * (double)dd[r], ds2 = sinu * (double)dy[r];
-    double *o = rg + (int64_t)r * 6;
+    double *o = rg + (int64_t)r * kRowGeom;
     o[0] = ds0; o[1] = ds1; o[2] = ds2;
     o[3] = 1.0 / ds0; o[4] = 1.0 / ds1; o[5] = 1.0 / ds2;
+    o[6] = da_row ? da_row[r] : da;
+    o[7] = 0.0;
 }
 
 __global__ void __launch_bounds__(256)
@@ -202,7 +208,8 @@ struct PkVD { double v, d, I, h; };    // new volume / depth before the noflow z
 template <int SRC>
 __device__ __forceinline__ void pk_vol_depth(const PkConsts &k, const double *__restrict__ lut,
                                              const PkIn &x, const double2 g0, const double2 g1,
-                                             const double2 g2, Acc &acc, PkVD &o) {
+                                             const double2 g2, const double da, Acc &acc,
+                                             PkVD &o) {
     const unsigned code = x.g & 0xffu, cmask = (x.g >> 8) & 0xffu, ai = (x.g >> 16) & 0xffu;
     // row_geom = {ds_ew, ds_diag, ds_ns, 1/ds_ew, 1/ds_diag, 1/ds_ns}
     const bool dg = (code & 0x55u) != 0u, ns = (code & 0x88u) != 0u;
@@ -216,10 +223,10 @@ __device__ __forceinline__ void pk_vol_depth(const PkConsts &k, const double *__
         double IN = np_min(fc, k.P_total);                            // :567
         if (k.low_rain) IN = k.P_total;                               // infil_base :984-993
         o.I = x.I + (IN * dt);                                        // :797
-        acc.s[S_VOL_IN] += (IN * k.da) * dt;                          // :732-736
+        acc.s[S_VOL_IN] += (IN * da) * dt;                          // :732-736
         if (!isfinite(IN)) acc.n[S_NNAN_IN - kNSum] += 1u;
         const double R = k.Psum - (0.0 + IN);                         // channels_base :1649
-        const double Rv = (R * k.da) * dt;
+        const double Rv = (R * da) * dt;
         acc.s[S_VOL_R] += Rv;                                         // :1666-1670
         v = x.vol + Rv;                                               // :2086
     } else if (SRC == PK_SRC_FULL) {
@@ -229,9 +236,9 @@ __device__ __forceinline__ void pk_vol_depth(const PkConsts &k, const double *__
         if (k.flags & TFB_CH_SRC_MET) {                               // met_base :1300-1388
             P_rain = k.P * ((Ta > k.T_rs) ? 1.0 : 0.0);
             P_snow = k.P * ((Ta <= k.T_rs) ? 1.0 : 0.0);
-            acc.s[S_VOL_P] += (k.P * k.da) * dt;
-            acc.s[S_VOL_PR] += (P_rain * k.da) * dt;
-            acc.s[S_VOL_PS] += (P_snow * k.da) * dt;
+            acc.s[S_VOL_P] += (k.P * da) * dt;
+            acc.s[S_VOL_PR] += (P_rain * da) * dt;
+            acc.s[S_VOL_PS] += (P_snow * da) * dt;
         }
         if (k.flags & TFB_CH_SRC_SNOW) {                              // snow_degree_day :293-360
             double M = k.c0_864 * (Ta - k.T0);
@@ -241,13 +248,13 @@ __device__ __forceinline__ void pk_vol_depth(const PkConsts &k, const double *__
             double hn = x.h + (P_snow * dt);                          // snow_base :559-609
             hn = hn - (M * dt);
             o.h = np_max0(hn);
-            acc.s[S_VOL_SM] += (M * k.da) * dt;
+            acc.s[S_VOL_SM] += (M * da) * dt;
         }
         if (k.flags & TFB_CH_SRC_EVAP) {                              // evap_priestley_taylor :308-413
             const double Qet = (k.alpha * (0.406 + (0.011 * Ta))) * (k.Qnet + k.Qc);
             ET = np_max0(Qet / 2.5E+9);
             et_grid = true;
-            acc.s[S_VOL_ET] += (ET * k.da) * dt;
+            acc.s[S_VOL_ET] += (ET * da) * dt;
         }
         if (k.flags & TFB_CH_SRC_INFIL) {                             // infil_green_ampt :511-578
             const double P_total = P_rain + SM;
@@ -255,20 +262,22 @@ __device__ __forceinline__ void pk_vol_depth(const PkConsts &k, const double *__
             IN = np_min(fc, P_total);
             if (P_total < k.Ks) IN = P_total;
             o.I = x.I + (IN * dt);
-            acc.s[S_VOL_IN] += (IN * k.da) * dt;
+            acc.s[S_VOL_IN] += (IN * da) * dt;
             if (!isfinite(IN)) acc.n[S_NNAN_IN - kNSum] += 1u;
         }
         if (et_grid) {                                                // channels_base :1625-1629
-            if (x.vol < ((ET * k.da) * dt)) ET = 0.0;
+            if (x.vol < ((ET * da) * dt)) ET = 0.0;
         } else {
             ET = 0.0;
         }
         const double R = (((P_rain + SM) + k.GW) + k.MR) - (ET + IN);
-        const double Rv = (R * k.da) * dt;
+        const double Rv = (R * da) * dt;
         acc.s[S_VOL_R] += Rv;
         v = x.vol + Rv;
     } else {
-        v = x.vol + k.Rdadt;
+        const double Rv = (k.Runi * da) * dt;
+        if (k.r_grid) acc.s[S_VOL_R] += Rv;                           // :1666-1670 (da varies)
+        v = x.vol + Rv;
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) add_if(v, cmask, 1u << j, dt * x.ch[j]);   // :2116-2131
@@ -505,10 +514,11 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
                 x.ch[0] = q[2 * kQW]; x.ch[1] = q[kQW]; x.ch[2] = q[0]; x.ch[3] = q[1];
                 x.ch[4] = q[2]; x.ch[5] = q[kQW + 2]; x.ch[6] = q[2 * kQW + 2]; x.ch[7] = q[2 * kQW + 1];
                 x.qself = q[kQW + 1];
-                const double2 *rgp = reinterpret_cast<const double2 *>(p.row_geom + (int64_t)r * 6);
+                const double2 *rgp = reinterpret_cast<const double2 *>(p.row_geom + (int64_t)r * kRowGeom);
                 const double2 g0 = __ldg(rgp), g1 = __ldg(rgp + 1), g2 = __ldg(rgp + 2);
+                const double da_r = __ldg(rgp + 3).x;
                 PkVD o;
-                pk_vol_depth<SRC>(k, lut, x, g0, g1, g2, acc, o);
+                pk_vol_depth<SRC>(k, lut, x, g0, g1, g2, da_r, acc, o);
                 const int64_t i = (int64_t)r * a.nx + c0;
                 const bool nf = (x.g & 0xffu) == 0u;
                 if (kKW) {
@@ -553,8 +563,9 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
                 const double2 b1 = *reinterpret_cast<const double2 *>(q + 2 * kQW + 2);
                 // columns: *0.y = c0-1, *1.x = c0, *1.y = c0+1, *E = c0+2
                 const double aE = q[4], mE = q[kQW + 4], bE = q[2 * kQW + 4];
-                const double2 *rgp = reinterpret_cast<const double2 *>(p.row_geom + (int64_t)r * 6);
+                const double2 *rgp = reinterpret_cast<const double2 *>(p.row_geom + (int64_t)r * kRowGeom);
                 const double2 g0 = __ldg(rgp), g1 = __ldg(rgp + 1), g2 = __ldg(rgp + 2);
+                const double da_r = __ldg(rgp + 3).x;
                 const int64_t i = (int64_t)r * a.nx + c0;
                 PkVD o0, o1;
                 double u0 = 0.0, u1 = 0.0, Q0 = 0.0, Q1 = 0.0;
@@ -565,7 +576,7 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
                     x.qself = m1.x;
                     x.ch[0] = b0.y; x.ch[1] = m0.y; x.ch[2] = a0.y; x.ch[3] = a1.x;
                     x.ch[4] = a1.y; x.ch[5] = m1.y; x.ch[6] = b1.y; x.ch[7] = b1.x;
-                    pk_vol_depth<SRC>(k, lut, x, g0, g1, g2, acc, o0);
+                    pk_vol_depth<SRC>(k, lut, x, g0, g1, g2, da_r, acc, o0);
                     if (kKW) {
                         const bool dg = (geo.x & 0x55u) != 0u, ns = (geo.x & 0x88u) != 0u;
                         pk_velocity(a, k, lut, geo.x, o0.d, x.w, coef.x, dg ? g2.x : (ns ? g2.y : g1.y),
@@ -578,7 +589,7 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
                     x.qself = m1.y;
                     x.ch[0] = b1.x; x.ch[1] = m1.x; x.ch[2] = a1.x; x.ch[3] = a1.y;
                     x.ch[4] = aE; x.ch[5] = mE; x.ch[6] = bE; x.ch[7] = b1.y;
-                    pk_vol_depth<SRC>(k, lut, x, g0, g1, g2, acc, o1);
+                    pk_vol_depth<SRC>(k, lut, x, g0, g1, g2, da_r, acc, o1);
                     if (kKW) {
                         const bool dg = (geo.y & 0x55u) != 0u, ns = (geo.y & 0x88u) != 0u;
                         pk_velocity(a, k, lut, geo.y, o1.d, x.w, coef.y, dg ? g2.x : (ns ? g2.y : g1.y),
@@ -692,7 +703,7 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
                 int dr, dcol;
                 code_offset(code, dr, dcol);
                 const double d_par = dc[dr * kQW + dcol];                 // new depth of the D8 parent
-                const double2 *rgp = reinterpret_cast<const double2 *>(p.row_geom + (int64_t)r * 6);
+                const double2 *rgp = reinterpret_cast<const double2 *>(p.row_geom + (int64_t)r * kRowGeom);
                 const double2 g1 = __ldg(rgp + 1), g2 = __ldg(rgp + 2);
                 const bool dg = (code & 0x55u) != 0u, ns = (code & 0x88u) != 0u;
                 const double inv_ds = dg ? g2.x : (ns ? g2.y : g1.y);
@@ -721,7 +732,7 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
                 const double *dT = reinterpret_cast<const double *>(st + SL::oD);
                 const double *dc = dT + (row + 1) * kQW + ct + 2;
                 const double2 dv = *reinterpret_cast<const double2 *>(dc);
-                const double2 *rgp = reinterpret_cast<const double2 *>(p.row_geom + (int64_t)r * 6);
+                const double2 *rgp = reinterpret_cast<const double2 *>(p.row_geom + (int64_t)r * kRowGeom);
                 const double2 g1 = __ldg(rgp + 1), g2 = __ldg(rgp + 2);
                 const int64_t i = (int64_t)r * a.nx + c0;
                 double uo[2], Qo[2], dd_[2];
@@ -774,10 +785,11 @@ extern "C" int tfb_channels_pack_geo32(const uint8_t *code, const uint8_t *angle
 }
 
 extern "C" int tfb_channels_pack_rows(const float *dx, const float *dy, const float *dd,
-                                      double sinu, int32_t ny, double *row_geom, void *stream) {
+                                      double sinu, const double *da_row, double da, int32_t ny,
+                                      double *row_geom, void *stream) {
     TFB_ARG_CHECK(dx && dy && dd && row_geom && ny > 0);
-    pack_rows_kernel<<<(ny + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dx, dy, dd, sinu, ny,
-                                                                       row_geom);
+    pack_rows_kernel<<<(ny + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dx, dy, dd, sinu, da_row,
+                                                                       da, ny, row_geom);
     TFB_CUDA_CHECK(cudaGetLastError());
     return TFB_OK;
 }
@@ -935,7 +947,7 @@ int prepare(const tfb_channels_step_args *ap, const tfb_channels_packed *pp, boo
     TFB_ARG_CHECK(((a.flags & TFB_CH_DIFFUSIVE) != 0) == diffusive);
     if (diffusive) TFB_ARG_CHECK(p.inv_rough && p.S32 && a.halo != 0 ? a.halo >= 1 : true);
     else TFB_ARG_CHECK(p.coef != nullptr);
-    TFB_ARG_CHECK(!a.sinu.ptr && !a.da.ptr);
+    TFB_ARG_CHECK(!a.sinu.ptr);      // the pixel area comes from row_geom (scalar or per row)
     TFB_ARG_CHECK(!a.P_rain.ptr && !a.SM.ptr && !a.GW.ptr && !a.MR.ptr && !a.ET.ptr && !a.IN.ptr);
     auto al16 = [](const void *q) { return (((uintptr_t)q) & 15u) == 0; };
     TFB_ARG_CHECK(al16(a.vol) && al16(a.vol_out) && al16(a.Q_in) && al16(a.Q_out) && al16(a.d) &&
@@ -952,9 +964,9 @@ int prepare(const tfb_channels_step_args *ap, const tfb_channels_packed *pp, boo
     k.n_tiles = 0;                                   // set per tile configuration by the launcher
     k.flags = src;
     if (src == 0) {
-        TFB_ARG_CHECK(a.is_R_grid == 0);
-        const double R = k.Psum - (0.0 + a.IN.val);
-        k.Rdadt = (R * a.da.val) * a.dt;
+        TFB_ARG_CHECK((a.is_R_grid != 0) == (a.da.ptr != nullptr));
+        k.Runi = k.Psum - (0.0 + a.IN.val);
+        k.r_grid = a.is_R_grid ? 1 : 0;
         src_mode = PK_SRC_NONE;
         return TFB_OK;
     }

@@ -89,7 +89,9 @@ def read_rti(path):
 def make_rti(ncols, nrows, xres, yres, data_type='FLOAT', byte_order=None,
              pixel_geom=1, grid_file='grid.rtg', y_south_edge=0.0,
              x_west_edge=0.0, gmin=-9999.0, gmax=-9999.0):
-    """Header for a new grid (fixed-length pixels by default: xres, yres [m])."""
+    """Header for a new grid: fixed-length pixels (pixel_geom 1: xres, yres [m]) or
+    fixed-angle pixels (pixel_geom 0: xres, yres [arcsec], edges in degrees)."""
+    unit = 1.0 if int(pixel_geom) == 1 else 1.0 / 3600.0
     info = SimpleNamespace(
         grid_file=grid_file, data_source='Unknown', ncols=int(ncols),
         nrows=int(nrows), data_type=data_type.upper(),
@@ -97,9 +99,10 @@ def make_rti(ncols, nrows, xres, yres, data_type='FLOAT', byte_order=None,
         pixel_geom=int(pixel_geom), xres=np.float64(xres), yres=np.float64(yres),
         zres=np.float32(1.0), z_units='METERS',
         y_south_edge=np.float64(y_south_edge),
-        y_north_edge=np.float64(y_south_edge + nrows * yres),
-        x_east_edge=np.float64(x_west_edge + ncols * xres),
-        x_west_edge=np.float64(x_west_edge), box_units='METERS',
+        y_north_edge=np.float64(y_south_edge + nrows * yres * unit),
+        x_east_edge=np.float64(x_west_edge + ncols * xres * unit),
+        x_west_edge=np.float64(x_west_edge),
+        box_units='METERS' if int(pixel_geom) == 1 else 'DEGREES',
         gmin=np.float32(gmin), gmax=np.float32(gmax), UTM_zone='UNKNOWN')
     return _finish_info(info)
 

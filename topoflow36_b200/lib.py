@@ -137,7 +137,7 @@ SIGNATURES = {
     'tfb_channels_step': (C.c_int, [C.POINTER(ChannelsStepArgs), vp]),
     'tfb_sizeof_channels_packed': (_i64, []),
     'tfb_channels_pack_geo32': (C.c_int, [vp, vp, _i32, _i32, _i32, vp, vp]),
-    'tfb_channels_pack_rows': (C.c_int, [vp, vp, vp, _f64, _i32, vp, vp]),
+    'tfb_channels_pack_rows': (C.c_int, [vp, vp, vp, _f64, vp, _f64, _i32, vp, vp]),
     'tfb_channels_step_packed': (C.c_int, [C.POINTER(ChannelsStepArgs),
                                            C.POINTER(ChannelsPacked), vp]),
     'tfb_channels_step_packed_dw_a': (C.c_int, [C.POINTER(ChannelsStepArgs),

@@ -214,7 +214,7 @@ class ChannelsEngine(object):
         if ((not self.manning) or self.diag or self.flood or self.attenuate
                 or (self.flags & L.CH_WRITE_R)):
             return
-        if self.nx % 4 or self.sinu_grid is not None or self._da_is_grid:
+        if self.nx % 4 or self.sinu_grid is not None:
             return
         dev = self.device
         full = lambda g, v: (self.own(g) if g is not None
@@ -260,9 +260,11 @@ class ChannelsEngine(object):
                                                  None if aidx is None else aidx.data_ptr(), self.ny,
                                                  self.nx, self.halo, geo32.data_ptr(),
                                                  L.stream_ptr()), 'tfb_channels_pack_geo32')
-        rowg = torch.empty((self.ny, 6), dtype=torch.float64, device=dev)
+        rowg = torch.empty((self.ny, 8), dtype=torch.float64, device=dev)
         L.check(self.lib.tfb_channels_pack_rows(self._prow(self.dx), self._prow(self.dy),
-                                                self._prow(self.dd), float(a.sinu.val), self.ny,
+                                                self._prow(self.dd), float(a.sinu.val),
+                                                self._prow(self.da_rows) if self._da_is_grid
+                                                else None, float(a.da.val), self.ny,
                                                 rowg.data_ptr(), L.stream_ptr()),
                 'tfb_channels_pack_rows')
         orow = a.outlet_row - self.row0

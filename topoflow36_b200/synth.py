@@ -135,15 +135,19 @@ def write_case(case_dir, DEM, slope, width, angle, nval=None, z0val=None,
                kinematic=True, manning=True, link_flats=1, outlet=None,
                n_steps=100, d0=0.0, sinu=1.0, scalar_angle=None,
                scalar_width=None, check_stability='Yes', byte_order=None, flood=False,
-               d_bankfull=None, attenuate_days=None):
+               d_bankfull=None, attenuate_days=None, geographic=None):
     """Write a stand-alone routing case into `case_dir` (all files side by
     side; in_directory = out_directory = '.').  Returns the channels CFG path."""
     os.makedirs(case_dir, exist_ok=True)
     ny, nx = DEM.shape
     finite = DEM[np.isfinite(DEM)]
+    geo = {}
+    if geographic is not None:
+        # fixed-angle pixels: dx, dy in arcseconds, (south edge [deg N], west edge [deg E])
+        geo = dict(pixel_geom=0, y_south_edge=geographic[0], x_west_edge=geographic[1])
     info = grid_io.make_rti(nx, ny, dx, dy, byte_order=byte_order,
                             grid_file=site + '_DEM.rtg',
-                            gmin=float(finite.min()), gmax=float(finite.max()))
+                            gmin=float(finite.min()), gmax=float(finite.max()), **geo)
     p = lambda name: os.path.join(case_dir, name)
     grid_io.write_rti(p(site + '.rti'), info)
     grid_io.write_rtg(p(site + '_DEM.rtg'), DEM, info)
