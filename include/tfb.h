@@ -339,6 +339,39 @@ int tfb_channels_step_packed_dw_a(const tfb_channels_step_args *a,
 int tfb_channels_step_packed_dw_b(const tfb_channels_step_args *a,
                                   const tfb_channels_packed *p, void *stream);
 
+/* ---- peer-memory halo (NVLink / NVSwitch) ----------------------------------
+ * One process per GPU; the slabs' discharge buffers are allocated with
+ * tfb_peer_alloc, their CUDA-IPC handles exchanged by the host, and the
+ * neighbours' halo rows mapped with tfb_peer_open.  tfb_channels_step_packed_p2p
+ * then fuses the halo exchange into the routing kernel: the warps that compute
+ * the first / last owned row store the new discharge ALSO into the neighbour's
+ * halo row (peer stores over NVLink, overlapped with the rest of the grid), and
+ * the last CTA publishes "step k done" in a flag word in the neighbour's memory.
+ * Before a step is launched the stream waits (cuStreamWaitValue32, no spinning
+ * kernel) until both neighbours have finished the previous step -- which orders
+ * both the halo reads and the re-use of the double-buffered halo rows.  No NCCL
+ * call per step.  Kinematic wave only (the diffusive wave keeps NCCL). */
+typedef struct {
+    double *up_Q;             /* neighbour above: its LOWER halo row of the buffer this
+                                 step writes (row ny_up of its owned rows), or NULL   */
+    double *down_Q;           /* neighbour below: its UPPER halo row (row -1), or NULL */
+    uint32_t *up_flag;        /* word in the neighbour's memory: steps I have completed */
+    uint32_t *down_flag;
+    const uint32_t *from_up;  /* LOCAL words the neighbours write (NULL: no neighbour) */
+    const uint32_t *from_down;
+    uint32_t step;            /* 0-based index of this step                            */
+} tfb_peer_halo;
+
+int64_t tfb_sizeof_peer_halo(void);
+/* cudaMalloc + zero fill + IPC handle (64 bytes) of a buffer peers may map */
+int tfb_peer_alloc(int64_t bytes, void **ptr, uint8_t *handle64);
+int tfb_peer_open(const uint8_t *handle64, void **ptr);
+int tfb_peer_close(void *ptr);
+int tfb_peer_free(void *ptr);
+int tfb_channels_step_packed_p2p(const tfb_channels_step_args *a,
+                                 const tfb_channels_packed *p,
+                                 const tfb_peer_halo *peer, void *stream);
+
 /* multi-GPU: fold globally reduced sums (DEVICE, TFB_NSUM doubles laid out as
  * tfb_channels_step leaves them in partials[]) into the scalar block */
 int tfb_channels_fold(const tfb_channels_step_args *a, const double *sums,

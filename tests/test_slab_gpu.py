@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, kinematic, infil, q, devgen=False):
+def _worker(rank, world, port, kinematic, infil, q, devgen=False, p2p=False):
     import torch
     import torch.distributed as dist
     from topoflow36_b200 import cases
@@ -39,7 +39,9 @@ def _worker(rank, world, port, kinematic, infil, q, devgen=False):
             lay = slab.layout
         else:
             slab, parts = cases.build_engine(ny, nx, kinematic=kinematic, infil=infil, rank=rank,
-                                             world=world, device=dev, return_parts=True, dt=2.0)
+                                             world=world, device=dev, return_parts=True, dt=2.0,
+                                             p2p=p2p)
+            assert (slab.peer is not None) == bool(p2p)
             one = cases.build_engine(ny * world, nx, kinematic=kinematic, infil=infil, device=dev,
                                      tile_rows=ny, dt=2.0)
             lay = parts['layout']
@@ -77,9 +79,12 @@ def _worker(rank, world, port, kinematic, infil, q, devgen=False):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('kinematic,infil,devgen', [(True, False, False), (True, True, False),
-                                                    (False, False, False), (True, True, True)])
-def test_two_slabs_equal_one_grid(kinematic, infil, devgen):
+@pytest.mark.parametrize('kinematic,infil,devgen,p2p', [
+    (True, False, False, False), (True, True, False, False), (False, False, False, False),
+    (True, True, True, False), (True, False, False, True), (True, True, False, True)])
+def test_two_slabs_equal_one_grid(kinematic, infil, devgen, p2p):
+    """p2p = True: the halo rows travel through NVLink peer stores inside the routing
+    kernel (tfb_channels_step_packed_p2p) instead of NCCL send/recv."""
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
@@ -88,7 +93,7 @@ def test_two_slabs_equal_one_grid(kinematic, infil, devgen):
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, kinematic, infil, q, devgen))
+    procs = [ctx.Process(target=_worker, args=(r, world, port, kinematic, infil, q, devgen, p2p))
              for r in range(world)]
     for p in procs:
         p.start()

@@ -185,7 +185,7 @@ def build_engine_device(ny, nx, kinematic=True, infil=False, dt=1.0, rank=0, wor
 
 def build_engine(ny, nx, kinematic=True, infil=False, diag=False, dt=1.0, rank=0, world=1,
                  seed=1234, device=None, group=None, link_flats=True, return_parts=False,
-                 tile_rows=None, sources=None):
+                 tile_rows=None, sources=None, p2p=False):
     """Engine (and SlabChannels wrapper when world > 1) for rank `rank` of a
     (world*ny, nx) synthetic grid."""
     import torch
@@ -202,15 +202,20 @@ def build_engine(ny, nx, kinematic=True, infil=False, diag=False, dt=1.0, rank=0
     width, angle, nval = slab_params(ny, nx, lay.row0, halo, seed=seed)
     DEG = np.pi / np.float64(180)
     ang = np.float64(angle) * DEG
+    peer = None
+    if p2p and world > 1 and kinematic:
+        from .slab import PeerHalos
+        peer = PeerHalos(lay, device, group)
     eng = ChannelsEngine(ny, nx, dt=dt, code=d8['code'], dx=d8['dx'], dy=d8['dy'], dd=d8['dd'],
                          S_bed=d8['S_bed'], width=np.float64(width), angle=ang,
                          rough=np.float64(nval), kinematic=kinematic, diag=diag,
                          outlet=(ny_global - 2, nx // 2), row0=lay.row0, ny_global=ny_global,
                          halo=halo, device=device, finalize=True,
-                         n_pixels_global=ny * nx)
+                         n_pixels_global=ny * nx,
+                         q_buffers=None if peer is None else peer.q_buffers)
     apply_sources(eng, sources or ('ga' if infil else 'none'), row0=lay.row0, halo=halo, seed=seed)
     torch.cuda.current_stream().synchronize()
-    stepper = SlabChannels(lay, eng, group) if world > 1 else eng
+    stepper = SlabChannels(lay, eng, group, peer=peer) if world > 1 else eng
     if return_parts:
         return stepper, dict(DEM=DEM, d8=d8, width=width, angle=angle, nval=nval, layout=lay)
     return stepper

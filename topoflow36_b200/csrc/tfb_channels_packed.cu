@@ -336,6 +336,7 @@ __device__ __forceinline__ void pk_velocity(const tfb_channels_step_args &a, con
 }
 
 struct PkMaps { CUtensorMap Q, vol, coef, I, H, T, w, geo; };
+struct PkPeer { double *up_Q, *down_Q; uint32_t *up_flag, *down_flag; uint32_t value; };
 struct PkMapsB { CUtensorMap D, N, S, w, geo; };
 
 // CTA-level reduction of the per-thread accumulators, per-CTA row, last-CTA fold in
@@ -343,7 +344,7 @@ struct PkMapsB { CUtensorMap D, N, S, w, geo; };
 // status only (pass B).
 template <int NWARPS>
 __device__ __forceinline__ void pk_finish(const tfb_channels_step_args &a, Acc &acc, float rate_max,
-                                          bool consumer, int fail, int mode,
+                                          bool consumer, int fail, int mode, const PkPeer &peer,
                                           double (*sm)[kPartialStride], double *tot, bool *is_last) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (consumer) {
@@ -377,7 +378,8 @@ __device__ __forceinline__ void pk_finish(const tfb_channels_step_args &a, Acc &
         if (tid == S_NNAN_D && fail) v += 1.0e9;          // pipeline failure poisons the step
         a.partials[(int64_t)(blockIdx.x + 2) * kPartialStride + tid] = v;
     }
-    __threadfence();
+    if (peer.up_Q || peer.down_Q) __threadfence_system();   // peer halo stores are visible
+    else __threadfence();
     __syncthreads();
     if (tid == 0) {
         const unsigned tk = atomicAdd(a.ticket, 1u);
@@ -417,6 +419,14 @@ __device__ __forceinline__ void pk_finish(const tfb_channels_step_args &a, Acc &
             else { fold_status(a, h); mirror_scalars(a); }
         }
         a.ticket[0] = 0u;                                 // re-arm for the next launch
+        // every CTA has fenced its peer stores before taking a ticket: tell the
+        // neighbours that this step's halo rows are in their memory
+        if (peer.up_flag || peer.down_flag) {
+            __threadfence_system();
+            if (peer.up_flag) *reinterpret_cast<volatile uint32_t *>(peer.up_flag) = peer.value;
+            if (peer.down_flag) *reinterpret_cast<volatile uint32_t *>(peer.down_flag) = peer.value;
+            __threadfence_system();
+        }
     }
 }
 
@@ -427,7 +437,7 @@ __device__ __forceinline__ void pk_finish(const tfb_channels_step_args &a, Acc &
 template <int SRC, int VAR, class TC>
 __global__ void __launch_bounds__(TC::threads, 1)
 channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed p,
-                       const PkConsts k, const __grid_constant__ PkMaps maps) {
+                       const PkConsts k, const __grid_constant__ PkMaps maps, const PkPeer peer) {
     using SL = StageLayout<SRC, VAR, TC>;
     constexpr int kTR = TC::R, kTW = TC::W, kQW = TC::QW, kConsumerWarps = TC::warps, kThreads = TC::threads;
     constexpr int NS = SL::stages;
@@ -529,6 +539,8 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
                                 x.qself, p.outlet_rough, r, c0, acc, rate_max, u, Qn);
                     a.u[i] = u;
                     a.Q_out[i] = Qn;
+                    if (r == 0 && peer.up_Q) peer.up_Q[c0] = Qn;              // NVLink peer store
+                    if (r == a.ny - 1 && peer.down_Q) peer.down_Q[c0] = Qn;
                 }
                 if (nf) { acc.s[S_VOL_EDGE] += o.v; o.v = 0.0; if (kKW) o.d = 0.0; }   // :2960-2966
                 a.vol_out[i] = o.v;
@@ -600,6 +612,10 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
                 if (kKW) {
                     *reinterpret_cast<double2 *>(a.u + i) = make_double2(u0, u1);
                     *reinterpret_cast<double2 *>(a.Q_out + i) = make_double2(Q0, Q1);
+                    if (r == 0 && peer.up_Q)                                  // NVLink peer stores
+                        *reinterpret_cast<double2 *>(peer.up_Q + c0) = make_double2(Q0, Q1);
+                    if (r == a.ny - 1 && peer.down_Q)
+                        *reinterpret_cast<double2 *>(peer.down_Q + c0) = make_double2(Q0, Q1);
                 }
                 // update_edge_values :2960-2966 (pass A keeps the PRE-zero depth for the
                 // free-surface slope of pass B, which then zeroes it)
@@ -621,8 +637,8 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
             if (++stage == NS) { stage = 0; phase ^= 1u; }
         }
     }
-    pk_finish<kConsumerWarps>(a, acc, rate_max, warp < kConsumerWarps, s_fail, kKW ? 0 : 1, sm, tot,
-                              &is_last);
+    pk_finish<kConsumerWarps>(a, acc, rate_max, warp < kConsumerWarps, s_fail, kKW ? 0 : 1, peer, sm,
+                              tot, &is_last);
 }
 
 // ---------------------------------------------------------------------------
@@ -766,7 +782,8 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
             if (++stage == NS) { stage = 0; phase ^= 1u; }
         }
     }
-    pk_finish<kConsumerWarps>(a, acc, rate_max, warp < kConsumerWarps, s_fail, 2, sm, tot, &is_last);
+    pk_finish<kConsumerWarps>(a, acc, rate_max, warp < kConsumerWarps, s_fail, 2, PkPeer{}, sm, tot,
+                              &is_last);
 }
 
 }  // namespace tfb
@@ -856,7 +873,7 @@ int get_map(const void *ptr, int64_t rows, int64_t cols, CUtensorMapDataType dty
 
 template <int SRC, int VAR, class TC>
 int launch_main(const tfb_channels_step_args &a, const tfb_channels_packed &p, PkConsts k,
-                cudaStream_t st) {
+                cudaStream_t st, const PkPeer &peer = PkPeer{}) {
     using SL = StageLayout<SRC, VAR, TC>;
     constexpr int kTR = TC::R, kQR = TC::QR, kTW = TC::W, kQW = TC::QW, kThreads = TC::threads;
     k.tiles_x = (a.nx + kTW - 1) / kTW;
@@ -891,7 +908,7 @@ int launch_main(const tfb_channels_step_args &a, const tfb_channels_packed &p, P
     }
     int64_t grid = sm_count();
     if (grid > k.n_tiles) grid = k.n_tiles;
-    channels_packed_kernel<SRC, VAR, TC><<<(int)grid, kThreads, smem, st>>>(a, p, k, m);
+    channels_packed_kernel<SRC, VAR, TC><<<(int)grid, kThreads, smem, st>>>(a, p, k, m, peer);
     TFB_CUDA_CHECK(cudaGetLastError());
     return TFB_OK;
 }
@@ -1037,6 +1054,87 @@ extern "C" int tfb_channels_step_packed(const tfb_channels_step_args *ap,
     if (mode == PK_SRC_NONE) return launch_main<PK_SRC_NONE, PK_KW, CfgNone>(*ap, *pp, k, st);
     if (mode == PK_SRC_GA) return launch_main<PK_SRC_GA, PK_KW, CfgGA>(*ap, *pp, k, st);
     return launch_main<PK_SRC_FULL, PK_KW, CfgFull>(*ap, *pp, k, st);
+}
+
+// ---- peer-memory halo -----------------------------------------------------------------
+namespace {
+typedef CUresult (*StreamWaitFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+StreamWaitFn g_wait32 = nullptr;
+
+int stream_wait_geq(cudaStream_t st, const uint32_t *addr, uint32_t value) {
+    if (!g_wait32) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        TFB_CUDA_CHECK(cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) {
+            tfb::set_error("cuStreamWaitValue32 not available from the driver");
+            return TFB_ERR_CUDA;
+        }
+        g_wait32 = (StreamWaitFn)fn;
+    }
+    const CUresult rc = g_wait32((CUstream)st, (CUdeviceptr)(uintptr_t)addr, value,
+                                 CU_STREAM_WAIT_VALUE_GEQ);
+    if (rc != CUDA_SUCCESS) {
+        tfb::set_error("cuStreamWaitValue32 failed (%d)", (int)rc);
+        return TFB_ERR_CUDA;
+    }
+    return TFB_OK;
+}
+}  // namespace
+
+extern "C" int64_t tfb_sizeof_peer_halo(void) { return (int64_t)sizeof(tfb_peer_halo); }
+
+extern "C" int tfb_peer_alloc(int64_t bytes, void **ptr, uint8_t *handle64) {
+    TFB_ARG_CHECK(bytes > 0 && ptr && handle64);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    TFB_CUDA_CHECK(cudaMalloc(ptr, (size_t)bytes));
+    TFB_CUDA_CHECK(cudaMemset(*ptr, 0, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    TFB_CUDA_CHECK(cudaIpcGetMemHandle(&h, *ptr));
+    memcpy(handle64, &h, 64);
+    return TFB_OK;
+}
+
+extern "C" int tfb_peer_open(const uint8_t *handle64, void **ptr) {
+    TFB_ARG_CHECK(handle64 && ptr);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    TFB_CUDA_CHECK(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return TFB_OK;
+}
+
+extern "C" int tfb_peer_close(void *ptr) {
+    TFB_ARG_CHECK(ptr != nullptr);
+    TFB_CUDA_CHECK(cudaIpcCloseMemHandle(ptr));
+    return TFB_OK;
+}
+
+extern "C" int tfb_peer_free(void *ptr) {
+    TFB_ARG_CHECK(ptr != nullptr);
+    TFB_CUDA_CHECK(cudaFree(ptr));
+    return TFB_OK;
+}
+
+extern "C" int tfb_channels_step_packed_p2p(const tfb_channels_step_args *ap,
+                                            const tfb_channels_packed *pp,
+                                            const tfb_peer_halo *ph, void *stream) {
+    TFB_ARG_CHECK(ph != nullptr);
+    PkConsts k;
+    int mode = 0;
+    int rc = prepare(ap, pp, false, k, mode);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    // both neighbours must have finished the previous step: their halo rows are in
+    // my memory, and they no longer read the halo rows this step overwrites
+    if (ph->from_up && (rc = stream_wait_geq(st, ph->from_up, ph->step))) return rc;
+    if (ph->from_down && (rc = stream_wait_geq(st, ph->from_down, ph->step))) return rc;
+    PkPeer peer;
+    peer.up_Q = ph->up_Q; peer.down_Q = ph->down_Q;
+    peer.up_flag = ph->up_flag; peer.down_flag = ph->down_flag;
+    peer.value = ph->step + 1u;
+    if (mode == PK_SRC_NONE) return launch_main<PK_SRC_NONE, PK_KW, CfgNone>(*ap, *pp, k, st, peer);
+    if (mode == PK_SRC_GA) return launch_main<PK_SRC_GA, PK_KW, CfgGA>(*ap, *pp, k, st, peer);
+    return launch_main<PK_SRC_FULL, PK_KW, CfgFull>(*ap, *pp, k, st, peer);
 }
 
 extern "C" int tfb_channels_step_packed_dw_a(const tfb_channels_step_args *ap,

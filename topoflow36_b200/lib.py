@@ -101,6 +101,12 @@ class MetEnergyArgs(C.Structure):
                 [(n, vp) for n in _OUT])
 
 
+class PeerHalo(C.Structure):
+    """tfb_peer_halo: neighbours' halo rows and step flags mapped with CUDA IPC."""
+    _fields_ = [('up_Q', vp), ('down_Q', vp), ('up_flag', vp), ('down_flag', vp),
+                ('from_up', vp), ('from_down', vp), ('step', C.c_uint32)]
+
+
 class ChannelsPacked(C.Structure):
     """tfb_channels_packed: compact static inputs of the packed fast path."""
     _fields_ = [('geo32', vp), ('width32', vp), ('coef', vp), ('angle_lut', vp),
@@ -144,6 +150,13 @@ SIGNATURES = {
                                                 C.POINTER(ChannelsPacked), vp]),
     'tfb_channels_step_packed_dw_b': (C.c_int, [C.POINTER(ChannelsStepArgs),
                                                 C.POINTER(ChannelsPacked), vp]),
+    'tfb_sizeof_peer_halo': (_i64, []),
+    'tfb_peer_alloc': (C.c_int, [_i64, C.POINTER(vp), C.c_char_p]),
+    'tfb_peer_open': (C.c_int, [C.c_char_p, C.POINTER(vp)]),
+    'tfb_peer_close': (C.c_int, [vp]),
+    'tfb_peer_free': (C.c_int, [vp]),
+    'tfb_channels_step_packed_p2p': (C.c_int, [C.POINTER(ChannelsStepArgs),
+                                               C.POINTER(ChannelsPacked), C.POINTER(PeerHalo), vp]),
     'tfb_channels_fold': (C.c_int, [C.POINTER(ChannelsStepArgs), vp, vp]),
     'tfb_sources_partials_len': (_i64, []),
     'tfb_channels_minmax': (C.c_int, [vp, vp, vp, vp, _i32, _i32, vp, vp, vp,
@@ -192,6 +205,8 @@ def load():
                           C.sizeof(ChannelsStepArgs)))
     if lib.tfb_sizeof_channels_scalars() != C.sizeof(ChannelsScalars):
         raise TfbError('tfb_channels_scalars layout mismatch')
+    if lib.tfb_sizeof_peer_halo() != C.sizeof(PeerHalo):
+        raise TfbError('tfb_peer_halo layout mismatch')
     if lib.tfb_sizeof_met_energy_args() != C.sizeof(MetEnergyArgs):
         raise TfbError('tfb_met_energy_args layout mismatch')
     if lib.tfb_sizeof_channels_packed() != C.sizeof(ChannelsPacked):

@@ -35,7 +35,8 @@ class ChannelsEngine(object):
                  write_R=False, outlet=(0, 0), rho_H2O=1000.0, row0=0,
                  ny_global=None, halo=0, device=None, finalize=True,
                  n_pixels_global=None, packed=True, flood=False, d_bankfull=10.0,
-                 flood_manning_n=0.10, width_ratio=5.0, attenuate=False, n_days=5.0):
+                 flood_manning_n=0.10, width_ratio=5.0, attenuate=False, n_days=5.0,
+                 q_buffers=None):
         if not torch.cuda.is_available():
             raise L.TfbError('ChannelsEngine needs a CUDA device (no CPU path)')
         self.lib = L.load()
@@ -120,7 +121,11 @@ class ChannelsEngine(object):
         # ---- state ---------------------------------------------------------
         z = lambda: self._zeros(torch.float64)
         self.vol_buf = [z(), z() if not kinematic else None]
-        self.Q_buf = [z(), z()]
+        # the two discharge buffers may come from peer-mappable allocations (slab.PeerHalos)
+        self.Q_buf = list(q_buffers) if q_buffers is not None else [z(), z()]
+        for t in self.Q_buf:
+            if tuple(t.shape) != (self.ny + 2 * self.halo, self.nx) or t.dtype != torch.float64:
+                raise L.TfbError('q_buffers must be (ny + 2*halo, nx) float64 CUDA tensors')
         self.qcur = 0             # Q buffer the NEXT step reads
         self.scur = 0             # state buffer (vol, I, h_swe) the next step reads
         self.d, self.u = z(), z()
@@ -509,7 +514,9 @@ class ChannelsEngine(object):
                 return True
         return False
 
-    def step(self, time_min=0.0):
+    def step(self, time_min=0.0, peer=None):
+        """Advance one time step.  `peer` (slab.PeerHalos) switches the kinematic packed
+        step to the fused peer-memory halo exchange."""
         a = self.args
         a.flags = self.flags | (L.CH_ET_INPLACE if a.ET.ptr else 0)
         a.time_min = float(time_min)
@@ -524,7 +531,12 @@ class ChannelsEngine(object):
             setattr(a, name, self._p(buf[self.scur if dbl else 0]))
             setattr(a, name + '_out', self._p(buf[self.scur ^ 1 if dbl else 0]))
         if self._packed_ok():
-            if self.kinematic:
+            if self.kinematic and peer is not None:
+                ph = peer.descriptor(self.qcur ^ 1, self.n_steps)
+                L.check(self.lib.tfb_channels_step_packed_p2p(
+                    C.byref(a), C.byref(self.packed), C.byref(ph), L.stream_ptr()),
+                    'tfb_channels_step_packed_p2p')
+            elif self.kinematic:
                 L.check(self.lib.tfb_channels_step_packed(C.byref(a), C.byref(self.packed),
                                                           L.stream_ptr()), 'tfb_channels_step_packed')
             else:
@@ -538,6 +550,8 @@ class ChannelsEngine(object):
                     C.byref(a), C.byref(self.packed), L.stream_ptr()), 'tfb_channels_step_packed_dw_b')
             self.last_path = 'packed'
         else:
+            if peer is not None:
+                raise L.TfbError('the peer-memory halo needs the packed kinematic step')
             if getattr(self, 'generic_released', False):
                 raise L.TfbError('this configuration needs the generic kernel, but its static '
                                  'inputs were released (release_generic_inputs)')

@@ -99,6 +99,79 @@ def exchange_halos(tensors, layout, rows=None, group=None):
             req.wait()
 
 
+class _DevArray(object):
+    """Minimal __cuda_array_interface__ carrier so torch can wrap a raw allocation."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {'shape': tuple(shape), 'typestr': typestr,
+                                         'data': (int(ptr), False), 'version': 2, 'strides': None}
+
+
+class PeerHalos(object):
+    """Peer-memory halo exchange for the kinematic packed step (include/tfb.h,
+    tfb_channels_step_packed_p2p): this rank's two discharge buffers and a 2-word flag
+    block are allocated with tfb_peer_alloc, the CUDA-IPC handles go round with one
+    all_gather_object, and the neighbours' buffers are mapped into this process.  After
+    that a step needs no NCCL call: the kernel stores its boundary discharge rows into
+    the neighbours' halo rows over NVLink and the streams order themselves with
+    cuStreamWaitValue32 on the flag words."""
+
+    def __init__(self, layout, device, group=None):
+        self.layout, self.group = layout, group
+        self.lib = L.load()
+        lay = layout
+        rows = lay.ny + 2 * lay.halo
+        nbytes = rows * lay.nx * 8
+        self._mine, handles = [], []
+        for _ in range(3):                       # Q buffer 0, Q buffer 1, flags
+            p = C.c_void_p()
+            h = C.create_string_buffer(64)
+            L.check(self.lib.tfb_peer_alloc(nbytes if len(self._mine) < 2 else 256, C.byref(p), h),
+                    'tfb_peer_alloc')
+            self._mine.append(p.value)
+            handles.append(h.raw)
+        self.q_buffers = [torch.as_tensor(_DevArray(self._mine[k], (rows, lay.nx), '<f8'),
+                                          device=device) for k in range(2)]
+        info = [None] * lay.world_size
+        dist.all_gather_object(info, dict(handles=handles, ny=lay.ny), group=group)
+        self._open = {}
+        self.nbr = {}
+        for name, r in (('up', lay.up), ('down', lay.down)):
+            if r is None:
+                continue
+            ptrs = []
+            for h in info[r]['handles']:
+                p = C.c_void_p()
+                L.check(self.lib.tfb_peer_open(h, C.byref(p)), 'tfb_peer_open')
+                ptrs.append(p.value)
+            self._open[name] = ptrs
+            self.nbr[name] = dict(q=ptrs[:2], flags=ptrs[2], ny=info[r]['ny'])
+        dist.barrier(group=group)
+
+    def descriptor(self, q_out, step):
+        lay = self.layout
+        row = lay.nx * 8
+        ph = L.PeerHalo()
+        if 'up' in self.nbr:
+            n = self.nbr['up']
+            ph.up_Q = n['q'][q_out] + (lay.halo + n['ny']) * row     # its first LOWER halo row
+            ph.up_flag = n['flags'] + 4                              # its "from_down" word
+            ph.from_up = self._mine[2]
+        if 'down' in self.nbr:
+            n = self.nbr['down']
+            ph.down_Q = n['q'][q_out] + (lay.halo - 1) * row         # its last UPPER halo row
+            ph.down_flag = n['flags']                                # its "from_up" word
+            ph.from_down = self._mine[2] + 4
+        ph.step = int(step)
+        return ph
+
+    def close(self):
+        for ptrs in self._open.values():
+            for p in ptrs:
+                self.lib.tfb_peer_close(p)
+        self._open = {}
+
+
 class SlabChannels(object):
     """A ChannelsEngine per rank + the per-step halo exchange.
 
@@ -115,8 +188,9 @@ class SlabChannels(object):
                    'vol_P', 'vol_PR', 'vol_PS', 'vol_SM', 'vol_ET', 'vol_IN')
     _CNT_FIELDS = ('n_neg_d', 'n_nan_d', 'n_inf_d', 'n_neg_u', 'n_nan_u', 'n_inf_u', 'n_nan_IN')
 
-    def __init__(self, layout, engine, group=None):
+    def __init__(self, layout, engine, group=None, peer=None):
         self.layout, self.engine, self.group = layout, engine, group
+        self.peer = peer if (peer is not None and layout.world_size > 1) else None
         if layout.world_size > 1 and not engine.args.finalize:
             raise L.TfbError('SlabChannels needs an engine built with finalize=True')
         self.device = engine.device
@@ -140,7 +214,14 @@ class SlabChannels(object):
         exchange_halos(ts, lay, rows, self.group)
 
     def step(self, time_min=0.0):
-        self.engine.step(time_min)
+        e = self.engine
+        if self.peer is not None and e.kinematic and e._packed_ok():
+            e.step(time_min, peer=self.peer)      # halo rows travel inside the kernel
+            return
+        if self.peer is not None:
+            raise L.TfbError('peer-memory halos were set up but this step is not eligible '
+                             '(needs the packed kinematic path on every step)')
+        e.step(time_min)
         self.exchange_state()
 
     def read_scalars(self):
