@@ -232,6 +232,9 @@ def main():
                          'configs[3] (diffusive wave + met/snow/evap/infil fused); dw = diffusive only')
     ap.add_argument('--device-gen', action='store_true',
                     help='synthesise the case on the GPU (needed for 65536-wide slabs)')
+    ap.add_argument('--halo', default='p2p', choices=['p2p', 'nccl'],
+                    help='N > 1: boundary rows by NVLink peer stores fused into the kernel '
+                         '(kinematic wave, default) or by NCCL send/recv after it')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     args = ap.parse_args()
@@ -272,14 +275,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    use_p2p = (world > 1 and kin and args.halo == 'p2p')
     if args.device_gen:
         stepper = cases.build_engine_device(ny, NX, kinematic=kin, sources=sources, rank=rank,
-                                            world=world, device=dev)
+                                            world=world, device=dev, p2p=use_p2p)
         parts = None
         args.no_e2e = args.no_e2e or world == 1
     else:
         stepper, parts = cases.build_engine(ny, NX, kinematic=kin, sources=sources, rank=rank,
-                                            world=world, device=dev, return_parts=True)
+                                            world=world, device=dev, return_parts=True,
+                                            p2p=use_p2p)
         args.no_e2e = args.no_e2e or (world == 1 and args.workload != 'kw_ga' and args.workload != 'kw')
     eng = stepper.engine if world > 1 else stepper
     cells = ny * NX * world
@@ -432,7 +437,10 @@ def main():
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'grid': [ny * world, NX], 'rows_per_gpu': ny,
-                   'partition': 'row slabs, 1 halo row of Q per neighbour per step over NCCL'
+                   'partition': ('row slabs, 1 halo row of Q per neighbour per step, %s'
+                                 % ('NVLink peer stores fused into the routing kernel + '
+                                    'cuStreamWaitValue32 flags (no NCCL call per step)' if use_p2p
+                                    else 'NCCL send/recv after the kernel'))
                    if world > 1 else 'single GPU',
                    'l2': 'working set %.2f GB per step per GPU >> 126 MB L2, no flush needed'
                          % (ny * NX * bpc / 1e9)},

@@ -152,7 +152,8 @@ def device_slab_params(ny, nx, row0, halo, device, seed=1234, chunk=2048):
 
 
 def build_engine_device(ny, nx, kinematic=True, infil=False, dt=1.0, rank=0, world=1, seed=1234,
-                        device=None, group=None, link_flats=True, lean_memory=True, sources=None):
+                        device=None, group=None, link_flats=True, lean_memory=True, sources=None,
+                        p2p=False):
     """Like build_engine, but every array is generated on the GPU (any size that
     fits HBM) and the generic fp64 static inputs are released once the packed
     encoding exists."""
@@ -169,18 +170,23 @@ def build_engine_device(ny, nx, kinematic=True, infil=False, dt=1.0, rank=0, wor
     del DEM
     width, nval = device_slab_params(ny, nx, lay.row0, halo, device, seed=seed)
     ang = float(np.float64(np.float32(45.0)) * (np.pi / np.float64(180)))
+    peer = None
+    if p2p and world > 1 and kinematic:
+        from .slab import make_peer_halos
+        peer = make_peer_halos(lay, device, group)
     eng = ChannelsEngine(ny, nx, dt=dt, code=d8['code'], dx=d8['dx'], dy=d8['dy'], dd=d8['dd'],
                          S_bed=d8['S_bed'], width=width, angle=ang, tan_angle=float(np.tan(ang)),
                          cos_angle=float(np.cos(ang)), rough=nval, kinematic=kinematic,
                          outlet=(ny_global - 2, nx // 2), row0=lay.row0, ny_global=ny_global,
-                         halo=halo, device=device, finalize=True, n_pixels_global=ny * nx)
+                         halo=halo, device=device, finalize=True, n_pixels_global=ny * nx,
+                         q_buffers=None if peer is None else peer.q_buffers)
     del width, nval, d8
     apply_sources(eng, sources or ('ga' if infil else 'none'), row0=lay.row0, halo=halo, seed=seed)
     if lean_memory and eng.packed is not None:
         eng.release_generic_inputs()
     torch.cuda.current_stream().synchronize()
     torch.cuda.empty_cache()
-    return SlabChannels(lay, eng, group) if world > 1 else eng
+    return SlabChannels(lay, eng, group, peer=peer) if world > 1 else eng
 
 
 def build_engine(ny, nx, kinematic=True, infil=False, diag=False, dt=1.0, rank=0, world=1,
@@ -204,8 +210,8 @@ def build_engine(ny, nx, kinematic=True, infil=False, diag=False, dt=1.0, rank=0
     ang = np.float64(angle) * DEG
     peer = None
     if p2p and world > 1 and kinematic:
-        from .slab import PeerHalos
-        peer = PeerHalos(lay, device, group)
+        from .slab import make_peer_halos
+        peer = make_peer_halos(lay, device, group)
     eng = ChannelsEngine(ny, nx, dt=dt, code=d8['code'], dx=d8['dx'], dy=d8['dy'], dd=d8['dd'],
                          S_bed=d8['S_bed'], width=np.float64(width), angle=ang,
                          rough=np.float64(nval), kinematic=kinematic, diag=diag,

@@ -135,6 +135,8 @@ class channels_component(BMI_base.BMI_component):
         self.layout = None            # SlabLayout in multi-GPU (row-slab) mode
         self.stepper = None           # SlabChannels wrapper in slab mode, else the engine
         self.group = None             # torch.distributed process group (None = world)
+        self.P2P_HALO = False         # slab mode, kinematic, uniform forcing: halo rows by
+                                      # NVLink peer stores inside the kernel instead of NCCL
 
     # ---------------------------------------------------------------- attributes
     def __getattr__(self, name):
@@ -442,7 +444,11 @@ class channels_component(BMI_base.BMI_component):
             self.remove_bad_slopes()                                   # :1316
         self.S_bed = self.slope
         rough = self.nval if self.MANNING else self.z0val
-        own = (lambda g: g) if lay is None else (lambda g: g)
+        peer = None
+        if lay is not None and self.P2P_HALO and self.KINEMATIC_WAVE:
+            from .slab import make_peer_halos
+            peer = make_peer_halos(lay, self.device or torch.device('cuda', torch.cuda.current_device()),
+                                   self.group)
         self.engine = ChannelsEngine(
             ny_loc, self.nx, dt=float(self.dt), code=code, dx=dxh, dy=dyh,
             dd=ddh, S_bed=self.S_bed, width=self.width, angle=self.angle,
@@ -454,6 +460,7 @@ class channels_component(BMI_base.BMI_component):
             write_R=bool(self.WRITE_R), outlet=(int(self.outlet_ID[0]), int(self.outlet_ID[1])),
             rho_H2O=float(self.rho_H2O), device=self.device, row0=row0, ny_global=self.ny,
             halo=halo, finalize=True, n_pixels_global=ny_loc * self.nx,
+            q_buffers=None if peer is None else peer.q_buffers,
             flood=self.FLOOD_OPTION, attenuate=self.ATTENUATE,
             n_days=float(getattr(self, 'n_days', 5.0)),
             d_bankfull=self.d_bankfull if np.ndim(self.d_bankfull) == 2 else float(self.d_bankfull))
@@ -463,7 +470,7 @@ class channels_component(BMI_base.BMI_component):
             self.stepper = self.engine
         else:
             from .slab import SlabChannels
-            self.stepper = SlabChannels(lay, self.engine, self.group)
+            self.stepper = SlabChannels(lay, self.engine, self.group, peer=peer)
         self.update_total_channel_water_volume()
         self.vol_chan_sum0 = self.vol_chan_sum.copy()
         torch.cuda.current_stream().synchronize()

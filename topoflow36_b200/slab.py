@@ -116,36 +116,49 @@ class PeerHalos(object):
     the neighbours' halo rows over NVLink and the streams order themselves with
     cuStreamWaitValue32 on the flag words."""
 
-    def __init__(self, layout, device, group=None):
+    def __init__(self, layout, device, group=None, _collective_guard=False):
         self.layout, self.group = layout, group
         self.lib = L.load()
+        self.ok = True
         lay = layout
         rows = lay.ny + 2 * lay.halo
         nbytes = rows * lay.nx * 8
         self._mine, handles = [], []
-        for _ in range(3):                       # Q buffer 0, Q buffer 1, flags
-            p = C.c_void_p()
-            h = C.create_string_buffer(64)
-            L.check(self.lib.tfb_peer_alloc(nbytes if len(self._mine) < 2 else 256, C.byref(p), h),
-                    'tfb_peer_alloc')
-            self._mine.append(p.value)
-            handles.append(h.raw)
-        self.q_buffers = [torch.as_tensor(_DevArray(self._mine[k], (rows, lay.nx), '<f8'),
-                                          device=device) for k in range(2)]
+        try:
+            for _ in range(3):                   # Q buffer 0, Q buffer 1, flags
+                p = C.c_void_p()
+                h = C.create_string_buffer(64)
+                L.check(self.lib.tfb_peer_alloc(nbytes if len(self._mine) < 2 else 256,
+                                                C.byref(p), h), 'tfb_peer_alloc')
+                self._mine.append(p.value)
+                handles.append(h.raw)
+            self.q_buffers = [torch.as_tensor(_DevArray(self._mine[k], (rows, lay.nx), '<f8'),
+                                              device=device) for k in range(2)]
+        except Exception:
+            if not _collective_guard:
+                raise
+            self.ok, handles = False, None       # still take part in the collectives below
         info = [None] * lay.world_size
         dist.all_gather_object(info, dict(handles=handles, ny=lay.ny), group=group)
         self._open = {}
         self.nbr = {}
-        for name, r in (('up', lay.up), ('down', lay.down)):
-            if r is None:
-                continue
-            ptrs = []
-            for h in info[r]['handles']:
-                p = C.c_void_p()
-                L.check(self.lib.tfb_peer_open(h, C.byref(p)), 'tfb_peer_open')
-                ptrs.append(p.value)
-            self._open[name] = ptrs
-            self.nbr[name] = dict(q=ptrs[:2], flags=ptrs[2], ny=info[r]['ny'])
+        if any(i['handles'] is None for i in info):
+            self.ok = False
+        try:
+            for name, r in (('up', lay.up), ('down', lay.down)):
+                if r is None or not self.ok:
+                    continue
+                ptrs = []
+                for h in info[r]['handles']:
+                    p = C.c_void_p()
+                    L.check(self.lib.tfb_peer_open(h, C.byref(p)), 'tfb_peer_open')
+                    ptrs.append(p.value)
+                self._open[name] = ptrs
+                self.nbr[name] = dict(q=ptrs[:2], flags=ptrs[2], ny=info[r]['ny'])
+        except L.TfbError:
+            if not _collective_guard:
+                raise
+            self.ok = False                       # make_peer_halos lets every rank fall back
         dist.barrier(group=group)
 
     def descriptor(self, q_out, step):
@@ -170,6 +183,27 @@ class PeerHalos(object):
             for p in ptrs:
                 self.lib.tfb_peer_close(p)
         self._open = {}
+
+
+def make_peer_halos(layout, device, group=None):
+    """PeerHalos on every rank, or None on every rank: if CUDA IPC is not usable on any
+    rank (containers without shared /dev/shm or IPC permission, no peer access) all
+    ranks agree to fall back to the NCCL halo exchange."""
+    ph, ok = None, 1.0
+    try:
+        ph = PeerHalos(layout, device, group, _collective_guard=True)
+        ok = 1.0 if ph.ok else 0.0
+    except Exception as exc:                      # pragma: no cover (depends on the host)
+        import warnings
+        warnings.warn('peer-memory halos unavailable, using NCCL send/recv: %s' % (exc,))
+        ok = 0.0
+    t = torch.tensor([ok], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    if float(t.item()) < 1.0:
+        if ph is not None:
+            ph.close()
+        return None
+    return ph
 
 
 class SlabChannels(object):
