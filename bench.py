@@ -288,7 +288,7 @@ def main():
         args.no_e2e = args.no_e2e or (world == 1 and args.workload != 'kw_ga' and args.workload != 'kw')
     eng = stepper.engine if world > 1 else stepper
     cells = ny * NX * world
-    launches_per_step = 1 if kin else 2
+    launches_per_step = 1 if kin else 3       # DW: depth pass, velocity pass, noflow zeroing
 
     # ---- `value`: state resident in HBM, no host round trip per step ----------
     tmin = 0.0

@@ -302,6 +302,8 @@ typedef struct {
     /* diffusive wave only (coef may then be NULL): */
     const double *inv_rough;  /* 1 / n                                   (8 B / cell) */
     const float *S32;         /* bed slope as float32 (lossless)         (4 B / cell) */
+    const int64_t *noflow_idx; /* flat indices (owned rows) of the cells with code 0  */
+    int64_t n_noflow;
 } tfb_channels_packed;
 
 int64_t tfb_sizeof_channels_packed(void);
@@ -327,16 +329,22 @@ int tfb_channels_pack_rows(const float *dx, const float *dy, const float *dd,
 int tfb_channels_step_packed(const tfb_channels_step_args *a,
                              const tfb_channels_packed *p, void *stream);
 
-/* Diffusive wave through the packed path: two launches per step.  Pass A updates
+/* Diffusive wave through the packed path: two launches per step (+ a tiny third).  Pass A updates
  * the volumes and writes the NEW depth of every cell (update_flow_volume :1951,
  * update_channel_depth :2250, fused sources, volume integrals); a slab run then
  * exchanges one boundary row of `d`; pass B forms the free-surface slope from the
  * new depths of each cell and its D8 parent (update_free_surface_slope
- * :2583-2618), the velocity and the next discharge, and zeroes the depth of
- * noflow cells.  Same eligibility rules as tfb_channels_step_packed. */
+ * :2583-2618), the velocity and the next discharge.  Same eligibility rules as
+ * tfb_channels_step_packed. */
 int tfb_channels_step_packed_dw_a(const tfb_channels_step_args *a,
                                   const tfb_channels_packed *p, void *stream);
 int tfb_channels_step_packed_dw_b(const tfb_channels_step_args *a,
+                                  const tfb_channels_packed *p, void *stream);
+/* third, tiny launch of the diffusive step: d = 0 at the noflow cells
+ * (update_edge_values :2966).  It cannot be part of pass B, whose tiles read the
+ * PRE-zero depth of noflow parents in neighbouring tiles (:2583-2618 runs before
+ * :2938 in the reference). */
+int tfb_channels_step_packed_dw_c(const tfb_channels_step_args *a,
                                   const tfb_channels_packed *p, void *stream);
 
 /* ---- peer-memory halo (NVLink / NVSwitch) ----------------------------------

@@ -57,6 +57,7 @@ struct PkConsts {
     double Ks, gkq;          // Green-Ampt: Ks, (G*(Ks-Ki))*(qs-qi)
     int low_rain;            // P_total < Ks  (infil_base.py:954-995)
     int n_tiles, tiles_x;
+    int tiles_y, n_boundary;     // tiles of the first and last tile row come FIRST in the order
     // general fused sources (PK_SRC_FULL): every parameter a scalar, T_air may be a grid
     unsigned flags;
     int tair_grid;
@@ -335,6 +336,21 @@ __device__ __forceinline__ void pk_velocity(const tfb_channels_step_args &a, con
     u_out = u;
 }
 
+// Processing order: the tiles that hold the slab's first and last owned rows first (they
+// are the only ones that read the halo rows and that feed the neighbours), then the rest.
+__device__ __forceinline__ void tile_of(const PkConsts &k, int s, int &ty, int &tx) {
+    if (s < k.tiles_x) { ty = 0; tx = s; return; }
+    if (s < k.n_boundary) { ty = k.tiles_y - 1; tx = s - k.tiles_x; return; }
+    const int q = s - k.n_boundary;
+    ty = 1 + q / k.tiles_x;
+    tx = q - (ty - 1) * k.tiles_x;
+}
+
+__global__ void zero_at_kernel(double *__restrict__ x, const int64_t *__restrict__ idx, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[__ldg(idx + i)] = 0.0;
+}
+
 struct PkMaps { CUtensorMap Q, vol, coef, I, H, T, w, geo; };
 struct PkPeer { double *up_Q, *down_Q; uint32_t *up_flag, *down_flag; uint32_t value; };
 struct PkMapsB { CUtensorMap D, N, S, w, geo; };
@@ -419,14 +435,7 @@ __device__ __forceinline__ void pk_finish(const tfb_channels_step_args &a, Acc &
             else { fold_status(a, h); mirror_scalars(a); }
         }
         a.ticket[0] = 0u;                                 // re-arm for the next launch
-        // every CTA has fenced its peer stores before taking a ticket: tell the
-        // neighbours that this step's halo rows are in their memory
-        if (peer.up_flag || peer.down_flag) {
-            __threadfence_system();
-            if (peer.up_flag) *reinterpret_cast<volatile uint32_t *>(peer.up_flag) = peer.value;
-            if (peer.down_flag) *reinterpret_cast<volatile uint32_t *>(peer.down_flag) = peer.value;
-            __threadfence_system();
-        }
+        a.ticket[1] = 0u;                                 // boundary-tile counter (peer halos)
     }
 }
 
@@ -449,11 +458,13 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
     __shared__ __align__(8) uint64_t full_bar[NS], empty_bar[NS];
     __shared__ bool is_last;
     __shared__ int s_fail;
+    __shared__ unsigned s_bcount[NS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < p.n_angles * 4; i += kThreads) lut[i] = __ldg(p.angle_lut + i);
     if (tid < kConsumerWarps * kPartialStride) (&sm[0][0])[tid] = 0.0;
     if (tid == 0) {
         s_fail = 0;
+        for (int q = 0; q < NS; ++q) s_bcount[q] = 0u;
         for (int s = 0; s < NS; ++s) {
             mbar_init(&full_bar[s], 1u);
             mbar_init(&empty_bar[s], (unsigned)kConsumerWarps);
@@ -482,7 +493,8 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
                                                               (use_h ? 1 : 0) + (use_t ? 1 : 0)) + 2 * TC::nF);
             for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
                 if (!mbar_wait(&empty_bar[stage], phase ^ 1u)) { s_fail = 1; break; }
-                const int ty = t / k.tiles_x, txi = t - ty * k.tiles_x;
+                int ty, txi;
+                tile_of(k, t, ty, txi);
                 const int c0 = txi * kTW, r0 = ty * kTR;
                 unsigned char *st = smem + (size_t)stage * SL::bytes;
                 mbar_arrive_expect_tx(&full_bar[stage], tx);
@@ -504,7 +516,8 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
         unsigned phase = 0;
         for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
             if (!mbar_wait(&full_bar[stage], phase)) { s_fail = 1; break; }
-            const int ty = t / k.tiles_x, txi = t - ty * k.tiles_x;
+            int ty, txi;
+            tile_of(k, t, ty, txi);
             if constexpr (TC::cpl == 1) {
             const int row = warp / TC::wpr, ct = ((warp % TC::wpr) << 5) + lane;  // wpr warps per tile row
             const int c0 = txi * kTW + ct, r = ty * kTR + row;
@@ -632,6 +645,21 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
                 }
             }
             }
+            if ((peer.up_flag || peer.down_flag) && t < k.n_boundary) {
+                // this warp's share of a boundary tile is in the neighbours' halo rows; when
+                // the LAST boundary tile of the grid is complete the neighbours may start
+                // their next step (they no longer wait for the rest of this kernel)
+                __threadfence_system();
+                __syncwarp();
+                if (lane == 0 && atomicAdd(&s_bcount[stage], 1u) == (unsigned)kConsumerWarps - 1u) {
+                    s_bcount[stage] = 0u;
+                    if (atomicAdd(a.ticket + 1, 1u) == (unsigned)k.n_boundary - 1u) {
+                        __threadfence_system();
+                        if (peer.up_flag) *reinterpret_cast<volatile uint32_t *>(peer.up_flag) = peer.value;
+                        if (peer.down_flag) *reinterpret_cast<volatile uint32_t *>(peer.down_flag) = peer.value;
+                    }
+                }
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[stage]);            // slot may be refilled
             if (++stage == NS) { stage = 0; phase ^= 1u; }
@@ -685,7 +713,8 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
             unsigned phase = 0;
             for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
                 if (!mbar_wait(&empty_bar[stage], phase ^ 1u)) { s_fail = 1; break; }
-                const int ty = t / k.tiles_x, txi = t - ty * k.tiles_x;
+                int ty, txi;
+                tile_of(k, t, ty, txi);
                 const int c0 = txi * kTW, r0 = ty * kTR;
                 unsigned char *st = smem + (size_t)stage * SL::bytes;
                 mbar_arrive_expect_tx(&full_bar[stage], (unsigned)SL::tx_bytes);
@@ -702,7 +731,8 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
         unsigned phase = 0;
         for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
             if (!mbar_wait(&full_bar[stage], phase)) { s_fail = 1; break; }
-            const int ty = t / k.tiles_x, txi = t - ty * k.tiles_x;
+            int ty, txi;
+            tile_of(k, t, ty, txi);
             if constexpr (TC::cpl == 1) {
             const int row = warp / TC::wpr, ct = ((warp % TC::wpr) << 5) + lane;
             const int c0 = txi * kTW + ct, r = ty * kTR + row;
@@ -732,7 +762,6 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
                             acc, rate_max, u, Qn);
                 a.u[i] = u;
                 a.Q_out[i] = Qn;
-                if (code == 0u) a.d[i] = 0.0;                              // :2966
             }
             } else {
             const int row = warp / TC::wpr, ct = ((warp % TC::wpr) << 6) + lane * 2;
@@ -751,7 +780,7 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
                 const double2 *rgp = reinterpret_cast<const double2 *>(p.row_geom + (int64_t)r * kRowGeom);
                 const double2 g1 = __ldg(rgp + 1), g2 = __ldg(rgp + 2);
                 const int64_t i = (int64_t)r * a.nx + c0;
-                double uo[2], Qo[2], dd_[2];
+                double uo[2], Qo[2];
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     const unsigned g = j ? geo.y : geo.x;
@@ -769,12 +798,9 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
                         qs = __ldg(a.Q_in + i + j);
                     pk_velocity(a, k, lut, g, d, (double)(j ? w.y : w.x), umul, inv_ds, qs,
                                 p.outlet_rough, r, c0 + j, acc, rate_max, uo[j], Qo[j]);
-                    dd_[j] = (code == 0u) ? 0.0 : d;                  // :2966
                 }
                 *reinterpret_cast<double2 *>(a.u + i) = make_double2(uo[0], uo[1]);
                 *reinterpret_cast<double2 *>(a.Q_out + i) = make_double2(Qo[0], Qo[1]);
-                if (((geo.x & 0xffu) == 0u) || ((geo.y & 0xffu) == 0u))
-                    *reinterpret_cast<double2 *>(a.d + i) = make_double2(dd_[0], dd_[1]);
             }
             }
             __syncwarp();
@@ -877,7 +903,9 @@ int launch_main(const tfb_channels_step_args &a, const tfb_channels_packed &p, P
     using SL = StageLayout<SRC, VAR, TC>;
     constexpr int kTR = TC::R, kQR = TC::QR, kTW = TC::W, kQW = TC::QW, kThreads = TC::threads;
     k.tiles_x = (a.nx + kTW - 1) / kTW;
-    k.n_tiles = k.tiles_x * ((a.ny + kTR - 1) / kTR);
+    k.tiles_y = (a.ny + kTR - 1) / kTR;
+    k.n_tiles = k.tiles_x * k.tiles_y;
+    k.n_boundary = k.tiles_x * (k.tiles_y > 1 ? 2 : 1);
     static_assert(SL::stages >= 2, "ring needs at least two slots");
     PkMaps m;
     const int64_t rows_h = (int64_t)a.ny + 2 * a.halo;
@@ -919,7 +947,9 @@ int launch_dwb(const tfb_channels_step_args &a, const tfb_channels_packed &p, Pk
     using SL = StageLayoutB<TC>;
     constexpr int kTR = TC::R, kQR = TC::QR, kTW = TC::W, kQW = TC::QW, kThreads = TC::threads;
     k.tiles_x = (a.nx + kTW - 1) / kTW;
-    k.n_tiles = k.tiles_x * ((a.ny + kTR - 1) / kTR);
+    k.tiles_y = (a.ny + kTR - 1) / kTR;
+    k.n_tiles = k.tiles_x * k.tiles_y;
+    k.n_boundary = k.tiles_x * (k.tiles_y > 1 ? 2 : 1);
     PkMapsB m;
     const int64_t rows_h = (int64_t)a.ny + 2 * a.halo;
     const size_t hb = (size_t)a.halo * a.nx;
@@ -1054,6 +1084,16 @@ extern "C" int tfb_channels_step_packed(const tfb_channels_step_args *ap,
     if (mode == PK_SRC_NONE) return launch_main<PK_SRC_NONE, PK_KW, CfgNone>(*ap, *pp, k, st);
     if (mode == PK_SRC_GA) return launch_main<PK_SRC_GA, PK_KW, CfgGA>(*ap, *pp, k, st);
     return launch_main<PK_SRC_FULL, PK_KW, CfgFull>(*ap, *pp, k, st);
+}
+
+extern "C" int tfb_channels_step_packed_dw_c(const tfb_channels_step_args *ap,
+                                             const tfb_channels_packed *pp, void *stream) {
+    TFB_ARG_CHECK(ap && pp && ap->d && pp->n_noflow >= 0 && (pp->n_noflow == 0 || pp->noflow_idx));
+    if (pp->n_noflow == 0) return TFB_OK;
+    zero_at_kernel<<<(unsigned)((pp->n_noflow + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        ap->d, pp->noflow_idx, pp->n_noflow);
+    TFB_CUDA_CHECK(cudaGetLastError());
+    return TFB_OK;
 }
 
 // ---- peer-memory halo -----------------------------------------------------------------

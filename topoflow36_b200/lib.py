@@ -111,7 +111,7 @@ class ChannelsPacked(C.Structure):
     """tfb_channels_packed: compact static inputs of the packed fast path."""
     _fields_ = [('geo32', vp), ('width32', vp), ('coef', vp), ('angle_lut', vp),
                 ('row_geom', vp), ('outlet_rough', C.c_double), ('n_angles', C.c_int32),
-                ('inv_rough', vp), ('S32', vp)]
+                ('inv_rough', vp), ('S32', vp), ('noflow_idx', vp), ('n_noflow', C.c_int64)]
 
 
 _i32, _i64, _f32, _f64 = C.c_int32, C.c_int64, C.c_float, C.c_double
@@ -157,6 +157,8 @@ SIGNATURES = {
     'tfb_peer_free': (C.c_int, [vp]),
     'tfb_channels_step_packed_p2p': (C.c_int, [C.POINTER(ChannelsStepArgs),
                                                C.POINTER(ChannelsPacked), C.POINTER(PeerHalo), vp]),
+    'tfb_channels_step_packed_dw_c': (C.c_int, [C.POINTER(ChannelsStepArgs),
+                                                C.POINTER(ChannelsPacked), vp]),
     'tfb_channels_fold': (C.c_int, [C.POINTER(ChannelsStepArgs), vp, vp]),
     'tfb_sources_partials_len': (_i64, []),
     'tfb_channels_minmax': (C.c_int, [vp, vp, vp, vp, _i32, _i32, vp, vp, vp,

@@ -284,7 +284,12 @@ class ChannelsEngine(object):
         pk.S32 = None if S32 is None else S32.data_ptr()
         pk.angle_lut, pk.row_geom = lut.data_ptr(), rowg.data_ptr()
         pk.outlet_rough, pk.n_angles = n_out, int(uniq.shape[0])
-        self._pack_keep = (geo32, w32, coef, inv_rough, S32, lut, rowg)
+        nf = None
+        if not self.kinematic:
+            # noflow cells of the owned rows, as flat indices relative to the first owned row
+            nf = torch.nonzero(self.own(self.code).reshape(-1) == 0).reshape(-1).contiguous()
+            pk.noflow_idx, pk.n_noflow = nf.data_ptr(), int(nf.numel())
+        self._pack_keep = (geo32, w32, coef, inv_rough, S32, lut, rowg, nf)
         self.packed = pk
 
     def release_generic_inputs(self):
@@ -548,6 +553,8 @@ class ChannelsEngine(object):
                     self.mid_step_hook()
                 L.check(self.lib.tfb_channels_step_packed_dw_b(
                     C.byref(a), C.byref(self.packed), L.stream_ptr()), 'tfb_channels_step_packed_dw_b')
+                L.check(self.lib.tfb_channels_step_packed_dw_c(
+                    C.byref(a), C.byref(self.packed), L.stream_ptr()), 'tfb_channels_step_packed_dw_c')
             self.last_path = 'packed'
         else:
             if peer is not None:
