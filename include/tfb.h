@@ -455,6 +455,48 @@ typedef struct {
 int64_t tfb_sizeof_met_energy_args(void);
 int tfb_met_energy(const tfb_met_energy_args *a, void *stream);
 
+/* ------------------------------------------------------------------------
+ * DEM / channel-geometry preparation.
+ * ---------------------------------------------------------------------- */
+
+/* Depression filling, IN PLACE on the float32 DEM: utils/fill_pits.py
+ * fill_pits() :358-640 (priority flood from the seeds of get_start_pixels()
+ * :178-356: valid border cells, cells next to nodata, cells holding
+ * closed_code; non-finite values become `nodata`).  The result is the unique
+ * lowest surface >= DEM that drains to the seeds, computed by tiled chaotic
+ * relaxation (bit-identical to the heap order of the reference).
+ * close_nodata = 0: what the reference does -- :404-409 uses the ROW numbers of
+ * the nodata cells as flat cell IDs, so nodata cells stay open and are flooded
+ * up to their rim while cells with flat index r < ny (r a row holding nodata)
+ * are walled off; close_nodata = 1: the documented intent (nodata cells closed).
+ * `scratch` = DEVICE, tfb_fill_pits_scratch_bytes(ny, nx) bytes.  HOST outputs:
+ * n_raised (cells whose elevation was raised), n_rounds (relaxation rounds). */
+int64_t tfb_fill_pits_scratch_bytes(int32_t ny, int32_t nx);
+int tfb_fill_pits(float *dem, int32_t ny, int32_t nx, float nodata, float closed_code,
+                  int32_t close_nodata, void *scratch, int64_t *n_raised, int32_t *n_rounds, void *stream);
+
+/* slope = (z - z[first downstream cell that is lower]) / path length, fp64:
+ * utils/new_slopes.py get_new_slope_grid() :174-316, including its treatment of
+ * walkers that run past their noflow cell (parent ID 0 = cell (0, 0)).
+ * `scratch` = DEVICE int32[2*ny*nx + 1]; longest_path (HOST, may be NULL) = the
+ * number of iterations the reference's loop executes. */
+int tfb_d8_new_slope(const float *dem, const uint8_t *code, const float *dx,
+                     const float *dy, const float *dd, int32_t ny, int32_t nx,
+                     float nodata, int32_t *scratch, double *slope,
+                     int32_t *longest_path, void *stream);
+
+/* smallest positive value and maximum of a float32 grid (HOST outputs; +inf / 0
+ * when no value is positive) -- the A1, A2 of get_grid_from_TCA(). */
+int tfb_area_range(const float *A, int64_t n, float *min_pos, float *max_val, void *stream);
+
+/* grid = c * A^p, 1.0 where A <= 0: utils/parameterize.py get_grid_from_TCA()
+ * :93-215 (channel width, Manning n, bankfull depth from contributing area).
+ * single_precision != 0 rounds A^p and the product to float32 as numpy does
+ * when p and c are float32 there (the "p and g1 given" branch).  Either output
+ * may be NULL. */
+int tfb_power_law_grid(const float *A, int64_t n, double c, double p,
+                       int32_t single_precision, double *out64, float *out32, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,6 +64,8 @@ def load():
         lib.tfo_d8_flow_grid.argtypes = [vp, i32, i32, C.c_float, C.c_float, C.c_float, f64, i32,
                                          vp, vp, C.POINTER(C.c_int)]
         lib.tfo_d8_area.argtypes = [vp, i32, i32, f64, vp, vp, vp]
+        lib.tfo_fill_pits.argtypes = [vp, i32, i32, C.c_float, C.c_float, i32]
+        lib.tfo_fill_pits.restype = C.c_int64
         _lib = lib
     return _lib
 
@@ -83,6 +85,16 @@ def d8_flow_grid(DEM, dx, dy, dd, nodata=-9999.0, link_flats=True):
                                  float(nodata), int(link_flats), _p(res), _p(code), C.byref(n))
     assert rc == 0
     return code, n.value
+
+
+def fill_pits(DEM, nodata=-9999.0, closed_basin_code=-32000.0, close_nodata=False):
+    """In place on a C-contiguous float32 array; returns the number of raised cells."""
+    assert DEM.dtype == np.float32 and DEM.flags.c_contiguous and DEM.ndim == 2
+    n = load().tfo_fill_pits(_p(DEM), DEM.shape[0], DEM.shape[1], nodata, closed_basin_code,
+                             int(bool(close_nodata)))
+    if n < 0:
+        raise MemoryError('tfo_fill_pits')
+    return int(n)
 
 
 def d8_area(code, pixel_area, with_counts=False):

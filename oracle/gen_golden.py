@@ -481,6 +481,69 @@ def gen_met_energy():
     np.savez_compressed(os.path.join(GOLD, 'met_energy.npz'), **out)
 
 
+def gen_prep(work):
+    """DEM / geometry preparation: the reference's fill_pits() on DEMs
+    with many depressions, nodata holes, NaNs and a closed-basin code; its
+    get_new_slope_grid() and get_grid_from_TCA() run from files."""
+    from topoflow.utils import fill_pits as fp, new_slopes as ns, parameterize as pz
+    from topoflow36_b200 import grid_io
+    import time as _time
+    import types
+    # fill_pits.py:511 calls time.sleep(float32(0.001)), a TypeError on Python 3.12:
+    # give the module a `time` whose sleep() takes anything (nothing else is touched)
+    fp.time = types.SimpleNamespace(time=_time.time, sleep=lambda s: None)
+    out = {}
+    # 1. depression filling: rough DEM without regional tilt -> depressions of all sizes
+    for tag, (ny, nx), seed in (('a', (97, 131), 5), ('b', (160, 75), 6)):
+        DEM = synth.fractal_dem(ny, nx, seed=seed, sigma=3.0, sy=0.0005, sx=0.0002)
+        DEM = np.float32(np.round(DEM * 8.0) / 8.0)
+        DEM[30:34, 40:47] = -9999.0
+        DEM[0, 5:9] = -9999.0                    # nodata on the border
+        DEM[1, 20] = -9999.0                     # on the interior's rim (wrapped rolls)
+        DEM[60, 10] = np.nan
+        DEM[70, 50] = np.inf
+        DEM[50, 60] = -32000.0                   # closed-basin code
+        if tag == 'b':
+            DEM[ny - 2, 30:33] = -9999.0
+            DEM[100:103, nx - 2] = -9999.0
+        out['fill_%s_in' % tag] = DEM.copy()
+        D2 = DEM.copy()
+        rh.quiet_call(fp.fill_pits, D2, 'FLOAT', nx, ny, SILENT=True)
+        out['fill_%s_out' % tag] = D2
+    # 2. path-length slopes and power-law grids, from files
+    ny, nx = 150, 131
+    DEM = synth.fractal_dem(ny, nx, seed=21, sigma=1.5, sy=0.004, sx=0.002)
+    DEM = np.float32(np.round(DEM * 4.0) / 4.0)
+    DEM[40:43, 50:53] = -9999.0
+    w, a, n = synth.channel_params(ny, nx, seed=21)
+    cdir = os.path.join(work, 'prep')
+    synth.write_case(cdir, DEM, np.zeros_like(DEM), w, a, nval=n, link_flats=1)
+    cfg_dir = cdir + os.sep
+    rh.quiet_call(ns.get_new_slope_grid, site_prefix='Synth', case_prefix='Case1',
+                  cfg_dir=cfg_dir, slope_file='Synth_newslope.rtg')
+    info = grid_io.read_rti(os.path.join(cdir, 'Synth.rti'))
+    out['slope_DEM'] = DEM
+    out['slope_new'] = grid_io.read_rtg(os.path.join(cdir, 'Synth_newslope.rtg'), info)
+    import topoflow.components.d8_global as d8g
+    d8 = d8g.d8_component()
+    rh.quiet_call(d8.initialize, cfg_file=os.path.join(cdir, 'Case1_d8_global.cfg'),
+                  SILENT=True, REPORT=False)
+    rh.quiet_call(d8.update, 0)
+    out['slope_code'] = np.uint8(d8.d8_grid)
+    area = np.float32(d8.A)
+    grid_io.write_rtg(os.path.join(cdir, 'Synth_area.rtg'), area, info)
+    out['tca_area'] = area
+    cases = {'w': dict(g1=25.0, g2=1.5),                        # min/max of A (float64 p)
+             'n': dict(g1=0.03, p=-0.2),                        # p given (float32 branch)
+             'd': dict(A1=50.0, g1=3.0, A2=0.01, g2=0.2)}       # two points
+    for tag, kw in cases.items():
+        rh.quiet_call(pz.get_grid_from_TCA, site_prefix='Synth', topo_dir=cfg_dir,
+                      area_file='Synth_area.rtg', out_file='Synth_tca_%s.rtg' % tag,
+                      REPORT=False, **kw)
+        out['tca_' + tag] = grid_io.read_rtg(os.path.join(cdir, 'Synth_tca_%s.rtg' % tag), info)
+    np.savez_compressed(os.path.join(GOLD, 'prep.npz'), **out)
+
+
 def main():
     rh.import_reference()
     os.makedirs(GOLD, exist_ok=True)
@@ -493,6 +556,7 @@ def main():
         gen_attenuate(work)
         gen_geographic(work)
         gen_d8(work)
+        gen_prep(work)
         gen_sources()
         gen_met_energy()
         with open(os.path.join(GOLD, 'meta.json'), 'w') as fh:

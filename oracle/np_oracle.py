@@ -284,6 +284,136 @@ def d8_slope(DEM, code, ds):
 
 
 # ---------------------------------------------------------------------------
+# DEM / geometry preparation  (utils/fill_pits.py, new_slopes.py, parameterize.py)
+# ---------------------------------------------------------------------------
+def fill_pits_seeds(DEM, nodata=np.float32(-9999), closed_basin_code=-32000):
+    """utils/fill_pits.py get_start_pixels :178-356 -> boolean seed grid.  Non-finite
+    values of DEM are set to nodata IN PLACE (:232-235).  The 8 'neighbours' of an
+    interior cell are rolls of the interior sub-array (they wrap inside it)."""
+    ny, nx = DEM.shape
+    DEM[~np.isfinite(DEM)] = nodata
+    seed = np.zeros((ny, nx), dtype=bool)
+    seed[0, :] = DEM[0, :] > nodata
+    seed[-1, :] = DEM[-1, :] > nodata
+    seed[1:-1, 0] = DEM[1:-1, 0] > nodata
+    seed[1:-1, -1] = DEM[1:-1, -1] > nodata
+    zc = DEM[1:ny - 1, 1:nx - 1]
+    zs = np.full(zc.shape, np.inf, dtype=DEM.dtype)
+    for dr in (-1, 0, 1):
+        for dc in (-1, 0, 1):
+            if dr or dc:
+                zs = np.minimum(zs, np.roll(np.roll(zc, dr, axis=0), dc, axis=1))
+    seed[1:-1, 1:-1] = (zc == closed_basin_code) | ((zc > nodata) & (zs <= nodata))
+    return seed
+
+
+def fill_pits(DEM, nodata=np.float32(-9999), closed_basin_code=-32000, close_nodata=False):
+    """utils/fill_pits.py fill_pits :358-640 with the heapq branch (USE_MY_HEAP = False):
+    priority flood from the seeds; an OPEN neighbour of the popped cell is raised to the
+    popped elevation if lower, then pushed.  In place; returns the number raised.
+    Neighbour IDs are flat offsets checked against [0, n) only (:523-541), as there.
+
+    What the reference DOES with nodata (close_nodata=False, the default here): :404-409
+    takes ``where(DEM <= nodata)`` of the 2-D grid and keeps only its ROW numbers, then
+    closes the cells whose FLAT index equals one of those row numbers.  So the nodata
+    cells themselves stay open, lie lowest and are flooded up to their rim like any
+    depression, while a handful of cells with flat index < ny are walled off instead
+    (unless they are seeds, :437).  close_nodata=True is the documented intent (nodata
+    cells closed)."""
+    import heapq
+    ny, nx = DEM.shape
+    seed = fill_pits_seeds(DEM, nodata, closed_basin_code)
+    flat = DEM.reshape(-1)
+    n = flat.size
+    OPEN, CLOSED, ON_HEAP = 0, 1, 2
+    C = np.zeros(n, dtype=np.uint8)
+    if close_nodata:
+        C[flat <= nodata] = CLOSED
+    else:
+        C[np.where(DEM <= nodata)[0]] = CLOSED          # row numbers used as flat IDs
+    ids = np.flatnonzero(seed.reshape(-1))
+    heap = list(zip(flat[ids].tolist(), ids.tolist()))
+    heapq.heapify(heap)
+    C[ids] = ON_HEAP
+    incs = (-nx - 1, -nx, -nx + 1, -1, 1, nx - 1, nx, nx + 1)
+    zl = flat.tolist()
+    Cl = C.tolist()
+    n_raised = 0
+    while heap:
+        zmin, k = heapq.heappop(heap)
+        Cl[k] = CLOSED
+        for d in incs:
+            j = k + d
+            if 0 <= j < n and Cl[j] == OPEN:
+                if zl[j] < zmin:
+                    zl[j] = zmin
+                    n_raised += 1
+                Cl[j] = ON_HEAP
+                heapq.heappush(heap, (zl[j], j))
+    flat[:] = np.array(zl, dtype=DEM.dtype)
+    return n_raised
+
+
+def new_slope_grid(DEM, code, ds, nodata=-9999.0):
+    """utils/new_slopes.py get_new_slope_grid :174-316 -> (slope float64, n_reps).
+    All cells walk down their flow paths together; a cell takes the first positive drop
+    from ITS OWN elevation over the accumulated path length.  Walkers that pass a noflow
+    cell continue on cell (0, 0) (parent ID 0) until the longest path is done."""
+    ny, nx = code.shape
+    pr, pc = d8_parent_ids(code)
+    pid_grid = (pr * nx + pc).astype(np.int32)
+    z2 = DEM
+    pIDs = (pr, pc)
+    distance = np.float64(ds)
+    slope = np.zeros((ny, nx), dtype='float64')
+    n_reps = 0
+    DONE = False
+    while not DONE:
+        z1 = DEM[pIDs]
+        with np.errstate(invalid='ignore'):
+            dz = z2 - z1
+            w1 = np.logical_or(z1 <= nodata, code == 0)
+            dz[w1] = 0
+            wg = np.logical_and(slope == 0, dz > 0)
+        nb = np.invert(wg).sum()
+        if wg.sum() > 0:
+            slope[wg] = dz[wg] / distance[wg]
+        distance += ds[pIDs]
+        pID_vals = pid_grid[pIDs]
+        pIDs = divmod(pID_vals, nx)
+        n_reps += 1
+        DONE = (nb == 0) or (pID_vals.max() == 0) or (n_reps > 4 * nx)
+    return slope, n_reps
+
+
+def grid_from_TCA(A, A1=None, g1=None, A2=None, g2=None, p=None):
+    """utils/parameterize.py get_grid_from_TCA :93-215 without the file IO ->
+    (grid, c, p); numpy's own dtype rules decide float32 vs float64."""
+    if g1 is not None and g2 is not None and A1 is not None and A2 is not None:
+        p = np.log(g1 / g2) / np.log(A1 / A2)
+        c = g1 / (A1 ** p)
+    elif p is not None and g1 is not None:
+        A1 = A.max()
+        c = g1 / (A1 ** p)
+    elif g1 is not None and g2 is not None:
+        A1 = A.max()
+        A2 = A[A > 0].min()
+        p = np.log(g1 / g2) / np.log(A1 / A2)
+        c = g1 / (A1 ** p)
+    else:
+        raise ValueError('not enough input parameters to compute c & p')
+    w1 = (A <= 0)
+    if p < 0:
+        Ac = A.copy()
+        Ac[w1] = 1.0
+        grid = c * Ac ** p
+    else:
+        grid = c * A ** p
+    grid[w1] = 1.0
+    return grid, c, p
+
+
+# ---------------------------------------------------------------------------
 # Channel routing  (components/channels_base.py)
 # ---------------------------------------------------------------------------
 G_ACCEL = np.float64(9.81)

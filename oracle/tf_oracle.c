@@ -458,3 +458,85 @@ int tfo_d8_area(const uint8_t *code, int ny, int nx, double pixel_area,
     free(pending); free(queue);
     return 0;
 }
+
+/* ---------------------------------------------------------------------------
+ * Depression filling: utils/fill_pits.py fill_pits() :358-640, get_start_pixels()
+ * :178-356 -- priority flood with a binary heap of (elevation, ID) pairs, ordered
+ * like Python tuples.  close_nodata = 0 reproduces what the reference does with the
+ * "closed" array (:404-409: the ROW numbers of the nodata cells are used as flat IDs);
+ * see oracle/np_oracle.fill_pits.  In place; returns the number of raised cells.
+ * ------------------------------------------------------------------------- */
+typedef struct { float z; int64_t id; } tfo_hp;
+static inline int hp_less(tfo_hp a, tfo_hp b) { return a.z < b.z || (a.z == b.z && a.id < b.id); }
+static void hp_push(tfo_hp *h, int64_t *n, tfo_hp v) {
+    int64_t i = (*n)++;
+    while (i > 0) {
+        const int64_t p = (i - 1) >> 1;
+        if (!hp_less(v, h[p])) break;
+        h[i] = h[p]; i = p;
+    }
+    h[i] = v;
+}
+static tfo_hp hp_pop(tfo_hp *h, int64_t *n) {
+    const tfo_hp top = h[0], v = h[--(*n)];
+    int64_t i = 0;
+    for (;;) {
+        int64_t c = 2 * i + 1;
+        if (c >= *n) break;
+        if (c + 1 < *n && hp_less(h[c + 1], h[c])) ++c;
+        if (!hp_less(h[c], v)) break;
+        h[i] = h[c]; i = c;
+    }
+    if (*n > 0) h[i] = v;
+    return top;
+}
+
+int64_t tfo_fill_pits(float *dem, int ny, int nx, float nodata, float closed_code, int close_nodata)
+{
+    const int64_t n = (int64_t)ny * nx;
+    uint8_t *C = (uint8_t *)calloc((size_t)n, 1);       /* 0 open, 1 closed, 2 on heap */
+    uint8_t *seed = (uint8_t *)calloc((size_t)n, 1);
+    tfo_hp *heap = (tfo_hp *)malloc((size_t)n * sizeof(tfo_hp));
+    if (!C || !seed || !heap) { free(C); free(seed); free(heap); return -1; }
+    for (int64_t i = 0; i < n; ++i) if (!isfinite(dem[i])) dem[i] = nodata;       /* :232-235 */
+    for (int r = 0; r < ny; ++r)
+        for (int c = 0; c < nx; ++c) {
+            const int64_t i = (int64_t)r * nx + c;
+            const float z = dem[i];
+            if (r == 0 || r == ny - 1 || c == 0 || c == nx - 1) { seed[i] = z > nodata; continue; }
+            const int my = ny - 2, mx = nx - 2;           /* rolls of the interior sub-array */
+            float zs = INFINITY;
+            for (int k = 0; k < 8; ++k) {
+                int rr = r - 1 + NBR_DR[k], cc = c - 1 + NBR_DC[k];
+                rr = (rr < 0) ? rr + my : ((rr >= my) ? rr - my : rr);
+                cc = (cc < 0) ? cc + mx : ((cc >= mx) ? cc - mx : cc);
+                const float v = dem[(int64_t)(rr + 1) * nx + cc + 1];
+                if (v < zs) zs = v;
+            }
+            seed[i] = (z == closed_code) || (z > nodata && zs <= nodata);
+        }
+    for (int r = 0; r < ny; ++r)
+        for (int c = 0; c < nx; ++c)
+            if (dem[(int64_t)r * nx + c] <= nodata) {
+                if (close_nodata) C[(int64_t)r * nx + c] = 1;
+                else if (r < n) C[r] = 1;                 /* row number used as a flat ID */
+            }
+    int64_t nh = 0, n_raised = 0;
+    for (int64_t i = 0; i < n; ++i)
+        if (seed[i]) { C[i] = 2; tfo_hp v = {dem[i], i}; hp_push(heap, &nh, v); }
+    const int64_t incs[8] = {-nx - 1, -nx, -nx + 1, -1, 1, nx - 1, nx, nx + 1};
+    while (nh > 0) {
+        const tfo_hp t = hp_pop(heap, &nh);
+        C[t.id] = 1;
+        for (int k = 0; k < 8; ++k) {
+            const int64_t j = t.id + incs[k];             /* range check only (:523-541) */
+            if (j < 0 || j >= n || C[j] != 0) continue;
+            if (dem[j] < t.z) { dem[j] = t.z; ++n_raised; }
+            C[j] = 2;
+            tfo_hp v = {dem[j], j};
+            hp_push(heap, &nh, v);
+        }
+    }
+    free(C); free(seed); free(heap);
+    return n_raised;
+}

@@ -70,3 +70,17 @@ def test_treynor_storm(treynor, treynor_kw):
         assert rel_err(got, series[i]) <= 1e-12
     for n in GRIDS:
         assert rel_err(getattr(ch, n), treynor_kw['s1200_' + n]) <= 1e-12, n
+
+
+def test_c_fill_pits_vs_reference_fixture_and_numpy_oracle():
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'prep.npz')
+    d = np.load(gold)
+    from oracle import c_oracle as co, np_oracle as o
+    for t in 'ab':
+        D = d['fill_%s_in' % t].copy()
+        n = co.fill_pits(D)
+        assert np.array_equal(D, d['fill_%s_out' % t]) and n > 1000
+        D1, D2 = d['fill_%s_in' % t].copy(), d['fill_%s_in' % t].copy()
+        assert co.fill_pits(D1, close_nodata=True) == o.fill_pits(D2, close_nodata=True)
+        assert np.array_equal(D1, D2)

@@ -257,3 +257,24 @@ def test_geographic_pixels_bit_exact(geo_gold, tmp_path):
             assert np.array_equal(getattr(ch, n), g[tag + '_' + n], equal_nan=True), n
         for n in SCALARS:
             assert float(getattr(ch, n)) == float(g[tag + '_' + n]), n
+
+
+def test_prep_oracle_vs_reference_fixture():
+    """fill_pits / get_new_slope_grid / get_grid_from_TCA restatements against the
+    reference's outputs (tests/golden/prep.npz, gen_prep)."""
+    from conftest import load_golden
+    d = load_golden('prep.npz')
+    for t in 'ab':
+        D = d['fill_%s_in' % t].copy()
+        o.fill_pits(D)
+        assert np.array_equal(D, d['fill_%s_out' % t]), t
+    DEM, code = d['slope_DEM'], d['slope_code']
+    dx, dy, dd = o.pixel_dims(DEM.shape[0], 30.0, 30.0)
+    ds, _ = o.d8_ds_dw(code, dx, dy, dd)
+    S, reps = o.new_slope_grid(DEM, code, ds)
+    assert reps > 3 and np.array_equal(np.float32(S), d['slope_new'])
+    A = d['tca_area']
+    for tag, kw in {'w': dict(g1=25.0, g2=1.5), 'n': dict(g1=0.03, p=-0.2),
+                    'd': dict(A1=50.0, g1=3.0, A2=0.01, g2=0.2)}.items():
+        g, c, p = o.grid_from_TCA(A, **kw)
+        assert np.array_equal(np.float32(g), d['tca_' + tag]), tag

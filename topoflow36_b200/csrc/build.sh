@@ -11,7 +11,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17
        -fmad=false -prec-div=true -prec-sqrt=true -ftz=false
        -Xcompiler -fPIC -Xcompiler -O2)
 objs=()
-for f in tfb_capi tfb_channels tfb_channels_packed tfb_d8 tfb_sources; do
+for f in tfb_capi tfb_channels tfb_channels_packed tfb_d8 tfb_sources tfb_prep; do
   if [ ! -f "$here/$f.o" ] || [ "$here/$f.cu" -nt "$here/$f.o" ] || \
      [ "$here/tfb_common.cuh" -nt "$here/$f.o" ] || [ "$here/tfb_channels_common.cuh" -nt "$here/$f.o" ] || [ "$here/../../include/tfb.h" -nt "$here/$f.o" ]; then
     "$NVCC" "${FLAGS[@]}" ${TFB_EXTRA_NVCC_FLAGS:-} -c "$here/$f.cu" -o "$here/$f.o" &

@@ -431,6 +431,111 @@ extern "C" int tfb_d8_slope(const float *dem, const uint8_t *code, const float *
     return TFB_OK;
 }
 
+// ---------------------------------------------------------------- new slopes
+// utils/new_slopes.get_new_slope_grid (:174-316): every cell walks down its D8 flow
+// path until the drop from ITS OWN elevation is positive; slope = drop / path length.
+// The reference advances all cells together for J iterations, J = the longest flow
+// path of the grid; walkers that have passed their noflow cell sit on cell (0, 0)
+// (parent ID 0) and are compared with DEM[0, 0] there -- reproduced below.
+//
+// Longest flow path: the same last-child-continues walk as the area pass, carrying
+// the number of cells on the longest upstream chain.
+__global__ void __launch_bounds__(256)
+d8_longest_walk_kernel(int ny, int nx, int32_t *len, int32_t *word, int32_t *J) {
+    const int c0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r0 = blockIdx.y * blockDim.y + threadIdx.y;
+    if (c0 >= nx || r0 >= ny) return;
+    int r = r0, c = c0;
+    int w = word[(int64_t)r * nx + c];
+    if (((w >> 16) & 0xff) == 0 || ((w >> 8) & 0xff) != 0) return;    // not a source
+    int h = 1;
+    while (true) {
+        if (!(w & kWParent)) {                             // the next cell is a noflow cell
+            // parent ID 0 is the reference's "no parent" marker AND the ID of cell (0, 0):
+            // a path through (1, 1) -> NW already counts as finished on (1, 1)
+            if (r == 1 && c == 1 && ((w >> 16) & 0xff) == 64 && h > 1) h -= 1;
+            atomicMax(J, h);
+            break;
+        }
+        int dr, dc;
+        code_offset((unsigned)((w >> 16) & 0xff), dr, dc);
+        r += dr; c += dc;
+        const int64_t ip = (int64_t)r * nx + c;
+        if (w & kWOnly) {
+            w = __ldcg(word + ip);
+            h += 1;
+        } else {
+            atomicMax(&len[ip], h);
+            __threadfence();
+            const int old = atomicSub(&word[ip], 1);
+            if ((old & 0xf) != 1) break;
+            __threadfence();
+            h = 1 + atomicMax(&len[ip], 0);
+            w = old;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+d8_new_slope_kernel(const float *__restrict__ dem, const uint8_t *__restrict__ code,
+                    const float *__restrict__ dx, const float *__restrict__ dy,
+                    const float *__restrict__ dd, int ny, int nx, float nodata,
+                    const int32_t *__restrict__ Jp, double *__restrict__ slope) {
+    const int c0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r0 = blockIdx.y * blockDim.y + threadIdx.y;
+    if (c0 >= nx || r0 >= ny) return;
+    const int64_t i0 = (int64_t)r0 * nx + c0;
+    unsigned cd = code[i0];
+    double s = 0.0;
+    if (cd != 0) {                                   // own code 0: dz is forced to 0 (:221)
+        // iterations the reference executes: J, capped by n_reps > 4 nx (:255)
+        const int64_t cap = 4LL * nx + 1;
+        const int64_t J = (*Jp < 1) ? 1 : ((*Jp < cap) ? *Jp : cap);
+        const float z2 = dem[i0];
+        int r = r0, c = c0;
+        double dist = (double)ds_of(cd, dx[r], dy[r], dd[r]);
+        for (int64_t j = 1; j <= J; ++j) {
+            int dr = 0, dc = 0;
+            if (cd != 0) { code_offset(cd, dr, dc); r += dr; c += dc; }
+            else { r = 0; c = 0; }                   // parent ID of a noflow cell is 0
+            const float z1 = dem[(int64_t)r * nx + c];
+            if (!(z1 <= nodata)) {
+                const float dz = __fsub_rn(z2, z1);
+                if (dz > 0.0f) { s = (double)dz / dist; break; }
+            }
+            const bool was_noflow = (cd == 0);
+            cd = code[(int64_t)r * nx + c];
+            if (was_noflow) break;                   // on (0, 0): nothing changes any more
+            dist += (double)ds_of(cd, dx[r], dy[r], dd[r]);
+        }
+    }
+    slope[i0] = s;
+}
+
+extern "C" int tfb_d8_new_slope(const float *dem, const uint8_t *code, const float *dx,
+                                const float *dy, const float *dd, int32_t ny, int32_t nx,
+                                float nodata, int32_t *scratch, double *slope,
+                                int32_t *longest_path, void *stream) {
+    TFB_ARG_CHECK(dem && code && dx && dy && dd && scratch && slope && ny > 0 && nx > 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = (int64_t)ny * nx;
+    int32_t *word = scratch, *len = scratch + n, *J = scratch + 2 * n;
+    dim3 b(32, 8);
+    // the area pass's init kernel zeroes its fp32 output: used here for `len` (+ J)
+    TFB_CUDA_CHECK(cudaMemsetAsync(J, 0, sizeof(int32_t), st));
+    d8_area_init_kernel<<<grid2d(ny, nx, b), b, 0, st>>>(code, ny, nx, (float *)len, nullptr, word);
+    d8_longest_walk_kernel<<<grid2d(ny, nx, b), b, 0, st>>>(ny, nx, len, word, J);
+    d8_new_slope_kernel<<<grid2d(ny, nx, b), b, 0, st>>>(dem, code, dx, dy, dd, ny, nx, nodata,
+                                                        J, slope);
+    TFB_CUDA_CHECK(cudaGetLastError());
+    if (longest_path) {
+        TFB_CUDA_CHECK(cudaMemcpyAsync(longest_path, J, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        TFB_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (*longest_path < 1) *longest_path = 1;
+    }
+    return TFB_OK;
+}
+
 extern "C" int tfb_d8_area(const uint8_t *code, int32_t ny, int32_t nx, double pixel_area,
                            const double *pixel_area_row, float *A, int64_t *count,
                            int32_t *pending, int64_t *n_done, void *stream) {

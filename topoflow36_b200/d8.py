@@ -132,3 +132,16 @@ class D8Toolkit(object):
                                       self.dy.data_ptr(), self.dd.data_ptr(), self.ny, self.nx,
                                       S.data_ptr(), self._st()), 'tfb_d8_slope')
         return S
+
+    def new_slope(self):
+        """utils/new_slopes.get_new_slope_grid (:174-316): drop to the first LOWER cell
+        down the flow path over the path length, fp64.  Returns (slope, n_reps)."""
+        n = self.ny * self.nx
+        scratch = torch.empty(2 * n + 1, dtype=torch.int32, device=self.device)
+        S = torch.empty((self.ny, self.nx), dtype=torch.float64, device=self.device)
+        reps = C.c_int32(0)
+        L.check(self.lib.tfb_d8_new_slope(self.DEM.data_ptr(), self.code.data_ptr(),
+                                          self.dx.data_ptr(), self.dy.data_ptr(), self.dd.data_ptr(),
+                                          self.ny, self.nx, C.c_float(self.nodata), scratch.data_ptr(),
+                                          S.data_ptr(), C.byref(reps), self._st()), 'tfb_d8_new_slope')
+        return S, int(reps.value)

@@ -60,8 +60,6 @@ class d8_component(BMI_base.BMI_component):
                 setattr(self, k, v)
         if int(self.LR_PERIODIC) or int(self.TB_PERIODIC):
             raise NotImplementedError('periodic D8 boundaries are not part of the GPU path')
-        if int(self.FILL_PITS_IN_Z0):
-            raise NotImplementedError('FILL_PITS_IN_Z0: pit filling is out of scope (SURVEY 8f-3)')
         if not hasattr(self, 'DEM_file'):
             self.DEM_file = self.site_prefix + '_DEM.rtg'
         self.DEM_file = self.topo_directory + os.path.basename(self.DEM_file) \
@@ -71,6 +69,8 @@ class d8_component(BMI_base.BMI_component):
             self.status = 'initialized'
             return
         self.read_DEM()
+        # FILL_PITS_IN_Z0 is read but never acted on by the reference's d8_global (only
+        # d8_local.py:218 honours it); same here.  Fill explicitly with prep.fill_pits().
         dx, dy, dd = grid_io.pixel_sizes_by_row(self.rti)
         # cast to float32 as the reference does (d8_base.py:515-518)
         self.dx, self.dy, self.dd = np.float32(dx), np.float32(dy), np.float32(dd)

@@ -136,6 +136,13 @@ SIGNATURES = {
                               C.POINTER(_i64), vp]),
     'tfb_d8_slope': (C.c_int, [vp, vp, vp, vp, vp, _i32, _i32, vp, vp]),
     'tfb_d8_parent_ids': (C.c_int, [vp, _i32, _i32, vp, vp]),
+    'tfb_d8_new_slope': (C.c_int, [vp, vp, vp, vp, vp, _i32, _i32, _f32, vp, vp,
+                                   C.POINTER(_i32), vp]),
+    'tfb_fill_pits_scratch_bytes': (_i64, [_i32, _i32]),
+    'tfb_fill_pits': (C.c_int, [vp, _i32, _i32, _f32, _f32, _i32, vp, C.POINTER(_i64),
+                                C.POINTER(_i32), vp]),
+    'tfb_area_range': (C.c_int, [vp, _i64, C.POINTER(_f32), C.POINTER(_f32), vp]),
+    'tfb_power_law_grid': (C.c_int, [vp, _i64, _f64, _f64, _i32, vp, vp, vp]),
     'tfb_sizeof_channels_step_args': (_i64, []),
     'tfb_sizeof_channels_scalars': (_i64, []),
     'tfb_channels_partials_len': (_i64, [_i32, _i32]),
