@@ -116,6 +116,10 @@ int tfb_d8_slope(const float *dem, const uint8_t *code, const float *dx,
                  const float *dy, const float *dd, int32_t ny, int32_t nx,
                  float *S, void *stream);
 
+/* D8 "aspect": flow angle in radians, counter-clockwise from east, float32, 0
+ * for noflow cells (d8_global.update_aspect_grid :1350-1376). */
+int tfb_d8_aspect(const uint8_t *code, int64_t n, float *aspect, void *stream);
+
 /* parent_ID_grid (int32 flat IDs, 0 for noflow/border cells)
  * (d8_global.update_parent_ID_grid :578-650). */
 int tfb_d8_parent_ids(const uint8_t *code, int32_t ny, int32_t nx,
@@ -441,7 +445,7 @@ int tfb_evap_priestley_taylor(tfb_sg T_air, tfb_sg T_surf, tfb_sg Qn_SW,
  * input is scalar-or-grid; outputs are optional DEVICE grids.  julian_day (and
  * TSN_offset, the clock time relative to true solar noon [h]) are formed on the
  * host from the model date (met_base.update_julian_day :1938-1993).  Albedo is
- * an input: the 'aging' method's 3-day snowfall ring buffer is not on this path. */
+ * an input here; tfb_met_albedo updates it. */
 typedef struct {
     int32_t ny, nx;
     int32_t satterlund;       /* saturation vapour pressure method (else Brutsaert) */
@@ -451,6 +455,19 @@ typedef struct {
     double *e_sat_air, *e_air, *T_dew, *T_surf, *e_sat_surf, *Ri, *Dn, *Dh, *Qh, *W_p,
            *e_surf, *Qe, *Qn_SW, *em_air, *Qn_LW, *Q_sum;
 } tfb_met_energy_args;
+
+/* Albedo (met_base.update_albedo :1995-2045), in place on the DEVICE grid `albedo`.
+ * aging != 0: snow albedo 0.4 + 0.44 exp(-n r) with n = days since the snowfall of
+ * the last three days reached 3 cm; `ring` = DEVICE doubles [slots][ny*nx] holding
+ * the per-step snow depths P_snow*dt*rho_H2O/rho_snow (slots = int(259200/dt),
+ * met_base.py:1126-1133), `head` = slot that receives this step's value (the
+ * caller advances it by one, modulo slots, per call), `n_days` = DEVICE grid.
+ * aging == 0: the 'simple' method (0.75 on snow).  Both: 0.3 on snow-free ice,
+ * 0.15 on bare ground. */
+int tfb_met_albedo(tfb_sg P_snow, tfb_sg T_air, tfb_sg h_snow, tfb_sg h_ice,
+                   int32_t ny, int32_t nx, double dt, double rho_H2O, double rho_snow,
+                   int32_t aging, double *ring, int32_t slots, int32_t head,
+                   double *n_days, double *albedo, void *stream);
 
 int64_t tfb_sizeof_met_energy_args(void);
 int tfb_met_energy(const tfb_met_energy_args *a, void *stream);

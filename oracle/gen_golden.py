@@ -481,6 +481,40 @@ def gen_met_energy():
     np.savez_compressed(os.path.join(GOLD, 'met_energy.npz'), **out)
 
 
+def gen_albedo():
+    """met_base.update_albedo (:1995-2045), 'aging' and 'simple', called on a bare
+    meteorology component over 30 six-hour steps with two snowfalls; the ring-buffer
+    state is set up as initialize() does (:1121-1133)."""
+    from topoflow.components import met_base
+    ny, nx, dt = 9, 13, 21600.0
+    rng = np.random.default_rng(77)
+    out = {}
+    for method in ('aging', 'simple'):
+        m = met_base.met_component()
+        m.dt = dt
+        m.albedo_type = 'Grid'
+        m.albedo = rng.random((ny, nx)) * 0.5 + 0.2
+        m.rho_H2O, m.rho_snow = np.float64(1000.0), np.float64(250.0)
+        m.n = 0
+        m.days_per_dt = m.dt / 86400
+        m.P_snow_3day_grid = np.zeros((int(np.int64(259200 / m.dt)), ny, nx))
+        out[method + '_albedo0'] = m.albedo.copy()
+        series = {k: [] for k in ('P_snow', 'T_air', 'h_snow', 'h_ice', 'albedo', 'n')}
+        for step in range(30):
+            snowing = step in (2, 3, 27)
+            m.P_snow = (rng.random((ny, nx)) * (4e-6 if snowing else 2e-8))
+            m.T_air = rng.random((ny, nx)) * 8.0 - 5.0
+            m.h_snow = np.where(rng.random((ny, nx)) < 0.7, rng.random((ny, nx)) * 0.4, 0.0)
+            m.h_ice = np.where(rng.random((ny, nx)) < 0.3, 0.5, 0.0)
+            m.update_albedo(method=method)
+            for k in ('P_snow', 'T_air', 'h_snow', 'h_ice', 'albedo'):
+                series[k].append(np.array(getattr(m, k), dtype='float64'))
+            series['n'].append(np.zeros((ny, nx)) + m.n)
+        for k, v in series.items():
+            out[method + '_' + k] = np.stack(v)
+    np.savez_compressed(os.path.join(GOLD, 'albedo.npz'), **out)
+
+
 def gen_prep(work):
     """DEM / geometry preparation: the reference's fill_pits() on DEMs
     with many depressions, nodata holes, NaNs and a closed-basin code; its
@@ -530,6 +564,8 @@ def gen_prep(work):
                   SILENT=True, REPORT=False)
     rh.quiet_call(d8.update, 0)
     out['slope_code'] = np.uint8(d8.d8_grid)
+    d8.update_aspect_grid()
+    out['aspect'] = np.float32(d8.aspect)
     area = np.float32(d8.A)
     grid_io.write_rtg(os.path.join(cdir, 'Synth_area.rtg'), area, info)
     out['tca_area'] = area
@@ -559,6 +595,7 @@ def main():
         gen_prep(work)
         gen_sources()
         gen_met_energy()
+        gen_albedo()
         with open(os.path.join(GOLD, 'meta.json'), 'w') as fh:
             json.dump(meta, fh, indent=1, sort_keys=True)
     finally:

@@ -274,6 +274,15 @@ def d8_area_kahn(code, pixel_area, with_counts=False):
     return A
 
 
+def d8_aspect(code):
+    """components/d8_global.py:1350-1376: flow angle, radians CCW from east, float32."""
+    a = np.linspace(0.0, 2 * np.pi, 9)
+    aspect = np.zeros(code.shape, dtype='float32')
+    for cd, k in ((1, 1), (2, 0), (4, 7), (8, 6), (16, 5), (32, 4), (64, 3), (128, 2)):
+        aspect[code == cd] = a[k]
+    return aspect
+
+
 def d8_slope(DEM, code, ds):
     """components/d8_global.py:1334-1348."""
     pr, pc = d8_parent_ids(code)
@@ -861,6 +870,29 @@ def clear_sky_radiation(lat_deg, julian_day, W_p, th, alpha, beta, albedo, dust)
     dark = np.logical_or((th <= T_sr), (th >= T_ss))
     K_cs = np.where(dark, f(0), K_cs)
     return K_cs
+
+
+def albedo_update(st, P_snow, T_air, h_snow, h_ice, dt, rho_H2O=1000.0, rho_snow=300.0,
+                  method='aging'):
+    """met_base.update_albedo :1995-2045.  `st` = dict(albedo, n, ring) with ring of shape
+    (int(259200/dt), ny, nx) (met_base.py:1121-1133); updated in place, returns albedo."""
+    albedo = st['albedo']
+    if method == 'aging':
+        r = np.where((T_air > 0), 0.12, 0.05)
+        K, alpha0 = 0.44, 0.4
+        st['ring'] = np.roll(st['ring'], -1, axis=0)
+        st['ring'][st['ring'].shape[0] - 1] = P_snow * dt * (rho_H2O / rho_snow)
+        total = np.sum(st['ring'], axis=0)
+        st['n'] = np.where((total >= 0.03), 0, st['n'])
+        st['n'] = np.where((total < 0.03), st['n'] + dt / 86400, st['n'])
+        snow_albedo = alpha0 + K * np.exp(-st['n'] * r)
+        albedo = np.where((h_snow > 0), snow_albedo, albedo)
+    else:
+        albedo = np.where((h_snow > 0), np.float64(0.75), albedo)
+    albedo = np.where(((h_snow == 0) & (h_ice > 0)), np.float64(0.3), albedo)
+    albedo = np.where(((h_snow == 0) & (h_ice == 0)), np.float64(0.15), albedo)
+    st['albedo'] = albedo
+    return albedo
 
 
 def met_energy_chain(T_air, RH, uz, z, z0_air, h_snow, h_ice, p0, albedo, em_surf, lat_deg,

@@ -273,8 +273,26 @@ def test_prep_oracle_vs_reference_fixture():
     ds, _ = o.d8_ds_dw(code, dx, dy, dd)
     S, reps = o.new_slope_grid(DEM, code, ds)
     assert reps > 3 and np.array_equal(np.float32(S), d['slope_new'])
+    assert np.array_equal(o.d8_aspect(code), d['aspect'])
     A = d['tca_area']
     for tag, kw in {'w': dict(g1=25.0, g2=1.5), 'n': dict(g1=0.03, p=-0.2),
                     'd': dict(A1=50.0, g1=3.0, A2=0.01, g2=0.2)}.items():
         g, c, p = o.grid_from_TCA(A, **kw)
         assert np.array_equal(np.float32(g), d['tca_' + tag]), tag
+
+
+def test_albedo_oracle_vs_reference_fixture():
+    """met_base.update_albedo ('aging' with the 3-day snowfall ring, 'simple')."""
+    from conftest import load_golden
+    d = load_golden('albedo.npz')
+    for method in ('aging', 'simple'):
+        slots = int(np.int64(259200 / 21600.0))
+        st = dict(albedo=d[method + '_albedo0'].copy(), n=0, ring=np.zeros((slots, 9, 13)))
+        for k in range(30):
+            a = o.albedo_update(st, d[method + '_P_snow'][k], d[method + '_T_air'][k],
+                                d[method + '_h_snow'][k], d[method + '_h_ice'][k], 21600.0,
+                                1000.0, 250.0, method)
+            assert np.array_equal(a, d[method + '_albedo'][k]), (method, k)
+            if method == 'aging':
+                assert np.array_equal(np.zeros((9, 13)) + st['n'], d['aging_n'][k])
+    assert d['aging_n'].max() > 3.0

@@ -96,6 +96,7 @@ def test_new_slope_grid_vs_reference_fixture(prep):
     S_o, reps_o = o.new_slope_grid(DEM, prep['slope_code'], ds)
     assert reps == reps_o and np.array_equal(S, S_o)                 # fp64, bit for bit
     assert (S > 0).sum() > 0.9 * (prep['slope_code'] != 0).sum()
+    assert np.array_equal(tk.aspect().cpu().numpy(), prep['aspect'])    # update_aspect_grid
 
 
 def test_new_slope_grid_flat_paths_and_cell_00():

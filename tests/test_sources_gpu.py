@@ -5,6 +5,8 @@ compiled without FMA contraction, so equality is exact."""
 import numpy as np
 import pytest
 
+from conftest import rel_err
+
 pytestmark = pytest.mark.gpu
 
 
@@ -147,3 +149,22 @@ def test_unfused_coupling_on_device_equals_fused(sources_gold):
     assert abs(infil.vol_IN - s2.vol_IN) <= 1e-12 * s2.vol_IN
     assert abs(snow.vol_SM - s2.vol_SM) <= 1e-12 * max(s2.vol_SM, 1e-300)
     assert float(fused.Q.max()) > 0
+
+
+@pytest.mark.parametrize('method', ['aging', 'simple'])
+def test_albedo_vs_reference_fixture(method):
+    """met_base.update_albedo over 30 six-hour steps with two snowfalls: the 3-day ring,
+    the day counter and the albedo after every step (exp() differs from numpy's by <= 1 ulp)."""
+    from conftest import load_golden
+    from topoflow36_b200 import sources as S
+    d = load_golden('albedo.npz')
+    alb = S.Albedo(9, 13, 21600.0, albedo=d[method + '_albedo0'], method=method,
+                   rho_H2O=1000.0, rho_snow=250.0)
+    assert method == 'simple' or alb.slots == 12
+    for k in range(30):
+        alb.update(d[method + '_P_snow'][k], d[method + '_T_air'][k], d[method + '_h_snow'][k],
+                   d[method + '_h_ice'][k])
+        got = alb.albedo.cpu().numpy()
+        assert rel_err(got, d[method + '_albedo'][k]) <= 1e-15, k
+        if method == 'aging':
+            assert np.array_equal(alb.n.cpu().numpy(), d['aging_n'][k]), k

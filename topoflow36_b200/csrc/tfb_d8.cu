@@ -431,6 +431,33 @@ extern "C" int tfb_d8_slope(const float *dem, const uint8_t *code, const float *
     return TFB_OK;
 }
 
+// ---------------------------------------------------------------- aspect
+struct AspectLut { float a[9]; };
+__global__ void d8_aspect_kernel(const uint8_t *__restrict__ code, int64_t n, AspectLut lut,
+                                 float *__restrict__ aspect) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned cd = code[i];
+    // Jenson codes -> index into linspace(0, 2 pi, 9) (d8_global.py:1358-1373)
+    int k = 0;
+    switch (cd) {
+        case 1: k = 1; break;   case 2: k = 0; break;   case 4: k = 7; break;
+        case 8: k = 6; break;   case 16: k = 5; break;  case 32: k = 4; break;
+        case 64: k = 3; break;  case 128: k = 2; break; default: k = 0;
+    }
+    aspect[i] = (cd == 0) ? 0.0f : lut.a[k];
+}
+
+extern "C" int tfb_d8_aspect(const uint8_t *code, int64_t n, float *aspect, void *stream) {
+    TFB_ARG_CHECK(code && aspect && n > 0);
+    AspectLut lut;
+    const double step = (2.0 * 3.141592653589793 - 0.0) / 8.0;       // np.linspace
+    for (int k = 0; k < 9; ++k) lut.a[k] = (float)(k == 8 ? 2.0 * 3.141592653589793 : k * step);
+    d8_aspect_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(code, n, lut, aspect);
+    TFB_CUDA_CHECK(cudaGetLastError());
+    return TFB_OK;
+}
+
 // ---------------------------------------------------------------- new slopes
 // utils/new_slopes.get_new_slope_grid (:174-316): every cell walks down its D8 flow
 // path until the drop from ITS OWN elevation is positive; slope = drop / path length.

@@ -327,6 +327,45 @@ static int n_blocks(int64_t n) {
     return (int)(want < cap ? want : cap);
 }
 
+// ---- albedo (met_base.update_albedo :1995-2045) -----------------------------------------
+// 'aging' (Rohrer & Braun 1994): albedo = 0.4 + 0.44 exp(-n r) where snow lies, n = days
+// since the snowfall of the last 3 days (a ring of `slots` per-step snow depths) reached
+// 3 cm; 0.3 on bare ice, 0.15 on bare ground.  The reference rolls a (slots, ny, nx) array
+// and sums it over time with np.sum: a sequential sum oldest -> newest, kept here by
+// walking the ring from the slot after `head`.
+__global__ void __launch_bounds__(256)
+met_albedo_kernel(tfb_sg P_snow, tfb_sg T_air, tfb_sg h_snow, tfb_sg h_ice, int64_t ncell,
+                  double *__restrict__ ring, int slots, int head, double *__restrict__ n_days,
+                  double dt, double ws_ratio, double days_per_dt, int aging,
+                  double *__restrict__ albedo) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncell) return;
+    const double hs = sg_at(h_snow, i), hi = sg_at(h_ice, i);
+    double a = albedo[i];
+    if (aging) {
+        ring[(int64_t)head * ncell + i] = (sg_at(P_snow, i) * dt) * ws_ratio;       // newest (:2017)
+        int s = head + 1;
+        if (s == slots) s = 0;
+        double total = ring[(int64_t)s * ncell + i];                              // oldest
+        for (int k = 1; k < slots; ++k) {
+            if (++s == slots) s = 0;
+            total += ring[(int64_t)s * ncell + i];
+        }
+        double n = n_days[i];
+        if (total >= 0.03) n = 0.0;
+        else if (total < 0.03) n = n + days_per_dt;
+        n_days[i] = n;
+        const double r = (sg_at(T_air, i) > 0.0) ? 0.12 : 0.05;
+        const double snow_albedo = 0.4 + 0.44 * exp(-n * r);
+        if (hs > 0.0) a = snow_albedo;
+    } else {
+        if (hs > 0.0) a = 0.75;
+    }
+    if (hs == 0.0 && hi > 0.0) a = 0.3;
+    if (hs == 0.0 && hi == 0.0) a = 0.15;
+    albedo[i] = a;
+}
+
 }  // namespace tfb
 
 using namespace tfb;
@@ -417,6 +456,21 @@ extern "C" int tfb_channels_minmax(const double *Q, const double *u, const doubl
     const int64_t n = (int64_t)ny * nx;
     minmax_kernel<<<n_blocks(n), kThreads, 0, (cudaStream_t)stream>>>(
         Q, u, d, vol, ny, nx, out6, vol_sum, partials, ticket);
+    TFB_CUDA_CHECK(cudaGetLastError());
+    return TFB_OK;
+}
+
+extern "C" int tfb_met_albedo(tfb_sg P_snow, tfb_sg T_air, tfb_sg h_snow, tfb_sg h_ice,
+                              int32_t ny, int32_t nx, double dt, double rho_H2O, double rho_snow,
+                              int32_t aging, double *ring, int32_t slots, int32_t head,
+                              double *n_days, double *albedo, void *stream) {
+    TFB_ARG_CHECK(albedo && ny > 0 && nx > 0);
+    TFB_ARG_CHECK(!aging || (ring && n_days && slots > 0 && head >= 0 && head < slots));
+    const int64_t n = (int64_t)ny * nx;
+    const double ratio = rho_H2O / rho_snow;                                      // :2016
+    met_albedo_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        P_snow, T_air, h_snow, h_ice, n, ring, slots, head, n_days, dt, ratio, dt / 86400.0,
+        aging, albedo);
     TFB_CUDA_CHECK(cudaGetLastError());
     return TFB_OK;
 }

@@ -145,3 +145,10 @@ class D8Toolkit(object):
                                           self.ny, self.nx, C.c_float(self.nodata), scratch.data_ptr(),
                                           S.data_ptr(), C.byref(reps), self._st()), 'tfb_d8_new_slope')
         return S, int(reps.value)
+
+    def aspect(self):
+        """d8_global.update_aspect_grid (:1350-1376): flow angle [rad], float32."""
+        a = torch.empty((self.ny, self.nx), dtype=torch.float32, device=self.device)
+        L.check(self.lib.tfb_d8_aspect(self.code.data_ptr(), self.ny * self.nx, a.data_ptr(),
+                                       self._st()), 'tfb_d8_aspect')
+        return a

@@ -156,5 +156,8 @@ class d8_component(BMI_base.BMI_component):
             self.update_slope_grid()
         return self._slope_dev.cpu().numpy()
 
+    def update_aspect_grid(self, REPORT=False):
+        self.aspect = self.toolkit.aspect().cpu().numpy()
+
     def finalize(self):
         self.status = 'finalized'

@@ -136,6 +136,7 @@ SIGNATURES = {
                               C.POINTER(_i64), vp]),
     'tfb_d8_slope': (C.c_int, [vp, vp, vp, vp, vp, _i32, _i32, vp, vp]),
     'tfb_d8_parent_ids': (C.c_int, [vp, _i32, _i32, vp, vp]),
+    'tfb_d8_aspect': (C.c_int, [vp, _i64, vp, vp]),
     'tfb_d8_new_slope': (C.c_int, [vp, vp, vp, vp, vp, _i32, _i32, _f32, vp, vp,
                                    C.POINTER(_i32), vp]),
     'tfb_fill_pits_scratch_bytes': (_i64, [_i32, _i32]),
@@ -177,6 +178,8 @@ SIGNATURES = {
                                        vp]),
     'tfb_snow_degree_day': (C.c_int, [SG, SG, SG, SG, _f64, _f64, SG, _f64,
                                       _i32, _i32, vp, vp, vp, vp, vp, vp, vp]),
+    'tfb_met_albedo': (C.c_int, [SG, SG, SG, SG, _i32, _i32, _f64, _f64, _f64, _i32, vp, _i32,
+                                 _i32, vp, vp, vp]),
     'tfb_sizeof_met_energy_args': (_i64, []),
     'tfb_met_energy': (C.c_int, [C.POINTER(MetEnergyArgs), vp]),
     'tfb_evap_priestley_taylor': (C.c_int, [SG, SG, SG, SG, _f64, _f64, _f64,

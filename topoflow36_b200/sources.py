@@ -140,7 +140,7 @@ class MetEnergy(_Base):
     W_p, Qe, clear-sky Qn_SW on sloping cells (solar_funcs.Clear_Sky_Radiation), em_air,
     Qn_LW, Q_sum.  Inputs are scalars or (ny, nx) grids; `julian_day` and `TSN_offset`
     come from solar_host.julian_day / tsn_offset (the date arithmetic stays on the
-    host).  Albedo is an input (the reference's 'aging' ring buffer is not here)."""
+    host).  Albedo is an input (see Albedo below)."""
 
     def __init__(self, ny, nx, satterlund=False, dust_atten=0.08, **kw):
         _Base.__init__(self, ny, nx, 1.0, **kw)
@@ -158,3 +158,37 @@ class MetEnergy(_Base):
             setattr(a, n, getattr(self, n).data_ptr())
         import ctypes as C
         L.check(self.lib.tfb_met_energy(C.byref(a), L.stream_ptr()), 'tfb_met_energy')
+
+
+class Albedo(_Base):
+    """met_base.update_albedo (:1995-2045): 'aging' snow albedo (Rohrer & Braun 1994) with
+    the 3-day snowfall ring of met_base.py:1121-1133 kept on the device, or the 'simple'
+    method.  `albedo` is updated in place every update()."""
+
+    def __init__(self, ny, nx, dt, albedo=0.3, method='aging', rho_H2O=1000.0, rho_snow=300.0, **kw):
+        _Base.__init__(self, ny, nx, dt, **kw)
+        self.method = method
+        self.rho_H2O, self.rho_snow = float(rho_H2O), float(rho_snow)
+        self.albedo = self._zeros()
+        self.albedo += torch.as_tensor(np.float64(albedo)).to(self.device)
+        self.slots = int(np.int64(259200 / self.dt))
+        self.head = self.slots - 1 if self.slots > 0 else 0      # roll(-1): the new value goes last
+        if method == 'aging':
+            if self.slots < 1:
+                raise ValueError('albedo aging needs dt <= 3 days')
+            self.ring = torch.zeros((self.slots, self.ny, self.nx), dtype=torch.float64,
+                                    device=self.device)
+            self.n = self._zeros()
+        else:
+            self.ring = self.n = None
+
+    def update(self, P_snow, T_air, h_snow, h_ice):
+        aging = self.method == 'aging'
+        L.check(self.lib.tfb_met_albedo(
+            self._sg('P_snow', P_snow), self._sg('T_air', T_air), self._sg('h_snow', h_snow),
+            self._sg('h_ice', h_ice), self.ny, self.nx, self.dt, self.rho_H2O, self.rho_snow,
+            int(aging), self.ring.data_ptr() if aging else None, max(self.slots, 1), self.head,
+            self.n.data_ptr() if aging else None, self.albedo.data_ptr(), L.stream_ptr()),
+            'tfb_met_albedo')
+        if aging:
+            self.head = (self.head + 1) % self.slots
