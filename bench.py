@@ -305,7 +305,11 @@ def main():
     e1.record()
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    by_rank = [float(ms.item()) / args.steps]
     if world > 1:
+        every = torch.zeros(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(every, ms)
+        by_rank = [float(v) / args.steps for v in every.tolist()]
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if sampler else None
     ms_per_step = float(ms.item()) / args.steps
@@ -434,6 +438,7 @@ def main():
     out = {
         'metric': METRIC, 'value': value, 'unit': 'Gcell-updates/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
+        'ms_per_step_by_rank': by_rank,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'grid': [ny * world, NX], 'rows_per_gpu': ny,

@@ -357,12 +357,18 @@ int tfb_channels_step_packed_dw_c(const tfb_channels_step_args *a,
  * neighbours' halo rows mapped with tfb_peer_open.  tfb_channels_step_packed_p2p
  * then fuses the halo exchange into the routing kernel: the warps that compute
  * the first / last owned row store the new discharge ALSO into the neighbour's
- * halo row (peer stores over NVLink, overlapped with the rest of the grid), and
- * the last CTA publishes "step k done" in a flag word in the neighbour's memory.
- * Before a step is launched the stream waits (cuStreamWaitValue32, no spinning
- * kernel) until both neighbours have finished the previous step -- which orders
- * both the halo reads and the re-use of the double-buffered halo rows.  No NCCL
- * call per step.  Kinematic wave only (the diffusive wave keeps NCCL). */
+ * halo row (peer stores over NVLink).  The first and last tile rows are
+ * processed FIRST; when the last of them has retired one thread publishes
+ * "step k done" in a flag word in the neighbour's memory, so the transfer
+ * overlaps the rest of the grid.  On the receiving side the producer warp of a
+ * boundary tile polls its local flag (ld.acquire.sys, bounded) until the
+ * neighbour has published the previous step -- which orders both the halo reads
+ * and the re-use of the double-buffered halo rows -- before it issues that
+ * tile's TMA loads; in lock-step operation the flag has been set for almost a
+ * whole step by then.  No NCCL call, no stream memory operation and no extra
+ * kernel per step (TFB_P2P_STREAM_WAIT=1 in the environment selects
+ * cuStreamWaitValue32 in front of the launch instead).  Kinematic wave only (the
+ * diffusive wave keeps NCCL). */
 typedef struct {
     double *up_Q;             /* neighbour above: its LOWER halo row of the buffer this
                                  step writes (row ny_up of its owned rows), or NULL   */

@@ -352,7 +352,29 @@ __global__ void zero_at_kernel(double *__restrict__ x, const int64_t *__restrict
 }
 
 struct PkMaps { CUtensorMap Q, vol, coef, I, H, T, w, geo; };
-struct PkPeer { double *up_Q, *down_Q; uint32_t *up_flag, *down_flag; uint32_t value; };
+struct PkPeer {
+    double *up_Q, *down_Q;                  // the neighbours' halo rows of the new discharge
+    uint32_t *up_flag, *down_flag;          // their "rows from rank r have arrived" flags
+    uint32_t value;                         // published there when my boundary tiles are done
+    const uint32_t *from_up, *from_down;    // my flags, written by the neighbours
+    uint32_t need;                          // value they must hold before I touch a boundary tile
+};
+
+// Wait (bounded) until a neighbour has published step `need`: its halo row is in my memory
+// and it no longer reads the halo row of its own that my boundary tiles overwrite.
+__device__ __forceinline__ bool peer_flag_wait(const uint32_t *flag, uint32_t need) {
+    for (unsigned i = 0; i < (1u << 24); ++i) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v >= need) {
+            // the halo row is read by the TMA unit (async proxy) next
+            asm volatile("fence.proxy.async;" ::: "memory");
+            return true;
+        }
+        __nanosleep(64);
+    }
+    return false;
+}
 struct PkMapsB { CUtensorMap D, N, S, w, geo; };
 
 // CTA-level reduction of the per-thread accumulators, per-CTA row, last-CTA fold in
@@ -489,12 +511,25 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
         if (lane == 0) {
             int stage = 0;
             unsigned phase = 0;
+            bool up_ok = false, down_ok = false;
             const unsigned tx = (unsigned)(TC::nQ + TC::nD * (1 + (kKW ? 1 : 0) + (use_i ? 1 : 0) +
                                                               (use_h ? 1 : 0) + (use_t ? 1 : 0)) + 2 * TC::nF);
             for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
                 if (!mbar_wait(&empty_bar[stage], phase ^ 1u)) { s_fail = 1; break; }
                 int ty, txi;
                 tile_of(k, t, ty, txi);
+                if (kKW && t < k.n_boundary) {
+                    // peer-memory halo: the first / last tile row reads a row a neighbour
+                    // stored and overwrites (in its memory) a row it may still be reading
+                    if (peer.from_up && ty == 0 && !up_ok) {
+                        if (!peer_flag_wait(peer.from_up, peer.need)) { s_fail = 1; break; }
+                        up_ok = true;
+                    }
+                    if (peer.from_down && ty == k.tiles_y - 1 && !down_ok) {
+                        if (!peer_flag_wait(peer.from_down, peer.need)) { s_fail = 1; break; }
+                        down_ok = true;
+                    }
+                }
                 const int c0 = txi * kTW, r0 = ty * kTR;
                 unsigned char *st = smem + (size_t)stage * SL::bytes;
                 mbar_arrive_expect_tx(&full_bar[stage], tx);
@@ -1166,12 +1201,21 @@ extern "C" int tfb_channels_step_packed_p2p(const tfb_channels_step_args *ap,
     cudaStream_t st = (cudaStream_t)stream;
     // both neighbours must have finished the previous step: their halo rows are in
     // my memory, and they no longer read the halo rows this step overwrites
-    if (ph->from_up && (rc = stream_wait_geq(st, ph->from_up, ph->step))) return rc;
-    if (ph->from_down && (rc = stream_wait_geq(st, ph->from_down, ph->step))) return rc;
     PkPeer peer;
     peer.up_Q = ph->up_Q; peer.down_Q = ph->down_Q;
     peer.up_flag = ph->up_flag; peer.down_flag = ph->down_flag;
     peer.value = ph->step + 1u;
+    if (!getenv("TFB_P2P_STREAM_WAIT")) {
+        // the producer warps of the boundary tiles poll the flags themselves: no stream
+        // memory operation (several microseconds each) between consecutive steps
+        peer.from_up = ph->from_up; peer.from_down = ph->from_down;
+        peer.need = ph->step;
+    } else {
+        peer.from_up = peer.from_down = nullptr;
+        peer.need = 0u;
+        if (ph->from_up && (rc = stream_wait_geq(st, ph->from_up, ph->step))) return rc;
+        if (ph->from_down && (rc = stream_wait_geq(st, ph->from_down, ph->step))) return rc;
+    }
     if (mode == PK_SRC_NONE) return launch_main<PK_SRC_NONE, PK_KW, CfgNone>(*ap, *pp, k, st, peer);
     if (mode == PK_SRC_GA) return launch_main<PK_SRC_GA, PK_KW, CfgGA>(*ap, *pp, k, st, peer);
     return launch_main<PK_SRC_FULL, PK_KW, CfgFull>(*ap, *pp, k, st, peer);
