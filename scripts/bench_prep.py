@@ -60,6 +60,10 @@ def main():
     tk = D8Toolkit(DEM)
     tk.update()
     tk.new_slope()                                     # warm-up
+    ea, eb = ev(), ev()
+    ea.record()
+    tk.update_area(with_counts=True)                   # basin-wide networks on the filled DEM
+    eb.record()
     e0, e1, e2 = ev(), ev(), ev()
     e0.record()
     S, reps = tk.new_slope()
@@ -67,6 +71,8 @@ def main():
     W, c, p = P.grid_from_TCA(tk.A, g1=25.0, g2=1.5)
     e2.record()
     torch.cuda.synchronize()
+    ms['d8_area_filled_dem'] = ea.elapsed_time(eb)
+    checks['max_cells_draining_through_one_cell'] = int(tk.count.max())
     ms['new_slope'] = e0.elapsed_time(e1)
     ms['grid_from_TCA'] = e1.elapsed_time(e2)
     checks['longest_flow_path'] = reps

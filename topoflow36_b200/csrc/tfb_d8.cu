@@ -7,6 +7,7 @@
 // update_area_grid :1029-1332, update_slope_grid :1334-1348) and the tie table
 // of components/d8_base.py:711-772.  All of it is integer / fp32 work and must
 // be BIT-EXACT against the reference; nothing here may be re-associated.
+#include <stdlib.h>
 #include "tfb_common.cuh"
 
 #include <string.h>
@@ -563,6 +564,86 @@ extern "C" int tfb_d8_new_slope(const float *dem, const uint8_t *code, const flo
     return TFB_OK;
 }
 
+// Second form of the topological pass, without atomics.  Every cell owns one 64-bit word
+// {fp32 area, uint32 count}, 0 = not computed yet (a computed count is >= 1).  A walker
+// stores its cell's word, issues fence.sc and then reads the words of ALL children of the
+// next cell: if one is still 0 it stops (that child's walker will come by later), else
+// it sums them in the reference's order and goes on.  With sequentially consistent
+// fences between "store mine" and "load the siblings'" at least one of any two siblings
+// sees the other (the store-buffering litmus), so the last arrival always continues;
+// when two arrive within a fence latency of each other BOTH may continue -- they compute
+// and store identical words, which is harmless.  Per junction the critical path is one
+// fence and one round trip to L2 instead of fence + atomic + fence + loads.
+__device__ __forceinline__ unsigned long long pack_an(float a, unsigned n) {
+    return ((unsigned long long)n << 32) | (unsigned long long)__float_as_uint(a);
+}
+
+__global__ void __launch_bounds__(256)
+d8_area_walk2_kernel(int ny, int nx, double pixel_area, const double *__restrict__ pa_row,
+                     unsigned long long *cell, const int32_t *__restrict__ word) {
+    const int c0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r0 = blockIdx.y * blockDim.y + threadIdx.y;
+    if (c0 >= nx || r0 >= ny) return;
+    int r = r0, c = c0;
+    int64_t i = (int64_t)r * nx + c;
+    int w = __ldg(word + i);
+    if (((w >> 16) & 0xff) == 0 || ((w >> 8) & 0xff) != 0) return;    // not a source
+    float a = (float)(pa_row ? pa_row[r] : pixel_area);
+    unsigned n = 1u;
+    while (true) {
+        __stcg(cell + i, pack_an(a, n));
+        if (!(w & kWParent)) break;       // drains into a noflow cell
+        int dr, dc;
+        code_offset((unsigned)((w >> 16) & 0xff), dr, dc);
+        r += dr; c += dc;
+        const int64_t ip = (int64_t)r * nx + c;
+        const float pa = (float)(pa_row ? pa_row[r] : pixel_area);
+        const int wp = __ldg(word + ip);
+        if (w & kWOnly) {
+            a = pa + a;                   // the single child's value is still in the register
+            n = 1u + n;
+        } else {
+            asm volatile("fence.sc.gpu;" ::: "memory");
+            const int cm = (wp >> 8) & 0xff;
+            unsigned long long v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                v[k] = (cm & (1 << k))
+                           ? __ldcg(cell + ip + (int64_t)kNbrDRow[k] * nx + kNbrDCol[k]) : 1ull;
+            bool ready = true;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) ready = ready && (v[k] != 0ull);
+            if (!ready) break;            // a sibling arrives later and continues
+            a = pa;
+            n = 1u;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (cm & (1 << k)) {
+                    a += __uint_as_float((unsigned)(v[k] & 0xffffffffull));
+                    n += (unsigned)(v[k] >> 32);
+                }
+            }
+        }
+        w = wp;
+        i = ip;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+d8_area_unpack_kernel(const unsigned long long *cell, int64_t ncell, float *__restrict__ A,
+                      int64_t *count, unsigned long long *n_done) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool done = false;
+    if (i < ncell) {
+        const unsigned long long v = cell[i];          // may alias count[i]: read, then write
+        done = (v != 0ull);
+        A[i] = __uint_as_float((unsigned)(v & 0xffffffffull));
+        if (count) count[i] = (int64_t)(v >> 32);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, done);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_done, (unsigned long long)__popc(m));
+}
+
 extern "C" int tfb_d8_area(const uint8_t *code, int32_t ny, int32_t nx, double pixel_area,
                            const double *pixel_area_row, float *A, int64_t *count,
                            int32_t *pending, int64_t *n_done, void *stream) {
@@ -572,18 +653,40 @@ extern "C" int tfb_d8_area(const uint8_t *code, int32_t ny, int32_t nx, double p
     TFB_CUDA_CHECK(cudaMalloc(&d_done, sizeof(unsigned long long)));
     cudaError_t e = cudaMemsetAsync(d_done, 0, sizeof(unsigned long long), st);
     dim3 b(32, 8);
-    if (e == cudaSuccess) {
+    unsigned long long *tmp = nullptr;
+    const bool atomic_form = getenv("TFB_D8_AREA_ATOMIC") != nullptr ||
+                             (int64_t)ny * nx >= (1LL << 32);       // counts must fit 32 bits
+    if (e == cudaSuccess && atomic_form) {
         d8_area_init_kernel<<<grid2d(ny, nx, b), b, 0, st>>>(code, ny, nx, A, count, pending);
         d8_area_walk_kernel<<<grid2d(ny, nx, b), b, 0, st>>>(code, ny, nx, pixel_area,
                                                             pixel_area_row, A, count,
                                                             pending, d_done);
         e = cudaGetLastError();
+    } else if (e == cudaSuccess) {
+        const int64_t n = (int64_t)ny * nx;
+        unsigned long long *cell = (unsigned long long *)count;     // the words live in `count`
+        if (!cell) {
+            e = cudaMalloc(&tmp, (size_t)n * sizeof(unsigned long long));
+            cell = tmp;
+        }
+        if (e == cudaSuccess) {
+            // init zeroes A (and count = the words); without `count` the words are cleared here
+            d8_area_init_kernel<<<grid2d(ny, nx, b), b, 0, st>>>(code, ny, nx, A, count, pending);
+            if (tmp) e = cudaMemsetAsync(tmp, 0, (size_t)n * sizeof(unsigned long long), st);
+        }
+        if (e == cudaSuccess) {
+            d8_area_walk2_kernel<<<grid2d(ny, nx, b), b, 0, st>>>(ny, nx, pixel_area, pixel_area_row,
+                                                                 cell, pending);
+            d8_area_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cell, n, A, count, d_done);
+            e = cudaGetLastError();
+        }
     }
     unsigned long long h = 0;
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(&h, d_done, sizeof(h), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cudaFree(d_done);
+    if (tmp) cudaFree(tmp);
     if (e != cudaSuccess) {
         set_error("tfb_d8_area: %s", cudaGetErrorString(e));
         return TFB_ERR_CUDA;
