@@ -28,6 +28,16 @@ int sm_count() {
     return n;
 }
 
+// 256 bytes of device memory per device for the result words of the set-up functions
+// (allocated once, never freed: no cudaMalloc / cudaFree on their paths)
+void *small_scratch() {
+    static void *cached[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!cached[dev] && cudaMalloc(&cached[dev], 256) != cudaSuccess) cached[dev] = nullptr;
+    return cached[dev];
+}
+
 }  // namespace tfb
 
 extern "C" int tfb_abi_version(void) { return TFB_ABI_VERSION; }

@@ -359,8 +359,8 @@ extern "C" int tfb_d8_link_flats(int16_t *code, int16_t *scratch, int32_t ny, in
                                  int32_t max_reps, int32_t *n_reps, void *stream) {
     TFB_ARG_CHECK(code && scratch && ny > 0 && nx > 0);
     cudaStream_t st = (cudaStream_t)stream;
-    int32_t *d_cnt = nullptr;
-    TFB_CUDA_CHECK(cudaMalloc(&d_cnt, 2 * sizeof(int32_t)));
+    int32_t *d_cnt = (int32_t *)small_scratch();
+    TFB_ARG_CHECK(d_cnt != nullptr);
     int16_t *cur = code, *nxt = scratch;
     int reps = 0, rc = TFB_OK;
     while (true) {
@@ -389,7 +389,6 @@ extern "C" int tfb_d8_link_flats(int16_t *code, int16_t *scratch, int32_t ny, in
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { set_error("tfb_d8_link_flats: %s", cudaGetErrorString(e)); rc = TFB_ERR_CUDA; }
     }
-    cudaFree(d_cnt);
     if (n_reps) *n_reps = reps;
     return rc;
 }
@@ -469,15 +468,17 @@ extern "C" int tfb_d8_aspect(const uint8_t *code, int64_t n, float *aspect, void
 // Longest flow path: the same last-child-continues walk as the area pass, carrying
 // the number of cells on the longest upstream chain.
 __global__ void __launch_bounds__(256)
-d8_longest_walk_kernel(int ny, int nx, int32_t *len, int32_t *word, int32_t *J) {
+d8_longest_walk_kernel(int ny, int nx, int32_t *len, const int32_t *__restrict__ word, int32_t *J) {
     const int c0 = blockIdx.x * blockDim.x + threadIdx.x;
     const int r0 = blockIdx.y * blockDim.y + threadIdx.y;
     if (c0 >= nx || r0 >= ny) return;
     int r = r0, c = c0;
-    int w = word[(int64_t)r * nx + c];
+    int64_t i = (int64_t)r * nx + c;
+    int w = __ldg(word + i);
     if (((w >> 16) & 0xff) == 0 || ((w >> 8) & 0xff) != 0) return;    // not a source
-    int h = 1;
+    int h = 1;                        // cells on the longest chain that ends here (0 = unknown)
     while (true) {
+        __stcg(len + i, h);
         if (!(w & kWParent)) {                             // the next cell is a noflow cell
             // parent ID 0 is the reference's "no parent" marker AND the ID of cell (0, 0):
             // a path through (1, 1) -> NW already counts as finished on (1, 1)
@@ -489,18 +490,28 @@ d8_longest_walk_kernel(int ny, int nx, int32_t *len, int32_t *word, int32_t *J) 
         code_offset((unsigned)((w >> 16) & 0xff), dr, dc);
         r += dr; c += dc;
         const int64_t ip = (int64_t)r * nx + c;
+        const int wp = __ldg(word + ip);
         if (w & kWOnly) {
-            w = __ldcg(word + ip);
             h += 1;
         } else {
-            atomicMax(&len[ip], h);
-            __threadfence();
-            const int old = atomicSub(&word[ip], 1);
-            if ((old & 0xf) != 1) break;
-            __threadfence();
-            h = 1 + atomicMax(&len[ip], 0);
-            w = old;
+            // same protocol as d8_area_walk2_kernel: store mine, fence.sc, read all siblings
+            asm volatile("fence.sc.gpu;" ::: "memory");
+            const int cm = (wp >> 8) & 0xff;
+            int best = 0;
+            bool ready = true;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (cm & (1 << k)) {
+                    const int v = __ldcg(len + ip + (int64_t)kNbrDRow[k] * nx + kNbrDCol[k]);
+                    ready = ready && (v != 0);
+                    best = max(best, v);
+                }
+            }
+            if (!ready) break;
+            h = 1 + best;
         }
+        w = wp;
+        i = ip;
     }
 }
 
@@ -649,8 +660,8 @@ extern "C" int tfb_d8_area(const uint8_t *code, int32_t ny, int32_t nx, double p
                            int32_t *pending, int64_t *n_done, void *stream) {
     TFB_ARG_CHECK(code && A && pending && ny > 0 && nx > 0);
     cudaStream_t st = (cudaStream_t)stream;
-    unsigned long long *d_done = nullptr;
-    TFB_CUDA_CHECK(cudaMalloc(&d_done, sizeof(unsigned long long)));
+    unsigned long long *d_done = (unsigned long long *)small_scratch();
+    TFB_ARG_CHECK(d_done != nullptr);
     cudaError_t e = cudaMemsetAsync(d_done, 0, sizeof(unsigned long long), st);
     dim3 b(32, 8);
     unsigned long long *tmp = nullptr;
@@ -685,7 +696,6 @@ extern "C" int tfb_d8_area(const uint8_t *code, int32_t ny, int32_t nx, double p
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(&h, d_done, sizeof(h), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d_done);
     if (tmp) cudaFree(tmp);
     if (e != cudaSuccess) {
         set_error("tfb_d8_area: %s", cudaGetErrorString(e));

@@ -86,22 +86,29 @@ fill_init_kernel(float *dem, float *__restrict__ zz, float *__restrict__ W, int 
     if (z != raw) dem[i] = z;                                  // NaN / Inf -> nodata, in place
 }
 
+// One round: the warps of a persistent grid pop tiles from this round's work list; a tile
+// whose rim changed appends the neighbours that read that rim to the next round's list
+// (`queued[t]` = tile t sits in a list and has not been popped yet).
 __global__ void __launch_bounds__(32 * FWARPS)
 fill_relax_kernel(const float *__restrict__ zz, float *W, int ny, int nx, int tiles_y,
-                  int tiles_x, uint8_t *dirty_cur, uint8_t *dirty_next, unsigned *n_changed) {
+                  int tiles_x, const int *__restrict__ list_cur, int *list_next,
+                  unsigned *queued, const unsigned *n_cur, unsigned *n_next, unsigned *pop) {
     extern __shared__ float fsm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t = blockIdx.x * FWARPS + warp;
-    if (t >= tiles_y * tiles_x) return;
-    int is_dirty = 0;
-    if (lane == 0) {
-        is_dirty = dirty_cur[t];
-        if (is_dirty) dirty_cur[t] = 0;          // this buffer is the NEXT round's "next"
-    }
-    is_dirty = __shfl_sync(0xffffffffu, is_dirty, 0);
-    if (!is_dirty) return;
     float *sW = fsm + warp * ((FT + 2) * FSW + FT * FSZ);
     float *sZ = sW + (FT + 2) * FSW;
+    const unsigned n_tiles_round = *n_cur;
+    while (true) {
+    unsigned idx = 0;
+    if (lane == 0) idx = atomicAdd(pop, 1u);
+    idx = __shfl_sync(0xffffffffu, idx, 0);
+    if (idx >= n_tiles_round) break;
+    const int t = list_cur[idx];
+    if (lane == 0) {
+        atomicExch(queued + t, 0u);              // from here on a neighbour may queue me again
+        __threadfence();                         // ... and I read what it wrote before it tried
+    }
+    __syncwarp();
     const int ty = t / tiles_x, tx = t - ty * tiles_x;
     const int r0 = ty * FT, c0 = tx * FT;
     // load: W with a one-cell rim (outside the grid: +inf), z without
@@ -146,21 +153,31 @@ fill_relax_kernel(const float *__restrict__ zz, float *W, int ny, int nx, int ti
         any = true;
     }
 #undef TFB_RELAX
-    if (!any) return;
-    for (int i = 0; i < FT; ++i) {
-        const int r = r0 + i, c = c0 + lane;
-        if (r < ny && c < nx) __stcg(W + (int64_t)r * nx + c, sW[(i + 1) * FSW + lane + 1]);
+    if (any) {
+        for (int i = 0; i < FT; ++i) {
+            const int r = r0 + i, c = c0 + lane;
+            if (r < ny && c < nx) __stcg(W + (int64_t)r * nx + c, sW[(i + 1) * FSW + lane + 1]);
+        }
+        rim = __reduce_or_sync(0xffffffffu, rim);
+        __threadfence();                         // my W is visible before anybody is queued
+        if (lane < 8) {
+            // neighbour tile `lane` (NE, E, SE, S, SW, W, NW, N) reads my rim
+            const int dr = kNbrDRow[lane], dc = kNbrDCol[lane];
+            const unsigned need = (dr < 0 ? 1u : (dr > 0 ? 2u : 0u)) | (dc < 0 ? 4u : (dc > 0 ? 8u : 0u));
+            const int yy = ty + dr, xx = tx + dc;
+            if ((rim & need) == need && yy >= 0 && yy < tiles_y && xx >= 0 && xx < tiles_x) {
+                const int u = yy * tiles_x + xx;
+                if (atomicExch(queued + u, 1u) == 0u) list_next[atomicAdd(n_next, 1u)] = u;
+            }
+        }
     }
-    rim = __reduce_or_sync(0xffffffffu, rim);
-    if (lane < 8) {
-        // neighbour tile `lane` (NE, E, SE, S, SW, W, NW, N) reads my rim
-        const int dr = kNbrDRow[lane], dc = kNbrDCol[lane];
-        const unsigned need = (dr < 0 ? 1u : (dr > 0 ? 2u : 0u)) | (dc < 0 ? 4u : (dc > 0 ? 8u : 0u));
-        const int yy = ty + dr, xx = tx + dc;
-        if ((rim & need) == need && yy >= 0 && yy < tiles_y && xx >= 0 && xx < tiles_x)
-            dirty_next[yy * tiles_x + xx] = 1;
+    __syncwarp();
     }
-    if (lane == 0) atomicAdd(n_changed, 1u);
+}
+
+__global__ void fill_list_init_kernel(int *list, unsigned *queued, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { list[i] = i; queued[i] = 1u; }
 }
 
 __global__ void __launch_bounds__(256)
@@ -175,11 +192,6 @@ fill_finish_kernel(float *dem, const float *__restrict__ W, int64_t n,
     }
     const unsigned m = __ballot_sync(0xffffffffu, up);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_raised, (unsigned long long)__popc(m));
-}
-
-__global__ void fill_bytes_kernel(uint8_t *p, int64_t n, uint8_t v) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
 }
 
 // ---- power-law grid --------------------------------------------------------------------
@@ -220,59 +232,79 @@ power_law_kernel(const float *__restrict__ A, int64_t n, double c, double p, int
 }  // namespace tfb
 using namespace tfb;
 
+static inline int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
+constexpr int FBATCH = 16;       // rounds launched between two looks at the counters
+
 extern "C" int64_t tfb_fill_pits_scratch_bytes(int32_t ny, int32_t nx) {
     if (ny <= 0 || nx <= 0) return 0;
     const int64_t n = (int64_t)ny * nx;
     const int64_t tiles = (int64_t)((ny + FT - 1) / FT) * ((nx + FT - 1) / FT);
-    return 2 * n * (int64_t)sizeof(float) + ((2 * tiles + 255) / 256) * 256 + 256 +
-           (((int64_t)ny + 255) / 256) * 256;
+    // zz, W | two work lists | queued flags | counters | row flags
+    return 2 * n * (int64_t)sizeof(float) + 3 * align256(tiles * 4) + 512 + align256(ny);
 }
 
 extern "C" int tfb_fill_pits(float *dem, int32_t ny, int32_t nx, float nodata, float closed_code,
-                             int32_t close_nodata, void *scratch, int64_t *n_raised, int32_t *n_rounds, void *stream) {
+                             int32_t close_nodata, void *scratch, int64_t *n_raised,
+                             int32_t *n_rounds, void *stream) {
     TFB_ARG_CHECK(dem && scratch && ny > 0 && nx > 0);
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n = (int64_t)ny * nx;
     const int tiles_y = (ny + FT - 1) / FT, tiles_x = (nx + FT - 1) / FT;
     const int64_t tiles = (int64_t)tiles_y * tiles_x;
+    TFB_ARG_CHECK(tiles < (1LL << 31));
     float *zz = (float *)scratch, *W = zz + n;
-    uint8_t *dirty = (uint8_t *)(W + n);
-    constexpr int BATCH = 16;
-    unsigned *cnt = (unsigned *)(dirty + ((2 * tiles + 255) / 256) * 256);    // BATCH counters + n_raised
-    static_assert((BATCH + 2) * sizeof(unsigned) <= 256, "counter block");
-    uint8_t *row_flag = (uint8_t *)cnt + 256;
+    int *list0 = (int *)(W + n);
+    int *list1 = (int *)((char *)list0 + align256(tiles * 4));
+    unsigned *queued = (unsigned *)((char *)list1 + align256(tiles * 4));
+    // cnt[k] = length of round k's list (k = 0..FBATCH), pop[k] = tiles popped in round k
+    unsigned *cnt = (unsigned *)((char *)queued + align256(tiles * 4));
+    unsigned *pop = cnt + 32;
+    unsigned long long *raised = (unsigned long long *)(cnt + 64);
+    uint8_t *row_flag = (uint8_t *)cnt + 512;
+    static_assert(FBATCH + 1 <= 32 && FBATCH % 2 == 0, "counter block");
     TFB_CUDA_CHECK(cudaFuncSetAttribute(fill_relax_kernel,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, FSMEM));
     dim3 b(32, 8), g((nx + 31) / 32, (ny + 7) / 8);
     fill_rowflag_kernel<<<ny, 256, 0, st>>>(dem, nx, nodata, row_flag);
     fill_init_kernel<<<g, b, 0, st>>>(dem, zz, W, ny, nx, nodata, closed_code, close_nodata, row_flag);
-    fill_bytes_kernel<<<(unsigned)((tiles + 255) / 256), 256, 0, st>>>(dirty, tiles, 1);
-    fill_bytes_kernel<<<(unsigned)((tiles + 255) / 256), 256, 0, st>>>(dirty + tiles, tiles, 0);
+    fill_list_init_kernel<<<(unsigned)((tiles + 255) / 256), 256, 0, st>>>(list0, queued, (int)tiles);
     TFB_CUDA_CHECK(cudaGetLastError());
+    int ctas_per_sm = 1;
+    TFB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, fill_relax_kernel,
+                                                                 32 * FWARPS, FSMEM));
+    const int64_t want = (tiles + FWARPS - 1) / FWARPS;
+    const int64_t cap = (int64_t)sm_count() * (ctas_per_sm > 0 ? ctas_per_sm : 1);
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    unsigned h[64];
+    memset(h, 0, sizeof(h));
+    h[0] = (unsigned)tiles;
     int rounds = 0;
     bool done = false;
     // every relaxation lowers at least one of finitely many values: the loop terminates;
     // the bound only guards against a broken device
     const int64_t max_rounds = 8 * ((int64_t)tiles_y + tiles_x) * FT + 1024;
     while (!done && rounds < max_rounds) {
-        TFB_CUDA_CHECK(cudaMemsetAsync(cnt, 0, 256, st));
-        for (int k = 0; k < BATCH; ++k, ++rounds) {
-            uint8_t *cur = dirty + (rounds & 1) * tiles, *nxt = dirty + ((rounds + 1) & 1) * tiles;
-            fill_relax_kernel<<<(unsigned)((tiles + FWARPS - 1) / FWARPS), 32 * FWARPS, FSMEM, st>>>(
-                zz, W, ny, nx, tiles_y, tiles_x, cur, nxt, cnt + k);
+        TFB_CUDA_CHECK(cudaMemcpyAsync(cnt, h, 64 * sizeof(unsigned), cudaMemcpyHostToDevice, st));
+        for (int k = 0; k < FBATCH; ++k) {
+            int *cur = (k & 1) ? list1 : list0, *nxt = (k & 1) ? list0 : list1;
+            fill_relax_kernel<<<grid, 32 * FWARPS, FSMEM, st>>>(zz, W, ny, nx, tiles_y, tiles_x, cur,
+                                                                nxt, queued, cnt + k, cnt + k + 1, pop + k);
         }
         TFB_CUDA_CHECK(cudaGetLastError());
-        unsigned h[BATCH];
-        TFB_CUDA_CHECK(cudaMemcpyAsync(h, cnt, sizeof(h), cudaMemcpyDeviceToHost, st));
+        TFB_CUDA_CHECK(cudaMemcpyAsync(h, cnt, 33 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
         TFB_CUDA_CHECK(cudaStreamSynchronize(st));
-        for (int k = 0; k < BATCH; ++k)
-            if (h[k] == 0) { done = true; rounds = rounds - BATCH + k + 1; break; }
+        int ran = FBATCH;
+        for (int k = 1; k <= FBATCH; ++k)
+            if (h[k] == 0) { done = true; ran = k; break; }      // round k had nothing to do
+        rounds += ran;
+        const unsigned carry = h[FBATCH];
+        memset(h, 0, sizeof(h));
+        h[0] = carry;                                            // FBATCH is even: list0 again
     }
     if (!done) {
         set_error("tfb_fill_pits: no fixed point after %lld rounds", (long long)max_rounds);
         return TFB_ERR_NOT_CONVERGED;
     }
-    unsigned long long *raised = (unsigned long long *)(cnt + BATCH);
     TFB_CUDA_CHECK(cudaMemsetAsync(raised, 0, sizeof(*raised), st));
     fill_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dem, W, n, raised);
     TFB_CUDA_CHECK(cudaGetLastError());
@@ -288,8 +320,8 @@ extern "C" int tfb_area_range(const float *A, int64_t n, float *min_pos, float *
                               void *stream) {
     TFB_ARG_CHECK(A && n > 0 && min_pos && max_val);
     cudaStream_t st = (cudaStream_t)stream;
-    unsigned *d = nullptr;
-    TFB_CUDA_CHECK(cudaMalloc(&d, 2 * sizeof(unsigned)));
+    unsigned *d = (unsigned *)small_scratch();
+    TFB_ARG_CHECK(d != nullptr);
     const unsigned init[2] = {0x7f800000u, 0u};
     cudaError_t e = cudaMemcpyAsync(d, init, sizeof(init), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
@@ -299,7 +331,6 @@ extern "C" int tfb_area_range(const float *A, int64_t n, float *min_pos, float *
     unsigned h[2] = {0, 0};
     if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d);
     if (e != cudaSuccess) {
         set_error("tfb_area_range: %s", cudaGetErrorString(e));
         return TFB_ERR_CUDA;
