@@ -196,3 +196,35 @@ def test_emeli_resolves_to_the_gpu_component():
                 assert G._var_units_map[k] == R._var_units_map[k], k
     finally:
         emeli_dropin.uninstall()
+
+
+def _run_bench(args, env_extra=None):
+    import json
+    import subprocess
+    env = dict(os.environ)
+    env.update(env_extra or {})
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py')] + args, env=env, cwd=ROOT,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith('{')]
+    return [json.loads(l) for l in lines]
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver times beside the GPU arm):
+    one JSON line with the contract's keys; under torchrun only rank 0 works."""
+    out = _run_bench(['--impl', 'reference', '--steps', '2', '--warmup', '1',
+                      '--rows-per-gpu', '192', '--nx', '160'])
+    assert len(out) == 1
+    d = out[0]
+    assert d['impl'] == 'reference' and d['metric'] == 'routing Gcell-updates/sec'
+    assert d['unit'] == 'Gcell-updates/s' and d['higher_is_better'] is True
+    assert d['value'] > 0 and d['steps'] == 2 and d['n_gpus'] == 1
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['cpu_baseline']['value'] == d['value']
+    assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0,
+                        'd2h_bytes_per_step': 0}
+    assert 'workload' in d['config'] and d['vs_baseline'] is None
+    # a non-zero rank of a torchrun launch exits 0 without printing or working
+    assert _run_bench(['--impl', 'reference', '--gpus', '2', '--steps', '1', '--warmup', '0'],
+                      {'RANK': '1', 'LOCAL_RANK': '1', 'WORLD_SIZE': '2'}) == []

@@ -150,19 +150,23 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
 // register needs of the variant and is made per kernel instantiation (launch_main).
 constexpr int kSmemBudget = 196 * 1024;              // dynamic shared memory for the ring
 constexpr int kMaxWarps = 32;
-template <int ROWS, int CPL, int WIDTH = 64> struct TileCfg {
-    static constexpr int R = ROWS;
+template <int ROWS, int CPL, int WIDTH = 64, int RPW = 1> struct TileCfg {
+    static constexpr int R = ROWS * RPW;             // tile rows; a warp takes rows w, w + ROWS, ...
+    static constexpr int RP = ROWS;                  // rows per pass of the consumer warps
+    static constexpr int rpw = RPW;                  // passes: the per-tile bookkeeping (barrier
+                                                     // wait, tile index, slot arithmetic) is paid
+                                                     // once per RPW cells of a lane
     static constexpr int W = WIDTH;                  // tile columns
     static constexpr int QW = WIDTH + 4;             // halo box: cols c0-2 .. c0+W+1
     static constexpr int wpr = WIDTH / (32 * CPL);   // consumer warps per tile row
-    static constexpr int QR = ROWS + 2;              // halo box: rows r0-1 .. r0+R
+    static constexpr int QR = ROWS * RPW + 2;        // halo box: rows r0-1 .. r0+R
     static constexpr int cpl = CPL;
     static constexpr int warps = ROWS * wpr;         // consumer warps
     static constexpr int threads = (warps + 1) * 32; // + 1 producer warp
     static constexpr int szQ = ((QW * QR * 8 + 127) / 128) * 128;
-    static constexpr int szD = ((WIDTH * ROWS * 8 + 127) / 128) * 128;   // one fp64 tile
-    static constexpr int szF = ((WIDTH * ROWS * 4 + 127) / 128) * 128;   // one 32-bit tile
-    static constexpr int nD = WIDTH * ROWS * 8, nF = WIDTH * ROWS * 4, nQ = QW * QR * 8;  // TMA bytes
+    static constexpr int szD = ((WIDTH * R * 8 + 127) / 128) * 128;   // one fp64 tile
+    static constexpr int szF = ((WIDTH * R * 4 + 127) / 128) * 128;   // one 32-bit tile
+    static constexpr int nD = WIDTH * R * 8, nF = WIDTH * R * 4, nQ = QW * QR * 8;  // TMA bytes
 };
 
 // ring slot of the main kernel (kinematic step, or pass A of the diffusive step)
@@ -553,8 +557,10 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
             if (!mbar_wait(&full_bar[stage], phase)) { s_fail = 1; break; }
             int ty, txi;
             tile_of(k, t, ty, txi);
+#pragma unroll 1
+            for (int rr = 0; rr < TC::rpw; ++rr) {
             if constexpr (TC::cpl == 1) {
-            const int row = warp / TC::wpr, ct = ((warp % TC::wpr) << 5) + lane;  // wpr warps per tile row
+            const int row = warp / TC::wpr + rr * TC::RP, ct = ((warp % TC::wpr) << 5) + lane;  // wpr warps per tile row
             const int c0 = txi * kTW + ct, r = ty * kTR + row;
             const unsigned char *st = smem + (size_t)stage * SL::bytes;
             if (r < a.ny && c0 < a.nx) {
@@ -600,7 +606,7 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
                 }
             }
             } else {
-            const int row = warp / TC::wpr, ct = ((warp % TC::wpr) << 6) + lane * 2;
+            const int row = warp / TC::wpr + rr * TC::RP, ct = ((warp % TC::wpr) << 6) + lane * 2;
             const int c0 = txi * kTW + ct, r = ty * kTR + row;
             const unsigned char *st = smem + (size_t)stage * SL::bytes;
             if (r < a.ny && c0 < a.nx) {
@@ -678,6 +684,7 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
                         *reinterpret_cast<double2 *>(a.h_snow + i) =
                             make_double2(o0.h * k.ratio, o1.h * k.ratio);
                 }
+            }
             }
             }
             if ((peer.up_flag || peer.down_flag) && t < k.n_boundary) {
@@ -768,8 +775,10 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
             if (!mbar_wait(&full_bar[stage], phase)) { s_fail = 1; break; }
             int ty, txi;
             tile_of(k, t, ty, txi);
+#pragma unroll 1
+            for (int rr = 0; rr < TC::rpw; ++rr) {
             if constexpr (TC::cpl == 1) {
-            const int row = warp / TC::wpr, ct = ((warp % TC::wpr) << 5) + lane;
+            const int row = warp / TC::wpr + rr * TC::RP, ct = ((warp % TC::wpr) << 5) + lane;
             const int c0 = txi * kTW + ct, r = ty * kTR + row;
             const unsigned char *st = smem + (size_t)stage * SL::bytes;
             if (r < a.ny && c0 < a.nx) {
@@ -799,7 +808,7 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
                 a.Q_out[i] = Qn;
             }
             } else {
-            const int row = warp / TC::wpr, ct = ((warp % TC::wpr) << 6) + lane * 2;
+            const int row = warp / TC::wpr + rr * TC::RP, ct = ((warp % TC::wpr) << 6) + lane * 2;
             const int c0 = txi * kTW + ct, r = ty * kTR + row;
             const unsigned char *st = smem + (size_t)stage * SL::bytes;
             if (r < a.ny && c0 < a.nx) {
@@ -836,6 +845,7 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
                 }
                 *reinterpret_cast<double2 *>(a.u + i) = make_double2(uo[0], uo[1]);
                 *reinterpret_cast<double2 *>(a.Q_out + i) = make_double2(Qo[0], Qo[1]);
+            }
             }
             }
             __syncwarp();
@@ -1104,10 +1114,28 @@ int prepare(const tfb_channels_step_args *ap, const tfb_channels_packed *pp, boo
 #ifndef TFB_PK_NONE_W
 #define TFB_PK_NONE_W 64
 #endif
-typedef TileCfg<TFB_PK_NONE_ROWS, 1, TFB_PK_NONE_W> CfgNone;
-typedef TileCfg<TFB_PK_GA_ROWS, TFB_PK_GA_CPL, TFB_PK_GA_W> CfgGA;
-typedef TileCfg<15, 2> CfgFull;
-typedef TileCfg<15, 1> CfgDwB;
+#ifndef TFB_PK_NONE_RPW
+#define TFB_PK_NONE_RPW 2
+#endif
+#ifndef TFB_PK_GA_RPW
+#define TFB_PK_GA_RPW 1
+#endif
+#ifndef TFB_PK_FULL_RPW
+#define TFB_PK_FULL_RPW 1
+#endif
+#ifndef TFB_PK_DWB_RPW
+#define TFB_PK_DWB_RPW 2
+#endif
+typedef TileCfg<TFB_PK_NONE_ROWS, 1, TFB_PK_NONE_W, TFB_PK_NONE_RPW> CfgNone;
+typedef TileCfg<TFB_PK_GA_ROWS, TFB_PK_GA_CPL, TFB_PK_GA_W, TFB_PK_GA_RPW> CfgGA;
+#ifndef TFB_PK_FULL_ROWS
+#define TFB_PK_FULL_ROWS 15
+#endif
+#ifndef TFB_PK_FULL_CPL
+#define TFB_PK_FULL_CPL 2
+#endif
+typedef TileCfg<TFB_PK_FULL_ROWS, TFB_PK_FULL_CPL, 64, TFB_PK_FULL_RPW> CfgFull;
+typedef TileCfg<15, 1, 64, TFB_PK_DWB_RPW> CfgDwB;
 
 extern "C" int tfb_channels_step_packed(const tfb_channels_step_args *ap,
                                         const tfb_channels_packed *pp, void *stream) {
