@@ -340,9 +340,13 @@ __device__ __forceinline__ void pk_velocity(const tfb_channels_step_args &a, con
     u_out = u;
 }
 
-// Processing order: the tiles that hold the slab's first and last owned rows first (they
-// are the only ones that read the halo rows and that feed the neighbours), then the rest.
+// Processing order.  Row-major; with the peer-memory halo (PEER) the tiles that hold the
+// slab's first and last owned rows come first (they are the only ones that read the halo
+// rows and that feed the neighbours), then the rest.  The peer logic and this order cost
+// 2.4 % on one GPU (same-box A/B), hence a template parameter and not a run-time flag.
+template <bool PEER>
 __device__ __forceinline__ void tile_of(const PkConsts &k, int s, int &ty, int &tx) {
+    if constexpr (!PEER) { ty = s / k.tiles_x; tx = s - ty * k.tiles_x; return; }
     if (s < k.tiles_x) { ty = 0; tx = s; return; }
     if (s < k.n_boundary) { ty = k.tiles_y - 1; tx = s - k.tiles_x; return; }
     const int q = s - k.n_boundary;
@@ -469,7 +473,7 @@ __device__ __forceinline__ void pk_finish(const tfb_channels_step_args &a, Acc &
 // main kernel: the kinematic step (VAR = PK_KW) or pass A of the diffusive step
 // (VAR = PK_DWA: new volume, new depth and source state only)
 // ---------------------------------------------------------------------------
-template <int SRC, int VAR, class TC>
+template <int SRC, int VAR, class TC, bool PEER>
 __global__ void __launch_bounds__(TC::threads, 1)
 channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed p,
                        const PkConsts k, const __grid_constant__ PkMaps maps, const PkPeer peer) {
@@ -521,8 +525,8 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
             for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
                 if (!mbar_wait(&empty_bar[stage], phase ^ 1u)) { s_fail = 1; break; }
                 int ty, txi;
-                tile_of(k, t, ty, txi);
-                if (kKW && t < k.n_boundary) {
+                tile_of<PEER>(k, t, ty, txi);
+                if (PEER && kKW && t < k.n_boundary) {
                     // peer-memory halo: the first / last tile row reads a row a neighbour
                     // stored and overwrites (in its memory) a row it may still be reading
                     if (peer.from_up && ty == 0 && !up_ok) {
@@ -556,7 +560,7 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
         for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
             if (!mbar_wait(&full_bar[stage], phase)) { s_fail = 1; break; }
             int ty, txi;
-            tile_of(k, t, ty, txi);
+            tile_of<PEER>(k, t, ty, txi);
 #pragma unroll 1
             for (int rr = 0; rr < TC::rpw; ++rr) {
             if constexpr (TC::cpl == 1) {
@@ -593,8 +597,8 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
                                 x.qself, p.outlet_rough, r, c0, acc, rate_max, u, Qn);
                     a.u[i] = u;
                     a.Q_out[i] = Qn;
-                    if (r == 0 && peer.up_Q) peer.up_Q[c0] = Qn;              // NVLink peer store
-                    if (r == a.ny - 1 && peer.down_Q) peer.down_Q[c0] = Qn;
+                    if (PEER && r == 0 && peer.up_Q) peer.up_Q[c0] = Qn;      // NVLink peer store
+                    if (PEER && r == a.ny - 1 && peer.down_Q) peer.down_Q[c0] = Qn;
                 }
                 if (nf) { acc.s[S_VOL_EDGE] += o.v; o.v = 0.0; if (kKW) o.d = 0.0; }   // :2960-2966
                 a.vol_out[i] = o.v;
@@ -666,9 +670,9 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
                 if (kKW) {
                     *reinterpret_cast<double2 *>(a.u + i) = make_double2(u0, u1);
                     *reinterpret_cast<double2 *>(a.Q_out + i) = make_double2(Q0, Q1);
-                    if (r == 0 && peer.up_Q)                                  // NVLink peer stores
+                    if (PEER && r == 0 && peer.up_Q)                          // NVLink peer stores
                         *reinterpret_cast<double2 *>(peer.up_Q + c0) = make_double2(Q0, Q1);
-                    if (r == a.ny - 1 && peer.down_Q)
+                    if (PEER && r == a.ny - 1 && peer.down_Q)
                         *reinterpret_cast<double2 *>(peer.down_Q + c0) = make_double2(Q0, Q1);
                 }
                 // update_edge_values :2960-2966 (pass A keeps the PRE-zero depth for the
@@ -687,7 +691,7 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
             }
             }
             }
-            if ((peer.up_flag || peer.down_flag) && t < k.n_boundary) {
+            if (PEER && (peer.up_flag || peer.down_flag) && t < k.n_boundary) {
                 // this warp's share of a boundary tile is in the neighbours' halo rows; when
                 // the LAST boundary tile of the grid is complete the neighbours may start
                 // their next step (they no longer wait for the rest of this kernel)
@@ -756,7 +760,7 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
             for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
                 if (!mbar_wait(&empty_bar[stage], phase ^ 1u)) { s_fail = 1; break; }
                 int ty, txi;
-                tile_of(k, t, ty, txi);
+                tile_of<false>(k, t, ty, txi);
                 const int c0 = txi * kTW, r0 = ty * kTR;
                 unsigned char *st = smem + (size_t)stage * SL::bytes;
                 mbar_arrive_expect_tx(&full_bar[stage], (unsigned)SL::tx_bytes);
@@ -774,7 +778,7 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
         for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
             if (!mbar_wait(&full_bar[stage], phase)) { s_fail = 1; break; }
             int ty, txi;
-            tile_of(k, t, ty, txi);
+            tile_of<false>(k, t, ty, txi);
 #pragma unroll 1
             for (int rr = 0; rr < TC::rpw; ++rr) {
             if constexpr (TC::cpl == 1) {
@@ -942,9 +946,9 @@ int get_map(const void *ptr, int64_t rows, int64_t cols, CUtensorMapDataType dty
     return TFB_OK;
 }
 
-template <int SRC, int VAR, class TC>
-int launch_main(const tfb_channels_step_args &a, const tfb_channels_packed &p, PkConsts k,
-                cudaStream_t st, const PkPeer &peer = PkPeer{}) {
+template <int SRC, int VAR, class TC, bool PEER>
+int launch_main_(const tfb_channels_step_args &a, const tfb_channels_packed &p, PkConsts k,
+                 cudaStream_t st, const PkPeer &peer) {
     using SL = StageLayout<SRC, VAR, TC>;
     constexpr int kTR = TC::R, kQR = TC::QR, kTW = TC::W, kQW = TC::QW, kThreads = TC::threads;
     k.tiles_x = (a.nx + kTW - 1) / kTW;
@@ -975,15 +979,26 @@ int launch_main(const tfb_channels_step_args &a, const tfb_channels_packed &p, P
     int dev = 0;
     TFB_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev >= 64 || !attr_set[dev]) {
-        TFB_CUDA_CHECK(cudaFuncSetAttribute(channels_packed_kernel<SRC, VAR, TC>,
+        TFB_CUDA_CHECK(cudaFuncSetAttribute(channels_packed_kernel<SRC, VAR, TC, PEER>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         if (dev < 64) attr_set[dev] = true;
     }
     int64_t grid = sm_count();
     if (grid > k.n_tiles) grid = k.n_tiles;
-    channels_packed_kernel<SRC, VAR, TC><<<(int)grid, kThreads, smem, st>>>(a, p, k, m, peer);
+    channels_packed_kernel<SRC, VAR, TC, PEER><<<(int)grid, kThreads, smem, st>>>(a, p, k, m, peer);
     TFB_CUDA_CHECK(cudaGetLastError());
     return TFB_OK;
+}
+
+template <int SRC, int VAR, class TC>
+int launch_main(const tfb_channels_step_args &a, const tfb_channels_packed &p, const PkConsts &k,
+                cudaStream_t st) {
+    return launch_main_<SRC, VAR, TC, false>(a, p, k, st, PkPeer{});
+}
+template <int SRC, class TC>
+int launch_main_peer(const tfb_channels_step_args &a, const tfb_channels_packed &p, const PkConsts &k,
+                     cudaStream_t st, const PkPeer &peer) {
+    return launch_main_<SRC, PK_KW, TC, true>(a, p, k, st, peer);
 }
 
 template <class TC>
@@ -1244,9 +1259,9 @@ extern "C" int tfb_channels_step_packed_p2p(const tfb_channels_step_args *ap,
         if (ph->from_up && (rc = stream_wait_geq(st, ph->from_up, ph->step))) return rc;
         if (ph->from_down && (rc = stream_wait_geq(st, ph->from_down, ph->step))) return rc;
     }
-    if (mode == PK_SRC_NONE) return launch_main<PK_SRC_NONE, PK_KW, CfgNone>(*ap, *pp, k, st, peer);
-    if (mode == PK_SRC_GA) return launch_main<PK_SRC_GA, PK_KW, CfgGA>(*ap, *pp, k, st, peer);
-    return launch_main<PK_SRC_FULL, PK_KW, CfgFull>(*ap, *pp, k, st, peer);
+    if (mode == PK_SRC_NONE) return launch_main_peer<PK_SRC_NONE, CfgNone>(*ap, *pp, k, st, peer);
+    if (mode == PK_SRC_GA) return launch_main_peer<PK_SRC_GA, CfgGA>(*ap, *pp, k, st, peer);
+    return launch_main_peer<PK_SRC_FULL, CfgFull>(*ap, *pp, k, st, peer);
 }
 
 extern "C" int tfb_channels_step_packed_dw_a(const tfb_channels_step_args *ap,
