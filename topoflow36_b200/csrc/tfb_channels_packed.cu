@@ -149,7 +149,6 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
 // (2R + 1 warps: more latency hiding, 64 registers).  The best choice depends on the
 // register needs of the variant and is made per kernel instantiation (launch_main).
 constexpr int kSmemBudget = 196 * 1024;              // dynamic shared memory for the ring
-constexpr int kMaxWarps = 32;
 template <int ROWS, int CPL, int WIDTH = 64, int RPW = 1> struct TileCfg {
     static constexpr int R = ROWS * RPW;             // tile rows; a warp takes rows w, w + ROWS, ...
     static constexpr int RP = ROWS;                  // rows per pass of the consumer warps

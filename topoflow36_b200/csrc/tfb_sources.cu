@@ -12,9 +12,8 @@
 namespace tfb {
 
 constexpr int kThreads = 256;
-constexpr int kMaxSums = 4;
 
-// grid-stride element loop + deterministic reduction of up to kMaxSums sums
+// grid-stride element loop + deterministic reduction of up to 4 sums
 template <int NS, typename F>
 __device__ __forceinline__ void reduce_and_fold(double (&acc)[NS], double *partials,
                                                 unsigned *ticket, double *sums_out, F) {
