@@ -370,7 +370,9 @@ struct PkPeer {
 // Wait (bounded) until a neighbour has published step `need`: its halo row is in my memory
 // and it no longer reads the halo row of its own that my boundary tiles overwrite.
 __device__ __forceinline__ bool peer_flag_wait(const uint32_t *flag, uint32_t need) {
-    for (unsigned i = 0; i < (1u << 24); ++i) {
+    // ~1 us per poll while spinning: gives a neighbour held up on its host (output, GC) about
+    // a minute before the step is reported as failed instead of hanging the device
+    for (unsigned i = 0; i < (1u << 26); ++i) {
         uint32_t v;
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
         if (v >= need) {
@@ -378,7 +380,7 @@ __device__ __forceinline__ bool peer_flag_wait(const uint32_t *flag, uint32_t ne
             asm volatile("fence.proxy.async;" ::: "memory");
             return true;
         }
-        __nanosleep(64);
+        __nanosleep(i < 1024u ? 64 : 512);
     }
     return false;
 }
