@@ -232,7 +232,7 @@ def main():
                          'configs[3] (diffusive wave + met/snow/evap/infil fused); dw = diffusive only')
     ap.add_argument('--device-gen', action='store_true',
                     help='synthesise the case on the GPU (needed for 65536-wide slabs)')
-    ap.add_argument('--halo', default='p2p', choices=['p2p', 'nccl'],
+    ap.add_argument('--halo', default='p2p', choices=['p2p', 'nccl', 'p2p-dw'],
                     help='N > 1: boundary rows by NVLink peer stores fused into the kernel '
                          '(kinematic wave, default) or by NCCL send/recv after it')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -275,7 +275,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    use_p2p = (world > 1 and kin and args.halo == 'p2p')
+    # the diffusive passes also run with the peer halo (--halo p2p-dw), but measured slower than
+    # NCCL on 2 GPUs (0.367 vs 0.358 ms/step): NCCL stays their default
+    use_p2p = (world > 1 and (args.halo == 'p2p-dw' or (args.halo == 'p2p' and kin)))
     if args.device_gen:
         stepper = cases.build_engine_device(ny, NX, kinematic=kin, sources=sources, rank=rank,
                                             world=world, device=dev, p2p=use_p2p)
@@ -443,8 +445,8 @@ def main():
         'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'grid': [ny * world, NX], 'rows_per_gpu': ny,
                    'partition': ('row slabs, 1 halo row of Q per neighbour per step, %s'
-                                 % ('NVLink peer stores fused into the routing kernel + '
-                                    'cuStreamWaitValue32 flags (no NCCL call per step)' if use_p2p
+                                 % ('NVLink peer stores fused into the routing kernel(s), flag words '
+                                    'polled by the boundary tiles (no NCCL call per step)' if use_p2p
                                     else 'NCCL send/recv after the kernel'))
                    if world > 1 else 'single GPU',
                    'l2': 'working set %.2f GB per step per GPU >> 126 MB L2, no flush needed'

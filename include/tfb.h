@@ -367,8 +367,7 @@ int tfb_channels_step_packed_dw_c(const tfb_channels_step_args *a,
  * tile's TMA loads; in lock-step operation the flag has been set for almost a
  * whole step by then.  No NCCL call, no stream memory operation and no extra
  * kernel per step (TFB_P2P_STREAM_WAIT=1 in the environment selects
- * cuStreamWaitValue32 in front of the launch instead).  Kinematic wave only (the
- * diffusive wave keeps NCCL). */
+ * cuStreamWaitValue32 in front of the launch instead). */
 typedef struct {
     double *up_Q;             /* neighbour above: its LOWER halo row of the buffer this
                                  step writes (row ny_up of its owned rows), or NULL   */
@@ -389,6 +388,20 @@ int tfb_peer_free(void *ptr);
 int tfb_channels_step_packed_p2p(const tfb_channels_step_args *a,
                                  const tfb_channels_packed *p,
                                  const tfb_peer_halo *peer, void *stream);
+/* The two passes of the diffusive step with the same peer-memory halo.  `step` is a
+ * PHASE counter here: 2n for pass A of step n (waits for the neighbours' 2n =
+ * their pass B of step n-1 has read its depth halo and stored my discharge halo;
+ * publishes 2n+1), 2n+1 for pass B (waits for 2n+1 = the neighbours' pass A
+ * stored my depth halo; publishes 2n+2).  up_Q / down_Q address the neighbours'
+ * halo rows of the array the pass WRITES: the depth `d` (pre-zero values) for
+ * pass A, the discharge buffer for pass B.  d and both discharge buffers must
+ * therefore come from tfb_peer_alloc. */
+int tfb_channels_step_packed_dw_a_p2p(const tfb_channels_step_args *a,
+                                      const tfb_channels_packed *p,
+                                      const tfb_peer_halo *peer, void *stream);
+int tfb_channels_step_packed_dw_b_p2p(const tfb_channels_step_args *a,
+                                      const tfb_channels_packed *p,
+                                      const tfb_peer_halo *peer, void *stream);
 
 /* multi-GPU: fold globally reduced sums (DEVICE, TFB_NSUM doubles laid out as
  * tfb_channels_step leaves them in partials[]) into the scalar block */

@@ -81,10 +81,12 @@ def _worker(rank, world, port, kinematic, infil, q, devgen=False, p2p=False):
 
 @pytest.mark.parametrize('kinematic,infil,devgen,p2p', [
     (True, False, False, False), (True, True, False, False), (False, False, False, False),
-    (True, True, True, False), (True, False, False, True), (True, True, False, True)])
+    (True, True, True, False), (True, False, False, True), (True, True, False, True),
+    (False, False, False, True), (False, True, False, True)])
 def test_two_slabs_equal_one_grid(kinematic, infil, devgen, p2p):
     """p2p = True: the halo rows travel through NVLink peer stores inside the routing
-    kernel (tfb_channels_step_packed_p2p) instead of NCCL send/recv."""
+    kernel (tfb_channels_step_packed_p2p; diffusive wave: ..._dw_a_p2p stores the boundary
+    depths, ..._dw_b_p2p the boundary discharges) instead of NCCL send/recv."""
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:

@@ -171,15 +171,16 @@ def build_engine_device(ny, nx, kinematic=True, infil=False, dt=1.0, rank=0, wor
     width, nval = device_slab_params(ny, nx, lay.row0, halo, device, seed=seed)
     ang = float(np.float64(np.float32(45.0)) * (np.pi / np.float64(180)))
     peer = None
-    if p2p and world > 1 and kinematic:
+    if p2p and world > 1:
         from .slab import make_peer_halos
-        peer = make_peer_halos(lay, device, group)
+        peer = make_peer_halos(lay, device, group, with_depth=not kinematic)
     eng = ChannelsEngine(ny, nx, dt=dt, code=d8['code'], dx=d8['dx'], dy=d8['dy'], dd=d8['dd'],
                          S_bed=d8['S_bed'], width=width, angle=ang, tan_angle=float(np.tan(ang)),
                          cos_angle=float(np.cos(ang)), rough=nval, kinematic=kinematic,
                          outlet=(ny_global - 2, nx // 2), row0=lay.row0, ny_global=ny_global,
                          halo=halo, device=device, finalize=True, n_pixels_global=ny * nx,
-                         q_buffers=None if peer is None else peer.q_buffers)
+                         q_buffers=None if peer is None else peer.q_buffers,
+                         d_buffer=None if peer is None else peer.d_buffer)
     del width, nval, d8
     apply_sources(eng, sources or ('ga' if infil else 'none'), row0=lay.row0, halo=halo, seed=seed)
     if lean_memory and eng.packed is not None:
@@ -209,16 +210,17 @@ def build_engine(ny, nx, kinematic=True, infil=False, diag=False, dt=1.0, rank=0
     DEG = np.pi / np.float64(180)
     ang = np.float64(angle) * DEG
     peer = None
-    if p2p and world > 1 and kinematic:
+    if p2p and world > 1:
         from .slab import make_peer_halos
-        peer = make_peer_halos(lay, device, group)
+        peer = make_peer_halos(lay, device, group, with_depth=not kinematic)
     eng = ChannelsEngine(ny, nx, dt=dt, code=d8['code'], dx=d8['dx'], dy=d8['dy'], dd=d8['dd'],
                          S_bed=d8['S_bed'], width=np.float64(width), angle=ang,
                          rough=np.float64(nval), kinematic=kinematic, diag=diag,
                          outlet=(ny_global - 2, nx // 2), row0=lay.row0, ny_global=ny_global,
                          halo=halo, device=device, finalize=True,
                          n_pixels_global=ny * nx,
-                         q_buffers=None if peer is None else peer.q_buffers)
+                         q_buffers=None if peer is None else peer.q_buffers,
+                         d_buffer=None if peer is None else peer.d_buffer)
     apply_sources(eng, sources or ('ga' if infil else 'none'), row0=lay.row0, halo=halo, seed=seed)
     torch.cuda.current_stream().synchronize()
     stepper = SlabChannels(lay, eng, group, peer=peer) if world > 1 else eng

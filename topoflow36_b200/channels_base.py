@@ -445,10 +445,10 @@ class channels_component(BMI_base.BMI_component):
         self.S_bed = self.slope
         rough = self.nval if self.MANNING else self.z0val
         peer = None
-        if lay is not None and self.P2P_HALO and self.KINEMATIC_WAVE:
+        if lay is not None and self.P2P_HALO:
             from .slab import make_peer_halos
             peer = make_peer_halos(lay, self.device or torch.device('cuda', torch.cuda.current_device()),
-                                   self.group)
+                                   self.group, with_depth=not self.KINEMATIC_WAVE)
         self.engine = ChannelsEngine(
             ny_loc, self.nx, dt=float(self.dt), code=code, dx=dxh, dy=dyh,
             dd=ddh, S_bed=self.S_bed, width=self.width, angle=self.angle,
@@ -461,6 +461,7 @@ class channels_component(BMI_base.BMI_component):
             rho_H2O=float(self.rho_H2O), device=self.device, row0=row0, ny_global=self.ny,
             halo=halo, finalize=True, n_pixels_global=ny_loc * self.nx,
             q_buffers=None if peer is None else peer.q_buffers,
+            d_buffer=None if peer is None else peer.d_buffer,
             flood=self.FLOOD_OPTION, attenuate=self.ATTENUATE,
             n_days=float(getattr(self, 'n_days', 5.0)),
             d_bankfull=self.d_bankfull if np.ndim(self.d_bankfull) == 2 else float(self.d_bankfull))

@@ -527,7 +527,7 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
                 if (!mbar_wait(&empty_bar[stage], phase ^ 1u)) { s_fail = 1; break; }
                 int ty, txi;
                 tile_of<PEER>(k, t, ty, txi);
-                if (PEER && kKW && t < k.n_boundary) {
+                if (PEER && t < k.n_boundary) {
                     // peer-memory halo: the first / last tile row reads a row a neighbour
                     // stored and overwrites (in its memory) a row it may still be reading
                     if (peer.from_up && ty == 0 && !up_ok) {
@@ -600,6 +600,10 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
                     a.Q_out[i] = Qn;
                     if (PEER && r == 0 && peer.up_Q) peer.up_Q[c0] = Qn;      // NVLink peer store
                     if (PEER && r == a.ny - 1 && peer.down_Q) peer.down_Q[c0] = Qn;
+                }
+                if (PEER && !kKW) {          // pass A: the PRE-zero depth goes to the neighbours
+                    if (r == 0 && peer.up_Q) peer.up_Q[c0] = o.d;
+                    if (r == a.ny - 1 && peer.down_Q) peer.down_Q[c0] = o.d;
                 }
                 if (nf) { acc.s[S_VOL_EDGE] += o.v; o.v = 0.0; if (kKW) o.d = 0.0; }   // :2960-2966
                 a.vol_out[i] = o.v;
@@ -678,6 +682,12 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
                 }
                 // update_edge_values :2960-2966 (pass A keeps the PRE-zero depth for the
                 // free-surface slope of pass B, which then zeroes it)
+                if (PEER && !kKW) {          // pass A: the PRE-zero depth goes to the neighbours
+                    if (r == 0 && peer.up_Q)
+                        *reinterpret_cast<double2 *>(peer.up_Q + c0) = make_double2(o0.d, o1.d);
+                    if (r == a.ny - 1 && peer.down_Q)
+                        *reinterpret_cast<double2 *>(peer.down_Q + c0) = make_double2(o0.d, o1.d);
+                }
                 if (nf0) { acc.s[S_VOL_EDGE] += o0.v; o0.v = 0.0; if (kKW) o0.d = 0.0; }
                 if (nf1) { acc.s[S_VOL_EDGE] += o1.v; o1.v = 0.0; if (kKW) o1.d = 0.0; }
                 *reinterpret_cast<double2 *>(a.vol_out + i) = make_double2(o0.v, o1.v);
@@ -720,10 +730,10 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
 // pass B of the diffusive step: free-surface slope from the NEW depths of the
 // cell and its D8 parent (channels_base.py:2583-2618), velocity, next discharge
 // ---------------------------------------------------------------------------
-template <class TC>
+template <class TC, bool PEER>
 __global__ void __launch_bounds__(TC::threads, 1)
 channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_packed p,
-                           const PkConsts k, const __grid_constant__ PkMapsB maps) {
+                           const PkConsts k, const __grid_constant__ PkMapsB maps, const PkPeer peer) {
     using SL = StageLayoutB<TC>;
     constexpr int kTR = TC::R, kTW = TC::W, kQW = TC::QW, kConsumerWarps = TC::warps, kThreads = TC::threads;
     constexpr int NS = SL::stages;
@@ -734,11 +744,13 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
     __shared__ __align__(8) uint64_t full_bar[NS], empty_bar[NS];
     __shared__ bool is_last;
     __shared__ int s_fail;
+    __shared__ unsigned s_bcount[NS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < p.n_angles * 4; i += kThreads) lut[i] = __ldg(p.angle_lut + i);
     if (tid < kConsumerWarps * kPartialStride) (&sm[0][0])[tid] = 0.0;
     if (tid == 0) {
         s_fail = 0;
+        for (int q = 0; q < NS; ++q) s_bcount[q] = 0u;
         for (int s = 0; s < NS; ++s) {
             mbar_init(&full_bar[s], 1u);
             mbar_init(&empty_bar[s], (unsigned)kConsumerWarps);
@@ -758,10 +770,22 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
         if (lane == 0) {
             int stage = 0;
             unsigned phase = 0;
+            bool up_ok = false, down_ok = false;
             for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
                 if (!mbar_wait(&empty_bar[stage], phase ^ 1u)) { s_fail = 1; break; }
                 int ty, txi;
-                tile_of<false>(k, t, ty, txi);
+                tile_of<PEER>(k, t, ty, txi);
+                if (PEER && t < k.n_boundary) {
+                    // the depth halo rows were stored by the neighbours' pass A of this step
+                    if (peer.from_up && ty == 0 && !up_ok) {
+                        if (!peer_flag_wait(peer.from_up, peer.need)) { s_fail = 1; break; }
+                        up_ok = true;
+                    }
+                    if (peer.from_down && ty == k.tiles_y - 1 && !down_ok) {
+                        if (!peer_flag_wait(peer.from_down, peer.need)) { s_fail = 1; break; }
+                        down_ok = true;
+                    }
+                }
                 const int c0 = txi * kTW, r0 = ty * kTR;
                 unsigned char *st = smem + (size_t)stage * SL::bytes;
                 mbar_arrive_expect_tx(&full_bar[stage], (unsigned)SL::tx_bytes);
@@ -779,7 +803,7 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
         for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
             if (!mbar_wait(&full_bar[stage], phase)) { s_fail = 1; break; }
             int ty, txi;
-            tile_of<false>(k, t, ty, txi);
+            tile_of<PEER>(k, t, ty, txi);
 #pragma unroll 1
             for (int rr = 0; rr < TC::rpw; ++rr) {
             if constexpr (TC::cpl == 1) {
@@ -811,6 +835,8 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
                             acc, rate_max, u, Qn);
                 a.u[i] = u;
                 a.Q_out[i] = Qn;
+                if (PEER && r == 0 && peer.up_Q) peer.up_Q[c0] = Qn;      // NVLink peer store
+                if (PEER && r == a.ny - 1 && peer.down_Q) peer.down_Q[c0] = Qn;
             }
             } else {
             const int row = warp / TC::wpr + rr * TC::RP, ct = ((warp % TC::wpr) << 6) + lane * 2;
@@ -850,15 +876,32 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
                 }
                 *reinterpret_cast<double2 *>(a.u + i) = make_double2(uo[0], uo[1]);
                 *reinterpret_cast<double2 *>(a.Q_out + i) = make_double2(Qo[0], Qo[1]);
+                if (PEER && r == 0 && peer.up_Q)
+                    *reinterpret_cast<double2 *>(peer.up_Q + c0) = make_double2(Qo[0], Qo[1]);
+                if (PEER && r == a.ny - 1 && peer.down_Q)
+                    *reinterpret_cast<double2 *>(peer.down_Q + c0) = make_double2(Qo[0], Qo[1]);
             }
             }
+            }
+            if (PEER && (peer.up_flag || peer.down_flag) && t < k.n_boundary) {
+                // as in the main kernel: publish when the LAST boundary tile is complete
+                __threadfence_system();
+                __syncwarp();
+                if (lane == 0 && atomicAdd(&s_bcount[stage], 1u) == (unsigned)kConsumerWarps - 1u) {
+                    s_bcount[stage] = 0u;
+                    if (atomicAdd(a.ticket + 1, 1u) == (unsigned)k.n_boundary - 1u) {
+                        __threadfence_system();
+                        if (peer.up_flag) *reinterpret_cast<volatile uint32_t *>(peer.up_flag) = peer.value;
+                        if (peer.down_flag) *reinterpret_cast<volatile uint32_t *>(peer.down_flag) = peer.value;
+                    }
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[stage]);
             if (++stage == NS) { stage = 0; phase ^= 1u; }
         }
     }
-    pk_finish<kConsumerWarps>(a, acc, rate_max, warp < kConsumerWarps, s_fail, 2, PkPeer{}, sm, tot,
+    pk_finish<kConsumerWarps>(a, acc, rate_max, warp < kConsumerWarps, s_fail, 2, peer, sm, tot,
                               &is_last);
 }
 
@@ -996,15 +1039,15 @@ int launch_main(const tfb_channels_step_args &a, const tfb_channels_packed &p, c
                 cudaStream_t st) {
     return launch_main_<SRC, VAR, TC, false>(a, p, k, st, PkPeer{});
 }
-template <int SRC, class TC>
+template <int SRC, class TC, int VAR = PK_KW>
 int launch_main_peer(const tfb_channels_step_args &a, const tfb_channels_packed &p, const PkConsts &k,
                      cudaStream_t st, const PkPeer &peer) {
-    return launch_main_<SRC, PK_KW, TC, true>(a, p, k, st, peer);
+    return launch_main_<SRC, VAR, TC, true>(a, p, k, st, peer);
 }
 
-template <class TC>
+template <class TC, bool PEER>
 int launch_dwb(const tfb_channels_step_args &a, const tfb_channels_packed &p, PkConsts k,
-               cudaStream_t st) {
+               cudaStream_t st, const PkPeer &peer) {
     using SL = StageLayoutB<TC>;
     constexpr int kTR = TC::R, kQR = TC::QR, kTW = TC::W, kQW = TC::QW, kThreads = TC::threads;
     k.tiles_x = (a.nx + kTW - 1) / kTW;
@@ -1025,13 +1068,13 @@ int launch_dwb(const tfb_channels_step_args &a, const tfb_channels_packed &p, Pk
     int dev = 0;
     TFB_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev >= 64 || !attr_set[dev]) {
-        TFB_CUDA_CHECK(cudaFuncSetAttribute(channels_packed_dwb_kernel<TC>,
+        TFB_CUDA_CHECK(cudaFuncSetAttribute(channels_packed_dwb_kernel<TC, PEER>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         if (dev < 64) attr_set[dev] = true;
     }
     int64_t grid = sm_count();
     if (grid > k.n_tiles) grid = k.n_tiles;
-    channels_packed_dwb_kernel<TC><<<(int)grid, kThreads, smem, st>>>(a, p, k, m);
+    channels_packed_dwb_kernel<TC, PEER><<<(int)grid, kThreads, smem, st>>>(a, p, k, m, peer);
     TFB_CUDA_CHECK(cudaGetLastError());
     return TFB_OK;
 }
@@ -1234,6 +1277,29 @@ extern "C" int tfb_peer_free(void *ptr) {
     return TFB_OK;
 }
 
+namespace {
+// kernel-side view of a tfb_peer_halo: publish step + 1 when my boundary tiles are done,
+// wait (in the boundary tiles' producers, or on the stream) for the neighbours' `step`
+int make_peer(const tfb_peer_halo *ph, cudaStream_t st, PkPeer &peer) {
+    peer.up_Q = ph->up_Q; peer.down_Q = ph->down_Q;
+    peer.up_flag = ph->up_flag; peer.down_flag = ph->down_flag;
+    peer.value = ph->step + 1u;
+    if (!getenv("TFB_P2P_STREAM_WAIT")) {
+        // the producer warps of the boundary tiles poll the flags themselves: no stream
+        // memory operation (several microseconds each) between consecutive launches
+        peer.from_up = ph->from_up; peer.from_down = ph->from_down;
+        peer.need = ph->step;
+        return TFB_OK;
+    }
+    int rc;
+    peer.from_up = peer.from_down = nullptr;
+    peer.need = 0u;
+    if (ph->from_up && (rc = stream_wait_geq(st, ph->from_up, ph->step))) return rc;
+    if (ph->from_down && (rc = stream_wait_geq(st, ph->from_down, ph->step))) return rc;
+    return TFB_OK;
+}
+}  // namespace
+
 extern "C" int tfb_channels_step_packed_p2p(const tfb_channels_step_args *ap,
                                             const tfb_channels_packed *pp,
                                             const tfb_peer_halo *ph, void *stream) {
@@ -1246,23 +1312,26 @@ extern "C" int tfb_channels_step_packed_p2p(const tfb_channels_step_args *ap,
     // both neighbours must have finished the previous step: their halo rows are in
     // my memory, and they no longer read the halo rows this step overwrites
     PkPeer peer;
-    peer.up_Q = ph->up_Q; peer.down_Q = ph->down_Q;
-    peer.up_flag = ph->up_flag; peer.down_flag = ph->down_flag;
-    peer.value = ph->step + 1u;
-    if (!getenv("TFB_P2P_STREAM_WAIT")) {
-        // the producer warps of the boundary tiles poll the flags themselves: no stream
-        // memory operation (several microseconds each) between consecutive steps
-        peer.from_up = ph->from_up; peer.from_down = ph->from_down;
-        peer.need = ph->step;
-    } else {
-        peer.from_up = peer.from_down = nullptr;
-        peer.need = 0u;
-        if (ph->from_up && (rc = stream_wait_geq(st, ph->from_up, ph->step))) return rc;
-        if (ph->from_down && (rc = stream_wait_geq(st, ph->from_down, ph->step))) return rc;
-    }
+    if ((rc = make_peer(ph, st, peer))) return rc;
     if (mode == PK_SRC_NONE) return launch_main_peer<PK_SRC_NONE, CfgNone>(*ap, *pp, k, st, peer);
     if (mode == PK_SRC_GA) return launch_main_peer<PK_SRC_GA, CfgGA>(*ap, *pp, k, st, peer);
     return launch_main_peer<PK_SRC_FULL, CfgFull>(*ap, *pp, k, st, peer);
+}
+
+extern "C" int tfb_channels_step_packed_dw_a_p2p(const tfb_channels_step_args *ap,
+                                                 const tfb_channels_packed *pp,
+                                                 const tfb_peer_halo *ph, void *stream) {
+    TFB_ARG_CHECK(ph != nullptr);
+    PkConsts k;
+    int mode = 0;
+    int rc = prepare(ap, pp, true, k, mode);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    PkPeer peer;
+    if ((rc = make_peer(ph, st, peer))) return rc;
+    if (mode == PK_SRC_NONE) return launch_main_peer<PK_SRC_NONE, CfgNone, PK_DWA>(*ap, *pp, k, st, peer);
+    if (mode == PK_SRC_GA) return launch_main_peer<PK_SRC_GA, CfgGA, PK_DWA>(*ap, *pp, k, st, peer);
+    return launch_main_peer<PK_SRC_FULL, CfgFull, PK_DWA>(*ap, *pp, k, st, peer);
 }
 
 extern "C" int tfb_channels_step_packed_dw_a(const tfb_channels_step_args *ap,
@@ -1283,5 +1352,18 @@ extern "C" int tfb_channels_step_packed_dw_b(const tfb_channels_step_args *ap,
     int mode = 0;
     const int rc = prepare(ap, pp, true, k, mode);
     if (rc) return rc;
-    return launch_dwb<CfgDwB>(*ap, *pp, k, (cudaStream_t)stream);
+    return launch_dwb<CfgDwB, false>(*ap, *pp, k, (cudaStream_t)stream, PkPeer{});
+}
+
+extern "C" int tfb_channels_step_packed_dw_b_p2p(const tfb_channels_step_args *ap,
+                                                 const tfb_channels_packed *pp,
+                                                 const tfb_peer_halo *ph, void *stream) {
+    TFB_ARG_CHECK(ph != nullptr);
+    PkConsts k;
+    int mode = 0;
+    int rc = prepare(ap, pp, true, k, mode);
+    if (rc) return rc;
+    PkPeer peer;
+    if ((rc = make_peer(ph, (cudaStream_t)stream, peer))) return rc;
+    return launch_dwb<CfgDwB, true>(*ap, *pp, k, (cudaStream_t)stream, peer);
 }

@@ -165,6 +165,10 @@ SIGNATURES = {
     'tfb_peer_free': (C.c_int, [vp]),
     'tfb_channels_step_packed_p2p': (C.c_int, [C.POINTER(ChannelsStepArgs),
                                                C.POINTER(ChannelsPacked), C.POINTER(PeerHalo), vp]),
+    'tfb_channels_step_packed_dw_a_p2p': (C.c_int, [C.POINTER(ChannelsStepArgs),
+                                                    C.POINTER(ChannelsPacked), C.POINTER(PeerHalo), vp]),
+    'tfb_channels_step_packed_dw_b_p2p': (C.c_int, [C.POINTER(ChannelsStepArgs),
+                                                    C.POINTER(ChannelsPacked), C.POINTER(PeerHalo), vp]),
     'tfb_channels_step_packed_dw_c': (C.c_int, [C.POINTER(ChannelsStepArgs),
                                                 C.POINTER(ChannelsPacked), vp]),
     'tfb_channels_fold': (C.c_int, [C.POINTER(ChannelsStepArgs), vp, vp]),

@@ -36,7 +36,7 @@ class ChannelsEngine(object):
                  ny_global=None, halo=0, device=None, finalize=True,
                  n_pixels_global=None, packed=True, flood=False, d_bankfull=10.0,
                  flood_manning_n=0.10, width_ratio=5.0, attenuate=False, n_days=5.0,
-                 q_buffers=None):
+                 q_buffers=None, d_buffer=None):
         if not torch.cuda.is_available():
             raise L.TfbError('ChannelsEngine needs a CUDA device (no CPU path)')
         self.lib = L.load()
@@ -128,7 +128,9 @@ class ChannelsEngine(object):
                 raise L.TfbError('q_buffers must be (ny + 2*halo, nx) float64 CUDA tensors')
         self.qcur = 0             # Q buffer the NEXT step reads
         self.scur = 0             # state buffer (vol, I, h_swe) the next step reads
-        self.d, self.u = z(), z()
+        self.d, self.u = (d_buffer if d_buffer is not None else z()), z()
+        if tuple(self.d.shape) != (self.ny + 2 * self.halo, self.nx) or self.d.dtype != torch.float64:
+            raise L.TfbError('d_buffer must be a (ny + 2*halo, nx) float64 CUDA tensor')
         a.d, a.u = self._p(self.d), self._p(self.u)
         if diag:
             for n in _DIAG_NAMES:
@@ -520,8 +522,8 @@ class ChannelsEngine(object):
         return False
 
     def step(self, time_min=0.0, peer=None):
-        """Advance one time step.  `peer` (slab.PeerHalos) switches the kinematic packed
-        step to the fused peer-memory halo exchange."""
+        """Advance one time step.  `peer` (slab.PeerHalos) switches the packed step to the
+        fused peer-memory halo exchange (kinematic: one launch; diffusive: both passes)."""
         a = self.args
         a.flags = self.flags | (L.CH_ET_INPLACE if a.ET.ptr else 0)
         a.time_min = float(time_min)
@@ -544,6 +546,19 @@ class ChannelsEngine(object):
             elif self.kinematic:
                 L.check(self.lib.tfb_channels_step_packed(C.byref(a), C.byref(self.packed),
                                                           L.stream_ptr()), 'tfb_channels_step_packed')
+            elif peer is not None:
+                # diffusive wave, peer halo: pass A stores its boundary depths, pass B its
+                # boundary discharges into the neighbours' halo rows; phases 2n and 2n + 1
+                ph = peer.descriptor(0, 2 * self.n_steps, depth=True)
+                L.check(self.lib.tfb_channels_step_packed_dw_a_p2p(
+                    C.byref(a), C.byref(self.packed), C.byref(ph), L.stream_ptr()),
+                    'tfb_channels_step_packed_dw_a_p2p')
+                ph = peer.descriptor(self.qcur ^ 1, 2 * self.n_steps + 1)
+                L.check(self.lib.tfb_channels_step_packed_dw_b_p2p(
+                    C.byref(a), C.byref(self.packed), C.byref(ph), L.stream_ptr()),
+                    'tfb_channels_step_packed_dw_b_p2p')
+                L.check(self.lib.tfb_channels_step_packed_dw_c(
+                    C.byref(a), C.byref(self.packed), L.stream_ptr()), 'tfb_channels_step_packed_dw_c')
             else:
                 # diffusive wave: new depths first, (slab: exchange one row of d), then
                 # free-surface slope, velocity and discharge
@@ -558,7 +573,7 @@ class ChannelsEngine(object):
             self.last_path = 'packed'
         else:
             if peer is not None:
-                raise L.TfbError('the peer-memory halo needs the packed kinematic step')
+                raise L.TfbError('the peer-memory halo needs the packed step')
             if getattr(self, 'generic_released', False):
                 raise L.TfbError('this configuration needs the generic kernel, but its static '
                                  'inputs were released (release_generic_inputs)')

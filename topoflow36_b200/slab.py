@@ -116,8 +116,9 @@ class PeerHalos(object):
     the neighbours' halo rows over NVLink and the streams order themselves with
     cuStreamWaitValue32 on the flag words."""
 
-    def __init__(self, layout, device, group=None, _collective_guard=False):
+    def __init__(self, layout, device, group=None, _collective_guard=False, with_depth=False):
         self.layout, self.group = layout, group
+        self.with_depth = bool(with_depth)       # diffusive wave: the depth grid crosses too
         self.lib = L.load()
         self.ok = True
         lay = layout
@@ -125,15 +126,17 @@ class PeerHalos(object):
         nbytes = rows * lay.nx * 8
         self._mine, handles = [], []
         try:
-            for _ in range(3):                   # Q buffer 0, Q buffer 1, flags
+            sizes = [nbytes, nbytes, 256] + ([nbytes] if self.with_depth else [])
+            for nb in sizes:                     # Q buffer 0, Q buffer 1, flags, (depth)
                 p = C.c_void_p()
                 h = C.create_string_buffer(64)
-                L.check(self.lib.tfb_peer_alloc(nbytes if len(self._mine) < 2 else 256,
-                                                C.byref(p), h), 'tfb_peer_alloc')
+                L.check(self.lib.tfb_peer_alloc(nb, C.byref(p), h), 'tfb_peer_alloc')
                 self._mine.append(p.value)
                 handles.append(h.raw)
             self.q_buffers = [torch.as_tensor(_DevArray(self._mine[k], (rows, lay.nx), '<f8'),
                                               device=device) for k in range(2)]
+            self.d_buffer = (torch.as_tensor(_DevArray(self._mine[3], (rows, lay.nx), '<f8'),
+                                             device=device) if self.with_depth else None)
         except Exception:
             if not _collective_guard:
                 raise
@@ -154,25 +157,31 @@ class PeerHalos(object):
                     L.check(self.lib.tfb_peer_open(h, C.byref(p)), 'tfb_peer_open')
                     ptrs.append(p.value)
                 self._open[name] = ptrs
-                self.nbr[name] = dict(q=ptrs[:2], flags=ptrs[2], ny=info[r]['ny'])
+                self.nbr[name] = dict(q=ptrs[:2], flags=ptrs[2], ny=info[r]['ny'],
+                                      d=ptrs[3] if len(ptrs) > 3 else None)
         except L.TfbError:
             if not _collective_guard:
                 raise
             self.ok = False                       # make_peer_halos lets every rank fall back
         dist.barrier(group=group)
 
-    def descriptor(self, q_out, step):
+    def descriptor(self, q_out, step, depth=False):
+        """tfb_peer_halo for one launch: the neighbours' halo rows of the discharge buffer
+        `q_out` (or of the depth grid) and the flag words; `step` = step index for the
+        kinematic kernel, phase counter (2n, 2n+1) for the two diffusive passes."""
         lay = self.layout
         row = lay.nx * 8
         ph = L.PeerHalo()
         if 'up' in self.nbr:
             n = self.nbr['up']
-            ph.up_Q = n['q'][q_out] + (lay.halo + n['ny']) * row     # its first LOWER halo row
+            base = n['d'] if depth else n['q'][q_out]
+            ph.up_Q = base + (lay.halo + n['ny']) * row              # its first LOWER halo row
             ph.up_flag = n['flags'] + 4                              # its "from_down" word
             ph.from_up = self._mine[2]
         if 'down' in self.nbr:
             n = self.nbr['down']
-            ph.down_Q = n['q'][q_out] + (lay.halo - 1) * row         # its last UPPER halo row
+            base = n['d'] if depth else n['q'][q_out]
+            ph.down_Q = base + (lay.halo - 1) * row                  # its last UPPER halo row
             ph.down_flag = n['flags']                                # its "from_up" word
             ph.from_down = self._mine[2] + 4
         ph.step = int(step)
@@ -185,13 +194,13 @@ class PeerHalos(object):
         self._open = {}
 
 
-def make_peer_halos(layout, device, group=None):
+def make_peer_halos(layout, device, group=None, with_depth=False):
     """PeerHalos on every rank, or None on every rank: if CUDA IPC is not usable on any
     rank (containers without shared /dev/shm or IPC permission, no peer access) all
     ranks agree to fall back to the NCCL halo exchange."""
     ph, ok = None, 1.0
     try:
-        ph = PeerHalos(layout, device, group, _collective_guard=True)
+        ph = PeerHalos(layout, device, group, _collective_guard=True, with_depth=with_depth)
         ok = 1.0 if ph.ok else 0.0
     except Exception as exc:                      # pragma: no cover (depends on the host)
         import warnings
@@ -229,18 +238,24 @@ class SlabChannels(object):
             raise L.TfbError('SlabChannels needs an engine built with finalize=True')
         self.device = engine.device
         self.n_launches_per_step = 1
-        if layout.world_size > 1 and not engine.kinematic:
+        self._state_halos_stale = False
+        if layout.world_size > 1 and not engine.kinematic and self.peer is None:
             # packed diffusive step: the new depths of the boundary rows cross the link
             # between pass A and pass B
             engine.mid_step_hook = lambda: exchange_halos([engine.d], layout, [1], group)
+        if self.peer is not None and not engine.kinematic and not self.peer.with_depth:
+            raise L.TfbError('diffusive peer halos need PeerHalos(with_depth=True)')
 
     def __getattr__(self, name):           # state access falls through to the engine
         return getattr(self.__dict__['engine'], name)
 
-    def exchange_state(self):
+    def exchange_state(self, discharge_only=False):
+        """Halo rows after a step.  The packed kernels read neighbour rows of the discharge
+        only (and, between the diffusive passes, of the depth); the generic diffusive
+        kernel re-derives the parent's new depth and needs the state rows as well."""
         e, lay = self.engine, self.layout
         ts, rows = [e.Q_buf[e.qcur]], [lay.halo]
-        if not e.kinematic:
+        if not e.kinematic and not discharge_only:
             ts.append(e._sbuf(e.vol_buf)); rows.append(1)
             for buf in (e.I_buf, e.h_swe_buf, e.vol_stored_buf):
                 if buf is not None:
@@ -249,14 +264,22 @@ class SlabChannels(object):
 
     def step(self, time_min=0.0):
         e = self.engine
-        if self.peer is not None and e.kinematic and e._packed_ok():
-            e.step(time_min, peer=self.peer)      # halo rows travel inside the kernel
+        packed = e._packed_ok()
+        if self.peer is not None and packed:
+            e.step(time_min, peer=self.peer)      # halo rows travel inside the kernel(s)
+            self._state_halos_stale = not e.kinematic
             return
         if self.peer is not None:
             raise L.TfbError('peer-memory halos were set up but this step is not eligible '
-                             '(needs the packed kinematic path on every step)')
+                             '(needs the packed path on every step)')
+        if not packed and self._state_halos_stale:
+            # first generic step after packed ones: its state halo rows were not kept current
+            self.exchange_state()
+            self._state_halos_stale = False
         e.step(time_min)
-        self.exchange_state()
+        self.exchange_state(discharge_only=packed)
+        if packed and not e.kinematic:
+            self._state_halos_stale = True
 
     def read_scalars(self):
         """Global scalar block (collective: every rank must call it).  ONE all-gather
