@@ -138,6 +138,14 @@ class channels_component(BMI_base.BMI_component):
         self.P2P_HALO = False         # slab mode, kinematic, uniform forcing: halo rows by
                                       # NVLink peer stores inside the kernel instead of NCCL
 
+    @property
+    def input_device(self):
+        """torch.device on which set_value() takes CUDA tensors as they are (None before
+        initialize()); emeli_dropin.gpu_framework asks the time interpolator for tensors
+        on it."""
+        e = self.__dict__.get('engine')
+        return None if e is None else e.device
+
     # ---------------------------------------------------------------- attributes
     def __getattr__(self, name):
         # only reached when normal lookup fails: device-backed grids

@@ -11,8 +11,11 @@ in the reference tree is edited; ``uninstall()`` restores the originals.
 
 Needs the reference importable (``import topoflow``); it is only the coupler
 that comes from there -- the components run on the GPU through libtfb_b200.so.
-Run EMELI with ``time_interp_method='None'`` (emeli.py:893): the Linear
+Run EMELI with ``time_interp_method='None'`` (emeli.py:893): the reference's Linear
 interpolator copies every provided grid each step (time_interpolation.py:81-118).
+For Linear interpolation use ``gpu_framework()``: an ``emeli.framework`` subclass
+that builds the device-aware interpolator of ``topoflow36_b200.time_interpolation``
+and asks it for CUDA tensors when the user component takes them.
 """
 import importlib
 import sys
@@ -53,3 +56,42 @@ def uninstall():
         else:
             setattr(pkg, name, old_attr)
         del _saved[full]
+
+
+def gpu_framework():
+    """``emeli.framework`` subclass (option ii) for Linear time interpolation
+    with device users: identical coupling logic, but
+
+    * the ``time_interpolation`` module EMELI instantiates (emeli.py:1004) is the
+      device-aware one of this package, and
+    * ``get_required_vars`` (emeli.py:1500-1515) passes ``device=`` for users that
+      expose ``input_device`` (the GPU Channels component), so their grids arrive as
+      CUDA tensors computed on the device instead of fresh host arrays."""
+    from topoflow.framework import emeli
+    from . import time_interpolation as ti
+
+    class framework(emeli.framework):
+
+        def run_model(self, *args, **kwargs):
+            saved = emeli.time_interpolation
+            emeli.time_interpolation = ti            # the name emeli.py resolves at :1004
+            try:
+                return emeli.framework.run_model(self, *args, **kwargs)
+            finally:
+                emeli.time_interpolation = saved
+
+        def get_required_vars(self, user_name, bmi_time):
+            u_bmi = self.comp_set[user_name]
+            dev = getattr(u_bmi, 'input_device', None)
+            aware = getattr(self.time_interpolator, 'device_aware', False)
+            for long_var_name in u_bmi.get_input_var_names():
+                provider_name = self.var_providers[long_var_name][0]
+                if dev is not None and aware:
+                    values = self.time_interpolator.get_values(long_var_name, provider_name,
+                                                               bmi_time, device=dev)
+                else:
+                    values = self.time_interpolator.get_values(long_var_name, provider_name,
+                                                               bmi_time)
+                u_bmi.set_value(long_var_name, values)
+
+    return framework
