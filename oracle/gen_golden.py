@@ -21,7 +21,7 @@ sys.path.insert(0, ROOT)
 from oracle import ref_harness as rh          # noqa: E402
 from topoflow36_b200 import grid_io, synth    # noqa: E402
 
-GOLD = os.path.join(ROOT, 'tests', 'golden')
+GOLD = os.environ.get('TFB_GOLDEN_DIR') or os.path.join(ROOT, 'tests', 'golden')
 
 LONG = {'P_rain': 'atmosphere_water__rainfall_volume_flux',
         'MR': 'glacier_ice__melt_volume_flux',

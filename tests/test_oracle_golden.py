@@ -4,6 +4,7 @@ These are the checks that PIN the oracle: every fixture under tests/golden was
 produced by the unmodified reference (oracle/gen_golden.py) or ships with it
 (Treynor_flow.rtg / Treynor_area.rtg, RiverTools output)."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -296,3 +297,28 @@ def test_albedo_oracle_vs_reference_fixture():
             if method == 'aging':
                 assert np.array_equal(np.zeros((9, 13)) + st['n'], d['aging_n'][k])
     assert d['aging_n'].max() > 3.0
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not os.path.isdir('/root/reference'), reason='reference tree not present')
+def test_committed_fixtures_are_what_the_reference_produces(tmp_path):
+    """Re-run oracle/gen_golden.py (the UNMODIFIED reference, a few seconds) into a scratch
+    directory: every array of every committed fixture must come out identical."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, TFB_GOLDEN_DIR=str(tmp_path))
+    r = subprocess.run([sys.executable, os.path.join(root, 'oracle', 'gen_golden.py')], env=env,
+                       cwd=root, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stderr[-2000:]
+    gold = os.path.join(root, 'tests', 'golden')
+    names = sorted(f for f in os.listdir(gold) if f.endswith('.npz'))
+    assert len(names) == 12 and names == sorted(f for f in os.listdir(str(tmp_path)) if f.endswith('.npz'))
+    for f in names:
+        a, b = np.load(os.path.join(gold, f)), np.load(os.path.join(str(tmp_path), f))
+        assert sorted(a.files) == sorted(b.files), f
+        for k in a.files:
+            assert np.array_equal(a[k], b[k], equal_nan=True), (f, k)
+    assert json.load(open(os.path.join(gold, 'meta.json'))) == \
+        json.load(open(os.path.join(str(tmp_path), 'meta.json')))
