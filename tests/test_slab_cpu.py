@@ -87,3 +87,30 @@ def test_halo_exchange_gloo(world, halo):
         p.join(timeout=60)
     assert sorted(r for r, _ in res) == list(range(world))
     assert all(ok for _, ok in res), res
+
+
+def test_peer_halo_descriptor_addresses():
+    """PeerHalos.descriptor() is pure address arithmetic: the neighbours' halo rows of the
+    discharge buffer a launch writes (or of the depth grid) and the flag words.  Checked
+    here without a device for halo widths 1 (kinematic) and 2 (diffusive)."""
+    from topoflow36_b200 import slab as S
+    for halo in (1, 2):
+        lay = S.SlabLayout(3 * 10, 16, 1, 3, halo)              # the middle rank of three
+        ph = object.__new__(S.PeerHalos)
+        ph.layout = lay
+        ph._mine = [0x1000, 0x2000, 0x3000, 0x4000]             # Q0, Q1, flags, d
+        ph.nbr = {'up': dict(q=[0x10000, 0x20000], flags=0x30000, ny=10, d=0x40000),
+                  'down': dict(q=[0x50000, 0x60000], flags=0x70000, ny=10, d=0x80000)}
+        row = lay.nx * 8
+        d = ph.descriptor(1, 7)
+        assert d.up_Q == 0x20000 + (halo + 10) * row            # its first lower halo row
+        assert d.down_Q == 0x60000 + (halo - 1) * row           # its last upper halo row
+        assert d.up_flag == 0x30000 + 4 and d.down_flag == 0x70000
+        assert d.from_up == 0x3000 and d.from_down == 0x3000 + 4 and d.step == 7
+        d = ph.descriptor(0, 14, depth=True)                    # pass A of the diffusive step
+        assert d.up_Q == 0x40000 + (halo + 10) * row and d.down_Q == 0x80000 + (halo - 1) * row
+        assert d.step == 14
+        # the first rank has no neighbour above
+        ph.nbr.pop('up')
+        d = ph.descriptor(0, 0)
+        assert not d.up_Q and not d.up_flag and not d.from_up and d.down_Q
