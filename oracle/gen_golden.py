@@ -164,6 +164,48 @@ def gen_synth_channels(work):
     np.savez_compressed(os.path.join(GOLD, 'synth_channels.npz'), **out)
 
 
+def gen_sinu_d0(work):
+    """Sinuosity 1.3 (flow lengths * sinu, slope / sinu: channels_base.py:1242-1247) and an
+    initial depth of 5 cm (:1331-1336) on the 61 x 83 synthetic case, KW and DW, scalar
+    forcing, 120 steps with rain for the first 80."""
+    import topoflow.components.d8_global as d8g
+    ny, nx = 61, 83
+    DEM = synth.fractal_dem(ny, nx, seed=7, sigma=1.0)
+    width, angle, nval = synth.channel_params(ny, nx, seed=7)
+    out = dict(DEM=DEM, width=width, angle=angle, nval=nval, sinu=np.float64(1.3),
+               d0=np.float64(0.05))
+    for kin in (True, False):
+        tag = 'kw' if kin else 'dw'
+        cdir = os.path.join(work, 'sinu_' + tag)
+        cfg = synth.write_case(cdir, DEM, np.zeros_like(DEM), width, angle, nval=nval, dt=2.0,
+                               kinematic=kin, outlet=(ny - 2, nx // 2), sinu=1.3, d0=0.05)
+        d8 = d8g.d8_component()
+        rh.quiet_call(d8.initialize, cfg_file=os.path.join(cdir, 'Case1_d8_global.cfg'),
+                      SILENT=True, REPORT=False)
+        rh.quiet_call(d8.update, 0)
+        d8.update_noflow_IDs()
+        d8.update_slope_grid()
+        info = grid_io.read_rti(os.path.join(cdir, 'Synth.rti'))
+        grid_io.write_rtg(os.path.join(cdir, 'Synth_slope.rtg'), d8.S, info)
+        if kin:
+            out['code'] = np.array(d8.d8_grid)
+            out['slope'] = np.float32(d8.S)
+            out['ds32'] = np.float32(d8.ds)
+            out['dw32'] = np.float32(d8.dw)
+        c = standalone_channels(cfg, kin, dict(
+            P_rain=z(60 / 3.6e6), MR=z(0), GW=z(0), SM=z(0), rho_H2O=z(1000.0), ET=z(0), IN=z(0)))
+        for k, v in snapshot(c).items():
+            out[tag + '_init_' + k] = v
+        for i in range(120):
+            if i == 80:
+                c.set_value(LONG['P_rain'], z(0))
+            rh.quiet_call(c.update)
+        for k, v in snapshot(c).items():
+            out[tag + '_' + k] = v
+        out[tag + '_S_bed'] = np.array(c.S_bed)
+    np.savez_compressed(os.path.join(GOLD, 'sinu_d0_channels.npz'), **out)
+
+
 def gen_flood(work):
     """FLOOD_OPTION (rectangle-over-trapezoid overbank flow) on the 61 x 83 synthetic
     case with shallow banks, KW and DW, 150 steps of heavy rain then recession."""
@@ -588,6 +630,7 @@ def main():
         meta = {'numpy': np.__version__, 'reference': 'peckhams/topoflow36 @ /root/reference'}
         meta['treynor_emeli'] = gen_treynor(work)
         gen_synth_channels(work)
+        gen_sinu_d0(work)
         gen_flood(work)
         gen_attenuate(work)
         gen_geographic(work)

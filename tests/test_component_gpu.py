@@ -154,3 +154,36 @@ def test_diffusive_component_vs_engine(tmp_path, synth_channels):
     for s in ('vol_R', 'vol_Q', 'vol_edge', 'Q_peak'):
         want = float(g['dw_man_' + s])
         assert abs(float(getattr(c, s)) - want) <= RTOL * abs(want), s
+
+
+@pytest.mark.parametrize('kin', [True, False])
+def test_sinuosity_and_initial_depth_from_cfg(tmp_path, kin):
+    """sinu = 1.3 and d0 = 0.05 m read from the CFG: flow lengths * sinu, slope / sinu
+    (channels_base.py:1242-1247) and the initial A_wet / P_wet / vol (:1331-1336), then
+    120 steps, against the reference fixture (tests/golden/sinu_d0_channels.npz)."""
+    from conftest import load_golden
+    from topoflow36_b200 import channels_kinematic_wave as ckw, channels_diffusive_wave as cdw, synth
+    g = load_golden('sinu_d0_channels.npz')
+    tag = 'kw' if kin else 'dw'
+    ny, nx = g['code'].shape
+    cfg = synth.write_case(str(tmp_path), g['DEM'], g['slope'], g['width'], g['angle'],
+                           nval=g['nval'], dt=2.0, kinematic=kin, outlet=(ny - 2, nx // 2),
+                           sinu=float(g['sinu']), d0=float(g['d0']))
+    c = (ckw if kin else cdw).channels_component()
+    c.DIAGNOSTICS = True
+    c.initialize(cfg_file=cfg, mode='nondriver', SILENT=True)
+    assert np.array_equal(c.d8.d8_grid, g['code'])
+    for n in ('vol', 'd', 'A_wet', 'P_wet'):                 # state right after initialize()
+        assert rel_err(getattr(c, n), g[tag + '_init_' + n]) <= RTOL, n
+    for k, v in dict(P_rain=z(60 / 3.6e6), MR=z(0), GW=z(0), SM=z(0), rho_H2O=z(1000.0),
+                     ET=z(0), IN=z(0)).items():
+        c.set_value(LONG[k], v)
+    for i in range(120):
+        if i == 80:
+            c.set_value(LONG['P_rain'], z(0))
+        c.update()
+    for n in ('vol', 'd', 'u', 'Q', 'Rh', 'f', 'froude') + (() if kin else ('S_free',)):
+        assert rel_err(getattr(c, n), g[tag + '_' + n]) <= RTOL, n
+    for s in ('vol_R', 'vol_Q', 'vol_edge', 'Q_outlet', 'Q_peak'):
+        want = float(g[tag + '_' + s])
+        assert abs(float(getattr(c, s)) - want) <= RTOL * abs(want), s

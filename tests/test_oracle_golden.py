@@ -314,7 +314,7 @@ def test_committed_fixtures_are_what_the_reference_produces(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     gold = os.path.join(root, 'tests', 'golden')
     names = sorted(f for f in os.listdir(gold) if f.endswith('.npz'))
-    assert len(names) == 12 and names == sorted(f for f in os.listdir(str(tmp_path)) if f.endswith('.npz'))
+    assert len(names) == 13 and names == sorted(f for f in os.listdir(str(tmp_path)) if f.endswith('.npz'))
     for f in names:
         a, b = np.load(os.path.join(gold, f)), np.load(os.path.join(str(tmp_path), f))
         assert sorted(a.files) == sorted(b.files), f
@@ -322,3 +322,30 @@ def test_committed_fixtures_are_what_the_reference_produces(tmp_path):
             assert np.array_equal(a[k], b[k], equal_nan=True), (f, k)
     assert json.load(open(os.path.join(gold, 'meta.json'))) == \
         json.load(open(os.path.join(str(tmp_path), 'meta.json')))
+
+
+@pytest.mark.parametrize('kin', [True, False])
+def test_sinuosity_and_initial_depth_bit_exact(kin):
+    """sinu = 1.3 (flow lengths * sinu, slope / sinu) and d0 = 0.05 m (initial A_wet,
+    P_wet, vol): initialize_computed_vars :1137-1405 and 120 steps, KW and DW."""
+    from conftest import load_golden
+    g = load_golden('sinu_d0_channels.npz')
+    tag = 'kw' if kin else 'dw'
+    code = g['code']
+    ch = o.Channels(code, g['ds32'], g['dw32'], g['slope'], g['width'], g['angle'], nval=g['nval'],
+                    da=900.0, dt=2.0, kinematic=kin, outlet=(code.shape[0] - 2, code.shape[1] // 2),
+                    sinu=float(g['sinu']), d0=float(g['d0']))
+    assert np.array_equal(ch.S_bed, g[tag + '_S_bed'])
+    for n in GRIDS:
+        assert np.array_equal(getattr(ch, n), g[tag + '_init_' + n], equal_nan=True), n
+    z = lambda v: np.array(v, dtype='float64')
+    ch.P_rain = z(60 / 3.6e6)
+    for i in range(120):
+        if i == 80:
+            ch.P_rain = z(0)
+        ch.step()
+    for n in GRIDS + (() if kin else ('S_free',)):
+        assert np.array_equal(getattr(ch, n), g[tag + '_' + n], equal_nan=True), n
+    for n in SCALARS:
+        assert float(getattr(ch, n)) == float(g[tag + '_' + n]), n
+    assert float(g[tag + '_Q_outlet']) > 0.1

@@ -455,12 +455,19 @@ class ChannelsEngine(object):
         else:
             d.fill_(float(d0))
         vol = self.own(self._sbuf(self.vol_buf))
-        if float(d.abs().max()) == 0.0:
-            vol.zero_()
-            return
         def g(name):
             t = getattr(self, name + '_grid')
             return self.own(t) if t is not None else getattr(a, name).val
+        def as_divisor(v):       # a python-scalar divisor would let torch multiply by 1/v
+            return v if isinstance(v, torch.Tensor) else torch.full(
+                (1, 1), float(v), dtype=torch.float64, device=self.device)
+        if getattr(self, 'P_wet', None) is not None:
+            # the diagnostics exist from initialize() on (channels_base.py:1331-1333)
+            self.own(self.P_wet).copy_(g('width') + ((2.0 * d) / as_divisor(g('cos_angle'))))
+            self.own(self.A_wet).zero_()
+        if float(d.abs().max()) == 0.0:
+            vol.zero_()
+            return
         ds32 = torch.empty((self.ny + 2 * self.halo, self.nx), dtype=torch.float32,
                            device=self.device)
         L.check(self.lib.tfb_d8_ds_dw(self.code.data_ptr(), self.dx.data_ptr(),
@@ -471,6 +478,8 @@ class ChannelsEngine(object):
         L2 = d * g('tan_angle')
         A_wet = d * (g('width') + L2)
         vol.copy_(A_wet * ds)
+        if getattr(self, 'A_wet', None) is not None:
+            self.own(self.A_wet).copy_(A_wet)
 
     # ------------------------------------------------------------------ step
     # Q is always double-buffered (neighbours read the old Q while the new one
