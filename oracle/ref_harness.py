@@ -1,7 +1,7 @@
 """Harness that imports and drives the UNMODIFIED reference (peckhams/topoflow36)
 in this container.  TEST INFRASTRUCTURE ONLY -- nothing in the product package
-imports this module, and nothing here runs on the GPU box (the reference tree
-does not exist there).
+imports this module, and on the GPU box it only ever reads the staged copy
+under oracle/_ref/ (``make -C oracle _ref``; /root/reference does not exist there).
 
 It is used (a) by ``oracle/gen_golden.py`` to produce the committed fixtures
 under ``tests/golden/`` and (b) by the ``-m "not gpu"`` tests, when
@@ -21,7 +21,32 @@ import shutil
 import sys
 import types
 
-REF_ROOT = os.environ.get("TF_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    """The live read-only tree in the build container; on the GPU box (where it does
+    not exist) the archive that ``make -C oracle _ref`` staged as oracle/_ref/topoflow_ref.tar.gz,
+    unpacked into a scratch directory for the life of the process."""
+    env = os.environ.get("TF_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/topoflow/components"):
+        return "/root/reference"
+    tar = os.path.join(_HERE, "_ref", "topoflow_ref.tar.gz")
+    if os.path.isfile(tar):
+        import atexit
+        import tarfile
+        import tempfile
+        tmp = tempfile.mkdtemp(prefix="tf_ref_")
+        atexit.register(shutil.rmtree, tmp, ignore_errors=True)
+        with tarfile.open(tar) as t:
+            t.extractall(tmp)
+        return tmp
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 
 def reference_available():

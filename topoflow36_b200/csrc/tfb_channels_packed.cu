@@ -1096,7 +1096,7 @@ int prepare(const tfb_channels_step_args *ap, const tfb_channels_packed *pp, boo
     TFB_ARG_CHECK(!(a.flags & (TFB_CH_LAW_OF_WALL | TFB_CH_DIAG | TFB_CH_WRITE_R | TFB_CH_FLOOD |
                                TFB_CH_ATTENUATE)));
     TFB_ARG_CHECK(((a.flags & TFB_CH_DIFFUSIVE) != 0) == diffusive);
-    if (diffusive) TFB_ARG_CHECK(p.inv_rough && p.S32 && a.halo != 0 ? a.halo >= 1 : true);
+    if (diffusive) TFB_ARG_CHECK(p.inv_rough != nullptr && p.S32 != nullptr);
     else TFB_ARG_CHECK(p.coef != nullptr);
     TFB_ARG_CHECK(!a.sinu.ptr);      // the pixel area comes from row_geom (scalar or per row)
     TFB_ARG_CHECK(!a.P_rain.ptr && !a.SM.ptr && !a.GW.ptr && !a.MR.ptr && !a.ET.ptr && !a.IN.ptr);
