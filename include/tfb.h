@@ -182,6 +182,15 @@ typedef struct {
                                  EVERY grid pointer (0, or >=1 KW / >=2 DW for a
                                  slab with neighbours); rows beyond that read as
                                  code 0 / Q 0                                   */
+    int32_t pitch;            /* elements between the starts of consecutive rows of
+                                 EVERY per-cell (ny, nx) grid pointer of this struct
+                                 and of tfb_channels_packed (0 = nx: dense rows).
+                                 The TMA path needs 16-byte row strides, so a caller
+                                 with nx % 4 != 0 (Treynor: nx = 29) allocates rows
+                                 of pitch = nx rounded up to 4 elements; columns
+                                 [nx, pitch) are never read as cells nor written.
+                                 Per-ROW arrays (dx, dy, dd, da.ptr, row_geom) are
+                                 not affected                                      */
     const uint16_t *geo;      /* packed per-cell word from tfb_channels_pack_geo:
                                  low byte D8 code, high byte child mask          */
     const float *dx, *dy, *dd;        /* per-row pixel sizes (ny), float32       */

@@ -63,7 +63,7 @@ def snapshot(c, diag=True):
 
 
 def gen_treynor(work):
-    cfg_dir, _ = rh.stage_treynor(work)
+    cfg_dir, out_dir = rh.stage_treynor(work)
     topo = os.path.join(os.path.dirname(cfg_dir.rstrip(os.sep)), '__topo')
     info = grid_io.read_rti(os.path.join(topo, 'Treynor.rti'))
     rd = lambda n, t=None: grid_io.read_rtg(os.path.join(topo, 'Treynor_' + n + '.rtg'), info, t)
@@ -84,8 +84,27 @@ def gen_treynor(work):
     emeli_out = {n: float(getattr(ch, n)) for n in SCALARS}
     emeli_out['n_steps'] = int(ch.time_index)
     emeli_out['vol_chan_sum'] = float(ch.vol_chan_sum)
-    np.savez_compressed(os.path.join(GOLD, 'treynor_emeli_final.npz'),
-                        **{n: np.array(getattr(ch, n)) for n in ('vol', 'd', 'u', 'Q')})
+    final = {n: np.array(getattr(ch, n)) for n in ('vol', 'd', 'u', 'Q')}
+    # the files that run wrote (utils/rts_files.py, text_ts_files.py, rti_files.py): RTS
+    # stacks in the data set's byte order (Treynor: MSB), outlet series, RTI side-car
+    raw = lambda fn: np.frombuffer(open(os.path.join(out_dir, fn), 'rb').read(), dtype=np.uint8)
+    final['file_2D_Q_rts'] = raw('June_20_67_2D-Q.rts')
+    final['file_2D_d_rts'] = raw('June_20_67_2D-d.rts')
+    final['file_0D_Q_txt'] = raw('June_20_67_0D-Q.txt')
+    rti = open(os.path.join(out_dir, 'June_20_67_2D-Q.rti')).read().replace(out_dir, '<out_directory>/')
+    final['file_2D_Q_rti'] = np.frombuffer(rti.encode(), dtype=np.uint8)
+    # ---- (1b) the same run without time interpolation (emeli.py:893): the coupling the
+    # GPU drop-in recommends
+    f = emeli.framework()
+    rh.quiet_call(f.run_model, driver_comp_name='topoflow_driver', cfg_prefix='June_20_67',
+                  cfg_directory=cfg_dir, SILENT=True, time_interp_method='None')
+    ch = f.comp_set['tf_channels_kin_wave']
+    for n in ('vol', 'd', 'u', 'Q'):
+        final['none_' + n] = np.array(getattr(ch, n))
+    for n in SCALARS + ('vol_chan_sum',):
+        final['none_' + n] = np.float64(getattr(ch, n))
+    final['none_n_steps'] = np.int64(ch.time_index)
+    np.savez_compressed(os.path.join(GOLD, 'treynor_emeli_final.npz'), **final)
 
     # ---- (2) stand-alone KW run forced by the 1-minute rain series -----------
     # P is held for 10 channel steps (60 s / 6 s) like the met component does

@@ -41,7 +41,7 @@ def _find_root():
         tmp = tempfile.mkdtemp(prefix="tf_ref_")
         atexit.register(shutil.rmtree, tmp, ignore_errors=True)
         with tarfile.open(tar) as t:
-            t.extractall(tmp)
+            t.extractall(tmp, filter='data')
         return tmp
     return "/root/reference"
 
@@ -105,6 +105,13 @@ def _inert_module(name):
 
 def install_import_shims():
     """Register inert stand-ins for the optional, off-hot-path dependencies."""
+    try:
+        # torch must finish its own first import BEFORE the stand-ins exist: its lazy
+        # sub-imports probe optional packages (matplotlib among them) and choke on an
+        # inert module
+        import torch  # noqa: F401
+    except ImportError:
+        pass
     if "netCDF4" not in sys.modules:
         try:
             import netCDF4  # noqa: F401

@@ -54,6 +54,22 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / scale)
 
 
+def cell_rel_err(a, b, floor_frac=1e-12):
+    """Per-cell relative error  max_i |a_i - b_i| / max(|b_i|, floor)  with the absolute
+    floor = floor_frac * max|b|.  rel_err() above normalises by the grid maximum and is
+    blind to large relative errors in small-valued cells (most of a grid early in a
+    storm); this one is not.  The floor is needed because cells whose volume the
+    reference clamps to exactly 0 (np.maximum(vol, 0), channels_base.py:2145) may hold
+    a last-bit residue here: below 1e-12 of the grid maximum a difference counts as
+    absolute."""
+    a = np.asarray(a, dtype='float64')
+    b = np.asarray(b, dtype='float64')
+    scale = np.abs(b).max()
+    if scale == 0:
+        return float(np.abs(a).max())
+    return float((np.abs(a - b) / np.maximum(np.abs(b), floor_frac * scale)).max())
+
+
 @pytest.fixture(scope='session')
 def flood_gold():
     return load_golden('flood_channels.npz')

@@ -9,7 +9,7 @@ equality where no libm call is on the data path."""
 import numpy as np
 import pytest
 
-from conftest import rel_err
+from conftest import cell_rel_err, rel_err
 from oracle import np_oracle as o
 
 pytestmark = pytest.mark.gpu
@@ -84,6 +84,138 @@ def test_treynor_storm_vs_reference_fixture(treynor, treynor_kw):
     assert worst <= RTOL, worst
     s = eng.read_scalars()
     assert s.n_neg_d == 0 and s.n_inf_d == 0 and s.n_neg_u == 0 and s.n_nan_u == 0
+
+
+def test_treynor_storm_on_the_packed_kernel(treynor, treynor_kw):
+    """The same 1200-step storm on the BENCHMARKED kernel (channels_packed_kernel, TMA
+    ring): nx = 29 rides on pitched rows (include/tfb.h `pitch`), forcing is scalar as
+    in the EMELI run.  Hydrograph every step, state grids at three checkpoints --
+    also per cell (cell_rel_err <= 1e-9, the north-star tolerance)."""
+    DEM = treynor['DEM']
+    dx, dy, dd = o.pixel_dims(DEM.shape[0], treynor['xres'], treynor['yres'])
+    eng = _engine(treynor['flow'], dx, dy, dd, treynor['slope'], treynor['width'],
+                  treynor['angle'], treynor['nval'], dt=6.0, da=900.0, outlet=(34, 16))
+    rain = treynor['rain_mmph']
+    series = treynor_kw['outlet_series']
+    worst = worst_cell = 0.0
+    for i in range(1200):
+        m = i // 10
+        P = np.float64(rain[m]) / (1000.0 * 3600.0) if m < rain.size else 0.0
+        eng.set_input('P_rain', P)
+        eng.step(time_min=(i * 6.0) / 60.0)
+        assert eng.last_path == 'packed'
+        s = eng.read_scalars()
+        got = np.array([s.Q_outlet, s.u_outlet, s.d_outlet, s.f_outlet])
+        worst = max(worst, rel_err(got, series[i]))
+        if (i + 1) in (100, 400, 1200):
+            snap = {n: treynor_kw['s%d_%s' % (i + 1, n)] for n in GRIDS + SCALARS}
+            _cmp_grids(eng, snap, ('vol', 'd', 'u', 'Q'))
+            _cmp_scalars(eng, snap)
+            for n in ('vol', 'd', 'u', 'Q'):
+                got = (eng.Q if n == 'Q' else eng.vol if n == 'vol' else eng.own(getattr(eng, n)))
+                worst_cell = max(worst_cell, cell_rel_err(got.cpu().numpy(), snap[n]))
+    assert worst <= RTOL, worst
+    assert worst_cell <= 1e-9, worst_cell
+    s = eng.read_scalars()
+    assert s.n_neg_d == 0 and s.n_inf_d == 0 and s.n_neg_u == 0 and s.n_nan_u == 0
+
+
+@pytest.mark.parametrize('variant', ['kw_ga', 'dw_full'])
+def test_packed_storm_rise_and_recession(variant):
+    """A whole storm on the benchmarked kernels at 512^2: 500 steps of 50 mm/h rain on
+    pre-wetted soil, then 1000 steps of recession (1500 steps, dt = 2 s).  kw_ga = the
+    bench default (kinematic wave + fused Green-Ampt) against the numpy restatement of
+    the reference path; dw_full = diffusive wave + all fused sources (configs[3]) against
+    the C restatement.  Grids are compared at four checkpoints, by grid maximum
+    (<= 1e-11) and per cell (<= 1e-9 with the floor of conftest.cell_rel_err).
+    Per cell, the diffusive wave's velocity and discharge get 1e-6: u ~ sqrt|S_free| with
+    S_free = S_bed + (d - d_parent)/ds (:2606), so where the water surface is almost
+    level the last-bit differences of the packed path's depths (reciprocal
+    multiplications, include/tfb.h) are amplified by S_bed/|S_free| -- ill-conditioned
+    in the reference's own formula, invisible in the grid-maximum norm."""
+    import os
+    from oracle import c_oracle
+    from topoflow36_b200 import cases
+    n = 512
+    kin = variant == 'kw_ga'
+    tile = cases.noise_tile(n, n, seed=7)
+    DEM = cases.slab_dem(n, n, 0, n, 0, tile)
+    dx, dy, dd = o.pixel_dims(n, 30.0, 30.0)
+    code, _ = c_oracle.d8_flow_grid(DEM, dx, dy, dd)
+    ds32, dw32 = o.d8_ds_dw(code, dx, dy, dd)
+    with np.errstate(all='ignore'):
+        slope = np.float32(o.d8_slope(DEM, code, ds32))
+    width, angle, nval = cases.slab_params(n, n, 0, 0, seed=7)
+    outlet = tuple(int(v) for v in np.unravel_index(
+        np.argmax(c_oracle.d8_area(code, 900.0 / 1e6, with_counts=True)[1]), code.shape))
+    eng = _engine(code, dx, dy, dd, slope, width, angle, nval, dt=2.0, da=900.0,
+                  kinematic=kin, outlet=outlet)
+    eng.set_input('P_rain', cases.RAIN_50MMPH)
+    if kin:
+        ch = o.Channels(code, ds32, dw32, slope, width, angle, nval=nval, da=900.0, dt=2.0,
+                        outlet=outlet)
+        ch.P_rain = np.array(cases.RAIN_50MMPH)
+        eng.enable_fused_sources(infil=True, I0=cases.I0_WET)
+        I = np.zeros((n, n)) + cases.I0_WET
+    else:
+        ch = c_oracle.Channels(code, dx, dy, dd, slope, width, angle, nval, dt=2.0,
+                               kinematic=False, outlet=outlet, diag=False)
+        ch.nthreads = os.cpu_count() or 1
+        ch.set_input('P_rain', cases.RAIN_50MMPH)
+        src = dict(FULL_SRC, I0=0.5)            # soil wet enough for 50 mm/h to run off
+        eng.enable_fused_sources(**src)
+        ch.enable_fused(**src)
+        rng = np.random.default_rng(3)
+        Ta = 2.0 + 3.0 * (2.0 * rng.random((n, n)) - 1.0)
+        for nm, v in (('T_air', Ta), ('c0', 2.7), ('T0', -0.2), ('T_surf', 5.0), ('Qn_SW', 300.0),
+                      ('Qn_LW', -40.0)):
+            eng.set_input(nm, v)
+            ch.set_input(nm, v)
+    for k, v in cases.GA_TREYNOR.items():
+        eng.set_input(k, v)
+        if not kin:
+            ch.set_input(k, v)
+    worst = 0.0
+    worst_cell = dict(vol=0.0, d=0.0, u=0.0, Q=0.0)
+    q_series = []
+    with np.errstate(all='ignore'):
+        for i in range(1500):
+            if i == 500:
+                eng.set_input('P_rain', 0.0)
+                if kin:
+                    ch.P_rain = np.array(0.0)
+                else:
+                    ch.set_input('P_rain', 0.0)
+            if kin:
+                ch.IN, I = o.green_ampt_step(I, ch.P_rain, 0.0, dt=2.0, **cases.GA_TREYNOR)
+            else:
+                ch.time_min = i * 2.0 / 60.0
+            ch.step()
+            eng.step(time_min=i * 2.0 / 60.0)
+            if (i + 1) % 100 == 0:
+                s = eng.read_scalars()
+                q_series.append(s.Q_outlet)
+                want = float(ch.Q_outlet)
+                assert abs(s.Q_outlet - want) <= RTOL * max(abs(want), 1e-300), (i, s.Q_outlet, want)
+            if (i + 1) in (250, 500, 900, 1500):
+                for nm in ('vol', 'd', 'u', 'Q'):
+                    got = (eng.Q if nm == 'Q' else eng.vol if nm == 'vol'
+                           else eng.own(getattr(eng, nm))).cpu().numpy()
+                    worst = max(worst, rel_err(got, getattr(ch, nm)))
+                    worst_cell[nm] = max(worst_cell[nm], cell_rel_err(got, getattr(ch, nm)))
+    assert eng.last_path == 'packed'
+    assert worst <= RTOL, worst
+    for nm, e in worst_cell.items():
+        assert e <= (1e-9 if (kin or nm in ('vol', 'd')) else 1e-6), worst_cell
+    # a real hydrograph at the largest-area cell: it rises, peaks and recedes
+    q = np.array(q_series)
+    assert q.max() > 0 and q.argmax() < len(q) - 2 and q[-1] < 0.8 * q.max(), q
+    s = eng.read_scalars()
+    for nm in ('vol_R', 'vol_edge', 'vol_Q', 'Q_peak', 'T_peak', 'vol_IN'):
+        want = float(getattr(ch, nm)) if hasattr(ch, nm) else None
+        if want is not None:
+            assert abs(getattr(s, nm) - want) <= RTOL * max(abs(want), 1e-300), nm
+    assert s.n_neg_d == s.n_inf_d == s.n_neg_u == s.n_nan_u == s.n_inf_u == 0
 
 
 @pytest.mark.parametrize('tag', ['kw_man', 'kw_low', 'dw_man', 'dw_low'])
@@ -406,12 +538,15 @@ def test_flood_component_from_cfg(tmp_path, flood_gold):
     assert abs(float(c.vol_flood_sum) - g['kw_vol_flood'].sum()) <= 1e-11 * g['kw_vol_flood'].sum()
 
 
-@pytest.mark.parametrize('shape', [(1, 4), (2, 8), (15, 64), (16, 68), (31, 132), (47, 260), (100, 60)])
+@pytest.mark.parametrize('shape', [(1, 4), (2, 8), (15, 64), (16, 68), (31, 132), (47, 260), (100, 60),
+                                   (44, 29), (5, 7), (3, 1), (20, 33), (17, 67), (33, 130)])
 @pytest.mark.parametrize('kinematic', [True, False])
 def test_packed_path_ragged_shapes(shape, kinematic):
     """TMA tiles that hang over the grid edge (zero-filled by the TMA unit), grids
-    smaller than one 64 x 15 tile, a single row: packed kinematic (1 launch) and
-    diffusive (2 launches) steps against the numpy oracle, with fused Green-Ampt."""
+    smaller than one 64 x 15 tile, a single row or column, widths that are not a
+    multiple of 4 or odd (rows padded to the pitch; the lane holding the last column
+    of an odd grid has no second cell): packed kinematic (1 launch) and diffusive
+    (2 launches) steps against the numpy oracle, with fused Green-Ampt."""
     from topoflow36_b200 import cases
     ny, nx = shape
     rng = np.random.default_rng(ny * 1000 + nx)

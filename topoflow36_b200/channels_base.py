@@ -230,6 +230,11 @@ class channels_component(BMI_base.BMI_component):
 
     def get_value_ptr(self, long_var_name):
         name = self.get_var_name(long_var_name)
+        if name == 'R' and 'R' in self.__dict__:
+            # uniform forcing: R is the 0-D array of update_R (:1649), kept on the host.
+            # Should a provider switch to grids later, the R grid is materialised then.
+            self._R_requested = True
+            return self.__dict__['R']
         if name in _DEVICE_GRIDS and self.engine is not None:
             if name in _DIAG or (name == 'S_free' and not self.engine.kinematic):
                 if not self.engine.diag and self.engine.n_steps == 0:
@@ -480,6 +485,11 @@ class channels_component(BMI_base.BMI_component):
         else:
             from .slab import SlabChannels
             self.stepper = SlabChannels(lay, self.engine, self.group, peer=peer)
+        if getattr(self.engine, 'R', None) is None:
+            # R as the reference has it with uniform forcing: a 0-D array (:1649); a
+            # device grid takes its place when an input arrives as a grid (_update_R)
+            self.__dict__['R'] = self.initialize_scalar(0.0, dtype='float64')
+        self._R_requested = False
         self.update_total_channel_water_volume()
         self.vol_chan_sum0 = self.vol_chan_sum.copy()
         torch.cuda.current_stream().synchronize()
@@ -593,6 +603,26 @@ class channels_component(BMI_base.BMI_component):
         if rho != e.args.rho_H2O:
             e.args.rho_H2O = rho
 
+    def _update_R(self):
+        """Host side of update_R (:1548-1655) for uniform forcing: R = (P_rain + SM + GW +
+        MR) - (ET + IN) as a 0-D array, a scalar ET being dropped (:1629).  With any grid
+        input (or fused sources) R is a grid: the 0-D stand-in is retired, and if some
+        user holds a reference to R the kernel materialises the grid from now on."""
+        if 'R' not in self.__dict__:
+            return
+        e = self.engine
+        if not (e.flags & 0xF00) and not any(not isinstance(e.src[n], float) for n in _SRC_INPUTS):
+            v = e.src
+            self.__dict__['R'].fill((((v['P_rain'] + v['SM']) + v['GW']) + v['MR']) - (0.0 + v['IN']))
+            return
+        del self.__dict__['R']
+        if self._R_requested:
+            import torch
+            e.R = e._zeros(torch.float64)
+            e.args.R = e._p(e.R)
+            e.flags |= L.CH_WRITE_R
+            self._exported.add('R')
+
     def update(self, dt=-1.0):
         if self.comp_status.lower() == 'disabled':
             return
@@ -600,6 +630,7 @@ class channels_component(BMI_base.BMI_component):
         if self.mode == 'driver' and not self.SILENT:
             self.print_time_and_value(self.Q_outlet, 'Q_out', '[m^3/s]')
         self._bind_inputs()
+        self._update_R()
         self.stepper.step(float(self.time_min))
         if self._et_host is not None:
             # provider's ET array is masked in place (channels_base.py:1625-1627)
@@ -720,9 +751,10 @@ class channels_component(BMI_base.BMI_component):
         npart = e.lib.tfb_sources_partials_len()
         part = torch.zeros(npart, dtype=torch.float64, device=e.device)
         tick = torch.zeros(1, dtype=torch.int32, device=e.device)
-        Q = e.Q.contiguous()
+        # dense (ny, nx) views for the reduction kernel (copies only when rows are padded)
+        Q, u_, d_, vol_ = (t.contiguous() for t in (e.Q, e.own(e.u), e.own(e.d), e.vol))
         L.check(e.lib.tfb_channels_minmax(
-            Q.data_ptr(), e.own(e.u).data_ptr(), e.own(e.d).data_ptr(), e.vol.data_ptr(),
+            Q.data_ptr(), u_.data_ptr(), d_.data_ptr(), vol_.data_ptr(),
             e.ny, e.nx, out.data_ptr(), out[6:].data_ptr(), part.data_ptr(), tick.data_ptr(),
             L.stream_ptr()), 'tfb_channels_minmax')
         h = out.cpu().numpy()
@@ -770,7 +802,11 @@ class channels_component(BMI_base.BMI_component):
                 f = getattr(self, v + '_gs_file', self.case_prefix + '_2D-' + v + '.nc')
                 path = self.out_directory + os.path.splitext(os.path.basename(f))[0] + '.rts'
                 os.makedirs(self.out_directory, exist_ok=True)
-                self._out[('gs', v)] = open(self._unique(path), 'wb')
+                path = self._unique(path)
+                self._out[('gs', v)] = open(path, 'wb')
+                # side-car header like rts_files.open_new_file (:255-268, MAKE_RTI): the
+                # data set's own geometry and BYTE ORDER, FLOAT frames, min/max unknown
+                grid_io.write_output_rti(path, self.rti, 'FLOAT')
             if getattr(self, 'SAVE_%s_PIXELS' % K):
                 f = getattr(self, v + '_ts_file', self.case_prefix + '_0D-' + v + '.txt')
                 path = self.out_directory + os.path.splitext(os.path.basename(f))[0] + '.txt'
@@ -817,7 +853,10 @@ class channels_component(BMI_base.BMI_component):
                     if fh is None:
                         continue
                     if kind == 'gs':
-                        np.float32(grid).tofile(fh)
+                        frame = np.float32(grid)                     # rts_files.add_grid :375-389
+                        if self.rti.SWAP_ENDIAN:
+                            frame = frame.byteswap()
+                        frame.tofile(fh)
                     else:
                         self._write_ts_line(fh, grid[self.outlet_IDs])
                 elif kind == 'gs':
@@ -832,7 +871,9 @@ class channels_component(BMI_base.BMI_component):
                     self._write_ts_line(fh, vals)
 
     def _write_ts_line(self, fh, vals):
-        fh.write(('%15.7f' % float(self.time_min)) + ''.join('%15.7f' % x for x in vals) + '\n')
+        # text_ts_files.add_values :149-161 (20-wide columns), values_at_IDs :170-198 (float32)
+        fh.write(('%20.7f' % float(self.time_min))
+                 + ''.join('%20.7f' % x for x in np.float32(vals)) + '\n')
 
     def _async_frame(self, v, fh):
         import queue
@@ -868,6 +909,12 @@ class channels_component(BMI_base.BMI_component):
         k = w['free'].get()                           # blocks only if 3 frames are in flight
         cur = torch.cuda.current_stream()
         w['stage'][k].copy_(self._device_tensor(v))    # device snapshot + fp32 cast, compute stream
+        if self.rti.SWAP_ENDIAN:
+            # frames go out in the data set's byte order (rts_files.add_grid :387-389):
+            # the four bytes of every float32 are reversed on the device, so the host
+            # side still writes the pinned buffer as it is
+            b = w['stage'][k].view(torch.uint8).view(self.ny, self.nx, 4)
+            b.copy_(b.flip(2))
         ready = torch.cuda.Event()
         ready.record(cur)
         with torch.cuda.stream(w['stream']):

@@ -271,7 +271,7 @@ __device__ __forceinline__ void vol_depth(const tfb_channels_step_args &a, const
 }
 
 // predicated loads of the children's discharge
-__device__ __forceinline__ void load_children(const double *__restrict__ Qp, int nx,
+__device__ __forceinline__ void load_children(const double *__restrict__ Qp, int nx /* row pitch */,
                                               unsigned cmask, double *Qc) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -313,12 +313,12 @@ __device__ __forceinline__ void finish_cell(const tfb_channels_step_args &a,
         if (noflow) { pr = -a.row0; pc = 0; }
         double d_par = 0.0;
         if (pr >= -a.halo && pr < a.ny + a.halo) {
-            const int64_t ip = (int64_t)pr * a.nx + pc;
+            const int64_t ip = (int64_t)pr * a.pitch + pc;
             Cell gp;
             load_cell_scalar(a, pr, ip, gp);
             double Qc[8], vp, Rp, df_par;
             SrcState nsp;
-            load_children(a.Q_in + ip, a.nx, gp.cmask, Qc);
+            load_children(a.Q_in + ip, a.pitch, gp.cmask, Qc);
             vol_depth<SRC, UR, false>(a, k, ip, gp, Qc, vp, d_par, df_par, Rp, nsp, nullptr);
             if (a.flags & TFB_CH_FLOOD) d_par = d_par + df_par;      // total depth :2593-2596
         }
@@ -454,7 +454,7 @@ channels_step_kernel(const tfb_channels_step_args a, const ChConsts k) {
         if (c0 >= a.nx) continue;
         const int r_end = min(a.ny, (ty + 1) * kTileRows);
         for (int r = ty * kTileRows + threadIdx.y; r < r_end; r += kBY) {
-            const int64_t i = (int64_t)r * a.nx + c0;
+            const int64_t i = (int64_t)r * a.pitch + c0;
             // ---- own inputs, 128-bit where possible -----------------------
             unsigned gw[VEC];
             if (VEC == 2) {
@@ -490,7 +490,7 @@ channels_step_kernel(const tfb_channels_step_args a, const ChConsts k) {
             double Qc[VEC][8];
 #pragma unroll
             for (int j = 0; j < VEC; ++j)
-                load_children(a.Q_in + i + j, a.nx, gw[j] >> 8, Qc[j]);
+                load_children(a.Q_in + i + j, a.pitch, gw[j] >> 8, Qc[j]);
             V<VEC> o_vol, o_d, o_u, o_Q;
             V<VEC> o_Rh, o_A, o_P, o_f, o_tau, o_us, o_fr, o_S, o_R;
 #pragma unroll
@@ -714,8 +714,9 @@ extern "C" int tfb_channels_pack_geo(const uint8_t *code, int32_t ny, int32_t nx
 
 extern "C" int tfb_channels_step(const tfb_channels_step_args *ap, void *stream) {
     TFB_ARG_CHECK(ap != nullptr);
-    const tfb_channels_step_args &a = *ap;
-    TFB_ARG_CHECK(a.ny > 0 && a.nx > 0 && a.halo >= 0);
+    tfb_channels_step_args a = *ap;
+    if (a.pitch == 0) a.pitch = a.nx;                  // dense rows
+    TFB_ARG_CHECK(a.ny > 0 && a.nx > 0 && a.halo >= 0 && a.pitch >= a.nx);
     TFB_ARG_CHECK(a.geo && a.dx && a.dy && a.dd);
     TFB_ARG_CHECK(a.vol && a.vol_out && a.Q_in && a.Q_out && a.d && a.u);
     TFB_ARG_CHECK(a.Q_in != a.Q_out);
@@ -749,7 +750,7 @@ extern "C" int tfb_channels_step(const tfb_channels_step_args *ap, void *stream)
     cudaStream_t st = (cudaStream_t)stream;
     // 128-bit path needs every row 16-byte aligned: even nx and aligned bases
     auto al16 = [](const void *p) { return p == nullptr || (((uintptr_t)p) & 15u) == 0; };
-    const bool vec2 = (a.nx % 2 == 0) && al16(a.vol) && al16(a.vol_out) && al16(a.Q_in) &&
+    const bool vec2 = (a.nx % 2 == 0) && (a.pitch % 2 == 0) && al16(a.vol) && al16(a.vol_out) && al16(a.Q_in) &&
                       al16(a.Q_out) && al16(a.d) && al16(a.u) && al16(a.S_bed) &&
                       al16(a.sqrtS) && al16(a.width.ptr) && al16(a.tan_angle.ptr) &&
                       al16(a.cos_angle.ptr) && al16(a.rough.ptr) && al16(a.sinu.ptr) &&

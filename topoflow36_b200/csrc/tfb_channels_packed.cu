@@ -588,7 +588,7 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
                 const double da_r = __ldg(rgp + 3).x;
                 PkVD o;
                 pk_vol_depth<SRC>(k, lut, x, g0, g1, g2, da_r, acc, o);
-                const int64_t i = (int64_t)r * a.nx + c0;
+                const int64_t i = (int64_t)r * a.pitch + c0;
                 const bool nf = (x.g & 0xffu) == 0u;
                 if (kKW) {
                     const bool dg = (x.g & 0x55u) != 0u, ns = (x.g & 0x88u) != 0u;
@@ -641,7 +641,12 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
                 const double2 *rgp = reinterpret_cast<const double2 *>(p.row_geom + (int64_t)r * kRowGeom);
                 const double2 g0 = __ldg(rgp), g1 = __ldg(rgp + 1), g2 = __ldg(rgp + 2);
                 const double da_r = __ldg(rgp + 3).x;
-                const int64_t i = (int64_t)r * a.nx + c0;
+                const int64_t i = (int64_t)r * a.pitch + c0;
+                // odd nx: the lane that holds the last column has no second cell.  Its
+                // inputs are the TMA unit's zero fill (code 0, vol 0, Q 0); with pixel
+                // area 0, width 1 and I = 1 it is a dry noflow cell that adds exactly
+                // 0 to every sum and counter, and its stores land in the row padding
+                const bool dead1 = (c0 + 1 >= a.nx);
                 PkVD o0, o1;
                 double u0 = 0.0, u1 = 0.0, Q0 = 0.0, Q1 = 0.0;
                 {   // cell 0 (col c0): west = *0.y, same = *1.x, east = *1.y; children in the
@@ -660,11 +665,12 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
                 }
                 {   // cell 1 (col c0+1): west = *1.x, same = *1.y, east = *E
                     PkIn x;
-                    x.g = geo.y; x.vol = vol.y; x.I = Iv.y; x.h = Hv.y; x.Ta = Tv.y; x.w = (double)w.y;
+                    x.g = geo.y; x.vol = vol.y; x.I = dead1 ? 1.0 : Iv.y; x.h = Hv.y; x.Ta = Tv.y;
+                    x.w = dead1 ? 1.0 : (double)w.y;
                     x.qself = m1.y;
                     x.ch[0] = b1.x; x.ch[1] = m1.x; x.ch[2] = a1.x; x.ch[3] = a1.y;
                     x.ch[4] = aE; x.ch[5] = mE; x.ch[6] = bE; x.ch[7] = b1.y;
-                    pk_vol_depth<SRC>(k, lut, x, g0, g1, g2, da_r, acc, o1);
+                    pk_vol_depth<SRC>(k, lut, x, g0, g1, g2, dead1 ? 0.0 : da_r, acc, o1);
                     if (kKW) {
                         const bool dg = (geo.y & 0x55u) != 0u, ns = (geo.y & 0x88u) != 0u;
                         pk_velocity(a, k, lut, geo.y, o1.d, x.w, coef.y, dg ? g2.x : (ns ? g2.y : g1.y),
@@ -827,7 +833,7 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
                 const bool dg = (code & 0x55u) != 0u, ns = (code & 0x88u) != 0u;
                 const double inv_ds = dg ? g2.x : (ns ? g2.y : g1.y);
                 const double Sf = Sb + ((d - d_par) * inv_ds);            // :2606-2607
-                const int64_t i = (int64_t)r * a.nx + c0;
+                const int64_t i = (int64_t)r * a.pitch + c0;
                 double qs = 0.0;
                 if (r + a.row0 == a.outlet_row && c0 == a.outlet_col) qs = __ldg(a.Q_in + i);
                 double u, Qn;
@@ -854,7 +860,7 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
                 const double2 dv = *reinterpret_cast<const double2 *>(dc);
                 const double2 *rgp = reinterpret_cast<const double2 *>(p.row_geom + (int64_t)r * kRowGeom);
                 const double2 g1 = __ldg(rgp + 1), g2 = __ldg(rgp + 2);
-                const int64_t i = (int64_t)r * a.nx + c0;
+                const int64_t i = (int64_t)r * a.pitch + c0;
                 double uo[2], Qo[2];
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
@@ -939,9 +945,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 struct MapKey {
-    const void *ptr; int64_t rows, cols; int dtype; int box0, box1; int dev;
+    const void *ptr; int64_t rows, cols, pitch; int dtype; int box0, box1; int dev;
     bool operator==(const MapKey &o) const {
-        return ptr == o.ptr && rows == o.rows && cols == o.cols && dtype == o.dtype &&
+        return ptr == o.ptr && rows == o.rows && cols == o.cols && pitch == o.pitch && dtype == o.dtype &&
                box0 == o.box0 && box1 == o.box1 && dev == o.dev;
     }
 };
@@ -950,11 +956,11 @@ std::mutex g_map_mu;
 std::vector<MapEntry> g_maps;
 EncodeTiledFn g_encode = nullptr;
 
-int get_map(const void *ptr, int64_t rows, int64_t cols, CUtensorMapDataType dtype, int esize,
-            int box0, int box1, CUtensorMap *out) {
+int get_map(const void *ptr, int64_t rows, int64_t cols, int64_t pitch, CUtensorMapDataType dtype,
+            int esize, int box0, int box1, CUtensorMap *out) {
     int dev = 0;
     TFB_CUDA_CHECK(cudaGetDevice(&dev));
-    const MapKey key{ptr, rows, cols, (int)dtype, box0, box1, dev};
+    const MapKey key{ptr, rows, cols, pitch, (int)dtype, box0, box1, dev};
     std::lock_guard<std::mutex> lock(g_map_mu);
     for (const MapEntry &e : g_maps)
         if (e.key == key) { *out = e.map; return TFB_OK; }
@@ -970,7 +976,8 @@ int get_map(const void *ptr, int64_t rows, int64_t cols, CUtensorMapDataType dty
         g_encode = (EncodeTiledFn)fn;
     }
     const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    const cuuint64_t gstride[1] = {(cuuint64_t)cols * (cuuint64_t)esize};
+    // the tensor is `cols` wide (cells beyond it read as zero fill), its rows `pitch` apart
+    const cuuint64_t gstride[1] = {(cuuint64_t)pitch * (cuuint64_t)esize};
     const cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
     const cuuint32_t estr[2] = {1u, 1u};
     MapEntry e;
@@ -1002,22 +1009,22 @@ int launch_main_(const tfb_channels_step_args &a, const tfb_channels_packed &p, 
     static_assert(SL::stages >= 2, "ring needs at least two slots");
     PkMaps m;
     const int64_t rows_h = (int64_t)a.ny + 2 * a.halo;
-    const size_t hb = (size_t)a.halo * a.nx;               // elements between allocation and row 0
+    const size_t hb = (size_t)a.halo * a.pitch;            // elements between allocation and row 0
     const CUtensorMapDataType F64 = CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
     int rc;
-    if ((rc = get_map(a.Q_in - hb, rows_h, a.nx, F64, 8, kQW, kQR, &m.Q))) return rc;
-    if ((rc = get_map(a.vol - hb, rows_h, a.nx, F64, 8, kTW, kTR, &m.vol))) return rc;
+    if ((rc = get_map(a.Q_in - hb, rows_h, a.nx, a.pitch, F64, 8, kQW, kQR, &m.Q))) return rc;
+    if ((rc = get_map(a.vol - hb, rows_h, a.nx, a.pitch, F64, 8, kTW, kTR, &m.vol))) return rc;
     m.coef = m.I = m.H = m.T = m.vol;
     if (VAR == PK_KW)
-        if ((rc = get_map(p.coef, a.ny, a.nx, F64, 8, kTW, kTR, &m.coef))) return rc;
+        if ((rc = get_map(p.coef, a.ny, a.nx, a.pitch, F64, 8, kTW, kTR, &m.coef))) return rc;
     const bool use_h = (SRC == PK_SRC_FULL) && (k.flags & TFB_CH_SRC_SNOW);
     const bool use_i = (SRC == PK_SRC_GA) || ((SRC == PK_SRC_FULL) && (k.flags & TFB_CH_SRC_INFIL));
     const bool use_t = (SRC == PK_SRC_FULL) && k.tair_grid;
-    if (use_i) if ((rc = get_map(a.I - hb, rows_h, a.nx, F64, 8, kTW, kTR, &m.I))) return rc;
-    if (use_h) if ((rc = get_map(a.h_swe - hb, rows_h, a.nx, F64, 8, kTW, kTR, &m.H))) return rc;
-    if (use_t) if ((rc = get_map(a.T_air.ptr - hb, rows_h, a.nx, F64, 8, kTW, kTR, &m.T))) return rc;
-    if ((rc = get_map(p.width32, a.ny, a.nx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, kTW, kTR, &m.w))) return rc;
-    if ((rc = get_map(p.geo32, a.ny, a.nx, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, kTW, kTR, &m.geo))) return rc;
+    if (use_i) if ((rc = get_map(a.I - hb, rows_h, a.nx, a.pitch, F64, 8, kTW, kTR, &m.I))) return rc;
+    if (use_h) if ((rc = get_map(a.h_swe - hb, rows_h, a.nx, a.pitch, F64, 8, kTW, kTR, &m.H))) return rc;
+    if (use_t) if ((rc = get_map(a.T_air.ptr - hb, rows_h, a.nx, a.pitch, F64, 8, kTW, kTR, &m.T))) return rc;
+    if ((rc = get_map(p.width32, a.ny, a.nx, a.pitch, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, kTW, kTR, &m.w))) return rc;
+    if ((rc = get_map(p.geo32, a.ny, a.nx, a.pitch, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, kTW, kTR, &m.geo))) return rc;
     const int smem = SL::stages * SL::bytes;
     static bool attr_set[64] = {false};
     int dev = 0;
@@ -1056,13 +1063,13 @@ int launch_dwb(const tfb_channels_step_args &a, const tfb_channels_packed &p, Pk
     k.n_boundary = k.tiles_x * (k.tiles_y > 1 ? 2 : 1);
     PkMapsB m;
     const int64_t rows_h = (int64_t)a.ny + 2 * a.halo;
-    const size_t hb = (size_t)a.halo * a.nx;
+    const size_t hb = (size_t)a.halo * a.pitch;
     int rc;
-    if ((rc = get_map(a.d - hb, rows_h, a.nx, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, kQW, kQR, &m.D))) return rc;
-    if ((rc = get_map(p.inv_rough, a.ny, a.nx, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, kTW, kTR, &m.N))) return rc;
-    if ((rc = get_map(p.S32, a.ny, a.nx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, kTW, kTR, &m.S))) return rc;
-    if ((rc = get_map(p.width32, a.ny, a.nx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, kTW, kTR, &m.w))) return rc;
-    if ((rc = get_map(p.geo32, a.ny, a.nx, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, kTW, kTR, &m.geo))) return rc;
+    if ((rc = get_map(a.d - hb, rows_h, a.nx, a.pitch, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, kQW, kQR, &m.D))) return rc;
+    if ((rc = get_map(p.inv_rough, a.ny, a.nx, a.pitch, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, kTW, kTR, &m.N))) return rc;
+    if ((rc = get_map(p.S32, a.ny, a.nx, a.pitch, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, kTW, kTR, &m.S))) return rc;
+    if ((rc = get_map(p.width32, a.ny, a.nx, a.pitch, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, kTW, kTR, &m.w))) return rc;
+    if ((rc = get_map(p.geo32, a.ny, a.nx, a.pitch, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, kTW, kTR, &m.geo))) return rc;
     const int smem = SL::stages * SL::bytes;
     static bool attr_set[64] = {false};
     int dev = 0;
@@ -1080,12 +1087,14 @@ int launch_dwb(const tfb_channels_step_args &a, const tfb_channels_packed &p, Pk
 }
 
 // argument checks and constants shared by the three entry points
-int prepare(const tfb_channels_step_args *ap, const tfb_channels_packed *pp, bool diffusive,
-            PkConsts &k, int &src_mode) {
+int prepare(const tfb_channels_step_args *ap, tfb_channels_step_args &a,
+            const tfb_channels_packed *pp, bool diffusive, PkConsts &k, int &src_mode) {
     TFB_ARG_CHECK(ap != nullptr && pp != nullptr);
-    const tfb_channels_step_args &a = *ap;
+    a = *ap;
+    if (a.pitch == 0) a.pitch = a.nx;                // dense rows
     const tfb_channels_packed &p = *pp;
-    TFB_ARG_CHECK(a.ny > 0 && a.nx > 0 && a.halo >= 0 && (a.nx % 4) == 0);
+    // TMA: 16-byte row strides for the 8-byte and the 4-byte streams alike
+    TFB_ARG_CHECK(a.ny > 0 && a.nx > 0 && a.halo >= 0 && a.pitch >= a.nx && (a.pitch % 4) == 0);
     TFB_ARG_CHECK(p.geo32 && p.width32 && p.angle_lut && p.row_geom && p.n_angles >= 1 &&
                   p.n_angles <= 256);
     TFB_ARG_CHECK(a.vol && a.vol_out && a.Q_in && a.Q_out && a.d && a.u);
@@ -1200,12 +1209,13 @@ extern "C" int tfb_channels_step_packed(const tfb_channels_step_args *ap,
                                         const tfb_channels_packed *pp, void *stream) {
     PkConsts k;
     int mode = 0;
-    const int rc = prepare(ap, pp, false, k, mode);
+    tfb_channels_step_args an;
+    const int rc = prepare(ap, an, pp, false, k, mode);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (mode == PK_SRC_NONE) return launch_main<PK_SRC_NONE, PK_KW, CfgNone>(*ap, *pp, k, st);
-    if (mode == PK_SRC_GA) return launch_main<PK_SRC_GA, PK_KW, CfgGA>(*ap, *pp, k, st);
-    return launch_main<PK_SRC_FULL, PK_KW, CfgFull>(*ap, *pp, k, st);
+    if (mode == PK_SRC_NONE) return launch_main<PK_SRC_NONE, PK_KW, CfgNone>(an, *pp, k, st);
+    if (mode == PK_SRC_GA) return launch_main<PK_SRC_GA, PK_KW, CfgGA>(an, *pp, k, st);
+    return launch_main<PK_SRC_FULL, PK_KW, CfgFull>(an, *pp, k, st);
 }
 
 extern "C" int tfb_channels_step_packed_dw_c(const tfb_channels_step_args *ap,
@@ -1306,16 +1316,17 @@ extern "C" int tfb_channels_step_packed_p2p(const tfb_channels_step_args *ap,
     TFB_ARG_CHECK(ph != nullptr);
     PkConsts k;
     int mode = 0;
-    int rc = prepare(ap, pp, false, k, mode);
+    tfb_channels_step_args an;
+    int rc = prepare(ap, an, pp, false, k, mode);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     // both neighbours must have finished the previous step: their halo rows are in
     // my memory, and they no longer read the halo rows this step overwrites
     PkPeer peer;
     if ((rc = make_peer(ph, st, peer))) return rc;
-    if (mode == PK_SRC_NONE) return launch_main_peer<PK_SRC_NONE, CfgNone>(*ap, *pp, k, st, peer);
-    if (mode == PK_SRC_GA) return launch_main_peer<PK_SRC_GA, CfgGA>(*ap, *pp, k, st, peer);
-    return launch_main_peer<PK_SRC_FULL, CfgFull>(*ap, *pp, k, st, peer);
+    if (mode == PK_SRC_NONE) return launch_main_peer<PK_SRC_NONE, CfgNone>(an, *pp, k, st, peer);
+    if (mode == PK_SRC_GA) return launch_main_peer<PK_SRC_GA, CfgGA>(an, *pp, k, st, peer);
+    return launch_main_peer<PK_SRC_FULL, CfgFull>(an, *pp, k, st, peer);
 }
 
 extern "C" int tfb_channels_step_packed_dw_a_p2p(const tfb_channels_step_args *ap,
@@ -1324,35 +1335,38 @@ extern "C" int tfb_channels_step_packed_dw_a_p2p(const tfb_channels_step_args *a
     TFB_ARG_CHECK(ph != nullptr);
     PkConsts k;
     int mode = 0;
-    int rc = prepare(ap, pp, true, k, mode);
+    tfb_channels_step_args an;
+    int rc = prepare(ap, an, pp, true, k, mode);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     PkPeer peer;
     if ((rc = make_peer(ph, st, peer))) return rc;
-    if (mode == PK_SRC_NONE) return launch_main_peer<PK_SRC_NONE, CfgNone, PK_DWA>(*ap, *pp, k, st, peer);
-    if (mode == PK_SRC_GA) return launch_main_peer<PK_SRC_GA, CfgGA, PK_DWA>(*ap, *pp, k, st, peer);
-    return launch_main_peer<PK_SRC_FULL, CfgFull, PK_DWA>(*ap, *pp, k, st, peer);
+    if (mode == PK_SRC_NONE) return launch_main_peer<PK_SRC_NONE, CfgNone, PK_DWA>(an, *pp, k, st, peer);
+    if (mode == PK_SRC_GA) return launch_main_peer<PK_SRC_GA, CfgGA, PK_DWA>(an, *pp, k, st, peer);
+    return launch_main_peer<PK_SRC_FULL, CfgFull, PK_DWA>(an, *pp, k, st, peer);
 }
 
 extern "C" int tfb_channels_step_packed_dw_a(const tfb_channels_step_args *ap,
                                              const tfb_channels_packed *pp, void *stream) {
     PkConsts k;
     int mode = 0;
-    const int rc = prepare(ap, pp, true, k, mode);
+    tfb_channels_step_args an;
+    const int rc = prepare(ap, an, pp, true, k, mode);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (mode == PK_SRC_NONE) return launch_main<PK_SRC_NONE, PK_DWA, CfgNone>(*ap, *pp, k, st);
-    if (mode == PK_SRC_GA) return launch_main<PK_SRC_GA, PK_DWA, CfgGA>(*ap, *pp, k, st);
-    return launch_main<PK_SRC_FULL, PK_DWA, CfgFull>(*ap, *pp, k, st);
+    if (mode == PK_SRC_NONE) return launch_main<PK_SRC_NONE, PK_DWA, CfgNone>(an, *pp, k, st);
+    if (mode == PK_SRC_GA) return launch_main<PK_SRC_GA, PK_DWA, CfgGA>(an, *pp, k, st);
+    return launch_main<PK_SRC_FULL, PK_DWA, CfgFull>(an, *pp, k, st);
 }
 
 extern "C" int tfb_channels_step_packed_dw_b(const tfb_channels_step_args *ap,
                                              const tfb_channels_packed *pp, void *stream) {
     PkConsts k;
     int mode = 0;
-    const int rc = prepare(ap, pp, true, k, mode);
+    tfb_channels_step_args an;
+    const int rc = prepare(ap, an, pp, true, k, mode);
     if (rc) return rc;
-    return launch_dwb<CfgDwB, false>(*ap, *pp, k, (cudaStream_t)stream, PkPeer{});
+    return launch_dwb<CfgDwB, false>(an, *pp, k, (cudaStream_t)stream, PkPeer{});
 }
 
 extern "C" int tfb_channels_step_packed_dw_b_p2p(const tfb_channels_step_args *ap,
@@ -1361,9 +1375,10 @@ extern "C" int tfb_channels_step_packed_dw_b_p2p(const tfb_channels_step_args *a
     TFB_ARG_CHECK(ph != nullptr);
     PkConsts k;
     int mode = 0;
-    int rc = prepare(ap, pp, true, k, mode);
+    tfb_channels_step_args an;
+    int rc = prepare(ap, an, pp, true, k, mode);
     if (rc) return rc;
     PkPeer peer;
     if ((rc = make_peer(ph, (cudaStream_t)stream, peer))) return rc;
-    return launch_dwb<CfgDwB, true>(*ap, *pp, k, (cudaStream_t)stream, peer);
+    return launch_dwb<CfgDwB, true>(an, *pp, k, (cudaStream_t)stream, peer);
 }

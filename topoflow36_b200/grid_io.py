@@ -143,6 +143,46 @@ def write_rti(path, info):
         fh.write('\n'.join(lines))
 
 
+def write_output_rti(grid_path, info, data_type='FLOAT'):
+    """Side-car header of an OUTPUT grid stack: what rts_files.open_new_file (:255-268)
+    derives from the data set's RTI -- same geometry, same byte order, the stack's data
+    type, `TopoFlow 3.0` as source, min / max unknown (-9999) -- laid out with the labels
+    and number formats of rti_files.write_info (:430-540), which both the reference and
+    read_rti() parse."""
+    f = lambda v: ('%22.12f' % float(v)).strip()
+    lines = [
+        'RiverTools Info File', '',
+        ';--------------------', ';Description of Grid', ';--------------------',
+        'Grid filename:  ' + str(grid_path),
+        'Grid source:    TopoFlow 3.0', ' ',
+        ';----------------------', ';Grid dimensions, etc.', ';----------------------',
+        'Number of columns:  %d' % info.ncols,
+        'Number of rows:     %d' % info.nrows,
+        'Data type:          ' + data_type.upper(),
+        'Byte order:         ' + info.byte_order, '',
+        ';--------------------', ';Pixel geometry info', ';--------------------',
+        'Pixel geometry code:  %d' % int(info.pixel_geom),
+        'Pixel x-resolution:   ' + f(info.xres),
+        'Pixel y-resolution:   ' + f(info.yres),
+        'Pixel z-resolution:   ' + f(info.zres),
+        'Z-resolution units:   ' + info.z_units, '',
+        ';--------------------------------------------------',
+        ';Bounding box coordinates (degrees lat/lon or UTM)',
+        ';--------------------------------------------------',
+        'South edge y-coordinate:  ' + f(info.y_south_edge),
+        'North edge y-coordinate:  ' + f(info.y_north_edge),
+        'East  edge x-coordinate:  ' + f(info.x_east_edge),
+        'West  edge x-coordinate:  ' + f(info.x_west_edge),
+        'Measurement units:        ' + info.box_units, '',
+        ';------------------', ';Min and max value', ';------------------',
+        'Minimum value:  ' + f(-9999.0),
+        'Maximum value:  ' + f(-9999.0), '',
+        ';---------', ';UTM zone', ';---------',
+        'UTM zone: ' + str(info.UTM_zone), '', '']
+    with open(os.path.splitext(grid_path)[0] + '.rti', 'w') as fh:
+        fh.write('\n'.join(lines))
+
+
 def read_rtg(path, info, rtg_type=None):
     """Read a whole grid as (nrows, ncols) in the file's own dtype."""
     dtype = _NUMPY_TYPE[(rtg_type or info.data_type).upper()]

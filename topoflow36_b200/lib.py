@@ -62,7 +62,7 @@ class ChannelsStepArgs(C.Structure):
         ('is_R_grid', C.c_int32),
         ('dt', C.c_double), ('time_min', C.c_double), ('rho_H2O', C.c_double),
         ('n_pixels_global', C.c_int64),
-        ('halo', C.c_int32),
+        ('halo', C.c_int32), ('pitch', C.c_int32),
         ('geo', vp), ('dx', vp), ('dy', vp), ('dd', vp),
         ('sinu', SG), ('da', SG), ('S_bed', vp), ('sqrtS', vp), ('width', SG),
         ('tan_angle', SG), ('cos_angle', SG), ('rough', SG),

@@ -7,9 +7,13 @@ component (``channels_base.py`` in this package) and the C ABI; it has no
 numerical code of its own apart from the one-time initial volume
 (channels_base.py:1331-1336 in the reference).
 
-Layout: every per-cell tensor is allocated as (ny + 2*halo, nx) and the kernels
+Layout: every per-cell tensor is allocated as (ny + 2*halo, pitch) and the kernels
 get a pointer to the first OWNED row, so neighbour rows of an adjacent slab are
-ordinary memory.  ``halo = 0`` for a single GPU.
+ordinary memory.  ``halo = 0`` for a single GPU.  ``pitch`` = nx rounded up to a
+multiple of 4 elements (= nx for every grid whose width already is): the TMA unit
+needs 16-byte row strides for the 8-byte and the 4-byte streams alike.  Columns
+[nx, pitch) hold zeros (D8 code 0, no water), are never stepped and never show in
+``own()`` views; the one-time set-up kernels simply see a grid ``pitch`` wide.
 """
 import ctypes as C
 
@@ -21,6 +25,12 @@ from . import lib as L
 _DIAG_NAMES = ('Rh', 'A_wet', 'P_wet', 'f', 'tau', 'u_star', 'froude')
 _SRC_SG = ('P_rain', 'SM', 'GW', 'MR', 'IN', 'ET', 'T_air', 'c0', 'T0', 'T_surf',
            'Qn_SW', 'Qn_LW', 'Ks', 'Ki', 'qs', 'qi', 'G', 'h_table', 'elev')
+
+
+def row_pitch(nx):
+    """Elements per row of every per-cell device array: nx rounded up to 4 (16-byte
+    row strides for fp64, fp32 and 32-bit words alike; include/tfb.h `pitch`)."""
+    return (int(nx) + 3) // 4 * 4
 
 
 def _is_grid(x):
@@ -43,6 +53,7 @@ class ChannelsEngine(object):
         self.device = torch.device(device if device is not None
                                    else 'cuda:%d' % torch.cuda.current_device())
         self.ny, self.nx, self.halo = int(ny), int(nx), int(halo)
+        self.pitch = row_pitch(self.nx)
         self.row0 = int(row0)
         self.ny_global = int(ny_global if ny_global is not None else ny)
         self.kinematic, self.manning, self.diag = kinematic, manning, diag
@@ -52,6 +63,7 @@ class ChannelsEngine(object):
         self.args = a
         a.ny, a.nx, a.row0, a.ny_global = self.ny, self.nx, self.row0, self.ny_global
         a.halo = self.halo
+        a.pitch = self.pitch
         a.outlet_row, a.outlet_col = int(outlet[0]), int(outlet[1])
         a.dt = self.dt
         a.rho_H2O = float(rho_H2O)
@@ -79,7 +91,7 @@ class ChannelsEngine(object):
         self.code = self._grid(code, torch.uint8)
         # packed geo word per cell: D8 code + child mask (parent-side gather)
         self.geo = self._zeros(torch.int16)
-        L.check(self.lib.tfb_channels_pack_geo(self._p(self.code), self.ny, self.nx, self.halo,
+        L.check(self.lib.tfb_channels_pack_geo(self._p(self.code), self.ny, self.pitch, self.halo,
                                                self._p(self.geo), L.stream_ptr()),
                 'tfb_channels_pack_geo')
         a.geo = self._p(self.geo)
@@ -124,13 +136,13 @@ class ChannelsEngine(object):
         # the two discharge buffers may come from peer-mappable allocations (slab.PeerHalos)
         self.Q_buf = list(q_buffers) if q_buffers is not None else [z(), z()]
         for t in self.Q_buf:
-            if tuple(t.shape) != (self.ny + 2 * self.halo, self.nx) or t.dtype != torch.float64:
-                raise L.TfbError('q_buffers must be (ny + 2*halo, nx) float64 CUDA tensors')
+            if tuple(t.shape) != (self.ny + 2 * self.halo, self.pitch) or t.dtype != torch.float64:
+                raise L.TfbError('q_buffers must be (ny + 2*halo, pitch) float64 CUDA tensors')
         self.qcur = 0             # Q buffer the NEXT step reads
         self.scur = 0             # state buffer (vol, I, h_swe) the next step reads
         self.d, self.u = (d_buffer if d_buffer is not None else z()), z()
-        if tuple(self.d.shape) != (self.ny + 2 * self.halo, self.nx) or self.d.dtype != torch.float64:
-            raise L.TfbError('d_buffer must be a (ny + 2*halo, nx) float64 CUDA tensor')
+        if tuple(self.d.shape) != (self.ny + 2 * self.halo, self.pitch) or self.d.dtype != torch.float64:
+            raise L.TfbError('d_buffer must be a (ny + 2*halo, pitch) float64 CUDA tensor')
         a.d, a.u = self._p(self.d), self._p(self.u)
         if diag:
             for n in _DIAG_NAMES:
@@ -183,17 +195,21 @@ class ChannelsEngine(object):
             self._try_pack()
 
     # ------------------------------------------------------------ flood option
-    def _ds64(self):
-        """Flow length ds = sinu * ds_d8 (float64 values of the float32 D8 grid)."""
-        a = self.args
-        ds32 = torch.empty((self.ny + 2 * self.halo, self.nx), dtype=torch.float32,
+    def _ds32(self):
+        """float32 D8 flow lengths of the haloed (pitch-wide) grid (d8_global.py:960-1027)."""
+        ds32 = torch.empty((self.ny + 2 * self.halo, self.pitch), dtype=torch.float32,
                            device=self.device)
         L.check(self.lib.tfb_d8_ds_dw(self.code.data_ptr(), self.dx.data_ptr(),
                                       self.dy.data_ptr(), self.dd.data_ptr(),
-                                      self.ny + 2 * self.halo, self.nx,
+                                      self.ny + 2 * self.halo, self.pitch,
                                       ds32.data_ptr(), None, L.stream_ptr()), 'tfb_d8_ds_dw')
+        return ds32
+
+    def _ds64(self):
+        """Flow length ds = sinu * ds_d8 (float64 values of the float32 D8 grid)."""
+        a = self.args
         sn = self.sinu_grid if self.sinu_grid is not None else a.sinu.val
-        return sn * ds32.double()
+        return sn * self._ds32().double()
 
     def _init_flood(self, d_bankfull, flood_manning_n, width_ratio):
         """FLOOD_OPTION state (channels_base.py:1346-1388): bankfull channel volume
@@ -214,16 +230,24 @@ class ChannelsEngine(object):
     # ------------------------------------------------------------ packed path
     def _try_pack(self):
         """Build the compact static inputs of tfb_channels_step_packed when the
-        configuration allows it (kinematic, Manning, no diagnostics, nx % 4 == 0,
-        scalar sinuosity / pixel area, float32-exact widths, <= 256 distinct
-        bank angles).  Everything is lossless; otherwise the generic kernel runs."""
+        configuration allows it (Manning, no diagnostics, scalar sinuosity, float32-exact
+        widths, <= 256 distinct bank angles).  Everything is lossless; otherwise the
+        generic kernel runs.  Every per-cell array is (ny, pitch) like the state."""
         a = self.args
         if ((not self.manning) or self.diag or self.flood or self.attenuate
                 or (self.flags & L.CH_WRITE_R)):
             return
-        if self.nx % 4 or self.sinu_grid is not None:
+        if self.sinu_grid is not None:
             return
         dev = self.device
+
+        def padc(t):
+            """(ny, nx) -> (ny, pitch), zero padding (no copy when pitch == nx)."""
+            if t is None or self.pitch == self.nx:
+                return None if t is None else t.contiguous()
+            out = torch.zeros((self.ny, self.pitch), dtype=t.dtype, device=dev)
+            out[:, :self.nx] = t
+            return out
         full = lambda g, v: (self.own(g) if g is not None
                              else torch.full((self.ny, self.nx), float(v), dtype=torch.float64,
                                              device=dev))
@@ -251,21 +275,22 @@ class ChannelsEngine(object):
         lut[:, 2] = 1.0 / c
         lut[:, 3] = 2.0 * (2.0 * t)
         aidx = (None if inv is None
-                else inv.to(torch.uint8).reshape(self.ny, self.nx).contiguous())
+                else padc(inv.to(torch.uint8).reshape(self.ny, self.nx)))
         rough = full(self.rough_grid, a.rough.val)
         coef = inv_rough = S32 = None
         if self.kinematic:
-            coef = (self.own(self.sqrtS) / rough).contiguous()
+            coef = padc(self.own(self.sqrtS) / rough)
         else:
             S = self.own(self.S_bed)
-            S32 = S.float().contiguous()
+            S32 = S.float()
             if not bool((S32.double() == S).all()):
                 return
-            inv_rough = (1.0 / rough).contiguous()
-        geo32 = torch.empty((self.ny, self.nx), dtype=torch.int32, device=dev)
+            S32 = padc(S32)
+            inv_rough = padc(1.0 / rough)
+        geo32 = torch.empty((self.ny, self.pitch), dtype=torch.int32, device=dev)
         L.check(self.lib.tfb_channels_pack_geo32(self._p(self.code),
                                                  None if aidx is None else aidx.data_ptr(), self.ny,
-                                                 self.nx, self.halo, geo32.data_ptr(),
+                                                 self.pitch, self.halo, geo32.data_ptr(),
                                                  L.stream_ptr()), 'tfb_channels_pack_geo32')
         rowg = torch.empty((self.ny, 8), dtype=torch.float64, device=dev)
         L.check(self.lib.tfb_channels_pack_rows(self._prow(self.dx), self._prow(self.dy),
@@ -279,7 +304,7 @@ class ChannelsEngine(object):
         if 0 <= orow < self.ny and 0 <= a.outlet_col < self.nx:
             n_out = float(rough[orow, a.outlet_col])
         pk = L.ChannelsPacked()
-        w32 = w32.contiguous()
+        w32 = padc(w32)
         pk.geo32, pk.width32 = geo32.data_ptr(), w32.data_ptr()
         pk.coef = None if coef is None else coef.data_ptr()
         pk.inv_rough = None if inv_rough is None else inv_rough.data_ptr()
@@ -289,7 +314,9 @@ class ChannelsEngine(object):
         nf = None
         if not self.kinematic:
             # noflow cells of the owned rows, as flat indices relative to the first owned row
-            nf = torch.nonzero(self.own(self.code).reshape(-1) == 0).reshape(-1).contiguous()
+            # (whole pitched rows: the padding columns hold code 0 and depth 0 anyway)
+            nf = torch.nonzero(self.code[self.halo:self.halo + self.ny].reshape(-1) == 0) \
+                .reshape(-1).contiguous()
             pk.noflow_idx, pk.n_noflow = nf.data_ptr(), int(nf.numel())
         self._pack_keep = (geo32, w32, coef, inv_rough, S32, lut, rowg, nf)
         self.packed = pk
@@ -324,25 +351,26 @@ class ChannelsEngine(object):
 
     # ------------------------------------------------------------ allocation
     def _zeros(self, dtype):
-        return torch.zeros((self.ny + 2 * self.halo, self.nx), dtype=dtype, device=self.device)
+        return torch.zeros((self.ny + 2 * self.halo, self.pitch), dtype=dtype, device=self.device)
 
     def own(self, t):
-        """(ny, nx) view of the rows this slab owns."""
-        return t[self.halo:self.halo + self.ny]
+        """(ny, nx) view of the rows this slab owns (without the row padding)."""
+        t = t[self.halo:self.halo + self.ny]
+        return t if t.shape[1] == self.nx else t[:, :self.nx]
 
     def _p(self, t):
-        return t.data_ptr() + self.halo * self.nx * t.element_size()
+        return t.data_ptr() + self.halo * t.stride(0) * t.element_size()
 
     def _prow(self, t):
         return t.data_ptr() + self.halo * t.element_size()
 
     def _grid(self, x, dtype):
-        """Upload an (ny, nx) or (ny+2h, nx) array into a haloed tensor."""
+        """Upload an (ny, nx) or (ny+2h, nx) array into a haloed (pitched) tensor."""
         full = self._zeros(dtype)
         src = torch.as_tensor(x) if not isinstance(x, torch.Tensor) else x
         src = src.to(dtype=dtype, device=self.device)
-        if src.shape[0] == self.ny + 2 * self.halo:
-            full.copy_(src)
+        if src.shape[0] == self.ny + 2 * self.halo and self.halo:
+            full[:, :src.shape[1]].copy_(src)
         else:
             if tuple(src.shape) != (self.ny, self.nx):
                 raise L.TfbError('grid shape %s != (%d, %d)' % (tuple(src.shape), self.ny, self.nx))
@@ -380,7 +408,7 @@ class ChannelsEngine(object):
             raise KeyError(name)
         if _is_grid(val):
             if (isinstance(val, torch.Tensor) and val.is_cuda and val.dtype == torch.float64
-                    and val.is_contiguous() and self.halo == 0
+                    and val.is_contiguous() and self.halo == 0 and self.pitch == self.nx
                     and tuple(val.shape) == (self.ny, self.nx)):
                 t = val
                 sgv = L.SG(t.data_ptr(), 0.0)
@@ -391,7 +419,7 @@ class ChannelsEngine(object):
                     t = self._zeros(torch.float64)
                 src = torch.as_tensor(val) if not isinstance(val, torch.Tensor) else val
                 src = src.to(dtype=torch.float64, device=self.device)
-                (t if src.shape[0] == t.shape[0] else self.own(t)).copy_(src)
+                (t[:, :self.nx] if (src.shape[0] == t.shape[0] and self.halo) else self.own(t)).copy_(src)
                 sgv = L.SG(self._p(t), 0.0)
             self.src[name] = t
         else:
@@ -468,13 +496,7 @@ class ChannelsEngine(object):
         if float(d.abs().max()) == 0.0:
             vol.zero_()
             return
-        ds32 = torch.empty((self.ny + 2 * self.halo, self.nx), dtype=torch.float32,
-                           device=self.device)
-        L.check(self.lib.tfb_d8_ds_dw(self.code.data_ptr(), self.dx.data_ptr(),
-                                      self.dy.data_ptr(), self.dd.data_ptr(),
-                                      self.ny + 2 * self.halo, self.nx,
-                                      ds32.data_ptr(), None, L.stream_ptr()), 'tfb_d8_ds_dw')
-        ds = g('sinu') * self.own(ds32).double()
+        ds = g('sinu') * self.own(self._ds32()).double()
         L2 = d * g('tan_angle')
         A_wet = d * (g('width') + L2)
         vol.copy_(A_wet * ds)

@@ -45,6 +45,7 @@ class SlabLayout(object):
         self.row0, self.ny = self.parts[rank]
         if self.world_size > 1 and min(n for _, n in self.parts) < max(1, halo):
             raise ValueError('slabs thinner than the halo: %r' % (self.parts,))
+        self.pitch = (self.nx + 3) // 4 * 4          # row pitch of the device arrays (routing.row_pitch)
         self.up = rank - 1 if rank > 0 else None
         self.down = rank + 1 if rank < world_size - 1 else None
 
@@ -123,7 +124,7 @@ class PeerHalos(object):
         self.ok = True
         lay = layout
         rows = lay.ny + 2 * lay.halo
-        nbytes = rows * lay.nx * 8
+        nbytes = rows * lay.pitch * 8
         self._mine, handles = [], []
         try:
             sizes = [nbytes, nbytes, 256] + ([nbytes] if self.with_depth else [])
@@ -133,9 +134,9 @@ class PeerHalos(object):
                 L.check(self.lib.tfb_peer_alloc(nb, C.byref(p), h), 'tfb_peer_alloc')
                 self._mine.append(p.value)
                 handles.append(h.raw)
-            self.q_buffers = [torch.as_tensor(_DevArray(self._mine[k], (rows, lay.nx), '<f8'),
+            self.q_buffers = [torch.as_tensor(_DevArray(self._mine[k], (rows, lay.pitch), '<f8'),
                                               device=device) for k in range(2)]
-            self.d_buffer = (torch.as_tensor(_DevArray(self._mine[3], (rows, lay.nx), '<f8'),
+            self.d_buffer = (torch.as_tensor(_DevArray(self._mine[3], (rows, lay.pitch), '<f8'),
                                              device=device) if self.with_depth else None)
         except Exception:
             if not _collective_guard:
@@ -170,7 +171,7 @@ class PeerHalos(object):
         `q_out` (or of the depth grid) and the flag words; `step` = step index for the
         kinematic kernel, phase counter (2n, 2n+1) for the two diffusive passes."""
         lay = self.layout
-        row = lay.nx * 8
+        row = lay.pitch * 8
         ph = L.PeerHalo()
         if 'up' in self.nbr:
             n = self.nbr['up']
@@ -188,10 +189,16 @@ class PeerHalos(object):
         return ph
 
     def close(self):
+        """Unmap the neighbours' buffers and free this rank's own peer allocations (the
+        tensors wrapped around them must not be used afterwards)."""
         for ptrs in self._open.values():
             for p in ptrs:
                 self.lib.tfb_peer_close(p)
         self._open = {}
+        self.q_buffers, self.d_buffer = None, None
+        for p in self._mine:
+            self.lib.tfb_peer_free(p)
+        self._mine = []
 
 
 def make_peer_halos(layout, device, group=None, with_depth=False):
