@@ -9,23 +9,37 @@ One "step" = one `update()` of the channel-routing component over the whole grid
 fractal DEM, 4096 x 4096 cells per GPU, kinematic wave + Manning, fused
 Green-Ampt infiltration, uniform 50 mm/h rain, fp64, dt = 1 s.  With N > 1 the
 grid is (N*4096) x 4096, one 4096-row slab per GPU (weak scaling), boundary
-discharge rows exchanged over NCCL every step.
+discharge rows exchanged by NVLink peer stores inside the kernel.
 
-Prints ONE JSON line (rank 0).  `value` is timed with the state resident in
-HBM; `e2e` drives the BMI component (`channels_kinematic_wave.channels_component`
-read from CFG/RTG files it wrote itself) with host inputs through `set_value()`
-and a device->host read of the scalar block (Q_outlet, ...) every update.
-`--impl reference` times the CPU restatement of the reference's numpy path
-(oracle/tf_oracle.c, all host threads) -- the reference itself is pure Python
-and absent on the GPU box.
+Prints ONE JSON line (rank 0):
+  value     timed with the state resident in HBM (CUDA events, max over ranks; at N > 1 the
+            ranks rendez-vous ON THE DEVICE right before the first timed launch)
+  e2e       the BMI component (`channels_kinematic_wave.channels_component`, initialised
+            from CFG/RTG files, slab mode under torch.distributed at N > 1) with host
+            inputs through `set_value()` and a read of Q_outlet every update,
+            CHECK_STABILITY at its default (on); `e2e_grid_inputs` the same with the
+            infiltration and evaporation rates arriving as fresh host GRIDS every step
+            (what a coupled EMELI run delivers)
+  roofline  algorithmic bytes per launch / measured launch time against the measured HBM
+            copy peak (`frac`), and the same with the DRAM bytes ncu counted (`frac_dram`)
+  sanity    parity INSIDE the bench: N = 1: the first 60 steps of this very engine against
+            the C restatement of the reference at the bench size (`parity_rel_err` per
+            grid, line fails above 1e-9); N > 1: an (N*256)-row case stepped 30 steps as N
+            slabs and whole on one GPU, compared bit for bit (`slab_equals_single`)
+  config3 / config4   BASELINE configs[3] (32768^2 diffusive wave + all fused sources, row
+            slabs, N >= 2) and configs[4] (8192 x 65536 per GPU, kinematic wave, the
+            65536^2 continental case at N = 8), a few steps each, so the scaling records
+            hold them
+`--impl reference` times the UNMODIFIED reference (staged by `make -C oracle _ref`): its
+channels_component.update() fed by its Green-Ampt methods, numpy on one core, on a bounded
+sample of the same workload; the C restatement on all host threads is reported beside it.
 """
 import argparse
 import json
 import os
-import subprocess
+import shutil
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -37,87 +51,130 @@ NY_PER_GPU = 4096
 NX = 4096
 BYTES_PER_CELL = {'kw': 81, 'kw_ga': 97, 'dw': 106, 'dw_full': 146}
 METRIC = 'routing Gcell-updates/sec'
-WORKLOAD = ('synthetic fractal DEM %dx%d per GPU, kinematic wave + Manning, fused Green-Ampt '
-            'infiltration (pre-wetted soil, I0=0.1 m), uniform 50 mm/h rain, fp64, dt=1s'
-            % (NY_PER_GPU, NX))
+PARITY_TOL = 1e-9          # north-star tolerance on Q / depth / velocity (BASELINE.json)
+
+
+def workload_text(ny, nx, workload, device_gen=False):
+    kin = workload.startswith('kw')
+    src = {'kw_ga': 'fused Green-Ampt infiltration (pre-wetted soil, I0=0.1 m), ', 'kw': '', 'dw': '',
+           'dw_full': 'fused rain/snow split + degree-day melt + Priestley-Taylor ET + Green-Ampt '
+                      '(T_air grid), '}[workload]
+    return ('synthetic %s DEM %dx%d per GPU, %s wave + Manning, %suniform 50 mm/h rain, fp64, dt=1s'
+            % ('closed-form (device-generated)' if device_gen else 'fractal', ny, nx,
+               'kinematic' if kin else 'diffusive', src))
+
+
+def make_config(ny, nx, world, workload, device_gen, use_p2p):
+    """`config` of the JSON line -- the SAME dict for the GPU arm and the reference arm."""
+    bpc = BYTES_PER_CELL[workload]
+    return {'workload': workload_text(ny, nx, workload, device_gen), 'grid': [ny * world, nx],
+            'rows_per_gpu': ny,
+            'partition': ('single GPU' if world == 1 else
+                          'row slabs, 1 halo row of Q per neighbour per step, %s'
+                          % ('NVLink peer stores fused into the routing kernel(s), flag words polled '
+                             'by the boundary tiles (no NCCL call per step)' if use_p2p
+                             else 'NCCL send/recv after the kernel')),
+            'l2': 'working set %.2f GB per step per GPU >> 126 MB L2, no flush needed'
+                  % (ny * nx * bpc / 1e9)}
 
 
 # ------------------------------------------------------------------ clocks
 class ClockSampler(object):
-    """nvidia-smi samples of SM clock and throttle reasons DURING a timed region."""
-    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-         'clocks_event_reasons.sw_power_cap')
-    NAMES = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+    """SM clock and throttle reasons read through NVML IN-PROCESS while the timed launches
+    execute: the host enqueues the K steps ahead of the device and then polls NVML until
+    the closing event has fired, so even a 20-step region (a few milliseconds) is sampled
+    from the inside.  Further samples are taken the same way in the e2e legs."""
+    BITS = (('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40), ('sw_thermal_slowdown', 0x20),
+            ('sw_power_cap', 0x4))
 
-    def __init__(self, index=0, period_ms=50):
-        self.index, self.period_ms = index, period_ms
-        self.rows, self.proc, self.th = [], None, None
-
-    def start(self):
+    def __init__(self, device):
+        self.rows, self.region = [], []
+        self.h = self.nv = None
         try:
-            self.proc = subprocess.Popen(
-                ['nvidia-smi', '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
-                 '-i', str(self.index), '-lms', str(self.period_ms)],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            self.proc = None
-            return
-        self.th = threading.Thread(target=self._read, daemon=True)
-        self.th.start()
-
-    def _read(self):
-        for line in self.proc.stdout:
-            p = [x.strip() for x in line.split(',')]
-            if len(p) >= 7:
-                self.rows.append(p)
-
-    def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(self.period_ms / 1000.0)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        self.th.join(timeout=2)
-        sm, mx, pw, reasons = [], [], [], set()
-        for p in self.rows:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self.nv = pynvml
             try:
-                sm.append(float(p[0])); mx.append(float(p[1])); pw.append(float(p[2]))
-            except ValueError:
-                continue
-            for name, v in zip(self.NAMES, p[3:7]):
-                if v.lower().startswith('active'):
-                    reasons.add(name)
-        if not sm:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
-        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)),
-                'power_w_max': float(max(pw)), 'samples': len(sm), 'reasons': sorted(reasons)}
+                uuid = 'GPU-' + str(torch.cuda.get_device_properties(device).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(device.index or 0)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as exc:            # no NVML: reported, not fatal
+            self.err = repr(exc)
+            self.h = None
+
+    def sample(self, in_region=False):
+        if self.h is None:
+            return
+        nv = self.nv
+        try:
+            mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            why = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+        except Exception:
+            return
+        (self.region if in_region else self.rows).append((mhz, why, pw))
+
+    def poll_until(self, event, in_region=False, pause=0.0005):
+        """Sample while `event` (recorded after the last launch) has not fired."""
+        self.sample(in_region)
+        while not event.query():
+            self.sample(in_region)
+            time.sleep(pause)
+
+    def report(self):
+        if self.h is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None,
+                    'reasons': ['NVML unavailable: %s' % getattr(self, 'err', '')]}
+        rows = self.region + self.rows
+        if not rows:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': ['no samples']}
+        why = 0
+        for _, w, _ in rows:
+            why |= w
+        core = self.region or rows
+        return {'sm_mhz': float(np.median([r[0] for r in core])),
+                'sm_min_mhz': float(min(r[0] for r in rows)), 'sm_max_mhz': self.max_mhz,
+                'power_w_max': float(max(r[2] for r in rows)),
+                'samples_in_value_region': len(self.region), 'samples': len(rows),
+                'how': 'NVML polled in-process while the timed launches execute (median over the '
+                       'value region), plus the e2e legs',
+                'reasons': [n for n, b in self.BITS if why & b]}
 
 
-# ------------------------------------------------------------- CPU baseline
-def cpu_port_rate(budget_s, n_steps=None, warmup=1, threads=None):
-    """Time the C restatement of the reference path (oracle/tf_oracle.c) on the
-    host cores over a bounded sample of the workload: the first `ny_s` rows of the
-    same synthetic generator (own D8 on the CPU), KW + fused Green-Ampt.  Returns
-    (Gcell/s, description, cores, ms_per_step, steps)."""
+# ------------------------------------------------------------- CPU baselines
+def _sample_case(ny_s, nx, seed=1234):
+    """The first `ny_s` rows of the bench's synthetic generator, prepared on the CPU."""
     from oracle import c_oracle, np_oracle as o
     from topoflow36_b200 import cases
+    tile = cases.noise_tile(ny_s, nx, seed=seed)
+    DEM = cases.slab_dem(ny_s, nx, 0, ny_s, 0, tile)
+    dx, dy, dd = o.pixel_dims(ny_s, 30.0, 30.0)
+    code, _ = c_oracle.d8_flow_grid(DEM, dx, dy, dd)
+    ds32, _ = o.d8_ds_dw(code, dx, dy, dd)
+    with np.errstate(all='ignore'):
+        slope = np.float32(o.d8_slope(DEM, code, ds32))
+    width, angle, nval = cases.slab_params(ny_s, nx, 0, 0, seed=seed)
+    return dict(DEM=DEM, code=code, slope=slope, width=width, angle=angle, nval=nval,
+                dx=dx, dy=dy, dd=dd)
+
+
+def cpu_port_rate(budget_s, n_steps=None, warmup=1, threads=None, nx=None, ny_max=None):
+    """oracle/tf_oracle.c (the C restatement of the reference path, pthreads) on the host
+    cores over a bounded sample: the first `ny_s` rows of the same synthetic generator, KW +
+    fused Green-Ampt.  Returns (Gcell/s, description, cores, ms_per_step, steps)."""
+    from oracle import c_oracle
+    from topoflow36_b200 import cases
+    nx = nx or NX
+    ny_max = ny_max or NY_PER_GPU
     threads = threads or (os.cpu_count() or 1)
 
     def build(ny_s):
-        tile = cases.noise_tile(ny_s, NX, seed=1234)
-        DEM = cases.slab_dem(ny_s, NX, 0, ny_s, 0, tile)
-        dx, dy, dd = o.pixel_dims(ny_s, 30.0, 30.0)
-        code, _ = c_oracle.d8_flow_grid(DEM, dx, dy, dd)
-        ds32, _ = o.d8_ds_dw(code, dx, dy, dd)
-        with np.errstate(all='ignore'):
-            slope = o.d8_slope(DEM, code, ds32)
-        width, angle, nval = cases.slab_params(ny_s, NX, 0, 0, seed=1234)
-        ch = c_oracle.Channels(code, dx, dy, dd, slope, width, angle, nval, dt=1.0,
-                               outlet=(ny_s - 2, NX // 2), diag=False)
+        p = _sample_case(ny_s, nx)
+        ch = c_oracle.Channels(p['code'], p['dx'], p['dy'], p['dd'], p['slope'], p['width'],
+                               p['angle'], p['nval'], dt=1.0, outlet=(ny_s - 2, nx // 2), diag=False)
         ch.nthreads = threads
         ch.set_input('P_rain', cases.RAIN_50MMPH)
         ch.enable_fused(infil=True, I0=cases.I0_WET)
@@ -125,17 +182,15 @@ def cpu_port_rate(budget_s, n_steps=None, warmup=1, threads=None):
             ch.set_input(k, v)
         return ch
 
-    # calibrate on a thin strip, then size the sample to the budget
-    ch = build(128)
+    cal = min(128, ny_max)
+    ch = build(cal)                                          # calibrate on a thin strip
     ch.step()
     t0 = time.perf_counter()
     for _ in range(3):
         ch.step()
-    rate = 3 * 128 * NX / (time.perf_counter() - t0)        # cells/s
-    if n_steps is None:
-        n_steps = 10
-    cells_per_step = rate * budget_s / float(n_steps + warmup)
-    ny_s = int(min(NY_PER_GPU, max(64, cells_per_step // NX)))
+    rate = 3 * cal * nx / (time.perf_counter() - t0)        # cells/s
+    n_steps = n_steps or 10
+    ny_s = int(min(ny_max, max(64, rate * budget_s / float(n_steps + warmup) // nx)))
     ch = build(ny_s)
     for _ in range(warmup):
         ch.step()
@@ -143,83 +198,302 @@ def cpu_port_rate(budget_s, n_steps=None, warmup=1, threads=None):
     for _ in range(n_steps):
         ch.step()
     dt = time.perf_counter() - t0
-    val = n_steps * ny_s * NX / dt / 1e9
     desc = ('first %d of %d rows x %d cols of the same synthetic case (own D8), %d steps, '
-            'C restatement of the numpy path, %d pthreads' % (ny_s, NY_PER_GPU, NX, n_steps, threads))
-    return val, desc, threads, dt / n_steps * 1e3, n_steps
+            'C restatement of the numpy path, %d pthreads' % (ny_s, ny_max, nx, n_steps, threads))
+    return n_steps * ny_s * nx / dt / 1e9, desc, threads, dt / n_steps * 1e3, n_steps
 
 
-def cpu_numpy_rate(n=1024, n_steps=6):
-    """The reference's OWN CPU path is whole-grid numpy (one core).  It cannot travel to
-    the GPU box, so its numpy restatement (oracle/np_oracle.py, the same expressions in
-    the same order, bit-exact against it) is timed instead on an n x n sub-case: KW +
-    Green-Ampt, like the benchmark.  Returns (Gcell/s, description)."""
-    from oracle import c_oracle, np_oracle as o
-    from topoflow36_b200 import cases
-    tile = cases.noise_tile(n, n, seed=1234)
-    DEM = cases.slab_dem(n, n, 0, n, 0, tile)
-    dx, dy, dd = o.pixel_dims(n, 30.0, 30.0)
-    code, _ = c_oracle.d8_flow_grid(DEM, dx, dy, dd)
-    ds32, dw32 = o.d8_ds_dw(code, dx, dy, dd)
-    with np.errstate(all='ignore'):
-        slope = o.d8_slope(DEM, code, ds32)
-    width, angle, nval = cases.slab_params(n, n, 0, 0, seed=1234)
-    ch = o.Channels(code, ds32, dw32, slope, width, angle, nval=nval, dt=1.0,
-                    outlet=(n - 2, n // 2), check_stability=True)
-    ch.P_rain = np.array(cases.RAIN_50MMPH)
-    I = np.zeros((n, n)) + cases.I0_WET
+def _reference_stepper(ny_s, nx, work):
+    """The UNMODIFIED reference on the bench workload: channels_kinematic_wave's
+    channels_component (components/channels_base.py:803-962) initialised from CFG/RTG files,
+    its infiltration rate from the reference's own Green-Ampt methods
+    (infil_green_ampt.py:511-578, infil_base.py:654-811) on a bare infil_component."""
+    from oracle import ref_harness as rh
+    from topoflow36_b200 import cases, synth
+    rh.import_reference()
+    from topoflow.components import channels_kinematic_wave as ckw, infil_green_ampt
+    p = _sample_case(ny_s, nx)
+    cfg = synth.write_case(work, p['DEM'], p['slope'], p['width'], p['angle'], nval=p['nval'],
+                           dt=1.0, kinematic=True, manning=True, n_steps=10 ** 9)
+    c = ckw.channels_component()
+    rh.quiet_call(c.initialize, cfg_file=cfg, mode='driver', SILENT=True)   # CHECK_STABILITY default
+    z = lambda v: np.array(v, dtype='float64')
+    g = infil_green_ampt.infil_component()
+    g.DEBUG, g.RICHARDS = False, False
+    g.dt, g.P_rain, g.SM = z(1.0), z(cases.RAIN_50MMPH), z(0.0)
+    for k, v in cases.GA_TREYNOR.items():
+        setattr(g, k, [z(v)])
+    g.I = np.zeros((ny_s, nx)) + cases.I0_WET
+    g.h_table, g.elev = np.zeros((ny_s, nx)), np.ones((ny_s, nx))
+    LONG = {nm: ln for ln, nm in c._var_name_map.items()}
+    for k, v in dict(MR=0.0, GW=0.0, SM=0.0, ET=0.0, rho_H2O=1000.0, P_rain=cases.RAIN_50MMPH).items():
+        c.set_value(LONG[k], z(v))
+    c.n_steps = 10 ** 9
 
     def step():
-        nonlocal I
-        ch.IN, I = o.green_ampt_step(I, ch.P_rain, 0.0, dt=1.0, **cases.GA_TREYNOR)
-        ch.step()
-    with np.errstate(all='ignore'):
-        step()
-        t0 = time.perf_counter()
-        for _ in range(n_steps):
+        g.update_surface_influx(); g.update_infil_rate(); g.adjust_infil_rate(); g.update_I()
+        c.set_value(LONG['IN'], g.IN)
+        c.update()
+    return lambda: rh.quiet_call(step)
+
+
+def cpu_reference_rate(budget_s, n_steps, warmup, nx=None, ny_max=None):
+    """Time the unmodified reference (numpy, one core) on a bounded sample sized so that
+    `warmup + n_steps` updates take about `budget_s`.  Returns None when the reference is
+    not staged (oracle/_ref)."""
+    from oracle import ref_harness as rh
+    if not rh.reference_available():
+        return None
+    nx = nx or NX
+    ny_max = ny_max or NY_PER_GPU
+    work = tempfile.mkdtemp(prefix='tfb_ref_')
+    try:
+        with np.errstate(all='ignore'):
+            # calibrate out of cache (512 rows: ~100 MB of temporaries per numpy pass)
+            cal = min(512, ny_max)
+            step = _reference_stepper(cal, nx, os.path.join(work, 'cal'))
             step()
-        dt = time.perf_counter() - t0
-    return n_steps * n * n / dt / 1e9, ('%d x %d sub-case, %d steps, numpy restatement of the '
-                                        'reference path (np_oracle), 1 core' % (n, n, n_steps))
+            t0 = time.perf_counter()
+            step(); step()
+            rate = 2 * cal * nx / (time.perf_counter() - t0)
+            ny_s = int(min(ny_max, max(min(128, ny_max), rate * budget_s / float(n_steps + warmup) // nx)))
+            step = _reference_stepper(ny_s, nx, os.path.join(work, 'run'))
+            for _ in range(warmup):
+                step()
+            t0 = time.perf_counter()
+            for _ in range(n_steps):
+                step()
+            dt = time.perf_counter() - t0
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+    desc = ('first %d of %d rows x %d cols of the same synthetic case, %d steps after %d warm-up: the '
+            'UNMODIFIED reference (oracle/_ref) -- channels_kinematic_wave.channels_component.update() '
+            'fed by infil_green_ampt methods, CHECK_STABILITY default, outputs off; numpy is '
+            'single-threaded: 1 of %d cores busy' % (ny_s, ny_max, nx, n_steps, warmup,
+                                                     os.cpu_count() or 1))
+    return {'value': n_steps * ny_s * nx / dt / 1e9, 'unit': 'Gcell-updates/s', 'cores': 1,
+            'kind': 'reference', 'sample': desc, 'ms_per_step': dt / n_steps * 1e3, 'steps': n_steps}
+
+
+def cpu_baseline_block(ref_budget, port_budget, n_steps, warmup):
+    """cpu_baseline of the JSON line: the reference itself when staged (kind "reference"),
+    with the C port on all host threads beside it; the port alone otherwise."""
+    v, desc, cores, ms, _ = cpu_port_rate(port_budget)
+    port = {'value': v, 'unit': 'Gcell-updates/s', 'cores': cores, 'kind': 'port', 'sample': desc}
+    ref = cpu_reference_rate(ref_budget, n_steps, warmup)
+    if ref is None:
+        port['note'] = 'oracle/_ref not staged: reference itself not timed'
+        return port
+    ref['port_all_threads'] = port
+    return ref
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    # keep the whole run within ~2 minutes whatever K the driver asks for
-    val, desc, cores, ms, steps = cpu_port_rate(100.0, n_steps=args.steps, warmup=args.warmup)
+    cfg = make_config(args.rows_per_gpu, args.nx, args.gpus, args.workload, args.device_gen,
+                      args.gpus > 1 and args.halo != 'nccl')
+    # the whole run stays within ~2 minutes whatever K the driver asks for
+    ref = cpu_reference_rate(75.0, args.steps, args.warmup, nx=args.nx, ny_max=args.rows_per_gpu)
+    if ref is None:
+        v, desc, cores, ms, steps = cpu_port_rate(90.0, n_steps=args.steps, warmup=args.warmup,
+                                                  nx=args.nx, ny_max=args.rows_per_gpu)
+        ref = {'value': v, 'unit': 'Gcell-updates/s', 'cores': cores, 'kind': 'port', 'sample': desc,
+               'ms_per_step': ms, 'steps': steps}
+        note = 'oracle/_ref not staged on this box: timed oracle/tf_oracle.c (C port, all host threads)'
+    else:
+        v, desc, cores, _, _ = cpu_port_rate(15.0, nx=args.nx, ny_max=args.rows_per_gpu)
+        ref['port_all_threads'] = {'value': v, 'unit': 'Gcell-updates/s', 'cores': cores,
+                                   'kind': 'port', 'sample': desc}
+        note = ('the unmodified reference through its own public API and stock code path (pure '
+                'Python/numpy, one process); the C restatement on all host threads is in '
+                'cpu_baseline.port_all_threads')
     out = {
-        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'Gcell-updates/s',
-        'n_gpus': args.gpus, 'steps': steps, 'warmup': args.warmup, 'ms_per_step': ms,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-        'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'sample': desc},
-        'cpu_baseline': {'value': val, 'unit': 'Gcell-updates/s', 'cores': cores, 'kind': 'port',
-                         'sample': desc},
-        'e2e': {'value': val, 'unit': 'Gcell-updates/s', 'h2d_bytes_per_step': 0,
+        'impl': 'reference', 'metric': METRIC, 'value': ref['value'], 'unit': 'Gcell-updates/s',
+        'n_gpus': args.gpus, 'steps': ref['steps'], 'warmup': args.warmup,
+        'ms_per_step': ref['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': cfg,
+        'cpu_baseline': ref,
+        'e2e': {'value': ref['value'], 'unit': 'Gcell-updates/s', 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
-        'gpu_launches': 0,
-        'note': ('the reference is pure Python/numpy (5-8 Mcell-updates/s on one core, SURVEY.md '
-                 'section 6) and cannot travel to the GPU box; this arm times oracle/tf_oracle.c, '
-                 'the same arithmetic in C on all host threads -- a far stronger CPU baseline'),
+        'gpu_launches': 0, 'note': note,
     }
     print(json.dumps(out))
 
 
+# ------------------------------------------------------------- parity legs
+def parity_vs_c_oracle(eng, parts, nx, n_steps=60):
+    """N = 1: step the freshly built bench engine `n_steps` and the C restatement of the
+    reference path on the same inputs; per-grid max-norm relative error."""
+    from oracle import c_oracle, np_oracle as o
+    from topoflow36_b200 import cases
+    from topoflow36_b200.d8 import D8Toolkit
+    import torch
+    ny = eng.ny
+    code = eng.own(eng.code).cpu().numpy()
+    S32 = parts['d8'].get('slope32')
+    if S32 is None:
+        tk = D8Toolkit(parts['DEM'], device=eng.device)
+        tk.update_flow_grid()
+        S32 = tk.slope().cpu().numpy()
+        del tk
+        parts['slope32'] = S32
+    dx, dy, dd = o.pixel_dims(ny, 30.0, 30.0)
+    ch = c_oracle.Channels(code, dx, dy, dd, S32, parts['width'], parts['angle'], parts['nval'],
+                           dt=1.0, kinematic=eng.kinematic, outlet=(ny - 2, nx // 2), diag=False)
+    ch.nthreads = os.cpu_count() or 1
+    ch.set_input('P_rain', cases.RAIN_50MMPH)
+    if eng.I_buf is not None:
+        ch.enable_fused(infil=True, I0=cases.I0_WET)
+        for k, v in cases.GA_TREYNOR.items():
+            ch.set_input(k, v)
+    t0 = time.perf_counter()
+    for i in range(n_steps):
+        eng.step(i / 60.0)
+        ch.time_min = i / 60.0
+        ch.step()
+    torch.cuda.synchronize()
+    err = {}
+    for n in ('vol', 'd', 'u', 'Q') + (('I',) if eng.I_buf is not None else ()):
+        got = (eng.Q if n == 'Q' else getattr(eng, n) if n in ('vol', 'I')
+               else eng.own(getattr(eng, n))).cpu().numpy()
+        want = getattr(ch, n)
+        scale = np.abs(want).max()
+        err[n] = float(np.abs(got - want).max() / scale) if scale > 0 else float(np.abs(got).max())
+    s = eng.read_scalars()
+    for n in ('vol_R', 'vol_edge', 'vol_IN'):
+        want = float(getattr(ch, n))
+        err[n] = abs(getattr(s, n) - want) / max(abs(want), 1e-300)
+    return {'parity_rel_err': err, 'parity_steps': n_steps, 'parity_ok': max(err.values()) <= PARITY_TOL,
+            'parity_against': 'oracle/tf_oracle.c (pinned to the reference by tests/test_c_oracle.py) on '
+                              'the bench grid, same inputs, from the initial state',
+            'parity_path': eng.last_path, 'parity_wall_s': round(time.perf_counter() - t0, 1)}
+
+
+def slab_equals_single(world, rank, dev, nx, kin, sources, use_p2p, n_steps=30, rows=256):
+    """N > 1: an (N*rows) x nx case stepped as N slabs (the bench's halo transport) and whole
+    on this rank's own GPU; every rank compares ITS rows bit for bit."""
+    import torch
+    import torch.distributed as dist
+    from topoflow36_b200 import cases
+    slab, parts = cases.build_engine(rows, nx, kinematic=kin, sources=sources, rank=rank, world=world,
+                                     device=dev, return_parts=True, p2p=use_p2p)
+    one = cases.build_engine(rows * world, nx, kinematic=kin, sources=sources, device=dev,
+                             tile_rows=rows)
+    lay = parts['layout']
+    sl = slice(lay.row0, lay.row0 + lay.ny)
+    e = slab.engine
+    bad = int((e.own(e.code) != one.own(one.code)[sl]).sum())
+    for i in range(n_steps):
+        slab.step(i / 60.0)
+        one.step(i / 60.0)
+    for a, b in ((e.vol, one.vol), (e.own(e.d), one.own(one.d)), (e.own(e.u), one.own(one.u)),
+                 (e.Q, one.Q)):
+        bad += int((a != b[sl]).sum())
+    moved = float(one.Q.abs().max()) > 0
+    t = torch.tensor([bad, 0 if moved else 1], dtype=torch.int64, device=dev)
+    dist.all_reduce(t)
+    sg, s1 = slab.read_scalars(), one.read_scalars()
+    rel = max(abs(getattr(sg, n) - getattr(s1, n)) / max(abs(getattr(s1, n)), 1e-300)
+              for n in ('vol_R', 'vol_edge'))
+    if slab.peer is not None:
+        torch.cuda.synchronize()
+        dist.barrier()
+        slab.peer.close()
+    return {'slab_equals_single': int(t[0]) == 0 and int(t[1]) == 0, 'slab_cells_differing': int(t[0]),
+            'slab_case': '%d x %d as %d slabs of %d rows vs one GPU, %d steps, %s halo, grids vol/d/u/Q '
+                         'and D8 codes bit for bit' % (rows * world, nx, world, rows, n_steps,
+                                                       'peer-memory' if slab.peer is not None else 'NCCL'),
+            'slab_integrals_rel_err': rel, 'slab_path': e.last_path}
+
+
+# -------------------------------------------------------------- timing helper
+def timed_steps(stepper, steps, warmup, world, dev, tmin0=0.0, sampler=None):
+    """W warm-up steps, then K timed steps between CUDA events; at N > 1 a tiny all-reduce
+    on the compute stream right before the first event is the device-side rendez-vous.
+    Returns (max ms per step over ranks, per-rank list, host (t0, t1) of the region)."""
+    import torch
+    import torch.distributed as dist
+    tmin = tmin0
+    for _ in range(warmup):
+        stepper.step(tmin); tmin += 1.0 / 60.0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if world > 1:
+        sync = torch.zeros(1, device=dev)
+        dist.all_reduce(sync)                    # completes on all ranks at (nearly) the same time
+    h0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        stepper.step(tmin); tmin += 1.0 / 60.0
+    e1.record()
+    if sampler is not None:
+        sampler.poll_until(e1, in_region=True)
+    torch.cuda.synchronize()
+    h1 = time.perf_counter()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    by_rank = [float(ms.item()) / steps]
+    if world > 1:
+        every = torch.zeros(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(every, ms)
+        by_rank = [float(v) / steps for v in every.tolist()]
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item()) / steps, by_rank, (h0, h1), tmin
+
+
+def mass_sanity(stepper, eng, world):
+    import torch
+    import torch.distributed as dist
+    sc = stepper.read_scalars()
+    stored = eng.vol.sum().reshape(1)
+    qmax = eng.Q.max().reshape(1)
+    if world > 1:
+        dist.all_reduce(stored)
+        dist.all_reduce(qmax, op=dist.ReduceOp.MAX)
+    return sc, {'Q_outlet': sc.Q_outlet, 'Q_max': float(qmax), 'vol_R': sc.vol_R, 'vol_IN': sc.vol_IN,
+                'mass_balance_rel_err': abs(sc.vol_R - (float(stored) + sc.vol_edge)) / max(sc.vol_R, 1e-300),
+                'bad_values': int(sc.n_neg_d + sc.n_inf_d + sc.n_neg_u + sc.n_nan_u + sc.n_inf_u)}
+
+
+def extra_config(tag, ny, nx, workload, world, rank, dev, halo, steps=10, warmup=3):
+    """One of the larger BASELINE configs as a block of the JSON line (device-generated)."""
+    import torch
+    from topoflow36_b200 import cases
+    kin = workload.startswith('kw')
+    sources = {'kw_ga': 'ga', 'kw': 'none', 'dw': 'none', 'dw_full': 'full'}[workload]
+    use_p2p = world > 1 and (halo == 'p2p-dw' or (halo == 'p2p' and kin))
+    t0 = time.perf_counter()
+    stepper = cases.build_engine_device(ny, nx, kinematic=kin, sources=sources, rank=rank,
+                                        world=world, device=dev, p2p=use_p2p)
+    eng = stepper.engine if world > 1 else stepper
+    build_s = time.perf_counter() - t0
+    ms, by_rank, _, _ = timed_steps(stepper, steps, warmup, world, dev)
+    _, sanity = mass_sanity(stepper, eng, world)
+    bpc = BYTES_PER_CELL[workload]
+    out = {'config': make_config(ny, nx, world, workload, True, use_p2p),
+           'value': ny * nx * world / (ms * 1e-3) / 1e9, 'unit': 'Gcell-updates/s',
+           'ms_per_step': ms, 'ms_per_step_by_rank': by_rank, 'steps': steps, 'warmup': warmup,
+           'path': eng.last_path, 'roofline_frac': ny * nx * bpc / (ms * 1e-3) / 1e9,
+           'sanity': sanity, 'build_s': round(build_s, 1),
+           'hbm_gb_allocated': round(torch.cuda.max_memory_allocated(dev) / 1e9, 1)}
+    peer = getattr(stepper, 'peer', None)
+    del stepper, eng
+    if peer is not None:
+        torch.cuda.synchronize()
+        import torch.distributed as dist
+        dist.barrier()
+        peer.close()
+    torch.cuda.empty_cache()
+    return tag, out
+
+
 # -------------------------------------------------------------------- main
-def write_component_case(work, eng_parts, dt=1.0):
-    """Lay the synthetic case out in the reference's file formats so the BMI
-    component can be initialised exactly as EMELI would (CFG + RTI + RTG)."""
-    from topoflow36_b200 import synth
-    p = eng_parts
-    return synth.write_case(work, p['DEM'], p['slope32'], p['width'], p['angle'], nval=p['nval'],
-                            dt=dt, kinematic=True, manning=True, n_steps=10 ** 9,
-                            check_stability='No')
-
-
 def main():
-    global NX, WORKLOAD
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=1000)
@@ -237,6 +511,9 @@ def main():
                          '(kinematic wave, default) or by NCCL send/recv after it')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-parity', action='store_true')
+    ap.add_argument('--no-extra', action='store_true',
+                    help='skip the config3 / config4 blocks (BASELINE configs[3], [4])')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -258,143 +535,199 @@ def main():
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    ny = args.rows_per_gpu
-    NX = args.nx
+    ny, nx = args.rows_per_gpu, args.nx
+    default_case = (ny, nx, args.workload, args.device_gen) == (NY_PER_GPU, NX, 'kw_ga', False)
     infil = (args.workload == 'kw_ga')
     kin = args.workload.startswith('kw')
     sources = {'kw_ga': 'ga', 'kw': 'none', 'dw': 'none', 'dw_full': 'full'}[args.workload]
-    WORKLOAD = ('synthetic %s DEM %dx%d per GPU, %s wave + Manning, %suniform 50 mm/h rain, '
-                'fp64, dt=1s' % ('closed-form (device-generated)' if args.device_gen else 'fractal',
-                                 ny, NX, 'kinematic' if kin else 'diffusive',
-                                 {'ga': 'fused Green-Ampt infiltration (pre-wetted soil, I0=0.1 m), ',
-                                  'none': '', 'full': 'fused rain/snow split + degree-day melt + '
-                                  'Priestley-Taylor ET + Green-Ampt (T_air grid), '}[sources]))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # the diffusive passes also run with the peer halo (--halo p2p-dw), but measured slower than
-    # NCCL on 2 GPUs (0.367 vs 0.358 ms/step): NCCL stays their default
+    # the diffusive passes also run with the peer halo (--halo p2p-dw); NCCL is their default
     use_p2p = (world > 1 and (args.halo == 'p2p-dw' or (args.halo == 'p2p' and kin)))
+    config = make_config(ny, nx, world, args.workload, args.device_gen, use_p2p)
+    sampler = ClockSampler(dev) if rank == 0 else None
+
+    sanity_extra = {}
+    if world > 1 and not args.no_parity:
+        sanity_extra.update(slab_equals_single(world, rank, dev, nx, kin, sources, use_p2p))
     if args.device_gen:
-        stepper = cases.build_engine_device(ny, NX, kinematic=kin, sources=sources, rank=rank,
+        stepper = cases.build_engine_device(ny, nx, kinematic=kin, sources=sources, rank=rank,
                                             world=world, device=dev, p2p=use_p2p)
         parts = None
-        args.no_e2e = args.no_e2e or world == 1
     else:
-        stepper, parts = cases.build_engine(ny, NX, kinematic=kin, sources=sources, rank=rank,
+        stepper, parts = cases.build_engine(ny, nx, kinematic=kin, sources=sources, rank=rank,
                                             world=world, device=dev, return_parts=True,
                                             p2p=use_p2p)
-        args.no_e2e = args.no_e2e or (world == 1 and args.workload != 'kw_ga' and args.workload != 'kw')
     eng = stepper.engine if world > 1 else stepper
-    cells = ny * NX * world
+    cells = ny * nx * world
     launches_per_step = 1 if kin else 3       # DW: depth pass, velocity pass, noflow zeroing
+    tmin0 = 0.0
+    if (world == 1 and parts is not None and not args.no_parity and sources in ('ga', 'none')
+            and ny * nx <= 4096 * 4096):
+        sanity_extra.update(parity_vs_c_oracle(eng, parts, nx))
+        tmin0 = 1.0
 
     # ---- `value`: state resident in HBM, no host round trip per step ----------
-    tmin = 0.0
-    for _ in range(args.warmup):
-        stepper.step(tmin); tmin += 1.0 / 60.0
-    sampler = ClockSampler(index=local) if rank == 0 else None
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    if sampler:
-        sampler.start()
-    e0.record()
-    for _ in range(args.steps):
-        stepper.step(tmin); tmin += 1.0 / 60.0
-    e1.record()
-    barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    by_rank = [float(ms.item()) / args.steps]
-    if world > 1:
-        every = torch.zeros(world, dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(every, ms)
-        by_rank = [float(v) / args.steps for v in every.tolist()]
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    clocks = sampler.stop() if sampler else None
-    ms_per_step = float(ms.item()) / args.steps
+    ms_per_step, by_rank, region, tmin = timed_steps(stepper, args.steps, args.warmup, world, dev,
+                                                     tmin0, sampler)
     value = cells / (ms_per_step * 1e-3) / 1e9
-    sc = stepper.read_scalars()
+    sc, sanity = mass_sanity(stepper, eng, world)
+    sanity.update(sanity_extra)
     path_used = eng.last_path
-    stored = eng.vol.sum().reshape(1)
-    qmax = eng.Q.max().reshape(1)
-    if world > 1:
-        dist.all_reduce(stored)
-        dist.all_reduce(qmax, op=dist.ReduceOp.MAX)
-    sanity = {'Q_outlet': sc.Q_outlet, 'Q_max': float(qmax), 'vol_R': sc.vol_R, 'vol_IN': sc.vol_IN,
-              'mass_balance_rel_err': abs(sc.vol_R - (float(stored) + sc.vol_edge)) / max(sc.vol_R, 1e-300),
-              'bad_values': int(sc.n_neg_d + sc.n_inf_d + sc.n_neg_u + sc.n_nan_u + sc.n_inf_u)}
 
     # ---- `e2e`: through the public API with host inputs and a host read -------
-    e2e = None
-    if not args.no_e2e:
-        if world == 1:
+    e2e = e2e_grid = None
+    if not args.no_e2e and parts is not None and kin:
+        import ctypes
+        from topoflow36_b200 import channels_kinematic_wave as ckw, synth
+        from topoflow36_b200.d8 import D8Toolkit
+        lay = parts['layout']
+        peer = getattr(stepper, 'peer', None)
+        del stepper, eng
+        if peer is not None:
+            torch.cuda.synchronize()
+            dist.barrier()
+            peer.close()
+        torch.cuda.empty_cache()
+        # the case in the reference's file formats (CFG + RTI + RTG), written by rank 0 from the
+        # slabs' own rows, so the BMI component is initialised exactly as EMELI would
+        work = None
+        if rank == 0:
             work = tempfile.mkdtemp(prefix='tfb_bench_')
-            from topoflow36_b200 import channels_kinematic_wave as ckw
-            from topoflow36_b200.d8 import D8Toolkit
-            S32 = parts['d8'].get('slope32')
-            if S32 is None:
-                tk = D8Toolkit(parts['DEM'], device=dev)
-                tk.update_flow_grid()
-                S32 = tk.slope().cpu().numpy()
-                del tk
-            parts['slope32'] = S32
-            del stepper, eng
-            torch.cuda.empty_cache()
-            cfg = write_component_case(work, parts)
+        if world > 1:
+            box = [work]
+            dist.broadcast_object_list(box, src=0)
+            work = box[0]
+        hd = lay.halo + 1 if world > 1 else 0              # the slab DEM carries hd halo rows
+        DEM_own = np.ascontiguousarray(parts['DEM'][hd:hd + ny])
+        # bed slope of the owned rows as the D8 toolkit left it (float32 values; the bad
+        # slopes already hold the global minimum, channels_base.py:4164-4260)
+        S32 = parts['d8']['S_bed'].float().cpu().numpy()
+        h = lay.halo
+        rows = lambda a: np.ascontiguousarray(a[h:h + ny] if a.shape[0] == ny + 2 * h else a)
+        pieces = dict(DEM=DEM_own, slope=np.float32(S32), width=rows(parts['width']),
+                      angle=rows(parts['angle']), nval=rows(parts['nval']))
+        if world > 1:
+            gathered = [None] * world if rank == 0 else None
+            dist.gather_object(pieces, gathered, dst=0)
+            if rank == 0:
+                pieces = {k: np.concatenate([g[k] for g in gathered], 0) for k in pieces}
+        if rank == 0:
+            cfg = synth.write_case(work, pieces['DEM'], pieces['slope'], pieces['width'],
+                                   pieces['angle'], nval=pieces['nval'], dt=1.0, kinematic=True,
+                                   manning=True, n_steps=10 ** 9,
+                                   outlet=(ny * world - 2, nx // 2))     # CHECK_STABILITY default: Yes
+        del pieces
+        if world > 1:
+            box = [cfg if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            cfg = box[0]
+
+        def component():
             comp = ckw.channels_component()
             comp.device = dev
+            comp.P2P_HALO = use_p2p
             if infil:
                 comp.enable_fused_sources(infil=True, I0=cases.I0_WET)
             comp.initialize(cfg_file=cfg, mode='nondriver', SILENT=True)
             if infil:
                 for k, v in cases.GA_TREYNOR.items():
                     comp.set_source_input(k, v)
-            LONG = {n: ln for ln, n in comp._var_name_map.items()}
-            host_in = {n: np.array(0.0) for n in ('MR', 'GW', 'ET', 'IN', 'SM')}
-            host_in['P_rain'] = np.array(cases.RAIN_50MMPH)
-            host_in['rho_H2O'] = np.array(1000.0)
+            return comp
+        comp = component()
+        LONG = {n: ln for ln, n in comp._var_name_map.items()}
+        host_in = {n: np.array(0.0) for n in ('MR', 'GW', 'ET', 'IN', 'SM')}
+        host_in['P_rain'] = np.array(cases.RAIN_50MMPH)
+        host_in['rho_H2O'] = np.array(1000.0)
 
-            def e2e_step():
-                for n, v in host_in.items():                 # what EMELI does each step
-                    comp.set_value(LONG[n], v)
-                comp.update()                                # 1 launch + D2H of the scalar block
-                return float(comp.Q_outlet)
-            h2d = 8 * len(host_in)
-            import ctypes
-            d2h = ctypes.sizeof(L.ChannelsScalars)
-            import shutil
-        else:
-            def e2e_step():
-                eng.set_input('P_rain', float(np.array(cases.RAIN_50MMPH)))
-                stepper.step(0.0)
-                return stepper.read_scalars().Q_outlet       # all-reduce + D2H
-            h2d = 8
-            import ctypes
-            d2h = ctypes.sizeof(L.ChannelsScalars)
+        def e2e_step():
+            for n, v in host_in.items():                 # what EMELI does each step
+                comp.set_value(LONG[n], v)
+            comp.update()                                # launch + scalar block to the host
+            return float(comp.Q_outlet)
+
+        def time_e2e(step_fn, n_e2e):
+            for _ in range(args.warmup):
+                step_fn()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                step_fn()
+            torch.cuda.synchronize()
+            if sampler:
+                sampler.sample()
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            return float(dt.item())
         n_e2e = max(10, args.steps // 4)
-        for _ in range(args.warmup):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            q = e2e_step()
-        barrier()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {'value': cells * n_e2e / float(dt.item()) / 1e9, 'unit': 'Gcell-updates/s',
-               'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'steps': n_e2e,
-               'ms_per_step': float(dt.item()) / n_e2e * 1e3,
-               'api': ('channels_kinematic_wave.channels_component: set_value() x7 + update() + '
-                       'Q_outlet read per step' if world == 1 else
-                       'SlabChannels.step() + collective read_scalars() per step'),
-               'init_h2d_bytes': int(ny * NX * (4 + 8 * 6)) if world == 1 else None}
+        dt = time_e2e(e2e_step, n_e2e)
+        e2e = {'value': cells * n_e2e / dt / 1e9, 'unit': 'Gcell-updates/s',
+               'h2d_bytes_per_step': 8 * len(host_in),
+               'd2h_bytes_per_step': ctypes.sizeof(L.ChannelsScalars) * (world if world > 1 else 1),
+               'steps': n_e2e, 'ms_per_step': dt / n_e2e * 1e3, 'path': comp.engine.last_path,
+               'check_stability': bool(comp.CHECK_STABILITY),
+               'api': 'channels_kinematic_wave.channels_component%s: set_value() x7 + update() + '
+                      'Q_outlet read per step' % ('' if world == 1 else ' in slab mode (one per rank)'),
+               'init_h2d_bytes': int(ny * nx * (4 + 8 * 6))}
+        comp.finalize()
+        del comp
+        torch.cuda.empty_cache()
+        # ---- the same with grid inputs: IN and ET arrive as fresh host grids every step ----
         if world == 1:
+            comp = ckw.channels_component()
+            comp.device = dev
+            comp.initialize(cfg_file=cfg, mode='nondriver', SILENT=True)
+            rng = np.random.default_rng(7)
+            IN_h = [2e-6 * rng.random((ny, nx)) for _ in range(2)]
+            ET_h = [1e-7 * rng.random((ny, nx)) for _ in range(2)]
+            k = [0]
+
+            def grid_step():
+                for n, v in host_in.items():
+                    if n not in ('IN', 'ET'):
+                        comp.set_value(LONG[n], v)
+                comp.set_value(LONG['IN'], IN_h[k[0] & 1])         # a different array object each step
+                comp.set_value(LONG['ET'], ET_h[k[0] & 1])
+                k[0] += 1
+                comp.update()
+                return float(comp.Q_outlet)
+            n_g = max(10, min(50, args.steps // 4))
+            dtg = time_e2e(grid_step, n_g)
+            gridded = 2
+            e2e_grid = {'value': cells * n_g / dtg / 1e9, 'unit': 'Gcell-updates/s',
+                        'h2d_bytes_per_step': gridded * ny * nx * 8 + 8 * 5,
+                        'd2h_bytes_per_step': ctypes.sizeof(L.ChannelsScalars) + ny * nx * 8,
+                        'steps': n_g, 'ms_per_step': dtg / n_g * 1e3, 'path': comp.engine.last_path,
+                        'pcie_floor_ms': gridded * ny * nx * 8 / 50e9 * 1e3 + ny * nx * 8 / 50e9 * 1e3,
+                        'api': 'set_value() with (ny, nx) float64 numpy grids for IN and ET (the rest '
+                               '0-D) + update(); the masked ET grid is copied back into the provider\'s '
+                               'array (channels_base.py:1625-1627) every step'}
             comp.finalize()
+            del comp
+            torch.cuda.empty_cache()
+        if rank == 0:
             shutil.rmtree(work, ignore_errors=True)
+
+    # ---- BASELINE configs[3] and [4] as extra blocks ---------------------------------
+    extras = {}
+    if not args.no_extra and default_case:
+        try:
+            peer = getattr(stepper, 'peer', None)
+            del stepper, eng
+            if peer is not None:
+                torch.cuda.synchronize()
+                dist.barrier()
+                peer.close()
+        except NameError:                     # the e2e leg already released them
+            pass
+        torch.cuda.empty_cache()
+        tag, blk = extra_config('config4', 8192, 65536, 'kw', world, rank, dev, args.halo)
+        extras[tag] = blk
+        if world >= 2:
+            tag, blk = extra_config('config3', 32768 // world, 32768, 'dw_full', world, rank, dev, args.halo)
+            extras[tag] = blk
+    clocks = sampler.report() if sampler else None
 
     if rank != 0:
         if world > 1:
@@ -409,17 +742,18 @@ def main():
         pass
     peak = float(peaks.get('hbm_gbs', 6650.0))
     bpc = BYTES_PER_CELL[args.workload]
-    cells_per_launch = ny * NX
+    cells_per_launch = ny * nx
     achieved = cells_per_launch * bpc / (ms_per_step * 1e-3) / 1e9
     traffic = None
     try:
         prof = json.load(open(os.path.join(ROOT, 'profiles', 'kernel_traffic.json')))
         traffic = (prof.get(args.workload + '_4096', {}).get('dram_bytes_per_launch')
-                   if (ny, NX) == (4096, 4096) else None)
+                   if (ny, nx) == (4096, 4096) else None)
     except (OSError, ValueError):
         pass
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved / peak, 'traffic': traffic,
+                'frac_dram': (traffic / (ms_per_step * 1e-3) / 1e9 / peak) if traffic else None,
                 'peak_source': 'MEASURED_PEAKS.json hbm_gbs (measured)' if peaks
                 else 'B200_PROFILING.md fallback 6.65 TB/s',
                 'kernel': ('channels_packed_kernel<SRC=%s, %s>%s (TMA ring)'
@@ -428,35 +762,31 @@ def main():
                 'path': path_used,
                 'algorithmic_bytes_per_cell': bpc, 'cells_per_launch': cells_per_launch,
                 'launch_ms': ms_per_step,
-                'note': '%d launch(es) per step; time = timed region / steps (CUDA events)' % launches_per_step}
+                'note': ('%d launch(es) per step; time = timed region / steps (CUDA events); frac = '
+                         'algorithmic bytes (SURVEY 8d contract), frac_dram = DRAM bytes ncu counted '
+                         'for this kernel (static inputs are packed: 16 B instead of 42 B per cell)'
+                         % launches_per_step)}
 
     cpu = None
-    if world == 1 and not args.no_cpu_baseline and infil and NX == 4096:
-        v, desc, cores, _, _ = cpu_port_rate(15.0)
-        cpu = {'value': v, 'unit': 'Gcell-updates/s', 'cores': cores, 'kind': 'port', 'sample': desc}
-        nv, ndesc = cpu_numpy_rate()
-        cpu['numpy_path'] = {'value': nv, 'unit': 'Gcell-updates/s', 'cores': 1, 'sample': ndesc}
+    if world == 1 and not args.no_cpu_baseline and default_case:
+        cpu = cpu_baseline_block(20.0, 10.0, 10, 2)
 
     out = {
         'metric': METRIC, 'value': value, 'unit': 'Gcell-updates/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
         'ms_per_step_by_rank': by_rank,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-        'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'grid': [ny * world, NX], 'rows_per_gpu': ny,
-                   'partition': ('row slabs, 1 halo row of Q per neighbour per step, %s'
-                                 % ('NVLink peer stores fused into the routing kernel(s), flag words '
-                                    'polled by the boundary tiles (no NCCL call per step)' if use_p2p
-                                    else 'NCCL send/recv after the kernel'))
-                   if world > 1 else 'single GPU',
-                   'l2': 'working set %.2f GB per step per GPU >> 126 MB L2, no flush needed'
-                         % (ny * NX * bpc / 1e9)},
-        'e2e': e2e, 'gpu_launches': launches_per_step * args.steps,
+        'data': 'synthetic', 'config': config,
+        'e2e': e2e, 'e2e_grid_inputs': e2e_grid, 'gpu_launches': launches_per_step * args.steps,
         'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks, 'sanity': sanity,
     }
+    out.update(extras)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+    if sanity.get('parity_ok') is False or sanity.get('slab_equals_single') is False:
+        raise SystemExit('bench.py: parity check FAILED: %r' % {k: v for k, v in sanity.items()
+                                                                if k.startswith(('parity', 'slab'))})
 
 
 if __name__ == '__main__':

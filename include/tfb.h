@@ -164,6 +164,9 @@ typedef struct {
     int64_t n_neg_u, n_nan_u, n_inf_u;             /* check_flow_velocity :3352 */
     int64_t n_nan_IN;                              /* infil_base.py:906-950   */
     int64_t step_count;
+    int64_t n_step_failed;    /* launches (cumulative) in which a bounded wait of the TMA
+                                 pipeline or of the peer-memory halo timed out: the grids
+                                 of such a step are NOT valid; the host raises on it    */
 } tfb_channels_scalars;
 
 typedef struct {
@@ -264,7 +267,8 @@ typedef struct {
                                  [0,15) sums and bad-value counts, [15] "this
                                  rank owns the outlet", [16] dt_cfl_min (reduce
                                  with MIN or ignore), [17,21) outlet Q,u,d,f
-                                 (zero on non-owners), rest padding            */
+                                 (zero on non-owners), [22] CTAs whose bounded
+                                 waits timed out, rest padding                  */
 
 /* sizeof() of the two structs above, so a binding can verify its own layout */
 int64_t tfb_sizeof_channels_step_args(void);

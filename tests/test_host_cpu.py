@@ -220,7 +220,15 @@ def test_bench_reference_arm_contract():
     assert d['impl'] == 'reference' and d['metric'] == 'routing Gcell-updates/sec'
     assert d['unit'] == 'Gcell-updates/s' and d['higher_is_better'] is True
     assert d['value'] > 0 and d['steps'] == 2 and d['n_gpus'] == 1
-    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    # the unmodified reference when it is staged (here: /root/reference), else the C port
+    from oracle import ref_harness as rh
+    if rh.reference_available():
+        assert d['cpu_baseline']['kind'] == 'reference' and d['cpu_baseline']['cores'] == 1
+        assert d['cpu_baseline']['port_all_threads']['kind'] == 'port'
+    else:
+        assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    for k in ('workload', 'grid', 'rows_per_gpu', 'partition', 'l2'):   # same keys as the GPU arm
+        assert k in d['config'], k
     assert d['cpu_baseline']['value'] == d['value']
     assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0,
                         'd2h_bytes_per_step': 0}

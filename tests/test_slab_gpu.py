@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, kinematic, infil, q, devgen=False, p2p=False):
+def _worker(rank, world, port, kinematic, infil, q, devgen=False, p2p=False, d0=0.0, packed=True):
     import torch
     import torch.distributed as dist
     from topoflow36_b200 import cases
@@ -40,10 +40,10 @@ def _worker(rank, world, port, kinematic, infil, q, devgen=False, p2p=False):
         else:
             slab, parts = cases.build_engine(ny, nx, kinematic=kinematic, infil=infil, rank=rank,
                                              world=world, device=dev, return_parts=True, dt=2.0,
-                                             p2p=p2p)
+                                             p2p=p2p, d0=d0, packed=packed)
             assert (slab.peer is not None) == bool(p2p)
             one = cases.build_engine(ny * world, nx, kinematic=kinematic, infil=infil, device=dev,
-                                     tile_rows=ny, dt=2.0)
+                                     tile_rows=ny, dt=2.0, d0=d0, packed=packed)
             lay = parts['layout']
         rows = slice(lay.row0, lay.row0 + lay.ny)
         fails = []
@@ -79,11 +79,18 @@ def _worker(rank, world, port, kinematic, infil, q, devgen=False, p2p=False):
         dist.destroy_process_group()
 
 
+def test_two_slabs_initial_depth_generic_diffusive():
+    """d0 = 5 cm with the GENERIC diffusive kernel, which re-derives the parent's depth from
+    the halo rows of the state: they must hold the neighbours' initial volumes before the
+    first step (SlabChannels starts with stale state halos)."""
+    test_two_slabs_equal_one_grid(False, True, False, False, d0=0.05, packed=False)
+
+
 @pytest.mark.parametrize('kinematic,infil,devgen,p2p', [
     (True, False, False, False), (True, True, False, False), (False, False, False, False),
     (True, True, True, False), (True, False, False, True), (True, True, False, True),
     (False, False, False, True), (False, True, False, True)])
-def test_two_slabs_equal_one_grid(kinematic, infil, devgen, p2p):
+def test_two_slabs_equal_one_grid(kinematic, infil, devgen, p2p, d0=0.0, packed=True):
     """p2p = True: the halo rows travel through NVLink peer stores inside the routing
     kernel (tfb_channels_step_packed_p2p; diffusive wave: ..._dw_a_p2p stores the boundary
     depths, ..._dw_b_p2p the boundary discharges) instead of NCCL send/recv."""
@@ -95,7 +102,8 @@ def test_two_slabs_equal_one_grid(kinematic, infil, devgen, p2p):
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, kinematic, infil, q, devgen, p2p))
+    procs = [ctx.Process(target=_worker, args=(r, world, port, kinematic, infil, q, devgen, p2p,
+                                               d0, packed))
              for r in range(world)]
     for p in procs:
         p.start()

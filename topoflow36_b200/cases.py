@@ -192,7 +192,7 @@ def build_engine_device(ny, nx, kinematic=True, infil=False, dt=1.0, rank=0, wor
 
 def build_engine(ny, nx, kinematic=True, infil=False, diag=False, dt=1.0, rank=0, world=1,
                  seed=1234, device=None, group=None, link_flats=True, return_parts=False,
-                 tile_rows=None, sources=None, p2p=False):
+                 tile_rows=None, sources=None, p2p=False, d0=0.0, packed=True):
     """Engine (and SlabChannels wrapper when world > 1) for rank `rank` of a
     (world*ny, nx) synthetic grid."""
     import torch
@@ -218,7 +218,7 @@ def build_engine(ny, nx, kinematic=True, infil=False, diag=False, dt=1.0, rank=0
                          rough=np.float64(nval), kinematic=kinematic, diag=diag,
                          outlet=(ny_global - 2, nx // 2), row0=lay.row0, ny_global=ny_global,
                          halo=halo, device=device, finalize=True,
-                         n_pixels_global=ny * nx,
+                         n_pixels_global=ny * nx, d0=d0, packed=packed,
                          q_buffers=None if peer is None else peer.q_buffers,
                          d_buffer=None if peer is None else peer.d_buffer)
     apply_sources(eng, sources or ('ga' if infil else 'none'), row0=lay.row0, halo=halo, seed=seed)

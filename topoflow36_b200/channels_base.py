@@ -659,6 +659,14 @@ class channels_component(BMI_base.BMI_component):
         into pinned host memory (one stream synchronise, no copy; in slab mode one
         all-reduce forms the global values -- collective)."""
         s = self.stepper.read_scalars()
+        if s.n_step_failed:
+            # a bounded wait inside the kernel ran out (TMA pipeline, or a slab neighbour that
+            # never delivered its halo rows): the grids of that step are not valid
+            self.status = 'failed'
+            self.DONE = True
+            raise L.TfbError('routing step failed on the device: %d launch(es) gave up waiting for '
+                             'the tile pipeline or for a neighbour slab\'s halo rows'
+                             % s.n_step_failed)
         for n in _SCALAR_BLOCK:
             getattr(self, n).fill(getattr(s, n))
         self.dt_cfl_min.fill(s.dt_cfl_min)

@@ -620,7 +620,7 @@ channels_step_kernel(const tfb_channels_step_args a, const ChConsts k) {
         h[P_UOUT] = has_out ? outp[P_UOUT] : 0.0;
         h[P_DOUT] = has_out ? outp[P_DOUT] : 0.0;
         h[P_FOUT] = has_out ? outp[P_FOUT] : 0.0;
-        h[P_HASOUT] = 0.0; h[22] = 0.0; h[23] = 0.0;
+        h[P_HASOUT] = 0.0; h[P_FAIL] = 0.0; h[23] = 0.0;
         outp[P_HASOUT] = 0.0;
         if (a.finalize) fold_scalars(a, h);
         *a.ticket = 0u;    // re-arm for the next step

@@ -24,7 +24,7 @@ constexpr int kNCnt = 7;        // counters   (slots 8..14)
 constexpr int kPartialStride = 24;
 static_assert(kPartialStride == TFB_NSUM, "TFB_NSUM must equal the partial stride");
 constexpr int P_HASOUT_SUM = 15, P_DTMIN = 16, P_QOUT = 17, P_UOUT = 18, P_DOUT = 19,
-              P_FOUT = 20, P_HASOUT = 21;
+              P_FOUT = 20, P_HASOUT = 21, P_FAIL = 22;
 
 // (only slots 0..1 are live unless source terms are fused; the compiler drops
 // the dead registers because every use is guarded by a template constant)
@@ -70,6 +70,11 @@ __device__ inline void fold_status(const tfb_channels_step_args &a, const double
     s.vol_Q += (s.Q_outlet * a.dt);
     s.step_count += 1;
 }
+// (c) CTAs that gave up a bounded wait (TMA pipeline, peer halo): the step is invalid.
+// Cumulative, so the host sees it whenever it next reads the block.
+__device__ inline void fold_fail(const tfb_channels_step_args &a, const double *h) {
+    a.scalars->n_step_failed += (int64_t)h[P_FAIL];
+}
 // copy the scalar block to the pinned-host mirror, if any (called by the folding thread)
 __device__ inline void mirror_scalars(const tfb_channels_step_args &a) {
     if (!a.scalars_mirror) return;
@@ -82,6 +87,7 @@ __device__ inline void mirror_scalars(const tfb_channels_step_args &a) {
 __device__ inline void fold_scalars(const tfb_channels_step_args &a, const double *h) {
     fold_sums(a, h);
     fold_status(a, h);
+    fold_fail(a, h);
     mirror_scalars(a);
 }
 

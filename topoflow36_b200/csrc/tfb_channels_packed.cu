@@ -135,6 +135,19 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, unsigned phase) {
     }
     return false;
 }
+// consumers of a peer-halo kernel: the producer may legitimately sit in peer_flag_wait for
+// far longer than the bound above (a neighbour held up on its host); while it does
+// (`*producer_waiting` != 0) the poll budget is not consumed
+__device__ __forceinline__ bool mbar_wait_peer(uint64_t *bar, unsigned phase,
+                                               const volatile int *producer_waiting,
+                                               const volatile int *failed) {
+    for (unsigned i = 0; i < (1u << 26); ++i) {
+        if (mbar_try_wait(bar, phase)) return true;
+        if (*failed) return false;               // the producer gave up: no tile will come
+        if (*producer_waiting) i = 0u;
+    }
+    return false;
+}
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar,
                                             int c0, int c1) {
     asm volatile(
@@ -358,6 +371,7 @@ __global__ void zero_at_kernel(double *__restrict__ x, const int64_t *__restrict
     if (i < n) x[__ldg(idx + i)] = 0.0;
 }
 
+constexpr uint32_t kPeerPoison = 0xffffffffu;   // flag value a failed rank leaves with its neighbours
 struct PkMaps { CUtensorMap Q, vol, coef, I, H, T, w, geo; };
 struct PkPeer {
     double *up_Q, *down_Q;                  // the neighbours' halo rows of the new discharge
@@ -375,6 +389,7 @@ __device__ __forceinline__ bool peer_flag_wait(const uint32_t *flag, uint32_t ne
     for (unsigned i = 0; i < (1u << 26); ++i) {
         uint32_t v;
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v == kPeerPoison) return false;          // the neighbour's step failed: fail fast
         if (v >= need) {
             // the halo row is read by the TMA unit (async proxy) next
             asm volatile("fence.proxy.async;" ::: "memory");
@@ -391,7 +406,8 @@ struct PkMapsB { CUtensorMap D, N, S, w, geo; };
 // status only (pass B).
 template <int NWARPS>
 __device__ __forceinline__ void pk_finish(const tfb_channels_step_args &a, Acc &acc, float rate_max,
-                                          bool consumer, int fail, int mode, const PkPeer &peer,
+                                          bool consumer, const volatile int *failp, int mode,
+                                          const PkPeer &peer,
                                           double (*sm)[kPartialStride], double *tot, bool *is_last) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (consumer) {
@@ -415,6 +431,7 @@ __device__ __forceinline__ void pk_finish(const tfb_channels_step_args &a, Acc &
         if (lane == 0) sm[warp][P_DTMIN] = (double)__uint_as_float(rb);
     }
     __syncthreads();
+    const int fail = *failp;                 // read AFTER the barrier: any warp may have set it
     if (tid < kPartialStride) {
         double v = 0.0;
         if (tid == P_DTMIN) {
@@ -422,8 +439,13 @@ __device__ __forceinline__ void pk_finish(const tfb_channels_step_args &a, Acc &
         } else if (tid < S_NSLOT) {
             for (int w = 0; w < NWARPS; ++w) v += sm[w][tid];
         }
-        if (tid == S_NNAN_D && fail) v += 1.0e9;          // pipeline failure poisons the step
+        if (tid == P_FAIL) v = fail ? 1.0 : 0.0;          // this CTA gave up a bounded wait
         a.partials[(int64_t)(blockIdx.x + 2) * kPartialStride + tid] = v;
+    }
+    if (fail && tid == 0) {
+        // the neighbours must not wait a minute each for rows that will never come
+        if (peer.up_flag) *reinterpret_cast<volatile uint32_t *>(peer.up_flag) = kPeerPoison;
+        if (peer.down_flag) *reinterpret_cast<volatile uint32_t *>(peer.down_flag) = kPeerPoison;
     }
     if (peer.up_Q || peer.down_Q) __threadfence_system();   // peer halo stores are visible
     else __threadfence();
@@ -438,7 +460,7 @@ __device__ __forceinline__ void pk_finish(const tfb_channels_step_args &a, Acc &
     if (tid < kPartialStride) {
         const volatile double *P = a.partials;
         double v = 0.0;
-        if (tid < S_NSLOT || tid == P_DTMIN) {
+        if (tid < S_NSLOT || tid == P_DTMIN || tid == P_FAIL) {
             for (unsigned b = 0; b < gridDim.x; ++b) {
                 const double x = P[(int64_t)(b + 2) * kPartialStride + tid];
                 v = (tid == P_DTMIN) ? fmax(v, x) : (v + x);
@@ -458,12 +480,12 @@ __device__ __forceinline__ void pk_finish(const tfb_channels_step_args &a, Acc &
         h[P_UOUT] = has_out ? outp[P_UOUT] : 0.0;
         h[P_DOUT] = has_out ? outp[P_DOUT] : 0.0;
         h[P_FOUT] = has_out ? outp[P_FOUT] : 0.0;
-        h[P_HASOUT] = 0.0; h[22] = 0.0; h[23] = 0.0;
+        h[P_HASOUT] = 0.0; h[P_FAIL] = tot[P_FAIL]; h[23] = 0.0;
         if (mode != 1) outp[P_HASOUT] = 0.0;
         if (a.finalize) {
             if (mode == 0) fold_scalars(a, h);
-            else if (mode == 1) fold_sums(a, h);
-            else { fold_status(a, h); mirror_scalars(a); }
+            else if (mode == 1) { fold_sums(a, h); fold_fail(a, h); }
+            else { fold_status(a, h); fold_fail(a, h); mirror_scalars(a); }
         }
         a.ticket[0] = 0u;                                 // re-arm for the next launch
         a.ticket[1] = 0u;                                 // boundary-tile counter (peer halos)
@@ -488,13 +510,15 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
     __shared__ double tot[kPartialStride];
     __shared__ __align__(8) uint64_t full_bar[NS], empty_bar[NS];
     __shared__ bool is_last;
-    __shared__ int s_fail;
+    __shared__ volatile int s_fail;
+    __shared__ volatile int s_pwait;
     __shared__ unsigned s_bcount[NS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < p.n_angles * 4; i += kThreads) lut[i] = __ldg(p.angle_lut + i);
     if (tid < kConsumerWarps * kPartialStride) (&sm[0][0])[tid] = 0.0;
     if (tid == 0) {
         s_fail = 0;
+        s_pwait = 0;
         for (int q = 0; q < NS; ++q) s_bcount[q] = 0u;
         for (int s = 0; s < NS; ++s) {
             mbar_init(&full_bar[s], 1u);
@@ -531,11 +555,15 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
                     // peer-memory halo: the first / last tile row reads a row a neighbour
                     // stored and overwrites (in its memory) a row it may still be reading
                     if (peer.from_up && ty == 0 && !up_ok) {
-                        if (!peer_flag_wait(peer.from_up, peer.need)) { s_fail = 1; break; }
+                        s_pwait = 1;
+                        if (!peer_flag_wait(peer.from_up, peer.need)) { s_fail = 1; s_pwait = 0; break; }
+                        s_pwait = 0;
                         up_ok = true;
                     }
                     if (peer.from_down && ty == k.tiles_y - 1 && !down_ok) {
-                        if (!peer_flag_wait(peer.from_down, peer.need)) { s_fail = 1; break; }
+                        s_pwait = 1;
+                        if (!peer_flag_wait(peer.from_down, peer.need)) { s_fail = 1; s_pwait = 0; break; }
+                        s_pwait = 0;
                         down_ok = true;
                     }
                 }
@@ -559,7 +587,8 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
         int stage = 0;
         unsigned phase = 0;
         for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
-            if (!mbar_wait(&full_bar[stage], phase)) { s_fail = 1; break; }
+            if (!(PEER ? mbar_wait_peer(&full_bar[stage], phase, &s_pwait, &s_fail)
+                       : mbar_wait(&full_bar[stage], phase))) { s_fail = 1; break; }
             int ty, txi;
             tile_of<PEER>(k, t, ty, txi);
 #pragma unroll 1
@@ -728,7 +757,7 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
             if (++stage == NS) { stage = 0; phase ^= 1u; }
         }
     }
-    pk_finish<kConsumerWarps>(a, acc, rate_max, warp < kConsumerWarps, s_fail, kKW ? 0 : 1, peer, sm,
+    pk_finish<kConsumerWarps>(a, acc, rate_max, warp < kConsumerWarps, &s_fail, kKW ? 0 : 1, peer, sm,
                               tot, &is_last);
 }
 
@@ -749,13 +778,15 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
     __shared__ double tot[kPartialStride];
     __shared__ __align__(8) uint64_t full_bar[NS], empty_bar[NS];
     __shared__ bool is_last;
-    __shared__ int s_fail;
+    __shared__ volatile int s_fail;
+    __shared__ volatile int s_pwait;
     __shared__ unsigned s_bcount[NS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < p.n_angles * 4; i += kThreads) lut[i] = __ldg(p.angle_lut + i);
     if (tid < kConsumerWarps * kPartialStride) (&sm[0][0])[tid] = 0.0;
     if (tid == 0) {
         s_fail = 0;
+        s_pwait = 0;
         for (int q = 0; q < NS; ++q) s_bcount[q] = 0u;
         for (int s = 0; s < NS; ++s) {
             mbar_init(&full_bar[s], 1u);
@@ -784,11 +815,15 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
                 if (PEER && t < k.n_boundary) {
                     // the depth halo rows were stored by the neighbours' pass A of this step
                     if (peer.from_up && ty == 0 && !up_ok) {
-                        if (!peer_flag_wait(peer.from_up, peer.need)) { s_fail = 1; break; }
+                        s_pwait = 1;
+                        if (!peer_flag_wait(peer.from_up, peer.need)) { s_fail = 1; s_pwait = 0; break; }
+                        s_pwait = 0;
                         up_ok = true;
                     }
                     if (peer.from_down && ty == k.tiles_y - 1 && !down_ok) {
-                        if (!peer_flag_wait(peer.from_down, peer.need)) { s_fail = 1; break; }
+                        s_pwait = 1;
+                        if (!peer_flag_wait(peer.from_down, peer.need)) { s_fail = 1; s_pwait = 0; break; }
+                        s_pwait = 0;
                         down_ok = true;
                     }
                 }
@@ -807,7 +842,8 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
         int stage = 0;
         unsigned phase = 0;
         for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
-            if (!mbar_wait(&full_bar[stage], phase)) { s_fail = 1; break; }
+            if (!(PEER ? mbar_wait_peer(&full_bar[stage], phase, &s_pwait, &s_fail)
+                       : mbar_wait(&full_bar[stage], phase))) { s_fail = 1; break; }
             int ty, txi;
             tile_of<PEER>(k, t, ty, txi);
 #pragma unroll 1
@@ -907,7 +943,7 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
             if (++stage == NS) { stage = 0; phase ^= 1u; }
         }
     }
-    pk_finish<kConsumerWarps>(a, acc, rate_max, warp < kConsumerWarps, s_fail, 2, peer, sm, tot,
+    pk_finish<kConsumerWarps>(a, acc, rate_max, warp < kConsumerWarps, &s_fail, 2, peer, sm, tot,
                               &is_last);
 }
 

@@ -49,7 +49,7 @@ class ChannelsScalars(C.Structure):
         'dt_cfl_min')] +
         [(n, C.c_int64) for n in (
             'n_neg_d', 'n_nan_d', 'n_inf_d', 'n_neg_u', 'n_nan_u', 'n_inf_u',
-            'n_nan_IN', 'step_count')])
+            'n_nan_IN', 'step_count', 'n_step_failed')])
 
 
 class ChannelsStepArgs(C.Structure):

@@ -479,7 +479,10 @@ class ChannelsEngine(object):
         a = self.args
         d = self.own(self.d)
         if _is_grid(d0):
-            d.copy_(torch.as_tensor(d0).to(device=self.device, dtype=torch.float64))
+            t = torch.as_tensor(d0).to(device=self.device, dtype=torch.float64)
+            if self.halo and t.shape[0] == self.ny + 2 * self.halo:
+                t = t[self.halo:self.halo + self.ny]       # a slab's rows came with their halo
+            d.copy_(t)
         else:
             d.fill_(float(d0))
         vol = self.own(self._sbuf(self.vol_buf))
@@ -552,9 +555,11 @@ class ChannelsEngine(object):
                 return True
         return False
 
-    def step(self, time_min=0.0, peer=None):
+    def step(self, time_min=0.0, peer=None, peer_step=None):
         """Advance one time step.  `peer` (slab.PeerHalos) switches the packed step to the
-        fused peer-memory halo exchange (kinematic: one launch; diffusive: both passes)."""
+        fused peer-memory halo exchange (kinematic: one launch; diffusive: both passes);
+        `peer_step` = how many steps (diffusive: phases) used it before this one -- the
+        value the flag words are compared with (default: every step so far did)."""
         a = self.args
         a.flags = self.flags | (L.CH_ET_INPLACE if a.ET.ptr else 0)
         a.time_min = float(time_min)
@@ -570,7 +575,8 @@ class ChannelsEngine(object):
             setattr(a, name + '_out', self._p(buf[self.scur ^ 1 if dbl else 0]))
         if self._packed_ok():
             if self.kinematic and peer is not None:
-                ph = peer.descriptor(self.qcur ^ 1, self.n_steps)
+                ps = self.n_steps if peer_step is None else int(peer_step)
+                ph = peer.descriptor(self.qcur ^ 1, ps)
                 L.check(self.lib.tfb_channels_step_packed_p2p(
                     C.byref(a), C.byref(self.packed), C.byref(ph), L.stream_ptr()),
                     'tfb_channels_step_packed_p2p')
@@ -580,11 +586,12 @@ class ChannelsEngine(object):
             elif peer is not None:
                 # diffusive wave, peer halo: pass A stores its boundary depths, pass B its
                 # boundary discharges into the neighbours' halo rows; phases 2n and 2n + 1
-                ph = peer.descriptor(0, 2 * self.n_steps, depth=True)
+                ps = 2 * self.n_steps if peer_step is None else int(peer_step)
+                ph = peer.descriptor(0, ps, depth=True)
                 L.check(self.lib.tfb_channels_step_packed_dw_a_p2p(
                     C.byref(a), C.byref(self.packed), C.byref(ph), L.stream_ptr()),
                     'tfb_channels_step_packed_dw_a_p2p')
-                ph = peer.descriptor(self.qcur ^ 1, 2 * self.n_steps + 1)
+                ph = peer.descriptor(self.qcur ^ 1, ps + 1)
                 L.check(self.lib.tfb_channels_step_packed_dw_b_p2p(
                     C.byref(a), C.byref(self.packed), C.byref(ph), L.stream_ptr()),
                     'tfb_channels_step_packed_dw_b_p2p')

@@ -245,7 +245,12 @@ class SlabChannels(object):
             raise L.TfbError('SlabChannels needs an engine built with finalize=True')
         self.device = engine.device
         self.n_launches_per_step = 1
-        self._state_halos_stale = False
+        # the generic diffusive kernel re-derives the parent's depth from the HALO rows of
+        # vol / I / h_swe: an initial depth d0 > 0 (or h0_swe, I0) is only written into the
+        # owned rows, so the halo rows are filled from the neighbours before the first
+        # generic step
+        self._state_halos_stale = layout.world_size > 1 and not engine.kinematic
+        self.n_peer_steps = 0         # steps (diffusive: phases) taken with the peer-memory halo
         if layout.world_size > 1 and not engine.kinematic and self.peer is None:
             # packed diffusive step: the new depths of the boundary rows cross the link
             # between pass A and pass B
@@ -273,12 +278,14 @@ class SlabChannels(object):
         e = self.engine
         packed = e._packed_ok()
         if self.peer is not None and packed:
-            e.step(time_min, peer=self.peer)      # halo rows travel inside the kernel(s)
+            # halo rows travel inside the kernel(s); the flag words count PEER steps only,
+            # so NCCL steps in between (below) leave the protocol in step
+            e.step(time_min, peer=self.peer, peer_step=self.n_peer_steps)
+            self.n_peer_steps += 1 if e.kinematic else 2
             self._state_halos_stale = not e.kinematic
             return
-        if self.peer is not None:
-            raise L.TfbError('peer-memory halos were set up but this step is not eligible '
-                             '(needs the packed path on every step)')
+        # (with peer halos set up, a step the packed path cannot take -- grid forcing from a
+        # provider, say -- uses the NCCL exchange: the peer buffers are ordinary device tensors)
         if not packed and self._state_halos_stale:
             # first generic step after packed ones: its state halo rows were not kept current
             self.exchange_state()
@@ -295,7 +302,7 @@ class SlabChannels(object):
         if self.layout.world_size == 1:
             return e.read_scalars()
         nf, nc = len(self._SUM_FIELDS), len(self._CNT_FIELDS)
-        raw = e.scalars_dev.view(torch.float64)          # 20 doubles + 8 int64 bit patterns
+        raw = e.scalars_dev.view(torch.float64)          # 20 doubles + 9 int64 bit patterns
         if getattr(self, '_allv', None) is None:
             self._allv = torch.empty((self.layout.world_size, raw.numel()), dtype=torch.float64,
                                      device=self.device)
@@ -314,6 +321,7 @@ class SlabChannels(object):
         for k, n in enumerate(self._CNT_FIELDS):
             setattr(s, n, int(cnts[k]))
         s.step_count = e.n_steps
+        s.n_step_failed = int(hi[:, nf + 1 + nc + 1].sum())
         return s
 
     def global_dt_min(self):
