@@ -105,24 +105,28 @@ class ClockSampler(object):
             self.err = repr(exc)
             self.h = None
 
-    def sample(self, in_region=False):
+    def sample(self, in_region=False, clock_only=False):
         if self.h is None:
             return
         nv = self.nv
         try:
             mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-            why = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-            pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+            why = 0 if clock_only else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            pw = 0.0 if clock_only else nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
         except Exception:
             return
         (self.region if in_region else self.rows).append((mhz, why, pw))
 
-    def poll_until(self, event, in_region=False, pause=0.0005):
-        """Sample while `event` (recorded after the last launch) has not fired."""
+    def poll_until(self, event, in_region=False):
+        """Sample while `event` (recorded after the last launch) has not fired: the SM clock
+        back to back (one NVML call each, so a region of a few milliseconds still gets
+        several readings), throttle reasons and power at both ends."""
         self.sample(in_region)
+        n = 0
         while not event.query():
-            self.sample(in_region)
-            time.sleep(pause)
+            n += 1
+            self.sample(in_region, clock_only=(n % 16 != 0))
+        self.sample(in_region)
 
     def report(self):
         if self.h is None:
@@ -408,6 +412,13 @@ def slab_equals_single(world, rank, dev, nx, kin, sources, use_p2p, n_steps=30, 
             'slab_integrals_rel_err': rel, 'slab_path': e.last_path}
 
 
+def hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))).get('hbm_gbs', 6650.0))
+    except (OSError, ValueError):
+        return 6650.0
+
+
 # -------------------------------------------------------------- timing helper
 def timed_steps(stepper, steps, warmup, world, dev, tmin0=0.0, sampler=None):
     """W warm-up steps, then K timed steps between CUDA events; at N > 1 a tiny all-reduce
@@ -478,7 +489,9 @@ def extra_config(tag, ny, nx, workload, world, rank, dev, halo, steps=10, warmup
     out = {'config': make_config(ny, nx, world, workload, True, use_p2p),
            'value': ny * nx * world / (ms * 1e-3) / 1e9, 'unit': 'Gcell-updates/s',
            'ms_per_step': ms, 'ms_per_step_by_rank': by_rank, 'steps': steps, 'warmup': warmup,
-           'path': eng.last_path, 'roofline_frac': ny * nx * bpc / (ms * 1e-3) / 1e9,
+           'path': eng.last_path, 'algorithmic_bytes_per_cell': bpc,
+           'achieved_gbs_per_gpu': ny * nx * bpc / (ms * 1e-3) / 1e9,
+           'roofline_frac': ny * nx * bpc / (ms * 1e-3) / 1e9 / hbm_peak(),
            'sanity': sanity, 'build_s': round(build_s, 1),
            'hbm_gb_allocated': round(torch.cuda.max_memory_allocated(dev) / 1e9, 1)}
     peer = getattr(stepper, 'peer', None)

@@ -175,6 +175,7 @@ template <int ROWS, int CPL, int WIDTH = 64, int RPW = 1> struct TileCfg {
     static constexpr int cpl = CPL;
     static constexpr int warps = ROWS * wpr;         // consumer warps
     static constexpr int threads = (warps + 1) * 32; // + 1 producer warp
+    static_assert(WIDTH == 64, "peer_push_tile moves 2 columns per lane of one warp");
     static constexpr int szQ = ((QW * QR * 8 + 127) / 128) * 128;
     static constexpr int szD = ((WIDTH * R * 8 + 127) / 128) * 128;   // one fp64 tile
     static constexpr int szF = ((WIDTH * R * 4 + 127) / 128) * 128;   // one 32-bit tile
@@ -401,6 +402,41 @@ __device__ __forceinline__ bool peer_flag_wait(const uint32_t *flag, uint32_t ne
 }
 struct PkMapsB { CUtensorMap D, N, S, w, geo; };
 
+// Peer-memory halo, sending side -- executed by the PRODUCER warp (all 32 lanes), off the
+// consumers' critical path: when the ring slot of boundary tile `t` has been released
+// (every consumer warp has stored its results and arrived on the slot's `empty` barrier:
+// release / acquire at CTA scope), the warp copies the tile's share of the slab's first /
+// last owned row of `src` (the new discharge, or the new pre-zero depth in pass A of the
+// diffusive step) from local memory into the neighbour's halo row over NVLink, makes the
+// stores visible system-wide and counts the tile; the warp that completes the count
+// publishes the step in both neighbours' flag words.
+template <class TC>
+__device__ __forceinline__ void peer_push_tile(const tfb_channels_step_args &a, const PkConsts &k,
+                                               const PkPeer &peer, const double *__restrict__ src,
+                                               int ty, int txi, int lane) {
+    const int c = txi * TC::W + 2 * lane;                  // TC::W = 64 columns: 2 per lane
+    if (c < a.nx) {
+        const bool two = (c + 1 < a.nx);
+        if (ty == 0 && peer.up_Q) {
+            const double *sp = src + c;
+            if (two) *reinterpret_cast<double2 *>(peer.up_Q + c) = __ldcg(reinterpret_cast<const double2 *>(sp));
+            else peer.up_Q[c] = __ldcg(sp);
+        }
+        if (ty == k.tiles_y - 1 && peer.down_Q) {
+            const double *sp = src + (int64_t)(a.ny - 1) * a.pitch + c;
+            if (two) *reinterpret_cast<double2 *>(peer.down_Q + c) = __ldcg(reinterpret_cast<const double2 *>(sp));
+            else peer.down_Q[c] = __ldcg(sp);
+        }
+    }
+    __threadfence_system();                                // my lanes' peer stores are visible
+    __syncwarp();
+    if (lane == 0 && atomicAdd(a.ticket + 1, 1u) == (unsigned)k.n_boundary - 1u) {
+        __threadfence_system();                            // ... and so are the other CTAs' (counted)
+        if (peer.up_flag) *reinterpret_cast<volatile uint32_t *>(peer.up_flag) = peer.value;
+        if (peer.down_flag) *reinterpret_cast<volatile uint32_t *>(peer.down_flag) = peer.value;
+    }
+}
+
 // CTA-level reduction of the per-thread accumulators, per-CTA row, last-CTA fold in
 // CTA order (deterministic).  `mode`: 0 = everything, 1 = sums only (pass A), 2 =
 // status only (pass B).
@@ -447,8 +483,7 @@ __device__ __forceinline__ void pk_finish(const tfb_channels_step_args &a, Acc &
         if (peer.up_flag) *reinterpret_cast<volatile uint32_t *>(peer.up_flag) = kPeerPoison;
         if (peer.down_flag) *reinterpret_cast<volatile uint32_t *>(peer.down_flag) = kPeerPoison;
     }
-    if (peer.up_Q || peer.down_Q) __threadfence_system();   // peer halo stores are visible
-    else __threadfence();
+    __threadfence();          // (peer halo rows were fenced system-wide by peer_push_tile)
     __syncthreads();
     if (tid == 0) {
         const unsigned tk = atomicAdd(a.ticket, 1u);
@@ -512,14 +547,12 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
     __shared__ bool is_last;
     __shared__ volatile int s_fail;
     __shared__ volatile int s_pwait;
-    __shared__ unsigned s_bcount[NS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < p.n_angles * 4; i += kThreads) lut[i] = __ldg(p.angle_lut + i);
     if (tid < kConsumerWarps * kPartialStride) (&sm[0][0])[tid] = 0.0;
     if (tid == 0) {
         s_fail = 0;
         s_pwait = 0;
-        for (int q = 0; q < NS; ++q) s_bcount[q] = 0u;
         for (int s = 0; s < NS; ++s) {
             mbar_init(&full_bar[s], 1u);
             mbar_init(&empty_bar[s], (unsigned)kConsumerWarps);
@@ -540,47 +573,73 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
     const bool use_t = (SRC == PK_SRC_FULL) && k.tair_grid;
 
     if (warp == kConsumerWarps) {
-        // ---------------- producer: one lane streams tiles into the ring -------------
-        if (lane == 0) {
-            int stage = 0;
-            unsigned phase = 0;
-            bool up_ok = false, down_ok = false;
-            const unsigned tx = (unsigned)(TC::nQ + TC::nD * (1 + (kKW ? 1 : 0) + (use_i ? 1 : 0) +
-                                                              (use_h ? 1 : 0) + (use_t ? 1 : 0)) + 2 * TC::nF);
-            for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
-                if (!mbar_wait(&empty_bar[stage], phase ^ 1u)) { s_fail = 1; break; }
+        // ---------------- producer warp: lane 0 streams tiles into the ring; with the
+        // peer-memory halo the whole warp also forwards finished boundary rows -------------
+        int stage = 0;
+        unsigned phase = 0;
+        bool up_ok = false, down_ok = false;
+        const unsigned tx = (unsigned)(TC::nQ + TC::nD * (1 + (kKW ? 1 : 0) + (use_i ? 1 : 0) +
+                                                          (use_h ? 1 : 0) + (use_t ? 1 : 0)) + 2 * TC::nF);
+        const double *push_src = kKW ? a.Q_out : a.d;
+        // PEER: NS extra (load-free) turns drain the boundary tiles still in the ring
+        const int t_end = k.n_tiles + (PEER ? NS * (int)gridDim.x : 0);
+        for (int t = blockIdx.x; t < t_end; t += gridDim.x) {
+            const int t_prev = t - NS * (int)gridDim.x;           // tile that held this slot before
+            const bool push = PEER && t_prev >= 0 && t_prev < k.n_boundary;
+            const bool load = t < k.n_tiles;
+            if (load || push) {
+                int ok = 1;
+                if (lane == 0) ok = mbar_wait(&empty_bar[stage], phase ^ 1u) ? 1 : 0;
+                ok = __shfl_sync(kFull, ok, 0);
+                __syncwarp();                 // lane 0's acquire orders the other lanes' loads too
+                if (!ok) { s_fail = 1; break; }
+            }
+            if (push) {
+                int pty, ptx;
+                tile_of<PEER>(k, t_prev, pty, ptx);
+                peer_push_tile<TC>(a, k, peer, push_src, pty, ptx, lane);
+            }
+            if (load) {
                 int ty, txi;
                 tile_of<PEER>(k, t, ty, txi);
                 if (PEER && t < k.n_boundary) {
                     // peer-memory halo: the first / last tile row reads a row a neighbour
-                    // stored and overwrites (in its memory) a row it may still be reading
-                    if (peer.from_up && ty == 0 && !up_ok) {
-                        s_pwait = 1;
-                        if (!peer_flag_wait(peer.from_up, peer.need)) { s_fail = 1; s_pwait = 0; break; }
-                        s_pwait = 0;
-                        up_ok = true;
+                    // stored and (through peer_push_tile) overwrites, in its memory, a row it
+                    // may still be reading
+                    int ok = 1;
+                    if (lane == 0) {
+                        if (peer.from_up && ty == 0 && !up_ok) {
+                            s_pwait = 1;
+                            ok = peer_flag_wait(peer.from_up, peer.need) ? 1 : 0;
+                            s_pwait = 0;
+                            up_ok = true;
+                        }
+                        if (ok && peer.from_down && ty == k.tiles_y - 1 && !down_ok) {
+                            s_pwait = 1;
+                            ok = peer_flag_wait(peer.from_down, peer.need) ? 1 : 0;
+                            s_pwait = 0;
+                            down_ok = true;
+                        }
                     }
-                    if (peer.from_down && ty == k.tiles_y - 1 && !down_ok) {
-                        s_pwait = 1;
-                        if (!peer_flag_wait(peer.from_down, peer.need)) { s_fail = 1; s_pwait = 0; break; }
-                        s_pwait = 0;
-                        down_ok = true;
-                    }
+                    ok = __shfl_sync(kFull, ok, 0);
+                    if (!ok) { s_fail = 1; break; }
                 }
-                const int c0 = txi * kTW, r0 = ty * kTR;
-                unsigned char *st = smem + (size_t)stage * SL::bytes;
-                mbar_arrive_expect_tx(&full_bar[stage], tx);
-                // tensor rows are counted from the top of the halo'd allocation
-                tma_load_2d(st + SL::oQ, &maps.Q, &full_bar[stage], c0 - 2, r0 - 1 + a.halo);
-                tma_load_2d(st + SL::oVol, &maps.vol, &full_bar[stage], c0, r0 + a.halo);
-                if (kKW) tma_load_2d(st + SL::oCoef, &maps.coef, &full_bar[stage], c0, r0);
-                if (use_i) tma_load_2d(st + SL::oI, &maps.I, &full_bar[stage], c0, r0 + a.halo);
-                if (use_h) tma_load_2d(st + SL::oH, &maps.H, &full_bar[stage], c0, r0 + a.halo);
-                if (use_t) tma_load_2d(st + SL::oT, &maps.T, &full_bar[stage], c0, r0 + a.halo);
-                tma_load_2d(st + SL::oW, &maps.w, &full_bar[stage], c0, r0);
-                tma_load_2d(st + SL::oGeo, &maps.geo, &full_bar[stage], c0, r0);
-                if (++stage == NS) { stage = 0; phase ^= 1u; }
+                if (lane == 0) {
+                    const int c0 = txi * kTW, r0 = ty * kTR;
+                    unsigned char *st = smem + (size_t)stage * SL::bytes;
+                    mbar_arrive_expect_tx(&full_bar[stage], tx);
+                    // tensor rows are counted from the top of the halo'd allocation
+                    tma_load_2d(st + SL::oQ, &maps.Q, &full_bar[stage], c0 - 2, r0 - 1 + a.halo);
+                    tma_load_2d(st + SL::oVol, &maps.vol, &full_bar[stage], c0, r0 + a.halo);
+                    if (kKW) tma_load_2d(st + SL::oCoef, &maps.coef, &full_bar[stage], c0, r0);
+                    if (use_i) tma_load_2d(st + SL::oI, &maps.I, &full_bar[stage], c0, r0 + a.halo);
+                    if (use_h) tma_load_2d(st + SL::oH, &maps.H, &full_bar[stage], c0, r0 + a.halo);
+                    if (use_t) tma_load_2d(st + SL::oT, &maps.T, &full_bar[stage], c0, r0 + a.halo);
+                    tma_load_2d(st + SL::oW, &maps.w, &full_bar[stage], c0, r0);
+                    tma_load_2d(st + SL::oGeo, &maps.geo, &full_bar[stage], c0, r0);
+                }
             }
+            if (++stage == NS) { stage = 0; phase ^= 1u; }
         }
     } else {
         // ---------------- consumers: warp w computes row w of every tile -------------
@@ -627,12 +686,6 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
                                 x.qself, p.outlet_rough, r, c0, acc, rate_max, u, Qn);
                     a.u[i] = u;
                     a.Q_out[i] = Qn;
-                    if (PEER && r == 0 && peer.up_Q) peer.up_Q[c0] = Qn;      // NVLink peer store
-                    if (PEER && r == a.ny - 1 && peer.down_Q) peer.down_Q[c0] = Qn;
-                }
-                if (PEER && !kKW) {          // pass A: the PRE-zero depth goes to the neighbours
-                    if (r == 0 && peer.up_Q) peer.up_Q[c0] = o.d;
-                    if (r == a.ny - 1 && peer.down_Q) peer.down_Q[c0] = o.d;
                 }
                 if (nf) { acc.s[S_VOL_EDGE] += o.v; o.v = 0.0; if (kKW) o.d = 0.0; }   // :2960-2966
                 a.vol_out[i] = o.v;
@@ -710,19 +763,10 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
                 if (kKW) {
                     *reinterpret_cast<double2 *>(a.u + i) = make_double2(u0, u1);
                     *reinterpret_cast<double2 *>(a.Q_out + i) = make_double2(Q0, Q1);
-                    if (PEER && r == 0 && peer.up_Q)                          // NVLink peer stores
-                        *reinterpret_cast<double2 *>(peer.up_Q + c0) = make_double2(Q0, Q1);
-                    if (PEER && r == a.ny - 1 && peer.down_Q)
-                        *reinterpret_cast<double2 *>(peer.down_Q + c0) = make_double2(Q0, Q1);
                 }
                 // update_edge_values :2960-2966 (pass A keeps the PRE-zero depth for the
-                // free-surface slope of pass B, which then zeroes it)
-                if (PEER && !kKW) {          // pass A: the PRE-zero depth goes to the neighbours
-                    if (r == 0 && peer.up_Q)
-                        *reinterpret_cast<double2 *>(peer.up_Q + c0) = make_double2(o0.d, o1.d);
-                    if (r == a.ny - 1 && peer.down_Q)
-                        *reinterpret_cast<double2 *>(peer.down_Q + c0) = make_double2(o0.d, o1.d);
-                }
+                // free-surface slope of pass B, which then zeroes it -- and for the
+                // neighbour slabs, whose halo rows the producer warp fills from it)
                 if (nf0) { acc.s[S_VOL_EDGE] += o0.v; o0.v = 0.0; if (kKW) o0.d = 0.0; }
                 if (nf1) { acc.s[S_VOL_EDGE] += o1.v; o1.v = 0.0; if (kKW) o1.d = 0.0; }
                 *reinterpret_cast<double2 *>(a.vol_out + i) = make_double2(o0.v, o1.v);
@@ -736,21 +780,6 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
                 }
             }
             }
-            }
-            if (PEER && (peer.up_flag || peer.down_flag) && t < k.n_boundary) {
-                // this warp's share of a boundary tile is in the neighbours' halo rows; when
-                // the LAST boundary tile of the grid is complete the neighbours may start
-                // their next step (they no longer wait for the rest of this kernel)
-                __threadfence_system();
-                __syncwarp();
-                if (lane == 0 && atomicAdd(&s_bcount[stage], 1u) == (unsigned)kConsumerWarps - 1u) {
-                    s_bcount[stage] = 0u;
-                    if (atomicAdd(a.ticket + 1, 1u) == (unsigned)k.n_boundary - 1u) {
-                        __threadfence_system();
-                        if (peer.up_flag) *reinterpret_cast<volatile uint32_t *>(peer.up_flag) = peer.value;
-                        if (peer.down_flag) *reinterpret_cast<volatile uint32_t *>(peer.down_flag) = peer.value;
-                    }
-                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[stage]);            // slot may be refilled
@@ -780,14 +809,12 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
     __shared__ bool is_last;
     __shared__ volatile int s_fail;
     __shared__ volatile int s_pwait;
-    __shared__ unsigned s_bcount[NS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < p.n_angles * 4; i += kThreads) lut[i] = __ldg(p.angle_lut + i);
     if (tid < kConsumerWarps * kPartialStride) (&sm[0][0])[tid] = 0.0;
     if (tid == 0) {
         s_fail = 0;
         s_pwait = 0;
-        for (int q = 0; q < NS; ++q) s_bcount[q] = 0u;
         for (int s = 0; s < NS; ++s) {
             mbar_init(&full_bar[s], 1u);
             mbar_init(&empty_bar[s], (unsigned)kConsumerWarps);
@@ -804,39 +831,63 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
     float rate_max = 0.0f;
 
     if (warp == kConsumerWarps) {
-        if (lane == 0) {
-            int stage = 0;
-            unsigned phase = 0;
-            bool up_ok = false, down_ok = false;
-            for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
-                if (!mbar_wait(&empty_bar[stage], phase ^ 1u)) { s_fail = 1; break; }
+        // producer warp (see channels_packed_kernel): lane 0 issues the TMA loads, the whole
+        // warp forwards finished boundary rows of the new discharge to the neighbours
+        int stage = 0;
+        unsigned phase = 0;
+        bool up_ok = false, down_ok = false;
+        const int t_end = k.n_tiles + (PEER ? NS * (int)gridDim.x : 0);
+        for (int t = blockIdx.x; t < t_end; t += gridDim.x) {
+            const int t_prev = t - NS * (int)gridDim.x;
+            const bool push = PEER && t_prev >= 0 && t_prev < k.n_boundary;
+            const bool load = t < k.n_tiles;
+            if (load || push) {
+                int ok = 1;
+                if (lane == 0) ok = mbar_wait(&empty_bar[stage], phase ^ 1u) ? 1 : 0;
+                ok = __shfl_sync(kFull, ok, 0);
+                __syncwarp();                 // lane 0's acquire orders the other lanes' loads too
+                if (!ok) { s_fail = 1; break; }
+            }
+            if (push) {
+                int pty, ptx;
+                tile_of<PEER>(k, t_prev, pty, ptx);
+                peer_push_tile<TC>(a, k, peer, a.Q_out, pty, ptx, lane);
+            }
+            if (load) {
                 int ty, txi;
                 tile_of<PEER>(k, t, ty, txi);
                 if (PEER && t < k.n_boundary) {
                     // the depth halo rows were stored by the neighbours' pass A of this step
-                    if (peer.from_up && ty == 0 && !up_ok) {
-                        s_pwait = 1;
-                        if (!peer_flag_wait(peer.from_up, peer.need)) { s_fail = 1; s_pwait = 0; break; }
-                        s_pwait = 0;
-                        up_ok = true;
+                    int ok = 1;
+                    if (lane == 0) {
+                        if (peer.from_up && ty == 0 && !up_ok) {
+                            s_pwait = 1;
+                            ok = peer_flag_wait(peer.from_up, peer.need) ? 1 : 0;
+                            s_pwait = 0;
+                            up_ok = true;
+                        }
+                        if (ok && peer.from_down && ty == k.tiles_y - 1 && !down_ok) {
+                            s_pwait = 1;
+                            ok = peer_flag_wait(peer.from_down, peer.need) ? 1 : 0;
+                            s_pwait = 0;
+                            down_ok = true;
+                        }
                     }
-                    if (peer.from_down && ty == k.tiles_y - 1 && !down_ok) {
-                        s_pwait = 1;
-                        if (!peer_flag_wait(peer.from_down, peer.need)) { s_fail = 1; s_pwait = 0; break; }
-                        s_pwait = 0;
-                        down_ok = true;
-                    }
+                    ok = __shfl_sync(kFull, ok, 0);
+                    if (!ok) { s_fail = 1; break; }
                 }
-                const int c0 = txi * kTW, r0 = ty * kTR;
-                unsigned char *st = smem + (size_t)stage * SL::bytes;
-                mbar_arrive_expect_tx(&full_bar[stage], (unsigned)SL::tx_bytes);
-                tma_load_2d(st + SL::oD, &maps.D, &full_bar[stage], c0 - 2, r0 - 1 + a.halo);
-                tma_load_2d(st + SL::oN, &maps.N, &full_bar[stage], c0, r0);
-                tma_load_2d(st + SL::oS, &maps.S, &full_bar[stage], c0, r0);
-                tma_load_2d(st + SL::oW, &maps.w, &full_bar[stage], c0, r0);
-                tma_load_2d(st + SL::oGeo, &maps.geo, &full_bar[stage], c0, r0);
-                if (++stage == NS) { stage = 0; phase ^= 1u; }
+                if (lane == 0) {
+                    const int c0 = txi * kTW, r0 = ty * kTR;
+                    unsigned char *st = smem + (size_t)stage * SL::bytes;
+                    mbar_arrive_expect_tx(&full_bar[stage], (unsigned)SL::tx_bytes);
+                    tma_load_2d(st + SL::oD, &maps.D, &full_bar[stage], c0 - 2, r0 - 1 + a.halo);
+                    tma_load_2d(st + SL::oN, &maps.N, &full_bar[stage], c0, r0);
+                    tma_load_2d(st + SL::oS, &maps.S, &full_bar[stage], c0, r0);
+                    tma_load_2d(st + SL::oW, &maps.w, &full_bar[stage], c0, r0);
+                    tma_load_2d(st + SL::oGeo, &maps.geo, &full_bar[stage], c0, r0);
+                }
             }
+            if (++stage == NS) { stage = 0; phase ^= 1u; }
         }
     } else {
         int stage = 0;
@@ -877,8 +928,6 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
                             acc, rate_max, u, Qn);
                 a.u[i] = u;
                 a.Q_out[i] = Qn;
-                if (PEER && r == 0 && peer.up_Q) peer.up_Q[c0] = Qn;      // NVLink peer store
-                if (PEER && r == a.ny - 1 && peer.down_Q) peer.down_Q[c0] = Qn;
             }
             } else {
             const int row = warp / TC::wpr + rr * TC::RP, ct = ((warp % TC::wpr) << 6) + lane * 2;
@@ -918,25 +967,8 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
                 }
                 *reinterpret_cast<double2 *>(a.u + i) = make_double2(uo[0], uo[1]);
                 *reinterpret_cast<double2 *>(a.Q_out + i) = make_double2(Qo[0], Qo[1]);
-                if (PEER && r == 0 && peer.up_Q)
-                    *reinterpret_cast<double2 *>(peer.up_Q + c0) = make_double2(Qo[0], Qo[1]);
-                if (PEER && r == a.ny - 1 && peer.down_Q)
-                    *reinterpret_cast<double2 *>(peer.down_Q + c0) = make_double2(Qo[0], Qo[1]);
             }
             }
-            }
-            if (PEER && (peer.up_flag || peer.down_flag) && t < k.n_boundary) {
-                // as in the main kernel: publish when the LAST boundary tile is complete
-                __threadfence_system();
-                __syncwarp();
-                if (lane == 0 && atomicAdd(&s_bcount[stage], 1u) == (unsigned)kConsumerWarps - 1u) {
-                    s_bcount[stage] = 0u;
-                    if (atomicAdd(a.ticket + 1, 1u) == (unsigned)k.n_boundary - 1u) {
-                        __threadfence_system();
-                        if (peer.up_flag) *reinterpret_cast<volatile uint32_t *>(peer.up_flag) = peer.value;
-                        if (peer.down_flag) *reinterpret_cast<volatile uint32_t *>(peer.down_flag) = peer.value;
-                    }
-                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[stage]);
