@@ -319,15 +319,21 @@ typedef struct {
     /* diffusive wave only (coef may then be NULL): */
     const double *inv_rough;  /* 1 / n                                   (8 B / cell) */
     const float *S32;         /* bed slope as float32 (lossless)         (4 B / cell) */
-    const int64_t *noflow_idx; /* flat indices (owned rows) of the cells with code 0  */
+    const int64_t *noflow_idx; /* flat indices (owned rows, row pitch) of the cells with code 0 */
     int64_t n_noflow;
+    /* extended variants (tfb_channels_step_ext*): */
+    const double *rough64;    /* Manning n, or z0 for the law of the wall  (8 B / cell) */
+    const double *lut_tc;     /* n_angles x 2 doubles: tan, cos of every distinct bank
+                                 angle; geo32 carries a 16-bit index, so up to 65536
+                                 angles (the lean kernels keep their <= 256-entry
+                                 angle_lut in shared memory)                           */
 } tfb_channels_packed;
 
 int64_t tfb_sizeof_channels_packed(void);
 
 /* geo32 of the owned rows from the D8 codes (halo rows readable as in
  * tfb_channels_pack_geo) and a per-cell bank-angle index (owned rows) */
-int tfb_channels_pack_geo32(const uint8_t *code, const uint8_t *angle_idx,
+int tfb_channels_pack_geo32(const uint8_t *code, const uint16_t *angle_idx,
                             int32_t ny, int32_t nx, int32_t halo,
                             uint32_t *geo32, void *stream);
 
@@ -363,6 +369,25 @@ int tfb_channels_step_packed_dw_b(const tfb_channels_step_args *a,
  * :2938 in the reference). */
 int tfb_channels_step_packed_dw_c(const tfb_channels_step_args *a,
                                   const tfb_channels_packed *p, void *stream);
+
+/* ---- extended packed step -----------------------------------------------------
+ * The same TMA-ring kernels for what a COUPLED run delivers and the lean variants
+ * above reject: any of P_rain, SM, GW, MR, ET, IN as (ny, nx) grids that change
+ * every step (update_R, channels_base.py:1548-1655; the provider's ET grid is
+ * masked in place through a->ET_rw, :1625-1627; a->R is written with
+ * TFB_CH_WRITE_R), TFB_CH_LAW_OF_WALL (:4005-4063), TFB_CH_DIAG (all seven
+ * diagnostic grids, + S_free in pass B), up to 65536 distinct bank angles.  Needs
+ * p->S32, p->rough64, p->lut_tc besides geo32 / width32 / row_geom; no fused
+ * sources, flood option or ATTENUATE (those stay with tfb_channels_step).  The
+ * arithmetic keeps the reference's operation order (IEEE divisions), unlike the
+ * lean variants' reciprocal forms.  Diffusive wave: _dw_a, (slab: exchange one row
+ * of d), _dw_b, then tfb_channels_step_packed_dw_c as in the lean path. */
+int tfb_channels_step_ext(const tfb_channels_step_args *a,
+                          const tfb_channels_packed *p, void *stream);
+int tfb_channels_step_ext_dw_a(const tfb_channels_step_args *a,
+                               const tfb_channels_packed *p, void *stream);
+int tfb_channels_step_ext_dw_b(const tfb_channels_step_args *a,
+                               const tfb_channels_packed *p, void *stream);
 
 /* ---- peer-memory halo (NVLink / NVSwitch) ----------------------------------
  * One process per GPU; the slabs' discharge buffers are allocated with

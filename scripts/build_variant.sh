@@ -12,5 +12,5 @@ F=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false 
 /usr/local/cuda/bin/nvcc "${F[@]}" "$@" -c "$src/tfb_channels_packed.cu" -o "/tmp/pk_$name.o"
 /usr/local/cuda/bin/nvcc -shared -gencode arch=compute_100a,code=sm_100a \
   -o "$root/topoflow36_b200/_variants/libtfb_$name.so" "$src/tfb_capi.o" "$src/tfb_channels.o" \
-  "/tmp/pk_$name.o" "$src/tfb_d8.o" "$src/tfb_sources.o" "$src/tfb_prep.o" -lcudart
+  "/tmp/pk_$name.o" "$src/tfb_channels_ext.o" "$src/tfb_d8.o" "$src/tfb_sources.o" "$src/tfb_prep.o" -lcudart
 echo "built $name"

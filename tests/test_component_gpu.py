@@ -67,7 +67,8 @@ def test_treynor_storm_through_the_bmi_component(tmp_path, treynor, treynor_kw, 
         if n in (100, 400):
             assert rel_err(Q_ref, treynor_kw['s%d_Q' % n]) <= RTOL
     assert n == 1200 and c.time_index == 1200
-    assert c.engine.last_path == ('generic' if diag else 'packed')
+    assert c.engine.last_path == 'packed'
+    assert c.engine.last_kernel == ('ext' if diag else 'lean')
     assert abs(float(c.time_min) - 120.0) < 1e-9
     assert worst <= RTOL, worst
     for g in ('vol', 'd', 'u', 'Q') + (('Rh', 'A_wet', 'P_wet', 'f', 'tau', 'u_star', 'froude')

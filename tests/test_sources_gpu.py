@@ -139,7 +139,8 @@ def test_unfused_coupling_on_device_equals_fused(sources_gold):
             eng.set_input(n, t)                      # CUDA tensors: bound in place
         eng.step(time_min=i * dt / 60.0)
         fused.step(time_min=i * dt / 60.0)
-    assert fused.last_path == 'packed' and eng.last_path == 'generic'
+    # fused: lean packed kernel; un-fused (four forcing grids from device providers): extended one
+    assert fused.last_kernel == 'lean' and eng.last_kernel == 'ext'
     for a, b in ((eng.vol, fused.vol), (eng.own(eng.d), fused.own(fused.d)),
                  (eng.own(eng.u), fused.own(fused.u)), (eng.Q, fused.Q),
                  (infil.I, fused.I), (snow.h_swe, fused.h_swe)):

@@ -36,6 +36,17 @@ def apply_sources(eng, mode, row0=0, halo=0, seed=1234):
     eng.set_input('P_rain', RAIN_50MMPH)
     if mode == 'none':
         return
+    if mode == 'grid':
+        # what a coupled run delivers: infiltration and evaporation rates as (ny, nx) grids
+        # (keyed by the GLOBAL cell); they ride the extended packed kernels
+        ny, nx = eng.ny, eng.nx
+        dev = eng.device
+        ri = torch.arange(row0 - halo, row0 + ny + halo, device=dev, dtype=torch.int64)[:, None]
+        ci = torch.arange(nx, device=dev, dtype=torch.int64)[None, :]
+        for name, amp, sd in (('IN', 4e-6, 31), ('ET', 1e-7, 37)):
+            g = amp * _hash01(ri, ci, seed + sd)
+            eng.set_input(name, g if halo else g.contiguous())
+        return
     if mode == 'ga':
         eng.enable_fused_sources(infil=True, I0=I0_WET)
     else:

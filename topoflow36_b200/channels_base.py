@@ -635,7 +635,7 @@ class channels_component(BMI_base.BMI_component):
         if self._et_host is not None:
             # provider's ET array is masked in place (channels_base.py:1625-1627)
             import torch
-            torch.from_numpy(self._et_host).copy_(self.engine.own(self.engine.src['ET']))
+            self.engine.download('ET', self.engine.own(self.engine.src['ET']), self._et_host)
             if self.layout is not None and not self.KINEMATIC_WAVE:
                 from .slab import exchange_halos
                 exchange_halos([self.engine.src['ET']], self.layout, [1], self.group)

@@ -9,9 +9,9 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17
        -Xcompiler -fPIC -Xcompiler -O2)
 objs=()
 pids=()
-for f in tfb_capi tfb_channels tfb_channels_packed tfb_d8 tfb_sources tfb_prep; do
+for f in tfb_capi tfb_channels tfb_channels_packed tfb_channels_ext tfb_d8 tfb_sources tfb_prep; do
   if [ ! -f "$here/$f.o" ] || [ "$here/$f.cu" -nt "$here/$f.o" ] || \
-     [ "$here/tfb_common.cuh" -nt "$here/$f.o" ] || [ "$here/tfb_channels_common.cuh" -nt "$here/$f.o" ] || [ "$here/../../include/tfb.h" -nt "$here/$f.o" ]; then
+     [ "$here/tfb_common.cuh" -nt "$here/$f.o" ] || [ "$here/tfb_channels_common.cuh" -nt "$here/$f.o" ] || [ "$here/tfb_pk.cuh" -nt "$here/$f.o" ] || [ "$here/../../include/tfb.h" -nt "$here/$f.o" ]; then
     rm -f "$here/$f.o"       # a failed compile must not leave a stale object to link
     "$NVCC" "${FLAGS[@]}" ${TFB_EXTRA_NVCC_FLAGS:-} -c "$here/$f.cu" -o "$here/$f.o" &
     pids+=($!)

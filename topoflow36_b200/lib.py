@@ -111,7 +111,8 @@ class ChannelsPacked(C.Structure):
     """tfb_channels_packed: compact static inputs of the packed fast path."""
     _fields_ = [('geo32', vp), ('width32', vp), ('coef', vp), ('angle_lut', vp),
                 ('row_geom', vp), ('outlet_rough', C.c_double), ('n_angles', C.c_int32),
-                ('inv_rough', vp), ('S32', vp), ('noflow_idx', vp), ('n_noflow', C.c_int64)]
+                ('inv_rough', vp), ('S32', vp), ('noflow_idx', vp), ('n_noflow', C.c_int64),
+                ('rough64', vp), ('lut_tc', vp)]
 
 
 _i32, _i64, _f32, _f64 = C.c_int32, C.c_int64, C.c_float, C.c_double
@@ -156,6 +157,11 @@ SIGNATURES = {
                                            C.POINTER(ChannelsPacked), vp]),
     'tfb_channels_step_packed_dw_a': (C.c_int, [C.POINTER(ChannelsStepArgs),
                                                 C.POINTER(ChannelsPacked), vp]),
+    'tfb_channels_step_ext': (C.c_int, [C.POINTER(ChannelsStepArgs), C.POINTER(ChannelsPacked), vp]),
+    'tfb_channels_step_ext_dw_a': (C.c_int, [C.POINTER(ChannelsStepArgs),
+                                             C.POINTER(ChannelsPacked), vp]),
+    'tfb_channels_step_ext_dw_b': (C.c_int, [C.POINTER(ChannelsStepArgs),
+                                             C.POINTER(ChannelsPacked), vp]),
     'tfb_channels_step_packed_dw_b': (C.c_int, [C.POINTER(ChannelsStepArgs),
                                                 C.POINTER(ChannelsPacked), vp]),
     'tfb_sizeof_peer_halo': (_i64, []),

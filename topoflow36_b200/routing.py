@@ -158,6 +158,7 @@ class ChannelsEngine(object):
             a.R = self._p(self.R)
         # ---- sources default to scalar zeros --------------------------------
         self.src = {}
+        self._src_buf, self._stage_buf, self._registered, self._seen = {}, {}, {}, {}
         for n in _SRC_SG:
             self.set_input(n, 0.0)
         self.h_swe_buf = self.I_buf = None
@@ -186,6 +187,8 @@ class ChannelsEngine(object):
         if self.flood:
             self._init_flood(d_bankfull, flood_manning_n, width_ratio)
         self.packed = None
+        self.lean_ok = self.ext_ok = False
+        self.last_path = self.last_kernel = None
         self._scalars_dirty = False
         self.mid_step_hook = None
         self.use_packed = bool(packed)
@@ -229,15 +232,21 @@ class ChannelsEngine(object):
 
     # ------------------------------------------------------------ packed path
     def _try_pack(self):
-        """Build the compact static inputs of tfb_channels_step_packed when the
-        configuration allows it (Manning, no diagnostics, scalar sinuosity, float32-exact
-        widths, <= 256 distinct bank angles).  Everything is lossless; otherwise the
-        generic kernel runs.  Every per-cell array is (ny, pitch) like the state."""
+        """Build the compact static inputs of the packed (TMA ring) kernels once, when the
+        configuration allows it: scalar sinuosity, float32-exact widths, at most 65536
+        distinct bank angles, no flood option / ATTENUATE.  Everything is lossless and
+        every per-cell array is (ny, pitch) like the state.  Two families share them:
+
+          lean  tfb_channels_step_packed*: Manning, no per-step diagnostics, scalar forcing,
+                optionally fused sources; <= 256 angles (table in shared memory); kinematic
+                wave: coef = sqrt|S_bed| / n, diffusive: 1 / n and the float32 bed slope
+          ext   tfb_channels_step_ext*: grid forcing, law of the wall, diagnostics, R grid;
+                float32 bed slope + roughness (n or z0) + a {tan, cos} table in L2
+
+        Otherwise the generic kernel (tfb_channels_step) runs."""
         a = self.args
-        if ((not self.manning) or self.diag or self.flood or self.attenuate
-                or (self.flags & L.CH_WRITE_R)):
-            return
-        if self.sinu_grid is not None:
+        self.lean_ok = self.ext_ok = False
+        if self.flood or self.attenuate or self.sinu_grid is not None:
             return
         dev = self.device
 
@@ -266,27 +275,33 @@ class ChannelsEngine(object):
             key = torch.stack((tan.reshape(-1), cos.reshape(-1)), dim=1)
             uniq, inv = torch.unique(key, dim=0, return_inverse=True)
             del key, tan, cos
-            if uniq.shape[0] > 256:
+            if uniq.shape[0] > 65536:
                 return
+        n_angles = int(uniq.shape[0])
         t, c = uniq[:, 0], uniq[:, 1]
-        lut = torch.zeros((uniq.shape[0], 4), dtype=torch.float64, device=dev)
+        lut = torch.zeros((max(n_angles, 1), 4), dtype=torch.float64, device=dev)
         lut[:, 0] = t
         lut[:, 1] = torch.where(t == 0, torch.zeros_like(t), 1.0 / (2.0 * t))
         lut[:, 2] = 1.0 / c
         lut[:, 3] = 2.0 * (2.0 * t)
+        lut_tc = uniq.contiguous()                        # {tan, cos} as the reference uses them
         aidx = (None if inv is None
-                else padc(inv.to(torch.uint8).reshape(self.ny, self.nx)))
+                else padc(inv.to(torch.int16).reshape(self.ny, self.nx)))   # 16-bit pattern
         rough = full(self.rough_grid, a.rough.val)
-        coef = inv_rough = S32 = None
-        if self.kinematic:
-            coef = padc(self.own(self.sqrtS) / rough)
-        else:
-            S = self.own(self.S_bed)
-            S32 = S.float()
-            if not bool((S32.double() == S).all()):
-                return
-            S32 = padc(S32)
-            inv_rough = padc(1.0 / rough)
+        # the bed slope as float32 (RTG precision): lossless unless sinuosity != 1 rescaled it
+        S = self.own(self.S_bed)
+        S32 = S.float()
+        s32_ok = bool((S32.double() == S).all())
+        S32 = padc(S32) if s32_ok else None
+        coef = inv_rough = None
+        if self.manning:
+            if self.kinematic:
+                sq = self.own(self.sqrtS) if getattr(self, 'sqrtS', None) is not None \
+                    else torch.sqrt(torch.abs(S))
+                coef = padc(sq / rough)
+            elif s32_ok:
+                inv_rough = padc(1.0 / rough)
+        rough64 = padc(rough) if s32_ok else None
         geo32 = torch.empty((self.ny, self.pitch), dtype=torch.int32, device=dev)
         L.check(self.lib.tfb_channels_pack_geo32(self._p(self.code),
                                                  None if aidx is None else aidx.data_ptr(), self.ny,
@@ -309,8 +324,9 @@ class ChannelsEngine(object):
         pk.coef = None if coef is None else coef.data_ptr()
         pk.inv_rough = None if inv_rough is None else inv_rough.data_ptr()
         pk.S32 = None if S32 is None else S32.data_ptr()
-        pk.angle_lut, pk.row_geom = lut.data_ptr(), rowg.data_ptr()
-        pk.outlet_rough, pk.n_angles = n_out, int(uniq.shape[0])
+        pk.rough64 = None if rough64 is None else rough64.data_ptr()
+        pk.angle_lut, pk.row_geom, pk.lut_tc = lut.data_ptr(), rowg.data_ptr(), lut_tc.data_ptr()
+        pk.outlet_rough, pk.n_angles = n_out, n_angles
         nf = None
         if not self.kinematic:
             # noflow cells of the owned rows, as flat indices relative to the first owned row
@@ -318,8 +334,11 @@ class ChannelsEngine(object):
             nf = torch.nonzero(self.code[self.halo:self.halo + self.ny].reshape(-1) == 0) \
                 .reshape(-1).contiguous()
             pk.noflow_idx, pk.n_noflow = nf.data_ptr(), int(nf.numel())
-        self._pack_keep = (geo32, w32, coef, inv_rough, S32, lut, rowg, nf)
+        self._pack_keep = (geo32, w32, coef, inv_rough, S32, rough64, lut, lut_tc, rowg, nf, aidx)
         self.packed = pk
+        self.lean_ok = (self.manning and n_angles <= 256
+                        and (coef is not None if self.kinematic else inv_rough is not None))
+        self.ext_ok = s32_ok
 
     def release_generic_inputs(self):
         """Free the fp64 static grids the packed path does not read (width, tan,
@@ -337,17 +356,25 @@ class ChannelsEngine(object):
         self.generic_released = True
 
     def _packed_ok(self):
-        """Per-step eligibility: uniform forcing, at most scalar Green-Ampt fused."""
+        """Which packed family takes this step: 'lean' (the benchmarked production kernels),
+        'ext' (grid forcing / law of the wall / diagnostics / R grid), or None (generic
+        kernel: flood option, ATTENUATE, grid sinuosity, fused sources with grid parameters)."""
         if self.packed is None or not self.use_packed:
-            return False
+            return None
         src = self.flags & (L.CH_SRC_MET | L.CH_SRC_SNOW | L.CH_SRC_EVAP | L.CH_SRC_INFIL)
-        # fused sources with scalar parameters; only T_air may be a grid (set_input
-        # gives it the slab's halo layout)
-        if any(isinstance(self.src[n], torch.Tensor) for n in _SRC_SG if n != 'T_air'):
-            return False
-        if (src & L.CH_SRC_INFIL) and self.args.h_table.val >= self.args.elev.val:
-            return False
-        return True
+        grid_forcing = any(isinstance(self.src[n], torch.Tensor)
+                           for n in ('P_rain', 'SM', 'GW', 'MR', 'ET', 'IN'))
+        plain = not (self.diag or (self.flags & L.CH_WRITE_R) or not self.manning)
+        if self.lean_ok and plain and not grid_forcing:
+            # fused sources with scalar parameters; only T_air may be a grid
+            if any(isinstance(self.src[n], torch.Tensor) for n in _SRC_SG if n != 'T_air'):
+                return None
+            if (src & L.CH_SRC_INFIL) and self.args.h_table.val >= self.args.elev.val:
+                return None
+            return 'lean'
+        if self.ext_ok and not src:
+            return 'ext'
+        return None
 
     # ------------------------------------------------------------ allocation
     def _zeros(self, dtype):
@@ -413,13 +440,17 @@ class ChannelsEngine(object):
                 t = val
                 sgv = L.SG(t.data_ptr(), 0.0)
             else:
-                t = self.src.get(name)
-                if (not isinstance(t, torch.Tensor)
-                        or t.shape[0] != self.ny + 2 * self.halo):
-                    t = self._zeros(torch.float64)
-                src = torch.as_tensor(val) if not isinstance(val, torch.Tensor) else val
-                src = src.to(dtype=torch.float64, device=self.device)
-                (t[:, :self.nx] if (src.shape[0] == t.shape[0] and self.halo) else self.own(t)).copy_(src)
+                t = self._src_buf.get(name)          # a device buffer of OURS, kept across steps
+                if t is None:
+                    t = self._src_buf[name] = self._zeros(torch.float64)
+                haloed = bool(self.halo) and val.shape[0] == t.shape[0]
+                dst = t[:, :self.nx] if haloed else self.own(t)
+                if (isinstance(val, np.ndarray) and val.dtype == np.float64
+                        and val.flags.c_contiguous and val.nbytes >= self.PIN_MIN_BYTES):
+                    self._upload(name, val, dst)
+                else:
+                    src = torch.as_tensor(val) if not isinstance(val, torch.Tensor) else val
+                    dst.copy_(src.to(dtype=torch.float64, device=self.device))
                 sgv = L.SG(self._p(t), 0.0)
             self.src[name] = t
         else:
@@ -429,6 +460,92 @@ class ChannelsEngine(object):
         setattr(self.args, name, sgv)
         if name == 'ET':
             self.args.ET_rw = sgv.ptr
+
+    # ---- host grids: pinned transfers ---------------------------------------------------
+    # A coupled run hands the component (ny, nx) float64 numpy grids every step (EMELI's
+    # set_value, time_interpolation.py:653-670).  A pageable cudaMemcpy moves them at ~10 GB/s
+    # (measured on the B200 box: 13 ms per 4096^2 grid); here a grid goes through a pinned
+    # staging buffer (multi-threaded host copy + DMA at ~54 GB/s: ~5.4 ms), and an array that
+    # comes back at the same address -- providers that update their grids in place -- is
+    # page-locked where it lies (cudaHostRegister, once) and moved by DMA alone (2.5 ms).
+    PIN_MIN_BYTES = 1 << 20
+    PIN_PROVIDER_ARRAYS = True
+
+    def _stage(self, name):
+        st = self._stage_buf.get(name)
+        if st is None:
+            st = self._stage_buf[name] = [torch.empty((self.ny + 2 * self.halo, self.nx),
+                                                      dtype=torch.float64).pin_memory(), None]
+        if st[1] is not None:
+            st[1].synchronize()                    # the DMA that last used this buffer is done
+            st[1] = None
+        return st
+
+    def _is_registered(self, arr):
+        return self._registered.get(arr.ctypes.data) == arr.nbytes
+
+    def _maybe_register(self, arr):
+        """Page-lock a provider's array in place on its second sighting; unregistered again
+        when numpy frees it."""
+        ptr, nb = arr.ctypes.data, arr.nbytes
+        if self._registered.get(ptr) == nb:
+            return True
+        if not self.PIN_PROVIDER_ARRAYS or self._registered.get(ptr) == -1:
+            return False
+        n = self._seen.get(ptr, 0) + 1
+        if len(self._seen) > 64:
+            self._seen.clear()
+        self._seen[ptr] = n
+        if n < 2:
+            return False
+        rt = torch.cuda.cudart()
+        if int(rt.cudaHostRegister(ptr, nb, 0)) != 0:
+            self._registered[ptr] = -1             # not page-lockable: staging buffer from now on
+            return False
+        self._registered[ptr] = nb
+        import weakref
+        reg = self._registered
+
+        def _release(p=ptr):
+            if reg.pop(p, None) not in (None, -1):
+                rt.cudaHostUnregister(p)
+        base = arr
+        while isinstance(getattr(base, 'base', None), np.ndarray):
+            base = base.base                       # the object that owns the memory
+        try:
+            weakref.finalize(base, _release)
+        except TypeError:
+            pass
+        return True
+
+    def _upload(self, name, arr, dst):
+        """numpy (rows, nx) float64 -> device view `dst`, asynchronously on the current stream."""
+        if self._maybe_register(arr):
+            dst.copy_(torch.from_numpy(arr), non_blocking=True)
+            return
+        st = self._stage(name)
+        h = st[0][:arr.shape[0]]
+        h.copy_(torch.from_numpy(arr))             # host copy into pinned memory
+        dst.copy_(h, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        st[1] = ev
+
+    def download(self, name, src, arr):
+        """Device view `src` -> the provider's numpy array (in-place ET masking,
+        channels_base.py:1625-1627).  Returns after the data has landed."""
+        if (arr.dtype == np.float64 and arr.flags.c_contiguous and arr.nbytes >= self.PIN_MIN_BYTES):
+            if self._is_registered(arr):
+                torch.from_numpy(arr).copy_(src, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                return
+            st = self._stage(name)
+            h = st[0][:arr.shape[0]]
+            h.copy_(src, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            torch.from_numpy(arr).copy_(h)
+            return
+        torch.from_numpy(arr).copy_(src)
 
     def enable_fused_sources(self, met=False, snow=False, evap=False, infil=False,
                              T_rain_snow=0.0, rho_snow=300.0, alpha=1.26,
@@ -573,7 +690,26 @@ class ChannelsEngine(object):
             dbl = buf[1] is not None
             setattr(a, name, self._p(buf[self.scur if dbl else 0]))
             setattr(a, name + '_out', self._p(buf[self.scur ^ 1 if dbl else 0]))
-        if self._packed_ok():
+        path = self._packed_ok()
+        if path == 'ext':
+            if peer is not None:
+                raise L.TfbError('the peer-memory halo needs the lean packed step')
+            if self.kinematic:
+                L.check(self.lib.tfb_channels_step_ext(C.byref(a), C.byref(self.packed),
+                                                       L.stream_ptr()), 'tfb_channels_step_ext')
+            else:
+                L.check(self.lib.tfb_channels_step_ext_dw_a(
+                    C.byref(a), C.byref(self.packed), L.stream_ptr()), 'tfb_channels_step_ext_dw_a')
+                if self.mid_step_hook is not None:
+                    self.mid_step_hook()
+                L.check(self.lib.tfb_channels_step_ext_dw_b(
+                    C.byref(a), C.byref(self.packed), L.stream_ptr()), 'tfb_channels_step_ext_dw_b')
+                L.check(self.lib.tfb_channels_step_packed_dw_c(
+                    C.byref(a), C.byref(self.packed), L.stream_ptr()), 'tfb_channels_step_packed_dw_c')
+            self.last_path = 'packed'
+            self.last_kernel = 'ext'
+        elif path == 'lean':
+            self.last_kernel = 'lean'
             if self.kinematic and peer is not None:
                 ps = self.n_steps if peer_step is None else int(peer_step)
                 ph = peer.descriptor(self.qcur ^ 1, ps)
@@ -617,6 +753,7 @@ class ChannelsEngine(object):
                                  'inputs were released (release_generic_inputs)')
             L.check(self.lib.tfb_channels_step(C.byref(a), L.stream_ptr()), 'tfb_channels_step')
             self.last_path = 'generic'
+            self.last_kernel = 'generic'
         self.qcur ^= 1
         self.scur ^= 1
         self.n_steps += 1

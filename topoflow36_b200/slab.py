@@ -277,7 +277,7 @@ class SlabChannels(object):
     def step(self, time_min=0.0):
         e = self.engine
         packed = e._packed_ok()
-        if self.peer is not None and packed:
+        if self.peer is not None and packed == 'lean':
             # halo rows travel inside the kernel(s); the flag words count PEER steps only,
             # so NCCL steps in between (below) leave the protocol in step
             e.step(time_min, peer=self.peer, peer_step=self.n_peer_steps)
@@ -291,7 +291,7 @@ class SlabChannels(object):
             self.exchange_state()
             self._state_halos_stale = False
         e.step(time_min)
-        self.exchange_state(discharge_only=packed)
+        self.exchange_state(discharge_only=bool(packed))
         if packed and not e.kinematic:
             self._state_halos_stale = True
 
