@@ -110,6 +110,27 @@ int tfb_d8_area(const uint8_t *code, int32_t ny, int32_t nx, double pixel_area,
                 const double *pixel_area_row, float *A, int64_t *count,
                 int32_t *pending, int64_t *n_done, void *stream);
 
+/* Row-slab form of tfb_d8_area (one process per GPU; d8_global.update_area_grid
+ * :1029-1332 on a grid sharded by rows).  `code`, `cell` (uint64 words {fp32 area,
+ * uint32 count}) and `word` (int32 scratch) point at the first OWNED row of arrays
+ * that carry ONE halo row above and below.  _init clears the words and analyses the
+ * slab; _walk with resume = 0 runs the topological walk from the slab's own source
+ * cells -- a walker stops where its next cell belongs to a neighbour; the caller then
+ * exchanges the boundary rows of `cell` into the neighbours' halo rows (2 x nx x 8 B)
+ * and calls _walk with resume = 1, which lets every halo cell whose word has arrived
+ * continue into this slab; repeat until no boundary row changes on any rank.
+ * tfb_d8_area_unpack splits the words of n cells into A (float32) and count (int64,
+ * may be NULL); n_done (HOST, may be NULL) = cells that received an area.  Areas and
+ * counts are bit-identical to the single-GPU pass. */
+int tfb_d8_area_slab_init(const uint8_t *code, int32_t ny, int32_t nx, int32_t row0,
+                          int32_t ny_global, uint64_t *cell, int32_t *word,
+                          void *stream);
+int tfb_d8_area_slab_walk(int32_t ny, int32_t nx, double pixel_area,
+                          const double *pixel_area_row, uint64_t *cell,
+                          const int32_t *word, int32_t resume, void *stream);
+int tfb_d8_area_unpack(const uint64_t *cell, int64_t n, float *A, int64_t *count,
+                       int64_t *n_done, void *stream);
+
 /* S = (DEM - DEM[parent]) / ds in fp32, 0 at noflow cells
  * (d8_global.update_slope_grid :1334-1348). */
 int tfb_d8_slope(const float *dem, const uint8_t *code, const float *dx,

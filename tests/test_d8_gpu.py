@@ -101,3 +101,70 @@ def test_d8_2048_bit_exact_vs_c_oracle_and_exact_properties():
     acc.index_add_(0, pid[flow], cnt[flow])
     has_area = tk.A.reshape(-1) > 0
     assert torch.equal(cnt[has_area], (acc + 1)[has_area])
+
+
+@pytest.mark.parametrize('n_slabs', [1, 2, 3, 5])
+def test_area_across_row_slabs_equals_one_grid(n_slabs):
+    """The row-slab form of the contributing-area pass (tfb_d8_area_slab_*: walkers stop at a
+    slab boundary, the {area, count} words of the boundary rows are exchanged, the walk
+    resumes on the other side) driven for `n_slabs` virtual ranks on ONE device -- the halo
+    exchange of slab.slab_d8_area is replaced by row copies -- against the single-grid pass:
+    areas (fp32) and counts bit for bit, on a pit-filled DEM whose rivers cross every
+    boundary."""
+    import ctypes as C
+    import torch
+    from topoflow36_b200 import lib as L, prep, synth
+    from topoflow36_b200.d8 import D8Toolkit
+    lib = L.load()
+    ny, nx = 301, 257
+    DEM = synth.fractal_dem(ny, nx, seed=21, sigma=1.5, sy=0.004, sx=0.001)
+    t = torch.as_tensor(DEM).cuda()
+    prep.fill_pits_tensor(t)                       # long flow paths, large basins
+    tk = D8Toolkit(t.cpu().numpy())
+    tk.update(with_counts=True)
+    code = tk.code
+    pa = float(tk.pixel_area)
+    bounds = [round(k * ny / n_slabs) for k in range(n_slabs + 1)]
+    st = L.stream_ptr
+    slabs = []
+    for k in range(n_slabs):
+        r0, r1 = bounds[k], bounds[k + 1]
+        n = r1 - r0
+        c1 = torch.zeros((n + 2, nx), dtype=torch.uint8, device='cuda')
+        lo, hi = max(r0 - 1, 0), min(r1 + 1, ny)
+        c1[lo - (r0 - 1):hi - (r0 - 1)] = code[lo:hi]
+        cell = torch.zeros((n + 2, nx), dtype=torch.int64, device='cuda')
+        word = torch.zeros((n + 2, nx), dtype=torch.int32, device='cuda')
+        own = lambda x: x.data_ptr() + nx * x.element_size()
+        L.check(lib.tfb_d8_area_slab_init(own(c1), n, nx, r0, ny, own(cell), own(word), st()))
+        L.check(lib.tfb_d8_area_slab_walk(n, nx, pa, None, own(cell), own(word), 0, st()))
+        slabs.append(dict(n=n, r0=r0, cell=cell, word=word, c1=c1, own=own))
+    rounds = 0
+    sent = None
+    while True:
+        edge = torch.cat([torch.stack((s['cell'][1], s['cell'][s['n']])) for s in slabs])
+        if sent is not None and torch.equal(edge, sent):
+            break
+        sent = edge
+        for k, s in enumerate(slabs):              # the halo exchange
+            if k > 0:
+                s['cell'][0].copy_(slabs[k - 1]['cell'][slabs[k - 1]['n']])
+            if k < n_slabs - 1:
+                s['cell'][s['n'] + 1].copy_(slabs[k + 1]['cell'][1])
+        for s in slabs:
+            L.check(lib.tfb_d8_area_slab_walk(s['n'], nx, pa, None, s['own'](s['cell']),
+                                              s['own'](s['word']), 1, st()))
+        rounds += 1
+        assert rounds < 200
+    A = torch.empty((ny, nx), dtype=torch.float32, device='cuda')
+    cnt = torch.empty((ny, nx), dtype=torch.int64, device='cuda')
+    for s in slabs:
+        nd = C.c_int64(0)
+        a_, c_ = A[s['r0']:s['r0'] + s['n']], cnt[s['r0']:s['r0'] + s['n']]
+        L.check(lib.tfb_d8_area_unpack(s['own'](s['cell']), s['n'] * nx, a_.data_ptr(), c_.data_ptr(),
+                                       C.byref(nd), st()))
+    assert torch.equal(A, tk.A), int((A != tk.A).sum())
+    assert torch.equal(cnt, tk.count)
+    assert int(cnt.max()) > 2000                   # real rivers
+    if n_slabs > 1:
+        assert rounds >= 2                         # flow really crossed the boundaries

@@ -52,6 +52,15 @@ def _worker(rank, world, port, kinematic, infil, q, devgen=False, p2p=False, d0=
             fails.append('code (%d cells differ)' % int((slab.engine.own(slab.engine.code) != one.code[rows]).sum()))
         if not torch.equal(slab.engine.own(slab.engine.S_bed), one.S_bed[rows]):
             fails.append('S_bed')
+        if not devgen:
+            # contributing area across the slab boundary == single grid, bit for bit
+            from topoflow36_b200.slab import SlabLayout, slab_d8_area
+            A, cnt, rounds = slab_d8_area(parts['d8']['code'], lay, 900.0 / 1e6)
+            A1, cnt1, _ = slab_d8_area(one.own(one.code).contiguous(),
+                                       SlabLayout(ny * world, nx, 0, 1, 0), 900.0 / 1e6)
+            if not (torch.equal(A, A1[rows]) and torch.equal(cnt, cnt1[rows])):
+                fails.append('D8 area across slabs (%d cells differ, %d rounds)'
+                             % (int((cnt != cnt1[rows]).sum()), rounds))
         for i in range(steps):
             if i == 80:
                 slab.engine.set_input('P_rain', 0.0)

@@ -1,6 +1,7 @@
-"""The device-aware time interpolator (topoflow36_b200/time_interpolation.py)
-against the reference's framework/time_interpolation.py driven with identical mock
-providers (CPU, needs the reference tree), and its CUDA path against its numpy path."""
+"""The device-aware time interpolator (topoflow36_b200/time_interpolation.py, SURVEY 8f-4:
+subclasses of the reference's framework/time_interpolation.py classes) against the
+reference's own, driven with identical mock providers (CPU), and its CUDA path against
+its numpy path."""
 import os
 import sys
 
@@ -83,7 +84,17 @@ def test_interpolator_equals_the_reference(method, units):
         assert np.array_equal(got[0][2], got[1][2])          # Z: in-place provider -> step
 
 
+def _ref_or_skip():
+    """The device-aware classes subclass the reference's: it must be importable (the live
+    tree here, the staged oracle/_ref archive on the GPU box)."""
+    from oracle import ref_harness as rh
+    if not rh.reference_available():
+        pytest.skip('reference not available (make -C oracle _ref)')
+    rh.import_reference()
+
+
 def test_interpolation_hits_the_end_points():
+    _ref_or_skip()
     from topoflow36_b200 import time_interpolation as ours
     d = ours.time_interp_data(v1=np.array([[1.0, 2.0]]), t1=np.float64(0), long_var_name='x')
     d.update(np.array([[3.0, 6.0]]), np.float64(10.0))
@@ -100,6 +111,7 @@ def test_interpolation_hits_the_end_points():
 @pytest.mark.gpu
 def test_device_values_equal_host_values():
     import torch
+    _ref_or_skip()
     from topoflow36_b200 import time_interpolation as ours
     prov = _Provider(shape=(33, 41))
     ti = ours.time_interpolator({'met': prov}, ['met'], {'met': ['P', 'S', 'Z', 'T']}, 'Linear')

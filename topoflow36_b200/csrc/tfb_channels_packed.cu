@@ -108,136 +108,154 @@ struct PkIn { unsigned g; double vol, I, h, Ta, w, qself, ch[8]; };
 
 struct PkVD { double v, d, I, h; };    // new volume / depth before the noflow zeroing, new state
 
+// IEEE results for the operands the Newton primitives cannot take, chosen by SELECTS:
+// a / 0 = +-inf (NaN for 0 / 0), a / +-inf = +-0 (NaN for inf / inf); NaN operands go
+// through div_nr as NaN.  sqrt: 0 -> 0, +inf -> +inf, NaN -> NaN.
+__device__ __forceinline__ double div_sel(double a, double b) {
+    double q = div_nr(a, b);
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    if (b == 0.0) q = a * inf;
+    if (fabs(b) == inf) q = a * 0.0;
+    return q;
+}
+__device__ __forceinline__ double sqrt_sel(double x) {
+    const double r = sqrt_nr(x);
+    return (x > 0.0 && x <= 1.7976931348623157e308) ? r : x;
+}
+// x^(2/3) for any x >= 0 without a branch: values below 1e-30 are scaled by 2^300 (exact)
+// into the range of the float seed and the result scaled back by 2^-200
+__device__ __forceinline__ double pow23_sel(double x) {
+    const bool tiny = x < 1.0e-30;
+    const double xs = x * (tiny ? 2.037035976334486e90 : 1.0);           // 2^300
+    return pow23_nb(xs) * (tiny ? 6.223015277861142e-61 : 1.0);           // 2^-200
+}
+
 // new volume and depth of one cell: update_R :1548, update_flow_volume :1951,
-// update_channel_depth :2250 (+ the fused source terms in front of them)
+// update_channel_depth :2250 (+ the fused source terms in front of them).  STRAIGHT-LINE
+// code (selects, predicated adds, the Newton primitives of tfb_common.cuh): the calls for
+// the two cells a lane advances land in ONE basic block, so ptxas interleaves their
+// dependent fp64 chains.
 template <int SRC>
 __device__ __forceinline__ void pk_vol_depth(const PkConsts &k, const double *__restrict__ lut,
-                                             const PkIn &x, const double2 g0, const double2 g1,
-                                             const double2 g2, const double da, Acc &acc,
-                                             PkVD &o) {
-    const unsigned code = x.g & 0xffu, cmask = (x.g >> 8) & 0xffu, ai = (x.g >> 16) & 0xffu;
-    // row_geom = {ds_ew, ds_diag, ds_ns, 1/ds_ew, 1/ds_diag, 1/ds_ns}
-    const bool dg = (code & 0x55u) != 0u, ns = (code & 0x88u) != 0u;
-    const double ds = dg ? g0.y : (ns ? g1.x : g0.x);
-    const double inv_ds = dg ? g2.x : (ns ? g2.y : g1.y);
+                                             const PkIn &x, const double ds, const double inv_ds,
+                                             const double da, Acc &acc, PkVD &o) {
+    const unsigned cmask = (x.g >> 8) & 0xffu, ai = (x.g >> 16) & 0xffu;
     const double dt = k.dt;
     double v;
     o.I = 0.0; o.h = 0.0;
     if (SRC == PK_SRC_GA) {
-        const double fc = (k.gkq / x.I) + k.Ks;                       // infil_green_ampt :540-542
+        const double fc = div_sel(k.gkq, x.I) + k.Ks;                 // infil_green_ampt :540-542
         double IN = np_min(fc, k.P_total);                            // :567
-        if (k.low_rain) IN = k.P_total;                               // infil_base :984-993
+        IN = k.low_rain ? k.P_total : IN;                             // infil_base :984-993
         o.I = x.I + (IN * dt);                                        // :797
-        acc.s[S_VOL_IN] += (IN * da) * dt;                          // :732-736
-        if (!isfinite(IN)) acc.n[S_NNAN_IN - kNSum] += 1u;
+        acc.s[S_VOL_IN] += (IN * da) * dt;                            // :732-736
+        acc.n[S_NNAN_IN - kNSum] += isfinite(IN) ? 0u : 1u;
         const double R = k.Psum - (0.0 + IN);                         // channels_base :1649
         const double Rv = (R * da) * dt;
         acc.s[S_VOL_R] += Rv;                                         // :1666-1670
         v = x.vol + Rv;                                               // :2086
     } else if (SRC == PK_SRC_FULL) {
+        // every source term is evaluated and the disabled ones are dropped by selects on the
+        // (kernel-uniform) flags: no branch, and configs[3] enables all four anyway
+        const bool f_met = (k.flags & TFB_CH_SRC_MET) != 0u, f_snow = (k.flags & TFB_CH_SRC_SNOW) != 0u;
+        const bool f_evap = (k.flags & TFB_CH_SRC_EVAP) != 0u, f_inf = (k.flags & TFB_CH_SRC_INFIL) != 0u;
         const double Ta = k.tair_grid ? x.Ta : k.T_air;
-        double P_rain = k.P, P_snow = 0.0, SM = k.SMv, ET = 0.0, IN = k.INv;
-        bool et_grid = false;
-        if (k.flags & TFB_CH_SRC_MET) {                               // met_base :1300-1388
-            P_rain = k.P * ((Ta > k.T_rs) ? 1.0 : 0.0);
-            P_snow = k.P * ((Ta <= k.T_rs) ? 1.0 : 0.0);
-            acc.s[S_VOL_P] += (k.P * da) * dt;
-            acc.s[S_VOL_PR] += (P_rain * da) * dt;
-            acc.s[S_VOL_PS] += (P_snow * da) * dt;
-        }
-        if (k.flags & TFB_CH_SRC_SNOW) {                              // snow_degree_day :293-360
-            double M = k.c0_864 * (Ta - k.T0);
-            M = np_min(M, x.h / dt);                                  // snow_base :490-512
-            M = np_max0(M);
-            SM = M;
-            double hn = x.h + (P_snow * dt);                          // snow_base :559-609
-            hn = hn - (M * dt);
-            o.h = np_max0(hn);
-            acc.s[S_VOL_SM] += (M * da) * dt;
-        }
-        if (k.flags & TFB_CH_SRC_EVAP) {                              // evap_priestley_taylor :308-413
-            const double Qet = (k.alpha * (0.406 + (0.011 * Ta))) * (k.Qnet + k.Qc);
-            ET = np_max0(Qet / 2.5E+9);
-            et_grid = true;
-            acc.s[S_VOL_ET] += (ET * da) * dt;
-        }
-        if (k.flags & TFB_CH_SRC_INFIL) {                             // infil_green_ampt :511-578
-            const double P_total = P_rain + SM;
-            const double fc = (k.gkq / x.I) + k.Ks;
-            IN = np_min(fc, P_total);
-            if (P_total < k.Ks) IN = P_total;
-            o.I = x.I + (IN * dt);
-            acc.s[S_VOL_IN] += (IN * da) * dt;
-            if (!isfinite(IN)) acc.n[S_NNAN_IN - kNSum] += 1u;
-        }
-        if (et_grid) {                                                // channels_base :1625-1629
-            if (x.vol < ((ET * da) * dt)) ET = 0.0;
-        } else {
-            ET = 0.0;
-        }
+        // met_base :1300-1388
+        const double Pr_m = k.P * ((Ta > k.T_rs) ? 1.0 : 0.0);
+        const double Ps_m = k.P * ((Ta <= k.T_rs) ? 1.0 : 0.0);
+        const double P_rain = f_met ? Pr_m : k.P;
+        const double P_snow = f_met ? Ps_m : 0.0;
+        acc.s[S_VOL_P] += f_met ? ((k.P * da) * dt) : 0.0;
+        acc.s[S_VOL_PR] += f_met ? ((P_rain * da) * dt) : 0.0;
+        acc.s[S_VOL_PS] += f_met ? ((P_snow * da) * dt) : 0.0;
+        // snow_degree_day :293-360, snow_base :490-512, :559-609
+        double M = k.c0_864 * (Ta - k.T0);
+        M = np_min(M, div_nr(x.h, dt));
+        M = np_max0(M);
+        const double SM = f_snow ? M : k.SMv;
+        double hn = x.h + (P_snow * dt);
+        hn = hn - (M * dt);
+        o.h = np_max0(hn);
+        acc.s[S_VOL_SM] += f_snow ? ((M * da) * dt) : 0.0;
+        // evap_priestley_taylor :308-413
+        const double Qet = (k.alpha * (0.406 + (0.011 * Ta))) * (k.Qnet + k.Qc);
+        double ET = np_max0(div_nr(Qet, 2.5E+9));
+        acc.s[S_VOL_ET] += f_evap ? ((ET * da) * dt) : 0.0;
+        // infil_green_ampt :511-578
+        const double P_total = P_rain + SM;
+        const double fc = div_sel(k.gkq, x.I) + k.Ks;
+        double INg = np_min(fc, P_total);
+        INg = (P_total < k.Ks) ? P_total : INg;
+        const double IN = f_inf ? INg : k.INv;
+        o.I = x.I + (INg * dt);
+        acc.s[S_VOL_IN] += f_inf ? ((INg * da) * dt) : 0.0;
+        acc.n[S_NNAN_IN - kNSum] += (f_inf && !isfinite(INg)) ? 1u : 0u;
+        // channels_base :1625-1629: a grid ET is masked where the cell cannot supply it, a
+        // scalar ET (no evaporation component fused) is dropped
+        ET = (f_evap && !(x.vol < ((ET * da) * dt))) ? ET : 0.0;
         const double R = (((P_rain + SM) + k.GW) + k.MR) - (ET + IN);
         const double Rv = (R * da) * dt;
         acc.s[S_VOL_R] += Rv;
         v = x.vol + Rv;
     } else {
         const double Rv = (k.Runi * da) * dt;
-        if (k.r_grid) acc.s[S_VOL_R] += Rv;                           // :1666-1670 (da varies)
+        acc.s[S_VOL_R] += k.r_grid ? Rv : 0.0;                        // :1666-1670 (da varies)
         v = x.vol + Rv;
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) add_if(v, cmask, 1u << j, dt * x.ch[j]);   // :2116-2131
     v -= (x.qself * dt);                                              // :2138
     v = np_max0(v);                                                   // :2145
-    // update_channel_depth :2299-2330, :2379; table entry = {tan, 1/(2 tan), 1/cos, 4 tan}
+    // update_channel_depth :2299-2330, :2379; table entry = {tan, 1/(2 tan), 1/cos, 4 tan}.
+    // Both forms are evaluated: the trapezoid one, and v / (w ds) for vertical banks
     const double2 t01 = *reinterpret_cast<const double2 *>(lut + 4 * ai);
-    double d;
-    if (t01.x == 0.0) {
-        d = v / (x.w * ds);
-    } else {
-        double arg = (lut[4 * ai + 3] * v) * inv_ds;
-        arg += x.w * x.w;
-        d = (sqrt(arg) - x.w) * t01.y;
-    }
+    double arg = (lut[4 * ai + 3] * v) * inv_ds;
+    arg += x.w * x.w;
+    const double d_trap = (sqrt_sel(arg) - x.w) * t01.y;
+    const double d_rect = div_sel(v, x.w * ds);
+    const double d = (t01.x == 0.0) ? d_rect : d_trap;
     o.v = v;
     o.d = np_max0(d);
 }
 
-// hydraulic radius, velocity, next discharge, stability counters of one cell:
-// update_trapezoid_Rh :2643, manning_formula :3960, update_velocity_on_edges :2851,
-// update_outlet_values :2884, check_flow_depth :3193, check_flow_velocity :3352
-__device__ __forceinline__ void pk_velocity(const tfb_channels_step_args &a, const PkConsts &k,
-                                            const double *__restrict__ lut, unsigned g, double d,
-                                            double w, double umul, double inv_ds, double qself,
-                                            double outlet_rough, int r, int c, Acc &acc,
+// hydraulic radius, velocity, next discharge of one cell (straight-line): update_trapezoid_Rh
+// :2643, manning_formula :3960, update_velocity_on_edges :2851.  Returns "a stability check
+// trips on this cell" (check_flow_depth :3193, check_flow_velocity :3352): the caller counts.
+__device__ __forceinline__ bool pk_velocity(const double *__restrict__ lut, unsigned g, double d,
+                                            double w, double umul, double inv_ds,
                                             float &rate_max, double &u_out, double &Qn_out) {
     const unsigned code = g & 0xffu, ai = (g >> 16) & 0xffu;
     const bool noflow = (code == 0);
     const double tn = lut[4 * ai], invcos = lut[4 * ai + 2];          // {tan, 1/(2 tan), 1/cos, 4 tan}
     const double A_wet = d * (w + (d * tn));                          // :2668-2703
     double P_wet = w + ((2.0 * d) * invcos);
-    if (noflow) P_wet = 1.0;
-    double Rh = A_wet / P_wet;
-    if (noflow) Rh = 0.0;
-    double u = pow23(Rh) * umul;                                      // :3982-3983
-    if (noflow) u = 0.0;                                              // :2862
-    if (r + a.row0 == a.outlet_row && c == a.outlet_col) {            // :2896-2904
-        double f_o = 0.0;
-        if (d > 0.0) f_o = k.g * ((outlet_rough * outlet_rough) / cbrt(d));
-        double *po = a.partials + kPartialStride;
-        po[P_QOUT] = qself; po[P_UOUT] = u; po[P_DOUT] = d; po[P_FOUT] = f_o; po[P_HASOUT] = 1.0;
-    }
+    P_wet = noflow ? 1.0 : P_wet;
+    double Rh = div_nr(A_wet, P_wet);
+    Rh = noflow ? 0.0 : Rh;
+    double u = pow23_sel(Rh) * umul;                                  // :3982-3983
+    u = noflow ? 0.0 : u;                                             // :2862
     Qn_out = u * A_wet;                                               // next step :1697
     const double dz = noflow ? 0.0 : d;                               // :2960-2966
-    if (!(dz >= 0.0 && dz <= 1.7976931348623157e308 && u >= 0.0 && u <= 1.7976931348623157e308)) {
-        if (dz < 0.0) acc.n[S_NNEG_D - kNSum] += 1u;
-        if (dz != dz) acc.n[S_NNAN_D - kNSum] += 1u;
-        if (isinf(dz)) acc.n[S_NINF_D - kNSum] += 1u;
-        if (u < 0.0) acc.n[S_NNEG_U - kNSum] += 1u;
-        if (u != u) acc.n[S_NNAN_U - kNSum] += 1u;
-        if (isinf(u)) acc.n[S_NINF_U - kNSum] += 1u;
-    }
     rate_max = fmaxf(rate_max, (float)u * (float)inv_ds);             // CFL diagnostic: 1/dt_min
     u_out = u;
+    return !(dz >= 0.0 && dz <= 1.7976931348623157e308 && u >= 0.0 && u <= 1.7976931348623157e308);
+}
+// the rare tails, outside the straight-line block --------------------------------------------
+__device__ __forceinline__ void pk_count_bad(Acc &acc, unsigned g, double d, double u) {
+    const double dz = ((g & 0xffu) == 0u) ? 0.0 : d;
+    if (dz < 0.0) acc.n[S_NNEG_D - kNSum] += 1u;
+    if (dz != dz) acc.n[S_NNAN_D - kNSum] += 1u;
+    if (isinf(dz)) acc.n[S_NINF_D - kNSum] += 1u;
+    if (u < 0.0) acc.n[S_NNEG_U - kNSum] += 1u;
+    if (u != u) acc.n[S_NNAN_U - kNSum] += 1u;
+    if (isinf(u)) acc.n[S_NINF_U - kNSum] += 1u;
+}
+__device__ __forceinline__ void pk_outlet(const tfb_channels_step_args &a, double g, double qself,
+                                       double u, double d, double outlet_rough) {   // :2896-2904
+    double f_o = 0.0;
+    if (d > 0.0) f_o = g * ((outlet_rough * outlet_rough) / cbrt(d));
+    double *po = a.partials + kPartialStride;
+    po[P_QOUT] = qself; po[P_UOUT] = u; po[P_DOUT] = d; po[P_FOUT] = f_o; po[P_HASOUT] = 1.0;
 }
 
 __global__ void zero_at_kernel(double *__restrict__ x, const int64_t *__restrict__ idx, int64_t n) {
@@ -398,144 +416,162 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
             if (++stage == NS) { stage = 0; phase ^= 1u; }
         }
     } else {
-        // ---------------- consumers: warp w computes row w of every tile -------------
+        // ---------------- consumers: every lane advances NC = 2 cells TOGETHER -----------
+        // (two adjacent columns where a warp takes a whole tile row, two tile rows where it
+        // takes half a row): loads, then one straight-line block of arithmetic for both
+        // cells, then the stores -- the dependent fp64 chains of the two cells interleave
         int stage = 0;
         unsigned phase = 0;
+        constexpr int NC = (TC::cpl == 2) ? 2 : TC::rpw;
+        static_assert(NC == 1 || NC == 2, "one or two cells in flight per lane");
+        static_assert(TC::cpl == 1 || TC::rpw == 1, "two columns per lane: one row per warp and slot");
         for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
             if (!(PEER ? mbar_wait_peer(&full_bar[stage], phase, &s_pwait, &s_fail)
                        : mbar_wait(&full_bar[stage], phase))) { s_fail = 1; break; }
             int ty, txi;
             tile_of<PEER>(k, t, ty, txi);
-#pragma unroll 1
-            for (int rr = 0; rr < TC::rpw; ++rr) {
-            if constexpr (TC::cpl == 1) {
-            const int row = warp / TC::wpr + rr * TC::RP, ct = ((warp % TC::wpr) << 5) + lane;  // wpr warps per tile row
-            const int c0 = txi * kTW + ct, r = ty * kTR + row;
             const unsigned char *st = smem + (size_t)stage * SL::bytes;
-            if (r < a.ny && c0 < a.nx) {
-                const int e = row * kTW + ct;
-                PkIn x;
-                x.g = *reinterpret_cast<const unsigned *>(st + SL::oGeo + e * 4);
-                x.w = (double)*reinterpret_cast<const float *>(st + SL::oW + e * 4);
-                x.vol = *reinterpret_cast<const double *>(st + SL::oVol + e * 8);
-                x.I = use_i ? *reinterpret_cast<const double *>(st + SL::oI + e * 8) : 0.0;
-                x.h = use_h ? *reinterpret_cast<const double *>(st + SL::oH + e * 8) : 0.0;
-                x.Ta = use_t ? *reinterpret_cast<const double *>(st + SL::oT + e * 8) : 0.0;
-                // Q window: halo rows row .. row+2, halo cols ct+1 .. ct+3 (= c0-1 .. c0+1);
-                // children in the order SW, W, NW, N, NE, E, SE, S
-                const double *q = reinterpret_cast<const double *>(st + SL::oQ) + row * kQW + ct + 1;
-                x.ch[0] = q[2 * kQW]; x.ch[1] = q[kQW]; x.ch[2] = q[0]; x.ch[3] = q[1];
-                x.ch[4] = q[2]; x.ch[5] = q[kQW + 2]; x.ch[6] = q[2 * kQW + 2]; x.ch[7] = q[2 * kQW + 1];
-                x.qself = q[kQW + 1];
-                const double2 *rgp = reinterpret_cast<const double2 *>(p.row_geom + (int64_t)r * kRowGeom);
-                const double2 g0 = __ldg(rgp), g1 = __ldg(rgp + 1), g2 = __ldg(rgp + 2);
-                const double da_r = __ldg(rgp + 3).x;
-                PkVD o;
-                pk_vol_depth<SRC>(k, lut, x, g0, g1, g2, da_r, acc, o);
-                const int64_t i = (int64_t)r * a.pitch + c0;
-                const bool nf = (x.g & 0xffu) == 0u;
-                if (kKW) {
-                    const bool dg = (x.g & 0x55u) != 0u, ns = (x.g & 0x88u) != 0u;
-                    const double coef = *reinterpret_cast<const double *>(st + SL::oCoef + e * 8);
-                    double u, Qn;
-                    pk_velocity(a, k, lut, x.g, o.d, x.w, coef, dg ? g2.x : (ns ? g2.y : g1.y),
-                                x.qself, p.outlet_rough, r, c0, acc, rate_max, u, Qn);
-                    a.u[i] = u;
-                    a.Q_out[i] = Qn;
-                }
-                if (nf) { acc.s[S_VOL_EDGE] += o.v; o.v = 0.0; if (kKW) o.d = 0.0; }   // :2960-2966
-                a.vol_out[i] = o.v;
-                a.d[i] = o.d;
-                if (use_i) a.I_out[i] = o.I;
-                if (use_h) {
-                    a.h_swe_out[i] = o.h;
-                    if (a.h_snow) a.h_snow[i] = o.h * k.ratio;
-                }
-            }
-            } else {
-            const int row = warp / TC::wpr + rr * TC::RP, ct = ((warp % TC::wpr) << 6) + lane * 2;
-            const int c0 = txi * kTW + ct, r = ty * kTR + row;
-            const unsigned char *st = smem + (size_t)stage * SL::bytes;
-            if (r < a.ny && c0 < a.nx) {
-                const int e = row * kTW + ct;                          // element in the tile
-                const uint2 geo = *reinterpret_cast<const uint2 *>(st + SL::oGeo + e * 4);
-                const float2 w = *reinterpret_cast<const float2 *>(st + SL::oW + e * 4);
-                const double2 vol = *reinterpret_cast<const double2 *>(st + SL::oVol + e * 8);
-                double2 coef = make_double2(0.0, 0.0), Iv = coef, Hv = coef, Tv = coef;
-                if (kKW) coef = *reinterpret_cast<const double2 *>(st + SL::oCoef + e * 8);
-                if (use_i) Iv = *reinterpret_cast<const double2 *>(st + SL::oI + e * 8);
-                if (use_h) Hv = *reinterpret_cast<const double2 *>(st + SL::oH + e * 8);
-                if (use_t) Tv = *reinterpret_cast<const double2 *>(st + SL::oT + e * 8);
-                // Q window: halo rows warp, warp+1, warp+2; halo cols 2*lane .. 2*lane+4
-                const double *q = reinterpret_cast<const double *>(st + SL::oQ) + row * kQW + ct;
-                const double2 a0 = *reinterpret_cast<const double2 *>(q);
-                const double2 a1 = *reinterpret_cast<const double2 *>(q + 2);
-                const double2 m0 = *reinterpret_cast<const double2 *>(q + kQW);
-                const double2 m1 = *reinterpret_cast<const double2 *>(q + kQW + 2);
-                const double2 b0 = *reinterpret_cast<const double2 *>(q + 2 * kQW);
-                const double2 b1 = *reinterpret_cast<const double2 *>(q + 2 * kQW + 2);
-                // columns: *0.y = c0-1, *1.x = c0, *1.y = c0+1, *E = c0+2
-                const double aE = q[4], mE = q[kQW + 4], bE = q[2 * kQW + 4];
-                const double2 *rgp = reinterpret_cast<const double2 *>(p.row_geom + (int64_t)r * kRowGeom);
-                const double2 g0 = __ldg(rgp), g1 = __ldg(rgp + 1), g2 = __ldg(rgp + 2);
-                const double da_r = __ldg(rgp + 3).x;
-                const int64_t i = (int64_t)r * a.pitch + c0;
-                // odd nx: the lane that holds the last column has no second cell.  Its
-                // inputs are the TMA unit's zero fill (code 0, vol 0, Q 0); with pixel
-                // area 0, width 1 and I = 1 it is a dry noflow cell that adds exactly
-                // 0 to every sum and counter, and its stores land in the row padding
-                const bool dead1 = (c0 + 1 >= a.nx);
-                PkVD o0, o1;
-                double u0 = 0.0, u1 = 0.0, Q0 = 0.0, Q1 = 0.0;
-                {   // cell 0 (col c0): west = *0.y, same = *1.x, east = *1.y; children in the
-                    // order SW, W, NW, N, NE, E, SE, S
-                    PkIn x;
-                    x.g = geo.x; x.vol = vol.x; x.I = Iv.x; x.h = Hv.x; x.Ta = Tv.x; x.w = (double)w.x;
-                    x.qself = m1.x;
-                    x.ch[0] = b0.y; x.ch[1] = m0.y; x.ch[2] = a0.y; x.ch[3] = a1.x;
-                    x.ch[4] = a1.y; x.ch[5] = m1.y; x.ch[6] = b1.y; x.ch[7] = b1.x;
-                    pk_vol_depth<SRC>(k, lut, x, g0, g1, g2, da_r, acc, o0);
-                    if (kKW) {
-                        const bool dg = (geo.x & 0x55u) != 0u, ns = (geo.x & 0x88u) != 0u;
-                        pk_velocity(a, k, lut, geo.x, o0.d, x.w, coef.x, dg ? g2.x : (ns ? g2.y : g1.y),
-                                    x.qself, p.outlet_rough, r, c0, acc, rate_max, u0, Q0);
+            const int row0 = warp / TC::wpr;
+            const int ct = (TC::cpl == 2) ? (((warp % TC::wpr) << 6) + lane * 2) : (((warp % TC::wpr) << 5) + lane);
+            const int c0 = txi * kTW + ct, r0 = ty * kTR + row0;
+            if (r0 < a.ny && c0 < a.nx) {
+                PkIn x[NC];
+                int rj[NC], cj[NC];
+                bool live[NC];
+                double coef[NC];
+                if constexpr (TC::cpl == 2) {
+                    const int e = row0 * kTW + ct;                          // element in the tile
+                    const uint2 geo = *reinterpret_cast<const uint2 *>(st + SL::oGeo + e * 4);
+                    const float2 w = *reinterpret_cast<const float2 *>(st + SL::oW + e * 4);
+                    const double2 vol = *reinterpret_cast<const double2 *>(st + SL::oVol + e * 8);
+                    double2 cf = make_double2(0.0, 0.0), Iv = cf, Hv = cf, Tv = cf;
+                    if (kKW) cf = *reinterpret_cast<const double2 *>(st + SL::oCoef + e * 8);
+                    if (use_i) Iv = *reinterpret_cast<const double2 *>(st + SL::oI + e * 8);
+                    if (use_h) Hv = *reinterpret_cast<const double2 *>(st + SL::oH + e * 8);
+                    if (use_t) Tv = *reinterpret_cast<const double2 *>(st + SL::oT + e * 8);
+                    // Q window: halo rows row0 .. row0+2, halo cols ct .. ct+4
+                    const double *q = reinterpret_cast<const double *>(st + SL::oQ) + row0 * kQW + ct;
+                    const double2 a0 = *reinterpret_cast<const double2 *>(q);
+                    const double2 a1 = *reinterpret_cast<const double2 *>(q + 2);
+                    const double2 m0 = *reinterpret_cast<const double2 *>(q + kQW);
+                    const double2 m1 = *reinterpret_cast<const double2 *>(q + kQW + 2);
+                    const double2 b0 = *reinterpret_cast<const double2 *>(q + 2 * kQW);
+                    const double2 b1 = *reinterpret_cast<const double2 *>(q + 2 * kQW + 2);
+                    // columns: *0.y = c0-1, *1.x = c0, *1.y = c0+1, *E = c0+2
+                    const double aE = q[4], mE = q[kQW + 4], bE = q[2 * kQW + 4];
+                    // odd nx: the lane that holds the last column has no second cell.  Its inputs
+                    // are the TMA unit's zero fill (code 0, vol 0, Q 0); with pixel area 0,
+                    // width 1 and I = 1 it is a dry noflow cell that adds exactly 0 to every sum
+                    // and counter, and its stores land in the row padding
+                    live[0] = true; live[1] = (c0 + 1 < a.nx);
+                    rj[0] = rj[1] = r0; cj[0] = c0; cj[1] = c0 + 1;
+                    // children in the order SW, W, NW, N, NE, E, SE, S
+                    x[0].g = geo.x; x[0].vol = vol.x; x[0].I = Iv.x; x[0].h = Hv.x; x[0].Ta = Tv.x;
+                    x[0].w = (double)w.x; x[0].qself = m1.x; coef[0] = cf.x;
+                    x[0].ch[0] = b0.y; x[0].ch[1] = m0.y; x[0].ch[2] = a0.y; x[0].ch[3] = a1.x;
+                    x[0].ch[4] = a1.y; x[0].ch[5] = m1.y; x[0].ch[6] = b1.y; x[0].ch[7] = b1.x;
+                    x[1].g = geo.y; x[1].vol = vol.y; x[1].I = live[1] ? Iv.y : 1.0; x[1].h = Hv.y;
+                    x[1].Ta = Tv.y; x[1].w = live[1] ? (double)w.y : 1.0; x[1].qself = m1.y; coef[1] = cf.y;
+                    x[1].ch[0] = b1.x; x[1].ch[1] = m1.x; x[1].ch[2] = a1.x; x[1].ch[3] = a1.y;
+                    x[1].ch[4] = aE; x[1].ch[5] = mE; x[1].ch[6] = bE; x[1].ch[7] = b1.y;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NC; ++j) {
+                        const int row = row0 + j * TC::RP;
+                        const int e = row * kTW + ct;
+                        rj[j] = ty * kTR + row; cj[j] = c0;
+                        live[j] = (rj[j] < a.ny);
+                        x[j].g = *reinterpret_cast<const unsigned *>(st + SL::oGeo + e * 4);
+                        x[j].w = live[j] ? (double)*reinterpret_cast<const float *>(st + SL::oW + e * 4) : 1.0;
+                        x[j].vol = *reinterpret_cast<const double *>(st + SL::oVol + e * 8);
+                        x[j].I = (use_i && live[j]) ? *reinterpret_cast<const double *>(st + SL::oI + e * 8) : 1.0;
+                        x[j].h = use_h ? *reinterpret_cast<const double *>(st + SL::oH + e * 8) : 0.0;
+                        x[j].Ta = use_t ? *reinterpret_cast<const double *>(st + SL::oT + e * 8) : 0.0;
+                        coef[j] = kKW ? *reinterpret_cast<const double *>(st + SL::oCoef + e * 8) : 0.0;
+                        // Q window: halo rows row .. row+2, halo cols ct+1 .. ct+3 (= c0-1 .. c0+1)
+                        const double *q = reinterpret_cast<const double *>(st + SL::oQ) + row * kQW + ct + 1;
+                        x[j].ch[0] = q[2 * kQW]; x[j].ch[1] = q[kQW]; x[j].ch[2] = q[0]; x[j].ch[3] = q[1];
+                        x[j].ch[4] = q[2]; x[j].ch[5] = q[kQW + 2]; x[j].ch[6] = q[2 * kQW + 2];
+                        x[j].ch[7] = q[2 * kQW + 1];
+                        x[j].qself = q[kQW + 1];
                     }
                 }
-                {   // cell 1 (col c0+1): west = *1.x, same = *1.y, east = *E
-                    PkIn x;
-                    x.g = geo.y; x.vol = vol.y; x.I = dead1 ? 1.0 : Iv.y; x.h = Hv.y; x.Ta = Tv.y;
-                    x.w = dead1 ? 1.0 : (double)w.y;
-                    x.qself = m1.y;
-                    x.ch[0] = b1.x; x.ch[1] = m1.x; x.ch[2] = a1.x; x.ch[3] = a1.y;
-                    x.ch[4] = aE; x.ch[5] = mE; x.ch[6] = bE; x.ch[7] = b1.y;
-                    pk_vol_depth<SRC>(k, lut, x, g0, g1, g2, dead1 ? 0.0 : da_r, acc, o1);
-                    if (kKW) {
-                        const bool dg = (geo.y & 0x55u) != 0u, ns = (geo.y & 0x88u) != 0u;
-                        pk_velocity(a, k, lut, geo.y, o1.d, x.w, coef.y, dg ? g2.x : (ns ? g2.y : g1.y),
-                                    x.qself, p.outlet_rough, r, c0 + 1, acc, rate_max, u1, Q1);
+                // flow length of the cell's direction class, its reciprocal, pixel area of the row
+                double ds[NC], ids[NC], da[NC];
+#pragma unroll
+                for (int j = 0; j < NC; ++j) {
+                    const int rr = live[j] ? rj[j] : r0;
+                    const double2 *rgp = reinterpret_cast<const double2 *>(p.row_geom + (int64_t)rr * kRowGeom);
+                    const double2 g0 = __ldg(rgp), g1 = __ldg(rgp + 1), g2 = __ldg(rgp + 2);
+                    const unsigned code = x[j].g & 0xffu;
+                    const bool dg = (code & 0x55u) != 0u, ns = (code & 0x88u) != 0u;
+                    ds[j] = dg ? g0.y : (ns ? g1.x : g0.x);
+                    ids[j] = dg ? g2.x : (ns ? g2.y : g1.y);
+                    da[j] = live[j] ? __ldg(rgp + 3).x : 0.0;
+                }
+                // ---------------- the straight-line block --------------------------------
+                PkVD o[NC];
+                double u[NC], Qn[NC];
+                bool bad[NC];
+#pragma unroll
+                for (int j = 0; j < NC; ++j) pk_vol_depth<SRC>(k, lut, x[j], ds[j], ids[j], da[j], acc, o[j]);
+#pragma unroll
+                for (int j = 0; j < NC; ++j) {
+                    u[j] = 0.0; Qn[j] = 0.0; bad[j] = false;
+                    if (kKW) bad[j] = pk_velocity(lut, x[j].g, o[j].d, x[j].w, coef[j], ids[j], rate_max, u[j], Qn[j]);
+                }
+                double d_pre[NC];
+#pragma unroll
+                for (int j = 0; j < NC; ++j) {
+                    // update_edge_values :2960-2966 (pass A keeps the PRE-zero depth for the
+                    // free-surface slope of pass B, which then zeroes it -- and for the
+                    // neighbour slabs, whose halo rows the producer warp fills from it)
+                    const bool nf = (x[j].g & 0xffu) == 0u;
+                    d_pre[j] = o[j].d;
+                    acc.s[S_VOL_EDGE] += nf ? o[j].v : 0.0;
+                    o[j].v = nf ? 0.0 : o[j].v;
+                    if (kKW) o[j].d = nf ? 0.0 : o[j].d;
+                }
+                // ---------------- rare tails ------------------------------------------------
+                if (kKW) {
+#pragma unroll
+                    for (int j = 0; j < NC; ++j) {
+                        if (bad[j]) pk_count_bad(acc, x[j].g, d_pre[j], u[j]);
+                        if (live[j] && rj[j] + a.row0 == a.outlet_row && cj[j] == a.outlet_col)
+                            pk_outlet(a, k.g, x[j].qself, u[j], d_pre[j], p.outlet_rough);
                     }
                 }
-                const bool nf0 = (geo.x & 0xffu) == 0u, nf1 = (geo.y & 0xffu) == 0u;
-                if (kKW) {
-                    *reinterpret_cast<double2 *>(a.u + i) = make_double2(u0, u1);
-                    *reinterpret_cast<double2 *>(a.Q_out + i) = make_double2(Q0, Q1);
+                // ---------------- stores ----------------------------------------------------
+                if constexpr (TC::cpl == 2) {
+                    const int64_t i = (int64_t)r0 * a.pitch + c0;
+                    if (kKW) {
+                        *reinterpret_cast<double2 *>(a.u + i) = make_double2(u[0], u[1]);
+                        *reinterpret_cast<double2 *>(a.Q_out + i) = make_double2(Qn[0], Qn[1]);
+                    }
+                    *reinterpret_cast<double2 *>(a.vol_out + i) = make_double2(o[0].v, o[1].v);
+                    *reinterpret_cast<double2 *>(a.d + i) = make_double2(o[0].d, o[1].d);
+                    if (use_i) *reinterpret_cast<double2 *>(a.I_out + i) = make_double2(o[0].I, o[1].I);
+                    if (use_h) {
+                        *reinterpret_cast<double2 *>(a.h_swe_out + i) = make_double2(o[0].h, o[1].h);
+                        if (a.h_snow)
+                            *reinterpret_cast<double2 *>(a.h_snow + i) =
+                                make_double2(o[0].h * k.ratio, o[1].h * k.ratio);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NC; ++j) {
+                        if (!live[j]) continue;
+                        const int64_t i = (int64_t)rj[j] * a.pitch + c0;
+                        if (kKW) { a.u[i] = u[j]; a.Q_out[i] = Qn[j]; }
+                        a.vol_out[i] = o[j].v;
+                        a.d[i] = o[j].d;
+                        if (use_i) a.I_out[i] = o[j].I;
+                        if (use_h) {
+                            a.h_swe_out[i] = o[j].h;
+                            if (a.h_snow) a.h_snow[i] = o[j].h * k.ratio;
+                        }
+                    }
                 }
-                // update_edge_values :2960-2966 (pass A keeps the PRE-zero depth for the
-                // free-surface slope of pass B, which then zeroes it -- and for the
-                // neighbour slabs, whose halo rows the producer warp fills from it)
-                if (nf0) { acc.s[S_VOL_EDGE] += o0.v; o0.v = 0.0; if (kKW) o0.d = 0.0; }
-                if (nf1) { acc.s[S_VOL_EDGE] += o1.v; o1.v = 0.0; if (kKW) o1.d = 0.0; }
-                *reinterpret_cast<double2 *>(a.vol_out + i) = make_double2(o0.v, o1.v);
-                *reinterpret_cast<double2 *>(a.d + i) = make_double2(o0.d, o1.d);
-                if (use_i) *reinterpret_cast<double2 *>(a.I_out + i) = make_double2(o0.I, o1.I);
-                if (use_h) {
-                    *reinterpret_cast<double2 *>(a.h_swe_out + i) = make_double2(o0.h, o1.h);
-                    if (a.h_snow)
-                        *reinterpret_cast<double2 *>(a.h_snow + i) =
-                            make_double2(o0.h * k.ratio, o1.h * k.ratio);
-                }
-            }
-            }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[stage]);            // slot may be refilled
@@ -646,85 +682,61 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
             if (++stage == NS) { stage = 0; phase ^= 1u; }
         }
     } else {
+        // consumers: one cell per lane, the NC = rpw tile rows a warp takes advance together
         int stage = 0;
         unsigned phase = 0;
+        constexpr int NC = TC::rpw;
+        static_assert(TC::cpl == 1 && (NC == 1 || NC == 2), "pass B: one cell per lane, <= 2 rows per warp");
         for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
             if (!(PEER ? mbar_wait_peer(&full_bar[stage], phase, &s_pwait, &s_fail)
                        : mbar_wait(&full_bar[stage], phase))) { s_fail = 1; break; }
             int ty, txi;
             tile_of<PEER>(k, t, ty, txi);
-#pragma unroll 1
-            for (int rr = 0; rr < TC::rpw; ++rr) {
-            if constexpr (TC::cpl == 1) {
-            const int row = warp / TC::wpr + rr * TC::RP, ct = ((warp % TC::wpr) << 5) + lane;
-            const int c0 = txi * kTW + ct, r = ty * kTR + row;
             const unsigned char *st = smem + (size_t)stage * SL::bytes;
-            if (r < a.ny && c0 < a.nx) {
-                const int e = row * kTW + ct;
-                const unsigned g = *reinterpret_cast<const unsigned *>(st + SL::oGeo + e * 4);
-                const double w = (double)*reinterpret_cast<const float *>(st + SL::oW + e * 4);
-                const double Sb = (double)*reinterpret_cast<const float *>(st + SL::oS + e * 4);
-                const double invn = *reinterpret_cast<const double *>(st + SL::oN + e * 8);
-                const double *dc = reinterpret_cast<const double *>(st + SL::oD) + (row + 1) * kQW + ct + 2;
-                const double d = dc[0];
-                const unsigned code = g & 0xffu;
-                int dr, dcol;
-                code_offset(code, dr, dcol);
-                const double d_par = dc[dr * kQW + dcol];                 // new depth of the D8 parent
-                const double2 *rgp = reinterpret_cast<const double2 *>(p.row_geom + (int64_t)r * kRowGeom);
-                const double2 g1 = __ldg(rgp + 1), g2 = __ldg(rgp + 2);
-                const bool dg = (code & 0x55u) != 0u, ns = (code & 0x88u) != 0u;
-                const double inv_ds = dg ? g2.x : (ns ? g2.y : g1.y);
-                const double Sf = Sb + ((d - d_par) * inv_ds);            // :2606-2607
-                const int64_t i = (int64_t)r * a.pitch + c0;
-                double qs = 0.0;
-                if (r + a.row0 == a.outlet_row && c0 == a.outlet_col) qs = __ldg(a.Q_in + i);
-                double u, Qn;
-                pk_velocity(a, k, lut, g, d, w, sqrt(fabs(Sf)) * invn, inv_ds, qs, p.outlet_rough, r, c0,
-                            acc, rate_max, u, Qn);
-                a.u[i] = u;
-                a.Q_out[i] = Qn;
-            }
-            } else {
-            const int row = warp / TC::wpr + rr * TC::RP, ct = ((warp % TC::wpr) << 6) + lane * 2;
-            const int c0 = txi * kTW + ct, r = ty * kTR + row;
-            const unsigned char *st = smem + (size_t)stage * SL::bytes;
-            if (r < a.ny && c0 < a.nx) {
-                const int e = row * kTW + ct;
-                const uint2 geo = *reinterpret_cast<const uint2 *>(st + SL::oGeo + e * 4);
-                const float2 w = *reinterpret_cast<const float2 *>(st + SL::oW + e * 4);
-                const float2 S = *reinterpret_cast<const float2 *>(st + SL::oS + e * 4);
-                const double2 invn = *reinterpret_cast<const double2 *>(st + SL::oN + e * 8);
-                // depth tile with halo: own cell (row warp+1, col 2*lane+2)
-                const double *dT = reinterpret_cast<const double *>(st + SL::oD);
-                const double *dc = dT + (row + 1) * kQW + ct + 2;
-                const double2 dv = *reinterpret_cast<const double2 *>(dc);
-                const double2 *rgp = reinterpret_cast<const double2 *>(p.row_geom + (int64_t)r * kRowGeom);
-                const double2 g1 = __ldg(rgp + 1), g2 = __ldg(rgp + 2);
-                const int64_t i = (int64_t)r * a.pitch + c0;
-                double uo[2], Qo[2];
+            const int row0 = warp / TC::wpr, ct = ((warp % TC::wpr) << 5) + lane;
+            const int c0 = txi * kTW + ct, r0 = ty * kTR + row0;
+            if (r0 < a.ny && c0 < a.nx) {
+                unsigned g[NC];
+                int rj[NC];
+                bool live[NC], bad[NC];
+                double d[NC], w[NC], umul[NC], ids[NC], u[NC], Qn[NC];
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const unsigned g = j ? geo.y : geo.x;
-                    const unsigned code = g & 0xffu;
-                    const double d = j ? dv.y : dv.x;
+                for (int j = 0; j < NC; ++j) {
+                    const int row = row0 + j * TC::RP;
+                    const int e = row * kTW + ct;
+                    rj[j] = ty * kTR + row;
+                    live[j] = (rj[j] < a.ny);
+                    g[j] = *reinterpret_cast<const unsigned *>(st + SL::oGeo + e * 4);
+                    w[j] = live[j] ? (double)*reinterpret_cast<const float *>(st + SL::oW + e * 4) : 1.0;
+                    const double Sb = (double)*reinterpret_cast<const float *>(st + SL::oS + e * 4);
+                    const double invn = *reinterpret_cast<const double *>(st + SL::oN + e * 8);
+                    const double *dc = reinterpret_cast<const double *>(st + SL::oD) + (row + 1) * kQW + ct + 2;
+                    d[j] = dc[0];
+                    const unsigned code = g[j] & 0xffu;
                     int dr, dcol;
                     code_offset(code, dr, dcol);
-                    const double d_par = dc[j + dr * kQW + dcol];     // new depth of the D8 parent
+                    const double d_par = dc[dr * kQW + dcol];             // new depth of the D8 parent
+                    const double2 *rgp = reinterpret_cast<const double2 *>(
+                        p.row_geom + (int64_t)(live[j] ? rj[j] : r0) * kRowGeom);
+                    const double2 g1 = __ldg(rgp + 1), g2 = __ldg(rgp + 2);
                     const bool dg = (code & 0x55u) != 0u, ns = (code & 0x88u) != 0u;
-                    const double inv_ds = dg ? g2.x : (ns ? g2.y : g1.y);
-                    const double Sf = (double)(j ? S.y : S.x) + ((d - d_par) * inv_ds);   // :2606-2607
-                    const double umul = sqrt(fabs(Sf)) * (j ? invn.y : invn.x);
-                    double qs = 0.0;
-                    if (r + a.row0 == a.outlet_row && c0 + j == a.outlet_col)
-                        qs = __ldg(a.Q_in + i + j);
-                    pk_velocity(a, k, lut, g, d, (double)(j ? w.y : w.x), umul, inv_ds, qs,
-                                p.outlet_rough, r, c0 + j, acc, rate_max, uo[j], Qo[j]);
+                    ids[j] = dg ? g2.x : (ns ? g2.y : g1.y);
+                    const double Sf = Sb + ((d[j] - d_par) * ids[j]);     // :2606-2607
+                    umul[j] = sqrt_sel(fabs(Sf)) * invn;
                 }
-                *reinterpret_cast<double2 *>(a.u + i) = make_double2(uo[0], uo[1]);
-                *reinterpret_cast<double2 *>(a.Q_out + i) = make_double2(Qo[0], Qo[1]);
-            }
-            }
+#pragma unroll
+                for (int j = 0; j < NC; ++j)
+                    bad[j] = pk_velocity(lut, g[j], d[j], w[j], umul[j], ids[j], rate_max, u[j], Qn[j]);
+#pragma unroll
+                for (int j = 0; j < NC; ++j) {
+                    if (!live[j]) continue;
+                    const int64_t i = (int64_t)rj[j] * a.pitch + c0;
+                    if (bad[j]) pk_count_bad(acc, g[j], d[j], u[j]);
+                    if (rj[j] + a.row0 == a.outlet_row && c0 == a.outlet_col)
+                        pk_outlet(a, k.g, __ldg(a.Q_in + i), u[j], d[j], p.outlet_rough);
+                    a.u[i] = u[j];
+                    a.Q_out[i] = Qn[j];
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[stage]);
@@ -1027,7 +1039,10 @@ int prepare(const tfb_channels_step_args *ap, tfb_channels_step_args &a,
 #ifndef TFB_PK_DWB_RPW
 #define TFB_PK_DWB_RPW 2
 #endif
-typedef TileCfg<TFB_PK_NONE_ROWS, 1, TFB_PK_NONE_W, TFB_PK_NONE_RPW> CfgNone;
+#ifndef TFB_PK_NONE_CPL
+#define TFB_PK_NONE_CPL 1
+#endif
+typedef TileCfg<TFB_PK_NONE_ROWS, TFB_PK_NONE_CPL, TFB_PK_NONE_W, TFB_PK_NONE_RPW> CfgNone;
 typedef TileCfg<TFB_PK_GA_ROWS, TFB_PK_GA_CPL, TFB_PK_GA_W, TFB_PK_GA_RPW> CfgGA;
 #ifndef TFB_PK_FULL_ROWS
 #define TFB_PK_FULL_ROWS 15

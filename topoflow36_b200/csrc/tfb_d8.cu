@@ -640,6 +640,131 @@ d8_area_walk2_kernel(int ny, int nx, double pixel_area, const double *__restrict
     }
 }
 
+// ---- contributing area across row slabs (one process per GPU) ---------------------------
+// Same words, same last-child-continues walk, but a slab only owns rows [0, ny) of the
+// global grid and sees one halo row of D8 codes and of cell words on either side.  A walker
+// stops when its next cell belongs to the neighbour; the boundary rows of the words are then
+// exchanged (host: NCCL send/recv of two rows) and `resume` lets every halo cell whose word
+// has arrived act as the walker that has just stored it.  Rounds repeat until no boundary
+// row changes on any rank: one round per crossing of a slab boundary along the longest
+// dependency chain.  Per-cell sums keep the reference's neighbour order, so areas and
+// counts are bit-identical to the single-GPU pass (d8_global.update_area_grid :1029-1332).
+__global__ void __launch_bounds__(256)
+d8_area_slab_init_kernel(const uint8_t *__restrict__ code, int ny, int nx, int row0, int ny_global,
+                         unsigned long long *cell, int32_t *word) {
+    // code / cell / word point at the first OWNED row; rows -1 and ny are the halo
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = (int)(blockIdx.y * blockDim.y + threadIdx.y) - 1;
+    if (c >= nx || r > ny) return;
+    const int64_t i = (int64_t)r * nx + c;
+    cell[i] = 0ull;
+    const int lo = (row0 == 0) ? 0 : -1, hi = (row0 + ny == ny_global) ? ny : ny + 1;   // readable rows
+    auto cmask = [&](int rr0, int cc0) {
+        int m = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int rr = rr0 + kNbrDRow[k], cc = cc0 + kNbrDCol[k];
+            if (rr < lo || rr >= hi || cc < 0 || cc >= nx) continue;
+            if (code[(int64_t)rr * nx + cc] == (uint8_t)(1u << ((k + 4) & 7))) m |= (1 << k);
+        }
+        return m;
+    };
+    const bool in_grid = (r >= lo && r < hi);
+    const unsigned cd = in_grid ? code[i] : 0u;
+    int w = 0;
+    if (cd != 0) {
+        int dr, dc;
+        code_offset(cd, dr, dc);
+        const int pr = r + dr, pc = c + dc;
+        const bool owned = (r >= 0 && r < ny);
+        const int m = owned ? cmask(r, c) : 0;           // a halo cell's own children are not ours
+        w = __popc(m) | (m << 8) | ((int)cd << 16);
+        if (pr >= lo && pr < hi && pc >= 0 && pc < nx && code[(int64_t)pr * nx + pc] != 0) {
+            w |= kWParent;
+            // "only child" needs the parent's full neighbourhood: parents in owned rows
+            if (pr >= 0 && pr < ny && owned && __popc(cmask(pr, pc)) == 1) w |= kWOnly;
+        }
+    }
+    word[i] = w;
+}
+
+// the walk of d8_area_walk2_kernel from cell (r, c) holding {a, n}; `stored`: its word is
+// already in memory (a halo cell that arrived with the exchange)
+__device__ __forceinline__ void area_walk_slab(int ny, int nx, double pixel_area,
+                                               const double *__restrict__ pa_row,
+                                               unsigned long long *cell,
+                                               const int32_t *__restrict__ word, int r, int c,
+                                               int w, float a, unsigned n, bool stored) {
+    int64_t i = (int64_t)r * nx + c;
+    while (true) {
+        if (!stored) __stcg(cell + i, pack_an(a, n));
+        if (!(w & kWParent)) break;       // drains into a noflow cell
+        int dr, dc;
+        code_offset((unsigned)((w >> 16) & 0xff), dr, dc);
+        r += dr; c += dc;
+        if (r < 0 || r >= ny) break;      // the next cell is the neighbour's: it resumes there
+        const int64_t ip = (int64_t)r * nx + c;
+        const float pa = (float)(pa_row ? pa_row[r] : pixel_area);
+        const int wp = __ldg(word + ip);
+        if ((w & kWOnly) && !stored) {
+            a = pa + a;
+            n = 1u + n;
+        } else {
+            asm volatile("fence.sc.gpu;" ::: "memory");
+            const int cm = (wp >> 8) & 0xff;
+            unsigned long long v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                v[k] = (cm & (1 << k))
+                           ? __ldcg(cell + ip + (int64_t)kNbrDRow[k] * nx + kNbrDCol[k]) : 1ull;
+            bool ready = true;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) ready = ready && (v[k] != 0ull);
+            if (!ready) break;            // a sibling arrives later (perhaps in a later round)
+            if (stored && __ldcg(cell + ip) != 0ull) break;    // resumed before: already done
+            a = pa;
+            n = 1u;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (cm & (1 << k)) {
+                    a += __uint_as_float((unsigned)(v[k] & 0xffffffffull));
+                    n += (unsigned)(v[k] >> 32);
+                }
+            }
+        }
+        stored = false;
+        w = wp;
+        i = ip;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+d8_area_slab_walk_kernel(int ny, int nx, double pixel_area, const double *__restrict__ pa_row,
+                         unsigned long long *cell, const int32_t *__restrict__ word) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y * blockDim.y + threadIdx.y;
+    if (c >= nx || r >= ny) return;
+    const int w = __ldg(word + (int64_t)r * nx + c);
+    if (((w >> 16) & 0xff) == 0 || ((w >> 8) & 0xff) != 0) return;    // not a source
+    area_walk_slab(ny, nx, pixel_area, pa_row, cell, word, r, c, w,
+                   (float)(pa_row ? pa_row[r] : pixel_area), 1u, false);
+}
+
+__global__ void __launch_bounds__(256)
+d8_area_slab_resume_kernel(int ny, int nx, double pixel_area, const double *__restrict__ pa_row,
+                           unsigned long long *cell, const int32_t *__restrict__ word) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nx) return;
+    const int r = (blockIdx.y == 0) ? -1 : ny;                        // the two halo rows
+    const int64_t i = (int64_t)r * nx + c;
+    const int w = __ldg(word + i);
+    if (!(w & kWParent)) return;
+    const unsigned long long v = __ldcg(cell + i);
+    if (v == 0ull) return;                                            // not arrived yet
+    area_walk_slab(ny, nx, pixel_area, pa_row, cell, word, r, c, w,
+                   __uint_as_float((unsigned)(v & 0xffffffffull)), (unsigned)(v >> 32), true);
+}
+
 __global__ void __launch_bounds__(256)
 d8_area_unpack_kernel(const unsigned long long *cell, int64_t ncell, float *__restrict__ A,
                       int64_t *count, unsigned long long *n_done) {
@@ -701,6 +826,53 @@ extern "C" int tfb_d8_area(const uint8_t *code, int32_t ny, int32_t nx, double p
         set_error("tfb_d8_area: %s", cudaGetErrorString(e));
         return TFB_ERR_CUDA;
     }
+    if (n_done) *n_done = (int64_t)h;
+    return TFB_OK;
+}
+
+// ---- row-slab form of the area pass (see d8_area_slab_init_kernel) ---------------------------
+extern "C" int tfb_d8_area_slab_init(const uint8_t *code, int32_t ny, int32_t nx, int32_t row0,
+                                     int32_t ny_global, uint64_t *cell, int32_t *word,
+                                     void *stream) {
+    TFB_ARG_CHECK(code && cell && word && ny > 0 && nx > 0 && row0 >= 0 && row0 + ny <= ny_global);
+    dim3 b(32, 8), g((nx + 31) / 32, (ny + 2 + 7) / 8);
+    d8_area_slab_init_kernel<<<g, b, 0, (cudaStream_t)stream>>>(code, ny, nx, row0, ny_global,
+                                                               (unsigned long long *)cell, word);
+    TFB_CUDA_CHECK(cudaGetLastError());
+    return TFB_OK;
+}
+
+extern "C" int tfb_d8_area_slab_walk(int32_t ny, int32_t nx, double pixel_area,
+                                     const double *pixel_area_row, uint64_t *cell,
+                                     const int32_t *word, int32_t resume, void *stream) {
+    TFB_ARG_CHECK(cell && word && ny > 0 && nx > 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!resume) {
+        dim3 b(32, 8);
+        d8_area_slab_walk_kernel<<<grid2d(ny, nx, b), b, 0, st>>>(
+            ny, nx, pixel_area, pixel_area_row, (unsigned long long *)cell, word);
+    } else {
+        dim3 b(256, 1), g((nx + 255) / 256, 2);
+        d8_area_slab_resume_kernel<<<g, b, 0, st>>>(ny, nx, pixel_area, pixel_area_row,
+                                                    (unsigned long long *)cell, word);
+    }
+    TFB_CUDA_CHECK(cudaGetLastError());
+    return TFB_OK;
+}
+
+extern "C" int tfb_d8_area_unpack(const uint64_t *cell, int64_t n, float *A, int64_t *count,
+                                  int64_t *n_done, void *stream) {
+    TFB_ARG_CHECK(cell && A && n > 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long *d_done = (unsigned long long *)small_scratch();
+    TFB_ARG_CHECK(d_done != nullptr);
+    TFB_CUDA_CHECK(cudaMemsetAsync(d_done, 0, sizeof(unsigned long long), st));
+    d8_area_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+        (const unsigned long long *)cell, n, A, count, d_done);
+    TFB_CUDA_CHECK(cudaGetLastError());
+    unsigned long long h = 0;
+    TFB_CUDA_CHECK(cudaMemcpyAsync(&h, d_done, sizeof(h), cudaMemcpyDeviceToHost, st));
+    TFB_CUDA_CHECK(cudaStreamSynchronize(st));
     if (n_done) *n_done = (int64_t)h;
     return TFB_OK;
 }

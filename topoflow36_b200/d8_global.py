@@ -84,8 +84,7 @@ class d8_component(BMI_base.BMI_component):
     def _initialize_slab(self):
         """Row-sharded D8: this rank reads its rows (+ halo) of the DEM and runs the
         distributed flow-grid construction of slab.slab_d8 (global Jacobi flat
-        linking); contributing area is a whole-basin quantity and is not computed
-        in slab mode."""
+        linking) and the cross-slab contributing-area pass of slab.slab_d8_area."""
         if int(self.rti.pixel_geom) != 1:
             raise NotImplementedError('slab mode needs fixed-length pixels')
         if self.rti.data_type != 'FLOAT':
@@ -99,6 +98,12 @@ class d8_component(BMI_base.BMI_component):
                             nodata=getattr(self, 'nodata', -9999.0), kinematic=False,
                             device=self.device, group=self.group)
         self.n_flat_link_reps = self.slab['n_reps']
+        # contributing area (and exact cell counts) of the owned rows: the topological walk
+        # continues across the slab boundaries (slab.slab_d8_area), bit-identical to one GPU
+        from .slab import slab_d8_area
+        unit = 1.0e6 if str(self.A_units).lower().startswith('km') else 1.0
+        A, cnt, rounds = slab_d8_area(self.slab['code'], lay, float(self.da) / unit, self.group)
+        self.slab['A'], self.slab['count'], self.slab['area_rounds'] = A, cnt, rounds
 
     def read_DEM(self):
         if self.rti.data_type != 'FLOAT':

@@ -135,6 +135,9 @@ SIGNATURES = {
     'tfb_d8_ds_dw': (C.c_int, [vp, vp, vp, vp, _i32, _i32, vp, vp, vp]),
     'tfb_d8_area': (C.c_int, [vp, _i32, _i32, _f64, vp, vp, vp, vp,
                               C.POINTER(_i64), vp]),
+    'tfb_d8_area_slab_init': (C.c_int, [vp, _i32, _i32, _i32, _i32, vp, vp, vp]),
+    'tfb_d8_area_slab_walk': (C.c_int, [_i32, _i32, _f64, vp, vp, vp, _i32, vp]),
+    'tfb_d8_area_unpack': (C.c_int, [vp, _i64, vp, vp, C.POINTER(_i64), vp]),
     'tfb_d8_slope': (C.c_int, [vp, vp, vp, vp, vp, _i32, _i32, vp, vp]),
     'tfb_d8_parent_ids': (C.c_int, [vp, _i32, _i32, vp, vp]),
     'tfb_d8_aspect': (C.c_int, [vp, _i64, vp, vp]),

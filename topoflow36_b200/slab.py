@@ -418,3 +418,56 @@ def slab_d8(DEM, layout, dem_halo, link_flats=True, xres=30.0, yres=30.0, nodata
         S = torch.where(bad, smin.expand_as(S), S)
     return dict(code=code, S_bed=S.contiguous(), dx=np.array([dx]), dy=np.array([dy]),
                 dd=np.array([dd]), n_reps=n_reps)
+
+
+def slab_d8_area(code, layout, pixel_area, group=None, with_counts=True):
+    """Total contributing area of a row-sharded grid (d8_global.update_area_grid
+    :1029-1332), bit-identical to the single-GPU pass (tfb_d8_area).
+
+    `code`: this rank's uint8 D8 codes INCLUDING layout.halo >= 1 halo rows (as slab_d8
+    returns them); `pixel_area` in the units of the result (km^2: da / 1e6).  Each rank
+    walks its own flow paths; where a path leaves the slab the {area, count} words of the
+    boundary rows cross to the neighbour (two rows per exchange) and the walk resumes there
+    -- one round per slab boundary the longest dependency chain crosses.  Returns
+    (A float32 (ny, nx), count int64 (ny, nx) or None, rounds)."""
+    lib = L.load()
+    ny, nx, H = layout.ny, layout.nx, layout.halo
+    dev = code.device
+    st = L.stream_ptr
+    if layout.world_size > 1 and H < 1:
+        raise ValueError('slab_d8_area needs at least one halo row of codes')
+    c1 = torch.zeros((ny + 2, nx), dtype=torch.uint8, device=dev)      # exactly one halo row
+    if H >= 1:
+        c1.copy_(code[H - 1:H + ny + 1])
+    else:
+        c1[1:ny + 1].copy_(code)
+    cell = torch.zeros((ny + 2, nx), dtype=torch.int64, device=dev)
+    word = torch.zeros((ny + 2, nx), dtype=torch.int32, device=dev)
+    own = lambda t: t.data_ptr() + nx * t.element_size()
+    L.check(lib.tfb_d8_area_slab_init(own(c1), ny, nx, layout.row0, layout.ny_global, own(cell),
+                                      own(word), st()), 'tfb_d8_area_slab_init')
+    L.check(lib.tfb_d8_area_slab_walk(ny, nx, float(pixel_area), None, own(cell), own(word), 0, st()),
+            'tfb_d8_area_slab_walk')
+    rounds = 0
+    if layout.world_size > 1:
+        lay1 = SlabLayout(layout.ny_global, nx, layout.rank, layout.world_size, 1)
+        sent = None
+        while True:
+            edge = torch.stack((cell[1], cell[ny]))
+            changed = 1 if (sent is None or not torch.equal(edge, sent)) else 0
+            flag = torch.tensor([changed], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+            if int(flag.item()) == 0:
+                break
+            sent = edge
+            exchange_halos([cell], lay1, [1], group)
+            L.check(lib.tfb_d8_area_slab_walk(ny, nx, float(pixel_area), None, own(cell), own(word),
+                                              1, st()), 'tfb_d8_area_slab_walk')
+            rounds += 1
+    A = torch.empty((ny, nx), dtype=torch.float32, device=dev)
+    cnt = torch.empty((ny, nx), dtype=torch.int64, device=dev) if with_counts else None
+    n_done = C.c_int64(0)
+    L.check(lib.tfb_d8_area_unpack(own(cell), ny * nx, A.data_ptr(),
+                                   None if cnt is None else cnt.data_ptr(), C.byref(n_done), st()),
+            'tfb_d8_area_unpack')
+    return A, cnt, rounds
