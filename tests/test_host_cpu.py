@@ -175,6 +175,15 @@ def test_emeli_resolves_to_the_gpu_component():
             rh.quiet_call(f.instantiate_comp, name)
             bmi = f.comp_set[name]
             assert isinstance(bmi, gpu_base.channels_component)
+            # ... and it INHERITS the reference's plug-in base (north star), with the GPU
+            # class's methods in front of the reference's in the MRO
+            from topoflow.utils import BMI_base as ref_bmi
+            assert isinstance(bmi, ref_bmi.BMI_component)
+            mro = type(bmi).__mro__
+            assert mro.index(gpu_base.channels_component) < mro.index(ref_bmi.BMI_component)
+            assert type(bmi).update is gpu_base.channels_component.update
+            assert type(bmi).read_grid_info.__module__.startswith('topoflow36_b200')
+            assert type(bmi).get_bmi_version(bmi) == '2.1'
             assert bmi.get_attribute('cfg_extension') == ext
             for m in ('initialize', 'update', 'finalize', 'get_status', 'get_time_units',
                       'get_current_time', 'get_time_step', 'get_input_var_names',

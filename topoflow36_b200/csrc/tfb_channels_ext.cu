@@ -97,15 +97,14 @@ __device__ __forceinline__ void ext_cell(const tfb_channels_step_args &a, const 
         v -= (qself * dt);                                           // :2138
         v = np_max0(v);                                              // :2145
         // ---- update_channel_depth :2299-2330, :2379 ----------------------------------------
-        if (tc.x == 0.0) {
-            d = v / (w * ds);
-        } else {
-            const double denom = 2.0 * tc.x;
-            double arg = ((2.0 * denom) * v) / ds;
-            arg += w * w;
-            d = (sqrt(arg) - w) / denom;
-        }
-        d = np_max0(d);
+        // both forms, straight-line (exactly rounded Newton division / sqrt of tfb_common.cuh,
+        // IEEE special cases by selects); the bank angle picks one
+        const double denom = 2.0 * tc.x;
+        double arg = div_sel((2.0 * denom) * v, ds);
+        arg += w * w;
+        const double d_trap = div_sel(sqrt_sel(arg) - w, denom);
+        const double d_rect = div_sel(v, w * ds);
+        d = np_max0((tc.x == 0.0) ? d_rect : d_trap);
     }
     if (VAR == EXT_DWA) {
         // pass A ends here: the PRE-zero depth feeds the free-surface slope of pass B
@@ -127,25 +126,25 @@ __device__ __forceinline__ void ext_cell(const tfb_channels_step_args &a, const 
         // a noflow cell's "parent" is cell (0, 0) of the GLOBAL grid (parent ID 0, :2590-2607):
         // its pre-zero depth where this slab can see that row, 0 otherwise (as the generic kernel)
         if (noflow) d_par = k.d00_visible ? __ldg(a.d + k.d00_index) : 0.0;
-        S = S + ((d - d_par) / ds);                                  // :2606-2607
+        S = S + div_sel(d - d_par, ds);                              // :2606-2607
         slope_t = fabs(S);
         if (r + a.row0 == a.outlet_row && c == a.outlet_col) qself = __ldg(a.Q_in + i);
     }
     // ---- update_trapezoid_Rh :2668-2703 ------------------------------------------------------
     const double A_wet = d * (w + (d * tc.x));
-    double P_wet = w + ((2.0 * d) / tc.y);
-    if (noflow) P_wet = 1.0;
-    double Rh = A_wet / P_wet;
-    if (noflow) Rh = 0.0;
+    double P_wet = w + div_sel(2.0 * d, tc.y);
+    P_wet = noflow ? 1.0 : P_wet;
+    double Rh = div_sel(A_wet, P_wet);
+    Rh = noflow ? 0.0 : Rh;
     // ---- velocity: manning_formula :3960-4003 / law_of_the_wall :4005-4063 ---------------------
     double u, smooth = 0.0;
     if (!LOW) {
-        u = (pow23(Rh) * sqrt(fabs(S))) / rough;
+        u = div_sel(pow23_sel(Rh) * sqrt_sel(fabs(S)), rough);
     } else {
-        smooth = np_max((k.aval / rough) * d, 1.1);
-        u = (k.law_const * sqrt(Rh * fabs(S))) * log(smooth);
+        smooth = np_max(div_sel(k.aval, rough) * d, 1.1);
+        u = (k.law_const * sqrt_sel(Rh * fabs(S))) * log(smooth);
     }
-    if (noflow) u = 0.0;                                             // :2862
+    u = noflow ? 0.0 : u;                                            // :2862
     double f_cell = 0.0;
     const bool is_outlet = (r + a.row0 == a.outlet_row && c == a.outlet_col);
     if (DIAG || is_outlet) {
@@ -219,9 +218,9 @@ channels_ext_kernel(const tfb_channels_step_args a, const tfb_channels_packed p,
         if (lane == 0) {                              // producer: TMA loads of every stream
             int stage = 0;
             unsigned phase = 0;
+            int ty = (int)blockIdx.x / k.tiles_x, txi = (int)blockIdx.x - ty * k.tiles_x;
             for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
                 if (!mbar_wait(&empty_bar[stage], phase ^ 1u)) { s_fail = 1; break; }
-                const int ty = t / k.tiles_x, txi = t - ty * k.tiles_x;
                 const int c0 = txi * kTW, r0 = ty * kTR;
                 unsigned char *st = smem + (size_t)stage * k.stage_bytes;
                 uint64_t *bar = &full_bar[stage];
@@ -241,14 +240,16 @@ channels_ext_kernel(const tfb_channels_step_args a, const tfb_channels_packed p,
                     tma_load_2d(st + k.oRough, &maps.rough, bar, c0, r0);
                 }
                 if (++stage == NS) { stage = 0; phase ^= 1u; }
+                txi += (int)gridDim.x;                    // next tile of this CTA, no division
+                while (txi >= k.tiles_x) { txi -= k.tiles_x; ++ty; }
             }
         }
     } else {
         int stage = 0;
         unsigned phase = 0;
+        int ty = (int)blockIdx.x / k.tiles_x, txi = (int)blockIdx.x - ty * k.tiles_x;
         for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
             if (!mbar_wait(&full_bar[stage], phase)) { s_fail = 1; break; }
-            const int ty = t / k.tiles_x, txi = t - ty * k.tiles_x;
             const unsigned char *st = smem + (size_t)stage * k.stage_bytes;
 #pragma unroll 1
             for (int rr = 0; rr < TC::rpw; ++rr) {
@@ -260,6 +261,8 @@ channels_ext_kernel(const tfb_channels_step_args a, const tfb_channels_packed p,
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[stage]);
             if (++stage == NS) { stage = 0; phase ^= 1u; }
+            txi += (int)gridDim.x;
+            while (txi >= k.tiles_x) { txi -= k.tiles_x; ++ty; }
         }
     }
     pk_finish<kConsumerWarps>(a, acc, rate_max, warp < kConsumerWarps, &s_fail,

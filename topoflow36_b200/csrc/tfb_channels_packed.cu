@@ -108,28 +108,6 @@ struct PkIn { unsigned g; double vol, I, h, Ta, w, qself, ch[8]; };
 
 struct PkVD { double v, d, I, h; };    // new volume / depth before the noflow zeroing, new state
 
-// IEEE results for the operands the Newton primitives cannot take, chosen by SELECTS:
-// a / 0 = +-inf (NaN for 0 / 0), a / +-inf = +-0 (NaN for inf / inf); NaN operands go
-// through div_nr as NaN.  sqrt: 0 -> 0, +inf -> +inf, NaN -> NaN.
-__device__ __forceinline__ double div_sel(double a, double b) {
-    double q = div_nr(a, b);
-    const double inf = __longlong_as_double(0x7ff0000000000000ll);
-    if (b == 0.0) q = a * inf;
-    if (fabs(b) == inf) q = a * 0.0;
-    return q;
-}
-__device__ __forceinline__ double sqrt_sel(double x) {
-    const double r = sqrt_nr(x);
-    return (x > 0.0 && x <= 1.7976931348623157e308) ? r : x;
-}
-// x^(2/3) for any x >= 0 without a branch: values below 1e-30 are scaled by 2^300 (exact)
-// into the range of the float seed and the result scaled back by 2^-200
-__device__ __forceinline__ double pow23_sel(double x) {
-    const bool tiny = x < 1.0e-30;
-    const double xs = x * (tiny ? 2.037035976334486e90 : 1.0);           // 2^300
-    return pow23_nb(xs) * (tiny ? 6.223015277861142e-61 : 1.0);           // 2^-200
-}
-
 // new volume and depth of one cell: update_R :1548, update_flow_volume :1951,
 // update_channel_depth :2250 (+ the fused source terms in front of them).  STRAIGHT-LINE
 // code (selects, predicated adds, the Newton primitives of tfb_common.cuh): the calls for

@@ -19,15 +19,33 @@ and asks it for CUDA tensors when the user component takes them.
 """
 import importlib
 import sys
+import types
 
 _SWAPS = {'channels_kinematic_wave': 'topoflow36_b200.channels_kinematic_wave',
           'channels_diffusive_wave': 'topoflow36_b200.channels_diffusive_wave'}
 _saved = {}
 
 
-def install(modules=None):
+def _inheriting(mod):
+    """A copy of one of this package's component modules whose ``channels_component``
+    also derives from the reference's ``utils.BMI_base.BMI_component`` (north star: the
+    BMI API "inherited from BMI_base").  The GPU class comes first in the MRO, so every
+    method it defines is the one that runs; whatever else a caller may reach for on a
+    TopoFlow component (the remaining ~100 helpers of utils/BMI_base.py:189-2435) resolves
+    to the reference's own code, and ``isinstance(c, BMI_base.BMI_component)`` holds."""
+    from topoflow.utils import BMI_base as ref_bmi
+    shim = types.ModuleType(mod.__name__ + '_ref_bmi', mod.__doc__)
+    shim.__dict__.update({k: v for k, v in vars(mod).items() if not k.startswith('__')})
+    gpu_cls = mod.channels_component
+    shim.channels_component = type('channels_component', (gpu_cls, ref_bmi.BMI_component),
+                                   {'__module__': shim.__name__, '__doc__': gpu_cls.__doc__})
+    return shim
+
+
+def install(modules=None, inherit=True):
     """Route EMELI's component lookup to the GPU components.  Returns the list
-    of swapped reference module names."""
+    of swapped reference module names.  ``inherit``: derive the installed classes from
+    the reference's ``BMI_component`` as well (see ``_inheriting``)."""
     import topoflow.components as pkg          # the reference package
     done = []
     for ref_name, ours in _SWAPS.items():
@@ -35,6 +53,8 @@ def install(modules=None):
             continue
         full = 'topoflow.components.' + ref_name
         mod = importlib.import_module(ours)
+        if inherit:
+            mod = _inheriting(mod)
         _saved[full] = (sys.modules.get(full), getattr(pkg, ref_name, None))
         sys.modules[full] = mod
         setattr(pkg, ref_name, mod)
