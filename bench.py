@@ -680,7 +680,7 @@ def main():
             if world > 1:
                 dist.all_reduce(dt, op=dist.ReduceOp.MAX)
             return float(dt.item())
-        n_e2e = max(10, args.steps // 4)
+        n_e2e = max(100, args.steps)          # 0.3 ms each: enough calls for a steady figure
         dt = time_e2e(e2e_step, n_e2e)
         e2e = {'value': cells * n_e2e / dt / 1e9, 'unit': 'Gcell-updates/s',
                'h2d_bytes_per_step': 8 * len(host_in),

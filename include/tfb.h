@@ -46,6 +46,10 @@ typedef struct {
 
 int tfb_abi_version(void);
 const char *tfb_last_error(void);
+/* Block the calling host thread until `stream` has drained (cudaStreamSynchronize): how the
+ * component waits for the scalar block a step wrote into pinned host memory -- the
+ * reference reads Q_outlet etc. right after update() (channels_base.py:2884-2936). */
+int tfb_stream_synchronize(void *stream);
 /* name, SM count, cc major/minor of the current device */
 int tfb_device_info(char *name, int name_len, int *sm_count, int *cc_major,
                     int *cc_minor);

@@ -505,10 +505,12 @@ def test_packed_path_vs_c_oracle(kinematic, src):
     assert float(eng.Q.max()) > 0
 
 
+@pytest.mark.parametrize('packed', [True, False])
 @pytest.mark.parametrize('tag', ['kw', 'dw'])
-def test_flood_option_vs_reference_fixture(flood_gold, tag):
+def test_flood_option_vs_reference_fixture(flood_gold, tag, packed):
     """FLOOD_OPTION (rectangle-over-trapezoid overbank flow, channels_base.py
-    :1701-1862, :2149-2185, :2393-2448) against a stand-alone REFERENCE run."""
+    :1701-1862, :2149-2185, :2393-2448) against a stand-alone REFERENCE run: on the
+    extended packed kernels (the path a run takes) and on the generic kernel."""
     g = flood_gold
     kin = (tag == 'kw')
     code = g['code']
@@ -516,13 +518,13 @@ def test_flood_option_vs_reference_fixture(flood_gold, tag):
     dx, dy, dd = o.pixel_dims(ny, 30.0, 30.0)
     eng = _engine(code, dx, dy, dd, g['slope'], g['width'], g['angle'], g['nval'], dt=2.0,
                   da=900.0, kinematic=kin, diag=True, outlet=(ny - 2, nx // 2), flood=True,
-                  d_bankfull=np.float64(g['d_bankfull']))
+                  d_bankfull=np.float64(g['d_bankfull']), packed=packed)
     eng.set_input('P_rain', 150 / 3.6e6)
     for i in range(150):
         if i == 100:
             eng.set_input('P_rain', 0.0)
         eng.step(time_min=(i * 2.0) / 60.0)
-    assert eng.last_path == 'generic'
+    assert (eng.last_path, eng.last_kernel) == (('packed', 'ext') if packed else ('generic', 'generic'))
     want = {n: g[tag + '_' + n] for n in GRIDS + SCALARS}
     _cmp_grids(eng, want, GRIDS)
     assert rel_err(eng.own(eng.d_flood).cpu().numpy(), g[tag + '_d_flood']) <= RTOL
@@ -533,10 +535,12 @@ def test_flood_option_vs_reference_fixture(flood_gold, tag):
     _cmp_scalars(eng, want)
 
 
+@pytest.mark.parametrize('packed', [True, False])
 @pytest.mark.parametrize('tag', ['kw', 'dw'])
-def test_attenuate_vs_reference_fixture(flood_gold, attenuate_gold, tag):
+def test_attenuate_vs_reference_fixture(flood_gold, attenuate_gold, tag, packed):
     """ATTENUATE (per-cell linear reservoir in front of the channel,
-    channels_base.py:2077-2084) against a stand-alone REFERENCE run."""
+    channels_base.py:2077-2084) against a stand-alone REFERENCE run (extended packed
+    kernels and generic kernel)."""
     g0, g = flood_gold, attenuate_gold
     kin = (tag == 'kw')
     code = g0['code']
@@ -544,17 +548,56 @@ def test_attenuate_vs_reference_fixture(flood_gold, attenuate_gold, tag):
     dx, dy, dd = o.pixel_dims(ny, 30.0, 30.0)
     eng = _engine(code, dx, dy, dd, g0['slope'], g0['width'], g0['angle'], g0['nval'], dt=2.0,
                   da=900.0, kinematic=kin, diag=True, outlet=(ny - 2, nx // 2), attenuate=True,
-                  n_days=0.002)
+                  n_days=0.002, packed=packed)
     eng.set_input('P_rain', 150 / 3.6e6)
     for i in range(150):
         if i == 100:
             eng.set_input('P_rain', 0.0)
         eng.step(time_min=(i * 2.0) / 60.0)
+    assert (eng.last_path, eng.last_kernel) == (('packed', 'ext') if packed else ('generic', 'generic'))
     want = {n: g[tag + '_' + n] for n in GRIDS + SCALARS}
     _cmp_grids(eng, want, GRIDS)
     assert rel_err(eng.vol_stored.cpu().numpy(), g[tag + '_vol_stored']) <= RTOL
     assert g[tag + '_vol_stored'].max() > 1.0
     _cmp_scalars(eng, want)
+
+
+@pytest.mark.parametrize('tag', ['kw', 'dw'])
+def test_flood_with_attenuate_ext_equals_generic(flood_gold, tag):
+    """FLOOD_OPTION and ATTENUATE together with a grid infiltration rate and the law of the
+    wall (no reference fixture for the combination): the extended packed kernels against the
+    generic kernel, which keeps the reference's operation order."""
+    g = flood_gold
+    kin = (tag == 'kw')
+    code = g['code']
+    ny, nx = code.shape
+    dx, dy, dd = o.pixel_dims(ny, 30.0, 30.0)
+    rng = np.random.default_rng(5)
+    IN = 2e-6 * rng.random((ny, nx))
+    engs = []
+    for packed in (True, False):
+        eng = _engine(code, dx, dy, dd, g['slope'], g['width'], g['angle'], 0.01 + 0 * g['nval'],
+                      dt=2.0, da=900.0, kinematic=kin, manning=False, diag=True,
+                      outlet=(ny - 2, nx // 2), flood=True, d_bankfull=np.float64(g['d_bankfull']),
+                      attenuate=True, n_days=0.002, packed=packed)
+        eng.set_input('P_rain', 150 / 3.6e6)
+        eng.set_input('IN', IN)
+        for i in range(120):
+            if i == 90:
+                eng.set_input('P_rain', 0.0)
+            eng.step(time_min=(i * 2.0) / 60.0)
+        engs.append(eng)
+    a, b = engs
+    assert (a.last_kernel, b.last_kernel) == ('ext', 'generic')
+    for n in ('vol', 'Q'):
+        assert rel_err(getattr(a, n).cpu().numpy(), getattr(b, n).cpu().numpy()) <= 1e-12, n
+    for n in ('d', 'u', 'd_flood', 'vol_flood', 'Rh', 'f', 'tau', 'froude'):
+        assert rel_err(a.own(getattr(a, n)).cpu().numpy(), b.own(getattr(b, n)).cpu().numpy()) <= 1e-12, n
+    assert rel_err(a.vol_stored.cpu().numpy(), b.vol_stored.cpu().numpy()) <= 1e-12
+    assert float(a.own(a.d_flood).max()) > 0.01 and float(a.vol_stored.max()) > 0.5
+    sa, sb = a.read_scalars(), b.read_scalars()
+    for n in ('vol_R', 'vol_edge', 'vol_Q', 'Q_peak', 'd_peak', 'u_peak'):
+        assert abs(getattr(sa, n) - getattr(sb, n)) <= 1e-12 * max(abs(getattr(sb, n)), 1e-300), n
 
 
 def test_flood_component_from_cfg(tmp_path, flood_gold):

@@ -107,6 +107,12 @@ _EXTRA = [
 
 _SCALAR_BLOCK = ('vol_R', 'vol_Q', 'vol_edge', 'Q_outlet', 'u_outlet', 'd_outlet',
                  'f_outlet', 'Q_peak', 'T_peak', 'u_peak', 'Tu_peak', 'd_peak', 'Td_peak')
+# word offsets inside lib.ChannelsScalars (all fields are 8 bytes wide)
+_SC_FIELDS = [f[0] for f in L.ChannelsScalars._fields_]
+assert tuple(_SC_FIELDS[:len(_SCALAR_BLOCK)]) == _SCALAR_BLOCK
+_IX_DTMIN, _IX_FAIL = _SC_FIELDS.index('dt_cfl_min'), _SC_FIELDS.index('n_step_failed')
+_IX_CNT = _SC_FIELDS.index('n_neg_d')
+assert _SC_FIELDS[_IX_CNT:_IX_CNT + 6] == ['n_neg_d', 'n_nan_d', 'n_inf_d', 'n_neg_u', 'n_nan_u', 'n_inf_u']
 _SRC_INPUTS = ('P_rain', 'SM', 'GW', 'MR', 'ET', 'IN')
 _DIAG = ('Rh', 'A_wet', 'P_wet', 'f', 'tau', 'u_star', 'froude')
 # attribute -> how to find the device tensor (state & diagnostics)
@@ -330,8 +336,12 @@ class channels_component(BMI_base.BMI_component):
 
     def _init_host_scalars(self):
         z = lambda v=0.0: self.initialize_scalar(v, dtype='float64')
-        for n in _SCALAR_BLOCK:
-            setattr(self, n, z())
+        # the 13 values every step refreshes are 0-D VIEWS of one float64 block (still
+        # "mutable scalars" shared by reference, BMI_base.py:2230-2294): one vector copy
+        # from the pinned mirror updates them all
+        self._scalar_block = np.zeros(len(_SCALAR_BLOCK), dtype='float64')
+        for i, n in enumerate(_SCALAR_BLOCK):
+            setattr(self, n, self._scalar_block[i:i + 1].reshape(()))
         for n in ('vol_chan_sum', 'vol_chan_sum0', 'vol_flood_sum', 'Q_canals_in'):
             setattr(self, n, z())
         for n in ('Q_min', 'u_min', 'd_min'):
@@ -658,22 +668,37 @@ class channels_component(BMI_base.BMI_component):
         """Refresh the 0-D arrays in place from the scalar block the kernel wrote
         into pinned host memory (one stream synchronise, no copy; in slab mode one
         all-reduce forms the global values -- collective)."""
+        b = self.bad_counts
+        if self.layout is None:
+            # single GPU: straight from the pinned mirror (layout of lib.ChannelsScalars:
+            # 20 float64 words, then the int64 counters)
+            e = self.engine
+            f = e.sync_scalar_mirror()
+            i = e._scalars_i64
+            if i[_IX_FAIL]:
+                self._step_failed(int(i[_IX_FAIL]))
+            self._scalar_block[:] = f[:len(_SCALAR_BLOCK)]
+            self.dt_cfl_min.fill(f[_IX_DTMIN])
+            (b['n_neg_d'], b['n_nan_d'], b['n_inf_d'], b['n_neg_u'], b['n_nan_u'],
+             b['n_inf_u']) = i[_IX_CNT:_IX_CNT + 6].tolist()
+            return None
         s = self.stepper.read_scalars()
         if s.n_step_failed:
             # a bounded wait inside the kernel ran out (TMA pipeline, or a slab neighbour that
             # never delivered its halo rows): the grids of that step are not valid
-            self.status = 'failed'
-            self.DONE = True
-            raise L.TfbError('routing step failed on the device: %d launch(es) gave up waiting for '
-                             'the tile pipeline or for a neighbour slab\'s halo rows'
-                             % s.n_step_failed)
+            self._step_failed(s.n_step_failed)
         for n in _SCALAR_BLOCK:
             getattr(self, n).fill(getattr(s, n))
         self.dt_cfl_min.fill(s.dt_cfl_min)
-        b = self.bad_counts
         b['n_neg_d'], b['n_nan_d'], b['n_inf_d'] = s.n_neg_d, s.n_nan_d, s.n_inf_d
         b['n_neg_u'], b['n_nan_u'], b['n_inf_u'] = s.n_neg_u, s.n_nan_u, s.n_inf_u
         return s
+
+    def _step_failed(self, n):
+        self.status = 'failed'
+        self.DONE = True
+        raise L.TfbError('routing step failed on the device: %d launch(es) gave up waiting for '
+                         'the tile pipeline or for a neighbour slab\'s halo rows' % n)
 
     def _abort_banner(self, lines):
         star = '*******************************************'

@@ -44,6 +44,11 @@ extern "C" int tfb_abi_version(void) { return TFB_ABI_VERSION; }
 
 extern "C" const char *tfb_last_error(void) { return tfb::g_err; }
 
+extern "C" int tfb_stream_synchronize(void *stream) {
+    TFB_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    return TFB_OK;
+}
+
 extern "C" int tfb_device_info(char *name, int name_len, int *sm_count, int *cc_major,
                                int *cc_minor) {
     int dev = 0, n = 0;

@@ -8,7 +8,14 @@
 //   * the seven diagnostic grids materialised every step (update_trapezoid_Rh :2643,
 //     update_shear_stress / _speed :2620-2641, update_friction_factor :2714,
 //     update_froude_number :2867, + S_free for the diffusive wave :2583),
-//   * more than 256 distinct bank angles (16-bit index into a table in L2), any nx
+//   * more than 256 distinct bank angles (16-bit index into a table in L2), any nx,
+//   * ATTENUATE: the per-cell linear reservoir in front of the channel (:2077-2084), one
+//     more fp64 state stream in and out,
+//   * FLOOD_OPTION: rectangle-over-trapezoid overbank flow (update_flood_discharge :1701,
+//     update_discharge :1791, update_channel_volume :2149, update_flood_volume :2158,
+//     update_flood_depth :2393): a bankfull-volume stream, flood depth / flood volume grids
+//     out, and -- diffusive wave -- the flood depths of a cell and its D8 parent as a second
+//     halo tile in pass B (the free surface is the TOTAL depth :2593-2596)
 // -- for the kinematic wave (one launch) and the diffusive wave (pass A: volumes + new
 // depths, pass B: free-surface slope, velocity, discharge, diagnostics; the noflow depths are
 // zeroed by tfb_channels_step_packed_dw_c as in the lean path).
@@ -40,8 +47,11 @@ struct ExtConsts {
     int n_tiles, tiles_x, tiles_y;
     int d00_visible;           // pass B: global cell (0, 0) lies within this slab's rows + halo
     long long d00_index;       //         its offset from the first owned row
+    int atten, flood;          // ATTENUATE, FLOOD_OPTION
+    int oVs, oVb, oDf;         // ring-slot offsets: vol_stored, vol_bankfull (-1 = scalar), d_flood halo tile
+    double t_drain, vb_val, width_ratio, flood_n;
 };
-struct ExtMaps { CUtensorMap Q, vol, geo, w, S, rough, F[F_N]; };   // Q: discharge, or depth (pass B)
+struct ExtMaps { CUtensorMap Q, vol, geo, w, S, rough, F[F_N], vs, vb, df; };   // Q: discharge, or depth (pass B)
 
 template <int VAR, bool LOW, bool DIAG>
 __device__ __forceinline__ void ext_cell(const tfb_channels_step_args &a, const tfb_channels_packed &p,
@@ -60,6 +70,7 @@ __device__ __forceinline__ void ext_cell(const tfb_channels_step_args &a, const 
     const int64_t i = (int64_t)r * a.pitch + c;
     const double dt = k.dt;
     double v = 0.0, d = 0.0, qself = 0.0;
+    double df = 0.0, vf = 0.0;                   // FLOOD_OPTION: flood depth, volume above bankfull
     if (VAR != EXT_DWB) {
         // ---- update_R :1548-1655, update_R_integral :1657, update_flow_volume :1951 --------
         const double da = __ldg(rg + 6);
@@ -79,9 +90,17 @@ __device__ __forceinline__ void ext_cell(const tfb_channels_step_args &a, const 
             ET = 0.0;                                                // :1629 a scalar ET is dropped
         }
         const double R = (((f[F_P] + f[F_SM]) + f[F_GW]) + f[F_MR]) - (ET + f[F_IN]);   // :1649
-        const double Rv = (R * da) * dt;
+        double Rv = (R * da) * dt;
         if (k.r_grid) acc.s[S_VOL_R] += Rv;                          // :1666-1670
         if (k.write_R) a.R[i] = R;
+        if (k.atten) {
+            // ATTENUATE :2077-2084: the runoff fills a linear reservoir that drains into the channel
+            double vs = *reinterpret_cast<const double *>(st + k.oVs + e * 8) + Rv;
+            const double Q_sides = div_sel(vs, k.t_drain);
+            Rv = np_min(Q_sides * dt, vs);
+            vs = vs - Rv;
+            a.vol_stored_out[i] = np_max0(vs);
+        }
         v = vol + Rv;                                                // :2086
         // children in the reference's scatter order SW, W, NW, N, NE, E, SE, S :2116-2131
         const double *q = reinterpret_cast<const double *>(st + k.oQ) + row * QW + ct + 1;
@@ -96,14 +115,24 @@ __device__ __forceinline__ void ext_cell(const tfb_channels_step_args &a, const 
         qself = q[QW + 1];
         v -= (qself * dt);                                           // :2138
         v = np_max0(v);                                              // :2145
+        double vch = v;
+        if (k.flood) {
+            // update_channel_volume :2149, update_flood_volume :2158-2185, update_flood_depth
+            // :2393-2448: the channel depth below comes from min(vol, bankfull volume)
+            const double vb = (k.oVb >= 0) ? *reinterpret_cast<const double *>(st + k.oVb + e * 8)
+                                           : k.vb_val;
+            vf = np_max0(v - vb);
+            vch = np_min(v, vb);
+            df = np_max0(div_sel(vf, (k.width_ratio * w) * ds));
+        }
         // ---- update_channel_depth :2299-2330, :2379 ----------------------------------------
         // both forms, straight-line (exactly rounded Newton division / sqrt of tfb_common.cuh,
         // IEEE special cases by selects); the bank angle picks one
         const double denom = 2.0 * tc.x;
-        double arg = div_sel((2.0 * denom) * v, ds);
+        double arg = div_sel((2.0 * denom) * vch, ds);
         arg += w * w;
         const double d_trap = div_sel(sqrt_sel(arg) - w, denom);
-        const double d_rect = div_sel(v, w * ds);
+        const double d_rect = div_sel(vch, w * ds);
         d = np_max0((tc.x == 0.0) ? d_rect : d_trap);
     }
     if (VAR == EXT_DWA) {
@@ -111,6 +140,10 @@ __device__ __forceinline__ void ext_cell(const tfb_channels_step_args &a, const 
         if (noflow) { acc.s[S_VOL_EDGE] += v; v = 0.0; }             // :2960-2964
         a.vol_out[i] = v;
         a.d[i] = d;
+        if (k.flood) {               // pre-zero flood depth (pass B: free surface), final volume
+            a.d_flood[i] = df;
+            a.vol_flood[i] = noflow ? 0.0 : vf;
+        }
         return;
     }
     double S = (double)*reinterpret_cast<const float *>(st + k.oS + e * 4);
@@ -126,7 +159,16 @@ __device__ __forceinline__ void ext_cell(const tfb_channels_step_args &a, const 
         // a noflow cell's "parent" is cell (0, 0) of the GLOBAL grid (parent ID 0, :2590-2607):
         // its pre-zero depth where this slab can see that row, 0 otherwise (as the generic kernel)
         if (noflow) d_par = k.d00_visible ? __ldg(a.d + k.d00_index) : 0.0;
-        S = S + div_sel(d - d_par, ds);                              // :2606-2607
+        double d_tot = d;
+        if (k.flood) {               // free surface = channel + flood depth :2593-2596
+            const double *fc = reinterpret_cast<const double *>(st + k.oDf) + (row + 1) * QW + ct + 2;
+            df = fc[0];
+            double df_par = fc[dr * QW + dcol];
+            if (noflow) df_par = k.d00_visible ? __ldg(a.d_flood + k.d00_index) : 0.0;
+            d_par = d_par + df_par;
+            d_tot = d + df;
+        }
+        S = S + div_sel(d_tot - d_par, ds);                          // :2606-2607
         slope_t = fabs(S);
         if (r + a.row0 == a.outlet_row && c == a.outlet_col) qself = __ldg(a.Q_in + i);
     }
@@ -164,7 +206,16 @@ __device__ __forceinline__ void ext_cell(const tfb_channels_step_args &a, const 
         a.froude[i] = (d > 0.0) ? (u / sqrt(k.g * d)) : 0.0;
         if (VAR == EXT_DWB && a.S_free) a.S_free[i] = S;
     }
-    const double Qn = u * A_wet;                                     // next step :1697
+    double Qn = u * A_wet;                                           // next step :1697
+    if (k.flood) {
+        // update_flood_discharge :1701-1750 + update_discharge :1791-1862 for the NEXT step: the
+        // flood depth after the noflow zeroing (:2968-2970), S_bed or this step's S_free
+        const double dfz = noflow ? 0.0 : df;
+        const double uf = div_sel(pow23_sel(dfz) * sqrt_sel(fabs(S)), k.flood_n);
+        const double Af = (k.width_ratio * w) * dfz;
+        Qn = Qn + (uf * Af);
+        if (VAR == EXT_KW) { a.d_flood[i] = dfz; a.vol_flood[i] = noflow ? 0.0 : vf; }
+    }
     if (VAR == EXT_KW && noflow) { acc.s[S_VOL_EDGE] += v; v = 0.0; d = 0.0; }   // :2960-2966
     const double dz = noflow ? 0.0 : d;
     if (!(dz >= 0.0 && dz <= 1.7976931348623157e308 && u >= 0.0 && u <= 1.7976931348623157e308)) {
@@ -234,6 +285,10 @@ channels_ext_kernel(const tfb_channels_step_args a, const tfb_channels_packed p,
 #pragma unroll
                     for (int j = 0; j < F_N; ++j)
                         if (k.foff[j] >= 0) tma_load_2d(st + k.foff[j], &maps.F[j], bar, c0, r0 + a.halo);
+                    if (k.atten) tma_load_2d(st + k.oVs, &maps.vs, bar, c0, r0 + a.halo);
+                    if (k.flood && k.oVb >= 0) tma_load_2d(st + k.oVb, &maps.vb, bar, c0, r0 + a.halo);
+                } else if (k.flood) {
+                    tma_load_2d(st + k.oDf, &maps.df, bar, c0 - 2, r0 - 1 + a.halo);
                 }
                 if (VAR != EXT_DWA) {
                     tma_load_2d(st + k.oS, &maps.S, bar, c0, r0);
@@ -306,6 +361,10 @@ int launch_ext(const tfb_channels_step_args &a, const tfb_channels_packed &p, Ex
             k.fval[j] = F[j]->val;
             k.foff[j] = F[j]->ptr ? put(TC::szD, TC::nD) : -1;
         }
+        if (k.atten) k.oVs = put(TC::szD, TC::nD);
+        k.oVb = (k.flood && a.vol_bankfull.ptr) ? put(TC::szD, TC::nD) : -1;
+    } else if (k.flood) {
+        k.oDf = put(TC::szQ, TC::nQ);
     }
     if (VAR != EXT_DWA) {
         k.oS = put(TC::szF, TC::nF);
@@ -332,6 +391,12 @@ int launch_ext(const tfb_channels_step_args &a, const tfb_channels_packed &p, Ex
         for (int j = 0; j < F_N; ++j)
             if (F[j]->ptr)
                 if ((rc = pk_get_map(F[j]->ptr - hb, rows_h, a.nx, a.pitch, F64, 8, kTW, kTR, &m.F[j]))) return rc;
+        if (k.atten)
+            if ((rc = pk_get_map(a.vol_stored - hb, rows_h, a.nx, a.pitch, F64, 8, kTW, kTR, &m.vs))) return rc;
+        if (k.oVb >= 0)
+            if ((rc = pk_get_map(a.vol_bankfull.ptr - hb, rows_h, a.nx, a.pitch, F64, 8, kTW, kTR, &m.vb))) return rc;
+    } else if (k.flood) {
+        if ((rc = pk_get_map(a.d_flood - hb, rows_h, a.nx, a.pitch, F64, 8, kQW, kQR, &m.df))) return rc;
     }
     if (VAR != EXT_DWA) {
         if ((rc = pk_get_map(p.S32, a.ny, a.nx, a.pitch, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, kTW, kTR, &m.S))) return rc;
@@ -365,8 +430,11 @@ int prepare_ext(const tfb_channels_step_args *ap, tfb_channels_step_args &a,
                   p.n_angles >= 1 && p.n_angles <= 65536);
     TFB_ARG_CHECK(a.vol && a.vol_out && a.Q_in && a.Q_out && a.d && a.u);
     TFB_ARG_CHECK(a.Q_in != a.Q_out && a.scalars && a.partials && a.ticket && a.dt > 0.0);
-    TFB_ARG_CHECK(!(a.flags & (TFB_CH_FLOOD | TFB_CH_ATTENUATE | TFB_CH_SRC_MET | TFB_CH_SRC_SNOW |
-                               TFB_CH_SRC_EVAP | TFB_CH_SRC_INFIL)));
+    TFB_ARG_CHECK(!(a.flags & (TFB_CH_SRC_MET | TFB_CH_SRC_SNOW | TFB_CH_SRC_EVAP | TFB_CH_SRC_INFIL)));
+    if (a.flags & TFB_CH_FLOOD)
+        TFB_ARG_CHECK(a.d_flood && a.vol_flood && a.width_ratio > 0.0 && a.flood_manning_n > 0.0);
+    if (a.flags & TFB_CH_ATTENUATE)
+        TFB_ARG_CHECK(a.vol_stored && a.vol_stored_out && a.t_drain > 0.0);
     TFB_ARG_CHECK(((a.flags & TFB_CH_DIFFUSIVE) != 0) == diffusive);
     TFB_ARG_CHECK(!a.sinu.ptr);
     if (a.flags & TFB_CH_DIAG)
@@ -375,7 +443,8 @@ int prepare_ext(const tfb_channels_step_args *ap, tfb_channels_step_args &a,
     auto al16 = [](const void *q) { return (((uintptr_t)q) & 15u) == 0; };
     TFB_ARG_CHECK(al16(a.vol) && al16(a.Q_in) && al16(a.d) && al16(p.rough64) && al16(p.lut_tc) &&
                   al16(p.geo32) && al16(p.width32) && al16(p.S32) && al16(a.P_rain.ptr) &&
-                  al16(a.SM.ptr) && al16(a.GW.ptr) && al16(a.MR.ptr) && al16(a.ET.ptr) && al16(a.IN.ptr));
+                  al16(a.SM.ptr) && al16(a.GW.ptr) && al16(a.MR.ptr) && al16(a.ET.ptr) && al16(a.IN.ptr) &&
+                  al16(a.vol_stored) && al16(a.vol_bankfull.ptr) && al16(a.d_flood));
     memset(&k, 0, sizeof(k));
     k.g = 9.81; k.aval = 0.476; k.kappa = 0.408;
     k.law_const = sqrt(k.g) / k.kappa;                   // channels_base.py:528-531
@@ -387,6 +456,11 @@ int prepare_ext(const tfb_channels_step_args *ap, tfb_channels_step_args &a,
     if (!(a.flags & TFB_CH_ET_INPLACE)) a.ET_rw = nullptr;
     k.d00_visible = (-a.row0 >= -a.halo && -a.row0 < a.ny + a.halo) ? 1 : 0;
     k.d00_index = (long long)(-a.row0) * a.pitch;
+    k.atten = (a.flags & TFB_CH_ATTENUATE) ? 1 : 0;
+    k.flood = (a.flags & TFB_CH_FLOOD) ? 1 : 0;
+    k.oVs = k.oDf = 0; k.oVb = -1;
+    k.t_drain = a.t_drain; k.vb_val = a.vol_bankfull.val;
+    k.width_ratio = a.width_ratio; k.flood_n = a.flood_manning_n;
     const bool any_grid = a.P_rain.ptr || a.SM.ptr || a.GW.ptr || a.MR.ptr || a.ET.ptr || a.IN.ptr;
     TFB_ARG_CHECK(!any_grid || a.is_R_grid == 1);
     return TFB_OK;

@@ -1050,6 +1050,9 @@ extern "C" int tfb_channels_step_packed_dw_c(const tfb_channels_step_args *ap,
     if (pp->n_noflow == 0) return TFB_OK;
     zero_at_kernel<<<(unsigned)((pp->n_noflow + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         ap->d, pp->noflow_idx, pp->n_noflow);
+    if ((ap->flags & TFB_CH_FLOOD) && ap->d_flood)       // update_edge_values :2968-2970
+        zero_at_kernel<<<(unsigned)((pp->n_noflow + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+            ap->d_flood, pp->noflow_idx, pp->n_noflow);
     TFB_CUDA_CHECK(cudaGetLastError());
     return TFB_OK;
 }

@@ -176,6 +176,8 @@ class ChannelsEngine(object):
         # write it directly, so reading Q_outlet costs a stream synchronise, not a copy
         self._scalars_host = torch.zeros(C.sizeof(L.ChannelsScalars), dtype=torch.uint8).pin_memory()
         self._scalars_np = self._scalars_host.numpy()
+        self._scalars_f64 = self._scalars_np.view(np.float64)
+        self._scalars_i64 = self._scalars_np.view(np.int64)
         a.scalars_mirror = self._scalars_host.data_ptr()
         self.set_initial_depth(d0)
         self.n_steps = 0
@@ -189,6 +191,12 @@ class ChannelsEngine(object):
         self.packed = None
         self.lean_ok = self.ext_ok = False
         self.last_path = self.last_kernel = None
+        # per-step host work is on the critical path of a synchronous update(): the kernel
+        # choice and the buffer pointers of each double-buffer parity are computed once and
+        # reused until an input / option changes
+        self._dev_index = self.device.index if self.device.index is not None \
+            else torch.cuda.current_device()
+        self._cfg, self._cfg_key, self._ptr_cache = None, None, {}
         self._scalars_dirty = False
         self.mid_step_hook = None
         self.use_packed = bool(packed)
@@ -234,19 +242,21 @@ class ChannelsEngine(object):
     def _try_pack(self):
         """Build the compact static inputs of the packed (TMA ring) kernels once, when the
         configuration allows it: scalar sinuosity, float32-exact widths, at most 65536
-        distinct bank angles, no flood option / ATTENUATE.  Everything is lossless and
+        distinct bank angles.  Everything is lossless and
         every per-cell array is (ny, pitch) like the state.  Two families share them:
 
           lean  tfb_channels_step_packed*: Manning, no per-step diagnostics, scalar forcing,
                 optionally fused sources; <= 256 angles (table in shared memory); kinematic
                 wave: coef = sqrt|S_bed| / n, diffusive: 1 / n and the float32 bed slope
-          ext   tfb_channels_step_ext*: grid forcing, law of the wall, diagnostics, R grid;
-                float32 bed slope + roughness (n or z0) + a {tan, cos} table in L2
+          ext   tfb_channels_step_ext*: grid forcing, law of the wall, diagnostics, R grid,
+                FLOOD_OPTION, ATTENUATE; float32 bed slope + roughness (n or z0) + a
+                {tan, cos} table in L2
 
         Otherwise the generic kernel (tfb_channels_step) runs."""
         a = self.args
         self.lean_ok = self.ext_ok = False
-        if self.flood or self.attenuate or self.sinu_grid is not None:
+        self._cfg = None
+        if self.sinu_grid is not None:
             return
         dev = self.device
 
@@ -336,7 +346,7 @@ class ChannelsEngine(object):
             pk.noflow_idx, pk.n_noflow = nf.data_ptr(), int(nf.numel())
         self._pack_keep = (geo32, w32, coef, inv_rough, S32, rough64, lut, lut_tc, rowg, nf, aidx)
         self.packed = pk
-        self.lean_ok = (self.manning and n_angles <= 256
+        self.lean_ok = (self.manning and n_angles <= 256 and not self.flood and not self.attenuate
                         and (coef is not None if self.kinematic else inv_rough is not None))
         self.ext_ok = s32_ok
 
@@ -355,10 +365,20 @@ class ChannelsEngine(object):
         a.S_bed = a.sqrtS = a.geo = None
         self.generic_released = True
 
+    def _config(self):
+        """(kernel family, R-is-a-grid) of the next step, cached until an option or input
+        binding changes (`set_input`, `enable_fused_sources`, the flag word)."""
+        key = (self.flags, self.use_packed, self.diag)
+        if self._cfg is None or self._cfg_key != key:
+            self._cfg = (self._packed_ok(), 1 if self.is_R_grid() else 0)
+            self._cfg_key = key
+        return self._cfg
+
     def _packed_ok(self):
         """Which packed family takes this step: 'lean' (the benchmarked production kernels),
-        'ext' (grid forcing / law of the wall / diagnostics / R grid), or None (generic
-        kernel: flood option, ATTENUATE, grid sinuosity, fused sources with grid parameters)."""
+        'ext' (grid forcing / law of the wall / diagnostics / R grid / flood option /
+        ATTENUATE), or None (generic kernel: grid sinuosity, widths or slopes that are not
+        float32 values, fused sources with grid parameters)."""
         if self.packed is None or not self.use_packed:
             return None
         src = self.flags & (L.CH_SRC_MET | L.CH_SRC_SNOW | L.CH_SRC_EVAP | L.CH_SRC_INFIL)
@@ -433,6 +453,7 @@ class ChannelsEngine(object):
         CUDA tensor (used in place when it already has the slab's layout)."""
         if name not in _SRC_SG:
             raise KeyError(name)
+        self._cfg = None
         if _is_grid(val):
             if (isinstance(val, torch.Tensor) and val.is_cuda and val.dtype == torch.float64
                     and val.is_contiguous() and self.halo == 0 and self.pitch == self.nx
@@ -554,6 +575,8 @@ class ChannelsEngine(object):
         """Evaluate the met/snow/evap/infil source terms inside the routing
         kernel (TFB_CH_SRC_* flags) instead of taking them as inputs."""
         a = self.args
+        self._cfg = None
+        self._ptr_cache.clear()
         f = self.flags & ~(L.CH_SRC_MET | L.CH_SRC_SNOW | L.CH_SRC_EVAP | L.CH_SRC_INFIL)
         dbl = not self.kinematic
         if met:
@@ -678,34 +701,39 @@ class ChannelsEngine(object):
         `peer_step` = how many steps (diffusive: phases) used it before this one -- the
         value the flag words are compared with (default: every step so far did)."""
         a = self.args
+        st = L.stream_ptr(self._dev_index)
         a.flags = self.flags | (L.CH_ET_INPLACE if a.ET.ptr else 0)
         a.time_min = float(time_min)
-        a.is_R_grid = 1 if self.is_R_grid() else 0
-        a.Q_in = self._p(self.Q_buf[self.qcur])
-        a.Q_out = self._p(self.Q_buf[self.qcur ^ 1])
-        for name, buf in (('vol', self.vol_buf), ('h_swe', self.h_swe_buf),
-                          ('I', self.I_buf), ('vol_stored', self.vol_stored_buf)):
-            if buf is None:
-                continue
-            dbl = buf[1] is not None
-            setattr(a, name, self._p(buf[self.scur if dbl else 0]))
-            setattr(a, name + '_out', self._p(buf[self.scur ^ 1 if dbl else 0]))
-        path = self._packed_ok()
+        ptrs = self._ptr_cache.get((self.qcur, self.scur))
+        if ptrs is None:
+            ptrs = [('Q_in', self._p(self.Q_buf[self.qcur])),
+                    ('Q_out', self._p(self.Q_buf[self.qcur ^ 1]))]
+            for name, buf in (('vol', self.vol_buf), ('h_swe', self.h_swe_buf),
+                              ('I', self.I_buf), ('vol_stored', self.vol_stored_buf)):
+                if buf is None:
+                    continue
+                dbl = buf[1] is not None
+                ptrs.append((name, self._p(buf[self.scur if dbl else 0])))
+                ptrs.append((name + '_out', self._p(buf[self.scur ^ 1 if dbl else 0])))
+            self._ptr_cache[(self.qcur, self.scur)] = ptrs
+        for name, p in ptrs:
+            setattr(a, name, p)
+        path, a.is_R_grid = self._config()
         if path == 'ext':
             if peer is not None:
                 raise L.TfbError('the peer-memory halo needs the lean packed step')
             if self.kinematic:
                 L.check(self.lib.tfb_channels_step_ext(C.byref(a), C.byref(self.packed),
-                                                       L.stream_ptr()), 'tfb_channels_step_ext')
+                                                       st), 'tfb_channels_step_ext')
             else:
                 L.check(self.lib.tfb_channels_step_ext_dw_a(
-                    C.byref(a), C.byref(self.packed), L.stream_ptr()), 'tfb_channels_step_ext_dw_a')
+                    C.byref(a), C.byref(self.packed), st), 'tfb_channels_step_ext_dw_a')
                 if self.mid_step_hook is not None:
                     self.mid_step_hook()
                 L.check(self.lib.tfb_channels_step_ext_dw_b(
-                    C.byref(a), C.byref(self.packed), L.stream_ptr()), 'tfb_channels_step_ext_dw_b')
+                    C.byref(a), C.byref(self.packed), st), 'tfb_channels_step_ext_dw_b')
                 L.check(self.lib.tfb_channels_step_packed_dw_c(
-                    C.byref(a), C.byref(self.packed), L.stream_ptr()), 'tfb_channels_step_packed_dw_c')
+                    C.byref(a), C.byref(self.packed), st), 'tfb_channels_step_packed_dw_c')
             self.last_path = 'packed'
             self.last_kernel = 'ext'
         elif path == 'lean':
@@ -714,36 +742,36 @@ class ChannelsEngine(object):
                 ps = self.n_steps if peer_step is None else int(peer_step)
                 ph = peer.descriptor(self.qcur ^ 1, ps)
                 L.check(self.lib.tfb_channels_step_packed_p2p(
-                    C.byref(a), C.byref(self.packed), C.byref(ph), L.stream_ptr()),
+                    C.byref(a), C.byref(self.packed), C.byref(ph), st),
                     'tfb_channels_step_packed_p2p')
             elif self.kinematic:
                 L.check(self.lib.tfb_channels_step_packed(C.byref(a), C.byref(self.packed),
-                                                          L.stream_ptr()), 'tfb_channels_step_packed')
+                                                          st), 'tfb_channels_step_packed')
             elif peer is not None:
                 # diffusive wave, peer halo: pass A stores its boundary depths, pass B its
                 # boundary discharges into the neighbours' halo rows; phases 2n and 2n + 1
                 ps = 2 * self.n_steps if peer_step is None else int(peer_step)
                 ph = peer.descriptor(0, ps, depth=True)
                 L.check(self.lib.tfb_channels_step_packed_dw_a_p2p(
-                    C.byref(a), C.byref(self.packed), C.byref(ph), L.stream_ptr()),
+                    C.byref(a), C.byref(self.packed), C.byref(ph), st),
                     'tfb_channels_step_packed_dw_a_p2p')
                 ph = peer.descriptor(self.qcur ^ 1, ps + 1)
                 L.check(self.lib.tfb_channels_step_packed_dw_b_p2p(
-                    C.byref(a), C.byref(self.packed), C.byref(ph), L.stream_ptr()),
+                    C.byref(a), C.byref(self.packed), C.byref(ph), st),
                     'tfb_channels_step_packed_dw_b_p2p')
                 L.check(self.lib.tfb_channels_step_packed_dw_c(
-                    C.byref(a), C.byref(self.packed), L.stream_ptr()), 'tfb_channels_step_packed_dw_c')
+                    C.byref(a), C.byref(self.packed), st), 'tfb_channels_step_packed_dw_c')
             else:
                 # diffusive wave: new depths first, (slab: exchange one row of d), then
                 # free-surface slope, velocity and discharge
                 L.check(self.lib.tfb_channels_step_packed_dw_a(
-                    C.byref(a), C.byref(self.packed), L.stream_ptr()), 'tfb_channels_step_packed_dw_a')
+                    C.byref(a), C.byref(self.packed), st), 'tfb_channels_step_packed_dw_a')
                 if self.mid_step_hook is not None:
                     self.mid_step_hook()
                 L.check(self.lib.tfb_channels_step_packed_dw_b(
-                    C.byref(a), C.byref(self.packed), L.stream_ptr()), 'tfb_channels_step_packed_dw_b')
+                    C.byref(a), C.byref(self.packed), st), 'tfb_channels_step_packed_dw_b')
                 L.check(self.lib.tfb_channels_step_packed_dw_c(
-                    C.byref(a), C.byref(self.packed), L.stream_ptr()), 'tfb_channels_step_packed_dw_c')
+                    C.byref(a), C.byref(self.packed), st), 'tfb_channels_step_packed_dw_c')
             self.last_path = 'packed'
         else:
             if peer is not None:
@@ -751,7 +779,7 @@ class ChannelsEngine(object):
             if getattr(self, 'generic_released', False):
                 raise L.TfbError('this configuration needs the generic kernel, but its static '
                                  'inputs were released (release_generic_inputs)')
-            L.check(self.lib.tfb_channels_step(C.byref(a), L.stream_ptr()), 'tfb_channels_step')
+            L.check(self.lib.tfb_channels_step(C.byref(a), st), 'tfb_channels_step')
             self.last_path = 'generic'
             self.last_kernel = 'generic'
         self.qcur ^= 1
@@ -762,11 +790,18 @@ class ChannelsEngine(object):
         """The scalar block after the last step.  The kernel has already written it
         into the pinned host mirror; this only synchronises the stream.  (Before the
         first step, or after write_scalars, the block is copied explicitly.)"""
+        self.sync_scalar_mirror()
+        return L.ChannelsScalars.from_buffer_copy(self._scalars_np)
+
+    def sync_scalar_mirror(self):
+        """Wait until the pinned host mirror holds the scalar block of the last step;
+        returns it as float64 words (the 20 fp64 fields first, lib.ChannelsScalars)."""
         if self.n_steps == 0 or self._scalars_dirty:
             self._scalars_host.copy_(self.scalars_dev, non_blocking=True)
             self._scalars_dirty = False
-        torch.cuda.current_stream().synchronize()
-        return L.ChannelsScalars.from_buffer_copy(self._scalars_np)
+        L.check(self.lib.tfb_stream_synchronize(L.stream_ptr(self._dev_index)),
+                'tfb_stream_synchronize')
+        return self._scalars_f64
 
     def write_scalars(self, s):
         raw = torch.frombuffer(bytearray(bytes(s)), dtype=torch.uint8)

@@ -254,7 +254,10 @@ class SlabChannels(object):
         if layout.world_size > 1 and not engine.kinematic and self.peer is None:
             # packed diffusive step: the new depths of the boundary rows cross the link
             # between pass A and pass B
-            engine.mid_step_hook = lambda: exchange_halos([engine.d], layout, [1], group)
+            # (with FLOOD_OPTION the free surface is channel + flood depth: both rows)
+            engine.mid_step_hook = lambda: exchange_halos(
+                [engine.d] + ([engine.d_flood] if engine.flood else []), layout,
+                [1] * (2 if engine.flood else 1), group)
         if self.peer is not None and not engine.kinematic and not self.peer.with_depth:
             raise L.TfbError('diffusive peer halos need PeerHalos(with_depth=True)')
 
