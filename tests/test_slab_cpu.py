@@ -114,3 +114,52 @@ def test_peer_halo_descriptor_addresses():
         ph.nbr.pop('up')
         d = ph.descriptor(0, 0)
         assert not d.up_Q and not d.up_flag and not d.from_up and d.down_Q
+
+
+def _board_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    import numpy as np
+    import torch.distributed as dist
+    from topoflow36_b200 import slab as S
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        lay = S.SlabLayout(world * 8, 16, rank, world, 1)
+        ok = S.ScalarBoard.usable(lay)
+        board = S.ScalarBoard(lay, 232)
+        dist.barrier()
+        ok &= not os.path.exists(board._path)               # unlinked once everyone has mapped it
+        rng = np.random.default_rng(rank)
+        for k in range(1, 301):
+            mine = np.arange(29, dtype=np.float64) + 1000.0 * rank + k
+            if rank == k % world:
+                # a slow rank: the others must wait for it and must not overwrite its bank
+                import time
+                time.sleep(0.0005 * rng.random())
+            got = board.exchange(mine)
+            want = np.stack([np.arange(29, dtype=np.float64) + 1000.0 * r + k for r in range(world)])
+            ok &= bool(np.array_equal(got, want))
+        board.close()
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 4])
+def test_scalar_board_shared_memory(world):
+    """slab.ScalarBoard: the ranks' scalar blocks exchanged through one shared-memory segment
+    (two banks, sequence words) -- every read returns every rank's block of THAT read, also
+    when ranks arrive at different times."""
+    if not os.path.isdir('/dev/shm'):
+        pytest.skip('no /dev/shm')
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_board_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r for r, _ in res) == list(range(world))
+    assert all(ok for _, ok in res), res

@@ -666,33 +666,25 @@ class channels_component(BMI_base.BMI_component):
 
     def sync_scalars(self):
         """Refresh the 0-D arrays in place from the scalar block the kernel wrote
-        into pinned host memory (one stream synchronise, no copy; in slab mode one
-        all-reduce forms the global values -- collective)."""
+        into pinned host memory (one stream synchronise, no copy; in slab mode the
+        ranks' blocks meet in shared memory, slab.ScalarBoard, or in one all-gather, and
+        are reduced on the host -- collective)."""
         b = self.bad_counts
+        # the 8-byte words of lib.ChannelsScalars: straight from the pinned mirror on one GPU,
+        # reduced over the ranks' blocks in slab mode
         if self.layout is None:
-            # single GPU: straight from the pinned mirror (layout of lib.ChannelsScalars:
-            # 20 float64 words, then the int64 counters)
             e = self.engine
-            f = e.sync_scalar_mirror()
-            i = e._scalars_i64
-            if i[_IX_FAIL]:
-                self._step_failed(int(i[_IX_FAIL]))
-            self._scalar_block[:] = f[:len(_SCALAR_BLOCK)]
-            self.dt_cfl_min.fill(f[_IX_DTMIN])
-            (b['n_neg_d'], b['n_nan_d'], b['n_inf_d'], b['n_neg_u'], b['n_nan_u'],
-             b['n_inf_u']) = i[_IX_CNT:_IX_CNT + 6].tolist()
-            return None
-        s = self.stepper.read_scalars()
-        if s.n_step_failed:
+            f, i = e.sync_scalar_mirror(), e._scalars_i64
+        else:
+            f, i = self.stepper.read_scalar_words()
+        if i[_IX_FAIL]:
             # a bounded wait inside the kernel ran out (TMA pipeline, or a slab neighbour that
             # never delivered its halo rows): the grids of that step are not valid
-            self._step_failed(s.n_step_failed)
-        for n in _SCALAR_BLOCK:
-            getattr(self, n).fill(getattr(s, n))
-        self.dt_cfl_min.fill(s.dt_cfl_min)
-        b['n_neg_d'], b['n_nan_d'], b['n_inf_d'] = s.n_neg_d, s.n_nan_d, s.n_inf_d
-        b['n_neg_u'], b['n_nan_u'], b['n_inf_u'] = s.n_neg_u, s.n_nan_u, s.n_inf_u
-        return s
+            self._step_failed(int(i[_IX_FAIL]))
+        self._scalar_block[:] = f[:len(_SCALAR_BLOCK)]
+        self.dt_cfl_min.fill(f[_IX_DTMIN])
+        (b['n_neg_d'], b['n_nan_d'], b['n_inf_d'], b['n_neg_u'], b['n_nan_u'],
+         b['n_inf_u']) = i[_IX_CNT:_IX_CNT + 6].tolist()
 
     def _step_failed(self, n):
         self.status = 'failed'

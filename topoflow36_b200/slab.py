@@ -18,7 +18,14 @@ is bit-identical to a 1-GPU run in every grid (tests/test_slab_gpu.py), and the
 global sums differ only by summation order.
 """
 import ctypes as C
+import mmap
+import os
+import platform
+import socket
+import tempfile
+import time
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -201,6 +208,88 @@ class PeerHalos(object):
         self._mine = []
 
 
+class ScalarBoard(object):
+    """The ranks' scalar blocks side by side in ONE POSIX shared-memory segment (all ranks of
+    a slab run sit on one box): how `SlabChannels.read_scalars` forms the global values
+    without a collective.  A synchronous `update()` reads the scalars every step
+    (CHECK_STABILITY, Q_outlet for the driver); an NCCL all-gather + device-to-host copy +
+    stream synchronise there costs ~50 us per step on a 0.26 ms step, a 232-byte host copy
+    and a poll of the neighbours' sequence words ~5 us.
+
+    Layout: 2 banks x world slots of `SLOT` bytes; a slot = the block + a sequence word.
+    The k-th collective read uses bank k & 1: a rank copies its block in, THEN stores k
+    (x86-TSO: stores are seen in program order; other machines take the NCCL path), and
+    polls until every slot of the bank holds k.  Bank k & 1 is written again at read
+    k + 2, which a rank reaches only after EVERY rank has published k + 1, i.e. has finished
+    reading bank k & 1 -- no rank can overwrite a block another one is still reading.
+    No kernel writes here: each rank's kernel keeps writing its own pinned mirror."""
+    SLOT = 256
+
+    def __init__(self, layout, nbytes, group=None):
+        self.world, self.rank, self.nbytes = layout.world_size, layout.rank, int(nbytes)
+        assert self.nbytes + 8 <= self.SLOT and self.nbytes % 8 == 0
+        self.nw = self.nbytes // 8
+        size = 2 * self.world * self.SLOT
+        box = [None]
+        if self.rank == 0:
+            fd, path = tempfile.mkstemp(prefix='tfb_scalars_', dir='/dev/shm')
+            os.ftruncate(fd, size)
+            os.close(fd)
+            box[0] = path
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        dist.broadcast_object_list(box, src=src, group=group)
+        self._path = box[0]
+        fd = os.open(self._path, os.O_RDWR)
+        try:
+            self._mm = mmap.mmap(fd, size)
+        finally:
+            os.close(fd)
+        dist.barrier(group=group)                 # everyone has it mapped: the name can go
+        if self.rank == 0:
+            os.unlink(self._path)
+        words = np.frombuffer(self._mm, dtype=np.float64).reshape(2, self.world, self.SLOT // 8)
+        self._blocks = words[:, :, :self.nw]                         # (2, world, nw) float64
+        self._seq = words.view(np.int64)[:, :, self.SLOT // 8 - 1]   # (2, world) sequence words
+        self.k = 0
+
+    @staticmethod
+    def usable(layout, group=None):
+        """All ranks on one x86 host with /dev/shm (decided collectively)."""
+        ok = (platform.machine() in ('x86_64', 'AMD64') and os.path.isdir('/dev/shm')
+              and os.access('/dev/shm', os.W_OK) and os.environ.get('TFB_SCALAR_BOARD', '1') != '0')
+        try:
+            boot = open('/proc/sys/kernel/random/boot_id').read().strip()
+        except OSError:
+            boot = ''
+        mine = (socket.gethostname(), boot, bool(ok))
+        every = [None] * layout.world_size
+        dist.all_gather_object(every, mine, group=group)
+        return all(e[2] for e in every) and len(set(e[:2] for e in every)) == 1
+
+    def exchange(self, block_words, timeout_s=120.0):
+        """Collective: publish my block (float64 words), return all blocks (world, nw)."""
+        self.k += 1
+        k, b = self.k, self.k & 1
+        self._blocks[b, self.rank, :] = block_words[:self.nw]
+        self._seq[b, self.rank] = k
+        seq = self._seq[b]
+        t0 = None
+        while not (seq == k).all():
+            if t0 is None:
+                t0 = time.perf_counter()
+            elif time.perf_counter() - t0 > timeout_s:
+                raise L.TfbError('scalar board: rank(s) %s did not publish read %d within %g s'
+                                 % (np.nonzero(seq != k)[0].tolist(), k, timeout_s))
+        return self._blocks[b]
+
+    def close(self):
+        self._blocks = self._seq = None
+        try:
+            self._mm.close()
+        except (BufferError, ValueError):
+            pass
+
+
 def make_peer_halos(layout, device, group=None, with_depth=False):
     """PeerHalos on every rank, or None on every rank: if CUDA IPC is not usable on any
     rank (containers without shared /dev/shm or IPC permission, no peer access) all
@@ -260,6 +349,10 @@ class SlabChannels(object):
                 [1] * (2 if engine.flood else 1), group)
         if self.peer is not None and not engine.kinematic and not self.peer.with_depth:
             raise L.TfbError('diffusive peer halos need PeerHalos(with_depth=True)')
+        # global scalars without a collective where the ranks share a host (ScalarBoard)
+        self.board = None
+        if layout.world_size > 1 and dist.get_backend(group) == 'nccl' and ScalarBoard.usable(layout, group):
+            self.board = ScalarBoard(layout, C.sizeof(L.ChannelsScalars), group)
 
     def __getattr__(self, name):           # state access falls through to the engine
         return getattr(self.__dict__['engine'], name)
@@ -279,7 +372,7 @@ class SlabChannels(object):
 
     def step(self, time_min=0.0):
         e = self.engine
-        packed = e._packed_ok()
+        packed = e._config()[0]
         if self.peer is not None and packed == 'lean':
             # halo rows travel inside the kernel(s); the flag words count PEER steps only,
             # so NCCL steps in between (below) leave the protocol in step
@@ -298,34 +391,43 @@ class SlabChannels(object):
         if packed and not e.kinematic:
             self._state_halos_stale = True
 
-    def read_scalars(self):
-        """Global scalar block (collective: every rank must call it).  ONE all-gather
-        of the 28-value blocks, reduced on the device, one device->host copy."""
+    def read_scalar_words(self):
+        """Global scalar block (collective: every rank must call it) as the 8-byte words of
+        lib.ChannelsScalars: (float64 view, int64 view) of one array.  The ranks' blocks are
+        exchanged through the shared-memory ScalarBoard (one box) or ONE NCCL all-gather."""
         e = self.engine
         if self.layout.world_size == 1:
-            return e.read_scalars()
+            return e.sync_scalar_mirror(), e._scalars_i64
         nf, nc = len(self._SUM_FIELDS), len(self._CNT_FIELDS)
-        raw = e.scalars_dev.view(torch.float64)          # 20 doubles + 9 int64 bit patterns
-        if getattr(self, '_allv', None) is None:
-            self._allv = torch.empty((self.layout.world_size, raw.numel()), dtype=torch.float64,
-                                     device=self.device)
-            self._allh = torch.empty_like(self._allv, device='cpu').pin_memory()
-        dist.all_gather_into_tensor(self._allv, raw, group=self.group)
-        self._allh.copy_(self._allv, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        hf = self._allh.numpy()                          # (world, 28): reduced on the host
-        hi = hf.view('int64')
-        s = L.ChannelsScalars()
-        sums = hf[:, :nf].sum(0)
-        for k, n in enumerate(self._SUM_FIELDS):
-            setattr(s, n, float(sums[k]))
-        s.dt_cfl_min = float(hf[:, nf].min())            # a MIN, not a SUM
-        cnts = hi[:, nf + 1:nf + 1 + nc].sum(0)
-        for k, n in enumerate(self._CNT_FIELDS):
-            setattr(s, n, int(cnts[k]))
-        s.step_count = e.n_steps
-        s.n_step_failed = int(hi[:, nf + 1 + nc + 1].sum())
-        return s
+        if self.board is not None:
+            hf = self.board.exchange(e.sync_scalar_mirror())
+        else:
+            raw = e.scalars_dev.view(torch.float64)          # 20 doubles + 9 int64 bit patterns
+            if getattr(self, '_allv', None) is None:
+                self._allv = torch.empty((self.layout.world_size, raw.numel()), dtype=torch.float64,
+                                         device=self.device)
+                self._allh = torch.empty_like(self._allv, device='cpu').pin_memory()
+            dist.all_gather_into_tensor(self._allv, raw, group=self.group)
+            self._allh.copy_(self._allv, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            hf = self._allh.numpy()                          # (world, 29): reduced on the host
+        hi = hf.view(np.int64)
+        if getattr(self, '_red', None) is None:
+            self._red = np.zeros(hf.shape[1], dtype=np.float64)
+            self._red_i = self._red.view(np.int64)
+        out, out_i = self._red, self._red_i
+        out[:nf] = hf[:, :nf].sum(0)
+        out[nf] = hf[:, nf].min()                            # dt_cfl_min: a MIN, not a SUM
+        out_i[nf + 1:nf + 1 + nc] = hi[:, nf + 1:nf + 1 + nc].sum(0)
+        out_i[nf + 1 + nc] = e.n_steps                       # step_count
+        out_i[nf + 2 + nc] = hi[:, nf + 2 + nc].sum()        # n_step_failed
+        return out, out_i
+
+    def read_scalars(self):
+        """The global scalar block as a lib.ChannelsScalars (collective)."""
+        if self.layout.world_size == 1:
+            return self.engine.read_scalars()
+        return L.ChannelsScalars.from_buffer_copy(self.read_scalar_words()[0])
 
     def global_dt_min(self):
         return self.read_scalars().dt_cfl_min
