@@ -157,6 +157,7 @@ def _comp_worker(rank, world, port, case_dir, kinematic, q):
         scal = {n: float(getattr(c, n)) for n in ('vol_R', 'vol_edge', 'vol_Q', 'Q_outlet', 'Q_peak',
                                                    'T_peak')}
         c.finalize()
+        dist.barrier()                            # every rank's rows of the output frames are on disk
         scal['vol_chan_sum'] = float(c.vol_chan_sum)
         scal['Q_max'] = float(c.Q_max)
         ok, fails = True, []
@@ -175,6 +176,18 @@ def _comp_worker(rank, world, port, case_dir, kinematic, q):
                 if not np.array_equal(g, getattr(one, n)):
                     fails.append('%s differs in %d cells' % (n, int((g != getattr(one, n)).sum())))
             one.finalize()
+            # output files: every rank wrote its own rows of each frame into ONE stack; the
+            # single-GPU run found those names taken and wrote <name>_1 (BMI "_unique")
+            import glob
+            for stem in ('Case1_2D-Q', 'Case1_2D-d', 'Case1_0D-Q'):
+                ext = '.txt' if '0D' in stem else '.rts'
+                fa, fb = (os.path.join(case_dir, stem + sfx + ext) for sfx in ('', '_1'))
+                if not (os.path.exists(fa) and os.path.exists(fb)):
+                    fails.append('missing output %s: %s' % (stem, sorted(glob.glob(case_dir + '/Case1_*D*'))))
+                elif open(fa, 'rb').read() != open(fb, 'rb').read():
+                    fails.append('output file %s differs between 2 slabs and 1 GPU' % stem)
+                elif ext == '.rts' and os.path.getsize(fa) != 3 * ny * nx * 4:
+                    fails.append('%s: %d bytes, expected 3 frames' % (stem, os.path.getsize(fa)))
             for n, v in scal.items():
                 w = float(getattr(one, n))
                 if abs(v - w) > 1e-12 * max(abs(w), 1e-300):
@@ -205,8 +218,13 @@ def test_component_two_slabs_equal_one_gpu(tmp_path, kinematic):
     tk = D8Toolkit(DEM)
     tk.update_flow_grid()
     slope = tk.slope().cpu().numpy()
-    synth.write_case(str(tmp_path), DEM, slope, width, angle, nval=nval, dt=2.0,
-                     kinematic=kinematic, outlet=(ny - 2, nx // 2), check_stability='Yes')
+    cfg = synth.write_case(str(tmp_path), DEM, slope, width, angle, nval=nval, dt=2.0,
+                           kinematic=kinematic, outlet=(ny - 2, nx // 2), check_stability='Yes')
+    txt = open(cfg).read()
+    for k in ('SAVE_Q_GRIDS        | No', 'SAVE_D_GRIDS        | No', 'SAVE_Q_PIXELS       | No'):
+        assert k in txt
+        txt = txt.replace(k, k[:-2] + 'Yes')
+    open(cfg, 'w').write(txt)
     world = 2
     ctx = mp.get_context('spawn')
     q = ctx.Queue()

@@ -815,23 +815,41 @@ class channels_component(BMI_base.BMI_component):
     # two writers of the reference that need no netCDF (utils/rts_files.py,
     # utils/text_ts_files.py); frames are fetched from the device only when due.
     def open_output_files(self):
+        """Grid stacks: ONE file per variable.  In slab mode rank 0 creates it (and its RTI
+        side-car), every rank opens it and later writes ITS rows of each frame at their
+        offset -- no gather, the ranks write in parallel.  Outlet series: rank 0."""
         self._out = {}
-        if self.layout is not None and self.layout.rank != 0:
-            self._out_any = any(getattr(self, 'SAVE_%s_%s' % (K, kind))
-                                for K in 'QUDF' for kind in ('GRIDS', 'PIXELS'))
-            return
-        self._out_any = True
+        self._frame_no = {}
+        slab = self.layout is not None
+        rank0 = not slab or self.layout.rank == 0
+        self._out_any = any(getattr(self, 'SAVE_%s_%s' % (K, kind))
+                            for K in 'QUDF' for kind in ('GRIDS', 'PIXELS'))
         kinds = {'Q': 'Q', 'U': 'u', 'D': 'd', 'F': 'f'}
+        gs_paths = {}
         for K, v in kinds.items():
-            if getattr(self, 'SAVE_%s_GRIDS' % K):
+            if getattr(self, 'SAVE_%s_GRIDS' % K) and rank0:
                 f = getattr(self, v + '_gs_file', self.case_prefix + '_2D-' + v + '.nc')
                 path = self.out_directory + os.path.splitext(os.path.basename(f))[0] + '.rts'
                 os.makedirs(self.out_directory, exist_ok=True)
                 path = self._unique(path)
-                self._out[('gs', v)] = open(path, 'wb')
+                self._out[('gs', v)] = open(path, 'w+b')
+                gs_paths[v] = path
                 # side-car header like rts_files.open_new_file (:255-268, MAKE_RTI): the
                 # data set's own geometry and BYTE ORDER, FLOAT frames, min/max unknown
                 grid_io.write_output_rti(path, self.rti, 'FLOAT')
+        if slab and any(getattr(self, 'SAVE_%s_GRIDS' % K) for K in kinds):
+            import torch.distributed as dist
+            box = [gs_paths]
+            src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+            dist.broadcast_object_list(box, src=src, group=self.group)     # (also orders the create)
+            if not rank0:
+                for v, path in box[0].items():
+                    self._out[('gs', v)] = open(path, 'r+b')
+        for v in [k[1] for k in self._out if k[0] == 'gs']:
+            self._frame_no[v] = 0
+        if not rank0:
+            return
+        for K, v in kinds.items():
             if getattr(self, 'SAVE_%s_PIXELS' % K):
                 f = getattr(self, v + '_ts_file', self.case_prefix + '_0D-' + v + '.txt')
                 path = self.out_directory + os.path.splitext(os.path.basename(f))[0] + '.txt'
@@ -857,8 +875,9 @@ class channels_component(BMI_base.BMI_component):
         GPU: the frame is snapshotted on the device (cast to float32, ~50 us for 4096^2),
         copied to pinned host memory on a side stream and written by a background
         thread -- the step loop never waits for PCIe or the disk.  Outlet series are a
-        device-side gather of the monitored cells.  Slab mode: grids are gathered to
-        rank 0, which writes."""
+        device-side gather of the monitored cells.  Slab mode: every rank writes its own
+        rows of a frame into the shared file the same way (positional writes, no gather);
+        the monitored cells are summed over the ranks (each lives on one)."""
         if not getattr(self, '_out', None) and not (self.layout is not None and
                                                     getattr(self, '_out_any', False)):
             return
@@ -872,28 +891,27 @@ class channels_component(BMI_base.BMI_component):
                 if not getattr(self, flag + ('_GRIDS' if kind == 'gs' else '_PIXELS')):
                     continue
                 fh = self._out.get((kind, v))
-                if slab:
-                    # every rank takes part in the gather, rank 0 writes
-                    grid = self.gather_grid(v)
-                    if fh is None:
-                        continue
-                    if kind == 'gs':
-                        frame = np.float32(grid)                     # rts_files.add_grid :375-389
-                        if self.rti.SWAP_ENDIAN:
-                            frame = frame.byteswap()
-                        frame.tofile(fh)
-                    else:
-                        self._write_ts_line(fh, grid[self.outlet_IDs])
-                elif kind == 'gs':
+                if kind == 'gs':
+                    # this rank's rows of the frame, at their place in the file
                     self._async_frame(v, fh)
-                else:
-                    import torch
-                    if getattr(self, '_outlet_idx', None) is None:
-                        rows, cols = self.outlet_IDs
-                        self._outlet_idx = (torch.as_tensor(rows, device=self.engine.device),
-                                            torch.as_tensor(cols, device=self.engine.device))
-                    vals = self._device_tensor(v)[self._outlet_idx].cpu().numpy()
-                    self._write_ts_line(fh, vals)
+                    continue
+                import torch
+                if getattr(self, '_outlet_idx', None) is None:
+                    rows, cols = (np.asarray(x) for x in self.outlet_IDs)
+                    r0 = self.layout.row0 if slab else 0
+                    mine = (rows >= r0) & (rows < r0 + self.engine.ny)
+                    dev = self.engine.device
+                    self._outlet_idx = (torch.as_tensor(np.where(mine, rows - r0, 0), device=dev),
+                                        torch.as_tensor(np.where(mine, cols, 0), device=dev),
+                                        torch.as_tensor(mine, device=dev))
+                ri, ci, mine = self._outlet_idx
+                vals = torch.where(mine, self._device_tensor(v)[ri, ci], 0.0)
+                if slab:
+                    # a monitored cell lives on one rank: the sum over ranks is its value
+                    import torch.distributed as dist
+                    dist.all_reduce(vals, op=dist.ReduceOp.SUM, group=self.group)
+                if fh is not None:
+                    self._write_ts_line(fh, vals.cpu().numpy())
 
     def _write_ts_line(self, fh, vals):
         # text_ts_files.add_values :149-161 (20-wide columns), values_at_IDs :170-198 (float32)
@@ -905,14 +923,16 @@ class channels_component(BMI_base.BMI_component):
         import threading
         import torch
         w = getattr(self, '_writer', None)
+        ny_own = self.engine.ny                       # all rows on one GPU, this slab's otherwise
+        row0 = self.layout.row0 if self.layout is not None else 0
         if w is None:
             dev = self.engine.device
             n_slots = 3
             w = self._writer = dict(
                 stream=torch.cuda.Stream(device=dev), q=queue.Queue(), free=queue.Queue(),
-                stage=[torch.empty((self.ny, self.nx), dtype=torch.float32, device=dev)
+                stage=[torch.empty((ny_own, self.nx), dtype=torch.float32, device=dev)
                        for _ in range(n_slots)],
-                host=[torch.empty((self.ny, self.nx), dtype=torch.float32).pin_memory()
+                host=[torch.empty((ny_own, self.nx), dtype=torch.float32).pin_memory()
                       for _ in range(n_slots)], error=[])
             for k in range(n_slots):
                 w['free'].put(k)
@@ -922,10 +942,13 @@ class channels_component(BMI_base.BMI_component):
                     item = w['q'].get()
                     if item is None:
                         return
-                    k, ev, out = item
+                    k, ev, out, offset = item
                     try:
                         ev.synchronize()
-                        w['host'][k].numpy().tofile(out)
+                        buf = memoryview(w['host'][k].numpy()).cast('B')
+                        done = 0
+                        while done < len(buf):        # positional: ranks share the file
+                            done += os.pwrite(out.fileno(), buf[done:], offset + done)
                     except Exception as exc:            # surfaced at close_output_files()
                         w['error'].append(exc)
                     w['free'].put(k)
@@ -938,7 +961,7 @@ class channels_component(BMI_base.BMI_component):
             # frames go out in the data set's byte order (rts_files.add_grid :387-389):
             # the four bytes of every float32 are reversed on the device, so the host
             # side still writes the pinned buffer as it is
-            b = w['stage'][k].view(torch.uint8).view(self.ny, self.nx, 4)
+            b = w['stage'][k].view(torch.uint8).view(ny_own, self.nx, 4)
             b.copy_(b.flip(2))
         ready = torch.cuda.Event()
         ready.record(cur)
@@ -947,7 +970,10 @@ class channels_component(BMI_base.BMI_component):
             w['host'][k].copy_(w['stage'][k], non_blocking=True)
             done = torch.cuda.Event()
             done.record(w['stream'])
-        w['q'].put((k, done, fh))
+        # frame n of an (ny, nx) float32 stack (rts_files.add_grid :375-389), rows from row0
+        offset = (self._frame_no[v] * self.ny + row0) * self.nx * 4
+        self._frame_no[v] += 1
+        w['q'].put((k, done, fh, offset))
 
     def close_output_files(self):
         w = getattr(self, '_writer', None)
