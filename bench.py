@@ -284,6 +284,58 @@ def cpu_reference_rate(budget_s, n_steps, warmup, nx=None, ny_max=None):
             'kind': 'reference', 'sample': desc, 'ms_per_step': dt / n_steps * 1e3, 'steps': n_steps}
 
 
+def _ref_instance(k, ny_i, nx, n_steps, work, barrier, q):
+    """One of the concurrent reference instances of cpu_reference_all_cores (own process)."""
+    try:
+        with np.errstate(all='ignore'):
+            step = _reference_stepper(ny_i, nx, os.path.join(work, 'inst%d' % k))
+            step()
+            barrier.wait(timeout=600)
+            t0 = time.perf_counter()
+            for _ in range(n_steps):
+                step()
+            q.put((k, time.perf_counter() - t0))
+    except Exception as exc:                                  # noqa: BLE001 -- reported, not fatal
+        q.put((k, repr(exc)))
+
+
+def cpu_reference_all_cores(n_steps=5, ny_i=256, nx=None):
+    """The reference's best case on this host: `nproc` CONCURRENT
+    independent instances of the unmodified reference (numpy has no threading), each stepping
+    its own `ny_i`-row strip of the bench case; aggregate cells / slowest instance's time."""
+    import multiprocessing as mp
+    from oracle import ref_harness as rh
+    if not rh.reference_available():
+        return None
+    nx = nx or NX
+    n = os.cpu_count() or 1
+    ctx = mp.get_context('spawn')
+    work = tempfile.mkdtemp(prefix='tfb_refall_')
+    barrier, q = ctx.Barrier(n), ctx.Queue()
+    procs = [ctx.Process(target=_ref_instance, args=(k, ny_i, nx, n_steps, work, barrier, q))
+             for k in range(n)]
+    try:
+        for p_ in procs:
+            p_.start()
+        res = [q.get(timeout=900) for _ in procs]
+        for p_ in procs:
+            p_.join(timeout=60)
+    finally:
+        for p_ in procs:
+            if p_.is_alive():
+                p_.terminate()
+        shutil.rmtree(work, ignore_errors=True)
+    bad = [r for r in res if not isinstance(r[1], float)]
+    if bad:
+        return {'error': str(bad[0][1])[:200]}
+    dt = max(r[1] for r in res)
+    return {'value': n * n_steps * ny_i * nx / dt / 1e9, 'unit': 'Gcell-updates/s', 'cores': n,
+            'kind': 'reference',
+            'sample': '%d concurrent independent instances of the unmodified reference (one per host '
+                      'core), each %d steps on its own %d x %d strip of the bench case; aggregate '
+                      'cells over the slowest instance\'s time' % (n, n_steps, ny_i, nx)}
+
+
 def cpu_baseline_block(ref_budget, port_budget, n_steps, warmup):
     """cpu_baseline of the JSON line: the reference itself when staged (kind "reference"),
     with the C port on all host threads beside it; the port alone otherwise."""
@@ -294,6 +346,7 @@ def cpu_baseline_block(ref_budget, port_budget, n_steps, warmup):
         port['note'] = 'oracle/_ref not staged: reference itself not timed'
         return port
     ref['port_all_threads'] = port
+    ref['reference_all_cores'] = cpu_reference_all_cores()
     return ref
 
 
@@ -315,9 +368,11 @@ def run_reference(args):
         v, desc, cores, _, _ = cpu_port_rate(15.0, nx=args.nx, ny_max=args.rows_per_gpu)
         ref['port_all_threads'] = {'value': v, 'unit': 'Gcell-updates/s', 'cores': cores,
                                    'kind': 'port', 'sample': desc}
+        ref['reference_all_cores'] = cpu_reference_all_cores(nx=args.nx)
         note = ('the unmodified reference through its own public API and stock code path (pure '
-                'Python/numpy, one process); the C restatement on all host threads is in '
-                'cpu_baseline.port_all_threads')
+                'Python/numpy, one process); its best case on this host -- one independent instance '
+                'per core -- is in cpu_baseline.reference_all_cores, the C restatement on all host '
+                'threads in cpu_baseline.port_all_threads')
     out = {
         'impl': 'reference', 'metric': METRIC, 'value': ref['value'], 'unit': 'Gcell-updates/s',
         'n_gpus': args.gpus, 'steps': ref['steps'], 'warmup': args.warmup,
