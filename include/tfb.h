@@ -352,6 +352,13 @@ typedef struct {
                                  angle; geo32 carries a 16-bit index, so up to 65536
                                  angles (the lean kernels keep their <= 256-entry
                                  angle_lut in shared memory)                           */
+    /* extended variants, inputs that are NOT float32 values (a scalar width such as 3.3 m
+     * from the CFG; slopes divided by a sinuosity != 1, channels_base.py:1247): the fp64
+     * grid takes the place of width32 / S32 (which may then be NULL)        (8 B / cell) */
+    const double *width64;
+    const double *S64;
+    const double *sinu64;     /* sinuosity GRID (ds = sinu * ds_d8 per cell, :1242);
+                                 row_geom is then built with sinu = 1         (8 B / cell) */
 } tfb_channels_packed;
 
 int64_t tfb_sizeof_channels_packed(void);

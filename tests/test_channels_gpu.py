@@ -600,6 +600,42 @@ def test_flood_with_attenuate_ext_equals_generic(flood_gold, tag):
         assert abs(getattr(sa, n) - getattr(sb, n)) <= 1e-12 * max(abs(getattr(sb, n)), 1e-300), n
 
 
+@pytest.mark.parametrize('tag', ['kw', 'dw'])
+def test_sinuosity_grid_and_fp64_inputs_ext_equals_generic(flood_gold, tag):
+    """A sinuosity GRID (ds = sinu * ds_d8 per cell, channels_base.py:1242), a scalar width
+    that is no float32 value (3.3 m) and slopes that are no float32 values: the extended
+    packed kernels take them as fp64 streams; compared with the generic kernel."""
+    g = flood_gold
+    kin = (tag == 'kw')
+    code = g['code']
+    ny, nx = code.shape
+    dx, dy, dd = o.pixel_dims(ny, 30.0, 30.0)
+    rng = np.random.default_rng(11)
+    sinu = 1.0 + 0.4 * rng.random((ny, nx))
+    slope = np.float64(g['slope']) / sinu
+    engs = []
+    for packed in (True, False):
+        eng = _engine(code, dx, dy, dd, slope, 3.3, g['angle'], g['nval'], dt=2.0, da=900.0,
+                      kinematic=kin, diag=True, outlet=(ny - 2, nx // 2), sinu=sinu, packed=packed)
+        eng.set_input('P_rain', 120 / 3.6e6)
+        for i in range(100):
+            if i == 70:
+                eng.set_input('P_rain', 0.0)
+            eng.step(time_min=(i * 2.0) / 60.0)
+        engs.append(eng)
+    a, b = engs
+    assert (a.last_kernel, b.last_kernel) == ('ext', 'generic')
+    assert a.packed.width64 and a.packed.S64 and a.packed.sinu64 and not a.packed.width32
+    for n in ('vol', 'Q'):
+        assert rel_err(getattr(a, n).cpu().numpy(), getattr(b, n).cpu().numpy()) <= 1e-12, n
+    for n in ('d', 'u', 'Rh', 'f', 'tau', 'froude'):
+        assert rel_err(a.own(getattr(a, n)).cpu().numpy(), b.own(getattr(b, n)).cpu().numpy()) <= 1e-12, n
+    assert float(a.Q.max()) > 0
+    sa, sb = a.read_scalars(), b.read_scalars()
+    for n in ('vol_R', 'vol_edge', 'vol_Q', 'Q_peak', 'd_peak', 'u_peak'):
+        assert abs(getattr(sa, n) - getattr(sb, n)) <= 1e-12 * max(abs(getattr(sb, n)), 1e-300), n
+
+
 def test_flood_component_from_cfg(tmp_path, flood_gold):
     """FLOOD_OPTION read from the CFG file by the BMI component."""
     from topoflow36_b200 import channels_kinematic_wave as ckw, synth

@@ -49,9 +49,10 @@ struct ExtConsts {
     long long d00_index;       //         its offset from the first owned row
     int atten, flood;          // ATTENUATE, FLOOD_OPTION
     int oVs, oVb, oDf;         // ring-slot offsets: vol_stored, vol_bankfull (-1 = scalar), d_flood halo tile
+    int w64, s64, oSinu;       // width / bed slope streams are fp64 grids; sinuosity grid stream (-1 = none)
     double t_drain, vb_val, width_ratio, flood_n;
 };
-struct ExtMaps { CUtensorMap Q, vol, geo, w, S, rough, F[F_N], vs, vb, df; };   // Q: discharge, or depth (pass B)
+struct ExtMaps { CUtensorMap Q, vol, geo, w, S, rough, F[F_N], vs, vb, df, sinu; };   // Q: discharge, or depth (pass B)
 
 template <int VAR, bool LOW, bool DIAG>
 __device__ __forceinline__ void ext_cell(const tfb_channels_step_args &a, const tfb_channels_packed &p,
@@ -62,11 +63,13 @@ __device__ __forceinline__ void ext_cell(const tfb_channels_step_args &a, const 
     const unsigned geo = *reinterpret_cast<const unsigned *>(st + k.oGeo + e * 4);
     const unsigned code = geo & 0xffu, cmask = (geo >> 8) & 0xffu, ai = geo >> 16;
     const bool noflow = (code == 0u);
-    const double w = (double)*reinterpret_cast<const float *>(st + k.oW + e * 4);
+    const double w = k.w64 ? *reinterpret_cast<const double *>(st + k.oW + e * 8)
+                           : (double)*reinterpret_cast<const float *>(st + k.oW + e * 4);
     const double2 tc = __ldg(reinterpret_cast<const double2 *>(p.lut_tc) + ai);   // {tan, cos}
     const double *rg = p.row_geom + (int64_t)r * kRowGeom;          // ds_ew, ds_diag, ds_ns, ., ., ., da
     const bool dg = (code & 0x55u) != 0u, ns = (code & 0x88u) != 0u;
-    const double ds = __ldg(rg + (dg ? 1 : (ns ? 2 : 0)));
+    double ds = __ldg(rg + (dg ? 1 : (ns ? 2 : 0)));
+    if (k.oSinu >= 0) ds = *reinterpret_cast<const double *>(st + k.oSinu + e * 8) * ds;   // :1242
     const int64_t i = (int64_t)r * a.pitch + c;
     const double dt = k.dt;
     double v = 0.0, d = 0.0, qself = 0.0;
@@ -146,7 +149,8 @@ __device__ __forceinline__ void ext_cell(const tfb_channels_step_args &a, const 
         }
         return;
     }
-    double S = (double)*reinterpret_cast<const float *>(st + k.oS + e * 4);
+    double S = k.s64 ? *reinterpret_cast<const double *>(st + k.oS + e * 8)
+                     : (double)*reinterpret_cast<const float *>(st + k.oS + e * 4);
     const double rough = *reinterpret_cast<const double *>(st + k.oRough + e * 8);
     double slope_t = S;                                              // kinematic: S_bed as it is
     if (VAR == EXT_DWB) {
@@ -280,6 +284,7 @@ channels_ext_kernel(const tfb_channels_step_args a, const tfb_channels_packed p,
                 tma_load_2d(st + k.oQ, &maps.Q, bar, c0 - 2, r0 - 1 + a.halo);
                 tma_load_2d(st + k.oGeo, &maps.geo, bar, c0, r0);
                 tma_load_2d(st + k.oW, &maps.w, bar, c0, r0);
+                if (k.oSinu >= 0) tma_load_2d(st + k.oSinu, &maps.sinu, bar, c0, r0);
                 if (VAR != EXT_DWB) {
                     tma_load_2d(st + k.oVol, &maps.vol, bar, c0, r0 + a.halo);
 #pragma unroll
@@ -352,7 +357,8 @@ int launch_ext(const tfb_channels_step_args &a, const tfb_channels_packed &p, Ex
     auto put = [&](int bytes_padded, int bytes_tma) { const int o = off; off += bytes_padded; tx += (unsigned)bytes_tma; return o; };
     k.oQ = put(TC::szQ, TC::nQ);
     k.oGeo = put(TC::szF, TC::nF);
-    k.oW = put(TC::szF, TC::nF);
+    k.oW = k.w64 ? put(TC::szD, TC::nD) : put(TC::szF, TC::nF);
+    k.oSinu = p.sinu64 ? put(TC::szD, TC::nD) : -1;
     k.oVol = k.oS = k.oRough = 0;
     const tfb_sg *F[F_N] = {&a.P_rain, &a.SM, &a.GW, &a.MR, &a.ET, &a.IN};
     if (VAR != EXT_DWB) {
@@ -367,7 +373,7 @@ int launch_ext(const tfb_channels_step_args &a, const tfb_channels_packed &p, Ex
         k.oDf = put(TC::szQ, TC::nQ);
     }
     if (VAR != EXT_DWA) {
-        k.oS = put(TC::szF, TC::nF);
+        k.oS = k.s64 ? put(TC::szD, TC::nD) : put(TC::szF, TC::nF);
         k.oRough = put(TC::szD, TC::nD);
     }
     k.stage_bytes = off;
@@ -385,7 +391,13 @@ int launch_ext(const tfb_channels_step_args &a, const tfb_channels_packed &p, Ex
     const double *halo_src = (VAR == EXT_DWB) ? a.d : a.Q_in;
     if ((rc = pk_get_map(halo_src - hb, rows_h, a.nx, a.pitch, F64, 8, kQW, kQR, &m.Q))) return rc;
     if ((rc = pk_get_map(p.geo32, a.ny, a.nx, a.pitch, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, kTW, kTR, &m.geo))) return rc;
-    if ((rc = pk_get_map(p.width32, a.ny, a.nx, a.pitch, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, kTW, kTR, &m.w))) return rc;
+    if (k.w64) {
+        if ((rc = pk_get_map(p.width64, a.ny, a.nx, a.pitch, F64, 8, kTW, kTR, &m.w))) return rc;
+    } else {
+        if ((rc = pk_get_map(p.width32, a.ny, a.nx, a.pitch, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, kTW, kTR, &m.w))) return rc;
+    }
+    if (p.sinu64)
+        if ((rc = pk_get_map(p.sinu64, a.ny, a.nx, a.pitch, F64, 8, kTW, kTR, &m.sinu))) return rc;
     if (VAR != EXT_DWB) {
         if ((rc = pk_get_map(a.vol - hb, rows_h, a.nx, a.pitch, F64, 8, kTW, kTR, &m.vol))) return rc;
         for (int j = 0; j < F_N; ++j)
@@ -399,7 +411,11 @@ int launch_ext(const tfb_channels_step_args &a, const tfb_channels_packed &p, Ex
         if ((rc = pk_get_map(a.d_flood - hb, rows_h, a.nx, a.pitch, F64, 8, kQW, kQR, &m.df))) return rc;
     }
     if (VAR != EXT_DWA) {
-        if ((rc = pk_get_map(p.S32, a.ny, a.nx, a.pitch, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, kTW, kTR, &m.S))) return rc;
+        if (k.s64) {
+            if ((rc = pk_get_map(p.S64, a.ny, a.nx, a.pitch, F64, 8, kTW, kTR, &m.S))) return rc;
+        } else {
+            if ((rc = pk_get_map(p.S32, a.ny, a.nx, a.pitch, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, kTW, kTR, &m.S))) return rc;
+        }
         if ((rc = pk_get_map(p.rough64, a.ny, a.nx, a.pitch, F64, 8, kTW, kTR, &m.rough))) return rc;
     }
     const int smem = k.n_stages * k.stage_bytes;
@@ -426,8 +442,8 @@ int prepare_ext(const tfb_channels_step_args *ap, tfb_channels_step_args &a,
     if (a.pitch == 0) a.pitch = a.nx;
     const tfb_channels_packed &p = *pp;
     TFB_ARG_CHECK(a.ny > 0 && a.nx > 0 && a.halo >= 0 && a.pitch >= a.nx && (a.pitch % 4) == 0);
-    TFB_ARG_CHECK(p.geo32 && p.width32 && p.lut_tc && p.row_geom && p.S32 && p.rough64 &&
-                  p.n_angles >= 1 && p.n_angles <= 65536);
+    TFB_ARG_CHECK(p.geo32 && (p.width32 || p.width64) && p.lut_tc && p.row_geom &&
+                  (p.S32 || p.S64) && p.rough64 && p.n_angles >= 1 && p.n_angles <= 65536);
     TFB_ARG_CHECK(a.vol && a.vol_out && a.Q_in && a.Q_out && a.d && a.u);
     TFB_ARG_CHECK(a.Q_in != a.Q_out && a.scalars && a.partials && a.ticket && a.dt > 0.0);
     TFB_ARG_CHECK(!(a.flags & (TFB_CH_SRC_MET | TFB_CH_SRC_SNOW | TFB_CH_SRC_EVAP | TFB_CH_SRC_INFIL)));
@@ -436,13 +452,14 @@ int prepare_ext(const tfb_channels_step_args *ap, tfb_channels_step_args &a,
     if (a.flags & TFB_CH_ATTENUATE)
         TFB_ARG_CHECK(a.vol_stored && a.vol_stored_out && a.t_drain > 0.0);
     TFB_ARG_CHECK(((a.flags & TFB_CH_DIFFUSIVE) != 0) == diffusive);
-    TFB_ARG_CHECK(!a.sinu.ptr);
+    TFB_ARG_CHECK(!a.sinu.ptr || p.sinu64);        // a sinuosity grid comes as a packed stream
     if (a.flags & TFB_CH_DIAG)
         TFB_ARG_CHECK(a.Rh && a.A_wet && a.P_wet && a.f && a.tau && a.u_star && a.froude);
     if (a.flags & TFB_CH_WRITE_R) TFB_ARG_CHECK(a.R != nullptr);
     auto al16 = [](const void *q) { return (((uintptr_t)q) & 15u) == 0; };
     TFB_ARG_CHECK(al16(a.vol) && al16(a.Q_in) && al16(a.d) && al16(p.rough64) && al16(p.lut_tc) &&
-                  al16(p.geo32) && al16(p.width32) && al16(p.S32) && al16(a.P_rain.ptr) &&
+                  al16(p.geo32) && al16(p.width32) && al16(p.S32) && al16(p.width64) && al16(p.S64) &&
+                  al16(p.sinu64) && al16(a.P_rain.ptr) &&
                   al16(a.SM.ptr) && al16(a.GW.ptr) && al16(a.MR.ptr) && al16(a.ET.ptr) && al16(a.IN.ptr) &&
                   al16(a.vol_stored) && al16(a.vol_bankfull.ptr) && al16(a.d_flood));
     memset(&k, 0, sizeof(k));
@@ -459,6 +476,9 @@ int prepare_ext(const tfb_channels_step_args *ap, tfb_channels_step_args &a,
     k.atten = (a.flags & TFB_CH_ATTENUATE) ? 1 : 0;
     k.flood = (a.flags & TFB_CH_FLOOD) ? 1 : 0;
     k.oVs = k.oDf = 0; k.oVb = -1;
+    k.w64 = p.width32 ? 0 : 1;
+    k.s64 = p.S32 ? 0 : 1;
+    k.oSinu = -1;
     k.t_drain = a.t_drain; k.vb_val = a.vol_bankfull.val;
     k.width_ratio = a.width_ratio; k.flood_n = a.flood_manning_n;
     const bool any_grid = a.P_rain.ptr || a.SM.ptr || a.GW.ptr || a.MR.ptr || a.ET.ptr || a.IN.ptr;

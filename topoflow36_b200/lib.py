@@ -112,7 +112,7 @@ class ChannelsPacked(C.Structure):
     _fields_ = [('geo32', vp), ('width32', vp), ('coef', vp), ('angle_lut', vp),
                 ('row_geom', vp), ('outlet_rough', C.c_double), ('n_angles', C.c_int32),
                 ('inv_rough', vp), ('S32', vp), ('noflow_idx', vp), ('n_noflow', C.c_int64),
-                ('rough64', vp), ('lut_tc', vp)]
+                ('rough64', vp), ('lut_tc', vp), ('width64', vp), ('S64', vp), ('sinu64', vp)]
 
 
 _i32, _i64, _f32, _f64 = C.c_int32, C.c_int64, C.c_float, C.c_double

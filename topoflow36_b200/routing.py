@@ -241,23 +241,22 @@ class ChannelsEngine(object):
     # ------------------------------------------------------------ packed path
     def _try_pack(self):
         """Build the compact static inputs of the packed (TMA ring) kernels once, when the
-        configuration allows it: scalar sinuosity, float32-exact widths, at most 65536
-        distinct bank angles.  Everything is lossless and
+        configuration allows it (at most 65536 distinct bank angles).  Everything is lossless and
         every per-cell array is (ny, pitch) like the state.  Two families share them:
 
           lean  tfb_channels_step_packed*: Manning, no per-step diagnostics, scalar forcing,
                 optionally fused sources; <= 256 angles (table in shared memory); kinematic
                 wave: coef = sqrt|S_bed| / n, diffusive: 1 / n and the float32 bed slope
           ext   tfb_channels_step_ext*: grid forcing, law of the wall, diagnostics, R grid,
-                FLOOD_OPTION, ATTENUATE; float32 bed slope + roughness (n or z0) + a
-                {tan, cos} table in L2
+                FLOOD_OPTION, ATTENUATE, a sinuosity grid; bed slope and width as float32
+                where they are float32 values (RTG files), as fp64 grids otherwise (a scalar
+                width like 3.3 m, slopes divided by a sinuosity != 1) + roughness (n or z0)
+                + a {tan, cos} table in L2
 
         Otherwise the generic kernel (tfb_channels_step) runs."""
         a = self.args
         self.lean_ok = self.ext_ok = False
         self._cfg = None
-        if self.sinu_grid is not None:
-            return
         dev = self.device
 
         def padc(t):
@@ -272,8 +271,8 @@ class ChannelsEngine(object):
                                              device=dev))
         width = full(self.width_grid, a.width.val)
         w32 = width.float()
-        if not bool((w32.double() == width).all()):
-            return
+        w32_ok = bool((w32.double() == width).all())
+        w64 = None if w32_ok else padc(width)
         del width
         if self.tan_angle_grid is None and self.cos_angle_grid is None:
             uniq = torch.tensor([[a.tan_angle.val, a.cos_angle.val]], dtype=torch.float64,
@@ -304,14 +303,17 @@ class ChannelsEngine(object):
         s32_ok = bool((S32.double() == S).all())
         S32 = padc(S32) if s32_ok else None
         coef = inv_rough = None
-        if self.manning:
+        S64 = None if s32_ok else padc(S)
+        sinu64 = None if self.sinu_grid is None else padc(self.own(self.sinu_grid))
+        lean_geom = w32_ok and sinu64 is None          # the lean kernels: float32 widths, row-wise ds
+        if self.manning and lean_geom:
             if self.kinematic:
                 sq = self.own(self.sqrtS) if getattr(self, 'sqrtS', None) is not None \
                     else torch.sqrt(torch.abs(S))
                 coef = padc(sq / rough)
             elif s32_ok:
                 inv_rough = padc(1.0 / rough)
-        rough64 = padc(rough) if s32_ok else None
+        rough64 = padc(rough)
         geo32 = torch.empty((self.ny, self.pitch), dtype=torch.int32, device=dev)
         L.check(self.lib.tfb_channels_pack_geo32(self._p(self.code),
                                                  None if aidx is None else aidx.data_ptr(), self.ny,
@@ -319,7 +321,8 @@ class ChannelsEngine(object):
                                                  L.stream_ptr()), 'tfb_channels_pack_geo32')
         rowg = torch.empty((self.ny, 8), dtype=torch.float64, device=dev)
         L.check(self.lib.tfb_channels_pack_rows(self._prow(self.dx), self._prow(self.dy),
-                                                self._prow(self.dd), float(a.sinu.val),
+                                                self._prow(self.dd),
+                                                1.0 if sinu64 is not None else float(a.sinu.val),
                                                 self._prow(self.da_rows) if self._da_is_grid
                                                 else None, float(a.da.val), self.ny,
                                                 rowg.data_ptr(), L.stream_ptr()),
@@ -329,8 +332,11 @@ class ChannelsEngine(object):
         if 0 <= orow < self.ny and 0 <= a.outlet_col < self.nx:
             n_out = float(rough[orow, a.outlet_col])
         pk = L.ChannelsPacked()
-        w32 = padc(w32)
-        pk.geo32, pk.width32 = geo32.data_ptr(), w32.data_ptr()
+        w32 = padc(w32) if w32_ok else None
+        pk.geo32, pk.width32 = geo32.data_ptr(), (None if w32 is None else w32.data_ptr())
+        pk.width64 = None if w64 is None else w64.data_ptr()
+        pk.S64 = None if S64 is None else S64.data_ptr()
+        pk.sinu64 = None if sinu64 is None else sinu64.data_ptr()
         pk.coef = None if coef is None else coef.data_ptr()
         pk.inv_rough = None if inv_rough is None else inv_rough.data_ptr()
         pk.S32 = None if S32 is None else S32.data_ptr()
@@ -344,11 +350,13 @@ class ChannelsEngine(object):
             nf = torch.nonzero(self.code[self.halo:self.halo + self.ny].reshape(-1) == 0) \
                 .reshape(-1).contiguous()
             pk.noflow_idx, pk.n_noflow = nf.data_ptr(), int(nf.numel())
-        self._pack_keep = (geo32, w32, coef, inv_rough, S32, rough64, lut, lut_tc, rowg, nf, aidx)
+        self._pack_keep = (geo32, w32, coef, inv_rough, S32, rough64, lut, lut_tc, rowg, nf, aidx,
+                           w64, S64, sinu64)
         self.packed = pk
         self.lean_ok = (self.manning and n_angles <= 256 and not self.flood and not self.attenuate
+                        and lean_geom
                         and (coef is not None if self.kinematic else inv_rough is not None))
-        self.ext_ok = s32_ok
+        self.ext_ok = True
 
     def release_generic_inputs(self):
         """Free the fp64 static grids the packed path does not read (width, tan,
@@ -377,8 +385,8 @@ class ChannelsEngine(object):
     def _packed_ok(self):
         """Which packed family takes this step: 'lean' (the benchmarked production kernels),
         'ext' (grid forcing / law of the wall / diagnostics / R grid / flood option /
-        ATTENUATE), or None (generic kernel: grid sinuosity, widths or slopes that are not
-        float32 values, fused sources with grid parameters)."""
+        ATTENUATE / sinuosity grid / non-float32 widths or slopes), or None (generic kernel:
+        fused sources with grid parameters, more than 65536 bank angles)."""
         if self.packed is None or not self.use_packed:
             return None
         src = self.flags & (L.CH_SRC_MET | L.CH_SRC_SNOW | L.CH_SRC_EVAP | L.CH_SRC_INFIL)
