@@ -69,15 +69,16 @@ def test_larger_dem_vs_oracle_with_counts():
     assert np.array_equal(t.A.cpu().numpy(), A)
 
 
-def test_d8_2048_bit_exact_vs_c_oracle_and_exact_properties():
-    """A grid too large for the numpy oracle: the C restatement (itself pinned to
-    the reference fixtures in test_c_oracle.py) must agree bit for bit, and the
+@pytest.mark.parametrize('n', [2048, 8192])
+def test_d8_large_bit_exact_vs_c_oracle_and_exact_properties(n):
+    """Grids too large for the numpy oracle (2048^2; 8192^2 = 67 M cells, ~7 s of C oracle
+    on the host): the C restatement (itself pinned to the reference fixtures in
+    test_c_oracle.py) must agree bit for bit in codes, areas and counts, and the
     size-independent identities used at 16384^2 (scripts/bench_d8.py) must hold."""
     import torch
     from oracle import c_oracle
     from scripts import bench_d8
     from topoflow36_b200.d8 import D8Toolkit
-    n = 2048
     DEM = bench_d8.device_dem(n, seed=77)
     DEM = (torch.round(DEM * 8.0) / 8.0).contiguous()        # quantise: ties and flats appear
     tk = D8Toolkit(DEM)
