@@ -20,7 +20,8 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, kinematic, infil, q, devgen=False, p2p=False, d0=0.0, packed=True):
+def _worker(rank, world, port, kinematic, infil, q, devgen=False, p2p=False, d0=0.0, packed=True,
+            engine_kw=None):
     import torch
     import torch.distributed as dist
     from topoflow36_b200 import cases
@@ -40,10 +41,10 @@ def _worker(rank, world, port, kinematic, infil, q, devgen=False, p2p=False, d0=
         else:
             slab, parts = cases.build_engine(ny, nx, kinematic=kinematic, infil=infil, rank=rank,
                                              world=world, device=dev, return_parts=True, dt=2.0,
-                                             p2p=p2p, d0=d0, packed=packed)
+                                             p2p=p2p, d0=d0, packed=packed, **(engine_kw or {}))
             assert (slab.peer is not None) == bool(p2p)
             one = cases.build_engine(ny * world, nx, kinematic=kinematic, infil=infil, device=dev,
-                                     tile_rows=ny, dt=2.0, d0=d0, packed=packed)
+                                     tile_rows=ny, dt=2.0, d0=d0, packed=packed, **(engine_kw or {}))
             lay = parts['layout']
         rows = slice(lay.row0, lay.row0 + lay.ny)
         fails = []
@@ -68,8 +69,18 @@ def _worker(rank, world, port, kinematic, infil, q, devgen=False, p2p=False, d0=
             slab.step(i * 2.0 / 60.0)
             one.step(i * 2.0 / 60.0)
         e = slab.engine
-        for nm, a, b in (('vol', e.vol, one.vol), ('d', e.own(e.d), one.own(one.d)),
-                         ('u', e.own(e.u), one.own(one.u)), ('Q', e.Q, one.Q)):
+        extra = []
+        if engine_kw and engine_kw.get('flood'):
+            extra += [('d_flood', e.own(e.d_flood), one.own(one.d_flood)),
+                      ('vol_flood', e.own(e.vol_flood), one.own(one.vol_flood))]
+            if not float(one.d_flood.max()) > 0:
+                fails.append('no overbank flow')
+        if engine_kw and engine_kw.get('attenuate'):
+            extra += [('vol_stored', e.vol_stored, one.vol_stored)]
+        if engine_kw and e.last_kernel != 'ext':
+            fails.append('kernel %s, expected ext' % e.last_kernel)
+        for nm, a, b in [('vol', e.vol, one.vol), ('d', e.own(e.d), one.own(one.d)),
+                         ('u', e.own(e.u), one.own(one.u)), ('Q', e.Q, one.Q)] + extra:
             if not torch.equal(a, b[rows]):
                 ok = False
                 fails.append('%s (%d cells, max %g)' % (nm, int((a != b[rows]).sum()),
@@ -88,6 +99,16 @@ def _worker(rank, world, port, kinematic, infil, q, devgen=False, p2p=False, d0=
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize('kinematic', [True, False])
+def test_two_slabs_flood_and_attenuate_on_the_extended_kernels(kinematic):
+    """FLOOD_OPTION + ATTENUATE across a slab boundary (extended packed kernels, NCCL halo):
+    the diffusive pass B reads the neighbour's flood depths too (free surface = channel +
+    flood depth); 2 slabs must equal one grid bit for bit."""
+    test_two_slabs_equal_one_grid(kinematic, False, False, False,
+                                  engine_kw=dict(flood=True, d_bankfull=0.001, attenuate=True,
+                                                 n_days=0.002))
+
+
 def test_two_slabs_initial_depth_generic_diffusive():
     """d0 = 5 cm with the GENERIC diffusive kernel, which re-derives the parent's depth from
     the halo rows of the state: they must hold the neighbours' initial volumes before the
@@ -99,7 +120,7 @@ def test_two_slabs_initial_depth_generic_diffusive():
     (True, False, False, False), (True, True, False, False), (False, False, False, False),
     (True, True, True, False), (True, False, False, True), (True, True, False, True),
     (False, False, False, True), (False, True, False, True)])
-def test_two_slabs_equal_one_grid(kinematic, infil, devgen, p2p, d0=0.0, packed=True):
+def test_two_slabs_equal_one_grid(kinematic, infil, devgen, p2p, d0=0.0, packed=True, engine_kw=None):
     """p2p = True: the halo rows travel through NVLink peer stores inside the routing
     kernel (tfb_channels_step_packed_p2p; diffusive wave: ..._dw_a_p2p stores the boundary
     depths, ..._dw_b_p2p the boundary discharges) instead of NCCL send/recv."""
@@ -112,7 +133,7 @@ def test_two_slabs_equal_one_grid(kinematic, infil, devgen, p2p, d0=0.0, packed=
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, kinematic, infil, q, devgen, p2p,
-                                               d0, packed))
+                                               d0, packed, engine_kw))
              for r in range(world)]
     for p in procs:
         p.start()

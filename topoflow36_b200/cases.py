@@ -203,7 +203,7 @@ def build_engine_device(ny, nx, kinematic=True, infil=False, dt=1.0, rank=0, wor
 
 def build_engine(ny, nx, kinematic=True, infil=False, diag=False, dt=1.0, rank=0, world=1,
                  seed=1234, device=None, group=None, link_flats=True, return_parts=False,
-                 tile_rows=None, sources=None, p2p=False, d0=0.0, packed=True):
+                 tile_rows=None, sources=None, p2p=False, d0=0.0, packed=True, **engine_kw):
     """Engine (and SlabChannels wrapper when world > 1) for rank `rank` of a
     (world*ny, nx) synthetic grid."""
     import torch
@@ -231,7 +231,7 @@ def build_engine(ny, nx, kinematic=True, infil=False, diag=False, dt=1.0, rank=0
                          halo=halo, device=device, finalize=True,
                          n_pixels_global=ny * nx, d0=d0, packed=packed,
                          q_buffers=None if peer is None else peer.q_buffers,
-                         d_buffer=None if peer is None else peer.d_buffer)
+                         d_buffer=None if peer is None else peer.d_buffer, **engine_kw)
     apply_sources(eng, sources or ('ga' if infil else 'none'), row0=lay.row0, halo=halo, seed=seed)
     torch.cuda.current_stream().synchronize()
     stepper = SlabChannels(lay, eng, group, peer=peer) if world > 1 else eng
