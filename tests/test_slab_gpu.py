@@ -62,6 +62,18 @@ def _worker(rank, world, port, kinematic, infil, q, devgen=False, p2p=False, d0=
             if not (torch.equal(A, A1[rows]) and torch.equal(cnt, cnt1[rows])):
                 fails.append('D8 area across slabs (%d cells differ, %d rounds)'
                              % (int((cnt != cnt1[rows]).sum()), rounds))
+            # path-length slopes (new_slopes.get_new_slope_grid) of the sharded grid == one grid
+            from topoflow36_b200.slab import slab_new_slope
+            from topoflow36_b200.d8 import D8Toolkit
+            S_new, n_path = slab_new_slope(parts['DEM'], parts['d8']['code'], lay, lay.halo + 1,
+                                           device=dev)
+            tile = cases.noise_tile(ny, nx, seed=1234)
+            tk = D8Toolkit(cases.slab_dem(ny * world, nx, 0, ny * world, 0, tile), device=dev)
+            tk.update_flow_grid()
+            S1, n1 = tk.new_slope()
+            if not (torch.equal(S_new, S1[rows]) and n_path == n1 and float(S1.max()) > 0):
+                fails.append('new slopes across slabs (%d cells differ, longest path %d vs %d)'
+                             % (int((S_new != S1[rows]).sum()), n_path, n1))
         for i in range(steps):
             if i == 80:
                 slab.engine.set_input('P_rain', 0.0)

@@ -576,3 +576,51 @@ def slab_d8_area(code, layout, pixel_area, group=None, with_counts=True):
                                    None if cnt is None else cnt.data_ptr(), C.byref(n_done), st()),
             'tfb_d8_area_unpack')
     return A, cnt, rounds
+
+
+def slab_new_slope(DEM, code, layout, dem_halo, xres=30.0, yres=30.0, nodata=-9999.0,
+                   device=None, group=None):
+    """utils/new_slopes.get_new_slope_grid (:174-316) of a row-sharded grid: the drop to the
+    first LOWER cell down the D8 flow path over the path length, fp64.
+
+    That walk can cross any number of slabs, and the reference's global iteration count (the
+    longest flow path of the WHOLE grid, which decides what walkers that have passed their
+    noflow cell are compared with) couples all cells -- while the working set of even the
+    65536^2 grid (DEM 17 GB, codes 4 GB, 2 x 17 GB scratch, slope 34 GB) fits the 180 GB of
+    ONE B200.  So the owned rows are gathered on rank 0, the single-GPU kernels run there
+    (tfb_d8_new_slope) and every rank receives its rows: bit-identical to one GPU by
+    construction, one gather + one scatter over NVLink.
+
+    `DEM`: float32 rows with `dem_halo` halo rows, `code`: uint8 with layout.halo halo rows
+    (as slab_d8 takes / returns them).  Returns (slope float64 (ny, nx), longest path)."""
+    from .d8 import D8Toolkit
+    dev = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
+    ny, nx, H = layout.ny, layout.nx, layout.halo
+    dem = DEM if isinstance(DEM, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(DEM))
+    dem = dem.to(dev)[dem_halo:dem_halo + ny].contiguous()
+    cod = code.to(dev)[H:H + ny].contiguous()
+    if layout.world_size == 1:
+        tk = D8Toolkit(dem, xres=xres, yres=yres, nodata=nodata, device=dev)
+        tk.code = cod
+        return tk.new_slope()
+    root = dist.get_global_rank(group, 0) if group is not None else 0
+    is_root = layout.rank == 0
+    parts_z = [torch.empty((n, nx), dtype=torch.float32, device=dev) for _, n in layout.parts] \
+        if is_root else None
+    parts_c = [torch.empty((n, nx), dtype=torch.uint8, device=dev) for _, n in layout.parts] \
+        if is_root else None
+    dist.gather(dem, parts_z, dst=root, group=group)
+    dist.gather(cod, parts_c, dst=root, group=group)
+    out = torch.empty((ny, nx), dtype=torch.float64, device=dev)
+    reps = torch.zeros(1, dtype=torch.int64, device=dev)
+    pieces = None
+    if is_root:
+        tk = D8Toolkit(torch.cat(parts_z, 0), xres=xres, yres=yres, nodata=nodata, device=dev)
+        del parts_z
+        tk.code = torch.cat(parts_c, 0)
+        S, n = tk.new_slope()
+        reps[0] = n
+        pieces = [S[r0:r0 + n_].contiguous() for r0, n_ in layout.parts]
+    dist.scatter(out, pieces, src=root, group=group)
+    dist.broadcast(reps, src=root, group=group)
+    return out, int(reps.item())
