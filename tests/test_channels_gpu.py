@@ -739,3 +739,28 @@ def test_geographic_pixels_vs_reference_fixture(geo_gold, tag):
         _cmp_scalars(eng, want)
         if not diag:
             assert eng.last_path == 'packed'       # per-row pixel areas ride the fast path too
+
+
+@pytest.mark.parametrize('workload', ['kw_ga', 'dw'])
+def test_bench_size_parity_vs_c_oracle(workload):
+    """BASELINE configs[1] at ITS size (4096^2, the grid bench.py times) on the lean packed
+    kernels against the C restatement of the reference path, 40 steps from the initial state --
+    the same leg bench.py runs inside its JSON line (sanity.parity_rel_err)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from topoflow36_b200 import cases
+    n = 4096
+    kin = workload.startswith('kw')
+    eng, parts = cases.build_engine(n, n, kinematic=kin, sources='ga' if kin else 'none',
+                                    return_parts=True)
+    res = bench.parity_vs_c_oracle(eng, parts, n, n_steps=40)
+    assert res['parity_path'] == 'packed' and eng.last_kernel == 'lean'
+    assert max(res['parity_rel_err'].values()) <= 1e-11, res['parity_rel_err']
+    s = eng.read_scalars()
+    stored = float(eng.vol.sum())
+    infil = s.vol_IN if kin else 0.0
+    # water balance at full size: rain in = channels + edges + infiltrated
+    assert abs((s.vol_R) - (stored + s.vol_edge)) <= 1e-12 * abs(s.vol_R + infil)
+    assert s.n_neg_d == s.n_nan_d == s.n_inf_d == s.n_neg_u == s.n_nan_u == s.n_inf_u == 0
