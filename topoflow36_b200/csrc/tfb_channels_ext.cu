@@ -50,9 +50,10 @@ struct ExtConsts {
     int atten, flood;          // ATTENUATE, FLOOD_OPTION
     int oVs, oVb, oDf;         // ring-slot offsets: vol_stored, vol_bankfull (-1 = scalar), d_flood halo tile
     int w64, s64, oSinu;       // width / bed slope streams are fp64 grids; sinuosity grid stream (-1 = none)
+    int oRG;                   // the tile rows' geometry (8 doubles per row), one more TMA box
     double t_drain, vb_val, width_ratio, flood_n;
 };
-struct ExtMaps { CUtensorMap Q, vol, geo, w, S, rough, F[F_N], vs, vb, df, sinu; };   // Q: discharge, or depth (pass B)
+struct ExtMaps { CUtensorMap Q, vol, geo, w, S, rough, F[F_N], vs, vb, df, sinu, rg; };   // Q: discharge, or depth (pass B)
 
 template <int VAR, bool LOW, bool DIAG>
 __device__ __forceinline__ void ext_cell(const tfb_channels_step_args &a, const tfb_channels_packed &p,
@@ -66,9 +67,10 @@ __device__ __forceinline__ void ext_cell(const tfb_channels_step_args &a, const 
     const double w = k.w64 ? *reinterpret_cast<const double *>(st + k.oW + e * 8)
                            : (double)*reinterpret_cast<const float *>(st + k.oW + e * 4);
     const double2 tc = __ldg(reinterpret_cast<const double2 *>(p.lut_tc) + ai);   // {tan, cos}
-    const double *rg = p.row_geom + (int64_t)r * kRowGeom;          // ds_ew, ds_diag, ds_ns, ., ., ., da
+    // the row's geometry from the ring slot: ds_ew, ds_diag, ds_ns, ., ., ., da
+    const double *rg = reinterpret_cast<const double *>(st + k.oRG) + row * kRowGeom;
     const bool dg = (code & 0x55u) != 0u, ns = (code & 0x88u) != 0u;
-    double ds = __ldg(rg + (dg ? 1 : (ns ? 2 : 0)));
+    double ds = rg[dg ? 1 : (ns ? 2 : 0)];
     if (k.oSinu >= 0) ds = *reinterpret_cast<const double *>(st + k.oSinu + e * 8) * ds;   // :1242
     const int64_t i = (int64_t)r * a.pitch + c;
     const double dt = k.dt;
@@ -76,7 +78,7 @@ __device__ __forceinline__ void ext_cell(const tfb_channels_step_args &a, const 
     double df = 0.0, vf = 0.0;                   // FLOOD_OPTION: flood depth, volume above bankfull
     if (VAR != EXT_DWB) {
         // ---- update_R :1548-1655, update_R_integral :1657, update_flow_volume :1951 --------
-        const double da = __ldg(rg + 6);
+        const double da = rg[6];
         const double vol = *reinterpret_cast<const double *>(st + k.oVol + e * 8);
         double f[F_N];
 #pragma unroll
@@ -284,6 +286,7 @@ channels_ext_kernel(const tfb_channels_step_args a, const tfb_channels_packed p,
                 tma_load_2d(st + k.oQ, &maps.Q, bar, c0 - 2, r0 - 1 + a.halo);
                 tma_load_2d(st + k.oGeo, &maps.geo, bar, c0, r0);
                 tma_load_2d(st + k.oW, &maps.w, bar, c0, r0);
+                tma_load_2d(st + k.oRG, &maps.rg, bar, 0, r0);
                 if (k.oSinu >= 0) tma_load_2d(st + k.oSinu, &maps.sinu, bar, c0, r0);
                 if (VAR != EXT_DWB) {
                     tma_load_2d(st + k.oVol, &maps.vol, bar, c0, r0 + a.halo);
@@ -359,6 +362,7 @@ int launch_ext(const tfb_channels_step_args &a, const tfb_channels_packed &p, Ex
     k.oGeo = put(TC::szF, TC::nF);
     k.oW = k.w64 ? put(TC::szD, TC::nD) : put(TC::szF, TC::nF);
     k.oSinu = p.sinu64 ? put(TC::szD, TC::nD) : -1;
+    k.oRG = put(((kTR * kRowGeom * 8 + 127) / 128) * 128, kTR * kRowGeom * 8);
     k.oVol = k.oS = k.oRough = 0;
     const tfb_sg *F[F_N] = {&a.P_rain, &a.SM, &a.GW, &a.MR, &a.ET, &a.IN};
     if (VAR != EXT_DWB) {
@@ -398,6 +402,7 @@ int launch_ext(const tfb_channels_step_args &a, const tfb_channels_packed &p, Ex
     }
     if (p.sinu64)
         if ((rc = pk_get_map(p.sinu64, a.ny, a.nx, a.pitch, F64, 8, kTW, kTR, &m.sinu))) return rc;
+    if ((rc = pk_get_map(p.row_geom, a.ny, kRowGeom, kRowGeom, F64, 8, kRowGeom, kTR, &m.rg))) return rc;
     if (VAR != EXT_DWB) {
         if ((rc = pk_get_map(a.vol - hb, rows_h, a.nx, a.pitch, F64, 8, kTW, kTR, &m.vol))) return rc;
         for (int j = 0; j < F_N; ++j)

@@ -74,6 +74,12 @@ pack_geo32_kernel(const uint8_t *__restrict__ code, const uint16_t *__restrict__
     geo[i] = (uint32_t)code[i] | (m << 8) | ((uint32_t)(aidx ? aidx[i] : 0) << 16);
 }
 
+// TFB_PK_RG_TMA: the per-row geometry (flow lengths, reciprocals, pixel area: 8 doubles per
+// row) rides the ring as one more TMA box instead of being fetched by the consumers with
+// global loads at the head of every tile (the kernel's only long-scoreboard stalls)
+#ifndef TFB_PK_RG_TMA
+#define TFB_PK_RG_TMA 1      // same-box A/B: KW + Green-Ampt 0.254 -> 0.236 ms, KW 0.224 -> 0.216
+#endif
 // ring slot of the main kernel (kinematic step, or pass A of the diffusive step)
 template <int SRC, int VAR, class TC> struct StageLayout {
     static constexpr int kSzQ = TC::szQ, kSzD = TC::szD, kSzF = TC::szF;
@@ -88,7 +94,9 @@ template <int SRC, int VAR, class TC> struct StageLayout {
     static constexpr int oT = oH + (kFullSrc ? kSzD : 0);    // T_air   (FULL only)
     static constexpr int oW = oT + (kFullSrc ? kSzD : 0);
     static constexpr int oGeo = oW + kSzF;
-    static constexpr int bytes = oGeo + kSzF;
+    static constexpr int oRG = oGeo + kSzF;
+    static constexpr int nRG = TC::R * kRowGeom * 8;                       // TMA bytes of the row box
+    static constexpr int bytes = oRG + (TFB_PK_RG_TMA ? ((nRG + 127) / 128) * 128 : 0);
     static constexpr int stages = (kSmemBudget / bytes) > 6 ? 6 : (kSmemBudget / bytes);
 };
 // ring slot of pass B of the diffusive step
@@ -99,8 +107,10 @@ template <class TC> struct StageLayoutB {
     static constexpr int oS = oN + kSzD;                     // S_bed (f32)
     static constexpr int oW = oS + kSzF;
     static constexpr int oGeo = oW + kSzF;
-    static constexpr int bytes = oGeo + kSzF;
-    static constexpr int tx_bytes = TC::nQ + TC::nD + 3 * TC::nF;
+    static constexpr int oRG = oGeo + kSzF;
+    static constexpr int nRG = TC::R * kRowGeom * 8;
+    static constexpr int bytes = oRG + (TFB_PK_RG_TMA ? ((nRG + 127) / 128) * 128 : 0);
+    static constexpr int tx_bytes = TC::nQ + TC::nD + 3 * TC::nF + (TFB_PK_RG_TMA ? nRG : 0);
     static constexpr int stages = (kSmemBudget / bytes) > 6 ? 6 : (kSmemBudget / bytes);
 };
 
@@ -241,8 +251,8 @@ __global__ void zero_at_kernel(double *__restrict__ x, const int64_t *__restrict
     if (i < n) x[__ldg(idx + i)] = 0.0;
 }
 
-struct PkMaps { CUtensorMap Q, vol, coef, I, H, T, w, geo; };
-struct PkMapsB { CUtensorMap D, N, S, w, geo; };
+struct PkMaps { CUtensorMap Q, vol, coef, I, H, T, w, geo, rg; };
+struct PkMapsB { CUtensorMap D, N, S, w, geo, rg; };
 
 // Peer-memory halo, sending side -- executed by the PRODUCER warp (all 32 lanes), off the
 // consumers' critical path: when the ring slot of boundary tile `t` has been released
@@ -331,7 +341,8 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
         unsigned phase = 0;
         bool up_ok = false, down_ok = false;
         const unsigned tx = (unsigned)(TC::nQ + TC::nD * (1 + (kKW ? 1 : 0) + (use_i ? 1 : 0) +
-                                                          (use_h ? 1 : 0) + (use_t ? 1 : 0)) + 2 * TC::nF);
+                                                          (use_h ? 1 : 0) + (use_t ? 1 : 0)) + 2 * TC::nF +
+                                       (TFB_PK_RG_TMA ? SL::nRG : 0));
         const double *push_src = kKW ? a.Q_out : a.d;
         // PEER: NS extra (load-free) turns drain the boundary tiles still in the ring
         const int t_end = k.n_tiles + (PEER ? NS * (int)gridDim.x : 0);
@@ -389,6 +400,7 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
                     if (use_t) tma_load_2d(st + SL::oT, &maps.T, &full_bar[stage], c0, r0 + a.halo);
                     tma_load_2d(st + SL::oW, &maps.w, &full_bar[stage], c0, r0);
                     tma_load_2d(st + SL::oGeo, &maps.geo, &full_bar[stage], c0, r0);
+                    if (TFB_PK_RG_TMA) tma_load_2d(st + SL::oRG, &maps.rg, &full_bar[stage], 0, r0);
                 }
             }
             if (++stage == NS) { stage = 0; phase ^= 1u; }
@@ -479,13 +491,21 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
 #pragma unroll
                 for (int j = 0; j < NC; ++j) {
                     const int rr = live[j] ? rj[j] : r0;
+#if TFB_PK_RG_TMA
+                    const double2 *rgp = reinterpret_cast<const double2 *>(st + SL::oRG) +
+                                         (rr - ty * kTR) * (kRowGeom / 2);
+                    const double2 g0 = rgp[0], g1 = rgp[1], g2 = rgp[2];
+                    const double da_row = rgp[3].x;
+#else
                     const double2 *rgp = reinterpret_cast<const double2 *>(p.row_geom + (int64_t)rr * kRowGeom);
                     const double2 g0 = __ldg(rgp), g1 = __ldg(rgp + 1), g2 = __ldg(rgp + 2);
+                    const double da_row = __ldg(rgp + 3).x;
+#endif
                     const unsigned code = x[j].g & 0xffu;
                     const bool dg = (code & 0x55u) != 0u, ns = (code & 0x88u) != 0u;
                     ds[j] = dg ? g0.y : (ns ? g1.x : g0.x);
                     ids[j] = dg ? g2.x : (ns ? g2.y : g1.y);
-                    da[j] = live[j] ? __ldg(rgp + 3).x : 0.0;
+                    da[j] = live[j] ? da_row : 0.0;
                 }
                 // ---------------- the straight-line block --------------------------------
                 PkVD o[NC];
@@ -655,6 +675,7 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
                     tma_load_2d(st + SL::oS, &maps.S, &full_bar[stage], c0, r0);
                     tma_load_2d(st + SL::oW, &maps.w, &full_bar[stage], c0, r0);
                     tma_load_2d(st + SL::oGeo, &maps.geo, &full_bar[stage], c0, r0);
+                    if (TFB_PK_RG_TMA) tma_load_2d(st + SL::oRG, &maps.rg, &full_bar[stage], 0, r0);
                 }
             }
             if (++stage == NS) { stage = 0; phase ^= 1u; }
@@ -694,9 +715,15 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
                     int dr, dcol;
                     code_offset(code, dr, dcol);
                     const double d_par = dc[dr * kQW + dcol];             // new depth of the D8 parent
+#if TFB_PK_RG_TMA
+                    const double2 *rgp = reinterpret_cast<const double2 *>(st + SL::oRG) +
+                                         ((live[j] ? rj[j] : r0) - ty * kTR) * (kRowGeom / 2);
+                    const double2 g1 = rgp[1], g2 = rgp[2];
+#else
                     const double2 *rgp = reinterpret_cast<const double2 *>(
                         p.row_geom + (int64_t)(live[j] ? rj[j] : r0) * kRowGeom);
                     const double2 g1 = __ldg(rgp + 1), g2 = __ldg(rgp + 2);
+#endif
                     const bool dg = (code & 0x55u) != 0u, ns = (code & 0x88u) != 0u;
                     ids[j] = dg ? g2.x : (ns ? g2.y : g1.y);
                     const double Sf = Sb + ((d[j] - d_par) * ids[j]);     // :2606-2607
@@ -848,6 +875,9 @@ int launch_main_(const tfb_channels_step_args &a, const tfb_channels_packed &p, 
     if (use_t) if ((rc = get_map(a.T_air.ptr - hb, rows_h, a.nx, a.pitch, F64, 8, kTW, kTR, &m.T))) return rc;
     if ((rc = get_map(p.width32, a.ny, a.nx, a.pitch, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, kTW, kTR, &m.w))) return rc;
     if ((rc = get_map(p.geo32, a.ny, a.nx, a.pitch, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, kTW, kTR, &m.geo))) return rc;
+    m.rg = m.geo;
+    if (TFB_PK_RG_TMA)
+        if ((rc = get_map(p.row_geom, a.ny, kRowGeom, kRowGeom, F64, 8, kRowGeom, kTR, &m.rg))) return rc;
     const int smem = SL::stages * SL::bytes;
     static bool attr_set[64] = {false};
     int dev = 0;
@@ -893,6 +923,9 @@ int launch_dwb(const tfb_channels_step_args &a, const tfb_channels_packed &p, Pk
     if ((rc = get_map(p.S32, a.ny, a.nx, a.pitch, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, kTW, kTR, &m.S))) return rc;
     if ((rc = get_map(p.width32, a.ny, a.nx, a.pitch, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, kTW, kTR, &m.w))) return rc;
     if ((rc = get_map(p.geo32, a.ny, a.nx, a.pitch, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, kTW, kTR, &m.geo))) return rc;
+    m.rg = m.geo;
+    if (TFB_PK_RG_TMA)
+        if ((rc = get_map(p.row_geom, a.ny, kRowGeom, kRowGeom, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, kRowGeom, kTR, &m.rg))) return rc;
     const int smem = SL::stages * SL::bytes;
     static bool attr_set[64] = {false};
     int dev = 0;

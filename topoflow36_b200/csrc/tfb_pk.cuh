@@ -95,7 +95,10 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
 // per tile row (R + 1 warps, up to 128 registers per thread), 1 -> two warps per row
 // (2R + 1 warps: more latency hiding, 64 registers).  The best choice depends on the
 // register needs of the variant and is made per kernel instantiation (launch_main).
-constexpr int kSmemBudget = 196 * 1024;              // dynamic shared memory for the ring
+#ifndef TFB_PK_SMEM_KB
+#define TFB_PK_SMEM_KB 196
+#endif
+constexpr int kSmemBudget = TFB_PK_SMEM_KB * 1024;   // dynamic shared memory for the ring
 template <int ROWS, int CPL, int WIDTH = 64, int RPW = 1> struct TileCfg {
     static constexpr int R = ROWS * RPW;             // tile rows; a warp takes rows w, w + ROWS, ...
     static constexpr int RP = ROWS;                  // rows per pass of the consumer warps
