@@ -660,7 +660,8 @@ def test_flood_component_from_cfg(tmp_path, flood_gold):
 
 
 @pytest.mark.parametrize('shape', [(1, 4), (2, 8), (15, 64), (16, 68), (31, 132), (47, 260), (100, 60),
-                                   (44, 29), (5, 7), (3, 1), (20, 33), (17, 67), (33, 130)])
+                                   (44, 29), (5, 7), (3, 1), (20, 33), (17, 67), (33, 130),
+                                   (24, 64), (25, 66), (20, 64), (21, 70), (49, 129), (73, 65)])
 @pytest.mark.parametrize('kinematic', [True, False])
 def test_packed_path_ragged_shapes(shape, kinematic):
     """TMA tiles that hang over the grid edge (zero-filled by the TMA unit), grids

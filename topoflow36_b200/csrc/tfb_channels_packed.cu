@@ -1043,13 +1043,18 @@ int prepare(const tfb_channels_step_args *ap, tfb_channels_step_args &a,
 #define TFB_PK_GA_W 64
 #endif
 #ifndef TFB_PK_NONE_ROWS
-#define TFB_PK_NONE_ROWS 15
+#define TFB_PK_NONE_ROWS 24       // KW without sources: 2 cells per lane, 24-row tiles (25 warps, 72 registers,
+#endif                            // 4 ring slots).  Same-box A/B, round 2 (profiles/r02/ab_tiles*.log): 1 cell per
+                                  // lane x 2 rows per warp 0.2172 ms; 2 cells per lane: 15 rows 0.2094, 17 rows
+                                  // 0.2066, 20 rows 0.1956, 22 rows 0.1915, 24 rows 0.1869, 26 rows (3 slots) 0.2126
+#ifndef TFB_PK_NONEA_ROWS
+#define TFB_PK_NONEA_ROWS 20      // DW pass A without sources: 15 rows 0.2903 ms (step), 20 rows 0.2824, 24 rows 0.2824
 #endif
 #ifndef TFB_PK_NONE_W
 #define TFB_PK_NONE_W 64
 #endif
 #ifndef TFB_PK_NONE_RPW
-#define TFB_PK_NONE_RPW 2
+#define TFB_PK_NONE_RPW 1
 #endif
 #ifndef TFB_PK_GA_RPW
 #define TFB_PK_GA_RPW 1
@@ -1061,9 +1066,10 @@ int prepare(const tfb_channels_step_args *ap, tfb_channels_step_args &a,
 #define TFB_PK_DWB_RPW 2
 #endif
 #ifndef TFB_PK_NONE_CPL
-#define TFB_PK_NONE_CPL 1
+#define TFB_PK_NONE_CPL 2
 #endif
 typedef TileCfg<TFB_PK_NONE_ROWS, TFB_PK_NONE_CPL, TFB_PK_NONE_W, TFB_PK_NONE_RPW> CfgNone;
+typedef TileCfg<TFB_PK_NONEA_ROWS, TFB_PK_NONE_CPL, TFB_PK_NONE_W, TFB_PK_NONE_RPW> CfgNoneA;
 typedef TileCfg<TFB_PK_GA_ROWS, TFB_PK_GA_CPL, TFB_PK_GA_W, TFB_PK_GA_RPW> CfgGA;
 #ifndef TFB_PK_FULL_ROWS
 #define TFB_PK_FULL_ROWS 15
@@ -1213,7 +1219,7 @@ extern "C" int tfb_channels_step_packed_dw_a_p2p(const tfb_channels_step_args *a
     cudaStream_t st = (cudaStream_t)stream;
     PkPeer peer;
     if ((rc = make_peer(ph, st, peer))) return rc;
-    if (mode == PK_SRC_NONE) return launch_main_peer<PK_SRC_NONE, CfgNone, PK_DWA>(an, *pp, k, st, peer);
+    if (mode == PK_SRC_NONE) return launch_main_peer<PK_SRC_NONE, CfgNoneA, PK_DWA>(an, *pp, k, st, peer);
     if (mode == PK_SRC_GA) return launch_main_peer<PK_SRC_GA, CfgGA, PK_DWA>(an, *pp, k, st, peer);
     return launch_main_peer<PK_SRC_FULL, CfgFull, PK_DWA>(an, *pp, k, st, peer);
 }
@@ -1226,7 +1232,7 @@ extern "C" int tfb_channels_step_packed_dw_a(const tfb_channels_step_args *ap,
     const int rc = prepare(ap, an, pp, true, k, mode);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (mode == PK_SRC_NONE) return launch_main<PK_SRC_NONE, PK_DWA, CfgNone>(an, *pp, k, st);
+    if (mode == PK_SRC_NONE) return launch_main<PK_SRC_NONE, PK_DWA, CfgNoneA>(an, *pp, k, st);
     if (mode == PK_SRC_GA) return launch_main<PK_SRC_GA, PK_DWA, CfgGA>(an, *pp, k, st);
     return launch_main<PK_SRC_FULL, PK_DWA, CfgFull>(an, *pp, k, st);
 }
