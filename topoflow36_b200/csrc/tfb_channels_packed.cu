@@ -415,12 +415,13 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
         constexpr int NC = (TC::cpl == 2) ? 2 : TC::rpw;
         static_assert(NC == 1 || NC == 2, "one or two cells in flight per lane");
         static_assert(TC::cpl == 1 || TC::rpw == 1, "two columns per lane: one row per warp and slot");
-        // row-major tile order (no peer halo): the tile coordinates advance without a division
-        int ty = (int)blockIdx.x / k.tiles_x, txi = (int)blockIdx.x - ty * k.tiles_x;
+        // the tile coordinates advance without a division per tile (TileWalk, tfb_pk.cuh)
+        TileWalk<PEER> walk;
+        walk.init(k, (int)blockIdx.x);
         for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
             if (!(PEER ? mbar_wait_peer(&full_bar[stage], phase, &s_pwait, &s_fail)
                        : mbar_wait(&full_bar[stage], phase))) { s_fail = 1; break; }
-            if constexpr (PEER) tile_of<PEER>(k, t, ty, txi);
+            const int ty = walk.ty, txi = walk.tx;
             const unsigned char *st = smem + (size_t)stage * SL::bytes;
             const int row0 = warp / TC::wpr;
             const int ct = (TC::cpl == 2) ? (((warp % TC::wpr) << 6) + lane * 2) : (((warp % TC::wpr) << 5) + lane);
@@ -575,10 +576,7 @@ channels_packed_kernel(const tfb_channels_step_args a, const tfb_channels_packed
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[stage]);            // slot may be refilled
             if (++stage == NS) { stage = 0; phase ^= 1u; }
-            if constexpr (!PEER) {
-                txi += (int)gridDim.x;
-                while (txi >= k.tiles_x) { txi -= k.tiles_x; ++ty; }
-            }
+            walk.advance(k, (int)gridDim.x);
         }
     }
     pk_finish<kConsumerWarps>(a, acc, rate_max, warp < kConsumerWarps, &s_fail, kKW ? 0 : 1, peer, sm,
@@ -691,12 +689,13 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
         unsigned phase = 0;
         constexpr int NC = TC::rpw;
         static_assert(TC::cpl == 1 && (NC == 1 || NC == 2), "pass B: one cell per lane, <= 2 rows per warp");
-        // row-major tile order (no peer halo): the tile coordinates advance without a division
-        int ty = (int)blockIdx.x / k.tiles_x, txi = (int)blockIdx.x - ty * k.tiles_x;
+        // the tile coordinates advance without a division per tile (TileWalk, tfb_pk.cuh)
+        TileWalk<PEER> walk;
+        walk.init(k, (int)blockIdx.x);
         for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
             if (!(PEER ? mbar_wait_peer(&full_bar[stage], phase, &s_pwait, &s_fail)
                        : mbar_wait(&full_bar[stage], phase))) { s_fail = 1; break; }
-            if constexpr (PEER) tile_of<PEER>(k, t, ty, txi);
+            const int ty = walk.ty, txi = walk.tx;
             const unsigned char *st = smem + (size_t)stage * SL::bytes;
             const int row0 = warp / TC::wpr, ct = ((warp % TC::wpr) << 5) + lane;
             const int c0 = txi * kTW + ct, r0 = ty * kTR + row0;
@@ -752,10 +751,7 @@ channels_packed_dwb_kernel(const tfb_channels_step_args a, const tfb_channels_pa
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[stage]);
             if (++stage == NS) { stage = 0; phase ^= 1u; }
-            if constexpr (!PEER) {
-                txi += (int)gridDim.x;
-                while (txi >= k.tiles_x) { txi -= k.tiles_x; ++ty; }
-            }
+            walk.advance(k, (int)gridDim.x);
         }
     }
     pk_finish<kConsumerWarps>(a, acc, rate_max, warp < kConsumerWarps, &s_fail, 2, peer, sm, tot,

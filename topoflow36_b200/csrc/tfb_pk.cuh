@@ -139,6 +139,41 @@ __device__ __forceinline__ void tile_of(const PkConsts &k, int s, int &ty, int &
     tx = q - (ty - 1) * k.tiles_x;
 }
 
+// The same order walked WITHOUT a division per tile: position s advances by the grid size;
+// the interior part (row-major from tile row 1, or from row 0 without the peer halo) is
+// tracked incrementally, with one division when the walk enters it.
+template <bool PEER> struct TileWalk {
+    int ty, tx;                  // current tile
+    int s, ity, itx;
+    bool in;
+    __device__ __forceinline__ void set(const PkConsts &k) {
+        if constexpr (!PEER) { ty = ity; tx = itx; return; }
+        if (s < k.tiles_x) { ty = 0; tx = s; return; }
+        if (s < k.n_boundary) { ty = k.tiles_y - 1; tx = s - k.tiles_x; return; }
+        if (!in) {
+            const int q = s - k.n_boundary;
+            ity = 1 + q / k.tiles_x;
+            itx = q - (ity - 1) * k.tiles_x;
+            in = true;
+        }
+        ty = ity; tx = itx;
+    }
+    __device__ __forceinline__ void init(const PkConsts &k, int s0) {
+        s = s0; in = !PEER;
+        ity = PEER ? 0 : s0 / k.tiles_x;
+        itx = PEER ? 0 : s0 - ity * k.tiles_x;
+        set(k);
+    }
+    __device__ __forceinline__ void advance(const PkConsts &k, int step) {
+        s += step;
+        if (in) {
+            itx += step;
+            while (itx >= k.tiles_x) { itx -= k.tiles_x; ++ity; }
+        }
+        set(k);
+    }
+};
+
 constexpr uint32_t kPeerPoison = 0xffffffffu;   // flag value a failed rank leaves with its neighbours
 struct PkPeer {
     double *up_Q, *down_Q;                  // the neighbours' halo rows of the new discharge
