@@ -844,8 +844,9 @@ def main():
                 'algorithmic_bytes_per_cell': bpc, 'cells_per_launch': cells_per_launch,
                 'launch_ms': ms_per_step,
                 'note': ('%d launch(es) per step; time = timed region / steps (CUDA events); frac = '
-                         'algorithmic bytes (SURVEY 8d contract), frac_dram = DRAM bytes ncu counted '
-                         'for this kernel (static inputs are packed: 16 B instead of 42 B per cell)'
+                         'algorithmic bytes (SURVEY 8d contract) and can exceed 1 because the static '
+                         'inputs are packed (16 B instead of 42 B per cell); frac_dram = the DRAM bytes '
+                         'ncu counted for this kernel / time / peak: the distance from the HBM roofline'
                          % launches_per_step)}
 
     cpu = None
