@@ -239,6 +239,14 @@ class ScalarBoard(object):
         src = dist.get_global_rank(group, 0) if group is not None else 0
         dist.broadcast_object_list(box, src=src, group=group)
         self._path = box[0]
+        # same host name and boot id do not prove a shared /dev/shm (separate mount namespaces):
+        # every rank must SEE the segment, or all of them take the NCCL path
+        seen = [None] * self.world
+        dist.all_gather_object(seen, bool(self._path and os.path.exists(self._path)), group=group)
+        if not all(seen):
+            if self.rank == 0 and self._path and os.path.exists(self._path):
+                os.unlink(self._path)
+            raise OSError('ScalarBoard: /dev/shm is not shared by all ranks')
         fd = os.open(self._path, os.O_RDWR)
         try:
             self._mm = mmap.mmap(fd, size)
@@ -352,7 +360,10 @@ class SlabChannels(object):
         # global scalars without a collective where the ranks share a host (ScalarBoard)
         self.board = None
         if layout.world_size > 1 and dist.get_backend(group) == 'nccl' and ScalarBoard.usable(layout, group):
-            self.board = ScalarBoard(layout, C.sizeof(L.ChannelsScalars), group)
+            try:
+                self.board = ScalarBoard(layout, C.sizeof(L.ChannelsScalars), group)
+            except OSError:               # raised on EVERY rank (collective decision): NCCL all-gather
+                self.board = None
 
     def __getattr__(self, name):           # state access falls through to the engine
         return getattr(self.__dict__['engine'], name)
