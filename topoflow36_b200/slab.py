@@ -232,10 +232,13 @@ class ScalarBoard(object):
         size = 2 * self.world * self.SLOT
         box = [None]
         if self.rank == 0:
-            fd, path = tempfile.mkstemp(prefix='tfb_scalars_', dir='/dev/shm')
-            os.ftruncate(fd, size)
-            os.close(fd)
-            box[0] = path
+            try:
+                fd, path = tempfile.mkstemp(prefix='tfb_scalars_', dir='/dev/shm')
+                os.ftruncate(fd, size)
+                os.close(fd)
+                box[0] = path
+            except OSError:
+                box[0] = None             # the other ranks learn it through the broadcast
         src = dist.get_global_rank(group, 0) if group is not None else 0
         dist.broadcast_object_list(box, src=src, group=group)
         self._path = box[0]
