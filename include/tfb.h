@@ -174,6 +174,15 @@ int tfb_d8_parent_ids(const uint8_t *code, int32_t ny, int32_t nx,
 #define TFB_CH_SRC_SNOW    (1u << 9)  /* degree-day snowmelt fused            */
 #define TFB_CH_SRC_EVAP    (1u << 10) /* Priestley-Taylor ET fused            */
 #define TFB_CH_SRC_INFIL   (1u << 11) /* Green-Ampt infiltration fused        */
+#define TFB_CH_REVERSE     (1u << 12) /* packed kinematic step: walk the tiles bottom-up.  A
+                                         caller that alternates the bit makes every step start
+                                         on the rows the previous one wrote LAST, while they
+                                         still sit in the 126 MB L2.  Per-cell results do not
+                                         depend on it; the grid sums associate differently
+                                         (deterministically for a given bit).  Diffusive wave:
+                                         set it for pass B only (A top-down, B bottom-up: B
+                                         starts on the depths A wrote last, the next A on the
+                                         discharges B wrote last); pass A ignores it           */
 
 /* Device-resident scalar block: what the reference keeps in 0-D numpy arrays.
  * The step kernel's last block updates it; the host reads it when it needs

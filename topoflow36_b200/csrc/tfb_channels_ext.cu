@@ -51,6 +51,7 @@ struct ExtConsts {
     int oVs, oVb, oDf;         // ring-slot offsets: vol_stored, vol_bankfull (-1 = scalar), d_flood halo tile
     int w64, s64, oSinu;       // width / bed slope streams are fp64 grids; sinuosity grid stream (-1 = none)
     int oRG;                   // the tile rows' geometry (8 doubles per row), one more TMA box
+    int reverse;               // walk the tiles bottom-up (TFB_CH_REVERSE; pass B always): see tfb.h
     double t_drain, vb_val, width_ratio, flood_n;
 };
 struct ExtMaps { CUtensorMap Q, vol, geo, w, S, rough, F[F_N], vs, vb, df, sinu, rg; };   // Q: discharge, or depth (pass B)
@@ -277,7 +278,8 @@ channels_ext_kernel(const tfb_channels_step_args a, const tfb_channels_packed p,
         if (lane == 0) {                              // producer: TMA loads of every stream
             int stage = 0;
             unsigned phase = 0;
-            int ty = (int)blockIdx.x / k.tiles_x, txi = (int)blockIdx.x - ty * k.tiles_x;
+            const int i0 = k.reverse ? (k.n_tiles - 1 - (int)blockIdx.x) : (int)blockIdx.x;
+            int ty = i0 / k.tiles_x, txi = i0 - ty * k.tiles_x;
             for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
                 if (!mbar_wait(&empty_bar[stage], phase ^ 1u)) { s_fail = 1; break; }
                 const int c0 = txi * kTW, r0 = ty * kTR;
@@ -305,14 +307,20 @@ channels_ext_kernel(const tfb_channels_step_args a, const tfb_channels_packed p,
                     tma_load_2d(st + k.oRough, &maps.rough, bar, c0, r0);
                 }
                 if (++stage == NS) { stage = 0; phase ^= 1u; }
-                txi += (int)gridDim.x;                    // next tile of this CTA, no division
-                while (txi >= k.tiles_x) { txi -= k.tiles_x; ++ty; }
+                if (k.reverse) {                          // next tile of this CTA, no division
+                    txi -= (int)gridDim.x;
+                    while (txi < 0) { txi += k.tiles_x; --ty; }
+                } else {
+                    txi += (int)gridDim.x;
+                    while (txi >= k.tiles_x) { txi -= k.tiles_x; ++ty; }
+                }
             }
         }
     } else {
         int stage = 0;
         unsigned phase = 0;
-        int ty = (int)blockIdx.x / k.tiles_x, txi = (int)blockIdx.x - ty * k.tiles_x;
+        const int i0 = k.reverse ? (k.n_tiles - 1 - (int)blockIdx.x) : (int)blockIdx.x;
+        int ty = i0 / k.tiles_x, txi = i0 - ty * k.tiles_x;
         for (int t = blockIdx.x; t < k.n_tiles; t += gridDim.x) {
             if (!mbar_wait(&full_bar[stage], phase)) { s_fail = 1; break; }
             const unsigned char *st = smem + (size_t)stage * k.stage_bytes;
@@ -326,8 +334,13 @@ channels_ext_kernel(const tfb_channels_step_args a, const tfb_channels_packed p,
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[stage]);
             if (++stage == NS) { stage = 0; phase ^= 1u; }
-            txi += (int)gridDim.x;
-            while (txi >= k.tiles_x) { txi -= k.tiles_x; ++ty; }
+            if (k.reverse) {
+                txi -= (int)gridDim.x;
+                while (txi < 0) { txi += k.tiles_x; --ty; }
+            } else {
+                txi += (int)gridDim.x;
+                while (txi >= k.tiles_x) { txi -= k.tiles_x; ++ty; }
+            }
         }
     }
     pk_finish<kConsumerWarps>(a, acc, rate_max, warp < kConsumerWarps, &s_fail,
@@ -356,6 +369,8 @@ int launch_ext(const tfb_channels_step_args &a, const tfb_channels_packed &p, Ex
     k.tiles_x = (a.nx + kTW - 1) / kTW;
     k.tiles_y = (a.ny + kTR - 1) / kTR;
     k.n_tiles = k.tiles_x * k.tiles_y;
+    // kinematic: the caller alternates TFB_CH_REVERSE; diffusive: it sets the bit for pass B only
+    k.reverse = (VAR != EXT_DWA && (a.flags & TFB_CH_REVERSE)) ? 1 : 0;
     // ---- ring slot laid out for the streams this step really has ---------------------------
     int off = 0;
     unsigned tx = 0;

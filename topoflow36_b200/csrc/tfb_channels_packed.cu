@@ -862,6 +862,8 @@ int launch_main_(const tfb_channels_step_args &a, const tfb_channels_packed &p, 
     k.tiles_y = (a.ny + kTR - 1) / kTR;
     k.n_tiles = k.tiles_x * k.tiles_y;
     k.n_boundary = k.tiles_x * (k.tiles_y > 1 ? 2 : 1);
+    // serpentine: an odd kinematic step starts on the rows the even one wrote last (still in L2)
+    k.reverse = (!PEER && VAR == PK_KW && (a.flags & TFB_CH_REVERSE)) ? 1 : 0;
     static_assert(SL::stages >= 2, "ring needs at least two slots");
     PkMaps m;
     const int64_t rows_h = (int64_t)a.ny + 2 * a.halo;
@@ -920,6 +922,9 @@ int launch_dwb(const tfb_channels_step_args &a, const tfb_channels_packed &p, Pk
     k.tiles_y = (a.ny + kTR - 1) / kTR;
     k.n_tiles = k.tiles_x * k.tiles_y;
     k.n_boundary = k.tiles_x * (k.tiles_y > 1 ? 2 : 1);
+    // pass A walks top-down, pass B bottom-up: B starts on the depths A wrote last, the next
+    // step's A on the discharges B wrote last -- both while those rows are still in L2
+    k.reverse = (!PEER && (a.flags & TFB_CH_REVERSE)) ? 1 : 0;      // (the caller sets it for pass B)
     PkMapsB m;
     const int64_t rows_h = (int64_t)a.ny + 2 * a.halo;
     const size_t hb = (size_t)a.halo * a.pitch;

@@ -25,6 +25,7 @@ struct PkConsts {
     int low_rain;            // P_total < Ks  (infil_base.py:954-995)
     int n_tiles, tiles_x;
     int tiles_y, n_boundary;     // tiles of the first and last tile row come FIRST in the order
+    int reverse;                 // no peer halo: walk the tiles from the last one to the first
     // general fused sources (PK_SRC_FULL): every parameter a scalar, T_air may be a grid
     unsigned flags;
     int tair_grid;
@@ -131,7 +132,11 @@ __device__ __forceinline__ void add_if(double &v, unsigned m, unsigned bit, doub
 // 2.4 % on one GPU (same-box A/B), hence a template parameter and not a run-time flag.
 template <bool PEER>
 __device__ __forceinline__ void tile_of(const PkConsts &k, int s, int &ty, int &tx) {
-    if constexpr (!PEER) { ty = s / k.tiles_x; tx = s - ty * k.tiles_x; return; }
+    if constexpr (!PEER) {
+        if (k.reverse) s = k.n_tiles - 1 - s;
+        ty = s / k.tiles_x; tx = s - ty * k.tiles_x;
+        return;
+    }
     if (s < k.tiles_x) { ty = 0; tx = s; return; }
     if (s < k.n_boundary) { ty = k.tiles_y - 1; tx = s - k.tiles_x; return; }
     const int q = s - k.n_boundary;
@@ -160,15 +165,21 @@ template <bool PEER> struct TileWalk {
     }
     __device__ __forceinline__ void init(const PkConsts &k, int s0) {
         s = s0; in = !PEER;
-        ity = PEER ? 0 : s0 / k.tiles_x;
-        itx = PEER ? 0 : s0 - ity * k.tiles_x;
+        const int i0 = (!PEER && k.reverse) ? (k.n_tiles - 1 - s0) : s0;    // may be < 0: no tile
+        ity = PEER ? 0 : (i0 >= 0 ? i0 / k.tiles_x : 0);
+        itx = PEER ? 0 : (i0 >= 0 ? i0 - ity * k.tiles_x : 0);
         set(k);
     }
     __device__ __forceinline__ void advance(const PkConsts &k, int step) {
         s += step;
         if (in) {
-            itx += step;
-            while (itx >= k.tiles_x) { itx -= k.tiles_x; ++ity; }
+            if (!PEER && k.reverse) {
+                itx -= step;
+                while (itx < 0) { itx += k.tiles_x; --ity; }
+            } else {
+                itx += step;
+                while (itx >= k.tiles_x) { itx -= k.tiles_x; ++ity; }
+            }
         }
         set(k);
     }

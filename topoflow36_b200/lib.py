@@ -28,6 +28,7 @@ CH_SRC_MET = 1 << 8
 CH_SRC_SNOW = 1 << 9
 CH_SRC_EVAP = 1 << 10
 CH_SRC_INFIL = 1 << 11
+CH_REVERSE = 1 << 12
 NSUM = 24
 
 

@@ -16,6 +16,7 @@ needs 16-byte row strides for the 8-byte and the 4-byte streams alike.  Columns
 ``own()`` views; the one-time set-up kernels simply see a grid ``pitch`` wide.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -197,6 +198,7 @@ class ChannelsEngine(object):
         self._dev_index = self.device.index if self.device.index is not None \
             else torch.cuda.current_device()
         self._cfg, self._cfg_key, self._ptr_cache = None, None, {}
+        self.serpentine = os.environ.get('TFB_SERPENTINE', '1') != '0'
         self._scalars_dirty = False
         self.mid_step_hook = None
         self.use_packed = bool(packed)
@@ -710,7 +712,11 @@ class ChannelsEngine(object):
         value the flag words are compared with (default: every step so far did)."""
         a = self.args
         st = L.stream_ptr(self._dev_index)
-        a.flags = self.flags | (L.CH_ET_INPLACE if a.ET.ptr else 0)
+        # odd kinematic steps walk the grid bottom-up (TFB_CH_REVERSE, include/tfb.h): they start
+        # on the rows the previous step wrote last, which are still in L2
+        a.flags = (self.flags | (L.CH_ET_INPLACE if a.ET.ptr else 0)
+                   | (L.CH_REVERSE if (self.serpentine and
+                                       ((self.n_steps & 1) or not self.kinematic)) else 0))
         a.time_min = float(time_min)
         ptrs = self._ptr_cache.get((self.qcur, self.scur))
         if ptrs is None:
