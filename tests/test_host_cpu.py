@@ -245,3 +245,23 @@ def test_bench_reference_arm_contract():
     # a non-zero rank of a torchrun launch exits 0 without printing or working
     assert _run_bench(['--impl', 'reference', '--gpus', '2', '--steps', '1', '--warmup', '0'],
                       {'RANK': '1', 'LOCAL_RANK': '1', 'WORLD_SIZE': '2'}) == []
+
+
+def test_tile_walkers_on_the_host(tmp_path):
+    """The division-free tile walkers of the routing kernels (tfb_pk.cuh TileWalk, tile_of:
+    __host__ __device__) compiled as HOST code and checked against each other: every tile
+    exactly once for any grid shape / CTA count, forward, reversed (serpentine) and in the
+    boundary-first order of the peer-memory halo."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(nvcc):
+        pytest.skip('nvcc not available')
+    exe = str(tmp_path / 'tilewalk_test')
+    src = os.path.join(ROOT, 'tests', 'csrc', 'tilewalk_host_test.cu')
+    r = subprocess.run([nvcc, '-std=c++17', '-O1', '-gencode', 'arch=compute_100a,code=sm_100a',
+                        '-I', os.path.join(ROOT, 'include'), '-x', 'cu', src, '-o', exe],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.startswith('ok'), r.stdout[-500:]

@@ -131,7 +131,7 @@ __device__ __forceinline__ void add_if(double &v, unsigned m, unsigned bit, doub
 // rows and that feed the neighbours), then the rest.  The peer logic and this order cost
 // 2.4 % on one GPU (same-box A/B), hence a template parameter and not a run-time flag.
 template <bool PEER>
-__device__ __forceinline__ void tile_of(const PkConsts &k, int s, int &ty, int &tx) {
+__host__ __device__ __forceinline__ void tile_of(const PkConsts &k, int s, int &ty, int &tx) {
     if constexpr (!PEER) {
         if (k.reverse) s = k.n_tiles - 1 - s;
         ty = s / k.tiles_x; tx = s - ty * k.tiles_x;
@@ -151,7 +151,7 @@ template <bool PEER> struct TileWalk {
     int ty, tx;                  // current tile
     int s, ity, itx;
     bool in;
-    __device__ __forceinline__ void set(const PkConsts &k) {
+    __host__ __device__ __forceinline__ void set(const PkConsts &k) {
         if constexpr (!PEER) { ty = ity; tx = itx; return; }
         if (s < k.tiles_x) { ty = 0; tx = s; return; }
         if (s < k.n_boundary) { ty = k.tiles_y - 1; tx = s - k.tiles_x; return; }
@@ -163,14 +163,14 @@ template <bool PEER> struct TileWalk {
         }
         ty = ity; tx = itx;
     }
-    __device__ __forceinline__ void init(const PkConsts &k, int s0) {
+    __host__ __device__ __forceinline__ void init(const PkConsts &k, int s0) {
         s = s0; in = !PEER;
         const int i0 = (!PEER && k.reverse) ? (k.n_tiles - 1 - s0) : s0;    // may be < 0: no tile
         ity = PEER ? 0 : (i0 >= 0 ? i0 / k.tiles_x : 0);
         itx = PEER ? 0 : (i0 >= 0 ? i0 - ity * k.tiles_x : 0);
         set(k);
     }
-    __device__ __forceinline__ void advance(const PkConsts &k, int step) {
+    __host__ __device__ __forceinline__ void advance(const PkConsts &k, int step) {
         s += step;
         if (in) {
             if (!PEER && k.reverse) {
