@@ -32,7 +32,11 @@ Prints ONE JSON line (rank 0):
             hold them
 `--impl reference` times the UNMODIFIED reference (staged by `make -C oracle _ref`): its
 channels_component.update() fed by its Green-Ampt methods, numpy on one core, on a bounded
-sample of the same workload; the C restatement on all host threads is reported beside it.
+sample of the same workload; beside it `cpu_baseline.reference_all_cores` (one independent
+instance of the reference per host core, its best case) and `port_all_threads` (the C
+restatement of the path on all host threads).  The halo rows of both the kinematic step and
+the two diffusive passes travel by NVLink peer stores inside the kernels (`--halo nccl`
+selects grouped NCCL send/recv instead).
 """
 import argparse
 import json
