@@ -130,6 +130,44 @@ def gen_treynor(work):
     return emeli_out
 
 
+def gen_treynor_dw(work):
+    """The June-20-1967 storm on the reference's DIFFUSIVE-wave component (its Treynor data set
+    ships a kinematic CFG only: the same file under the diffusive name, with dt = 2 s -- at the
+    CFG's 6 s the explicit scheme of channels_diffusive_wave oscillates, outlet peaks of
+    1000 m^3/s; at 2 s the hydrograph is smooth, Q_peak 12.33 against 12.44 kinematic, and a
+    one-ulp perturbation of Manning's n stays at 1e-15 over the whole run).  3600 steps:
+    outlet series every step, all grids at three checkpoints."""
+    import re
+    cfg_dir, out_dir = rh.stage_treynor(os.path.join(work, 'dw'))
+    src = cfg_dir + 'June_20_67_channels_kinematic_wave.cfg'
+    dst = cfg_dir + 'June_20_67_channels_diffusive_wave.cfg'
+    txt = open(src).read()
+    txt2 = re.sub(r'^(dt\s*\|\s*)[0-9.]+', lambda m: m.group(1) + '2.0', txt, flags=re.M)
+    assert txt2 != txt
+    with open(dst, 'w') as fh:
+        fh.write(txt2)
+    rain = np.loadtxt(os.path.join(cfg_dir, 'June_20_67_rain_rates.txt'), dtype='float32')
+    ny, nx = 44, 29
+    c = standalone_channels(dst, False,
+                            dict(P_rain=z(0), MR=z(0), GW=z(0), SM=z(0), rho_H2O=z(1000.0),
+                                 ET=np.zeros((ny, nx)), IN=np.zeros((ny, nx))))
+    assert c.DIFFUSIVE_WAVE and float(c.dt) == 2.0
+    n_steps = 3600
+    series = np.zeros((n_steps, 4))
+    snaps = {}
+    for i in range(n_steps):
+        m = i // 30                                # the 1-minute rain value is held for 30 steps
+        P = np.float64(rain[m]) / (1000.0 * 3600.0) if m < rain.size else 0.0
+        c.set_value(LONG['P_rain'], z(P))
+        rh.quiet_call(c.update)
+        series[i] = (c.Q_outlet, c.u_outlet, c.d_outlet, c.f_outlet)
+        if (i + 1) in (600, 1300, 3600):
+            for k, v in snapshot(c).items():
+                snaps['s%d_%s' % (i + 1, k)] = v
+    np.savez_compressed(os.path.join(GOLD, 'treynor_dw_standalone.npz'),
+                        outlet_series=series, **snaps)
+
+
 def gen_synth_channels(work):
     """KW/DW x Manning/law-of-wall on a 61 x 83 synthetic case, 150 steps, rain
     for the first 100; ET and IN given as grids (exercises the ET masking)."""
@@ -648,6 +686,7 @@ def main():
     try:
         meta = {'numpy': np.__version__, 'reference': 'peckhams/topoflow36 @ /root/reference'}
         meta['treynor_emeli'] = gen_treynor(work)
+        gen_treynor_dw(work)
         gen_synth_channels(work)
         gen_sinu_d0(work)
         gen_flood(work)

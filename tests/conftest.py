@@ -30,6 +30,13 @@ def treynor_kw():
 
 
 @pytest.fixture(scope='session')
+def treynor_dw():
+    """The same storm on the reference's DIFFUSIVE-wave component, dt = 2 s, 3600 steps
+    (oracle/gen_golden.py gen_treynor_dw)."""
+    return load_golden('treynor_dw_standalone.npz')
+
+
+@pytest.fixture(scope='session')
 def synth_channels():
     return load_golden('synth_channels.npz')
 

@@ -72,6 +72,27 @@ def test_treynor_storm(treynor, treynor_kw):
         assert rel_err(getattr(ch, n), treynor_kw['s1200_' + n]) <= 1e-12, n
 
 
+def test_treynor_dw_storm(treynor, treynor_dw):
+    """Diffusive wave, dt = 2 s, 3600 steps of the same storm (rise + recession)."""
+    DEM = treynor['DEM']
+    dx, dy, dd = o.pixel_dims(DEM.shape[0], treynor['xres'], treynor['yres'])
+    ch = c_oracle.Channels(treynor['flow'], dx, dy, dd, treynor['slope'], treynor['width'],
+                           treynor['angle'], treynor['nval'], dt=2.0, kinematic=False, outlet=(34, 16))
+    ch.set_input('ET', np.zeros(DEM.shape))
+    ch.set_input('IN', np.zeros(DEM.shape))
+    rain = treynor['rain_mmph']
+    series = treynor_dw['outlet_series']
+    for i in range(3600):
+        m = i // 30
+        ch.set_input('P_rain', np.float64(rain[m]) / 3.6e6 if m < rain.size else 0.0)
+        ch.step()
+        got = np.array([ch.Q_outlet, ch.u_outlet, ch.d_outlet, ch.f_outlet])
+        assert rel_err(got, series[i]) <= 1e-12, i
+        if (i + 1) in (600, 1300, 3600):
+            for n in GRIDS:
+                assert rel_err(getattr(ch, n), treynor_dw['s%d_%s' % (i + 1, n)]) <= 1e-12, n
+
+
 def test_c_fill_pits_vs_reference_fixture_and_numpy_oracle():
     import os
     gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'prep.npz')

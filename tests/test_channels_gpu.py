@@ -122,6 +122,53 @@ def test_treynor_storm_on_the_packed_kernel(treynor, treynor_kw):
     assert s.n_neg_d == 0 and s.n_inf_d == 0 and s.n_neg_u == 0 and s.n_nan_u == 0
 
 
+@pytest.mark.parametrize('kernels', ['lean', 'ext'])
+def test_treynor_dw_storm_vs_reference_fixture(treynor, treynor_dw, kernels):
+    """The June-20-1967 storm on the DIFFUSIVE wave against the stand-alone run of the
+    reference's channels_diffusive_wave (dt = 2 s, 3600 steps: rise, peak 12.33 m^3/s, two hours
+    of recession; tests/golden/treynor_dw_standalone.npz): outlet values every 30 steps, all
+    grids at three checkpoints, also per cell.  'lean': scalar forcing -> pass A / pass B of the
+    production kernels on pitched rows (nx = 29); 'ext': grid ET / IN and all diagnostics
+    (incl. S_free) -> the extended kernels."""
+    DEM = treynor['DEM']
+    dx, dy, dd = o.pixel_dims(DEM.shape[0], treynor['xres'], treynor['yres'])
+    ext = (kernels == 'ext')
+    eng = _engine(treynor['flow'], dx, dy, dd, treynor['slope'], treynor['width'],
+                  treynor['angle'], treynor['nval'], dt=2.0, da=900.0, outlet=(34, 16),
+                  kinematic=False, diag=ext)
+    if ext:
+        eng.set_input('ET', np.zeros(DEM.shape))
+        eng.set_input('IN', np.zeros(DEM.shape))
+    rain = treynor['rain_mmph']
+    series = treynor_dw['outlet_series']
+    worst = worst_cell = 0.0
+    for i in range(3600):
+        m = i // 30
+        P = np.float64(rain[m]) / (1000.0 * 3600.0) if m < rain.size else 0.0
+        eng.set_input('P_rain', P)
+        eng.step(time_min=(i * 2.0) / 60.0)
+        if i % 30 == 29 or (i + 1) in (600, 1300, 3600):
+            s = eng.read_scalars()
+            got = np.array([s.Q_outlet, s.u_outlet, s.d_outlet, s.f_outlet])
+            worst = max(worst, rel_err(got, series[i]))
+        if (i + 1) in (600, 1300, 3600):
+            snap = {n: treynor_dw['s%d_%s' % (i + 1, n)] for n in GRIDS + SCALARS + ('S_free',)}
+            names = GRIDS if ext else ('vol', 'd', 'u', 'Q')
+            _cmp_grids(eng, snap, names)
+            if ext:
+                assert rel_err(eng.own(eng.S_free).cpu().numpy(), snap['S_free']) <= RTOL
+            _cmp_scalars(eng, snap)
+            for n in ('vol', 'd', 'u', 'Q'):
+                got = (eng.Q if n == 'Q' else eng.vol if n == 'vol' else eng.own(getattr(eng, n)))
+                worst_cell = max(worst_cell, cell_rel_err(got.cpu().numpy(), snap[n]))
+    assert worst <= RTOL, worst
+    assert worst_cell <= 1e-9, worst_cell
+    assert (eng.last_path, eng.last_kernel) == ('packed', 'ext' if ext else 'lean')
+    s = eng.read_scalars()
+    assert s.n_neg_d == 0 and s.n_inf_d == 0 and s.n_neg_u == 0 and s.n_nan_u == 0
+    assert 12.0 < s.Q_peak < 12.6
+
+
 @pytest.mark.parametrize('variant', ['kw_ga', 'dw_full'])
 def test_packed_storm_rise_and_recession(variant):
     """A whole storm on the benchmarked kernels at 512^2: 500 steps of 50 mm/h rain on

@@ -95,6 +95,35 @@ def test_treynor_kw_storm_bit_exact(treynor, treynor_kw):
                 assert float(getattr(ch, n)) == float(treynor_kw['s%d_%s' % (i + 1, n)]), n
 
 
+def test_treynor_dw_storm_bit_exact(treynor, treynor_dw):
+    """The June-20-1967 storm on the DIFFUSIVE wave (dt = 2 s, 3600 steps, rise and two hours
+    of recession): the numpy oracle against the stand-alone reference run, outlet values every
+    step and every grid (incl. S_free) at three checkpoints, bit for bit."""
+    DEM = treynor['DEM']
+    dx, dy, dd = o.pixel_dims(DEM.shape[0], treynor['xres'], treynor['yres'])
+    code = treynor['flow']
+    ds, dw = o.d8_ds_dw(code, dx, dy, dd)
+    ch = o.Channels(code, ds, dw, treynor['slope'], treynor['width'], treynor['angle'],
+                    nval=treynor['nval'], da=900.0, dt=2.0, kinematic=False, outlet=(34, 16))
+    ch.ET = np.zeros(code.shape)
+    ch.IN = np.zeros(code.shape)
+    rain = treynor['rain_mmph']
+    series = treynor_dw['outlet_series']
+    assert 12.0 < series[:, 0].max() < 12.6                  # a smooth hydrograph, not the dt = 6 s saw-tooth
+    for i in range(3600):
+        m = i // 30
+        P = np.float64(rain[m]) / (1000.0 * 3600.0) if m < rain.size else 0.0
+        ch.P_rain = np.array(P, dtype='float64')
+        ch.step()
+        assert (float(ch.Q_outlet), float(ch.u_outlet), float(ch.d_outlet),
+                float(ch.f_outlet)) == tuple(series[i]), i
+        if (i + 1) in (600, 1300, 3600):
+            for n in GRIDS + ('S_free',):
+                assert np.array_equal(getattr(ch, n), treynor_dw['s%d_%s' % (i + 1, n)]), n
+            for n in SCALARS:
+                assert float(getattr(ch, n)) == float(treynor_dw['s%d_%s' % (i + 1, n)]), n
+
+
 @pytest.mark.parametrize('tag', ['kw_man', 'kw_low', 'dw_man', 'dw_low'])
 def test_synth_channels_bit_exact(synth_channels, tag):
     g = synth_channels
@@ -314,7 +343,7 @@ def test_committed_fixtures_are_what_the_reference_produces(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     gold = os.path.join(root, 'tests', 'golden')
     names = sorted(f for f in os.listdir(gold) if f.endswith('.npz'))
-    assert len(names) == 13 and names == sorted(f for f in os.listdir(str(tmp_path)) if f.endswith('.npz'))
+    assert len(names) == 14 and names == sorted(f for f in os.listdir(str(tmp_path)) if f.endswith('.npz'))
     for f in names:
         a, b = np.load(os.path.join(gold, f)), np.load(os.path.join(str(tmp_path), f))
         assert sorted(a.files) == sorted(b.files), f
