@@ -1045,7 +1045,7 @@ int prepare(const tfb_channels_step_args *ap, tfb_channels_step_args &a,
 #endif
 #ifndef TFB_PK_NONE_ROWS
 #define TFB_PK_NONE_ROWS 24       // KW without sources: 2 cells per lane, 24-row tiles (25 warps, 72 registers,
-#endif                            // 4 ring slots).  Same-box A/B, round 2 (profiles/r02/ab_tiles*.log): 1 cell per
+#endif                            // 3 ring slots of 51 KB).  Same-box A/B, round 2 (profiles/r02/ab_tiles*.log): 1 cell per
                                   // lane x 2 rows per warp 0.2172 ms; 2 cells per lane: 15 rows 0.2094, 17 rows
                                   // 0.2066, 20 rows 0.1956, 22 rows 0.1915, 24 rows 0.1869, 26 rows (3 slots) 0.2126
 #ifndef TFB_PK_NONEA_ROWS
